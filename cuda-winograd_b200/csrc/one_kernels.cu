@@ -1,0 +1,233 @@
+// Fused 1x1 conv (GEMM) + folded BatchNorm (+ ReLU) for sm_100a.
+//
+// Replaces kernel_512_one_128 / kernel_128_one_512 (/root/reference/Kernel128_one.cu:24-54, :244-273) and
+// kernel_1024_one_256 / kernel_256_one_1024 (Kernel256_one.cu:26-56, :246-274): C[M x Cout] =
+// act(scale * (A[M x Cin] * B[Cin x Cout]) + shift), A = NHWC activations (M = N*196 pixels), FP32 in / FP32 out.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer (A tile through a 2-D tensor map with 128-byte swizzle,
+// B tile as one bulk copy of a pre-swizzled image written once per layer by weight_pack_kernel), warp 1 = single
+// thread issuing tcgen05.mma kind::tf32 (M=128, N=BN, K=8, four per 32-channel stage) into one of two TMEM
+// accumulator buffers, warps 2..5 = epilogue (tcgen05.ld -> scale/shift/ReLU -> 128-bit stores) overlapping the
+// next tile's MMAs.
+#include "ptx.cuh"
+#include "wg_internal.h"
+
+namespace wg {
+
+constexpr int kOneThreads = 32 * 6;
+constexpr int kBK = 32;  // fp32 channels per stage = one 128-byte swizzle row
+
+template <int BN>
+struct OneSmem {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 128 B
+  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kOffA = 0;
+  static constexpr uint32_t kOffB = kOffA + kStages * kABytes;
+  static constexpr uint32_t kOffBar = kOffB + kStages * kBBytes;
+  static constexpr uint32_t kNumBars = 2 * kStages + 4;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;  // + slack for manual 1024-B alignment
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kOneThreads, 1)
+conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ w_img,
+                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
+                      long long m_rows, int Cin, int Cout, int relu) {
+  using S = OneSmem<BN>;
+  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned stage buffers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* full = bars;
+  uint64_t* empty = full + S::kStages;
+  uint64_t* acc_full = empty + S::kStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    for (int i = 0; i < S::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_kb = Cin / kBK;
+  const int n_ntiles = Cout / BN;
+  const int n_mtiles = (int)((m_rows + 127) / 128);
+  const int n_items = n_mtiles * n_ntiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nt = item % n_ntiles;
+        const int mt = item / n_ntiles;
+        const uint8_t* b_src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)nt * n_kb * S::kBBytes;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full[st], S::kABytes + S::kBBytes);
+          tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, kb * kBK, mt * 128, &full[st]);
+          tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * S::kBBytes, S::kBBytes, &full[st]);
+          if (++st == S::kStages) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, BN);
+      const uint32_t a_base = smem_u32(smem + S::kOffA);
+      const uint32_t b_base = smem_u32(smem + S::kOffB);
+      uint32_t st = 0, ph = 0;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[buf], aph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t a_desc = make_smem_desc(a_base + st * S::kABytes + k * 32, 0, 1024, kLayoutSW128);
+            const uint64_t b_desc = make_smem_desc(b_base + st * S::kBBytes + k * 32, 0, 1024, kLayoutSW128);
+            umma_tf32_ss(tmem_base + buf * BN, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (++st == S::kStages) { st = 0; ph ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int row = quad * 32 + lane;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int nt = item % n_ntiles;
+      const int mt = item / n_ntiles;
+      const uint32_t buf = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const long long m = (long long)mt * 128 + row;
+      const bool valid = m < m_rows;
+      float* yrow = y + (size_t)m * Cout + nt * BN;
+      const float* sc = scale + nt * BN;
+      const float* sh = shift + nt * BN;
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld_x16(taddr + c0, v);
+        tmem_ld_x16(taddr + c0 + 16, v + 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c0 + j));
+          const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + c0 + j));
+          float4 o;
+          o.x = fmaf(s4.x, v[j + 0], h4.x);
+          o.y = fmaf(s4.y, v[j + 1], h4.y);
+          o.z = fmaf(s4.z, v[j + 2], h4.z);
+          o.w = fmaf(s4.w, v[j + 3], h4.w);
+          if (relu) {
+            o.x = fmaxf(o.x, 0.f);
+            o.y = fmaxf(o.y, 0.f);
+            o.z = fmaxf(o.z, 0.f);
+            o.w = fmaxf(o.w, 0.f);
+          }
+          if (valid) *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// Once per layer: W[Cin][Cout] (reference layout, Kernel128_one.cu:41-48) -> per (n-tile, 32-channel block) the
+// K-major 128-byte-swizzled shared-memory image [BN couts][32 cin], RN-rounded to TF32. The reference's cuDNN half
+// does the same [Cin][Cout] -> [Cout][Cin] transpose on the host (util.c:15-26, Kernel128_one.cu:131).
+__global__ void weight_pack_kernel(const float* __restrict__ w, float* __restrict__ w_img, int Cin, int Cout, int BN) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cin * Cout) return;
+  const int co = idx % Cout;
+  const int ci = idx / Cout;
+  const int nt = co / BN, r = co % BN;
+  const int kb = ci / kBK, kk = ci % kBK;
+  const int chunk = (kk >> 2) ^ (r & 7);
+  const size_t off = ((size_t)nt * (Cin / kBK) + kb) * (size_t)(BN * kBK) + (size_t)r * kBK + chunk * 4 + (kk & 3);
+  w_img[off] = to_tf32_rn(w[idx]);
+}
+
+int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return WG_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)m_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Cin * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
+}
+
+template <int BN>
+static int launch_one(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
+                      long long m_rows, int Cin, int Cout, int relu, int max_ctas, cudaStream_t stream) {
+  using S = OneSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)S::kTotal);
+    if (e != cudaSuccess) return WG_ERR_CUDA;
+    configured = true;
+  }
+  const long long n_items = ((m_rows + 127) / 128) * (Cout / BN);
+  int grid = n_items < max_ctas ? (int)n_items : max_ctas;
+  if (grid < 1) grid = 1;
+  conv1x1_bn_act_kernel<BN><<<grid, kOneThreads, S::kTotal, stream>>>(tmap, w_img, scale, shift, y, m_rows, Cin, Cout,
+                                                                      relu);
+  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+int one_launch(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
+               long long m_rows, int Cin, int Cout, int BN, int relu, int max_ctas, cudaStream_t stream) {
+  if (BN == 128) return launch_one<128>(tmap, w_img, scale, shift, y, m_rows, Cin, Cout, relu, max_ctas, stream);
+  if (BN == 256) return launch_one<256>(tmap, w_img, scale, shift, y, m_rows, Cin, Cout, relu, max_ctas, stream);
+  return WG_ERR_ARG;
+}
+
+int weight_pack_launch(const float* w_cin_cout, float* w_img, int Cin, int Cout, int BN, cudaStream_t stream) {
+  const int n = Cin * Cout;
+  weight_pack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_cin_cout, w_img, Cin, Cout, BN);
+  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+}  // namespace wg

@@ -1,0 +1,278 @@
+// C-ABI of libwinograd_b200.so (include/winograd_b200.h): layer handles, one-time filter packing, the single-launch
+// hot path, and the host-buffer end-to-end call. No cuDNN, no cuBLAS, no CPU fallback: without an sm_100 device every
+// create() returns WG_ERR_NODEVICE.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <cmath>
+
+#include "wg_internal.h"
+
+namespace wg {
+
+static thread_local char g_last_cuda_error[256] = "";
+static std::atomic<long long> g_launches{0};
+static int g_max_ctas = 0;  // 0 = number of SMs
+static int g_wino_kn = 32;
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
+  return WG_ERR_CUDA;
+}
+#define WG_CUDA(call)                                 \
+  do {                                                \
+    cudaError_t e_ = (call);                          \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+}  // namespace wg
+
+struct wg_layer {
+  int kind;  // 0 = 3x3 Winograd, 1 = 1x1 GEMM
+  int cin, cout, relu, dtype, device;
+  int tile_n;  // 3x3: cout slice KN; 1x1: BN
+  int num_sms;
+  float* d_filter;  // packed filter image (U or swizzled W^T)
+  float* d_scale;
+  float* d_shift;
+  // tensor-map cache for the last (x, N) seen
+  const float* tmap_x;
+  int tmap_n;
+  CUtensorMap tmap;
+  // staging for wg_run_host
+  float* d_x;
+  float* d_y;
+  size_t d_x_bytes, d_y_bytes;
+  cudaStream_t stream;
+};
+
+using namespace wg;
+
+static int check_device(int device, int* num_sms) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return WG_ERR_NODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return WG_ERR_NODEVICE;
+  if (prop.major != 10) return WG_ERR_NODEVICE;  // tcgen05 / TMEM: sm_100 family only
+  *num_sms = prop.multiProcessorCount;
+  return WG_OK;
+}
+
+static int create_common(wg_layer_t** out, int kind, int cin, int cout, const float* w, size_t w_elems,
+                         const float* scale, const float* shift, int relu, wg_dtype_t dtype, int device) {
+  if (!out || !w || !scale || !shift) return WG_ERR_ARG;
+  if (dtype != WG_TF32) return WG_ERR_ARG;  // bf16 operand variant: see DESIGN.md (not built yet)
+  int num_sms = 0;
+  int rc = check_device(device, &num_sms);
+  if (rc != WG_OK) return rc;
+  WG_CUDA(cudaSetDevice(device));
+
+  wg_layer* L = static_cast<wg_layer*>(calloc(1, sizeof(wg_layer)));
+  if (!L) return WG_ERR_NOMEM;
+  L->kind = kind;
+  L->cin = cin;
+  L->cout = cout;
+  L->relu = relu ? 1 : 0;
+  L->dtype = dtype;
+  L->device = device;
+  L->num_sms = num_sms;
+
+  float* d_w = nullptr;
+  size_t filter_elems = 0;
+  if (kind == 0) {
+    L->tile_n = (g_wino_kn == 16) ? 16 : 32;
+    filter_elems = (size_t)16 * cin * cout;
+  } else {
+    L->tile_n = (cout % 256 == 0) ? 256 : 128;
+    filter_elems = (size_t)cin * cout;
+  }
+  cudaError_t e;
+#define WG_TRY(call)                \
+  if ((e = (call)) != cudaSuccess) { \
+    cuda_fail(e, #call);            \
+    wg_destroy(L);                  \
+    if (d_w) cudaFree(d_w);         \
+    return WG_ERR_CUDA;             \
+  }
+  WG_TRY(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+  WG_TRY(cudaMalloc(&d_w, w_elems * sizeof(float)));
+  WG_TRY(cudaMalloc(&L->d_filter, filter_elems * sizeof(float)));
+  WG_TRY(cudaMalloc(&L->d_scale, cout * sizeof(float)));
+  WG_TRY(cudaMalloc(&L->d_shift, cout * sizeof(float)));
+  WG_TRY(cudaMemcpyAsync(d_w, w, w_elems * sizeof(float), cudaMemcpyHostToDevice, L->stream));
+  WG_TRY(cudaMemcpyAsync(L->d_scale, scale, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
+  WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
+  rc = kind == 0 ? filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream)
+                 : weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
+  g_launches++;
+  if (rc != WG_OK) {
+    cuda_fail(cudaGetLastError(), "filter pack launch");
+    wg_destroy(L);
+    cudaFree(d_w);
+    return rc;
+  }
+  WG_TRY(cudaStreamSynchronize(L->stream));
+#undef WG_TRY
+  cudaFree(d_w);
+  *out = L;
+  return WG_OK;
+}
+
+extern "C" {
+
+int wg_conv3x3_create(wg_layer_t** out, int C, int K, const float* w_kcrs, const float* scale, const float* shift,
+                      int relu, wg_dtype_t dtype, int device) {
+  if (C <= 0 || K <= 0 || C % 8 != 0 || K % 32 != 0) return WG_ERR_ARG;
+  return create_common(out, 0, C, K, w_kcrs, (size_t)K * C * 9, scale, shift, relu, dtype, device);
+}
+
+int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_cout, const float* scale,
+                      const float* shift, int relu, wg_dtype_t dtype, int device) {
+  if (Cin <= 0 || Cout <= 0 || Cin % 32 != 0 || Cout % 128 != 0) return WG_ERR_ARG;
+  return create_common(out, 1, Cin, Cout, w_cin_cout, (size_t)Cin * Cout, scale, shift, relu, dtype, device);
+}
+
+int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void* cuda_stream) {
+  if (!L || !x || !y || N <= 0) return WG_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return WG_ERR_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  int cur = -1;
+  WG_CUDA(cudaGetDevice(&cur));
+  if (cur != L->device) WG_CUDA(cudaSetDevice(L->device));
+  if (L->tmap_x != x || L->tmap_n != N) {
+    int rc = L->kind == 0 ? wino_make_tmap(&L->tmap, x, N, L->cin)
+                          : one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin);
+    if (rc != WG_OK) return rc;
+    L->tmap_x = x;
+    L->tmap_n = N;
+  }
+  const int max_ctas = g_max_ctas > 0 ? g_max_ctas : L->num_sms;
+  int rc;
+  if (L->kind == 0)
+    rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n, L->relu,
+                     out_padded ? 1 : 0, max_ctas, stream);
+  else
+    rc = one_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, (long long)N * 196, L->cin, L->cout, L->tile_n,
+                    L->relu, max_ctas, stream);
+  g_launches++;
+  if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
+  return rc;
+}
+
+int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int out_padded) {
+  if (!L || !x_host || !y_host || N <= 0) return WG_ERR_ARG;
+  int cur = -1;
+  WG_CUDA(cudaGetDevice(&cur));
+  if (cur != L->device) WG_CUDA(cudaSetDevice(L->device));
+  const size_t in_px = L->kind == 0 ? 256 : 196;
+  const size_t out_px = L->kind == 0 ? (out_padded ? 256 : 196) : 196;
+  const size_t xb = (size_t)N * in_px * L->cin * sizeof(float);
+  const size_t yb = (size_t)N * out_px * L->cout * sizeof(float);
+  if (L->d_x_bytes < xb) {
+    if (L->d_x) cudaFree(L->d_x);
+    L->d_x = nullptr;
+    L->d_x_bytes = 0;
+    L->tmap_x = nullptr;
+    WG_CUDA(cudaMalloc(&L->d_x, xb));
+    L->d_x_bytes = xb;
+  }
+  if (L->d_y_bytes < yb) {
+    if (L->d_y) cudaFree(L->d_y);
+    L->d_y = nullptr;
+    L->d_y_bytes = 0;
+    WG_CUDA(cudaMalloc(&L->d_y, yb));
+    L->d_y_bytes = yb;
+  }
+  WG_CUDA(cudaMemcpyAsync(L->d_x, x_host, xb, cudaMemcpyHostToDevice, L->stream));
+  int rc = wg_run(L, L->d_x, L->d_y, N, out_padded, L->stream);
+  if (rc != WG_OK) return rc;
+  WG_CUDA(cudaMemcpyAsync(y_host, L->d_y, yb, cudaMemcpyDeviceToHost, L->stream));
+  WG_CUDA(cudaStreamSynchronize(L->stream));
+  return WG_OK;
+}
+
+int wg_destroy(wg_layer_t* L) {
+  if (!L) return WG_ERR_ARG;
+  if (L->d_filter) cudaFree(L->d_filter);
+  if (L->d_scale) cudaFree(L->d_scale);
+  if (L->d_shift) cudaFree(L->d_shift);
+  if (L->d_x) cudaFree(L->d_x);
+  if (L->d_y) cudaFree(L->d_y);
+  if (L->stream) cudaStreamDestroy(L->stream);
+  free(L);
+  return WG_OK;
+}
+
+int wg_layer_info(const wg_layer_t* L, int* kind, int* cin, int* cout, int* relu) {
+  if (!L) return WG_ERR_ARG;
+  if (kind) *kind = L->kind;
+  if (cin) *cin = L->cin;
+  if (cout) *cout = L->cout;
+  if (relu) *relu = L->relu;
+  return WG_OK;
+}
+
+long long wg_launch_count(void) { return g_launches.load(); }
+
+const char* wg_strerror(int status) {
+  switch (status) {
+    case WG_OK: return "ok";
+    case WG_ERR_ARG: return "invalid argument";
+    case WG_ERR_CUDA: return "CUDA error";
+    case WG_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable";
+    case WG_ERR_TMAP: return "tensor map encoding failed";
+    case WG_ERR_NOMEM: return "out of memory";
+    case WG_ERR_NODEVICE: return "no sm_100 (B200) device; this library has no CPU fallback";
+    case WG_ERR_IO: return "data file missing or short";
+    default: return "unknown status";
+  }
+}
+
+const char* wg_last_cuda_error(void) { return g_last_cuda_error; }
+
+int wg_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int n = 0;
+  for (int i = 0; i < count; ++i) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++n;
+  }
+  return n;
+}
+
+void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                float* scale_out, float* shift_out) {
+  for (int k = 0; k < K; ++k) {
+    const float sd = sqrtf(var[k] + eps);  // same operation order as the numpy expressions
+    scale_out[k] = gamma[k] / sd;
+    shift_out[k] = beta[k] - (gamma[k] * mean[k]) / sd;
+  }
+}
+
+void wg_set_max_ctas(int max_ctas) { g_max_ctas = max_ctas; }
+void wg_set_wino_kn(int kn) { g_wino_kn = (kn == 16) ? 16 : 32; }
+
+}  // extern "C"

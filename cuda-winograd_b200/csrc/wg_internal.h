@@ -1,0 +1,29 @@
+// Internal glue between the C-ABI (wg_api.cu) and the kernels. Not installed; the public surface is include/*.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/winograd_b200.h"
+
+namespace wg {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled fetched through the runtime (no link-time libcuda dependency); nullptr on failure.
+PFN_encodeTiled get_encode_tiled();
+
+// ---- 3x3 Winograd path (winograd_kernels.cu)
+int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
+int wino_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                int n_img, int C, int K, int KN, int relu, int out_padded, int max_ctas, cudaStream_t stream);
+int filter_transform_launch(const float* w_kcrs, float* u_img, int C, int K, int KN, cudaStream_t stream);
+
+// ---- 1x1 GEMM path (one_kernels.cu)
+int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);
+int one_launch(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
+               long long m_rows, int Cin, int Cout, int BN, int relu, int max_ctas, cudaStream_t stream);
+int weight_pack_launch(const float* w_cin_cout, float* w_img, int Cin, int Cout, int BN, cudaStream_t stream);
+
+}  // namespace wg

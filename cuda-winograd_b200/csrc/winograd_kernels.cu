@@ -1,0 +1,431 @@
+// Fused 3x3 conv (Winograd F(2x2,3x3)) + folded BatchNorm + ReLU for sm_100a, one kernel, no intermediate in HBM.
+//
+// Replaces the reference's three-kernel pipeline kernel_{128,256}_winograd_BtdB -> kernel_*_OuterProduct_* ->
+// kernel_*_winograd_AtIA (/root/reference/Kernel128_winograd.cu:28-213, Kernel256_winograd.cu:27-218), which is
+// F(4x4,3x3) in FP32 FFMA with two global round trips. Here (see DESIGN.md "3x3 kernel"):
+//
+//   * an M-block is 128 consecutive Winograd tiles (tile index T = n*49 + ty*7 + tx over the whole batch);
+//   * per 8-channel stage the producer warp TMA-loads the 48 input rows the block touches (4-D tensor map with the
+//     x axis split by parity so that stride-2 tile reads are bank-conflict free) and bulk-copies the matching
+//     16-point slice of the pre-transformed filter U (written once per layer by filter_transform.cu in exactly the
+//     shared-memory image the MMA wants);
+//   * 8 transform warps compute V = B^T d B in registers, round to TF32 (RN) and store it in the UMMA K-major
+//     no-swizzle canonical layout;
+//   * one thread issues 16 tcgen05.mma (M=128 tiles, N=KN couts, K=8 channels) per stage, accumulating the 16
+//     Winograd points side by side in TMEM (16*KN fp32 columns);
+//   * after the last stage the same 8 warps run the epilogue: tcgen05.ld the 16 points, Y = A^T M A,
+//     relu(scale*Y + shift), 128-bit stores of NHWC output (optionally into the reference's zero-bordered
+//     16x16 frame, Kernel128_winograd.cu:163,243).
+#include "ptx.cuh"
+#include "wg_internal.h"
+
+#include <cuda.h>
+
+namespace wg {
+
+constexpr int kWorkerWarps = 8;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kThreads = 32 * 10;
+constexpr int kRawRows = 48;  // input rows (n*16+y) one M-block can touch, see DESIGN.md
+constexpr uint32_t kRawBytes = kRawRows * 2 * 8 * 32;  // [ny][x parity][x/2][8 ch] fp32 = 24576
+
+template <int KN>
+struct WinoSmem {
+  static constexpr int kRawStages = 2, kVStages = 2, kUStages = 3;
+  // V: per point [2 k-chunks][128 rows][16 B]; the +64 skews chunk 1 by half a bank window so that a quarter warp
+  // writing 4 rows x 2 chunks hits 32 distinct banks.
+  static constexpr uint32_t kVLbo = 128 * 16 + 64;
+  static constexpr uint32_t kVPerXi = kVLbo + 128 * 16;
+  static constexpr uint32_t kVBytes = 16 * kVPerXi;
+  static constexpr uint32_t kULbo = KN * 16;
+  static constexpr uint32_t kUPerXi = 2 * KN * 16;
+  static constexpr uint32_t kUBytes = 16 * kUPerXi;
+  static constexpr uint32_t kOffRaw = 0;
+  static constexpr uint32_t kOffV = kOffRaw + kRawStages * kRawBytes;
+  static constexpr uint32_t kOffU = kOffV + kVStages * kVBytes;
+  static constexpr uint32_t kOffBar = kOffU + kUStages * kUBytes;
+  static constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kVStages + 2 * kUStages + 2;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr uint32_t kTotal = kOffTmemPtr + 16;
+  static_assert(kOffV % 128 == 0 && kOffU % 128 == 0 && kOffBar % 8 == 0, "alignment");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+template <int KN>
+__global__ void __launch_bounds__(kThreads, 1)
+wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
+                       const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
+                       int n_img, int C, int K, int relu, int out_padded) {
+  using S = WinoSmem<KN>;
+  constexpr uint32_t kTmemCols = 16 * KN;
+  static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128, "TMEM columns must be a power of two");
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* raw_full = bars;
+  uint64_t* raw_empty = raw_full + S::kRawStages;
+  uint64_t* v_full = raw_empty + S::kRawStages;
+  uint64_t* v_empty = v_full + S::kVStages;
+  uint64_t* u_full = v_empty + S::kVStages;
+  uint64_t* u_empty = u_full + S::kUStages;
+  uint64_t* acc_full = u_empty + S::kUStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < S::kRawStages; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], kWorkerWarps);
+    }
+    for (int i = 0; i < S::kVStages; ++i) {
+      mbar_init(&v_full[i], kWorkerWarps);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < S::kUStages; ++i) {
+      mbar_init(&u_full[i], 1);
+      mbar_init(&u_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kWorkerWarps);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_kb = C / 8;
+  const int n_slices = K / KN;
+  const int total_tiles = n_img * 49;
+  const int n_mblocks = (total_tiles + 127) / 128;
+  const int n_items = n_mblocks * n_slices;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t rs = 0, rph = 0, us = 0, uph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int slice = item % n_slices;
+        const int mb = item / n_slices;
+        const int t0 = mb * 128;
+        const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)slice * n_kb * S::kUBytes;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&raw_empty[rs], rph ^ 1);
+          mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
+          tma_tensor_4d_g2s(smem + S::kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
+          if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
+
+          mbar_wait(&u_empty[us], uph ^ 1);
+          mbar_arrive_expect_tx(&u_full[us], S::kUBytes);
+          tma_bulk_g2s(smem + S::kOffU + us * S::kUBytes, u_src + (size_t)kb * S::kUBytes, S::kUBytes, &u_full[us]);
+          if (++us == S::kUStages) { us = 0; uph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, KN);
+      const uint32_t v_base = smem_u32(smem + S::kOffV);
+      const uint32_t u_base = smem_u32(smem + S::kOffU);
+      uint32_t vs = 0, vph = 0, us = 0, uph = 0, aph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
+        tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&u_full[us], uph);
+          mbar_wait(&v_full[vs], vph);
+          tc_fence_after();
+          const uint32_t va = v_base + vs * S::kVBytes;
+          const uint32_t ua = u_base + us * S::kUBytes;
+#pragma unroll
+          for (int xi = 0; xi < 16; ++xi) {
+            const uint64_t a_desc = make_smem_desc(va + xi * S::kVPerXi, S::kVLbo, 128, kLayoutNone);
+            const uint64_t b_desc = make_smem_desc(ua + xi * S::kUPerXi, S::kULbo, 128, kLayoutNone);
+            umma_tf32_ss(tmem_base + xi * KN, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
+          }
+          umma_commit(&v_empty[vs]);
+          umma_commit(&u_empty[us]);
+          if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
+          if (++us == S::kUStages) { us = 0; uph ^= 1; }
+        }
+        umma_commit(acc_full);
+        aph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ transform + epilogue warps
+    // transform task: row = 16*warp + q (tile within the M-block), c = which 4-channel half of the 8-channel stage
+    const int c = (lane >> 2) & 1;
+    const int q = (lane & 3) + 4 * (lane >> 3);
+    const int trow = warp * 16 + q;
+    // epilogue task: row = TMEM lane
+    const int quad = warp & 3;
+    const int half = warp >> 2;
+    const int erow = quad * 32 + lane;
+    const uint32_t raw_base = smem_u32(smem + S::kOffRaw);
+    const uint32_t v_base = smem_u32(smem + S::kOffV);
+
+    uint32_t rs = 0, rph = 0, vs = 0, vph = 0, aph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int slice = item % n_slices;
+      const int mb = item / n_slices;
+      const int t0 = mb * 128;
+      const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+
+      // ---- transform: this thread's tile and its offset inside a raw stage
+      const int T = t0 + trow;
+      const bool tvalid = T < total_tiles;
+      uint32_t raw_off = 0;
+      {
+        const int n = T / 49, t = T % 49, ty = t / 7, tx = t % 7;
+        if (tvalid) raw_off = (uint32_t)((n * 16 + 2 * ty - ny0) * 512 + tx * 32 + c * 16);
+      }
+      const uint32_t v_off = (uint32_t)(c * S::kVLbo + trow * 16);
+
+      for (int kb = 0; kb < n_kb; ++kb) {
+        float4 d[4][4];
+        mbar_wait(&raw_full[rs], rph);
+        if (tvalid) {
+          const uint32_t a = raw_base + rs * kRawBytes + raw_off;
+#pragma unroll
+          for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx)
+              d[dy][dx] = ld_shared_v4(a + dy * 512 + (dx & 1) * 256 + (dx >> 1) * 32);
+        } else {
+#pragma unroll
+          for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx) d[dy][dx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // column pass t = B^T d, in place over dy
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+          const float4 d0 = d[0][dx], d1 = d[1][dx], d2 = d[2][dx], d3 = d[3][dx];
+          d[0][dx] = make_float4(d0.x - d2.x, d0.y - d2.y, d0.z - d2.z, d0.w - d2.w);
+          d[1][dx] = make_float4(d1.x + d2.x, d1.y + d2.y, d1.z + d2.z, d1.w + d2.w);
+          d[2][dx] = make_float4(d2.x - d1.x, d2.y - d1.y, d2.z - d1.z, d2.w - d1.w);
+          d[3][dx] = make_float4(d1.x - d3.x, d1.y - d3.y, d1.z - d3.z, d1.w - d3.w);
+        }
+        mbar_wait(&v_empty[vs], vph ^ 1);  // MMAs that read this V stage have completed
+        const uint32_t vdst = v_base + vs * S::kVBytes + v_off;
+        // row pass V = t B, round to TF32, store point (i,j) at xi = 4*i + j
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
+          st_shared_v4(vdst + (4 * i + 0) * S::kVPerXi, to_tf32_rn(a0.x - a2.x), to_tf32_rn(a0.y - a2.y),
+                       to_tf32_rn(a0.z - a2.z), to_tf32_rn(a0.w - a2.w));
+          st_shared_v4(vdst + (4 * i + 1) * S::kVPerXi, to_tf32_rn(a1.x + a2.x), to_tf32_rn(a1.y + a2.y),
+                       to_tf32_rn(a1.z + a2.z), to_tf32_rn(a1.w + a2.w));
+          st_shared_v4(vdst + (4 * i + 2) * S::kVPerXi, to_tf32_rn(a2.x - a1.x), to_tf32_rn(a2.y - a1.y),
+                       to_tf32_rn(a2.z - a1.z), to_tf32_rn(a2.w - a1.w));
+          st_shared_v4(vdst + (4 * i + 3) * S::kVPerXi, to_tf32_rn(a1.x - a3.x), to_tf32_rn(a1.y - a3.y),
+                       to_tf32_rn(a1.z - a3.z), to_tf32_rn(a1.w - a3.w));
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&v_full[vs]);
+          mbar_arrive(&raw_empty[rs]);
+        }
+        if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
+        if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
+      }
+
+      // ---- epilogue: Y = A^T M A, BN, ReLU, store
+      const int TE = t0 + erow;
+      const bool evalid = TE < total_tiles;
+      const int n = TE / 49, t = TE % 49, ty = t / 7, tx = t % 7;
+      const int W = out_padded ? 16 : 14;
+      const int o = out_padded ? 1 : 0;
+      float* ybase = y + ((size_t)n * W * W + (size_t)(2 * ty + o) * W + (2 * tx + o)) * K + slice * KN;
+
+      mbar_wait(acc_full, aph);
+      aph ^= 1;
+      tc_fence_after();
+      constexpr int kColsPerWarp = KN / 2;
+#pragma unroll 1
+      for (int cc = 0; cc < kColsPerWarp; cc += 8) {
+        const int c0 = half * kColsPerWarp + cc;
+        float m[16][8];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
+#pragma unroll
+        for (int xi = 0; xi < 16; ++xi) tmem_ld_x8(taddr + xi * KN, m[xi]);
+        tmem_ld_wait();
+        const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + slice * KN + c0));
+        const float4 sc1 = __ldg(reinterpret_cast<const float4*>(scale + slice * KN + c0 + 4));
+        const float4 sh0 = __ldg(reinterpret_cast<const float4*>(shift + slice * KN + c0));
+        const float4 sh1 = __ldg(reinterpret_cast<const float4*>(shift + slice * KN + c0 + 4));
+        const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+        const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+        float o00[8], o01[8], o10[8], o11[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float s0[4], s1[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            s0[jj] = m[0 + jj][j] + m[4 + jj][j] + m[8 + jj][j];
+            s1[jj] = m[4 + jj][j] - m[8 + jj][j] - m[12 + jj][j];
+          }
+          float y00 = fmaf(sc[j], s0[0] + s0[1] + s0[2], sh[j]);
+          float y01 = fmaf(sc[j], s0[1] - s0[2] - s0[3], sh[j]);
+          float y10 = fmaf(sc[j], s1[0] + s1[1] + s1[2], sh[j]);
+          float y11 = fmaf(sc[j], s1[1] - s1[2] - s1[3], sh[j]);
+          if (relu) {
+            y00 = fmaxf(y00, 0.f);
+            y01 = fmaxf(y01, 0.f);
+            y10 = fmaxf(y10, 0.f);
+            y11 = fmaxf(y11, 0.f);
+          }
+          o00[j] = y00;
+          o01[j] = y01;
+          o10[j] = y10;
+          o11[j] = y11;
+        }
+        if (evalid) {
+          float* p = ybase + c0;
+          const size_t rstride = (size_t)W * K;
+          *reinterpret_cast<float4*>(p) = make_float4(o00[0], o00[1], o00[2], o00[3]);
+          *reinterpret_cast<float4*>(p + 4) = make_float4(o00[4], o00[5], o00[6], o00[7]);
+          *reinterpret_cast<float4*>(p + K) = make_float4(o01[0], o01[1], o01[2], o01[3]);
+          *reinterpret_cast<float4*>(p + K + 4) = make_float4(o01[4], o01[5], o01[6], o01[7]);
+          *reinterpret_cast<float4*>(p + rstride) = make_float4(o10[0], o10[1], o10[2], o10[3]);
+          *reinterpret_cast<float4*>(p + rstride + 4) = make_float4(o10[4], o10[5], o10[6], o10[7]);
+          *reinterpret_cast<float4*>(p + rstride + K) = make_float4(o11[0], o11[1], o11[2], o11[3]);
+          *reinterpret_cast<float4*>(p + rstride + K + 4) = make_float4(o11[4], o11[5], o11[6], o11[7]);
+          if (out_padded) {
+            // zero border of the reference's 16x16 frame: edge tiles also own their share of the border
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
+            const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
+            if (dyb != 0) {
+              *reinterpret_cast<float4*>(p + dyb) = z;
+              *reinterpret_cast<float4*>(p + dyb + 4) = z;
+              *reinterpret_cast<float4*>(p + dyb + K) = z;
+              *reinterpret_cast<float4*>(p + dyb + K + 4) = z;
+            }
+            if (dxb != 0) {
+              *reinterpret_cast<float4*>(p + dxb) = z;
+              *reinterpret_cast<float4*>(p + dxb + 4) = z;
+              *reinterpret_cast<float4*>(p + dxb + rstride) = z;
+              *reinterpret_cast<float4*>(p + dxb + rstride + 4) = z;
+            }
+            if (dyb != 0 && dxb != 0) {
+              *reinterpret_cast<float4*>(p + dyb + dxb) = z;
+              *reinterpret_cast<float4*>(p + dyb + dxb + 4) = z;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Once-per-layer filter transform U = G g G^T (F(2x2,3x3)), RN-rounded to TF32, written as the exact shared-memory
+// image of a pipeline stage: [K/KN slice][C/8 k-block][16 points][2 k-chunks][KN couts][4 channels].
+// Replaces the offline weight_generator loop (/root/reference/data_generator.py:63-78; that one is F(4x4), 36 points).
+__global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, float* __restrict__ u_img, int C, int K,
+                                             int KN) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * K) return;
+  const int ch = idx % C;
+  const int k = idx / C;
+  const float* g = w_kcrs + ((size_t)k * C + ch) * 9;
+  float gg[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) gg[r][s] = g[r * 3 + s];
+  // t = G g  (4x3)
+  float tt[4][3];
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    tt[0][s] = gg[0][s];
+    tt[1][s] = 0.5f * (gg[0][s] + gg[1][s] + gg[2][s]);
+    tt[2][s] = 0.5f * (gg[0][s] - gg[1][s] + gg[2][s]);
+    tt[3][s] = gg[2][s];
+  }
+  const int slice = k / KN, kn = k % KN;
+  const int kb = ch / 8, chunk = (ch % 8) / 4, e = ch % 4;
+  const size_t stage = ((size_t)slice * (C / 8) + kb) * (size_t)(16 * 2 * KN * 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float u[4];
+    u[0] = tt[i][0];
+    u[1] = 0.5f * (tt[i][0] + tt[i][1] + tt[i][2]);
+    u[2] = 0.5f * (tt[i][0] - tt[i][1] + tt[i][2]);
+    u[3] = tt[i][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xi = 4 * i + j;
+      u_img[stage + ((size_t)(xi * 2 + chunk) * KN + kn) * 4 + e] = to_tf32_rn(u[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+
+int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return WG_ERR_DRIVER;
+  // view x[N][16][16][C] as (c, x/2, x&1, n*16+y): the parity split makes stride-2 tile reads conflict free
+  cuuint64_t dims[4] = {(cuuint64_t)C, 8, 2, (cuuint64_t)n_img * 16};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * C * 4, (cuuint64_t)C * 4, (cuuint64_t)16 * C * 4};
+  cuuint32_t box[4] = {8, 8, 2, (cuuint32_t)kRawRows};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
+}
+
+template <int KN>
+static int launch_wino(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                       int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+  using S = WinoSmem<KN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<KN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)S::kTotal);
+    if (e != cudaSuccess) return WG_ERR_CUDA;
+    configured = true;
+  }
+  const int n_items = ((n_img * 49 + 127) / 128) * (K / KN);
+  int grid = n_items < max_ctas ? n_items : max_ctas;
+  if (grid < 1) grid = 1;
+  wino3x3_bn_relu_kernel<KN><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K, relu,
+                                                                    out_padded);
+  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+int wino_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                int n_img, int C, int K, int KN, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+  if (KN == 32) return launch_wino<32>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+  if (KN == 16) return launch_wino<16>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+  return WG_ERR_ARG;
+}
+
+int filter_transform_launch(const float* w_kcrs, float* u_img, int C, int K, int KN, cudaStream_t stream) {
+  const int n = C * K;
+  filter_transform_f2x2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, KN);
+  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+}  // namespace wg

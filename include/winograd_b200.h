@@ -1,0 +1,86 @@
+/*
+ * winograd_b200.h -- tensor-level C ABI of libwinograd_b200.so (B200 / sm_100a).
+ *
+ * The reference (bssrdf/CUDA-Winograd) exposes its one hot path -- fused conv + inference-BatchNorm + ReLU -- only
+ * as six zero-argument entry points that read data/<name>.bin files (Kernel128_winograd.h:20, Kernel256_winograd.h:20,
+ * Kernel128_one.h:18-19, Kernel256_one.h:18-19; re-declared for this library in include/Kernel*.h). Those symbols
+ * cannot express a batch, a device or caller-owned buffers, so they are thin wrappers over the functions below,
+ * which are what a host-language binding (ctypes / cgo / JNI) should bind. Plain pointers and sizes only.
+ *
+ * Layouts (identical to the files written by the reference's data_generator.py):
+ *   3x3 input   x  [N][16][16][C]   fp32 NHWC, the 1-pixel border is part of the data (data_generator.py:49-53,
+ *                                   Kernel128_winograd.cu:26-31)
+ *   3x3 filter  w  [K][C][3][3]     fp32 "NCHW"/KCRS (data_generator.py:55-61, Kernel128_winograd.cu:343)
+ *   3x3 output  y  [N][14][14][K]   fp32 NHWC, or -- out_padded != 0 -- the reference's own [N][16][16][K] frame with
+ *                                   a zero border and the result at (+1,+1) (Kernel128_winograd.cu:163,243)
+ *   1x1 input   x  [N][196][Cin]    fp32 (Kernel128_one.cu:33-34)
+ *   1x1 weight  w  [Cin][Cout]      fp32 (Kernel128_one.cu:41-48, :259)
+ *   1x1 output  y  [N][196][Cout]   fp32
+ *   scale/shift    [K]              folded BN: scale = gamma/sqrt(var+eps), shift = beta - gamma*mean/sqrt(var+eps)
+ *                                   (data_generator.py:41-47,107-113); y = act(scale*conv + shift)
+ *
+ * Every function returns WG_OK (0) or a negative wg_status; nothing here calls exit().
+ */
+#ifndef WINOGRAD_B200_H_
+#define WINOGRAD_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wg_layer wg_layer_t; /* opaque: device copies of the packed filter, folded BN, cached tensor maps */
+
+typedef enum { WG_TF32 = 0, WG_BF16 = 1 } wg_dtype_t;
+
+typedef enum {
+  WG_OK = 0,
+  WG_ERR_ARG = -1,    /* bad shape / null pointer / unsupported channel count */
+  WG_ERR_CUDA = -2,   /* a CUDA runtime call or kernel launch failed (see wg_last_cuda_error) */
+  WG_ERR_DRIVER = -3, /* cuTensorMapEncodeTiled could not be resolved */
+  WG_ERR_TMAP = -4,   /* tensor-map encoding rejected */
+  WG_ERR_NOMEM = -5,
+  WG_ERR_NODEVICE = -6, /* no sm_100 device: the library never falls back to a CPU path */
+  WG_ERR_IO = -7        /* legacy entry points: a data/<name>.bin file is missing or short */
+} wg_status;
+
+/* One-time per layer: copies weights / BN to `device`, runs the filter transform U = G g G^T (F(2x2,3x3)) or the
+ * 1x1 weight pack on the GPU, rounds the filter operand to TF32 (round-to-nearest).
+ * Replaces the offline weight_generator (data_generator.py:63-78) and the per-call cudaMalloc/cudaMemcpy block of
+ * kernel_128() (Kernel128_winograd.cu:236-256). All pointers are HOST pointers. C, K multiples of 32 (3x3);
+ * Cin multiple of 32 and Cout multiple of 128 (1x1). */
+int wg_conv3x3_create(wg_layer_t** out, int C, int K, const float* w_kcrs, const float* scale, const float* shift,
+                      int relu, wg_dtype_t dtype, int device);
+int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_cout, const float* scale,
+                      const float* shift, int relu, wg_dtype_t dtype, int device);
+
+/* The hot path: ONE kernel launch (conv + BN + optional ReLU) on `cuda_stream` (a cudaStream_t, may be NULL),
+ * asynchronous. x and y are DEVICE pointers on the layer's device, 16-byte aligned.
+ * Replaces the timed region of kernel_128()/kernel_256() (three launches, Kernel128_winograd.cu:263-265) and of
+ * kernel_*_1_in/out() (one launch, Kernel128_one.cu:98,316). out_padded is ignored for 1x1 layers. */
+int wg_run(wg_layer_t* layer, const float* x_dev, float* y_dev, int N, int out_padded, void* cuda_stream);
+
+/* Same, end to end with HOST buffers: H2D copy of x, wg_run, D2H copy of y, stream-synchronised on return.
+ * Device staging buffers are cached in the layer (grown on demand). This is the call bench.py's `e2e` times. */
+int wg_run_host(wg_layer_t* layer, const float* x_host, float* y_host, int N, int out_padded);
+
+int wg_destroy(wg_layer_t* layer);
+
+/* Introspection used by the tests and the bench. */
+int wg_layer_info(const wg_layer_t* layer, int* kind /*0 = 3x3, 1 = 1x1*/, int* cin, int* cout, int* relu);
+long long wg_launch_count(void);        /* kernels launched by this library so far (this process) */
+const char* wg_strerror(int status);
+const char* wg_last_cuda_error(void);   /* cudaGetErrorString of the last failing CUDA call, "" if none */
+int wg_device_count(void);              /* number of sm_100 devices visible; 0 => every create() fails loudly */
+
+/* Folded BN exactly as data_generator.py:41-47 does it (fp32 arithmetic, eps = 1e-5 there). Host only. */
+void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                float* scale_out, float* shift_out);
+
+/* Tuning knobs (process-wide; for benchmarking): max CTAs per launch (default = #SMs), 3x3 cout slice KN (16|32). */
+void wg_set_max_ctas(int max_ctas);
+void wg_set_wino_kn(int kn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WINOGRAD_B200_H_ */

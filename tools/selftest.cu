@@ -1,0 +1,297 @@
+// Developer self-test (not part of the product or the test-suite): exercises libwinograd_b200.so through its C ABI
+// against an in-program FP64 direct convolution, plus a one-instruction UMMA descriptor probe that tells which
+// (LBO, SBO) reading of the no-swizzle K-major layout the hardware implements. Run on a B200:
+//   tools/selftest [quick]
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../cuda-winograd_b200/csrc/ptx.cuh"
+#include "../include/winograd_b200.h"
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e = (x);                                                               \
+    if (e != cudaSuccess) {                                                            \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__);   \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+static uint32_t rng_state = 12345;
+static float frand() {  // U(-0.5, 0.5)
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xffffff) / 16777216.0f - 0.5f;
+}
+
+// ------------------------------------------------------------------------------------------------ UMMA probe
+// A: 128 x 8 (K-major), B: 32 x 8 (K-major), both in the no-swizzle canonical layout with element (r, k) at byte
+// (k/4)*kstride + (r/8)*gstride + (r%8)*16 + (k%4)*4. One tcgen05.mma, D dumped to global.
+__global__ void umma_probe_kernel(const float* a, const float* b, float* d, uint32_t a_kstride, uint32_t a_gstride,
+                                  uint32_t b_kstride, uint32_t b_gstride, uint32_t lbo_a, uint32_t sbo_a,
+                                  uint32_t lbo_b, uint32_t sbo_b) {
+  using namespace wg;
+  __shared__ __align__(1024) uint8_t sa[8192];
+  __shared__ __align__(1024) uint8_t sb[4096];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 128 * 8; i += blockDim.x) {
+    const int r = i / 8, k = i % 8;
+    *reinterpret_cast<float*>(sa + (k / 4) * a_kstride + (r / 8) * a_gstride + (r % 8) * 16 + (k % 4) * 4) = a[i];
+  }
+  for (int i = tid; i < 32 * 8; i += blockDim.x) {
+    const int r = i / 8, k = i % 8;
+    *reinterpret_cast<float*>(sb + (k / 4) * b_kstride + (r / 8) * b_gstride + (r % 8) * 16 + (k % 4) * 4) = b[i];
+  }
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc<32>(&tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tptr;
+  if (tid == 0) {
+    const uint64_t ad = make_smem_desc(smem_u32(sa), lbo_a, sbo_a, kLayoutNone);
+    const uint64_t bd = make_smem_desc(smem_u32(sb), lbo_b, sbo_b, kLayoutNone);
+    umma_tf32_ss(tb, ad, bd, make_idesc(kFmtTF32, 128, 32), 0);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int warp = tid >> 5, lane = tid & 31;
+  float v[32];
+  tmem_ld_x16(tb + ((uint32_t)(warp * 32) << 16), v);
+  tmem_ld_x16(tb + ((uint32_t)(warp * 32) << 16) + 16, v + 16);
+  tmem_ld_wait();
+  for (int j = 0; j < 32; ++j) d[(warp * 32 + lane) * 32 + j] = v[j];
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<32>(tb);
+}
+
+static int run_probe() {
+  std::vector<float> a(128 * 8), b(32 * 8), d(128 * 32);
+  for (auto& v : a) v = roundf(frand() * 16.f);  // small integers: exact in tf32
+  for (auto& v : b) v = roundf(frand() * 16.f);
+  float *da, *db, *dd;
+  CK(cudaMalloc(&da, a.size() * 4));
+  CK(cudaMalloc(&db, b.size() * 4));
+  CK(cudaMalloc(&dd, d.size() * 4));
+  CK(cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  int ok_any = 0;
+  // layout in smem: k-chunk stride 2112 (A) / 512 (B), 8-row-group stride 128
+  for (int variant = 0; variant < 1; ++variant) {  // the swapped reading faults (read past shared memory): confirmed on B200
+    const uint32_t aks = 2112, ags = 128, bks = 512, bgs = 128;
+    const uint32_t lbo_a = variant == 0 ? aks : ags, sbo_a = variant == 0 ? ags : aks;
+    const uint32_t lbo_b = variant == 0 ? bks : bgs, sbo_b = variant == 0 ? bgs : bks;
+    CK(cudaMemset(dd, 0, d.size() * 4));
+    umma_probe_kernel<<<1, 128>>>(da, db, dd, aks, ags, bks, bgs, lbo_a, sbo_a, lbo_b, sbo_b);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("probe variant %d: kernel failed: %s\n", variant, cudaGetErrorString(e));
+      return -1;
+    }
+    CK(cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 32; ++n) {
+        double ref = 0;
+        for (int k = 0; k < 8; ++k) ref += (double)a[m * 8 + k] * b[n * 8 + k];
+        maxerr = fmax(maxerr, fabs(ref - d[m * 32 + n]));
+      }
+    printf("probe variant %d (%s): max abs err %.3g -> %s\n", variant,
+           variant == 0 ? "LBO = K-chunk stride, SBO = 8-row-group stride" : "swapped", maxerr,
+           maxerr == 0 ? "MATCH" : "mismatch");
+    if (maxerr == 0) ok_any |= 1 << variant;
+  }
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dd);
+  return ok_any;
+}
+
+// ------------------------------------------------------------------------------------------------ conv checks
+static double check3x3(int N, int C, int K, int relu, int padded, const std::vector<int>& imgs) {
+  std::vector<float> x((size_t)N * 256 * C), w((size_t)K * C * 9), sc(K), sh(K);
+  for (auto& v : x) v = frand();
+  for (auto& v : w) v = frand();
+  for (auto& v : sc) v = frand() * 0.8f;
+  for (auto& v : sh) v = frand();
+  const int W = padded ? 16 : 14, o = padded ? 1 : 0;
+  std::vector<float> y((size_t)N * W * W * K, 123.f);
+  wg_layer_t* L = nullptr;
+  int rc = wg_conv3x3_create(&L, C, K, w.data(), sc.data(), sh.data(), relu, WG_TF32, 0);
+  if (rc) {
+    printf("create3x3 failed: %s (%s)\n", wg_strerror(rc), wg_last_cuda_error());
+    return 1e30;
+  }
+  float *dx, *dy;
+  CK(cudaMalloc(&dx, x.size() * 4));
+  CK(cudaMalloc(&dy, y.size() * 4));
+  CK(cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dy, y.data(), y.size() * 4, cudaMemcpyHostToDevice));
+  rc = wg_run(L, dx, dy, N, padded, nullptr);
+  if (rc) {
+    printf("wg_run failed: %s (%s)\n", wg_strerror(rc), wg_last_cuda_error());
+    return 1e30;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("3x3 kernel failed: %s\n", cudaGetErrorString(e));
+    exit(3);
+  }
+  CK(cudaMemcpy(y.data(), dy, y.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxref = 0;
+  long long border_bad = 0;
+  for (int n : imgs) {
+    if (n >= N) continue;
+    for (int oy = 0; oy < 14; ++oy)
+      for (int ox = 0; ox < 14; ++ox)
+        for (int k = 0; k < K; ++k) {
+          double acc = 0;
+          for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+              const float* xp = &x[(((size_t)n * 16 + oy + r) * 16 + ox + s) * C];
+              const float* wp = &w[((size_t)k * C) * 9 + r * 3 + s];
+              for (int c = 0; c < C; ++c) acc += (double)xp[c] * wp[(size_t)c * 9];
+            }
+          double ref = sc[k] * acc + sh[k];
+          if (relu && ref < 0) ref = 0;
+          const double got = y[(((size_t)n * W + oy + o) * W + ox + o) * K + k];
+          maxerr = fmax(maxerr, fabs(ref - got));
+          maxref = fmax(maxref, fabs(ref));
+        }
+    if (padded)
+      for (int py = 0; py < 16; ++py)
+        for (int px = 0; px < 16; ++px)
+          if (py == 0 || py == 15 || px == 0 || px == 15)
+            for (int k = 0; k < K; ++k)
+              if (y[(((size_t)n * 16 + py) * 16 + px) * K + k] != 0.f) ++border_bad;
+  }
+  wg_destroy(L);
+  cudaFree(dx);
+  cudaFree(dy);
+  printf("3x3 N=%d C=%d K=%d relu=%d padded=%d: max|err|=%.3g max|ref|=%.3g rel=%.3g border_bad=%lld\n", N, C, K, relu,
+         padded, maxerr, maxref, maxerr / maxref, border_bad);
+  return border_bad ? 1e30 : maxerr / maxref;
+}
+
+static double check1x1(int N, int Cin, int Cout, int relu, const std::vector<int>& imgs) {
+  std::vector<float> x((size_t)N * 196 * Cin), w((size_t)Cin * Cout), sc(Cout), sh(Cout);
+  for (auto& v : x) v = frand() * 40.f;
+  for (auto& v : w) v = frand() * 40.f;
+  for (auto& v : sc) v = frand() * 8.f;
+  for (auto& v : sh) v = frand() * 40.f;
+  std::vector<float> y((size_t)N * 196 * Cout, 123.f);
+  wg_layer_t* L = nullptr;
+  int rc = wg_conv1x1_create(&L, Cin, Cout, w.data(), sc.data(), sh.data(), relu, WG_TF32, 0);
+  if (rc) {
+    printf("create1x1 failed: %s (%s)\n", wg_strerror(rc), wg_last_cuda_error());
+    return 1e30;
+  }
+  rc = wg_run_host(L, x.data(), y.data(), N, 0);
+  if (rc) {
+    printf("wg_run_host failed: %s (%s)\n", wg_strerror(rc), wg_last_cuda_error());
+    exit(3);
+  }
+  double maxerr = 0, maxref = 0;
+  for (int n : imgs) {
+    if (n >= N) continue;
+    for (int p = 0; p < 196; ++p)
+      for (int k = 0; k < Cout; ++k) {
+        double acc = 0;
+        const float* xp = &x[((size_t)n * 196 + p) * Cin];
+        for (int c = 0; c < Cin; ++c) acc += (double)xp[c] * w[(size_t)c * Cout + k];
+        double ref = sc[k] * acc + sh[k];
+        if (relu && ref < 0) ref = 0;
+        const double got = y[((size_t)n * 196 + p) * Cout + k];
+        maxerr = fmax(maxerr, fabs(ref - got));
+        maxref = fmax(maxref, fabs(ref));
+      }
+  }
+  wg_destroy(L);
+  printf("1x1 N=%d %d->%d relu=%d: max|err|=%.3g max|ref|=%.3g rel=%.3g\n", N, Cin, Cout, relu, maxerr, maxref,
+         maxerr / maxref);
+  return maxerr / maxref;
+}
+
+static void time_layer(int kind, int N, int C, int K, int relu) {
+  std::vector<float> w((size_t)K * C * (kind == 0 ? 9 : 1)), sc(K, 1.f), sh(K, 0.f);
+  for (auto& v : w) v = frand();
+  wg_layer_t* L = nullptr;
+  int rc = kind == 0 ? wg_conv3x3_create(&L, C, K, w.data(), sc.data(), sh.data(), relu, WG_TF32, 0)
+                     : wg_conv1x1_create(&L, C, K, w.data(), sc.data(), sh.data(), relu, WG_TF32, 0);
+  if (rc) return;
+  const size_t xe = (size_t)N * (kind == 0 ? 256 : 196) * C, ye = (size_t)N * 196 * K;
+  float *dx, *dy;
+  CK(cudaMalloc(&dx, xe * 4));
+  CK(cudaMalloc(&dy, ye * 4));
+  CK(cudaMemset(dx, 0, xe * 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) wg_run(L, dx, dy, N, 0, nullptr);
+  CK(cudaDeviceSynchronize());
+  const int iters = 20;
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i) wg_run(L, dx, dy, N, 0, nullptr);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double us = ms * 1000.0 / iters;
+  const double flops = 2.0 * N * 196 * C * K * (kind == 0 ? 9 : 1);
+  printf("time %s N=%d %d->%d: %.2f us/launch (L2-warm, back-to-back), %.1f TFLOP/s direct-equivalent\n",
+         kind == 0 ? "3x3" : "1x1", N, C, K, us, flops / us * 1e-6);
+  wg_destroy(L);
+  cudaFree(dx);
+  cudaFree(dy);
+}
+
+int main(int argc, char** argv) {
+  const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  printf("sm_100 devices: %d\n", wg_device_count());
+  if (wg_device_count() == 0) return 1;
+  int probe = run_probe();
+  printf("probe result mask: %d\n", probe);
+  int fails = 0;
+  auto bad = [&](double rel, double tol) {
+    if (!(rel <= tol)) ++fails;
+  };
+  bad(check3x3(1, 128, 128, 1, 0, {0}), 1e-3);
+  bad(check3x3(1, 128, 128, 1, 1, {0}), 1e-3);
+  bad(check3x3(3, 64, 64, 0, 0, {0, 1, 2}), 1e-3);
+  bad(check3x3(7, 32, 32, 1, 1, {0, 3, 6}), 1e-3);
+  bad(check1x1(1, 512, 128, 1, {0}), 1e-3);
+  bad(check1x1(1, 128, 512, 0, {0}), 1e-3);
+  bad(check1x1(3, 64, 256, 0, {0, 2}), 1e-3);
+  if (!quick) {
+    bad(check3x3(1, 256, 256, 1, 1, {0}), 1e-3);
+    bad(check3x3(256, 128, 128, 1, 0, {0, 131, 255}), 1e-3);
+    bad(check3x3(64, 256, 256, 1, 0, {0, 63}), 1e-3);
+    bad(check1x1(1, 1024, 256, 1, {0}), 1e-3);
+    bad(check1x1(1, 256, 1024, 0, {0}), 1e-3);
+    bad(check1x1(256, 512, 128, 1, {0, 255}), 1e-3);
+    bad(check1x1(256, 256, 1024, 0, {0, 255}), 1e-3);
+    time_layer(0, 1, 128, 128, 1);
+    time_layer(0, 256, 128, 128, 1);
+    time_layer(0, 1, 256, 256, 1);
+    time_layer(0, 256, 256, 256, 1);
+    time_layer(1, 1, 512, 128, 1);
+    time_layer(1, 256, 512, 128, 1);
+    time_layer(1, 256, 128, 512, 0);
+    time_layer(1, 256, 1024, 256, 1);
+    time_layer(1, 256, 256, 1024, 0);
+  }
+  printf("selftest: %d failing checks, %lld launches\n", fails, wg_launch_count());
+  return fails ? 1 : 0;
+}
