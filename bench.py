@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline number on B200, one JSON line on stdout (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                       # the CPU golden (oracle port) on the host cores
+    python bench.py --all-shapes                                 # extra: every README shape, N=1 latency + N=256
+
+Workload (BASELINE.json configs[1] shape at the configs[3] batch): fused 3x3 conv (Winograd F(2x2,3x3)) + BN + ReLU,
+Cin = Cout = 256, 14x14 maps (16x16 frames), 256 images per GPU per step, FP32 in/out, TF32 tensor-core arithmetic,
+synthetic seeded data in the reference's data_generator.py distributions. A step = ONE kernel launch over the batch.
+Batch-sharded across ranks with no collective on the hot path (weak scaling: 256 images per GPU).
+
+  value      images/s, inputs resident in HBM, CUDA events on the launch stream, max over ranks
+  e2e        images/s through the C-ABI call with HOST buffers (wg_run_host: pinned H2D + kernel + D2H every step)
+  roofline   direct-conv-equivalent FLOPs per launch / measured launch time vs the tensor peak
+  cpu_baseline  the NumPy FP32 golden (9 shifted sgemms + BN + ReLU, oracle/golden.py) timed on this box's host cores
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C_IN = C_OUT = 256
+IMAGES_PER_GPU = 256
+FLOP_PER_IMAGE = 2 * 196 * C_IN * C_OUT * 9            # direct-conv equivalent, SURVEY.md section 8d: 231.21 MFLOP
+BYTES_PER_IMAGE = (256 * C_IN + 196 * C_OUT) * 4       # compulsory fp32 in + out
+WEIGHT_BYTES = C_OUT * C_IN * 9 * 4 + 2 * C_OUT * 4
+METRIC = "fused_conv3x3_bn_relu_256x256_images_per_s"
+UNIT = "images/s"
+N_SETS = 4                                             # rotating buffer sets: 4 x 118 MB > 126 MB L2
+
+
+def workload_name():
+    return ("conv3x3 Winograd F(2x2,3x3)+BN+ReLU Cin=Cout=256 14x14 (16x16 frames), N=256 images/GPU/step, "
+            "fp32 I/O, tf32 MMA [BASELINE configs[1] shape at configs[3] batch]")
+
+
+def make_params(seed=0):
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    rs = np.random.RandomState(seed)
+    w = (rs.rand(C_OUT, C_IN, 3, 3) - 0.5).astype(np.float32)
+    gamma, beta, mean = ((rs.rand(C_OUT) - 0.5).astype(np.float32) for _ in range(3))
+    var = (rs.rand(C_OUT) * 3 + 5).astype(np.float32)
+    sd = np.sqrt(var + np.float32(1e-5))
+    return w, (gamma / sd).astype(np.float32), (beta - gamma * mean / sd).astype(np.float32)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs (NVML in-process, ~2 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+# ----------------------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import wg_loader
+    wg = wg_loader.load()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback for the product arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    w, scale, shift = make_params()
+    layer = wg.Conv3x3BnRelu(w, scale, shift, relu=True, device=local)
+    n = IMAGES_PER_GPU
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    xs = [torch.rand((n, 16, 16, C_IN), device=dev, generator=g) - 0.5 for _ in range(N_SETS)]
+    ys = [torch.empty((n, 14, 14, C_OUT), device=dev) for _ in range(N_SETS)]
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        layer(xs[i % N_SETS], out=ys[i % N_SETS])
+    barrier()
+
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = wg.launch_count()
+    sampler.start()
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        layer(xs[i % N_SETS], out=ys[i % N_SETS])
+    e1.record(stream)
+    barrier()
+    launches = wg.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if clocks["samples"] == 0 and sampler.ok:
+        # timed region shorter than one sampling period: sample the same loop again, untimed, to report clocks
+        sampler = ClockSampler(local)
+        sampler.start()
+        t_end = time.time() + 0.3
+        while time.time() < t_end:
+            for i in range(50):
+                layer(xs[i % N_SETS], out=ys[i % N_SETS])
+            torch.cuda.synchronize(dev)
+        clocks = sampler.stop()
+        clocks["note"] = "timed region shorter than the sampling period; sampled over an identical untimed loop after it"
+
+    # ---- e2e: host buffers through wg_run_host (pinned H2D + kernel + D2H each step)
+    xh = [torch.empty((n, 16, 16, C_IN), pin_memory=True).copy_(xs[i].cpu()) for i in range(2)]
+    yh = torch.empty((n, 14, 14, C_OUT), pin_memory=True)
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        layer.run_host_ptr(xh[i % 2].data_ptr(), yh.data_ptr(), n)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        layer.run_host_ptr(xh[i % 2].data_ptr(), yh.data_ptr(), n)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    loss_like = float(yh[0, 0, 0, 0])  # the step's result is read on the host
+
+    # ---- optional: the one exchange step, an all-gather of the output shards (north_star), timed separately
+    gather_ms = None
+    if dist is not None:
+        out_all = torch.empty((world * n, 14, 14, C_OUT), device=dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(out_all, ys[0])
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for i in range(5):
+            layer(xs[i % N_SETS], out=ys[i % N_SETS])
+            dist.all_gather_into_tensor(out_all, ys[i % N_SETS])
+        g1.record(stream)
+        barrier()
+        gather_ms = g0.elapsed_time(g1) / 5
+
+    if dist is not None:
+        t = torch.tensor([ms, e2e_s, gather_ms or 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s, gmax = (float(v) for v in t.tolist())
+        gather_ms = gmax if gather_ms is not None else None
+
+    if rank == 0:
+        pk = peaks()
+        ms_per_step = ms / args.steps
+        value = world * n * args.steps / (ms * 1e-3)
+        tflops = FLOP_PER_IMAGE * n / (ms_per_step * 1e-3) / 1e12
+        tf32_peak = pk["bf16_sustained"] / 2.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("wino3x3_256_n256_dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": workload_name(), "images_per_gpu": n, "global_batch": world * n,
+                       "parallelism": f"batch-sharded x{world}, no collective on the hot path",
+                       "l2": f"rotating {N_SETS} input/output sets ({N_SETS * n * BYTES_PER_IMAGE / 1e6:.0f} MB) > 126 MB L2",
+                       "peaks": pk["source"]},
+            "clocks": clocks,
+            "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 256 * C_IN * 4,
+                    "d2h_bytes_per_step": n * 196 * C_OUT * 4, "steps": e2e_steps, "api": "wg_run_host (C-ABI)",
+                    "result_read": loss_like},
+            "gpu_launches": int(launches) * world,
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": tflops / tf32_peak, "traffic": traffic,
+                         "kernel": "wino3x3_bn_relu_kernel<32>",
+                         "algorithmic": "direct-conv-equivalent 2*196*256*256*9 = 231.21 MFLOP/image x 256 images/launch",
+                         "peak_note": "dense TF32 = half of the measured sustained bf16 cuBLAS rate in " + pk["source"],
+                         "hbm": {"achieved_gbs": (BYTES_PER_IMAGE * n + WEIGHT_BYTES) / (ms_per_step * 1e-3) / 1e9,
+                                 "peak_gbs": pk["hbm"],
+                                 "frac": (BYTES_PER_IMAGE * n + WEIGHT_BYTES) / (ms_per_step * 1e-3) / 1e9 / pk["hbm"]}},
+        }
+        if gather_ms is not None:
+            line["with_output_allgather"] = {"ms_per_step": gather_ms, "value": world * n / (gather_ms * 1e-3),
+                                             "unit": UNIT, "collective": "nccl all_gather_into_tensor of fp32 output"}
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(budget_s=12.0)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------- CPU arm
+def _cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_step(x, w, scale, shift):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import golden
+    return golden.conv3x3_bn_relu_fp32(x, w, scale, shift, relu=True)
+
+
+def cpu_baseline(budget_s=12.0, sample_images=32):
+    """The NumPy FP32 golden on the host cores over a bounded sample of the same workload."""
+    import numpy as np
+    w, scale, shift = make_params()
+    rs = np.random.RandomState(1)
+    x = (rs.rand(sample_images, 16, 16, C_IN) - 0.5).astype(np.float32)
+    cpu_step(x[:2], w, scale, shift)
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        cpu_step(x, w, scale, shift)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or reps >= 200:
+            break
+    return {"value": reps * sample_images / el, "unit": UNIT, "cores": _cpu_threads(), "kind": "port",
+            "sample": f"{reps} x {sample_images} images of the same 256->256 3x3 layer, NumPy fp32 (9 shifted sgemms + "
+                      f"BN + ReLU, oracle/golden.py), {el:.1f} s", "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference has no CPU implementation and its CUDA/cuDNN program is not the CPU arm asked
+    for here; the arm is the oracle port (NumPy FP32 golden) with all host threads, same metric/config. Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np
+    w, scale, shift = make_params()
+    sample = 64
+    rs = np.random.RandomState(1)
+    x = (rs.rand(sample, 16, 16, C_IN) - 0.5).astype(np.float32)
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_step(x, w, scale, shift)
+    steps = max(1, min(args.steps, 50))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(x, w, scale, shift)
+    el = time.perf_counter() - t0
+    value = steps * sample / el
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(1, min(args.warmup, 3)), "ms_per_step": el / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "sample_images_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": _cpu_threads(), "kind": "port",
+                             "sample": f"{steps} steps x {sample} images, NumPy fp32 golden (oracle/golden.py)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- all README shapes
+def run_all_shapes(args):
+    """Every README shape: N=1 latency (L2-warm, like the reference's loop) and N=256 throughput (rotating buffers),
+    CUDA events. Writes profiles/all_shapes_latest.json; one summary line per shape on stderr."""
+    import numpy as np
+    import torch
+    import wg_loader
+    wg = wg_loader.load()
+    dev = torch.device("cuda", 0)
+    pk = peaks()
+    rows = []
+    shapes = [("3x3", 128, 128, True), ("3x3", 256, 256, True), ("1x1", 512, 128, True), ("1x1", 128, 512, False),
+              ("1x1", 1024, 256, True), ("1x1", 256, 1024, False)]
+    for kind, cin, cout, relu in shapes:
+        rs = np.random.RandomState(0)
+        if kind == "3x3":
+            layer = wg.Conv3x3BnRelu((rs.rand(cout, cin, 3, 3) - 0.5).astype(np.float32),
+                                     rs.rand(cout).astype(np.float32), rs.rand(cout).astype(np.float32), relu)
+            in_shape, out_shape, taps = (16, 16, cin), (14, 14, cout), 9
+        else:
+            layer = wg.Conv1x1Bn((rs.rand(cin, cout) - 0.5).astype(np.float32), rs.rand(cout).astype(np.float32),
+                                 rs.rand(cout).astype(np.float32), relu)
+            in_shape, out_shape, taps = (196, cin), (196, cout), 1
+        for n in (1, 256):
+            sets = 1 if n == 1 else N_SETS
+            xs = [torch.rand((n,) + in_shape, device=dev) - 0.5 for _ in range(sets)]
+            ys = [torch.empty((n,) + out_shape, device=dev) for _ in range(sets)]
+            for i in range(5):
+                layer(xs[i % sets], out=ys[i % sets])
+            torch.cuda.synchronize()
+            iters = 200
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                layer(xs[i % sets], out=ys[i % sets])
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / iters
+            flops = 2.0 * 196 * cin * cout * taps * n
+            byts = (np.prod(in_shape) + np.prod(out_shape)) * 4.0 * n + cin * cout * taps * 4.0
+            row = dict(kind=kind, cin=cin, cout=cout, relu=relu, n=n, us_per_layer=us,
+                       images_per_s=n / (us * 1e-6), tflops_direct_equiv=flops / us * 1e-6,
+                       hbm_gbs_algorithmic=byts / us * 1e-3,
+                       frac_tf32_peak=flops / us * 1e-6 / (pk["bf16_sustained"] / 2),
+                       frac_hbm_peak=byts / us * 1e-3 / pk["hbm"])
+            rows.append(row)
+            print(f"{kind} {cin:>4}->{cout:<4} N={n:<3} {us:9.2f} us  {row['tflops_direct_equiv']:7.1f} TF/s "
+                  f"({100 * row['frac_tf32_peak']:.1f}% tf32)  {row['hbm_gbs_algorithmic']:7.0f} GB/s "
+                  f"({100 * row['frac_hbm_peak']:.1f}% hbm)", file=sys.stderr)
+            del xs, ys
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "all_shapes_latest.json"), "w") as f:
+        json.dump(dict(peaks=pk, rows=rows), f, indent=1)
+    print(json.dumps({"all_shapes": rows}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--all-shapes", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.all_shapes:
+        return run_all_shapes(args)
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

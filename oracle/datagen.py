@@ -118,6 +118,17 @@ def generate_all(out, seed=0, f4x4=True, goldens=True):
     return result
 
 
+def generate_reference_main(out, seed=0):
+    """Exactly the call sequence of the reference's __main__ (data_generator.py:116-127): the 128 set, then the 1x1
+    set. With np.random.seed(seed) the reference script writes byte-identical files (tests/golden/ref_datagen_seed0.json)."""
+    os.makedirs(out, exist_ok=True)
+    rs = np.random.RandomState(seed)
+    bias_generator(rs, out, 128)
+    input_generator(rs, out, 128)
+    weight_generator(rs, out, 128, 128, f4x4=True)
+    onebyone_generator(rs, out)
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--out", default="data")

@@ -1,0 +1,169 @@
+"""CPU tests (-m "not gpu"): the C-ABI library builds, loads and exports what include/*.h declares; host-side helpers;
+loud failure without a GPU; batch sharding + output gather over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built(wg):
+    wg.build()
+    return wg
+
+
+def _declared_symbols():
+    names = set()
+    for h in ("winograd_b200.h", "wg_legacy.h", "util.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        for m in re.finditer(r"^[\w\s\*]+?\b(\w+)\s*\([^;{]*\)\s*;", src, flags=re.M):
+            if "typedef" not in m.group(0):
+                names.add(m.group(1))
+    return names
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = built.lib()
+    declared = _declared_symbols()
+    assert {"wg_run", "wg_conv3x3_create", "kernel_128", "kernel_256_1_out", "get_parameter"} <= declared
+    assert declared == set(built.ABI_SYMBOLS), declared ^ set(built.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/ but not exported"
+
+
+def test_compat_headers_have_the_reference_names():
+    for h in ("Kernel128_winograd.h", "Kernel256_winograd.h", "Kernel128_one.h", "Kernel256_one.h", "util.h"):
+        assert os.path.exists(os.path.join(ROOT, "include", h))
+    assert os.path.exists(os.path.join(ROOT, "Test")), "make builds the ./Test harness"
+
+
+def test_no_cudnn_no_cublas_in_product(built):
+    out = subprocess.run(["ldd", built.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cudnn" not in out and "cublas" not in out, out
+
+
+def test_sass_is_blackwell_native(built):
+    sass = subprocess.run(["cuobjdump", "-sass", built.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCQMMA" in sass or re.search(r"UTC\w*MMA", sass)   # tcgen05.mma
+    assert "UTMALDG" in sass and "UBLKCP" in sass                                     # TMA tensor + bulk copies
+    assert "LDTM" in sass                                                             # tcgen05.ld
+    assert "HMMA" not in sass.replace("UTCHMMA", "")                                   # no legacy mma.sync path
+
+
+def test_fold_bn_matches_reference_formula(built, golden_dir):
+    t = np.load(os.path.join(golden_dir, "ref_tiny.npz"))
+    sc, sh = built.fold_bn(t["bnScale_8"], t["bnBias_8"], t["eMean_8"], t["eVar_8"])
+    np.testing.assert_allclose(sc, t["bnScale_winograd_8"], rtol=2e-7)
+    np.testing.assert_allclose(sh, t["bnBias_winograd_8"], rtol=2e-7, atol=1e-8)
+
+
+def test_host_utils_match_reference_semantics(built, tmp_path):
+    L = built.lib()
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.get_parameter.restype = fp
+    L.get_parameter.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.transpose.restype = fp
+    L.transpose.argtypes = [fp, ctypes.c_int, ctypes.c_int]
+    L.output_checker.restype = ctypes.c_float
+    L.output_checker.argtypes = [fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.getTimeMicroseconds64.restype = ctypes.c_uint64
+    a = np.arange(12, dtype=np.float32)
+    p = tmp_path / "a.bin"
+    a.tofile(p)
+    buf = L.get_parameter(str(p).encode(), 12)
+    assert [buf[i] for i in range(12)] == list(a)
+    # transpose(weight, h, w): weight is [w][h] -> [h][w] (util.c:15-26)
+    t = L.transpose(buf, 3, 4)
+    got = np.array([t[i] for i in range(12)], np.float32).reshape(3, 4)
+    np.testing.assert_array_equal(got, a.reshape(4, 3).T)
+    t0, t1 = L.getTimeMicroseconds64(), L.getTimeMicroseconds64()
+    assert 0 <= t1 - t0 < 10_000_000
+    A = np.zeros((16, 16, 2), np.float32)
+    B = np.zeros((14, 14, 2), np.float32)
+    A[3, 4, 1] = 0.25
+    assert L.output_checker(A.ctypes.data_as(fp), B.ctypes.data_as(fp), 14, 2, 1) == 0.25
+
+
+def test_missing_file_exits_like_the_reference(built, tmp_path):
+    """util.c:36-39: a missing data file prints 'Bad file path' and exit(0)s the process."""
+    code = ("import sys; sys.path.insert(0, %r); import wg_loader; m = wg_loader.load(); m.kernel_128(); print('survived')"
+            % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], cwd=tmp_path, capture_output=True, text=True)
+    assert "Bad file path" in r.stdout and "survived" not in r.stdout and r.returncode == 0
+
+
+def test_fails_loudly_without_a_gpu(built):
+    if built.device_count() > 0:
+        pytest.skip("a B200 is visible")
+    w = np.zeros((32, 32, 3, 3), np.float32)
+    s = np.ones(32, np.float32)
+    with pytest.raises(built.WinogradB200Error, match="no sm_100"):
+        built.Conv3x3BnRelu(w, s, s)
+    with pytest.raises(built.WinogradB200Error, match="no sm_100"):
+        built.Conv1x1Bn(np.zeros((32, 128), np.float32), np.ones(128, np.float32), np.ones(128, np.float32), True)
+
+
+def test_bad_arguments_are_rejected(built):
+    L = built.lib()
+    h = ctypes.c_void_p()
+    fp = ctypes.POINTER(ctypes.c_float)
+    z = np.zeros(8, np.float32).ctypes.data_as(fp)
+    assert L.wg_conv3x3_create(ctypes.byref(h), 7, 32, z, z, z, 1, 0, 0) == -1      # C not a multiple of 8
+    assert L.wg_conv1x1_create(ctypes.byref(h), 32, 100, z, z, z, 1, 0, 0) == -1    # Cout not a multiple of 128
+    assert L.wg_run(None, None, None, 1, 0, None) == -1
+    assert L.wg_destroy(None) == -1
+    assert b"argument" in L.wg_strerror(-1)
+
+
+def test_shard_range_partitions_the_batch(wg):
+    for n in (1, 7, 255, 256, 257):
+        for world in (1, 2, 3, 4, 8):
+            r = [wg.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "oracle"))
+import numpy as np, torch, torch.distributed as dist
+import wg_loader, golden
+wg = wg_loader.load()
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[3])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+N = 5
+rs = np.random.RandomState(3)
+x = (rs.rand(N, 196, 32) - 0.5).astype(np.float32)
+w = (rs.rand(32, 128) - 0.5).astype(np.float32)
+sc = rs.rand(128).astype(np.float32); sh = rs.rand(128).astype(np.float32)
+lo, hi = wg.shard_range(N, rank, world)
+# the per-rank compute is stood in for by the ORACLE here (CPU test of the host-side shard/gather logic only)
+y_local = torch.from_numpy(golden.conv1x1_bn(x[lo:hi], w, sc, sh, True))
+y = wg.gather_output(y_local, N)
+full = golden.conv1x1_bn(x, w, sc, sh, True)
+assert y.shape == full.shape, (y.shape, full.shape)
+assert np.array_equal(y.numpy(), full)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_shard_and_gather_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER % {"root": ROOT})
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {r} ok" in o, o

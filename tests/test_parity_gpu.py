@@ -1,0 +1,200 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the oracle on the same seeded inputs.
+
+Tolerance (north_star): max|out - golden| / max|golden| <= 1e-3 for the TF32 path, stated once here as TOL_TF32.
+Nothing in this file reads /root/reference (it does not exist on the GPU box); the reference's own kernels, when
+checked, come prebuilt from oracle/_ref/ (see test_reference_gpu.py).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import datagen
+import golden
+
+pytestmark = pytest.mark.gpu
+TOL_TF32 = 1e-3
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a B200"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def lib_loaded(wg):
+    assert os.path.exists(wg.LIB_PATH), "libwinograd_b200.so must be prebuilt in-tree (make / __graft_entry__.build())"
+    assert wg.device_count() >= 1
+    return wg
+
+
+def _rand3x3(rs, n, c, k):
+    x = (rs.rand(n, 16, 16, c) - 0.5).astype(np.float32)
+    w = (rs.rand(k, c, 3, 3) - 0.5).astype(np.float32)
+    g, b, m = ((rs.rand(k) - 0.5).astype(np.float32) for _ in range(3))
+    v = (rs.rand(k) * 3 + 5).astype(np.float32)
+    sc, sh = golden.fold_bn(g, b, m, v)
+    return x, w, sc, sh
+
+
+# ------------------------------------------------------------------------------------------ the reference's six cases
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("padded", [False, True])
+def test_3x3_reference_shapes_n1(lib_loaded, torch_cuda, seeded_data, mode, padded):
+    """./Test 0 and ./Test 1 inputs (seeded restatement of data_generator.py), N = 1."""
+    torch = torch_cuda
+    _, t = seeded_data
+    d = t[mode]
+    layer = lib_loaded.Conv3x3BnRelu(d["w"], d["scale"], d["shift"], relu=True)
+    y = layer(torch.from_numpy(d["x"]).cuda(), out_padded=padded).cpu().numpy()
+    gold = d["golden"][None]
+    if padded:
+        assert y.shape == (1, 16, 16, d["w"].shape[0])
+        assert np.all(y[:, 0] == 0) and np.all(y[:, 15] == 0) and np.all(y[:, :, 0] == 0) and np.all(y[:, :, 15] == 0)
+        y = y[:, 1:15, 1:15]
+    assert golden.rel_err(y, gold) <= TOL_TF32
+
+
+@pytest.mark.parametrize("mode,cin,cout,relu", datagen.ONE_CASES)
+def test_1x1_reference_shapes_n1(lib_loaded, torch_cuda, seeded_data, mode, cin, cout, relu):
+    """./Test 2..5 inputs: prefixes of the shared *_one_1024 files; ReLU only for the `_in` shapes."""
+    torch = torch_cuda
+    _, t = seeded_data
+    d = t[mode]
+    layer = lib_loaded.Conv1x1Bn(np.ascontiguousarray(d["w"]), d["scale"], d["shift"], relu)
+    y = layer(torch.from_numpy(np.ascontiguousarray(d["x"]))[None].cuda()).cpu().numpy()[0]
+    assert golden.rel_err(y, d["golden"]) <= TOL_TF32
+    assert (y.min() >= 0) == relu
+
+
+# ------------------------------------------------------------------------------------------------------- batch / edges
+@pytest.mark.parametrize("n,c,k", [(2, 32, 32), (3, 64, 96), (5, 128, 128), (8, 8, 32), (11, 40, 64)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_3x3_ragged_batches(lib_loaded, torch_cuda, n, c, k, relu):
+    """Batches whose 49*N tiles do not fill the last 128-tile M-block, odd channel-block counts, no-ReLU variant."""
+    torch = torch_cuda
+    x, w, sc, sh = _rand3x3(np.random.RandomState(100 + n), n, c, k)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=relu)
+    y = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert golden.rel_err(y, golden.conv3x3_bn_relu(x, w, sc, sh, relu)) <= TOL_TF32
+
+
+@pytest.mark.parametrize("n,cin,cout", [(1, 32, 128), (2, 96, 256), (3, 64, 384), (7, 512, 128)])
+def test_1x1_ragged_batches(lib_loaded, torch_cuda, n, cin, cout):
+    torch = torch_cuda
+    rs = np.random.RandomState(200 + n)
+    x = ((rs.rand(n, 196, cin) - 0.5) * 40).astype(np.float32)
+    w = ((rs.rand(cin, cout) - 0.5) * 40).astype(np.float32)
+    sc = (rs.rand(cout) - 0.5).astype(np.float32)
+    sh = ((rs.rand(cout) - 0.5) * 40).astype(np.float32)
+    layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu=False)
+    y = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert golden.rel_err(y, golden.conv1x1_bn(x, w, sc, sh, False)) <= TOL_TF32
+
+
+def test_special_inputs(lib_loaded, torch_cuda):
+    """All-zero input -> relu(shift); a single one-hot pixel -> the filter tap itself (up to TF32 rounding of w)."""
+    torch = torch_cuda
+    rs = np.random.RandomState(5)
+    _, w, sc, sh = _rand3x3(rs, 1, 32, 32)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=False)
+    y0 = layer(torch.zeros(1, 16, 16, 32, device="cuda")).cpu().numpy()
+    np.testing.assert_array_equal(y0, np.broadcast_to(sh, y0.shape))
+    x = np.zeros((1, 16, 16, 32), np.float32)
+    x[0, 5, 6, 3] = 1.0
+    y = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    gold = golden.conv3x3_bn_relu(x, w, sc, sh, relu=False)
+    np.testing.assert_allclose(y, gold, atol=2e-3 * np.abs(w).max() * np.abs(sc).max() + 1e-6)
+
+
+# ------------------------------------------------------------------------------------------- BASELINE.json full sizes
+@pytest.mark.parametrize("c", [128, 256])
+def test_3x3_full_batch_256_properties(lib_loaded, torch_cuda, c):
+    """N = 256 (BASELINE.json configs[3]): oracle on a sample of images; batch invariance (image i inside the batch ==
+    image i alone, bit for bit -- tiles are independent GEMM rows); border of the padded frame exactly zero."""
+    torch = torch_cuda
+    n = 256
+    x, w, sc, sh = _rand3x3(np.random.RandomState(c), n, c, c)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True)
+    xd = torch.from_numpy(x).cuda()
+    y = layer(xd)
+    yp = layer(xd, out_padded=True)
+    torch.cuda.synchronize()
+    assert torch.equal(yp[:, 1:15, 1:15], y)
+    assert float(yp[:, 0].abs().max()) == 0 and float(yp[:, 15].abs().max()) == 0
+    assert float(yp[:, :, 0].abs().max()) == 0 and float(yp[:, :, 15].abs().max()) == 0
+    yh = y.cpu().numpy()
+    for i in (0, 1, 2, 77, 130, 255):
+        assert golden.rel_err(yh[i], golden.conv3x3_bn_relu(x[i:i + 1], w, sc, sh)[0]) <= TOL_TF32
+        alone = layer(xd[i:i + 1].contiguous()).cpu().numpy()[0]
+        np.testing.assert_array_equal(alone, yh[i])
+    # checksum of checksums against the oracle on a strided subset (keeps the CPU side to seconds)
+    sub = np.arange(0, n, 16)
+    gold = golden.conv3x3_bn_relu(x[sub], w, sc, sh)
+    assert abs(yh[sub].astype(np.float64).sum() - gold.astype(np.float64).sum()) <= 1e-3 * np.abs(gold).sum()
+
+
+@pytest.mark.parametrize("cin,cout,relu", [(512, 128, True), (128, 512, False), (1024, 256, True), (256, 1024, False)])
+def test_1x1_full_batch_256_properties(lib_loaded, torch_cuda, cin, cout, relu):
+    torch = torch_cuda
+    n = 256
+    rs = np.random.RandomState(cin)
+    x = ((rs.rand(n, 196, cin) - 0.5) * 40).astype(np.float32)
+    w = ((rs.rand(cin, cout) - 0.5) * 40).astype(np.float32)
+    sc = ((rs.rand(cout) - 0.5) * 8).astype(np.float32)
+    sh = ((rs.rand(cout) - 0.5) * 40).astype(np.float32)
+    layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu)
+    xd = torch.from_numpy(x).cuda()
+    yh = layer(xd).cpu().numpy()
+    for i in (0, 3, 128, 255):
+        assert golden.rel_err(yh[i], golden.conv1x1_bn(x[i], w, sc, sh, relu)) <= TOL_TF32
+        np.testing.assert_array_equal(layer(xd[i:i + 1].contiguous()).cpu().numpy()[0], yh[i])
+    if not relu:
+        # linearity in the input (no ReLU): f(2x) - shift == 2 (f(x) - shift), exactly (power-of-two scaling)
+        y2 = layer(xd[:4] * 2).cpu().numpy()
+        np.testing.assert_allclose(y2 - sh, 2 * (yh[:4] - sh), rtol=1e-5, atol=1e-2)
+
+
+# ----------------------------------------------------------------------------------------------------- API behaviour
+def test_host_buffer_call_equals_device_call_and_counts_launches(lib_loaded, torch_cuda):
+    torch = torch_cuda
+    x, w, sc, sh = _rand3x3(np.random.RandomState(9), 4, 64, 64)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh)
+    before = lib_loaded.launch_count()
+    y_dev = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert lib_loaded.launch_count() == before + 1          # ONE kernel per fused layer call
+    y_host = layer.run_host(x)
+    assert lib_loaded.launch_count() == before + 2
+    np.testing.assert_array_equal(y_dev, y_host)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        y_s = layer(torch.from_numpy(x).cuda())
+    s.synchronize()
+    np.testing.assert_array_equal(y_s.cpu().numpy(), y_dev)
+
+
+def test_legacy_entry_points_and_test_binary(lib_loaded, seeded_data, tmp_path):
+    """kernel_128() ... kernel_256_1_out(): read data/*.bin from the CWD, return (mine_us << 16) | baseline_us
+    (Kernel128_winograd.cu:433); ./Test n prints the reference's lines (Test.c:23,50-53)."""
+    out_dir, t = seeded_data
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(out_dir))
+    try:
+        for mode, fn in enumerate(lib_loaded.LEGACY_ENTRIES):
+            res = fn()
+            assert res >= 0 and (res & 0xFFFF) == 0 and (res >> 16) < 65536
+            gold = t[mode]["golden"]
+            cout = gold.shape[-1]
+            y = lib_loaded.legacy_last_output(cout)
+            assert golden.rel_err(y, gold.reshape(196, cout)) <= TOL_TF32
+        env = dict(os.environ, WG_TEST_ITERS="4")
+        r = subprocess.run([os.path.join(ROOT, "Test"), "0"], capture_output=True, text=True, env=env, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "---- Iter: 3 ----" in r.stdout and "TotalTime = " in r.stdout and "[max_error:" in r.stdout
+        assert "Average Total Time: [Mine:" in r.stdout
+    finally:
+        os.chdir(cwd)

@@ -1,0 +1,76 @@
+"""GPU tests (-m gpu): pin the oracle against THE REFERENCE'S OWN KERNELS run on the same seeded files.
+
+oracle/_ref/libref_dump.so is built in the build container from the sources where they lie under /root/reference
+(oracle/Makefile, oracle/ref_wrap.cu) and travels to the GPU box prebuilt; nothing here reads /root/reference.
+This is what turns "parity unpinned" (the reference ships no golden vectors) into a pinned
+oracle: reference arithmetic (F(4x4) FP32 FFMA, 3 kernels / FP32 1x1 kernels) == numpy golden, within the report's own
+acceptance rule for 3x3 (max abs ~1e-5, < 0.1 % of elements over 1e-5; report.pdf section 5) and within FP32 round-off
+of the U(-20,20) data for 1x1 (README.md:29 calls that table "[BUGGY NUMBERS]": absolute 1e-5 is meaningless there).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import datagen
+import golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libref_dump.so")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref/libref_dump.so not built (needs /root/reference at build time)")
+    try:
+        L = ctypes.CDLL(REF_LIB)
+    except OSError as e:  # e.g. libcudnn.so.9 missing on this box
+        pytest.skip(f"cannot load the reference build: {e}")
+    fp = ctypes.POINTER(ctypes.c_float)
+    for name in ("ref_dump_128w", "ref_dump_256w", "ref_dump_128_1_in", "ref_dump_128_1_out", "ref_dump_256_1_in",
+                 "ref_dump_256_1_out"):
+        getattr(L, name).argtypes = [fp] * 5
+    return L
+
+
+def _p(a):
+    return np.ascontiguousarray(a, np.float32).ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+@pytest.mark.parametrize("mode,ch", [(0, 128), (1, 256)])
+def test_reference_winograd_kernels_match_oracle(ref, seeded_data, mode, ch):
+    out_dir, t = seeded_data
+    d = t[mode]
+    u36 = np.fromfile(os.path.join(out_dir, f"weight_winograd_{ch}_{ch}.bin"), "<f4")
+    out = np.full((16, 16, ch), 9.0, np.float32)
+    fn = ref.ref_dump_128w if ch == 128 else ref.ref_dump_256w
+    x = np.ascontiguousarray(d["x"][0])
+    sh, sc = np.ascontiguousarray(d["shift"]), np.ascontiguousarray(d["scale"])
+    assert fn(_p(x), _p(u36), _p(sh), _p(sc), out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == 0
+    max_err, cnt = golden.output_checker(out, d["golden"], 14, ch, 1)
+    assert max_err < 1e-4, max_err
+    assert cnt < 0.001 * 196 * ch, cnt
+    assert out[0].max() == 0 and out[:, 0].max() == 0          # zero border of the padded frame
+    # and the numpy emulation of those kernels is the same arithmetic
+    if ch == 128:
+        emu = golden.reference_pipeline_f4x4(x, u36.reshape(36, ch, ch), sc, sh)
+        assert np.abs(emu - out).max() < 5e-5
+
+
+_ONE_FN = {2: "ref_dump_128_1_in", 3: "ref_dump_128_1_out", 4: "ref_dump_256_1_in", 5: "ref_dump_256_1_out"}
+
+
+@pytest.mark.parametrize("mode,cin,cout,relu", datagen.ONE_CASES)
+def test_reference_1x1_kernels_match_oracle(ref, seeded_data, mode, cin, cout, relu):
+    _, t = seeded_data
+    d = t[mode]
+    out = np.empty((196, cout), np.float32)
+    x, w = np.ascontiguousarray(d["x"]), np.ascontiguousarray(d["w"])
+    sh, sc = np.ascontiguousarray(d["shift"]), np.ascontiguousarray(d["scale"])
+    rc = getattr(ref, _ONE_FN[mode])(_p(x), _p(w), _p(sh), _p(sc), out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    assert rc == 0
+    assert golden.rel_err(out, d["golden"]) < 5e-6             # FP32 accumulation order only
+    assert (out.min() >= 0) == relu
