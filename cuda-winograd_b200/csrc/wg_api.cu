@@ -15,7 +15,7 @@ namespace wg {
 static thread_local char g_last_cuda_error[256] = "";
 static std::atomic<long long> g_launches{0};
 static int g_max_ctas = 0;  // 0 = number of SMs
-static int g_wino_kn = 32;
+static int g_wino_kn = 64;  // 64 = folded accumulation (default), 32 = one accumulator per Winograd point
 
 static int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
@@ -99,7 +99,7 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   float* d_w = nullptr;
   size_t filter_elems = 0;
   if (kind == 0) {
-    L->tile_n = (g_wino_kn == 16) ? 16 : 32;
+    L->tile_n = (g_wino_kn == 32 || cout % 64 != 0) ? 32 : 64;
     filter_elems = (size_t)16 * cin * cout;
   } else {
     L->tile_n = (cout % 256 == 0) ? 256 : 128;
@@ -273,6 +273,6 @@ void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean,
 }
 
 void wg_set_max_ctas(int max_ctas) { g_max_ctas = max_ctas; }
-void wg_set_wino_kn(int kn) { g_wino_kn = (kn == 16) ? 16 : 32; }
+void wg_set_wino_kn(int kn) { g_wino_kn = (kn == 32) ? 32 : 64; }
 
 }  // extern "C"

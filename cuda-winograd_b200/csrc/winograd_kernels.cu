@@ -6,14 +6,18 @@
 //
 //   * an M-block is 128 consecutive Winograd tiles (tile index T = n*49 + ty*7 + tx over the whole batch);
 //   * per 8-channel stage the producer warp TMA-loads the 48 input rows the block touches (4-D tensor map with the
-//     x axis split by parity so that stride-2 tile reads are bank-conflict free) and bulk-copies the matching
-//     16-point slice of the pre-transformed filter U (written once per layer by filter_transform.cu in exactly the
+//     x axis split by parity so that stride-2 tile reads are mostly bank-conflict free) and bulk-copies the matching
+//     slice of the pre-transformed filter U (written once per layer by filter_transform_f2x2_kernel in exactly the
 //     shared-memory image the MMA wants);
-//   * 8 transform warps compute V = B^T d B in registers, round to TF32 (RN) and store it in the UMMA K-major
+//   * 8 transform warps compute V = B^T d B in registers, round to TF32 (nearest) and store it in the UMMA K-major
 //     no-swizzle canonical layout;
-//   * one thread issues 16 tcgen05.mma (M=128 tiles, N=KN couts, K=8 channels) per stage, accumulating the 16
-//     Winograd points side by side in TMEM (16*KN fp32 columns);
-//   * after the last stage the same 8 warps run the epilogue: tcgen05.ld the 16 points, Y = A^T M A,
+//   * one thread issues the tcgen05.mma (M=128 tiles, N=KN couts, K=8 channels) of the stage into TMEM:
+//       FOLD = false: 16 MMAs, one accumulator per Winograd point (16*32 = 512 fp32 columns, KN = 32);
+//       FOLD = true : 24 MMAs; the tensor core itself applies the row half of the inverse transform by accumulating
+//                     Z[a][j] = sum_i A^T[a][i] M[i][j] (A^T = [[1,1,1,0],[0,1,-1,-1]], the -1 via the descriptor's
+//                     negate-A bit), so only 8 accumulators live in TMEM and KN = 64: the CUDA-core input transform and
+//                     its shared-memory traffic -- the measured bottleneck -- are repeated K/64 instead of K/32 times;
+//   * after the last stage the same 8 warps run the epilogue: tcgen05.ld, the remaining inverse transform,
 //     relu(scale*Y + shift), 128-bit stores of NHWC output (optionally into the reference's zero-bordered
 //     16x16 frame, Kernel128_winograd.cu:163,243).
 #include "ptx.cuh"
@@ -30,36 +34,44 @@ constexpr int kThreads = 32 * 10;
 constexpr int kRawRows = 48;  // input rows (n*16+y) one M-block can touch, see DESIGN.md
 constexpr uint32_t kRawBytes = kRawRows * 2 * 8 * 32;  // [ny][x parity][x/2][8 ch] fp32 = 24576
 
-template <int KN>
-struct WinoSmem {
-  static constexpr int kRawStages = 2, kVStages = 2, kUStages = 3;
+template <bool FOLD>
+struct WinoCfg {
+  static constexpr int KN = FOLD ? 64 : 32;              // output channels per work item
+  static constexpr int kUChunksPerStage = FOLD ? 2 : 1;  // bulk copies of U per 8-channel stage
+  static constexpr int kPointsPerUChunk = FOLD ? 8 : 16;
+  static constexpr int kRawStages = 2, kVStages = 2, kUBufs = 3;
   // V: per point [2 k-chunks][128 rows][16 B]; the +64 skews chunk 1 by half a bank window so that a quarter warp
   // writing 4 rows x 2 chunks hits 32 distinct banks.
   static constexpr uint32_t kVLbo = 128 * 16 + 64;
   static constexpr uint32_t kVPerXi = kVLbo + 128 * 16;
   static constexpr uint32_t kVBytes = 16 * kVPerXi;
   static constexpr uint32_t kULbo = KN * 16;
-  static constexpr uint32_t kUPerXi = 2 * KN * 16;
-  static constexpr uint32_t kUBytes = 16 * kUPerXi;
+  static constexpr uint32_t kUPerPoint = 2 * KN * 16;
+  static constexpr uint32_t kUChunkBytes = kPointsPerUChunk * kUPerPoint;  // 16 KB in both modes
   static constexpr uint32_t kOffRaw = 0;
   static constexpr uint32_t kOffV = kOffRaw + kRawStages * kRawBytes;
   static constexpr uint32_t kOffU = kOffV + kVStages * kVBytes;
-  static constexpr uint32_t kOffBar = kOffU + kUStages * kUBytes;
-  static constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kVStages + 2 * kUStages + 2;
+  static constexpr uint32_t kOffBar = kOffU + kUBufs * kUChunkBytes;
+  static constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kVStages + 2 * kUBufs + 2;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr uint32_t kTotal = kOffTmemPtr + 16;
   static_assert(kOffV % 128 == 0 && kOffU % 128 == 0 && kOffBar % 8 == 0, "alignment");
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
-template <int KN>
+// Round-to-nearest (ties away) of an fp32 to TF32 precision for a tensor-core operand: the MMA ignores the low 13
+// mantissa bits, so adding half a TF32 ulp to the bit pattern is all that is needed (1 integer add; cvt.rna.tf32.f32
+// compiles to three ALU instructions on sm_100a).
+__device__ __forceinline__ float tf32_operand(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
+template <bool FOLD>
 __global__ void __launch_bounds__(kThreads, 1)
 wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                        const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
                        int n_img, int C, int K, int relu, int out_padded) {
-  using S = WinoSmem<KN>;
-  constexpr uint32_t kTmemCols = 16 * KN;
-  static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128, "TMEM columns must be a power of two");
+  using S = WinoCfg<FOLD>;
+  constexpr int KN = S::KN;
+  constexpr uint32_t kTmemCols = 512;
   extern __shared__ __align__(1024) uint8_t smem[];
 
   const int warp = threadIdx.x >> 5;
@@ -71,8 +83,8 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
   uint64_t* v_full = raw_empty + S::kRawStages;
   uint64_t* v_empty = v_full + S::kVStages;
   uint64_t* u_full = v_empty + S::kVStages;
-  uint64_t* u_empty = u_full + S::kUStages;
-  uint64_t* acc_full = u_empty + S::kUStages;
+  uint64_t* u_empty = u_full + S::kUBufs;
+  uint64_t* acc_full = u_empty + S::kUBufs;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
 
@@ -86,7 +98,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
       mbar_init(&v_full[i], kWorkerWarps);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < S::kUStages; ++i) {
+    for (int i = 0; i < S::kUBufs; ++i) {
       mbar_init(&u_full[i], 1);
       mbar_init(&u_empty[i], 1);
     }
@@ -115,17 +127,22 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
         const int mb = item / n_slices;
         const int t0 = mb * 128;
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
-        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)slice * n_kb * S::kUBytes;
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) +
+                               (size_t)slice * n_kb * S::kUChunksPerStage * S::kUChunkBytes;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&raw_empty[rs], rph ^ 1);
           mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
           tma_tensor_4d_g2s(smem + S::kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
           if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
-
-          mbar_wait(&u_empty[us], uph ^ 1);
-          mbar_arrive_expect_tx(&u_full[us], S::kUBytes);
-          tma_bulk_g2s(smem + S::kOffU + us * S::kUBytes, u_src + (size_t)kb * S::kUBytes, S::kUBytes, &u_full[us]);
-          if (++us == S::kUStages) { us = 0; uph ^= 1; }
+#pragma unroll
+          for (int h = 0; h < S::kUChunksPerStage; ++h) {
+            mbar_wait(&u_empty[us], uph ^ 1);
+            mbar_arrive_expect_tx(&u_full[us], S::kUChunkBytes);
+            tma_bulk_g2s(smem + S::kOffU + us * S::kUChunkBytes,
+                         u_src + (size_t)(kb * S::kUChunksPerStage + h) * S::kUChunkBytes, S::kUChunkBytes,
+                         &u_full[us]);
+            if (++us == S::kUBufs) { us = 0; uph ^= 1; }
+          }
         }
       }
     }
@@ -133,6 +150,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, KN);
+      constexpr uint32_t idesc_neg = make_idesc(kFmtTF32, 128, KN, 1);  // D += (-A) * B
       const uint32_t v_base = smem_u32(smem + S::kOffV);
       const uint32_t u_base = smem_u32(smem + S::kOffU);
       uint32_t vs = 0, vph = 0, us = 0, uph = 0, aph = 0;
@@ -140,21 +158,51 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
         mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
         for (int kb = 0; kb < n_kb; ++kb) {
-          mbar_wait(&u_full[us], uph);
+          const uint32_t acc = kb > 0 ? 1u : 0u;
           mbar_wait(&v_full[vs], vph);
-          tc_fence_after();
           const uint32_t va = v_base + vs * S::kVBytes;
-          const uint32_t ua = u_base + us * S::kUBytes;
+          if constexpr (!FOLD) {
+            mbar_wait(&u_full[us], uph);
+            tc_fence_after();
+            const uint32_t ua = u_base + us * S::kUChunkBytes;
 #pragma unroll
-          for (int xi = 0; xi < 16; ++xi) {
-            const uint64_t a_desc = make_smem_desc(va + xi * S::kVPerXi, S::kVLbo, 128, kLayoutNone);
-            const uint64_t b_desc = make_smem_desc(ua + xi * S::kUPerXi, S::kULbo, 128, kLayoutNone);
-            umma_tf32_ss(tmem_base + xi * KN, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
+            for (int xi = 0; xi < 16; ++xi) {
+              const uint64_t a_desc = make_smem_desc(va + xi * S::kVPerXi, S::kVLbo, 128, kLayoutNone);
+              const uint64_t b_desc = make_smem_desc(ua + xi * S::kUPerPoint, S::kULbo, 128, kLayoutNone);
+              umma_tf32_ss(tmem_base + xi * KN, a_desc, b_desc, idesc, acc);
+            }
+            umma_commit(&u_empty[us]);
+            if (++us == S::kUBufs) { us = 0; uph ^= 1; }
+          } else {
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh) {
+              mbar_wait(&u_full[us], uph);
+              tc_fence_after();
+              const uint32_t ua = u_base + us * S::kUChunkBytes;
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const int j = jh * 2 + jj;
+                const uint32_t z0 = tmem_base + (j * 2 + 0) * KN;  // Z[0][j] = M0j + M1j + M2j
+                const uint32_t z1 = tmem_base + (j * 2 + 1) * KN;  // Z[1][j] = M1j - M2j - M3j
+                uint64_t a_desc[4], b_desc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  a_desc[i] = make_smem_desc(va + (4 * i + j) * S::kVPerXi, S::kVLbo, 128, kLayoutNone);
+                  b_desc[i] = make_smem_desc(ua + (i * 2 + jj) * S::kUPerPoint, S::kULbo, 128, kLayoutNone);
+                }
+                umma_tf32_ss(z0, a_desc[1], b_desc[1], idesc, acc);  // first writer of both accumulators
+                umma_tf32_ss(z1, a_desc[1], b_desc[1], idesc, acc);
+                umma_tf32_ss(z0, a_desc[0], b_desc[0], idesc, 1u);
+                umma_tf32_ss(z0, a_desc[2], b_desc[2], idesc, 1u);
+                umma_tf32_ss(z1, a_desc[2], b_desc[2], idesc_neg, 1u);
+                umma_tf32_ss(z1, a_desc[3], b_desc[3], idesc_neg, 1u);
+              }
+              umma_commit(&u_empty[us]);
+              if (++us == S::kUBufs) { us = 0; uph ^= 1; }
+            }
           }
           umma_commit(&v_empty[vs]);
-          umma_commit(&u_empty[us]);
           if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
-          if (++us == S::kUStages) { us = 0; uph ^= 1; }
         }
         umma_commit(acc_full);
         aph ^= 1;
@@ -215,38 +263,40 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
           d[2][dx] = make_float4(d2.x - d1.x, d2.y - d1.y, d2.z - d1.z, d2.w - d1.w);
           d[3][dx] = make_float4(d1.x - d3.x, d1.y - d3.y, d1.z - d3.z, d1.w - d3.w);
         }
+        // the raw stage is in registers now: hand it back to the producer before the row pass
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
+
         mbar_wait(&v_empty[vs], vph ^ 1);  // MMAs that read this V stage have completed
         const uint32_t vdst = v_base + vs * S::kVBytes + v_off;
         // row pass V = t B, round to TF32, store point (i,j) at xi = 4*i + j
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
-          st_shared_v4(vdst + (4 * i + 0) * S::kVPerXi, to_tf32_rn(a0.x - a2.x), to_tf32_rn(a0.y - a2.y),
-                       to_tf32_rn(a0.z - a2.z), to_tf32_rn(a0.w - a2.w));
-          st_shared_v4(vdst + (4 * i + 1) * S::kVPerXi, to_tf32_rn(a1.x + a2.x), to_tf32_rn(a1.y + a2.y),
-                       to_tf32_rn(a1.z + a2.z), to_tf32_rn(a1.w + a2.w));
-          st_shared_v4(vdst + (4 * i + 2) * S::kVPerXi, to_tf32_rn(a2.x - a1.x), to_tf32_rn(a2.y - a1.y),
-                       to_tf32_rn(a2.z - a1.z), to_tf32_rn(a2.w - a1.w));
-          st_shared_v4(vdst + (4 * i + 3) * S::kVPerXi, to_tf32_rn(a1.x - a3.x), to_tf32_rn(a1.y - a3.y),
-                       to_tf32_rn(a1.z - a3.z), to_tf32_rn(a1.w - a3.w));
+          st_shared_v4(vdst + (4 * i + 0) * S::kVPerXi, tf32_operand(a0.x - a2.x), tf32_operand(a0.y - a2.y),
+                       tf32_operand(a0.z - a2.z), tf32_operand(a0.w - a2.w));
+          st_shared_v4(vdst + (4 * i + 1) * S::kVPerXi, tf32_operand(a1.x + a2.x), tf32_operand(a1.y + a2.y),
+                       tf32_operand(a1.z + a2.z), tf32_operand(a1.w + a2.w));
+          st_shared_v4(vdst + (4 * i + 2) * S::kVPerXi, tf32_operand(a2.x - a1.x), tf32_operand(a2.y - a1.y),
+                       tf32_operand(a2.z - a1.z), tf32_operand(a2.w - a1.w));
+          st_shared_v4(vdst + (4 * i + 3) * S::kVPerXi, tf32_operand(a1.x - a3.x), tf32_operand(a1.y - a3.y),
+                       tf32_operand(a1.z - a3.z), tf32_operand(a1.w - a3.w));
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&v_full[vs]);
-          mbar_arrive(&raw_empty[rs]);
-        }
-        if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
+        if (lane == 0) mbar_arrive(&v_full[vs]);
         if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
       }
 
-      // ---- epilogue: Y = A^T M A, BN, ReLU, store
+      // ---- epilogue: (rest of) Y = A^T M A, BN, ReLU, store
       const int TE = t0 + erow;
       const bool evalid = TE < total_tiles;
       const int n = TE / 49, t = TE % 49, ty = t / 7, tx = t % 7;
       const int W = out_padded ? 16 : 14;
       const int o = out_padded ? 1 : 0;
       float* ybase = y + ((size_t)n * W * W + (size_t)(2 * ty + o) * W + (2 * tx + o)) * K + slice * KN;
+      const size_t rstride = (size_t)W * K;
 
       mbar_wait(acc_full, aph);
       aph ^= 1;
@@ -255,44 +305,60 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
 #pragma unroll 1
       for (int cc = 0; cc < kColsPerWarp; cc += 8) {
         const int c0 = half * kColsPerWarp + cc;
-        float m[16][8];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
+        float o00[8], o01[8], o10[8], o11[8];  // Y[a][b] before BN
+        if constexpr (!FOLD) {
+          float m[16][8];
 #pragma unroll
-        for (int xi = 0; xi < 16; ++xi) tmem_ld_x8(taddr + xi * KN, m[xi]);
-        tmem_ld_wait();
+          for (int xi = 0; xi < 16; ++xi) tmem_ld_x8(taddr + xi * KN, m[xi]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float s0[4], s1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              s0[j] = m[0 + j][e] + m[4 + j][e] + m[8 + j][e];
+              s1[j] = m[4 + j][e] - m[8 + j][e] - m[12 + j][e];
+            }
+            o00[e] = s0[0] + s0[1] + s0[2];
+            o01[e] = s0[1] - s0[2] - s0[3];
+            o10[e] = s1[0] + s1[1] + s1[2];
+            o11[e] = s1[1] - s1[2] - s1[3];
+          }
+        } else {
+          float z[8][8];  // z[j*2 + a][e]
+#pragma unroll
+          for (int p = 0; p < 8; ++p) tmem_ld_x8(taddr + p * KN, z[p]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            o00[e] = z[0][e] + z[2][e] + z[4][e];
+            o01[e] = z[2][e] - z[4][e] - z[6][e];
+            o10[e] = z[1][e] + z[3][e] + z[5][e];
+            o11[e] = z[3][e] - z[5][e] - z[7][e];
+          }
+        }
         const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + slice * KN + c0));
         const float4 sc1 = __ldg(reinterpret_cast<const float4*>(scale + slice * KN + c0 + 4));
         const float4 sh0 = __ldg(reinterpret_cast<const float4*>(shift + slice * KN + c0));
         const float4 sh1 = __ldg(reinterpret_cast<const float4*>(shift + slice * KN + c0 + 4));
         const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
         const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-        float o00[8], o01[8], o10[8], o11[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float s0[4], s1[4];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            s0[jj] = m[0 + jj][j] + m[4 + jj][j] + m[8 + jj][j];
-            s1[jj] = m[4 + jj][j] - m[8 + jj][j] - m[12 + jj][j];
-          }
-          float y00 = fmaf(sc[j], s0[0] + s0[1] + s0[2], sh[j]);
-          float y01 = fmaf(sc[j], s0[1] - s0[2] - s0[3], sh[j]);
-          float y10 = fmaf(sc[j], s1[0] + s1[1] + s1[2], sh[j]);
-          float y11 = fmaf(sc[j], s1[1] - s1[2] - s1[3], sh[j]);
+        for (int e = 0; e < 8; ++e) {
+          o00[e] = fmaf(sc[e], o00[e], sh[e]);
+          o01[e] = fmaf(sc[e], o01[e], sh[e]);
+          o10[e] = fmaf(sc[e], o10[e], sh[e]);
+          o11[e] = fmaf(sc[e], o11[e], sh[e]);
           if (relu) {
-            y00 = fmaxf(y00, 0.f);
-            y01 = fmaxf(y01, 0.f);
-            y10 = fmaxf(y10, 0.f);
-            y11 = fmaxf(y11, 0.f);
+            o00[e] = fmaxf(o00[e], 0.f);
+            o01[e] = fmaxf(o01[e], 0.f);
+            o10[e] = fmaxf(o10[e], 0.f);
+            o11[e] = fmaxf(o11[e], 0.f);
           }
-          o00[j] = y00;
-          o01[j] = y01;
-          o10[j] = y10;
-          o11[j] = y11;
         }
         if (evalid) {
           float* p = ybase + c0;
-          const size_t rstride = (size_t)W * K;
           *reinterpret_cast<float4*>(p) = make_float4(o00[0], o00[1], o00[2], o00[3]);
           *reinterpret_cast<float4*>(p + 4) = make_float4(o00[4], o00[5], o00[6], o00[7]);
           *reinterpret_cast<float4*>(p + K) = make_float4(o01[0], o01[1], o01[2], o01[3]);
@@ -303,24 +369,24 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
           *reinterpret_cast<float4*>(p + rstride + K + 4) = make_float4(o11[4], o11[5], o11[6], o11[7]);
           if (out_padded) {
             // zero border of the reference's 16x16 frame: edge tiles also own their share of the border
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
             const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
             if (dyb != 0) {
-              *reinterpret_cast<float4*>(p + dyb) = z;
-              *reinterpret_cast<float4*>(p + dyb + 4) = z;
-              *reinterpret_cast<float4*>(p + dyb + K) = z;
-              *reinterpret_cast<float4*>(p + dyb + K + 4) = z;
+              *reinterpret_cast<float4*>(p + dyb) = z4;
+              *reinterpret_cast<float4*>(p + dyb + 4) = z4;
+              *reinterpret_cast<float4*>(p + dyb + K) = z4;
+              *reinterpret_cast<float4*>(p + dyb + K + 4) = z4;
             }
             if (dxb != 0) {
-              *reinterpret_cast<float4*>(p + dxb) = z;
-              *reinterpret_cast<float4*>(p + dxb + 4) = z;
-              *reinterpret_cast<float4*>(p + dxb + rstride) = z;
-              *reinterpret_cast<float4*>(p + dxb + rstride + 4) = z;
+              *reinterpret_cast<float4*>(p + dxb) = z4;
+              *reinterpret_cast<float4*>(p + dxb + 4) = z4;
+              *reinterpret_cast<float4*>(p + dxb + rstride) = z4;
+              *reinterpret_cast<float4*>(p + dxb + rstride + 4) = z4;
             }
             if (dyb != 0 && dxb != 0) {
-              *reinterpret_cast<float4*>(p + dyb + dxb) = z;
-              *reinterpret_cast<float4*>(p + dyb + dxb + 4) = z;
+              *reinterpret_cast<float4*>(p + dyb + dxb) = z4;
+              *reinterpret_cast<float4*>(p + dyb + dxb + 4) = z4;
             }
           }
         }
@@ -338,10 +404,12 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Once-per-layer filter transform U = G g G^T (F(2x2,3x3)), RN-rounded to TF32, written as the exact shared-memory
-// image of a pipeline stage: [K/KN slice][C/8 k-block][16 points][2 k-chunks][KN couts][4 channels].
+// image of the pipeline's bulk copies:
+//   plain: [K/32 slice][C/8 k-block][16 points (i,j)]        [2 k-chunks][32 couts][4 channels]
+//   fold : [K/64 slice][C/8 k-block][2 j-halves][4 i][2 jj]  [2 k-chunks][64 couts][4 channels]   (j = 2*jh + jj)
 // Replaces the offline weight_generator loop (/root/reference/data_generator.py:63-78; that one is F(4x4), 36 points).
 __global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, float* __restrict__ u_img, int C, int K,
-                                             int KN) {
+                                             int KN, int fold) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * K) return;
   const int ch = idx % C;
@@ -363,7 +431,8 @@ __global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, f
   }
   const int slice = k / KN, kn = k % KN;
   const int kb = ch / 8, chunk = (ch % 8) / 4, e = ch % 4;
-  const size_t stage = ((size_t)slice * (C / 8) + kb) * (size_t)(16 * 2 * KN * 4);
+  const size_t point_floats = (size_t)2 * KN * 4;
+  const size_t stage = ((size_t)slice * (C / 8) + kb) * 16 * point_floats;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float u[4];
@@ -373,8 +442,8 @@ __global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, f
     u[3] = tt[i][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int xi = 4 * i + j;
-      u_img[stage + ((size_t)(xi * 2 + chunk) * KN + kn) * 4 + e] = to_tf32_rn(u[j]);
+      const int p = fold ? ((j >> 1) * 8 + i * 2 + (j & 1)) : (4 * i + j);
+      u_img[stage + p * point_floats + ((size_t)chunk * KN + kn) * 4 + e] = to_tf32_rn(u[j]);
     }
   }
 }
@@ -396,35 +465,35 @@ int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
 
-template <int KN>
+template <bool FOLD>
 static int launch_wino(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                        int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
-  using S = WinoSmem<KN>;
+  using S = WinoCfg<FOLD>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<KN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
     configured = true;
   }
-  const int n_items = ((n_img * 49 + 127) / 128) * (K / KN);
+  const int n_items = ((n_img * 49 + 127) / 128) * (K / S::KN);
   int grid = n_items < max_ctas ? n_items : max_ctas;
   if (grid < 1) grid = 1;
-  wino3x3_bn_relu_kernel<KN><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K, relu,
-                                                                    out_padded);
+  wino3x3_bn_relu_kernel<FOLD><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K, relu,
+                                                                      out_padded);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                 int n_img, int C, int K, int KN, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
-  if (KN == 32) return launch_wino<32>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
-  if (KN == 16) return launch_wino<16>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+  if (KN == 64) return launch_wino<true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+  if (KN == 32) return launch_wino<false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
   return WG_ERR_ARG;
 }
 
 int filter_transform_launch(const float* w_kcrs, float* u_img, int C, int K, int KN, cudaStream_t stream) {
   const int n = C * K;
-  filter_transform_f2x2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, KN);
+  filter_transform_f2x2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, KN, KN == 64 ? 1 : 0);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 

@@ -267,10 +267,20 @@ int main(int argc, char** argv) {
   auto bad = [&](double rel, double tol) {
     if (!(rel <= tol)) ++fails;
   };
-  bad(check3x3(1, 128, 128, 1, 0, {0}), 1e-3);
-  bad(check3x3(1, 128, 128, 1, 1, {0}), 1e-3);
-  bad(check3x3(3, 64, 64, 0, 0, {0, 1, 2}), 1e-3);
-  bad(check3x3(7, 32, 32, 1, 1, {0, 3, 6}), 1e-3);
+  for (int kn : {64, 32}) {
+    wg_set_wino_kn(kn);
+    printf("-- 3x3 variant KN=%d\n", kn);
+    bad(check3x3(1, 128, 128, 1, 0, {0}), 1e-3);
+    bad(check3x3(1, 128, 128, 1, 1, {0}), 1e-3);
+    bad(check3x3(3, 64, 64, 0, 0, {0, 1, 2}), 1e-3);
+    bad(check3x3(7, 32, 32, 1, 1, {0, 3, 6}), 1e-3);
+    if (!quick) {
+      bad(check3x3(256, 128, 128, 1, 0, {0, 131, 255}), 1e-3);
+      time_layer(0, 256, 128, 128, 1);
+      time_layer(0, 256, 256, 256, 1);
+    }
+  }
+  wg_set_wino_kn(64);
   bad(check1x1(1, 512, 128, 1, {0}), 1e-3);
   bad(check1x1(1, 128, 512, 0, {0}), 1e-3);
   bad(check1x1(3, 64, 256, 0, {0, 2}), 1e-3);
