@@ -7,8 +7,9 @@
 // Persistent, warp-specialised: warp 0 = TMA producer (A tile through a 2-D tensor map with 128-byte swizzle,
 // B tile as one bulk copy of a pre-swizzled image written once per layer by weight_pack_kernel), warp 1 = single
 // thread issuing tcgen05.mma kind::tf32 (M=128, N=BN, K=8, four per 32-channel stage) into one of two TMEM
-// accumulator buffers, warps 2..5 = epilogue (tcgen05.ld -> scale/shift/ReLU -> 128-bit stores) overlapping the
-// next tile's MMAs.
+// accumulator buffers, warps 2..5 = epilogue overlapping the next tile's MMAs: tcgen05.ld -> scale/shift/ReLU ->
+// 128-byte-swizzled shared staging (conflict-free 128-bit stores) -> per-warp TMA tensor stores of 32x32 sub-tiles
+// (full 128-byte lines to L2; rows beyond M are clipped by the tensor map).
 #include "ptx.cuh"
 #include "wg_internal.h"
 
@@ -22,20 +23,23 @@ struct OneSmem {
   static constexpr int kStages = BN == 256 ? 4 : 6;
   static constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 128 B
   static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kStageOutBytes = 32 * 128;  // one warp's 32 rows x 32 fp32 columns
   static constexpr uint32_t kOffA = 0;
   static constexpr uint32_t kOffB = kOffA + kStages * kABytes;
-  static constexpr uint32_t kOffBar = kOffB + kStages * kBBytes;
+  static constexpr uint32_t kOffOut = kOffB + kStages * kBBytes;  // [4 warps][2 buffers]
+  static constexpr uint32_t kOffBar = kOffOut + 4 * 2 * kStageOutBytes;
   static constexpr uint32_t kNumBars = 2 * kStages + 4;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;  // + slack for manual 1024-B alignment
+  static_assert(kOffOut % 1024 == 0, "swizzled staging must be 1024-byte aligned");
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kOneThreads, 1)
-conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ w_img,
-                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
-                      long long m_rows, int Cin, int Cout, int relu) {
+conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
+                      const float* __restrict__ w_img, const float* __restrict__ scale,
+                      const float* __restrict__ shift, long long m_rows, int Cin, int Cout, int relu) {
   using S = OneSmem<BN>;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers
   extern __shared__ uint8_t smem_raw[];
@@ -54,6 +58,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* _
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_y);
     for (int i = 0; i < S::kStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -120,49 +125,58 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* _
     }
   } else {
     const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
-    const int row = quad * 32 + lane;
-    uint32_t it = 0;
+    uint8_t* stage_out = smem + S::kOffOut + quad * 2 * S::kStageOutBytes;
+    const uint32_t stage_u32 = smem_u32(stage_out);
+    uint32_t it = 0, chunk = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int nt = item % n_ntiles;
       const int mt = item / n_ntiles;
       const uint32_t buf = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const long long m = (long long)mt * 128 + row;
-      const bool valid = m < m_rows;
-      float* yrow = y + (size_t)m * Cout + nt * BN;
       const float* sc = scale + nt * BN;
       const float* sh = shift + nt * BN;
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 32, ++chunk) {
         float v[32];
         tmem_ld_x16(taddr + c0, v);
         tmem_ld_x16(taddr + c0 + 16, v + 16);
+        // the staging buffer written two chunks ago must have been read by its TMA store
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
         tmem_ld_wait();
+        const uint32_t dst = stage_u32 + (chunk & 1) * S::kStageOutBytes + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c0 + j));
-          const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + c0 + j));
+        for (int j = 0; j < 8; ++j) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c0 + 4 * j));
+          const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + c0 + 4 * j));
           float4 o;
-          o.x = fmaf(s4.x, v[j + 0], h4.x);
-          o.y = fmaf(s4.y, v[j + 1], h4.y);
-          o.z = fmaf(s4.z, v[j + 2], h4.z);
-          o.w = fmaf(s4.w, v[j + 3], h4.w);
+          o.x = fmaf(s4.x, v[4 * j + 0], h4.x);
+          o.y = fmaf(s4.y, v[4 * j + 1], h4.y);
+          o.z = fmaf(s4.z, v[4 * j + 2], h4.z);
+          o.w = fmaf(s4.w, v[4 * j + 3], h4.w);
           if (relu) {
             o.x = fmaxf(o.x, 0.f);
             o.y = fmaxf(o.y, 0.f);
             o.z = fmaxf(o.z, 0.f);
             o.w = fmaxf(o.w, 0.f);
           }
-          if (valid) *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+          st_shared_v4(dst + ((j ^ (lane & 7)) << 4), o.x, o.y, o.z, o.w);  // 128-byte swizzle
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_tensor_2d_s2g(&tmap_y, stage_out + (chunk & 1) * S::kStageOutBytes, nt * BN + c0, mt * 128 + quad * 32);
+          tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -185,22 +199,31 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, float* __restric
   w_img[off] = to_tf32_rn(w[idx]);
 }
 
-int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin) {
+static int encode_2d(CUtensorMap* tmap, const float* base, int inner, long long rows, int box_inner, int box_rows) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return WG_ERR_DRIVER;
-  cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)m_rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Cin * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, 128};
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
 
+int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin) {
+  return encode_2d(tmap, x, Cin, m_rows, kBK, 128);
+}
+
+int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout) {
+  return encode_2d(tmap, y, Cout, m_rows, 32, 32);
+}
+
 template <int BN>
-static int launch_one(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
-                      long long m_rows, int Cin, int Cout, int relu, int max_ctas, cudaStream_t stream) {
+static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
+                      const float* shift, long long m_rows, int Cin, int Cout, int relu, int max_ctas,
+                      cudaStream_t stream) {
   using S = OneSmem<BN>;
   static bool configured = false;
   if (!configured) {
@@ -212,15 +235,18 @@ static int launch_one(const CUtensorMap& tmap, const float* w_img, const float* 
   const long long n_items = ((m_rows + 127) / 128) * (Cout / BN);
   int grid = n_items < max_ctas ? (int)n_items : max_ctas;
   if (grid < 1) grid = 1;
-  conv1x1_bn_act_kernel<BN><<<grid, kOneThreads, S::kTotal, stream>>>(tmap, w_img, scale, shift, y, m_rows, Cin, Cout,
-                                                                      relu);
+  conv1x1_bn_act_kernel<BN><<<grid, kOneThreads, S::kTotal, stream>>>(tmap, tmap_y, w_img, scale, shift, m_rows, Cin,
+                                                                      Cout, relu);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-int one_launch(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
-               long long m_rows, int Cin, int Cout, int BN, int relu, int max_ctas, cudaStream_t stream) {
-  if (BN == 128) return launch_one<128>(tmap, w_img, scale, shift, y, m_rows, Cin, Cout, relu, max_ctas, stream);
-  if (BN == 256) return launch_one<256>(tmap, w_img, scale, shift, y, m_rows, Cin, Cout, relu, max_ctas, stream);
+int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
+               const float* shift, long long m_rows, int Cin, int Cout, int BN, int relu, int max_ctas,
+               cudaStream_t stream) {
+  if (BN == 128)
+    return launch_one<128>(tmap, tmap_y, w_img, scale, shift, m_rows, Cin, Cout, relu, max_ctas, stream);
+  if (BN == 256)
+    return launch_one<256>(tmap, tmap_y, w_img, scale, shift, m_rows, Cin, Cout, relu, max_ctas, stream);
   return WG_ERR_ARG;
 }
 

@@ -55,6 +55,9 @@ struct wg_layer {
   const float* tmap_x;
   int tmap_n;
   CUtensorMap tmap;
+  const float* tmap_y_ptr;  // 1x1 only: output tensor map for the TMA-store epilogue
+  int tmap_y_n;
+  CUtensorMap tmap_out;
   // staging for wg_run_host
   float* d_x;
   float* d_y;
@@ -165,14 +168,20 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
     L->tmap_x = x;
     L->tmap_n = N;
   }
+  if (L->kind == 1 && (L->tmap_y_ptr != y || L->tmap_y_n != N)) {
+    int rc = one_make_tmap_out(&L->tmap_out, y, (long long)N * 196, L->cout);
+    if (rc != WG_OK) return rc;
+    L->tmap_y_ptr = y;
+    L->tmap_y_n = N;
+  }
   const int max_ctas = g_max_ctas > 0 ? g_max_ctas : L->num_sms;
   int rc;
   if (L->kind == 0)
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n, L->relu,
                      out_padded ? 1 : 0, max_ctas, stream);
   else
-    rc = one_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, (long long)N * 196, L->cin, L->cout, L->tile_n,
-                    L->relu, max_ctas, stream);
+    rc = one_launch(L->tmap, L->tmap_out, L->d_filter, L->d_scale, L->d_shift, (long long)N * 196, L->cin, L->cout,
+                    L->tile_n, L->relu, max_ctas, stream);
   g_launches++;
   if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
   return rc;
@@ -199,6 +208,7 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
     if (L->d_y) cudaFree(L->d_y);
     L->d_y = nullptr;
     L->d_y_bytes = 0;
+    L->tmap_y_ptr = nullptr;
     WG_CUDA(cudaMalloc(&L->d_y, yb));
     L->d_y_bytes = yb;
   }

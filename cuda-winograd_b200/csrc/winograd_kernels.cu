@@ -24,6 +24,7 @@
 #include "wg_internal.h"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace wg {
 
@@ -68,7 +69,7 @@ template <bool FOLD>
 __global__ void __launch_bounds__(kThreads, 1)
 wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                        const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
-                       int n_img, int C, int K, int relu, int out_padded) {
+                       int n_img, int C, int K, int relu, int out_padded, int ablate) {
   using S = WinoCfg<FOLD>;
   constexpr int KN = S::KN;
   constexpr uint32_t kTmemCols = 512;
@@ -161,7 +162,13 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
           const uint32_t acc = kb > 0 ? 1u : 0u;
           mbar_wait(&v_full[vs], vph);
           const uint32_t va = v_base + vs * S::kVBytes;
-          if constexpr (!FOLD) {
+          if (ablate & 8) {
+            for (int h = 0; h < S::kUChunksPerStage; ++h) {
+              mbar_wait(&u_full[us], uph);
+              umma_commit(&u_empty[us]);
+              if (++us == S::kUBufs) { us = 0; uph ^= 1; }
+            }
+          } else if constexpr (!FOLD) {
             mbar_wait(&u_full[us], uph);
             tc_fence_after();
             const uint32_t ua = u_base + us * S::kUChunkBytes;
@@ -241,7 +248,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
       for (int kb = 0; kb < n_kb; ++kb) {
         float4 d[4][4];
         mbar_wait(&raw_full[rs], rph);
-        if (tvalid) {
+        if (tvalid && !(ablate & 1)) {
           const uint32_t a = raw_base + rs * kRawBytes + raw_off;
 #pragma unroll
           for (int dy = 0; dy < 4; ++dy)
@@ -271,6 +278,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
         mbar_wait(&v_empty[vs], vph ^ 1);  // MMAs that read this V stage have completed
         const uint32_t vdst = v_base + vs * S::kVBytes + v_off;
         // row pass V = t B, round to TF32, store point (i,j) at xi = 4*i + j
+        if (!(ablate & 2))
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
@@ -283,7 +291,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
           st_shared_v4(vdst + (4 * i + 3) * S::kVPerXi, tf32_operand(a1.x - a3.x), tf32_operand(a1.y - a3.y),
                        tf32_operand(a1.z - a3.z), tf32_operand(a1.w - a3.w));
         }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        if (!(ablate & 4)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&v_full[vs]);
         if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
@@ -295,8 +303,9 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
       const int n = TE / 49, t = TE % 49, ty = t / 7, tx = t % 7;
       const int W = out_padded ? 16 : 14;
       const int o = out_padded ? 1 : 0;
-      float* ybase = y + ((size_t)n * W * W + (size_t)(2 * ty + o) * W + (2 * tx + o)) * K + slice * KN;
+      const int pix0 = evalid ? ((n * W + 2 * ty + o) * W + 2 * tx + o) : -1;  // first output pixel of this tile
       const size_t rstride = (size_t)W * K;
+      const uint32_t stg = v_base + warp * (32 * 512);  // this warp's 16 KB staging area inside the V buffers
 
       mbar_wait(acc_full, aph);
       aph ^= 1;
@@ -357,40 +366,69 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
             o11[e] = fmaxf(o11[e], 0.f);
           }
         }
-        if (evalid) {
-          float* p = ybase + c0;
-          *reinterpret_cast<float4*>(p) = make_float4(o00[0], o00[1], o00[2], o00[3]);
-          *reinterpret_cast<float4*>(p + 4) = make_float4(o00[4], o00[5], o00[6], o00[7]);
-          *reinterpret_cast<float4*>(p + K) = make_float4(o01[0], o01[1], o01[2], o01[3]);
-          *reinterpret_cast<float4*>(p + K + 4) = make_float4(o01[4], o01[5], o01[6], o01[7]);
-          *reinterpret_cast<float4*>(p + rstride) = make_float4(o10[0], o10[1], o10[2], o10[3]);
-          *reinterpret_cast<float4*>(p + rstride + 4) = make_float4(o10[4], o10[5], o10[6], o10[7]);
-          *reinterpret_cast<float4*>(p + rstride + K) = make_float4(o11[0], o11[1], o11[2], o11[3]);
-          *reinterpret_cast<float4*>(p + rstride + K + 4) = make_float4(o11[4], o11[5], o11[6], o11[7]);
-          if (out_padded) {
-            // zero border of the reference's 16x16 frame: edge tiles also own their share of the border
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
-            const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
+        // stage this 8-cout group in the (now idle) V buffers: [tile][pixel][128 B], 16-byte chunks XOR-swizzled by
+        // the tile index so that both the per-tile writes here and the per-pixel reads below are conflict free
+        {
+          const uint32_t sdst = stg + lane * 512;
+          const uint32_t sw = lane & 7;
+          const uint32_t k0 = (uint32_t)cc >> 2;
+          st_shared_v4(sdst + 0 * 128 + (((k0 + 0) ^ sw) << 4), o00[0], o00[1], o00[2], o00[3]);
+          st_shared_v4(sdst + 0 * 128 + (((k0 + 1) ^ sw) << 4), o00[4], o00[5], o00[6], o00[7]);
+          st_shared_v4(sdst + 1 * 128 + (((k0 + 0) ^ sw) << 4), o01[0], o01[1], o01[2], o01[3]);
+          st_shared_v4(sdst + 1 * 128 + (((k0 + 1) ^ sw) << 4), o01[4], o01[5], o01[6], o01[7]);
+          st_shared_v4(sdst + 2 * 128 + (((k0 + 0) ^ sw) << 4), o10[0], o10[1], o10[2], o10[3]);
+          st_shared_v4(sdst + 2 * 128 + (((k0 + 1) ^ sw) << 4), o10[4], o10[5], o10[6], o10[7]);
+          st_shared_v4(sdst + 3 * 128 + (((k0 + 0) ^ sw) << 4), o11[0], o11[1], o11[2], o11[3]);
+          st_shared_v4(sdst + 3 * 128 + (((k0 + 1) ^ sw) << 4), o11[4], o11[5], o11[6], o11[7]);
+        }
+      }
+      __syncwarp();
+      // write-out: kChunks lanes cover one output pixel's kColsPerWarp couts = one contiguous 64/128-byte run
+      if (!(ablate & 32)) {
+        constexpr int kChunks = kColsPerWarp / 4;      // 16-byte chunks per pixel owned by this warp (4 or 8)
+        constexpr int kTilesPerInstr = 32 / kChunks;   // 8 or 4
+        const int j = lane % kChunks;
+        const int tsub = lane / kChunks;
+        // with 4 chunks a quarter warp holds two tiles: pick tiles 4 apart so their swizzled chunks do not collide
+        const int tperm = kChunks == 8 ? tsub : ((tsub >> 1) | ((tsub & 1) << 2));
+        float* gcol = y + slice * KN + half * kColsPerWarp + j * 4;
+#pragma unroll
+        for (int it = 0; it < 32 / kTilesPerInstr; ++it) {
+          const int tl = it * kTilesPerInstr + tperm;
+          const int pix = __shfl_sync(0xffffffffu, pix0, tl);
+          const uint32_t src = stg + tl * 512 + ((j ^ (tl & 7)) << 4);
+          if (pix >= 0) {
+            float* g = gcol + (size_t)pix * K;
+            const float4 v0 = ld_shared_v4(src), v1 = ld_shared_v4(src + 128);
+            const float4 v2 = ld_shared_v4(src + 256), v3 = ld_shared_v4(src + 384);
+            *reinterpret_cast<float4*>(g) = v0;
+            *reinterpret_cast<float4*>(g + K) = v1;
+            *reinterpret_cast<float4*>(g + rstride) = v2;
+            *reinterpret_cast<float4*>(g + rstride + K) = v3;
+          }
+        }
+        if (out_padded && evalid && (ty == 0 || ty == 6 || tx == 0 || tx == 6)) {
+          // zero border of the reference's 16x16 frame: edge tiles also own their share of the border
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float* p = y + (size_t)pix0 * K + slice * KN + half * kColsPerWarp;
+          const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
+          const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
+#pragma unroll 1
+          for (int e = 0; e < kColsPerWarp; e += 4) {
             if (dyb != 0) {
-              *reinterpret_cast<float4*>(p + dyb) = z4;
-              *reinterpret_cast<float4*>(p + dyb + 4) = z4;
-              *reinterpret_cast<float4*>(p + dyb + K) = z4;
-              *reinterpret_cast<float4*>(p + dyb + K + 4) = z4;
+              *reinterpret_cast<float4*>(p + dyb + e) = z4;
+              *reinterpret_cast<float4*>(p + dyb + K + e) = z4;
             }
             if (dxb != 0) {
-              *reinterpret_cast<float4*>(p + dxb) = z4;
-              *reinterpret_cast<float4*>(p + dxb + 4) = z4;
-              *reinterpret_cast<float4*>(p + dxb + rstride) = z4;
-              *reinterpret_cast<float4*>(p + dxb + rstride + 4) = z4;
+              *reinterpret_cast<float4*>(p + dxb + e) = z4;
+              *reinterpret_cast<float4*>(p + dxb + rstride + e) = z4;
             }
-            if (dyb != 0 && dxb != 0) {
-              *reinterpret_cast<float4*>(p + dyb + dxb) = z4;
-              *reinterpret_cast<float4*>(p + dyb + dxb + 4) = z4;
-            }
+            if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(p + dyb + dxb + e) = z4;
           }
         }
       }
+      // every worker warp must be done with its staging area before any of them refills the V buffers
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
@@ -479,8 +517,13 @@ static int launch_wino(const CUtensorMap& tmap, const float* u_img, const float*
   const int n_items = ((n_img * 49 + 127) / 128) * (K / S::KN);
   int grid = n_items < max_ctas ? n_items : max_ctas;
   if (grid < 1) grid = 1;
+  static int ablate = -1;  // debug only: WG_DEBUG_ABLATE=<bitmask> switches pipeline pieces off for timing experiments
+  if (ablate < 0) {
+    const char* e = getenv("WG_DEBUG_ABLATE");
+    ablate = e ? atoi(e) : 0;
+  }
   wino3x3_bn_relu_kernel<FOLD><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K, relu,
-                                                                      out_padded);
+                                                                      out_padded, ablate);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 

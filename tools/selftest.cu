@@ -261,6 +261,11 @@ int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   printf("sm_100 devices: %d\n", wg_device_count());
   if (wg_device_count() == 0) return 1;
+  if (argc > 1 && !strcmp(argv[1], "time3x3")) {  // timing only (used with WG_DEBUG_ABLATE experiments)
+    time_layer(0, 256, 128, 128, 1);
+    time_layer(0, 256, 256, 256, 1);
+    return 0;
+  }
   int probe = run_probe();
   printf("probe result mask: %d\n", probe);
   int fails = 0;
