@@ -10,6 +10,8 @@
 // accumulator buffers, warps 2..5 = epilogue overlapping the next tile's MMAs: tcgen05.ld -> scale/shift/ReLU ->
 // 128-byte-swizzled shared staging (conflict-free 128-bit stores) -> per-warp TMA tensor stores of 32x32 sub-tiles
 // (full 128-byte lines to L2; rows beyond M are clipped by the tensor map).
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "wg_internal.h"
 
@@ -35,7 +37,10 @@ struct OneSmem {
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN>
+// CL = thread-block cluster size: the CL CTAs of a cluster work on CL consecutive M-tiles of the same N-tile and share
+// the weight tile -- each loads 1/CL of it and multicasts it to all (L2->SM traffic for B divided by CL; that feed,
+// ~10 TB/s on B200, is what capped the non-clustered kernel on the Cin=1024 shape).
+template <int BN, int CL>
 __global__ void __launch_bounds__(kOneThreads, 1)
 conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                       const float* __restrict__ w_img, const float* __restrict__ scale,
@@ -56,12 +61,14 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
 
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_y);
     for (int i = 0; i < S::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CL);  // every CTA of the cluster must have consumed a stage before it is refilled
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -71,27 +78,35 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_kb = Cin / kBK;
   const int n_ntiles = Cout / BN;
   const int n_mtiles = (int)((m_rows + 127) / 128);
-  const int n_items = n_mtiles * n_ntiles;
+  const int n_items = ((n_mtiles + CL - 1) / CL) * n_ntiles;  // an item = CL consecutive M-tiles x one N-tile
+  const int first_item = blockIdx.x / CL;
+  const int item_stride = gridDim.x / CL;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = first_item; item < n_items; item += item_stride) {
         const int nt = item % n_ntiles;
-        const int mt = item / n_ntiles;
+        const int mt = (item / n_ntiles) * CL + crank;
         const uint8_t* b_src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)nt * n_kb * S::kBBytes;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&full[st], S::kABytes + S::kBBytes);
           tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, kb * kBK, mt * 128, &full[st]);
-          tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * S::kBBytes, S::kBBytes, &full[st]);
+          if constexpr (CL == 1) {
+            tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * S::kBBytes, S::kBBytes, &full[st]);
+          } else {
+            constexpr uint32_t part = S::kBBytes / CL;  // rows [crank*BN/CL, (crank+1)*BN/CL) of the swizzled image
+            tma_bulk_g2s_mcast(smem + S::kOffB + st * S::kBBytes + crank * part,
+                               b_src + (size_t)kb * S::kBBytes + crank * part, part, &full[st], kClusterMask);
+          }
           if (++st == S::kStages) { st = 0; ph ^= 1; }
         }
       }
@@ -103,7 +118,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t b_base = smem_u32(smem + S::kOffB);
       uint32_t st = 0, ph = 0;
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int item = first_item; item < n_items; item += item_stride, ++it) {
         const uint32_t buf = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&acc_empty[buf], aph ^ 1);
@@ -117,7 +132,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint64_t b_desc = make_smem_desc(b_base + st * S::kBBytes + k * 32, 0, 1024, kLayoutSW128);
             umma_tf32_ss(tmem_base + buf * BN, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[st]);
+          if constexpr (CL == 1) umma_commit(&empty[st]); else umma_commit_mcast(&empty[st], kClusterMask);
           if (++st == S::kStages) { st = 0; ph ^= 1; }
         }
         umma_commit(&acc_full[buf]);
@@ -128,9 +143,9 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint8_t* stage_out = smem + S::kOffOut + quad * 2 * S::kStageOutBytes;
     const uint32_t stage_u32 = smem_u32(stage_out);
     uint32_t it = 0, chunk = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item = first_item; item < n_items; item += item_stride, ++it) {
       const int nt = item % n_ntiles;
-      const int mt = item / n_ntiles;
+      const int mt = (item / n_ntiles) * CL + crank;
       const uint32_t buf = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const float* sc = scale + nt * BN;
@@ -167,7 +182,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && (long long)mt * 128 + quad * 32 < m_rows) {
           tma_tensor_2d_s2g(&tmap_y, stage_out + (chunk & 1) * S::kStageOutBytes, nt * BN + c0, mt * 128 + quad * 32);
           tma_store_commit();
         }
@@ -180,7 +195,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may leave while peers still multicast to it
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
@@ -207,7 +222,7 @@ static int encode_2d(CUtensorMap* tmap, const float* base, int inner, long long 
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, wg::l2_promotion(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
@@ -220,33 +235,66 @@ int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int C
   return encode_2d(tmap, y, Cout, m_rows, 32, 32);
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
                       const float* shift, long long m_rows, int Cin, int Cout, int relu, int max_ctas,
                       cudaStream_t stream) {
   using S = OneSmem<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
     configured = true;
   }
-  const long long n_items = ((m_rows + 127) / 128) * (Cout / BN);
-  int grid = n_items < max_ctas ? (int)n_items : max_ctas;
-  if (grid < 1) grid = 1;
-  conv1x1_bn_act_kernel<BN><<<grid, kOneThreads, S::kTotal, stream>>>(tmap, tmap_y, w_img, scale, shift, m_rows, Cin,
-                                                                      Cout, relu);
-  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+  const long long n_mtiles = (m_rows + 127) / 128;
+  const long long n_items = ((n_mtiles + CL - 1) / CL) * (Cout / BN);
+  long long n_clusters = max_ctas / CL;
+  if (n_clusters > n_items) n_clusters = n_items;
+  if (n_clusters < 1) n_clusters = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_clusters * CL));
+  cfg.blockDim = dim3(kOneThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL>, tmap, tmap_y, w_img, scale, shift, m_rows,
+                                     Cin, Cout, relu);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
                const float* shift, long long m_rows, int Cin, int Cout, int BN, int relu, int max_ctas,
                cudaStream_t stream) {
-  if (BN == 128)
-    return launch_one<128>(tmap, tmap_y, w_img, scale, shift, m_rows, Cin, Cout, relu, max_ctas, stream);
-  if (BN == 256)
-    return launch_one<256>(tmap, tmap_y, w_img, scale, shift, m_rows, Cin, Cout, relu, max_ctas, stream);
+  // WG_ONE_CLUSTER=1|2|4 selects the cluster size. Default 1: measured on B200 (profiles/README.md) the multicast
+  // variants are no faster (2) or slower (4) -- the limiter is per-SM ingest / shared-memory bandwidth, which
+  // multicast does not reduce, not L2 output bandwidth.
+  static int cl = -1;
+  if (cl < 0) {
+    const char* e = getenv("WG_ONE_CLUSTER");
+    cl = e ? atoi(e) : 1;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+  }
+  const int use = (m_rows <= 128) ? 1 : cl;  // a single M-tile has nobody to share the weight tile with
+#define WG_ONE(BN_, CL_) \
+  return launch_one<BN_, CL_>(tmap, tmap_y, w_img, scale, shift, m_rows, Cin, Cout, relu, max_ctas, stream)
+  if (BN == 128) {
+    if (use == 1) WG_ONE(128, 1);
+    if (use == 2) WG_ONE(128, 2);
+    WG_ONE(128, 4);
+  }
+  if (BN == 256) {
+    if (use == 1) WG_ONE(256, 1);
+    if (use == 2) WG_ONE(256, 2);
+    WG_ONE(256, 4);
+  }
+#undef WG_ONE
   return WG_ERR_ARG;
 }
 

@@ -41,6 +41,20 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+CUtensorMapL2promotion l2_promotion() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WG_L2_PROMO");
+    v = e ? atoi(e) : 128;
+  }
+  switch (v) {
+    case 0: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    case 64: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+    case 256: return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    default: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  }
+}
+
 }  // namespace wg
 
 struct wg_layer {

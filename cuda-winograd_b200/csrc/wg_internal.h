@@ -14,6 +14,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 // cuTensorMapEncodeTiled fetched through the runtime (no link-time libcuda dependency); nullptr on failure.
 PFN_encodeTiled get_encode_tiled();
 
+// L2 promotion of the activation tensor maps (WG_L2_PROMO=0|64|128|256 overrides; experiments)
+CUtensorMapL2promotion l2_promotion();
+
 // ---- 3x3 Winograd path (winograd_kernels.cu)
 int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
 int wino_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,

@@ -69,7 +69,7 @@ template <bool FOLD>
 __global__ void __launch_bounds__(kThreads, 1)
 wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                        const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
-                       int n_img, int C, int K, int relu, int out_padded, int ablate) {
+                       int n_img, int C, int K, int relu, int out_padded, int mv, int ablate) {
   using S = WinoCfg<FOLD>;
   constexpr int KN = S::KN;
   constexpr uint32_t kTmemCols = 512;
@@ -116,7 +116,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
   const int n_kb = C / 8;
   const int n_slices = K / KN;
   const int total_tiles = n_img * 49;
-  const int n_mblocks = (total_tiles + 127) / 128;
+  const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host to balance waves
   const int n_items = n_mblocks * n_slices;
 
   if (warp == kProducerWarp) {
@@ -126,7 +126,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int slice = item % n_slices;
         const int mb = item / n_slices;
-        const int t0 = mb * 128;
+        const int t0 = mb * mv;
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) +
                                (size_t)slice * n_kb * S::kUChunksPerStage * S::kUChunkBytes;
@@ -232,12 +232,14 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int slice = item % n_slices;
       const int mb = item / n_slices;
-      const int t0 = mb * 128;
+      const int t0 = mb * mv;
       const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
 
       // ---- transform: this thread's tile and its offset inside a raw stage
       const int T = t0 + trow;
-      const bool tvalid = T < total_tiles;
+      const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
+      const bool tvalid = trow < valid_rows;
+      const bool warp_active = warp * 16 < valid_rows;  // warp-uniform: warps whose 16 rows are all padding only keep the barriers moving
       uint32_t raw_off = 0;
       {
         const int n = T / 49, t = T % 49, ty = t / 7, tx = t % 7;
@@ -248,6 +250,15 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
       for (int kb = 0; kb < n_kb; ++kb) {
         float4 d[4][4];
         mbar_wait(&raw_full[rs], rph);
+        if (!warp_active) {
+          // nothing to transform: release the raw stage and report "V ready" in step with the other warps
+          if (lane == 0) mbar_arrive(&raw_empty[rs]);
+          if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
+          mbar_wait(&v_empty[vs], vph ^ 1);
+          if (lane == 0) mbar_arrive(&v_full[vs]);
+          if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
+          continue;
+        }
         if (tvalid && !(ablate & 1)) {
           const uint32_t a = raw_base + rs * kRawBytes + raw_off;
 #pragma unroll
@@ -299,7 +310,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
 
       // ---- epilogue: (rest of) Y = A^T M A, BN, ReLU, store
       const int TE = t0 + erow;
-      const bool evalid = TE < total_tiles;
+      const bool evalid = erow < valid_rows;
       const int n = TE / 49, t = TE % 49, ty = t / 7, tx = t % 7;
       const int W = out_padded ? 16 : 14;
       const int o = out_padded ? 1 : 0;
@@ -311,8 +322,10 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
       aph ^= 1;
       tc_fence_after();
       constexpr int kColsPerWarp = KN / 2;
+      // warps whose 32 TMEM lanes hold only padding rows have nothing to drain (warp-uniform)
+      const int cc_end = quad * 32 < valid_rows ? kColsPerWarp : 0;
 #pragma unroll 1
-      for (int cc = 0; cc < kColsPerWarp; cc += 8) {
+      for (int cc = 0; cc < cc_end; cc += 8) {
         const int c0 = half * kColsPerWarp + cc;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
         float o00[8], o01[8], o10[8], o11[8];  // Y[a][b] before BN
@@ -384,7 +397,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
       }
       __syncwarp();
       // write-out: kChunks lanes cover one output pixel's kColsPerWarp couts = one contiguous 64/128-byte run
-      if (!(ablate & 32)) {
+      if (cc_end != 0 && !(ablate & 32)) {
         constexpr int kChunks = kColsPerWarp / 4;      // 16-byte chunks per pixel owned by this warp (4 or 8)
         constexpr int kTilesPerInstr = 32 / kChunks;   // 8 or 4
         const int j = lane % kChunks;
@@ -498,7 +511,7 @@ int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
   cuuint32_t box[4] = {8, 8, 2, (cuuint32_t)kRawRows};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, wg::l2_promotion(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
@@ -514,7 +527,32 @@ static int launch_wino(const CUtensorMap& tmap, const float* u_img, const float*
     if (e != cudaSuccess) return WG_ERR_CUDA;
     configured = true;
   }
-  const int n_items = ((n_img * 49 + 127) / 128) * (K / S::KN);
+  // Tiles per M-block: the MMA is always M=128, but only `mv` rows carry tiles. A smaller mv costs MMA efficiency
+  // (the tensor pipe has slack) and buys an item count that fills the last wave: per item, ~55 % of the cost (MMA
+  // operand reads, TMA) is fixed and ~45 % (the input transform) scales with the active 16-row warps.
+  const int total_tiles = n_img * 49;
+  const int n_slices = K / S::KN;
+  int mv = 128;
+  static int mv_env = -1;  // WG_WINO_MV=<16..128> pins it (experiments)
+  if (mv_env < 0) {
+    const char* e = getenv("WG_WINO_MV");
+    mv_env = e ? atoi(e) : 0;
+  }
+  if (mv_env >= 16 && mv_env <= 128) {
+    mv = mv_env;
+  } else {
+    double best = 1e30;
+    for (int cand = 128; cand >= 64; cand -= 16) {
+      const long long items = (long long)((total_tiles + cand - 1) / cand) * n_slices;
+      const long long waves = (items + max_ctas - 1) / max_ctas;
+      const double cost = (double)waves * (0.55 + 0.45 * cand / 128.0);
+      if (cost < best - 1e-9) {
+        best = cost;
+        mv = cand;
+      }
+    }
+  }
+  const int n_items = ((total_tiles + mv - 1) / mv) * n_slices;
   int grid = n_items < max_ctas ? n_items : max_ctas;
   if (grid < 1) grid = 1;
   static int ablate = -1;  // debug only: WG_DEBUG_ABLATE=<bitmask> switches pipeline pieces off for timing experiments
@@ -523,7 +561,7 @@ static int launch_wino(const CUtensorMap& tmap, const float* u_img, const float*
     ablate = e ? atoi(e) : 0;
   }
   wino3x3_bn_relu_kernel<FOLD><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K, relu,
-                                                                      out_padded, ablate);
+                                                                      out_padded, mv, ablate);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
