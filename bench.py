@@ -227,7 +227,7 @@ def run_gpu(args):
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": tflops / tf32_peak, "traffic": traffic,
-                         "kernel": "wino3x3_bn_relu_kernel<32>",
+                         "kernel": "wino3x3_bn_relu_kernel<FOLD=true, BF16=false>",
                          "algorithmic": "direct-conv-equivalent 2*196*256*256*9 = 231.21 MFLOP/image x 256 images/launch",
                          "peak_note": "dense TF32 = half of the measured sustained bf16 cuBLAS rate in " + pk["source"],
                          "hbm": {"achieved_gbs": (BYTES_PER_IMAGE * n + WEIGHT_BYTES) / (ms_per_step * 1e-3) / 1e9,
@@ -255,6 +255,15 @@ def _cpu_threads():
         return os.cpu_count() or 1
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is asked to use every host thread it can."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def cpu_step(x, w, scale, shift):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import golden
@@ -264,6 +273,7 @@ def cpu_step(x, w, scale, shift):
 def cpu_baseline(budget_s=12.0, sample_images=32):
     """The NumPy FP32 golden on the host cores over a bounded sample of the same workload."""
     import numpy as np
+    _use_all_host_threads()
     w, scale, shift = make_params()
     rs = np.random.RandomState(1)
     x = (rs.rand(sample_images, 16, 16, C_IN) - 0.5).astype(np.float32)
@@ -286,7 +296,11 @@ def run_reference(args):
     for here; the arm is the oracle port (NumPy FP32 golden) with all host threads, same metric/config. Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; BLAS reads it when numpy is first imported (nothing imported it yet)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(os.cpu_count() or 1)
     import numpy as np
+    _use_all_host_threads()
     w, scale, shift = make_params()
     sample = 64
     rs = np.random.RandomState(1)

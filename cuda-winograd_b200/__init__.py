@@ -174,10 +174,12 @@ class Conv3x3BnRelu(_Layer):
     Replaces kernel_128()/kernel_256()'s three launches (Kernel128_winograd.cu:263-265)."""
     kind = 0
 
-    def __init__(self, w_kcrs, scale, shift, relu=True, device=0):
+    def __init__(self, w_kcrs, scale, shift, relu=True, device=0, dtype=WG_TF32):
+        """dtype = WG_TF32 (default; tolerance 1e-3) or WG_BF16 (bf16 V/U operands, fp32 I/O and accumulation;
+        tolerance 1e-2; needs C % 16 == 0 and K % 64 == 0)."""
         k, c = w_kcrs.shape[0], w_kcrs.shape[1]
         assert tuple(w_kcrs.shape) == (k, c, 3, 3)
-        super().__init__(c, k, w_kcrs, scale, shift, relu, device)
+        super().__init__(c, k, w_kcrs, scale, shift, relu, device, dtype)
 
     def in_shape(self):
         return (16, 16, self.cin)

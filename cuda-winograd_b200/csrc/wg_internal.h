@@ -19,9 +19,10 @@ CUtensorMapL2promotion l2_promotion();
 
 // ---- 3x3 Winograd path (winograd_kernels.cu)
 int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
-int wino_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                int n_img, int C, int K, int KN, int relu, int out_padded, int max_ctas, cudaStream_t stream);
-int filter_transform_launch(const float* w_kcrs, float* u_img, int C, int K, int KN, cudaStream_t stream);
+int wino_launch(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift, float* y,
+                int n_img, int C, int K, int KN, int bf16, int relu, int out_padded, int max_ctas,
+                cudaStream_t stream);
+int filter_transform_launch(const float* w_kcrs, void* u_img, int C, int K, int KN, int bf16, cudaStream_t stream);
 
 // ---- 1x1 GEMM path (one_kernels.cu)
 int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);

@@ -24,6 +24,7 @@
 #include "wg_internal.h"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 namespace wg {
@@ -34,6 +35,13 @@ constexpr int kMmaWarp = 9;
 constexpr int kThreads = 32 * 10;
 constexpr int kRawRows = 48;  // input rows (n*16+y) one M-block can touch, see DESIGN.md
 constexpr uint32_t kRawBytes = kRawRows * 2 * 8 * 32;  // [ny][x parity][x/2][8 ch] fp32 = 24576
+
+template <bool BF16>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (BF16) umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else umma_tf32_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 
 template <bool FOLD>
 struct WinoCfg {
@@ -65,13 +73,18 @@ struct WinoCfg {
 // compiles to three ALU instructions on sm_100a).
 __device__ __forceinline__ float tf32_operand(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
-template <bool FOLD>
+// BF16 = true: V and U are bf16 operands (tcgen05.mma kind::f16, FP32 accumulate, K = 16 per instruction). A V stage
+// then covers 16 channels = two 8-channel raw stages (each fills one 16-byte k-chunk of every row); shared-memory
+// traffic per channel for V and U halves. Input/output stay fp32. Tolerance 1e-2 (north_star), measured ~3e-3.
+template <bool FOLD, bool BF16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
-wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
+wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* __restrict__ u_img,
                        const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
                        int n_img, int C, int K, int relu, int out_padded, int mv, int ablate) {
+  static_assert(!BF16 || FOLD, "the bf16 variant is built on the folded accumulation");
   using S = WinoCfg<FOLD>;
   constexpr int KN = S::KN;
+  constexpr int kRawPerV = BF16 ? 2 : 1;  // 8-channel raw stages per V stage
   constexpr uint32_t kTmemCols = 512;
   extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -129,18 +142,20 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
         const int t0 = mb * mv;
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) +
-                               (size_t)slice * n_kb * S::kUChunksPerStage * S::kUChunkBytes;
+                               (size_t)slice * (n_kb / kRawPerV) * S::kUChunksPerStage * S::kUChunkBytes;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&raw_empty[rs], rph ^ 1);
           mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
           tma_tensor_4d_g2s(smem + S::kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
           if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
+          if (kb % kRawPerV != 0) continue;  // the U chunks of a V stage go out with its first raw stage
+          const int kv = kb / kRawPerV;
 #pragma unroll
           for (int h = 0; h < S::kUChunksPerStage; ++h) {
             mbar_wait(&u_empty[us], uph ^ 1);
             mbar_arrive_expect_tx(&u_full[us], S::kUChunkBytes);
             tma_bulk_g2s(smem + S::kOffU + us * S::kUChunkBytes,
-                         u_src + (size_t)(kb * S::kUChunksPerStage + h) * S::kUChunkBytes, S::kUChunkBytes,
+                         u_src + (size_t)(kv * S::kUChunksPerStage + h) * S::kUChunkBytes, S::kUChunkBytes,
                          &u_full[us]);
             if (++us == S::kUBufs) { us = 0; uph ^= 1; }
           }
@@ -150,15 +165,16 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, KN);
-      constexpr uint32_t idesc_neg = make_idesc(kFmtTF32, 128, KN, 1);  // D += (-A) * B
+      constexpr uint32_t kFmt = BF16 ? kFmtBF16 : kFmtTF32;
+      constexpr uint32_t idesc = make_idesc(kFmt, 128, KN);
+      constexpr uint32_t idesc_neg = make_idesc(kFmt, 128, KN, 1);  // D += (-A) * B
       const uint32_t v_base = smem_u32(smem + S::kOffV);
       const uint32_t u_base = smem_u32(smem + S::kOffU);
       uint32_t vs = 0, vph = 0, us = 0, uph = 0, aph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = 0; kb < n_kb / kRawPerV; ++kb) {  // V stages
           const uint32_t acc = kb > 0 ? 1u : 0u;
           mbar_wait(&v_full[vs], vph);
           const uint32_t va = v_base + vs * S::kVBytes;
@@ -176,7 +192,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
             for (int xi = 0; xi < 16; ++xi) {
               const uint64_t a_desc = make_smem_desc(va + xi * S::kVPerXi, S::kVLbo, 128, kLayoutNone);
               const uint64_t b_desc = make_smem_desc(ua + xi * S::kUPerPoint, S::kULbo, 128, kLayoutNone);
-              umma_tf32_ss(tmem_base + xi * KN, a_desc, b_desc, idesc, acc);
+              umma_ss<BF16>(tmem_base + xi * KN, a_desc, b_desc, idesc, acc);
             }
             umma_commit(&u_empty[us]);
             if (++us == S::kUBufs) { us = 0; uph ^= 1; }
@@ -197,12 +213,12 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
                   a_desc[i] = make_smem_desc(va + (4 * i + j) * S::kVPerXi, S::kVLbo, 128, kLayoutNone);
                   b_desc[i] = make_smem_desc(ua + (i * 2 + jj) * S::kUPerPoint, S::kULbo, 128, kLayoutNone);
                 }
-                umma_tf32_ss(z0, a_desc[1], b_desc[1], idesc, acc);  // first writer of both accumulators
-                umma_tf32_ss(z1, a_desc[1], b_desc[1], idesc, acc);
-                umma_tf32_ss(z0, a_desc[0], b_desc[0], idesc, 1u);
-                umma_tf32_ss(z0, a_desc[2], b_desc[2], idesc, 1u);
-                umma_tf32_ss(z1, a_desc[2], b_desc[2], idesc_neg, 1u);
-                umma_tf32_ss(z1, a_desc[3], b_desc[3], idesc_neg, 1u);
+                umma_ss<BF16>(z0, a_desc[1], b_desc[1], idesc, acc);  // first writer of both accumulators
+                umma_ss<BF16>(z1, a_desc[1], b_desc[1], idesc, acc);
+                umma_ss<BF16>(z0, a_desc[0], b_desc[0], idesc, 1u);
+                umma_ss<BF16>(z0, a_desc[2], b_desc[2], idesc, 1u);
+                umma_ss<BF16>(z1, a_desc[2], b_desc[2], idesc_neg, 1u);
+                umma_ss<BF16>(z1, a_desc[3], b_desc[3], idesc_neg, 1u);
               }
               umma_commit(&u_empty[us]);
               if (++us == S::kUBufs) { us = 0; uph ^= 1; }
@@ -250,13 +266,17 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
       for (int kb = 0; kb < n_kb; ++kb) {
         float4 d[4][4];
         mbar_wait(&raw_full[rs], rph);
+        const int sub = kb % kRawPerV;               // which 16-byte k-chunk of the V rows this raw stage fills
+        const bool v_first = sub == 0, v_last = sub == kRawPerV - 1;
         if (!warp_active) {
           // nothing to transform: release the raw stage and report "V ready" in step with the other warps
           if (lane == 0) mbar_arrive(&raw_empty[rs]);
           if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
-          mbar_wait(&v_empty[vs], vph ^ 1);
-          if (lane == 0) mbar_arrive(&v_full[vs]);
-          if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
+          if (v_first) mbar_wait(&v_empty[vs], vph ^ 1);
+          if (v_last) {
+            if (lane == 0) mbar_arrive(&v_full[vs]);
+            if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
+          }
           continue;
         }
         if (tvalid && !(ablate & 1)) {
@@ -286,10 +306,22 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
         if (lane == 0) mbar_arrive(&raw_empty[rs]);
         if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
 
-        mbar_wait(&v_empty[vs], vph ^ 1);  // MMAs that read this V stage have completed
+        if (v_first) mbar_wait(&v_empty[vs], vph ^ 1);  // MMAs that read this V stage have completed
         const uint32_t vdst = v_base + vs * S::kVBytes + v_off;
-        // row pass V = t B, round to TF32, store point (i,j) at xi = 4*i + j
-        if (!(ablate & 2))
+        // row pass V = t B, round to the operand type, store point (i,j) at xi = 4*i + j
+        if constexpr (BF16) {
+          // 4 channels -> 8 bytes at [k-chunk sub][row][c*8]
+          const uint32_t bdst = v_base + vs * S::kVBytes + sub * S::kVLbo + trow * 16 + c * 8;
+          if (!(ablate & 2))
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
+            st_shared_bf16x4(bdst + (4 * i + 0) * S::kVPerXi, a0.x - a2.x, a0.y - a2.y, a0.z - a2.z, a0.w - a2.w);
+            st_shared_bf16x4(bdst + (4 * i + 1) * S::kVPerXi, a1.x + a2.x, a1.y + a2.y, a1.z + a2.z, a1.w + a2.w);
+            st_shared_bf16x4(bdst + (4 * i + 2) * S::kVPerXi, a2.x - a1.x, a2.y - a1.y, a2.z - a1.z, a2.w - a1.w);
+            st_shared_bf16x4(bdst + (4 * i + 3) * S::kVPerXi, a1.x - a3.x, a1.y - a3.y, a1.z - a3.z, a1.w - a3.w);
+          }
+        } else if (!(ablate & 2))
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
@@ -302,10 +334,12 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
           st_shared_v4(vdst + (4 * i + 3) * S::kVPerXi, tf32_operand(a1.x - a3.x), tf32_operand(a1.y - a3.y),
                        tf32_operand(a1.z - a3.z), tf32_operand(a1.w - a3.w));
         }
-        if (!(ablate & 4)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&v_full[vs]);
-        if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
+        if (v_last) {
+          if (!(ablate & 4)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&v_full[vs]);
+          if (++vs == S::kVStages) { vs = 0; vph ^= 1; }
+        }
       }
 
       // ---- epilogue: (rest of) Y = A^T M A, BN, ReLU, store
@@ -459,8 +493,10 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* 
 //   plain: [K/32 slice][C/8 k-block][16 points (i,j)]        [2 k-chunks][32 couts][4 channels]
 //   fold : [K/64 slice][C/8 k-block][2 j-halves][4 i][2 jj]  [2 k-chunks][64 couts][4 channels]   (j = 2*jh + jj)
 // Replaces the offline weight_generator loop (/root/reference/data_generator.py:63-78; that one is F(4x4), 36 points).
-__global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, float* __restrict__ u_img, int C, int K,
-                                             int KN, int fold) {
+//   bf16 : [K/64 slice][C/16 k-block][2 j-halves][4 i][2 jj] [2 k-chunks][64 couts][8 channels] as __nv_bfloat16 (RN)
+__global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, void* __restrict__ u_img_v, int C, int K,
+                                             int KN, int fold, int bf16) {
+  float* u_img = static_cast<float*>(u_img_v);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * K) return;
   const int ch = idx % C;
@@ -484,6 +520,11 @@ __global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, f
   const int kb = ch / 8, chunk = (ch % 8) / 4, e = ch % 4;
   const size_t point_floats = (size_t)2 * KN * 4;
   const size_t stage = ((size_t)slice * (C / 8) + kb) * 16 * point_floats;
+  // bf16 image: 16-channel k-blocks, 8 channels per 16-byte chunk, same bytes per point (2 * KN * 16)
+  __nv_bfloat16* u_bf = static_cast<__nv_bfloat16*>(u_img_v);
+  const size_t point_halfs = (size_t)2 * KN * 8;
+  const size_t stage_bf = ((size_t)slice * (C / 16) + ch / 16) * 16 * point_halfs;
+  const int chunk_bf = (ch % 16) / 8, e_bf = ch % 8;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float u[4];
@@ -494,7 +535,10 @@ __global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, f
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = fold ? ((j >> 1) * 8 + i * 2 + (j & 1)) : (4 * i + j);
-      u_img[stage + p * point_floats + ((size_t)chunk * KN + kn) * 4 + e] = to_tf32_rn(u[j]);
+      if (bf16)
+        u_bf[stage_bf + p * point_halfs + ((size_t)chunk_bf * KN + kn) * 8 + e_bf] = __float2bfloat16_rn(u[j]);
+      else
+        u_img[stage + p * point_floats + ((size_t)chunk * KN + kn) * 4 + e] = to_tf32_rn(u[j]);
     }
   }
 }
@@ -516,13 +560,13 @@ int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
 
-template <bool FOLD>
-static int launch_wino(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+template <bool FOLD, bool BF16>
+static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift, float* y,
                        int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
   using S = WinoCfg<FOLD>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<FOLD, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
     configured = true;
@@ -560,21 +604,28 @@ static int launch_wino(const CUtensorMap& tmap, const float* u_img, const float*
     const char* e = getenv("WG_DEBUG_ABLATE");
     ablate = e ? atoi(e) : 0;
   }
-  wino3x3_bn_relu_kernel<FOLD><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K, relu,
-                                                                      out_padded, mv, ablate);
+  wino3x3_bn_relu_kernel<FOLD, BF16><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K,
+                                                                            relu, out_padded, mv, ablate);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-int wino_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                int n_img, int C, int K, int KN, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
-  if (KN == 64) return launch_wino<true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
-  if (KN == 32) return launch_wino<false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+int wino_launch(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift, float* y,
+                int n_img, int C, int K, int KN, int bf16, int relu, int out_padded, int max_ctas,
+                cudaStream_t stream) {
+  if (bf16) {
+    if (KN != 64 || C % 16 != 0) return WG_ERR_ARG;
+    return launch_wino<true, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+  }
+  if (KN == 64)
+    return launch_wino<true, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+  if (KN == 32)
+    return launch_wino<false, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
   return WG_ERR_ARG;
 }
 
-int filter_transform_launch(const float* w_kcrs, float* u_img, int C, int K, int KN, cudaStream_t stream) {
+int filter_transform_launch(const float* w_kcrs, void* u_img, int C, int K, int KN, int bf16, cudaStream_t stream) {
   const int n = C * K;
-  filter_transform_f2x2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, KN, KN == 64 ? 1 : 0);
+  filter_transform_f2x2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, KN, KN == 64 ? 1 : 0, bf16);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 

@@ -83,6 +83,33 @@ def test_3x3_ragged_batches(lib_loaded, torch_cuda, n, c, k, relu):
     assert golden.rel_err(y, golden.conv3x3_bn_relu(x, w, sc, sh, relu)) <= TOL_TF32
 
 
+TOL_BF16 = 1e-2
+
+
+@pytest.mark.parametrize("n,c,k", [(1, 128, 128), (1, 256, 256), (3, 64, 64), (5, 48, 128), (64, 128, 128)])
+def test_3x3_bf16_operand_variant(lib_loaded, torch_cuda, n, c, k):
+    """The stated bf16 variant (north_star): bf16 V/U operands, fp32 I/O + accumulation, tolerance 1e-2."""
+    torch = torch_cuda
+    x, w, sc, sh = _rand3x3(np.random.RandomState(300 + n), n, c, k)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=lib_loaded.WG_BF16)
+    y = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    e = golden.rel_err(y, golden.conv3x3_bn_relu(x, w, sc, sh, True))
+    assert 1e-4 < e <= TOL_BF16, e      # really the bf16 path (TF32 would sit at ~4e-4), and inside its bar
+    yp = layer(torch.from_numpy(x).cuda(), out_padded=True).cpu().numpy()
+    np.testing.assert_array_equal(yp[:, 1:15, 1:15], y)
+    assert np.all(yp[:, 0] == 0) and np.all(yp[:, :, 15] == 0)
+
+
+def test_bf16_is_rejected_where_it_does_not_exist(lib_loaded):
+    with pytest.raises(lib_loaded.WinogradB200Error):   # the 1x1 activation operand is never touched by CUDA cores
+        lib_loaded._Layer.__init__(lib_loaded.Conv1x1Bn.__new__(lib_loaded.Conv1x1Bn), 32, 128,
+                                   np.zeros((32, 128), np.float32), np.ones(128, np.float32),
+                                   np.ones(128, np.float32), True, 0, lib_loaded.WG_BF16)
+    with pytest.raises(lib_loaded.WinogradB200Error):   # K must be a multiple of 64 for the folded bf16 kernel
+        lib_loaded.Conv3x3BnRelu(np.zeros((32, 32, 3, 3), np.float32), np.ones(32, np.float32),
+                                 np.ones(32, np.float32), dtype=lib_loaded.WG_BF16)
+
+
 @pytest.mark.parametrize("n,cin,cout", [(1, 32, 128), (2, 96, 256), (3, 64, 384), (7, 512, 128)])
 def test_1x1_ragged_batches(lib_loaded, torch_cuda, n, cin, cout):
     torch = torch_cuda

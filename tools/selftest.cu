@@ -23,6 +23,7 @@
   } while (0)
 
 static uint32_t rng_state = 12345;
+static wg_dtype_t g_dtype = WG_TF32;  // operand type used for the 3x3 layers
 static float frand() {  // U(-0.5, 0.5)
   rng_state = rng_state * 1664525u + 1013904223u;
   return ((rng_state >> 8) & 0xffffff) / 16777216.0f - 0.5f;
@@ -129,7 +130,7 @@ static double check3x3(int N, int C, int K, int relu, int padded, const std::vec
   const int W = padded ? 16 : 14, o = padded ? 1 : 0;
   std::vector<float> y((size_t)N * W * W * K, 123.f);
   wg_layer_t* L = nullptr;
-  int rc = wg_conv3x3_create(&L, C, K, w.data(), sc.data(), sh.data(), relu, WG_TF32, 0);
+  int rc = wg_conv3x3_create(&L, C, K, w.data(), sc.data(), sh.data(), relu, g_dtype, 0);
   if (rc) {
     printf("create3x3 failed: %s (%s)\n", wg_strerror(rc), wg_last_cuda_error());
     return 1e30;
@@ -228,7 +229,7 @@ static void time_layer(int kind, int N, int C, int K, int relu) {
   std::vector<float> w((size_t)K * C * (kind == 0 ? 9 : 1)), sc(K, 1.f), sh(K, 0.f);
   for (auto& v : w) v = frand();
   wg_layer_t* L = nullptr;
-  int rc = kind == 0 ? wg_conv3x3_create(&L, C, K, w.data(), sc.data(), sh.data(), relu, WG_TF32, 0)
+  int rc = kind == 0 ? wg_conv3x3_create(&L, C, K, w.data(), sc.data(), sh.data(), relu, g_dtype, 0)
                      : wg_conv1x1_create(&L, C, K, w.data(), sc.data(), sh.data(), relu, WG_TF32, 0);
   if (rc) return;
   const size_t xe = (size_t)N * (kind == 0 ? 256 : 196) * C, ye = (size_t)N * 196 * K;
@@ -286,6 +287,18 @@ int main(int argc, char** argv) {
     }
   }
   wg_set_wino_kn(64);
+  g_dtype = WG_BF16;
+  printf("-- 3x3 bf16 operand variant (tolerance 1e-2)\n");
+  bad(check3x3(1, 128, 128, 1, 1, {0}), 1e-2);
+  bad(check3x3(3, 64, 64, 0, 0, {0, 1, 2}), 1e-2);
+  bad(check3x3(7, 32, 64, 1, 1, {0, 3, 6}), 1e-2);
+  if (!quick) {
+    bad(check3x3(256, 128, 128, 1, 0, {0, 131, 255}), 1e-2);
+    bad(check3x3(64, 256, 256, 1, 0, {0, 63}), 1e-2);
+    time_layer(0, 256, 128, 128, 1);
+    time_layer(0, 256, 256, 256, 1);
+  }
+  g_dtype = WG_TF32;
   bad(check1x1(1, 512, 128, 1, {0}), 1e-3);
   bad(check1x1(1, 128, 512, 0, {0}), 1e-3);
   bad(check1x1(3, 64, 256, 0, {0, 2}), 1e-3);
