@@ -76,12 +76,15 @@ __device__ __forceinline__ float tf32_operand(float x) { return __uint_as_float(
 // BF16 = true: V and U are bf16 operands (tcgen05.mma kind::f16, FP32 accumulate, K = 16 per instruction). A V stage
 // then covers 16 channels = two 8-channel raw stages (each fills one 16-byte k-chunk of every row); shared-memory
 // traffic per channel for V and U halves. Input/output stay fp32. Tolerance 1e-2 (north_star), measured ~3e-3.
-template <bool FOLD, bool BF16 = false>
+// CS > 1: split-C mode for small batches (latency): a cluster of CS CTAs shares one work item, each CTA runs 1/CS of
+// the channel loop, the partial outputs are reduced through distributed shared memory (ld.shared::cluster).
+template <bool FOLD, bool BF16 = false, int CS = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* __restrict__ u_img,
                        const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
                        int n_img, int C, int K, int relu, int out_padded, int mv, int ablate) {
   static_assert(!BF16 || FOLD, "the bf16 variant is built on the folded accumulation");
+  static_assert(CS == 1 || FOLD, "split-C is built on the folded accumulation");
   using S = WinoCfg<FOLD>;
   constexpr int KN = S::KN;
   constexpr int kRawPerV = BF16 ? 2 : 1;  // 8-channel raw stages per V stage
@@ -90,6 +93,10 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // debug only (ablate & 64): phase timestamps of thread 0 of CTA 0, printed at exit
+  long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define WG_TS(i) do { if ((ablate & 64) && threadIdx.x == 0 && blockIdx.x == 0) ts[i] = clock64(); } while (0)
+  WG_TS(0);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
   uint64_t* raw_full = bars;
@@ -122,28 +129,35 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
   }
   if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  WG_TS(1);
 
   const int n_kb = C / 8;
   const int n_slices = K / KN;
   const int total_tiles = n_img * 49;
   const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host to balance waves
   const int n_items = n_mblocks * n_slices;
+  // CS > 1 (small batches): the CS CTAs of a cluster share one item and split its channel loop; partial results are
+  // summed through distributed shared memory after the loop. One item per cluster (the host sizes the grid so).
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+  const int item0 = blockIdx.x / CS, item_step = gridDim.x / CS;
+  const int kb_per = n_kb / CS;          // 8-channel raw stages this CTA runs
+  const int kb0 = (int)crank * kb_per;   // first one
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t rs = 0, rph = 0, us = 0, uph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = item0; item < n_items; item += item_step) {
         const int slice = item % n_slices;
         const int mb = item / n_slices;
         const int t0 = mb * mv;
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) +
                                (size_t)slice * (n_kb / kRawPerV) * S::kUChunksPerStage * S::kUChunkBytes;
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = kb0; kb < kb0 + kb_per; ++kb) {
           mbar_wait(&raw_empty[rs], rph ^ 1);
           mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
           tma_tensor_4d_g2s(smem + S::kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
@@ -171,10 +185,10 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
       const uint32_t v_base = smem_u32(smem + S::kOffV);
       const uint32_t u_base = smem_u32(smem + S::kOffU);
       uint32_t vs = 0, vph = 0, us = 0, uph = 0, aph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = item0; item < n_items; item += item_step) {
         mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
-        for (int kb = 0; kb < n_kb / kRawPerV; ++kb) {  // V stages
+        for (int kb = 0; kb < kb_per / kRawPerV; ++kb) {  // V stages
           const uint32_t acc = kb > 0 ? 1u : 0u;
           mbar_wait(&v_full[vs], vph);
           const uint32_t va = v_base + vs * S::kVBytes;
@@ -245,7 +259,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
     const uint32_t v_base = smem_u32(smem + S::kOffV);
 
     uint32_t rs = 0, rph = 0, vs = 0, vph = 0, aph = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = item0; item < n_items; item += item_step) {
       const int slice = item % n_slices;
       const int mb = item / n_slices;
       const int t0 = mb * mv;
@@ -263,9 +277,10 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
       }
       const uint32_t v_off = (uint32_t)(c * S::kVLbo + trow * 16);
 
-      for (int kb = 0; kb < n_kb; ++kb) {
+      for (int kb = kb0; kb < kb0 + kb_per; ++kb) {
         float4 d[4][4];
         mbar_wait(&raw_full[rs], rph);
+        if (kb == kb0) WG_TS(2);
         const int sub = kb % kRawPerV;               // which 16-byte k-chunk of the V rows this raw stage fills
         const bool v_first = sub == 0, v_last = sub == kRawPerV - 1;
         if (!warp_active) {
@@ -353,6 +368,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
       const uint32_t stg = v_base + warp * (32 * 512);  // this warp's 16 KB staging area inside the V buffers
 
       mbar_wait(acc_full, aph);
+      WG_TS(3);
       aph ^= 1;
       tc_fence_after();
       constexpr int kColsPerWarp = KN / 2;
@@ -394,6 +410,24 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
             o11[e] = z[3][e] - z[5][e] - z[7][e];
           }
         }
+        if constexpr (CS > 1) {
+          // split-C: these are partial sums over this CTA's channels. Park them (pre-BN) in local shared memory as
+          // part[row][pixel][KN couts] (1 KB rows, 16-byte chunks XOR-swizzled by the row) for the cluster reduction.
+          if (erow < 64) {
+            const uint32_t pdst = v_base + erow * 1024;
+            const uint32_t sw = erow & 15;
+            const uint32_t k0 = (uint32_t)c0 >> 2;
+            st_shared_v4(pdst + 0 * 256 + (((k0 + 0) ^ sw) << 4), o00[0], o00[1], o00[2], o00[3]);
+            st_shared_v4(pdst + 0 * 256 + (((k0 + 1) ^ sw) << 4), o00[4], o00[5], o00[6], o00[7]);
+            st_shared_v4(pdst + 1 * 256 + (((k0 + 0) ^ sw) << 4), o01[0], o01[1], o01[2], o01[3]);
+            st_shared_v4(pdst + 1 * 256 + (((k0 + 1) ^ sw) << 4), o01[4], o01[5], o01[6], o01[7]);
+            st_shared_v4(pdst + 2 * 256 + (((k0 + 0) ^ sw) << 4), o10[0], o10[1], o10[2], o10[3]);
+            st_shared_v4(pdst + 2 * 256 + (((k0 + 1) ^ sw) << 4), o10[4], o10[5], o10[6], o10[7]);
+            st_shared_v4(pdst + 3 * 256 + (((k0 + 0) ^ sw) << 4), o11[0], o11[1], o11[2], o11[3]);
+            st_shared_v4(pdst + 3 * 256 + (((k0 + 1) ^ sw) << 4), o11[4], o11[5], o11[6], o11[7]);
+          }
+          continue;
+        }
         const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + slice * KN + c0));
         const float4 sc1 = __ldg(reinterpret_cast<const float4*>(scale + slice * KN + c0 + 4));
         const float4 sh0 = __ldg(reinterpret_cast<const float4*>(shift + slice * KN + c0));
@@ -431,7 +465,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
       }
       __syncwarp();
       // write-out: kChunks lanes cover one output pixel's kColsPerWarp couts = one contiguous 64/128-byte run
-      if (cc_end != 0 && !(ablate & 32)) {
+      if (CS == 1 && cc_end != 0 && !(ablate & 32)) {
         constexpr int kChunks = kColsPerWarp / 4;      // 16-byte chunks per pixel owned by this warp (4 or 8)
         constexpr int kTilesPerInstr = 32 / kChunks;   // 8 or 4
         const int j = lane % kChunks;
@@ -476,15 +510,115 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
       }
       // every worker warp must be done with its staging area before any of them refills the V buffers
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      WG_TS(4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
     }
   }
 
+  if constexpr (CS > 1) {
+    // ---- split-C reduction over the cluster (deterministic: fixed summation order, no atomics)
+    __syncwarp();        // the single-lane roles rejoin their warps before the aligned cluster barrier
+    cluster_sync_all();  // every CTA's partial Y is parked in its shared memory
+    WG_TS(5);
+    // Push model (a pull over ld.shared::cluster measured 10.5 k clk for 50 KB per CTA): every CTA forwards each
+    // 16-byte piece of its partial Y to the CTA that owns those couts with a fire-and-forget st.shared::cluster into
+    // a receive area [source CTA][row][pixel][couts per owner] behind the parking area; one more cluster barrier, then
+    // the owner sums its CS inboxes locally in a fixed order.
+    constexpr int kChunksPerCta = KN / CS / 4;           // 16-byte cout chunks a CTA owns (16 couts = 4, 8 couts = 2)
+    constexpr uint32_t kInboxBytes = 64 * 4 * (KN / CS) * 4;  // one source's [64 rows][4 px][couts per owner] fp32
+    const uint32_t part_local = smem_u32(smem + S::kOffV);
+    const uint32_t recv_local = part_local + 64 * 1024;  // CS inboxes = 64 KB, the parking area is the 64 KB before
+    const bool reducer = warp < kWorkerWarps && item0 < n_items;
+    const int slice = item0 % n_slices;
+    const int t0 = (item0 / n_slices) * mv;
+    const int valid_rows = reducer ? min(min(mv, total_tiles - t0), 64) : 0;
+    if (reducer) {
+      uint32_t inbox_remote[CS];  // my inbox inside each owner CTA
+#pragma unroll
+      for (int p = 0; p < CS; ++p)
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                     : "=r"(inbox_remote[p])
+                     : "r"(recv_local + crank * kInboxBytes), "r"(p));
+      const int units = valid_rows * 4 * (KN / 4);  // (row, pixel, 16-byte chunk) over all KN couts
+      for (int u = threadIdx.x; u < units; u += kWorkerWarps * 32) {
+        const int chunk = u % (KN / 4);
+        const int rp = u / (KN / 4);  // row * 4 + pixel
+        const int row = rp >> 2;
+        const float4 v = ld_shared_v4(part_local + rp * 256 + ((chunk ^ (row & 15)) << 4));
+        const int owner = chunk / kChunksPerCta;
+        uint32_t dst = inbox_remote[0];
+#pragma unroll
+        for (int p = 1; p < CS; ++p) dst = owner == p ? inbox_remote[p] : dst;
+        dst += rp * (kChunksPerCta * 16) + (chunk % kChunksPerCta) * 16;
+        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z),
+                     "f"(v.w)
+                     : "memory");
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();  // all inboxes are filled (release/acquire at cluster scope)
+    WG_TS(6);
+    if (reducer) {
+      const int W = out_padded ? 16 : 14;
+      const int o = out_padded ? 1 : 0;
+      const int units = valid_rows * 4 * kChunksPerCta;  // (row, pixel, owned chunk)
+      for (int u = threadIdx.x; u < units; u += kWorkerWarps * 32) {
+        const int lc = u % kChunksPerCta;
+        const int rp = u / kChunksPerCta;
+        const int row = rp >> 2, px = rp & 3;
+        const int chunk = (int)crank * kChunksPerCta + lc;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < CS; ++p) {
+          const float4 v = ld_shared_v4(recv_local + p * kInboxBytes + rp * (kChunksPerCta * 16) + lc * 16);
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+        const int cout0 = slice * KN + chunk * 4;
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cout0));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cout0));
+        acc.x = fmaf(sc.x, acc.x, sh.x);
+        acc.y = fmaf(sc.y, acc.y, sh.y);
+        acc.z = fmaf(sc.z, acc.z, sh.z);
+        acc.w = fmaf(sc.w, acc.w, sh.w);
+        if (relu) {
+          acc.x = fmaxf(acc.x, 0.f);
+          acc.y = fmaxf(acc.y, 0.f);
+          acc.z = fmaxf(acc.z, 0.f);
+          acc.w = fmaxf(acc.w, 0.f);
+        }
+        const int T = t0 + row;
+        const int n = T / 49, t = T % 49, ty = t / 7, tx = t % 7;
+        const int pix = (n * W + 2 * ty + o + (px >> 1)) * W + 2 * tx + o + (px & 1);
+        float* g = y + (size_t)pix * K + cout0;
+        *reinterpret_cast<float4*>(g) = acc;
+        if (out_padded) {
+          // zero border of the reference's 16x16 frame, written by whichever corner pixel of an edge tile is nearest
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int a = px >> 1, b = px & 1;
+          const ptrdiff_t dyb = (ty == 0 && a == 0) ? -(ptrdiff_t)W * K : ((ty == 6 && a == 1) ? (ptrdiff_t)W * K : 0);
+          const ptrdiff_t dxb = (tx == 0 && b == 0) ? -(ptrdiff_t)K : ((tx == 6 && b == 1) ? (ptrdiff_t)K : 0);
+          if (dyb != 0) *reinterpret_cast<float4*>(g + dyb) = z4;
+          if (dxb != 0) *reinterpret_cast<float4*>(g + dxb) = z4;
+          if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(g + dyb + dxb) = z4;
+        }
+      }
+    }
+    WG_TS(7);  // no remote access after the second barrier: CTAs may retire independently
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc<kTmemCols>(tmem_base);
+  if ((ablate & 64) && threadIdx.x == 0 && blockIdx.x == 0)
+    printf("wg ts (clk from entry): prologue %lld raw0 %lld acc_full %lld epi %lld csync1 %lld reduce %lld csync2 %lld exit %lld\n",
+           ts[1] - ts[0], ts[2] - ts[0], ts[3] - ts[0], ts[4] - ts[0], ts[5] - ts[0], ts[6] - ts[0], ts[7] - ts[0],
+           clock64() - ts[0]);
+#undef WG_TS
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -560,10 +694,65 @@ int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
 
+// Small batches: one item per cluster of CS CTAs (64-tile M-blocks), channel loop split CS ways.
+template <bool BF16, int CS>
+static int launch_wino_split(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift,
+                             float* y, int n_img, int C, int K, int relu, int out_padded, cudaStream_t stream) {
+  using S = WinoCfg<true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<true, BF16, CS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kTotal);
+    if (e != cudaSuccess) return WG_ERR_CUDA;
+    configured = true;
+  }
+  const int mv = 64;
+  const int n_items = ((n_img * 49 + mv - 1) / mv) * (K / S::KN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_items * CS));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int ablate = -1;  // debug only, see launch_wino
+  if (ablate < 0) {
+    const char* env = getenv("WG_DEBUG_ABLATE");
+    ablate = env ? atoi(env) : 0;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_bn_relu_kernel<true, BF16, CS>, tmap, u_img, scale, shift, y, n_img,
+                                     C, K, relu, out_padded, mv, ablate);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
 template <bool FOLD, bool BF16>
 static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift, float* y,
                        int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
   using S = WinoCfg<FOLD>;
+  if constexpr (FOLD) {
+    // latency mode when the whole batch is a handful of items: split the channel loop over a cluster
+    static int cs_env = -1;  // WG_WINO_CS=1 disables, 4|8 forces (when legal); default auto
+    if (cs_env < 0) {
+      const char* e = getenv("WG_WINO_CS");
+      cs_env = e ? atoi(e) : 0;
+    }
+    const int n_kv = C / (BF16 ? 16 : 8);
+    const int items64 = ((n_img * 49 + 63) / 64) * (K / S::KN);
+    int cs = 1;
+    if (cs_env != 1) {
+      if (n_kv % 8 == 0 && (cs_env == 8 || (cs_env == 0 && items64 * 8 <= max_ctas))) cs = 8;
+      else if (n_kv % 4 == 0 && (cs_env == 4 || (cs_env == 0 && items64 * 4 <= max_ctas))) cs = 4;
+    }
+    if (cs == 8)
+      return launch_wino_split<BF16, 8>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, stream);
+    if (cs == 4)
+      return launch_wino_split<BF16, 4>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, stream);
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<FOLD, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -262,6 +262,17 @@ int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   printf("sm_100 devices: %d\n", wg_device_count());
   if (wg_device_count() == 0) return 1;
+  if (argc > 1 && !strcmp(argv[1], "timen1")) {  // small-batch latency only
+    for (int n : {1, 2, 4, 8}) {
+      time_layer(0, n, 128, 128, 1);
+      time_layer(0, n, 256, 256, 1);
+    }
+    time_layer(1, 1, 512, 128, 1);
+    time_layer(1, 1, 128, 512, 0);
+    time_layer(1, 1, 1024, 256, 1);
+    time_layer(1, 1, 256, 1024, 0);
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "time3x3")) {  // timing only (used with WG_DEBUG_ABLATE experiments)
     time_layer(0, 256, 128, 128, 1);
     time_layer(0, 256, 256, 256, 1);
