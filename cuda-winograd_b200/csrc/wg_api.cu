@@ -77,6 +77,10 @@ struct wg_layer {
   float* d_y;
   size_t d_x_bytes, d_y_bytes;
   cudaStream_t stream;
+  // wg_run_host pipeline: copy-in / compute / copy-out streams and per-chunk events (created on first use)
+  cudaStream_t s_h2d, s_d2h;
+  cudaEvent_t ev_in[64], ev_done[64];
+  int n_events;
 };
 
 using namespace wg;
@@ -228,10 +232,42 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
     WG_CUDA(cudaMalloc(&L->d_y, yb));
     L->d_y_bytes = yb;
   }
-  WG_CUDA(cudaMemcpyAsync(L->d_x, x_host, xb, cudaMemcpyHostToDevice, L->stream));
-  int rc = wg_run(L, L->d_x, L->d_y, N, out_padded, L->stream);
-  if (rc != WG_OK) return rc;
-  WG_CUDA(cudaMemcpyAsync(y_host, L->d_y, yb, cudaMemcpyDeviceToHost, L->stream));
+  // Chunked three-stream pipeline: H2D of chunk c+1, the kernel on chunk c and D2H of chunk c-1 overlap (PCIe is
+  // full duplex), so a large batch costs ~max(copy-in, copy-out) instead of their sum plus the kernel. Host buffers
+  // should be pinned for the copies to be asynchronous; pageable memory still works, just without the overlap.
+  if (!L->s_h2d) {
+    WG_CUDA(cudaStreamCreateWithFlags(&L->s_h2d, cudaStreamNonBlocking));
+    WG_CUDA(cudaStreamCreateWithFlags(&L->s_d2h, cudaStreamNonBlocking));
+  }
+  static int chunk_env = -1;  // WG_HOST_CHUNK=<images per chunk> (experiments); default 32
+  if (chunk_env < 0) {
+    const char* e = getenv("WG_HOST_CHUNK");
+    chunk_env = e ? atoi(e) : 0;
+  }
+  int chunk = chunk_env > 0 ? chunk_env : 32;
+  if ((N + chunk - 1) / chunk > 64) chunk = (N + 63) / 64;
+  const int n_chunks = (N + chunk - 1) / chunk;
+  while (L->n_events < n_chunks) {
+    WG_CUDA(cudaEventCreateWithFlags(&L->ev_in[L->n_events], cudaEventDisableTiming));
+    WG_CUDA(cudaEventCreateWithFlags(&L->ev_done[L->n_events], cudaEventDisableTiming));
+    L->n_events++;
+  }
+  const size_t x_img = in_px * L->cin, y_img = out_px * L->cout;  // floats per image
+  for (int c = 0; c < n_chunks; ++c) {
+    const int n0 = c * chunk;
+    const int nc = (N - n0) < chunk ? (N - n0) : chunk;
+    WG_CUDA(cudaMemcpyAsync(L->d_x + (size_t)n0 * x_img, x_host + (size_t)n0 * x_img, (size_t)nc * x_img * sizeof(float),
+                            cudaMemcpyHostToDevice, L->s_h2d));
+    WG_CUDA(cudaEventRecord(L->ev_in[c], L->s_h2d));
+    WG_CUDA(cudaStreamWaitEvent(L->stream, L->ev_in[c], 0));
+    int rc = wg_run(L, L->d_x + (size_t)n0 * x_img, L->d_y + (size_t)n0 * y_img, nc, out_padded, L->stream);
+    if (rc != WG_OK) return rc;
+    WG_CUDA(cudaEventRecord(L->ev_done[c], L->stream));
+    WG_CUDA(cudaStreamWaitEvent(L->s_d2h, L->ev_done[c], 0));
+    WG_CUDA(cudaMemcpyAsync(y_host + (size_t)n0 * y_img, L->d_y + (size_t)n0 * y_img, (size_t)nc * y_img * sizeof(float),
+                            cudaMemcpyDeviceToHost, L->s_d2h));
+  }
+  WG_CUDA(cudaStreamSynchronize(L->s_d2h));
   WG_CUDA(cudaStreamSynchronize(L->stream));
   return WG_OK;
 }
@@ -243,6 +279,12 @@ int wg_destroy(wg_layer_t* L) {
   if (L->d_shift) cudaFree(L->d_shift);
   if (L->d_x) cudaFree(L->d_x);
   if (L->d_y) cudaFree(L->d_y);
+  for (int i = 0; i < L->n_events; ++i) {
+    cudaEventDestroy(L->ev_in[i]);
+    cudaEventDestroy(L->ev_done[i]);
+  }
+  if (L->s_h2d) cudaStreamDestroy(L->s_h2d);
+  if (L->s_d2h) cudaStreamDestroy(L->s_d2h);
   if (L->stream) cudaStreamDestroy(L->stream);
   free(L);
   return WG_OK;

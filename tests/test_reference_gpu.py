@@ -60,6 +60,24 @@ def test_reference_winograd_kernels_match_oracle(ref, seeded_data, mode, ch):
         assert np.abs(emu - out).max() < 5e-5
 
 
+def test_reference_test_c_runs_against_this_library(seeded_data):
+    """oracle/_ref/Test_dropin = the reference's unmodified Test.c built against include/ + libwinograd_b200.so
+    (oracle/Makefile). `./Test 2` = 100 calls of kernel_128_1_in() on the seeded files, reference output format."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "Test_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/Test_dropin not built (needs /root/reference at build time)")
+    out_dir, _ = seeded_data
+    r = subprocess.run([exe, "2"], cwd=os.path.dirname(out_dir), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("---- Iter:") == 100 and r.stdout.count("TotalTime = ") >= 100
+    m = re.search(r"Average Total Time: \[Mine: (\d+) us\], \[cuDNN: (\d+) us\]", r.stdout)
+    assert m and 0 < int(m.group(1)) < 5000 and int(m.group(2)) == 0
+    errs = [float(v) for v in re.findall(r"\[max_error: ([0-9.]+)\]", r.stdout)]
+    assert len(errs) == 100 and max(errs) < 1e-3 * 7e4     # golden_test2.bin is in data/: TF32 error of ~7e4-sized outputs
+
+
 _ONE_FN = {2: "ref_dump_128_1_in", 3: "ref_dump_128_1_out", 4: "ref_dump_256_1_in", 5: "ref_dump_256_1_out"}
 
 
