@@ -202,7 +202,36 @@ class Conv1x1Bn(_Layer):
         return (196, self.cin)
 
     def out_shape(self, out_padded=False):
-        return (196, self.cout)
+        # out_padded: the zero-bordered frame a following 3x3 layer reads (chain mode)
+        return (16, 16, self.cout) if out_padded else (196, self.cout)
+
+
+class Bottleneck:
+    """ResNet bottleneck chain 1x1 (Cin->C, +BN+ReLU) -> 3x3 (C->C, +BN+ReLU) -> 1x1 (C->Cout, +BN, no ReLU), the
+    three layer kinds of the reference chained the way its layouts suggest (SURVEY.md section 8f rank 1;
+    BASELINE.json configs[4]): the first 1x1 writes the zero-bordered 16x16 frame (Kernel128_winograd.cu:163,243
+    layout) that the 3x3 consumes, the 3x3 writes dense [N,14,14,C] = [N,196,C] for the last 1x1. Three kernel
+    launches, intermediates stay in L2/HBM, no padding or layout pass in between. The residual add is not part of
+    the reference (its `_out` kernels stop before it, Kernel128_one.cu:272) and is not done here."""
+
+    def __init__(self, w1, s1, b1, w3, s3, b3, w2, s2, b2, device=0, dtype=WG_TF32):
+        self.l1 = Conv1x1Bn(w1, s1, b1, relu=True, device=device)
+        self.l3 = Conv3x3BnRelu(w3, s3, b3, relu=True, device=device, dtype=dtype)
+        self.l2 = Conv1x1Bn(w2, s2, b2, relu=False, device=device)
+        assert self.l1.cout == self.l3.cin and self.l3.cout == self.l2.cin
+        self._bufs = {}
+
+    def __call__(self, x, out=None):
+        import torch
+        n = x.shape[0]
+        key = (n, x.device.index)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty((n, 16, 16, self.l1.cout), device=x.device),
+                               torch.empty((n, 14, 14, self.l3.cout), device=x.device))
+        frame, mid = self._bufs[key]
+        self.l1(x, out=frame, out_padded=True)
+        self.l3(frame, out=mid)
+        return self.l2(mid.view(n, 196, self.l3.cout), out=out)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -82,7 +82,7 @@ int run_case(const LegacyCase& c) {
 
   // 2. computing: one launch + device sync, host wall clock like the reference (Kernel128_winograd.cu:261-270)
   const uint64_t t1 = getTimeMicroseconds64();
-  rc = wg_run(layer, d_x, d_y, 1, 1, nullptr);
+  rc = wg_run(layer, d_x, d_y, 1, c.kind == 0 ? 1 : 0, nullptr);  // 3x3: the reference's padded 16x16 frame
   cudaError_t s = cudaDeviceSynchronize();
   const uint64_t t2 = getTimeMicroseconds64();
   printf("TotalTime = %d us\n", (int)(t2 - t1));

@@ -44,7 +44,8 @@ template <int BN, int CL>
 __global__ void __launch_bounds__(kOneThreads, 1)
 conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                       const float* __restrict__ w_img, const float* __restrict__ scale,
-                      const float* __restrict__ shift, long long m_rows, int Cin, int Cout, int relu) {
+                      const float* __restrict__ shift, float* __restrict__ y_padded, long long m_rows, int Cin,
+                      int Cout, int relu) {
   using S = OneSmem<BN>;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers
   extern __shared__ uint8_t smem_raw[];
@@ -180,6 +181,33 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           }
           st_shared_v4(dst + ((j ^ (lane & 7)) << 4), o.x, o.y, o.z, o.w);  // 128-byte swizzle
         }
+        if (y_padded != nullptr) {
+          // chain mode: write into the zero-bordered [N][16][16][Cout] frame a following 3x3 layer reads
+          // (Kernel128_winograd.cu:163,243 layout). Rows are not affine in m there, so no TMA: 8 lanes write one
+          // pixel's 128 bytes, 4 pixels per instruction; edge pixels also write their share of the border zeros.
+          __syncwarp();
+          const int j = lane & 7, rsub = lane >> 3;
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int r = i8 * 4 + rsub;
+            const long long m = (long long)mt * 128 + quad * 32 + r;
+            if (m < m_rows) {
+              const int n = (int)(m / 196), p = (int)(m % 196), oy = p / 14, ox = p % 14;
+              const float4 val =
+                  ld_shared_v4(stage_u32 + (chunk & 1) * S::kStageOutBytes + r * 128 + ((j ^ (r & 7)) << 4));
+              float* g = y_padded + ((size_t)(n * 16 + oy + 1) * 16 + ox + 1) * Cout + nt * BN + c0 + j * 4;
+              *reinterpret_cast<float4*>(g) = val;
+              const ptrdiff_t dyb = oy == 0 ? -(ptrdiff_t)16 * Cout : (oy == 13 ? (ptrdiff_t)16 * Cout : 0);
+              const ptrdiff_t dxb = ox == 0 ? -(ptrdiff_t)Cout : (ox == 13 ? (ptrdiff_t)Cout : 0);
+              if (dyb != 0) *reinterpret_cast<float4*>(g + dyb) = z4;
+              if (dxb != 0) *reinterpret_cast<float4*>(g + dxb) = z4;
+              if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(g + dyb + dxb) = z4;
+            }
+          }
+          __syncwarp();  // staging buffer free again
+          continue;
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && (long long)mt * 128 + quad * 32 < m_rows) {
@@ -237,8 +265,8 @@ int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int C
 
 template <int BN, int CL>
 static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
-                      const float* shift, long long m_rows, int Cin, int Cout, int relu, int max_ctas,
-                      cudaStream_t stream) {
+                      const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int relu,
+                      int max_ctas, cudaStream_t stream) {
   using S = OneSmem<BN>;
   static bool configured = false;
   if (!configured) {
@@ -264,14 +292,14 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL>, tmap, tmap_y, w_img, scale, shift, m_rows,
-                                     Cin, Cout, relu);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL>, tmap, tmap_y, w_img, scale, shift, y_padded,
+                                     m_rows, Cin, Cout, relu);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
-               const float* shift, long long m_rows, int Cin, int Cout, int BN, int relu, int max_ctas,
-               cudaStream_t stream) {
+               const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int BN, int relu,
+               int max_ctas, cudaStream_t stream) {
   // WG_ONE_CLUSTER=1|2|4 selects the cluster size. Default 1: measured on B200 (profiles/README.md) the multicast
   // variants are no faster (2) or slower (4) -- the limiter is per-SM ingest / shared-memory bandwidth, which
   // multicast does not reduce, not L2 output bandwidth.
@@ -283,7 +311,7 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
   }
   const int use = (m_rows <= 128) ? 1 : cl;  // a single M-tile has nobody to share the weight tile with
 #define WG_ONE(BN_, CL_) \
-  return launch_one<BN_, CL_>(tmap, tmap_y, w_img, scale, shift, m_rows, Cin, Cout, relu, max_ctas, stream)
+  return launch_one<BN_, CL_>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas, stream)
   if (BN == 128) {
     if (use == 1) WG_ONE(128, 1);
     if (use == 2) WG_ONE(128, 2);

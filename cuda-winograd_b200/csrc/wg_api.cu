@@ -200,8 +200,8 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,
                      L->dtype == WG_BF16, L->relu, out_padded ? 1 : 0, max_ctas, stream);
   else
-    rc = one_launch(L->tmap, L->tmap_out, L->d_filter, L->d_scale, L->d_shift, (long long)N * 196, L->cin, L->cout,
-                    L->tile_n, L->relu, max_ctas, stream);
+    rc = one_launch(L->tmap, L->tmap_out, L->d_filter, L->d_scale, L->d_shift, out_padded ? y : nullptr,
+                    (long long)N * 196, L->cin, L->cout, L->tile_n, L->relu, max_ctas, stream);
   g_launches++;
   if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
   return rc;
@@ -213,7 +213,7 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
   WG_CUDA(cudaGetDevice(&cur));
   if (cur != L->device) WG_CUDA(cudaSetDevice(L->device));
   const size_t in_px = L->kind == 0 ? 256 : 196;
-  const size_t out_px = L->kind == 0 ? (out_padded ? 256 : 196) : 196;
+  const size_t out_px = out_padded ? 256 : 196;
   const size_t xb = (size_t)N * in_px * L->cin * sizeof(float);
   const size_t yb = (size_t)N * out_px * L->cout * sizeof(float);
   if (L->d_x_bytes < xb) {

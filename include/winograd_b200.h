@@ -56,7 +56,9 @@ int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_co
 /* The hot path: ONE kernel launch (conv + BN + optional ReLU) on `cuda_stream` (a cudaStream_t, may be NULL),
  * asynchronous. x and y are DEVICE pointers on the layer's device, 16-byte aligned.
  * Replaces the timed region of kernel_128()/kernel_256() (three launches, Kernel128_winograd.cu:263-265) and of
- * kernel_*_1_in/out() (one launch, Kernel128_one.cu:98,316). out_padded is ignored for 1x1 layers. */
+ * kernel_*_1_in/out() (one launch, Kernel128_one.cu:98,316). For a 1x1 layer out_padded != 0 writes the same
+ * zero-bordered [N][16][16][Cout] frame instead of [N][196][Cout], i.e. exactly the input a following 3x3 layer
+ * reads, so bottleneck chains 1x1 -> 3x3 -> 1x1 need no padding pass in between. */
 int wg_run(wg_layer_t* layer, const float* x_dev, float* y_dev, int N, int out_padded, void* cuda_stream);
 
 /* Same, end to end with HOST buffers: H2D copy of x, wg_run, D2H copy of y, stream-synchronised on return.

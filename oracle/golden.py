@@ -90,6 +90,18 @@ def pad_frame(y):
     return out
 
 
+def bottleneck_chain(x, w1, s1, b1, w3, s3, b3, w2, s2, b2):
+    """1x1 (+BN+ReLU) -> zero-pad 1 -> 3x3 (+BN+ReLU) -> 1x1 (+BN, no ReLU): the three reference layer kinds chained
+    (Kernel128_one.cu:24-54 -> Kernel128_winograd.cu:28-213 -> Kernel128_one.cu:244-273). x [N,196,Cin] -> [N,196,Cout].
+    Unlike the reference's stand-alone 3x3 test input (random border, data_generator.py:49-53) the frame between the
+    layers has a ZERO border -- that is what the reference's own padded output frame provides (Kernel128_winograd.cu:243)."""
+    n = x.shape[0]
+    a = conv1x1_bn(x, w1, s1, b1, True)
+    frame = pad_frame(a.reshape(n, 14, 14, -1))
+    m = conv3x3_bn_relu(frame, w3, s3, b3, True)
+    return conv1x1_bn(m.reshape(n, 196, -1), w2, s2, b2, False)
+
+
 # ------------------------------------------------------------------------------------------ brute force (tiny shapes)
 def conv3x3_bn_relu_loops(x, w, scale, shift, relu=True):
     """Pure-Python loops, float64; only for tiny C, K in tests."""

@@ -207,6 +207,43 @@ def test_1x1_full_batch_256_properties(lib_loaded, torch_cuda, cin, cout, relu):
         np.testing.assert_allclose(y2 - sh, 2 * (yh[:4] - sh), rtol=1e-5, atol=1e-2)
 
 
+# ------------------------------------------------------------------------------ "next" row: the bottleneck chain
+@pytest.mark.parametrize("n,cin,cout", [(1, 512, 128), (3, 64, 256), (5, 1024, 256)])
+def test_1x1_padded_frame_output(lib_loaded, torch_cuda, n, cin, cout):
+    """1x1 with out_padded: the [N,16,16,Cout] frame a 3x3 layer reads -- interior == dense result, border == 0."""
+    torch = torch_cuda
+    rs = np.random.RandomState(500 + n)
+    x = ((rs.rand(n, 196, cin) - 0.5) * 2).astype(np.float32)
+    w = (rs.rand(cin, cout) - 0.5).astype(np.float32)
+    sc, sh = (rs.rand(cout) - 0.5).astype(np.float32), (rs.rand(cout) - 0.5).astype(np.float32)
+    layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu=True)
+    xd = torch.from_numpy(x).cuda()
+    dense = layer(xd)
+    frame = torch.full((n, 16, 16, cout), 7.0, device="cuda")
+    layer(xd, out=frame, out_padded=True)
+    assert torch.equal(frame[:, 1:15, 1:15].reshape(n, 196, cout), dense)
+    fr = frame.cpu().numpy()
+    assert np.all(fr[:, 0] == 0) and np.all(fr[:, 15] == 0) and np.all(fr[:, :, 0] == 0) and np.all(fr[:, :, 15] == 0)
+
+
+@pytest.mark.parametrize("n,cin,c,cout", [(1, 512, 128, 512), (4, 1024, 256, 1024), (32, 512, 128, 512)])
+def test_bottleneck_chain_vs_oracle(lib_loaded, torch_cuda, n, cin, c, cout):
+    """BASELINE.json configs[4]: 1x1 -> 3x3 -> 1x1 (+BN, ReLU on the first two) through three fused launches."""
+    torch = torch_cuda
+    rs = np.random.RandomState(600 + n)
+    x = (rs.rand(n, 196, cin) - 0.5).astype(np.float32)
+    w1 = ((rs.rand(cin, c) - 0.5) * 0.2).astype(np.float32)
+    w3 = ((rs.rand(c, c, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    w2 = ((rs.rand(c, cout) - 0.5) * 0.2).astype(np.float32)
+    bn = [((rs.rand(k) + 0.5).astype(np.float32), (rs.rand(k) - 0.3).astype(np.float32)) for k in (c, c, cout)]
+    block = lib_loaded.Bottleneck(w1, *bn[0], w3, *bn[1], w2, *bn[2])
+    before = lib_loaded.launch_count()
+    y = block(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert lib_loaded.launch_count() == before + 3
+    gold = golden.bottleneck_chain(x, w1, *bn[0], w3, *bn[1], w2, *bn[2])
+    assert golden.rel_err(y, gold) <= 3 * TOL_TF32      # three TF32 layers in sequence
+
+
 # ----------------------------------------------------------------------------------------------------- API behaviour
 def test_host_buffer_call_equals_device_call_and_counts_launches(lib_loaded, torch_cuda):
     torch = torch_cuda
