@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libwinograd_b200.so")
 
-WG_TF32, WG_BF16 = 0, 1
+WG_TF32, WG_BF16, WG_FP16 = 0, 1, 2
 
 # every symbol include/winograd_b200.h, include/wg_legacy.h and include/util.h declare
 ABI_SYMBOLS = (

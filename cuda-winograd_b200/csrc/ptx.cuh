@@ -287,6 +287,13 @@ __device__ __forceinline__ void st_shared_bf16x4(uint32_t addr, float a, float b
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(d), "f"(c));
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
 }
+// four fp32 -> four fp16 (round to nearest even), one 8-byte shared store
+__device__ __forceinline__ void st_shared_f16x4(uint32_t addr, float a, float b, float c, float d) {
+  uint32_t lo, hi;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(d), "f"(c));
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));

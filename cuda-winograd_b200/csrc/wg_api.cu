@@ -101,9 +101,9 @@ static int check_device(int device, int* num_sms) {
 static int create_common(wg_layer_t** out, int kind, int cin, int cout, const float* w, size_t w_elems,
                          const float* scale, const float* shift, int relu, wg_dtype_t dtype, int device) {
   if (!out || !w || !scale || !shift) return WG_ERR_ARG;
-  if (dtype != WG_TF32 && dtype != WG_BF16) return WG_ERR_ARG;
+  if (dtype != WG_TF32 && dtype != WG_BF16 && dtype != WG_FP16) return WG_ERR_ARG;
   // bf16 operands: 3x3 only (the 1x1 activation operand goes HBM -> TMA -> MMA untouched, there is nothing to convert it)
-  if (dtype == WG_BF16 && (kind != 0 || cin % 16 != 0 || cout % 64 != 0)) return WG_ERR_ARG;
+  if (dtype != WG_TF32 && (kind != 0 || cin % 16 != 0 || cout % 64 != 0)) return WG_ERR_ARG;
   int num_sms = 0;
   int rc = check_device(device, &num_sms);
   if (rc != WG_OK) return rc;
@@ -122,7 +122,7 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   float* d_w = nullptr;
   size_t filter_elems = 0;
   if (kind == 0) {
-    L->tile_n = (dtype == WG_BF16) ? 64 : ((g_wino_kn == 32 || cout % 64 != 0) ? 32 : 64);
+    L->tile_n = (dtype != WG_TF32) ? 64 : ((g_wino_kn == 32 || cout % 64 != 0) ? 32 : 64);
     filter_elems = (size_t)16 * cin * cout;
   } else {
     L->tile_n = (cout % 256 == 0) ? 256 : 128;
@@ -144,7 +144,7 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   WG_TRY(cudaMemcpyAsync(d_w, w, w_elems * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_scale, scale, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
-  rc = kind == 0 ? filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, dtype == WG_BF16, L->stream)
+  rc = kind == 0 ? filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)dtype, L->stream)
                  : weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
   g_launches++;
   if (rc != WG_OK) {
@@ -198,7 +198,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   int rc;
   if (L->kind == 0)
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,
-                     L->dtype == WG_BF16, L->relu, out_padded ? 1 : 0, max_ctas, stream);
+                     L->dtype, L->relu, out_padded ? 1 : 0, max_ctas, stream);
   else
     rc = one_launch(L->tmap, L->tmap_out, L->d_filter, L->d_scale, L->d_shift, out_padded ? y : nullptr,
                     (long long)N * 196, L->cin, L->cout, L->tile_n, L->relu, max_ctas, stream);

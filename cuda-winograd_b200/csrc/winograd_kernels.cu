@@ -25,6 +25,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace wg {
@@ -82,7 +83,7 @@ template <bool FOLD, bool BF16 = false, int CS = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* __restrict__ u_img,
                        const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
-                       int n_img, int C, int K, int relu, int out_padded, int mv, int ablate) {
+                       int n_img, int C, int K, int relu, int out_padded, int mv, int fp16, int ablate) {
   static_assert(!BF16 || FOLD, "the bf16 variant is built on the folded accumulation");
   static_assert(CS == 1 || FOLD, "split-C is built on the folded accumulation");
   using S = WinoCfg<FOLD>;
@@ -179,9 +180,9 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t kFmt = BF16 ? kFmtBF16 : kFmtTF32;
-      constexpr uint32_t idesc = make_idesc(kFmt, 128, KN);
-      constexpr uint32_t idesc_neg = make_idesc(kFmt, 128, KN, 1);  // D += (-A) * B
+      const uint32_t fmt = BF16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
+      const uint32_t idesc = make_idesc(fmt, 128, KN);
+      const uint32_t idesc_neg = make_idesc(fmt, 128, KN, 1);  // D += (-A) * B
       const uint32_t v_base = smem_u32(smem + S::kOffV);
       const uint32_t u_base = smem_u32(smem + S::kOffU);
       uint32_t vs = 0, vph = 0, us = 0, uph = 0, aph = 0;
@@ -327,14 +328,25 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
         if constexpr (BF16) {
           // 4 channels -> 8 bytes at [k-chunk sub][row][c*8]
           const uint32_t bdst = v_base + vs * S::kVBytes + sub * S::kVLbo + trow * 16 + c * 8;
-          if (!(ablate & 2))
+          if (ablate & 2) {
+          } else if (fp16) {  // warp-uniform: fp16 operands (10-bit mantissa like TF32, range +-65504)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
-            st_shared_bf16x4(bdst + (4 * i + 0) * S::kVPerXi, a0.x - a2.x, a0.y - a2.y, a0.z - a2.z, a0.w - a2.w);
-            st_shared_bf16x4(bdst + (4 * i + 1) * S::kVPerXi, a1.x + a2.x, a1.y + a2.y, a1.z + a2.z, a1.w + a2.w);
-            st_shared_bf16x4(bdst + (4 * i + 2) * S::kVPerXi, a2.x - a1.x, a2.y - a1.y, a2.z - a1.z, a2.w - a1.w);
-            st_shared_bf16x4(bdst + (4 * i + 3) * S::kVPerXi, a1.x - a3.x, a1.y - a3.y, a1.z - a3.z, a1.w - a3.w);
+            for (int i = 0; i < 4; ++i) {
+              const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
+              st_shared_f16x4(bdst + (4 * i + 0) * S::kVPerXi, a0.x - a2.x, a0.y - a2.y, a0.z - a2.z, a0.w - a2.w);
+              st_shared_f16x4(bdst + (4 * i + 1) * S::kVPerXi, a1.x + a2.x, a1.y + a2.y, a1.z + a2.z, a1.w + a2.w);
+              st_shared_f16x4(bdst + (4 * i + 2) * S::kVPerXi, a2.x - a1.x, a2.y - a1.y, a2.z - a1.z, a2.w - a1.w);
+              st_shared_f16x4(bdst + (4 * i + 3) * S::kVPerXi, a1.x - a3.x, a1.y - a3.y, a1.z - a3.z, a1.w - a3.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
+              st_shared_bf16x4(bdst + (4 * i + 0) * S::kVPerXi, a0.x - a2.x, a0.y - a2.y, a0.z - a2.z, a0.w - a2.w);
+              st_shared_bf16x4(bdst + (4 * i + 1) * S::kVPerXi, a1.x + a2.x, a1.y + a2.y, a1.z + a2.z, a1.w + a2.w);
+              st_shared_bf16x4(bdst + (4 * i + 2) * S::kVPerXi, a2.x - a1.x, a2.y - a1.y, a2.z - a1.z, a2.w - a1.w);
+              st_shared_bf16x4(bdst + (4 * i + 3) * S::kVPerXi, a1.x - a3.x, a1.y - a3.y, a1.z - a3.z, a1.w - a3.w);
+            }
           }
         } else if (!(ablate & 2))
 #pragma unroll
@@ -669,7 +681,10 @@ __global__ void filter_transform_f2x2_kernel(const float* __restrict__ w_kcrs, v
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = fold ? ((j >> 1) * 8 + i * 2 + (j & 1)) : (4 * i + j);
-      if (bf16)
+      if (bf16 == 2)
+        static_cast<__half*>(u_img_v)[stage_bf + p * point_halfs + ((size_t)chunk_bf * KN + kn) * 8 + e_bf] =
+            __float2half_rn(u[j]);
+      else if (bf16)
         u_bf[stage_bf + p * point_halfs + ((size_t)chunk_bf * KN + kn) * 8 + e_bf] = __float2bfloat16_rn(u[j]);
       else
         u_img[stage + p * point_floats + ((size_t)chunk * KN + kn) * 4 + e] = to_tf32_rn(u[j]);
@@ -697,7 +712,7 @@ int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
 // Small batches: one item per cluster of CS CTAs (64-tile M-blocks), channel loop split CS ways.
 template <bool BF16, int CS>
 static int launch_wino_split(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift,
-                             float* y, int n_img, int C, int K, int relu, int out_padded, cudaStream_t stream) {
+                             float* y, int n_img, int C, int K, int relu, int out_padded, int fp16, cudaStream_t stream) {
   using S = WinoCfg<true>;
   static bool configured = false;
   if (!configured) {
@@ -726,13 +741,13 @@ static int launch_wino_split(const CUtensorMap& tmap, const void* u_img, const f
     ablate = env ? atoi(env) : 0;
   }
   cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_bn_relu_kernel<true, BF16, CS>, tmap, u_img, scale, shift, y, n_img,
-                                     C, K, relu, out_padded, mv, ablate);
+                                     C, K, relu, out_padded, mv, fp16, ablate);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 template <bool FOLD, bool BF16>
 static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift, float* y,
-                       int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+                       int n_img, int C, int K, int relu, int out_padded, int fp16, int max_ctas, cudaStream_t stream) {
   using S = WinoCfg<FOLD>;
   if constexpr (FOLD) {
     // latency mode when the whole batch is a handful of items: split the channel loop over a cluster
@@ -749,9 +764,9 @@ static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* 
       else if (n_kv % 4 == 0 && (cs_env == 4 || (cs_env == 0 && items64 * 4 <= max_ctas))) cs = 4;
     }
     if (cs == 8)
-      return launch_wino_split<BF16, 8>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, stream);
+      return launch_wino_split<BF16, 8>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, fp16, stream);
     if (cs == 4)
-      return launch_wino_split<BF16, 4>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, stream);
+      return launch_wino_split<BF16, 4>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, fp16, stream);
   }
   static bool configured = false;
   if (!configured) {
@@ -794,21 +809,23 @@ static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* 
     ablate = e ? atoi(e) : 0;
   }
   wino3x3_bn_relu_kernel<FOLD, BF16><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K,
-                                                                            relu, out_padded, mv, ablate);
+                                                                            relu, out_padded, mv, fp16, ablate);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_launch(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift, float* y,
                 int n_img, int C, int K, int KN, int bf16, int relu, int out_padded, int max_ctas,
                 cudaStream_t stream) {
+  // bf16: 0 = TF32 operands, 1 = bf16 operands, 2 = fp16 operands (same 16-bit kernel, other format code)
   if (bf16) {
     if (KN != 64 || C % 16 != 0) return WG_ERR_ARG;
-    return launch_wino<true, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+    return launch_wino<true, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, bf16 == 2, max_ctas,
+                                   stream);
   }
   if (KN == 64)
-    return launch_wino<true, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+    return launch_wino<true, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, 0, max_ctas, stream);
   if (KN == 32)
-    return launch_wino<false, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+    return launch_wino<false, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, 0, max_ctas, stream);
   return WG_ERR_ARG;
 }
 

@@ -30,7 +30,12 @@ extern "C" {
 
 typedef struct wg_layer wg_layer_t; /* opaque: device copies of the packed filter, folded BN, cached tensor maps */
 
-typedef enum { WG_TF32 = 0, WG_BF16 = 1 } wg_dtype_t;
+/* operand type of the tensor-core GEMMs (inputs, outputs and accumulation are always fp32):
+ *   WG_TF32  10-bit mantissa, fp32 range                      tolerance 1e-3   all layers (default)
+ *   WG_BF16   7-bit mantissa, fp32 range                      tolerance 1e-2   3x3 layers, C % 16 == 0, K % 64 == 0
+ *   WG_FP16  10-bit mantissa, |V| = |sum of 4 inputs| < 65504  tolerance 1e-3   3x3 layers, same constraints;
+ *            TF32-class accuracy at bf16 speed for bounded activations (e.g. post-BN/ReLU feature maps) */
+typedef enum { WG_TF32 = 0, WG_BF16 = 1, WG_FP16 = 2 } wg_dtype_t;
 
 typedef enum {
   WG_OK = 0,

@@ -117,6 +117,17 @@ def test_3x3_bf16_operand_variant(lib_loaded, torch_cuda, n, c, k):
     assert np.all(yp[:, 0] == 0) and np.all(yp[:, :, 15] == 0)
 
 
+@pytest.mark.parametrize("n,c,k", [(1, 128, 128), (2, 256, 256), (5, 48, 128), (64, 128, 128)])
+def test_3x3_fp16_operand_variant(lib_loaded, torch_cuda, n, c, k):
+    """fp16 V/U operands: the same 10-bit mantissa as TF32 (so the TF32 bar, 1e-3) at the bf16 variant's speed; valid
+    while |V| < 65504, which the reference's data distributions (and post-BN/ReLU feature maps) satisfy by far."""
+    torch = torch_cuda
+    x, w, sc, sh = _rand3x3(np.random.RandomState(700 + n), n, c, k)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=lib_loaded.WG_FP16)
+    y = layer(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert golden.rel_err(y, golden.conv3x3_bn_relu(x, w, sc, sh, True)) <= TOL_TF32
+
+
 def test_bf16_is_rejected_where_it_does_not_exist(lib_loaded):
     with pytest.raises(lib_loaded.WinogradB200Error):   # the 1x1 activation operand is never touched by CUDA cores
         lib_loaded._Layer.__init__(lib_loaded.Conv1x1Bn.__new__(lib_loaded.Conv1x1Bn), 32, 128,
