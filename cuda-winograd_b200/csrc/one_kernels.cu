@@ -268,12 +268,15 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
                       const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int relu,
                       int max_ctas, cudaStream_t stream) {
   using S = OneSmem<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
+  if (!(configured & dev_bit_)) {
     cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
-    configured = true;
+    configured |= dev_bit_;
   }
   const long long n_mtiles = (m_rows + 127) / 128;
   const long long n_items = ((n_mtiles + CL - 1) / CL) * (Cout / BN);

@@ -714,12 +714,15 @@ template <bool BF16, int CS>
 static int launch_wino_split(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift,
                              float* y, int n_img, int C, int K, int relu, int out_padded, int fp16, cudaStream_t stream) {
   using S = WinoCfg<true>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
+  if (!(configured & dev_bit_)) {
     cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<true, BF16, CS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
-    configured = true;
+    configured |= dev_bit_;
   }
   const int mv = 64;
   const int n_items = ((n_img * 49 + mv - 1) / mv) * (K / S::KN);
@@ -768,12 +771,15 @@ static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* 
     if (cs == 4)
       return launch_wino_split<BF16, 4>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, fp16, stream);
   }
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
+  if (!(configured & dev_bit_)) {
     cudaError_t e = cudaFuncSetAttribute(wino3x3_bn_relu_kernel<FOLD, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
-    configured = true;
+    configured |= dev_bit_;
   }
   // Tiles per M-block: the MMA is always M=128, but only `mv` rows carry tiles. A smaller mv costs MMA efficiency
   // (the tensor pipe has slack) and buys an item count that fills the last wave: per item, ~55 % of the cost (MMA

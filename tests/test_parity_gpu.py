@@ -273,6 +273,26 @@ def test_host_buffer_call_equals_device_call_and_counts_launches(lib_loaded, tor
     np.testing.assert_array_equal(y_s.cpu().numpy(), y_dev)
 
 
+def test_layers_on_two_devices_in_one_process(lib_loaded, torch_cuda):
+    """The ABI takes a device ordinal per layer: two layers on two GPUs driven from one process (needs >= 2 GPUs)."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("single-GPU box")
+    x, w, sc, sh = _rand3x3(np.random.RandomState(11), 16, 64, 64)
+    gold = golden.conv3x3_bn_relu(x, w, sc, sh)
+    for dev in (0, 1):
+        layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, device=dev)
+        y = layer(torch.from_numpy(x).to(f"cuda:{dev}")).cpu().numpy()
+        assert golden.rel_err(y, gold) <= TOL_TF32
+        one = lib_loaded.Conv1x1Bn(np.ascontiguousarray(w[:, :, 0, 0].T[:, :64].repeat(2, axis=1)),
+                                   np.ones(128, np.float32), np.zeros(128, np.float32), False, device=dev)
+        x1 = np.ascontiguousarray(x[:, 1:15, 1:15].reshape(16, 196, 64))
+        y1 = one(torch.from_numpy(x1).to(f"cuda:{dev}")).cpu().numpy()
+        g1 = golden.conv1x1_bn(x1, np.ascontiguousarray(w[:, :, 0, 0].T[:, :64].repeat(2, axis=1)),
+                               np.ones(128, np.float32), np.zeros(128, np.float32), False)
+        assert golden.rel_err(y1, g1) <= TOL_TF32
+
+
 def test_legacy_entry_points_and_test_binary(lib_loaded, seeded_data, tmp_path):
     """kernel_128() ... kernel_256_1_out(): read data/*.bin from the CWD, return (mine_us << 16) | baseline_us
     (Kernel128_winograd.cu:433); ./Test n prints the reference's lines (Test.c:23,50-53)."""
