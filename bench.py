@@ -238,6 +238,15 @@ def run_gpu(args):
             line["with_output_allgather"] = {"ms_per_step": gather_ms, "value": world * n / (gather_ms * 1e-3),
                                              "unit": UNIT, "collective": "nccl all_gather_into_tensor of fp32 output"}
         if world == 1:
+            # BASELINE.json's metric has two halves: us/layer at N=1 and throughput at N=256, for the six README
+            # shapes. The headline above is one of them; the rest ride along (outside the timed region, 60 launches each).
+            del xs, ys, xh, yh
+            torch.cuda.empty_cache()
+            line["all_shapes"] = [
+                {"layer": f"{r['kind']} {r['cin']}->{r['cout']}" + ("+relu" if r["relu"] else ""), "n": r["n"],
+                 "us_per_layer": round(r["us_per_layer"], 2), "images_per_s": round(r["images_per_s"]),
+                 "frac_tf32_peak": round(r["frac_tf32_peak"], 4), "frac_hbm_peak": round(r["frac_hbm_peak"], 4)}
+                for r in measure_shapes(wg, dev, iters=60, sets_n256=3, verbose=False)]
             line["cpu_baseline"] = cpu_baseline(budget_s=12.0)
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -326,14 +335,11 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- all README shapes
-def run_all_shapes(args):
+def measure_shapes(wg, dev, iters=200, sets_n256=N_SETS, verbose=True):
     """Every README shape: N=1 latency (L2-warm, like the reference's loop) and N=256 throughput (rotating buffers),
-    CUDA events. Writes profiles/all_shapes_latest.json; one summary line per shape on stderr."""
+    CUDA events. Returns one row per (shape, N)."""
     import numpy as np
     import torch
-    import wg_loader
-    wg = wg_loader.load()
-    dev = torch.device("cuda", 0)
     pk = peaks()
     rows = []
     shapes = [("3x3", 128, 128, True), ("3x3", 256, 256, True), ("1x1", 512, 128, True), ("1x1", 128, 512, False),
@@ -342,42 +348,52 @@ def run_all_shapes(args):
         rs = np.random.RandomState(0)
         if kind == "3x3":
             layer = wg.Conv3x3BnRelu((rs.rand(cout, cin, 3, 3) - 0.5).astype(np.float32),
-                                     rs.rand(cout).astype(np.float32), rs.rand(cout).astype(np.float32), relu)
+                                     rs.rand(cout).astype(np.float32), rs.rand(cout).astype(np.float32), relu,
+                                     device=dev.index)
             in_shape, out_shape, taps = (16, 16, cin), (14, 14, cout), 9
         else:
             layer = wg.Conv1x1Bn((rs.rand(cin, cout) - 0.5).astype(np.float32), rs.rand(cout).astype(np.float32),
-                                 rs.rand(cout).astype(np.float32), relu)
+                                 rs.rand(cout).astype(np.float32), relu, device=dev.index)
             in_shape, out_shape, taps = (196, cin), (196, cout), 1
         for n in (1, 256):
-            sets = 1 if n == 1 else N_SETS
+            sets = 1 if n == 1 else sets_n256
             xs = [torch.rand((n,) + in_shape, device=dev) - 0.5 for _ in range(sets)]
             ys = [torch.empty((n,) + out_shape, device=dev) for _ in range(sets)]
             for i in range(5):
                 layer(xs[i % sets], out=ys[i % sets])
-            torch.cuda.synchronize()
-            iters = 200
+            torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(iters):
                 layer(xs[i % sets], out=ys[i % sets])
             e1.record()
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(dev)
             us = e0.elapsed_time(e1) * 1e3 / iters
             flops = 2.0 * 196 * cin * cout * taps * n
-            byts = (np.prod(in_shape) + np.prod(out_shape)) * 4.0 * n + cin * cout * taps * 4.0
+            byts = float(np.prod(in_shape) + np.prod(out_shape)) * 4.0 * n + cin * cout * taps * 4.0
             row = dict(kind=kind, cin=cin, cout=cout, relu=relu, n=n, us_per_layer=us,
                        images_per_s=n / (us * 1e-6), tflops_direct_equiv=flops / us * 1e-6,
                        hbm_gbs_algorithmic=byts / us * 1e-3,
                        frac_tf32_peak=flops / us * 1e-6 / (pk["bf16_sustained"] / 2),
                        frac_hbm_peak=byts / us * 1e-3 / pk["hbm"])
             rows.append(row)
-            print(f"{kind} {cin:>4}->{cout:<4} N={n:<3} {us:9.2f} us  {row['tflops_direct_equiv']:7.1f} TF/s "
-                  f"({100 * row['frac_tf32_peak']:.1f}% tf32)  {row['hbm_gbs_algorithmic']:7.0f} GB/s "
-                  f"({100 * row['frac_hbm_peak']:.1f}% hbm)", file=sys.stderr)
+            if verbose:
+                print(f"{kind} {cin:>4}->{cout:<4} N={n:<3} {us:9.2f} us  {row['tflops_direct_equiv']:7.1f} TF/s "
+                      f"({100 * row['frac_tf32_peak']:.1f}% tf32)  {row['hbm_gbs_algorithmic']:7.0f} GB/s "
+                      f"({100 * row['frac_hbm_peak']:.1f}% hbm)", file=sys.stderr)
             del xs, ys
+        layer.close()
+    return rows
+
+
+def run_all_shapes(args):
+    """`--all-shapes`: the table above with 200 launches per cell; writes gpurun_out/all_shapes_latest.json."""
+    import torch
+    import wg_loader
+    rows = measure_shapes(wg_loader.load(), torch.device("cuda", 0))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "all_shapes_latest.json"), "w") as f:
-        json.dump(dict(peaks=pk, rows=rows), f, indent=1)
+        json.dump(dict(peaks=peaks(), rows=rows), f, indent=1)
     print(json.dumps({"all_shapes": rows}))
 
 
