@@ -233,6 +233,21 @@ class Bottleneck:
         self.l3(frame, out=mid)
         return self.l2(mid.view(n, 196, self.l3.cout), out=out)
 
+    def capture(self, x, out=None):
+        """Record the three launches on `x` into a CUDA graph (the launches are plain stream work: no allocation, no
+        sync inside wg_run) and return (replay, out): `replay()` re-runs the chain on the current contents of `x`
+        with ONE graph launch -- the launch-bound small-batch case. `x` and `out` must stay alive and in place."""
+        import torch
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty((n, 196, self.l2.cout), device=x.device)
+        self(x, out=out)                      # warm-up: tensor maps cached, kernels configured, buffers allocated
+        torch.cuda.synchronize(x.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self(x, out=out)
+        return graph.replay, out
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # The reference's six entry points, same names, same behaviour (read data/*.bin from the CWD, print the same lines,

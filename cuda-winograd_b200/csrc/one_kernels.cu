@@ -227,6 +227,174 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// Small batches (latency): split-K over a thread-block cluster. With M = N*196 rows there are only a handful of
+// 128-row tiles, and one CTA pulling its whole K extent is limited by per-SM ingest (~36 B/clk). Here the CS CTAs of
+// a cluster share one (M-tile, N-tile), each runs Cin/CS of the channel loop, then every CTA pushes the rows of its
+// partial accumulator to the CTA that owns them (st.shared::cluster into per-source inboxes laid over the now idle
+// stage buffers), one cluster barrier, fixed-order local sum, scale/shift/ReLU, 128-bit global stores.
+template <int BN, int CS>
+__global__ void __launch_bounds__(kOneThreads, 1)
+conv1x1_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ w_img,
+                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
+                      long long m_rows, int Cin, int Cout, int relu, int out_padded) {
+  using S = OneSmem<BN>;
+  constexpr uint32_t kTmemCols = BN;
+  constexpr int RO = 128 / CS;  // rows of the tile each CTA finishes
+  static_assert((size_t)128 * BN * 4 <= S::kOffOut, "inboxes must fit in the stage buffers");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* full = bars;
+  uint64_t* empty = full + S::kStages;
+  uint64_t* acc_full = empty + S::kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
+  const uint32_t crank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    for (int i = 0; i < S::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_kb = Cin / kBK;
+  const int n_ntiles = Cout / BN;
+  const int item = blockIdx.x / CS;  // one (M-tile, N-tile) per cluster
+  const int nt = item % n_ntiles;
+  const int mt = item / n_ntiles;
+  const int kb_per = n_kb / CS, kb0 = (int)crank * kb_per;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint8_t* b_src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)nt * n_kb * S::kBBytes;
+      uint32_t st = 0, ph = 0;
+      for (int kb = kb0; kb < kb0 + kb_per; ++kb) {
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], S::kABytes + S::kBBytes);
+        tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, kb * kBK, mt * 128, &full[st]);
+        tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * S::kBBytes, S::kBBytes, &full[st]);
+        if (++st == S::kStages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, BN);
+      const uint32_t a_base = smem_u32(smem + S::kOffA);
+      const uint32_t b_base = smem_u32(smem + S::kOffB);
+      uint32_t st = 0, ph = 0;
+      for (int kb = 0; kb < kb_per; ++kb) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) {
+          const uint64_t a_desc = make_smem_desc(a_base + st * S::kABytes + k * 32, 0, 1024, kLayoutSW128);
+          const uint64_t b_desc = make_smem_desc(b_base + st * S::kBBytes + k * 32, 0, 1024, kLayoutSW128);
+          umma_tf32_ss(tmem_base, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[st]);
+        if (++st == S::kStages) { st = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    mbar_wait(acc_full, 0);  // this CTA's MMAs are complete: its stage buffers are idle from here on
+    tc_fence_after();
+  }
+  __syncwarp();
+  cluster_sync_all();  // every CTA's stage buffers are idle -> they become the inboxes
+
+  const uint32_t inbox_local = smem_u32(smem);  // [source CTA][RO rows][BN] fp32
+  if (warp >= 2) {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // row of the tile = TMEM lane
+    const int owner = r / RO, lr = r % RO;
+    const bool valid = (long long)mt * 128 + r < m_rows;  // rows beyond M are never pushed (nor summed)
+    const bool warp_has_rows = (long long)mt * 128 + quad * 32 < m_rows;  // warp-uniform
+    uint32_t dst;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                 : "=r"(dst)
+                 : "r"(inbox_local + (uint32_t)((crank * RO + lr) * BN * 4)), "r"(owner));
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    if (warp_has_rows) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld_x16(taddr + c0, v);  // warp-collective: all 32 lanes, valid row or not
+        tmem_ld_x16(taddr + c0 + 16, v + 16);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (c0 + 4 * j) * 4),
+                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                         : "memory");
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncwarp();
+  cluster_sync_all();  // inboxes complete
+
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;  // 0..127
+    constexpr int kChunks = BN / 4;  // 16-byte chunks per row
+    for (int u = t; u < RO * kChunks; u += 128) {
+      const int lr = u / kChunks, ch = u % kChunks;
+      const long long m = (long long)mt * 128 + crank * RO + lr;
+      if (m >= m_rows) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < CS; ++p) {
+        const float4 v = ld_shared_v4(inbox_local + (uint32_t)(((p * RO + lr) * BN + ch * 4) * 4));
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
+      }
+      const int col = nt * BN + ch * 4;
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + col));
+      const float4 h4 = __ldg(reinterpret_cast<const float4*>(shift + col));
+      acc.x = fmaf(s4.x, acc.x, h4.x);
+      acc.y = fmaf(s4.y, acc.y, h4.y);
+      acc.z = fmaf(s4.z, acc.z, h4.z);
+      acc.w = fmaf(s4.w, acc.w, h4.w);
+      if (relu) {
+        acc.x = fmaxf(acc.x, 0.f);
+        acc.y = fmaxf(acc.y, 0.f);
+        acc.z = fmaxf(acc.z, 0.f);
+        acc.w = fmaxf(acc.w, 0.f);
+      }
+      if (!out_padded) {
+        *reinterpret_cast<float4*>(y + (size_t)m * Cout + col) = acc;
+      } else {
+        const int n = (int)(m / 196), p = (int)(m % 196), oy = p / 14, ox = p % 14;
+        float* g = y + ((size_t)(n * 16 + oy + 1) * 16 + ox + 1) * Cout + col;
+        *reinterpret_cast<float4*>(g) = acc;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const ptrdiff_t dyb = oy == 0 ? -(ptrdiff_t)16 * Cout : (oy == 13 ? (ptrdiff_t)16 * Cout : 0);
+        const ptrdiff_t dxb = ox == 0 ? -(ptrdiff_t)Cout : (ox == 13 ? (ptrdiff_t)Cout : 0);
+        if (dyb != 0) *reinterpret_cast<float4*>(g + dyb) = z4;
+        if (dxb != 0) *reinterpret_cast<float4*>(g + dxb) = z4;
+        if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(g + dyb + dxb) = z4;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
 // Once per layer: W[Cin][Cout] (reference layout, Kernel128_one.cu:41-48) -> per (n-tile, 32-channel block) the
 // K-major 128-byte-swizzled shared-memory image [BN couts][32 cin], RN-rounded to TF32. The reference's cuDNN half
 // does the same [Cin][Cout] -> [Cout][Cin] transpose on the host (util.c:15-26, Kernel128_one.cu:131).
@@ -300,9 +468,64 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
+template <int BN, int CS>
+static int launch_splitk(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
+                         int out_padded, long long m_rows, int Cin, int Cout, int relu, cudaStream_t stream) {
+  using S = OneSmem<BN>;
+  static unsigned long long configured = 0;
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
+  if (!(configured & dev_bit_)) {
+    cudaError_t e = cudaFuncSetAttribute(conv1x1_splitk_kernel<BN, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)S::kTotal);
+    if (e != cudaSuccess) return WG_ERR_CUDA;
+    configured |= dev_bit_;
+  }
+  const long long n_items = ((m_rows + 127) / 128) * (Cout / BN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_items * CS));
+  cfg.blockDim = dim3(kOneThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_splitk_kernel<BN, CS>, tmap, w_img, scale, shift, y, m_rows, Cin,
+                                     Cout, relu, out_padded);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
 int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
-               const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int BN, int relu,
+               const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout, int BN, int relu,
                int max_ctas, cudaStream_t stream) {
+  float* y_padded = out_padded ? y : nullptr;
+  {
+    // latency mode: a handful of tiles and a long channel loop -> split K over a cluster (WG_ONE_SPLITK=1 disables)
+    static int sk_env = -1;
+    if (sk_env < 0) {
+      const char* e = getenv("WG_ONE_SPLITK");
+      sk_env = e ? atoi(e) : 0;
+    }
+    const int n_kb = Cin / kBK;
+    const long long n_items = ((m_rows + 127) / 128) * (Cout / BN);
+    int cs = 1;
+    if (sk_env != 1 && n_kb >= 16) {  // Cin >= 512; measured: with Cin = 256 the reduction costs more than it saves
+      if (n_kb % 8 == 0 && n_items * 8 <= max_ctas) cs = 8;
+      else if (n_kb % 4 == 0 && n_items * 4 <= max_ctas) cs = 4;
+    }
+#define WG_SPLITK(BN_, CS_) \
+  return launch_splitk<BN_, CS_>(tmap, w_img, scale, shift, y, out_padded, m_rows, Cin, Cout, relu, stream)
+    if (cs == 8 && BN == 128) WG_SPLITK(128, 8);
+    if (cs == 8 && BN == 256) WG_SPLITK(256, 8);
+    if (cs == 4 && BN == 128) WG_SPLITK(128, 4);
+    if (cs == 4 && BN == 256) WG_SPLITK(256, 4);
+#undef WG_SPLITK
+  }
   // WG_ONE_CLUSTER=1|2|4 selects the cluster size. Default 1: measured on B200 (profiles/README.md) the multicast
   // variants are no faster (2) or slower (4) -- the limiter is per-SM ingest / shared-memory bandwidth, which
   // multicast does not reduce, not L2 output bandwidth.

@@ -200,7 +200,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,
                      L->dtype, L->relu, out_padded ? 1 : 0, max_ctas, stream);
   else
-    rc = one_launch(L->tmap, L->tmap_out, L->d_filter, L->d_scale, L->d_shift, out_padded ? y : nullptr,
+    rc = one_launch(L->tmap, L->tmap_out, L->d_filter, L->d_scale, L->d_shift, y, out_padded ? 1 : 0,
                     (long long)N * 196, L->cin, L->cout, L->tile_n, L->relu, max_ctas, stream);
   g_launches++;
   if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");

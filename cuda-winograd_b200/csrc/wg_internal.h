@@ -28,7 +28,7 @@ int filter_transform_launch(const float* w_kcrs, void* u_img, int C, int K, int 
 int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);
 int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout);
 int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
-               const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int BN, int relu,
+               const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout, int BN, int relu,
                int max_ctas, cudaStream_t stream);
 int weight_pack_launch(const float* w_cin_cout, float* w_img, int Cin, int Cout, int BN, cudaStream_t stream);
 

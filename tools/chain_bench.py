@@ -61,6 +61,8 @@ def main():
             row = dict(cin=cin, c=c, cout=cout, n=n)
             row["ours_tf32_us"] = timeit(lambda i: block(x_ours[i], out=outs[i]), sets, iters)
             row["ours_bf16_3x3_us"] = timeit(lambda i: block_bf16(x_ours[i], out=outs[i]), sets, iters)
+            replay, _ = block.capture(x_ours[0], out=outs[0])       # one CUDA-graph launch for the three kernels
+            row["ours_tf32_graph_us"] = timeit(lambda i: replay(), 1, iters)
 
             def cudnn_chain(i):
                 a = torch.cudnn_convolution_relu(x_cl[i], k1, b1, (1, 1), (0, 0), (1, 1), 1)
@@ -80,7 +82,7 @@ def main():
             flops = 2.0 * n * 196 * (cin * c + 9 * c * c + c * cout)
             row["ours_tflops_direct_equiv"] = flops / row["ours_tf32_us"] * 1e-6
             rows.append(row)
-            print(f"chain {cin}->{c}->{c}->{cout} N={n:<3} ours {row['ours_tf32_us']:8.1f} us (bf16 3x3 "
+            print(f"chain {cin}->{c}->{c}->{cout} N={n:<3} ours {row['ours_tf32_us']:8.1f} us (graph {row['ours_tf32_graph_us']:.1f}; bf16 3x3 "
                   f"{row['ours_bf16_3x3_us']:8.1f}) | cuDNN tf32 {row['cudnn_tf32_us']:8.1f} fp32 {row['cudnn_fp32_us']:8.1f} us"
                   f" | rel diff vs cuDNN fp32 {row['ours_vs_cudnn_fp32_rel']:.1e}", file=sys.stderr)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
