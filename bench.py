@@ -405,6 +405,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--all-shapes", action="store_true")
     args = ap.parse_args()
+    # keep stdout to the one JSON line: native libraries (NCCL prints its version banner there) get fd 2 instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
     if args.all_shapes:
