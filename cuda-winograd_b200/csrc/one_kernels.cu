@@ -48,6 +48,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                       int Cout, int relu) {
   using S = OneSmem<BN>;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage buffers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -91,8 +92,9 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int item_stride = gridDim.x / CL;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane == 0: lets ptxas keep descriptors in uniform registers (no per-MMA waterfall loop)
       uint32_t st = 0, ph = 0;
+      pdl_wait();  // activations come from the previous kernel in the stream
       for (int item = first_item; item < n_items; item += item_stride) {
         const int nt = item % n_ntiles;
         const int mt = (item / n_ntiles) * CL + crank;
@@ -113,7 +115,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane == 0: lets ptxas keep descriptors in uniform registers (no per-MMA waterfall loop)
       constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, BN);
       const uint32_t a_base = smem_u32(smem + S::kOffA);
       const uint32_t b_base = smem_u32(smem + S::kOffB);
@@ -227,20 +229,39 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-// Small batches (latency): split-K over a thread-block cluster. With M = N*196 rows there are only a handful of
-// 128-row tiles, and one CTA pulling its whole K extent is limited by per-SM ingest (~36 B/clk). Here the CS CTAs of
-// a cluster share one (M-tile, N-tile), each runs Cin/CS of the channel loop, then every CTA pushes the rows of its
-// partial accumulator to the CTA that owns them (st.shared::cluster into per-source inboxes laid over the now idle
-// stage buffers), one cluster barrier, fixed-order local sum, scale/shift/ReLU, 128-bit global stores.
-template <int BN, int CS>
+// Small batches (latency): one cluster per (128-row M-tile, 64-cout sub-tile), split-K across its CS CTAs.
+// With M = N*196 rows there are only a handful of 128-row tiles; what a layer costs at N=1 is (a) how fast the weights
+// (the bulk of the bytes) stream out of L2 -- ~36 B/clk per SM, so they are spread over as many SMs as possible: 64-cout
+// sub-tiles of the packed weight image and Cin/CS channels per CTA -- and (b) the reduction of the CS partial tiles,
+// which goes over distributed shared memory (~20 B/clk per SM), so the partial tile is kept small (128 x 64 fp32).
+// Each CTA pushes row r of its partial accumulator to the CTA owning that row (st.shared::cluster into a dedicated,
+// bank-swizzled inbox [source][row][64]), then arrives on the owner's mbarrier (release.cluster); the owner waits for
+// its 128 arrivals (acquire.cluster), sums the CS partials in fixed order, applies scale/shift/ReLU and writes 128-bit
+// runs. No cluster barrier after the prologue, no atomics, deterministic.
+constexpr int kNS = 64;
+
+struct SmallSmem {
+  static constexpr int kStages = 6;
+  static constexpr uint32_t kABytes = 128 * 128;
+  static constexpr uint32_t kBBytes = kNS * 128;
+  static constexpr uint32_t kOffA = 0;
+  static constexpr uint32_t kOffB = kOffA + kStages * kABytes;
+  static constexpr uint32_t kOffInbox = kOffB + kStages * kBBytes;  // [CS sources][128/CS rows][64] fp32
+  static constexpr uint32_t kOffBar = kOffInbox + 128 * kNS * 4;
+  static constexpr uint32_t kNumBars = 2 * kStages + 2;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;
+};
+
+template <int CS>
 __global__ void __launch_bounds__(kOneThreads, 1)
-conv1x1_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ w_img,
-                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
-                      long long m_rows, int Cin, int Cout, int relu, int out_padded) {
-  using S = OneSmem<BN>;
-  constexpr uint32_t kTmemCols = BN;
+conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ w_img,
+                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
+                     long long m_rows, int Cin, int Cout, int BN, int relu, int out_padded) {
+  using S = SmallSmem;
+  constexpr uint32_t kTmemCols = kNS;
   constexpr int RO = 128 / CS;  // rows of the tile each CTA finishes
-  static_assert((size_t)128 * BN * 4 <= S::kOffOut, "inboxes must fit in the stage buffers");
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -249,8 +270,9 @@ conv1x1_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* _
   uint64_t* full = bars;
   uint64_t* empty = full + S::kStages;
   uint64_t* acc_full = empty + S::kStages;
+  uint64_t* inbox_full = acc_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
-  const uint32_t crank = cluster_ctarank();
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -259,36 +281,50 @@ conv1x1_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* _
       mbar_init(&empty[i], 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(inbox_full, 128);  // RO rows x CS sources, one arrival per pushed row
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
   tc_fence_before();
-  cluster_sync_all();
+  if constexpr (CS > 1) cluster_sync_all(); else __syncthreads();  // peers exist, their barriers are initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_kb = Cin / kBK;
-  const int n_ntiles = Cout / BN;
-  const int item = blockIdx.x / CS;  // one (M-tile, N-tile) per cluster
-  const int nt = item % n_ntiles;
-  const int mt = item / n_ntiles;
+  const int n_sub = Cout / kNS;
+  const int item = blockIdx.x / CS;
+  const int ns = item % n_sub;
+  const int mt = item / n_sub;
   const int kb_per = n_kb / CS, kb0 = (int)crank * kb_per;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint8_t* b_src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)nt * n_kb * S::kBBytes;
-      uint32_t st = 0, ph = 0;
-      for (int kb = kb0; kb < kb0 + kb_per; ++kb) {
+    if (elect_one()) {  // elect.sync, not lane == 0: lets ptxas keep descriptors in uniform registers (no per-MMA waterfall loop)
+      // 64-row slice of the packed [Cout/BN][Cin/32][BN][32] image (the swizzle only depends on row % 8)
+      const int col0 = ns * kNS;
+      const uint8_t* b_src = reinterpret_cast<const uint8_t*>(w_img) +
+                             ((size_t)(col0 / BN) * n_kb * BN + (size_t)(col0 % BN)) * 128;
+      const size_t b_kb_stride = (size_t)BN * 128;
+      // weights do not depend on the previous kernel in the stream: request them before waiting for it
+      const int pre = kb_per < S::kStages ? kb_per : S::kStages;
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&full[i], S::kABytes + S::kBBytes);
+        tma_bulk_g2s(smem + S::kOffB + i * S::kBBytes, b_src + (size_t)(kb0 + i) * b_kb_stride, S::kBBytes, &full[i]);
+      }
+      pdl_wait();
+      for (int i = 0; i < pre; ++i)
+        tma_tensor_2d_g2s(smem + S::kOffA + i * S::kABytes, &tmap_a, (kb0 + i) * kBK, mt * 128, &full[i]);
+      uint32_t st = 0, ph = 1;  // stage ring continues after the `pre` primed stages
+      for (int i = pre; i < kb_per; ++i) {
         mbar_wait(&empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&full[st], S::kABytes + S::kBBytes);
-        tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, kb * kBK, mt * 128, &full[st]);
-        tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * S::kBBytes, S::kBBytes, &full[st]);
+        tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, (kb0 + i) * kBK, mt * 128, &full[st]);
+        tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)(kb0 + i) * b_kb_stride, S::kBBytes, &full[st]);
         if (++st == S::kStages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, BN);
+    if (elect_one()) {  // elect.sync, not lane == 0: lets ptxas keep descriptors in uniform registers (no per-MMA waterfall loop)
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, kNS);
       const uint32_t a_base = smem_u32(smem + S::kOffA);
       const uint32_t b_base = smem_u32(smem + S::kOffB);
       uint32_t st = 0, ph = 0;
@@ -307,62 +343,60 @@ conv1x1_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* _
       umma_commit(acc_full);
     }
   } else {
-    mbar_wait(acc_full, 0);  // this CTA's MMAs are complete: its stage buffers are idle from here on
-    tc_fence_after();
-  }
-  __syncwarp();
-  cluster_sync_all();  // every CTA's stage buffers are idle -> they become the inboxes
-
-  const uint32_t inbox_local = smem_u32(smem);  // [source CTA][RO rows][BN] fp32
-  if (warp >= 2) {
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // row of the tile = TMEM lane
-    const int owner = r / RO, lr = r % RO;
-    const bool valid = (long long)mt * 128 + r < m_rows;  // rows beyond M are never pushed (nor summed)
-    const bool warp_has_rows = (long long)mt * 128 + quad * 32 < m_rows;  // warp-uniform
-    uint32_t dst;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                 : "=r"(dst)
-                 : "r"(inbox_local + (uint32_t)((crank * RO + lr) * BN * 4)), "r"(owner));
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    if (warp_has_rows) {
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld_x16(taddr + c0, v);  // warp-collective: all 32 lanes, valid row or not
-        tmem_ld_x16(taddr + c0 + 16, v + 16);
-        tmem_ld_wait();
-        if (valid) {
+    const uint32_t inbox_local = smem_u32(smem + S::kOffInbox);
+    {  // push this CTA's partial rows to their owners
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;  // row of the tile = TMEM lane
+      const int owner = r / RO, lr = r % RO;
+      const bool valid = (long long)mt * 128 + r < m_rows;  // rows beyond M are never pushed (nor summed)
+      const bool warp_has_rows = (long long)mt * 128 + quad * 32 < m_rows;  // warp-uniform
+      uint32_t dst, dst_bar;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                   : "=r"(dst)
+                   : "r"(inbox_local + (uint32_t)((crank * RO + lr) * kNS * 4)), "r"(owner));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst_bar) : "r"(smem_u32(inbox_full)), "r"(owner));
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+      if (warp_has_rows) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (c0 + 4 * j) * 4),
-                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                         : "memory");
+        for (int c0 = 0; c0 < kNS; c0 += 32) {
+          float v[32];
+          tmem_ld_x16(taddr + c0, v);  // warp-collective: all 32 lanes, valid row or not
+          tmem_ld_x16(taddr + c0 + 16, v + 16);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t pos = (uint32_t)((c0 / 4 + j) ^ (lr & 15));  // 16-byte chunk, swizzled by row
+              asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + pos * 16), "f"(v[4 * j]),
+                           "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                           : "memory");
+            }
+          }
         }
       }
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(dst_bar) : "memory");
     }
-    tc_fence_before();
-  }
-  __syncwarp();
-  cluster_sync_all();  // inboxes complete
-
-  if (warp >= 2) {
+    mbar_wait_cluster(inbox_full, 0);  // all CS partials of this CTA's rows have landed
     const int t = threadIdx.x - 64;  // 0..127
-    constexpr int kChunks = BN / 4;  // 16-byte chunks per row
+    constexpr int kChunks = kNS / 4;  // 16-byte chunks per row
     for (int u = t; u < RO * kChunks; u += 128) {
       const int lr = u / kChunks, ch = u % kChunks;
       const long long m = (long long)mt * 128 + crank * RO + lr;
       if (m >= m_rows) continue;
+      const uint32_t pos = (uint32_t)(ch ^ (lr & 15));
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int p = 0; p < CS; ++p) {
-        const float4 v = ld_shared_v4(inbox_local + (uint32_t)(((p * RO + lr) * BN + ch * 4) * 4));
+        const float4 v = ld_shared_v4(inbox_local + (uint32_t)(((p * RO + lr) * kChunks + pos) * 16));
         acc.x += v.x;
         acc.y += v.y;
         acc.z += v.z;
         acc.w += v.w;
       }
-      const int col = nt * BN + ch * 4;
+      const int col = ns * kNS + ch * 4;
       const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + col));
       const float4 h4 = __ldg(reinterpret_cast<const float4*>(shift + col));
       acc.x = fmaf(s4.x, acc.x, h4.x);
@@ -456,47 +490,81 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   cfg.blockDim = dim3(kOneThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL>, tmap, tmap_y, w_img, scale, shift, y_padded,
                                      m_rows, Cin, Cout, relu);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-template <int BN, int CS>
-static int launch_splitk(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
-                         int out_padded, long long m_rows, int Cin, int Cout, int relu, cudaStream_t stream) {
-  using S = OneSmem<BN>;
-  static unsigned long long configured = 0;
+// how many CS-clusters of the small kernel can be resident at once on this device (cached per device and CS)
+template <int CS>
+static int small_max_clusters() {
+  static int cached[64];
   int dev_ = 0;
   cudaGetDevice(&dev_);
-  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
-  if (!(configured & dev_bit_)) {
-    cudaError_t e = cudaFuncSetAttribute(conv1x1_splitk_kernel<BN, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)S::kTotal);
-    if (e != cudaSuccess) return WG_ERR_CUDA;
-    configured |= dev_bit_;
+  int& slot = cached[dev_ & 63];
+  if (slot == 0) {
+    cudaFuncSetAttribute(conv1x1_small_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)SmallSmem::kTotal);
+    if (CS > 8) cudaFuncSetAttribute(conv1x1_small_kernel<CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS);
+    cfg.blockDim = dim3(kOneThreads);
+    cfg.dynamicSmemBytes = SmallSmem::kTotal;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CS > 1 ? 1 : 0;
+    int n = 0;
+    if (CS == 1) {
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev_);
+    } else if (cudaOccupancyMaxActiveClusters(&n, conv1x1_small_kernel<CS>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    slot = n > 0 ? n : -1;
   }
-  const long long n_items = ((m_rows + 127) / 128) * (Cout / BN);
+  return slot > 0 ? slot : 0;
+}
+
+template <int CS>
+static int launch_small(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
+                        int out_padded, long long m_rows, int Cin, int Cout, int BN, int relu, cudaStream_t stream) {
+  const long long n_items = ((m_rows + 127) / 128) * (Cout / kNS);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_items * CS));
   cfg.blockDim = dim3(kOneThreads);
-  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.dynamicSmemBytes = SmallSmem::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_splitk_kernel<BN, CS>, tmap, w_img, scale, shift, y, m_rows, Cin,
-                                     Cout, relu, out_padded);
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_small_kernel<CS>, tmap, w_img, scale, shift, y, m_rows, Cin, Cout,
+                                     BN, relu, out_padded);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
@@ -505,26 +573,42 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
                int max_ctas, cudaStream_t stream) {
   float* y_padded = out_padded ? y : nullptr;
   {
-    // latency mode: a handful of tiles and a long channel loop -> split K over a cluster (WG_ONE_SPLITK=1 disables)
-    static int sk_env = -1;
+    // latency mode: every (M-tile, 64-cout sub-tile) fits on the chip at once -> the small kernel, split-K factor CS
+    // chosen by a two-term model in clocks (weight/activation ingest of Cin/CS channels at ~36 B/clk, DSMEM reduction
+    // of (CS-1)/CS of a 32 KB partial at ~18 B/clk + fixed cost). WG_ONE_SPLITK=1 disables, WG_ONE_CS=n forces CS.
+    static int sk_env = -1, cs_env = 0;
     if (sk_env < 0) {
       const char* e = getenv("WG_ONE_SPLITK");
       sk_env = e ? atoi(e) : 0;
+      const char* c = getenv("WG_ONE_CS");
+      cs_env = c ? atoi(c) : 0;
     }
     const int n_kb = Cin / kBK;
-    const long long n_items = ((m_rows + 127) / 128) * (Cout / BN);
-    int cs = 1;
-    if (sk_env != 1 && n_kb >= 16) {  // Cin >= 512; measured: with Cin = 256 the reduction costs more than it saves
-      if (n_kb % 8 == 0 && n_items * 8 <= max_ctas) cs = 8;
-      else if (n_kb % 4 == 0 && n_items * 4 <= max_ctas) cs = 4;
+    const long long n_items = ((m_rows + 127) / 128) * (Cout / kNS);
+    if (sk_env != 1 && Cout % kNS == 0 && n_items <= max_ctas) {
+      int best = 0;
+      double best_t = 1e30;
+      for (int cs : {1, 2, 4, 8, 16}) {
+        if (n_kb % cs != 0 || n_items * cs > max_ctas) continue;
+        const int fit = cs == 1 ? small_max_clusters<1>() : cs == 2 ? small_max_clusters<2>()
+                      : cs == 4 ? small_max_clusters<4>() : cs == 8 ? small_max_clusters<8>()
+                                                                    : small_max_clusters<16>();
+        if (n_items > fit) continue;
+        const double t = (n_kb / cs) * 24576.0 / 36.0 + (cs > 1 ? (cs - 1.0) / cs * 32768.0 / 18.0 + 400.0 : 0.0);
+        if (cs_env == cs || (cs_env == 0 && t < best_t)) {
+          best = cs;
+          best_t = cs_env == cs ? -1.0 : t;
+        }
+      }
+#define WG_SMALL(CS_) \
+  return launch_small<CS_>(tmap, w_img, scale, shift, y, out_padded, m_rows, Cin, Cout, BN, relu, stream)
+      if (best == 1) WG_SMALL(1);
+      if (best == 2) WG_SMALL(2);
+      if (best == 4) WG_SMALL(4);
+      if (best == 8) WG_SMALL(8);
+      if (best == 16) WG_SMALL(16);
+#undef WG_SMALL
     }
-#define WG_SPLITK(BN_, CS_) \
-  return launch_splitk<BN_, CS_>(tmap, w_img, scale, shift, y, out_padded, m_rows, Cin, Cout, relu, stream)
-    if (cs == 8 && BN == 128) WG_SPLITK(128, 8);
-    if (cs == 8 && BN == 256) WG_SPLITK(256, 8);
-    if (cs == 4 && BN == 128) WG_SPLITK(128, 4);
-    if (cs == 4 && BN == 256) WG_SPLITK(256, 4);
-#undef WG_SPLITK
   }
   // WG_ONE_CLUSTER=1|2|4 selects the cluster size. Default 1: measured on B200 (profiles/README.md) the multicast
   // variants are no faster (2) or slower (4) -- the limiter is per-SM ingest / shared-memory bandwidth, which

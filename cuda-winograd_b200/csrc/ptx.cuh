@@ -78,6 +78,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, but acquiring at cluster scope: pairs with mbar_arrive_remote() of threads in other CTAs of the cluster whose
+// st.shared::cluster into this CTA's shared memory must be visible after the wait.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > WG_WAIT_TIMEOUT_NS) {
+      printf("wg: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every product kernel is launched with programmaticStreamSerializationAllowed: the next launch in the stream may be
+// scheduled once all CTAs of this grid have executed pdl_launch_dependents(), so its prologue (barrier init, TMEM
+// allocation, weight prefetch) overlaps this grid's execution. pdl_wait() blocks until the previous grid in the stream
+// has completed and its memory is visible; nothing the previous grid may write (or still read) is touched before it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxy fences
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / TMA reading shared memory)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -55,6 +55,15 @@ CUtensorMapL2promotion l2_promotion() {
   }
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WG_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 }  // namespace wg
 
 struct wg_layer {
@@ -63,12 +72,16 @@ struct wg_layer {
   int tile_n;  // 3x3: cout slice KN; 1x1: BN
   int num_sms;
   float* d_filter;  // packed filter image (U or swizzled W^T)
+  float* d_filter_small;  // 3x3 TF32 only: U in the plain KN=32 image the small-batch kernel reads (may alias d_filter)
   float* d_scale;
   float* d_shift;
   // tensor-map cache for the last (x, N) seen
   const float* tmap_x;
   int tmap_n;
   CUtensorMap tmap;
+  const float* tmap_small_x;  // 3x3 small-batch kernel: same view, 26-row box
+  int tmap_small_n;
+  CUtensorMap tmap_small;
   const float* tmap_y_ptr;  // 1x1 only: output tensor map for the TMA-store epilogue
   int tmap_y_n;
   CUtensorMap tmap_out;
@@ -147,6 +160,15 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   rc = kind == 0 ? filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)dtype, L->stream)
                  : weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
   g_launches++;
+  if (rc == WG_OK && kind == 0 && dtype == WG_TF32) {
+    if (L->tile_n == 32) {
+      L->d_filter_small = L->d_filter;
+    } else {
+      WG_TRY(cudaMalloc(&L->d_filter_small, filter_elems * sizeof(float)));
+      rc = filter_transform_launch(d_w, L->d_filter_small, cin, cout, 32, 0, L->stream);
+      g_launches++;
+    }
+  }
   if (rc != WG_OK) {
     cuda_fail(cudaGetLastError(), "filter pack launch");
     wg_destroy(L);
@@ -181,6 +203,24 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   int cur = -1;
   WG_CUDA(cudaGetDevice(&cur));
   if (cur != L->device) WG_CUDA(cudaSetDevice(L->device));
+  const int max_ctas = g_max_ctas > 0 ? g_max_ctas : L->num_sms;
+  if (L->kind == 0 && L->d_filter_small != nullptr) {
+    // small batches: the latency variant (one 64-tile x 32-cout item per cluster, split-C), see wino_small_kernel.cu
+    const int cs = wino_small_cs(N, L->cin, L->cout, max_ctas);
+    if (cs > 0) {
+      if (L->tmap_small_x != x || L->tmap_small_n != N) {
+        int rc = wino_small_make_tmap(&L->tmap_small, x, N, L->cin);
+        if (rc != WG_OK) return rc;
+        L->tmap_small_x = x;
+        L->tmap_small_n = N;
+      }
+      int rc = wino_small_launch(L->tmap_small, L->d_filter_small, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
+                                 L->relu, out_padded ? 1 : 0, cs, stream);
+      g_launches++;
+      if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
+      return rc;
+    }
+  }
   if (L->tmap_x != x || L->tmap_n != N) {
     int rc = L->kind == 0 ? wino_make_tmap(&L->tmap, x, N, L->cin)
                           : one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin);
@@ -194,7 +234,6 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
     L->tmap_y_ptr = y;
     L->tmap_y_n = N;
   }
-  const int max_ctas = g_max_ctas > 0 ? g_max_ctas : L->num_sms;
   int rc;
   if (L->kind == 0)
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,
@@ -274,6 +313,7 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
 
 int wg_destroy(wg_layer_t* L) {
   if (!L) return WG_ERR_ARG;
+  if (L->d_filter_small && L->d_filter_small != L->d_filter) cudaFree(L->d_filter_small);
   if (L->d_filter) cudaFree(L->d_filter);
   if (L->d_scale) cudaFree(L->d_scale);
   if (L->d_shift) cudaFree(L->d_shift);

@@ -17,12 +17,21 @@ PFN_encodeTiled get_encode_tiled();
 // L2 promotion of the activation tensor maps (WG_L2_PROMO=0|64|128|256 overrides; experiments)
 CUtensorMapL2promotion l2_promotion();
 
+// programmatic dependent launch on every product kernel (WG_PDL=0 disables; A/B measurements)
+bool pdl_enabled();
+
 // ---- 3x3 Winograd path (winograd_kernels.cu)
 int wino_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
 int wino_launch(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift, float* y,
                 int n_img, int C, int K, int KN, int bf16, int relu, int out_padded, int max_ctas,
                 cudaStream_t stream);
 int filter_transform_launch(const float* w_kcrs, void* u_img, int C, int K, int KN, int bf16, cudaStream_t stream);
+
+// small-batch latency variant (wino_small_kernel.cu): TF32 only, filter in the plain KN=32 image
+int wino_small_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
+int wino_small_cs(int n_img, int C, int K, int max_ctas);  // cluster split factor, 0 = use the persistent kernel
+int wino_small_launch(const CUtensorMap& tmap_small, const float* u_plain, const float* scale, const float* shift,
+                      float* y, int n_img, int C, int K, int relu, int out_padded, int cs, cudaStream_t stream);
 
 // ---- 1x1 GEMM path (one_kernels.cu)
 int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);

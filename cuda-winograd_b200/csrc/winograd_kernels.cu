@@ -90,6 +90,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
   constexpr int KN = S::KN;
   constexpr int kRawPerV = BF16 ? 2 : 1;  // 8-channel raw stages per V stage
   constexpr uint32_t kTmemCols = 512;
+  pdl_launch_dependents();  // the next launch in the stream may start its prologue (it waits before touching x / y)
   extern __shared__ __align__(1024) uint8_t smem[];
 
   const int warp = threadIdx.x >> 5;
@@ -149,8 +150,25 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane == 0: lets ptxas keep descriptors in uniform registers (no per-MMA waterfall loop)
       uint32_t rs = 0, rph = 0, us = 0, uph = 0;
+      bool u_primed = false;
+      if (item0 < n_items) {
+        // the filter does not depend on the previous kernel in the stream: request the first stage's U chunks before
+        // waiting for that kernel (programmatic dependent launch), the activations after
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) +
+                               (size_t)(item0 % n_slices) * (n_kb / kRawPerV) * S::kUChunksPerStage * S::kUChunkBytes;
+#pragma unroll
+        for (int h = 0; h < S::kUChunksPerStage; ++h) {
+          mbar_arrive_expect_tx(&u_full[us], S::kUChunkBytes);
+          tma_bulk_g2s(smem + S::kOffU + us * S::kUChunkBytes,
+                       u_src + (size_t)((kb0 / kRawPerV) * S::kUChunksPerStage + h) * S::kUChunkBytes, S::kUChunkBytes,
+                       &u_full[us]);
+          if (++us == S::kUBufs) { us = 0; uph ^= 1; }
+        }
+        u_primed = true;
+      }
+      pdl_wait();
       for (int item = item0; item < n_items; item += item_step) {
         const int slice = item % n_slices;
         const int mb = item / n_slices;
@@ -164,6 +182,10 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
           tma_tensor_4d_g2s(smem + S::kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
           if (++rs == S::kRawStages) { rs = 0; rph ^= 1; }
           if (kb % kRawPerV != 0) continue;  // the U chunks of a V stage go out with its first raw stage
+          if (u_primed) {  // already requested above
+            u_primed = false;
+            continue;
+          }
           const int kv = kb / kRawPerV;
 #pragma unroll
           for (int h = 0; h < S::kUChunksPerStage; ++h) {
@@ -179,7 +201,7 @@ wino3x3_bn_relu_kernel(const __grid_constant__ CUtensorMap tmap_x, const void* _
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane == 0: lets ptxas keep descriptors in uniform registers (no per-MMA waterfall loop)
       const uint32_t fmt = BF16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
       const uint32_t idesc = make_idesc(fmt, 128, KN);
       const uint32_t idesc_neg = make_idesc(fmt, 128, KN, 1);  // D += (-A) * B
@@ -731,13 +753,15 @@ static int launch_wino_split(const CUtensorMap& tmap, const void* u_img, const f
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   static int ablate = -1;  // debug only, see launch_wino
   if (ablate < 0) {
     const char* env = getenv("WG_DEBUG_ABLATE");
@@ -814,9 +838,19 @@ static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* 
     const char* e = getenv("WG_DEBUG_ABLATE");
     ablate = e ? atoi(e) : 0;
   }
-  wino3x3_bn_relu_kernel<FOLD, BF16><<<grid, kThreads, S::kTotal, stream>>>(tmap, u_img, scale, shift, y, n_img, C, K,
-                                                                            relu, out_padded, mv, fp16, ablate);
-  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_bn_relu_kernel<FOLD, BF16>, tmap, u_img, scale, shift, y, n_img, C,
+                                     K, relu, out_padded, mv, fp16, ablate);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_launch(const CUtensorMap& tmap, const void* u_img, const float* scale, const float* shift, float* y,

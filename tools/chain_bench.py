@@ -72,6 +72,11 @@ def main():
             for name, tf32 in (("cudnn_tf32_us", True), ("cudnn_fp32_us", False)):
                 torch.backends.cudnn.allow_tf32 = tf32
                 row[name] = timeit(cudnn_chain, sets, iters)
+                if n == 1:  # cuDNN's chain in a CUDA graph too, so that neither side pays Python dispatch
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        cudnn_chain(0)
+                    row[name.replace("_us", "_graph_us")] = timeit(lambda i: g.replay(), 1, iters)
             torch.backends.cudnn.allow_tf32 = False
             ref = cudnn_chain(0).permute(0, 2, 3, 1).reshape(n, 196, cout)
             got = block(x_ours[0])
@@ -83,7 +88,8 @@ def main():
             row["ours_tflops_direct_equiv"] = flops / row["ours_tf32_us"] * 1e-6
             rows.append(row)
             print(f"chain {cin}->{c}->{c}->{cout} N={n:<3} ours {row['ours_tf32_us']:8.1f} us (graph {row['ours_tf32_graph_us']:.1f}; bf16 3x3 "
-                  f"{row['ours_bf16_3x3_us']:8.1f}) | cuDNN tf32 {row['cudnn_tf32_us']:8.1f} fp32 {row['cudnn_fp32_us']:8.1f} us"
+                  f"{row['ours_bf16_3x3_us']:8.1f}) | cuDNN tf32 {row['cudnn_tf32_us']:8.1f} (graph "
+                  f"{row.get('cudnn_tf32_graph_us', float('nan')):.1f}) fp32 {row['cudnn_fp32_us']:8.1f} us"
                   f" | rel diff vs cuDNN fp32 {row['ours_vs_cudnn_fp32_rel']:.1e}", file=sys.stderr)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "chain_bench.json"), "w") as f:

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Reported baseline only (never on the product path): cuDNN's fused conv + bias + ReLU on the same B200, through
 torch (cudnn_convolution_relu -> cudnnConvolutionBiasActivationForward), BN scale folded into the weights and shift as
-bias, channels_last, TF32 allowed and not allowed, bf16 too; N=1 latency (L2-warm back-to-back, like Test.c's loop) and
-N=256 throughput (rotating buffers > L2). Also times this repo's kernels in the same process for a side-by-side table.
+bias, channels_last, TF32 allowed and not allowed, bf16 too; N=1 latency (L2-warm back-to-back launches captured in a CUDA graph so
+that neither side is bound by Python dispatch; the Python-loop figures are kept as *_hostloop_us) and N=256 throughput (rotating buffers > L2). Also times this repo's kernels in the same process for a side-by-side table.
 BASELINE.md section 2 asks for exactly this. Writes gpurun_out/cudnn_baseline.json.
 """
 import json
@@ -28,6 +28,26 @@ def timeit(fn, sets, iters):
     e0.record()
     for i in range(iters):
         fn(i % sets)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / iters
+
+
+def timeit_graph(fn, iters):
+    """N=1: a layer is shorter than one Python call, so time `iters` back-to-back calls captured once into a CUDA graph
+    (both for this repo's kernels and for cuDNN): the GPU-side latency a C caller's loop would see."""
+    for _ in range(3):
+        fn(0)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn(0)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / iters
@@ -61,6 +81,9 @@ def main():
             iters = 300 if n == 1 else 100
             row = dict(kind=kind, cin=cin, cout=cout, relu=relu, n=n)
             row["ours_tf32_us"] = timeit(lambda i: ours(x_ours[i], out=y_ours[i]), sets, iters)
+            if n == 1:
+                row["ours_tf32_hostloop_us"] = row["ours_tf32_us"]
+                row["ours_tf32_us"] = timeit_graph(lambda i: ours(x_ours[i], out=y_ours[i]), 100)
             for name, dt, tf32 in (("cudnn_fp32_us", torch.float32, False), ("cudnn_tf32_us", torch.float32, True),
                                    ("cudnn_bf16_us", torch.bfloat16, True)):
                 torch.backends.cudnn.allow_tf32 = tf32
@@ -72,6 +95,9 @@ def main():
                     f = lambda i: torch.nn.functional.conv2d(xs[i], wt, bt)
                 try:
                     row[name] = timeit(f, sets, iters)
+                    if n == 1:
+                        row[name.replace("_us", "_hostloop_us")] = row[name]
+                        row[name] = timeit_graph(f, 100)
                 except Exception as e:  # noqa: BLE001
                     row[name] = None
                     print("cudnn failed", name, kind, cin, cout, n, e, file=sys.stderr)

@@ -34,9 +34,11 @@ static float frand() {  // U(-0.5, 0.5)
 // (k/4)*kstride + (r/8)*gstride + (r%8)*16 + (k%4)*4. One tcgen05.mma, D dumped to global.
 __global__ void umma_probe_kernel(const float* a, const float* b, float* d, uint32_t a_kstride, uint32_t a_gstride,
                                   uint32_t b_kstride, uint32_t b_gstride, uint32_t lbo_a, uint32_t sbo_a,
-                                  uint32_t lbo_b, uint32_t sbo_b) {
+                                  uint32_t lbo_b, uint32_t sbo_b, int m64) {
   using namespace wg;
   __shared__ __align__(1024) uint8_t sa[8192];
+  __shared__ __align__(1024) uint8_t sz[8192];  // zeros: an M=128 MMA with it clears the accumulator (m64 probe)
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) reinterpret_cast<uint32_t*>(sz)[i] = 0;
   __shared__ __align__(1024) uint8_t sb[4096];
   __shared__ uint64_t bar;
   __shared__ uint32_t tptr;
@@ -62,7 +64,13 @@ __global__ void umma_probe_kernel(const float* a, const float* b, float* d, uint
   if (tid == 0) {
     const uint64_t ad = make_smem_desc(smem_u32(sa), lbo_a, sbo_a, kLayoutNone);
     const uint64_t bd = make_smem_desc(smem_u32(sb), lbo_b, sbo_b, kLayoutNone);
-    umma_tf32_ss(tb, ad, bd, make_idesc(kFmtTF32, 128, 32), 0);
+    if (m64) {  // where do the 64 rows of an M=64 accumulator land in TMEM? clear all 128 lanes, then M=64
+      const uint64_t zd = make_smem_desc(smem_u32(sz), lbo_a, sbo_a, kLayoutNone);
+      umma_tf32_ss(tb, zd, bd, make_idesc(kFmtTF32, 128, 32), 0);
+      umma_tf32_ss(tb, ad, bd, make_idesc(kFmtTF32, 64, 32), 0);
+    } else {
+      umma_tf32_ss(tb, ad, bd, make_idesc(kFmtTF32, 128, 32), 0);
+    }
     umma_commit(&bar);
   }
   mbar_wait(&bar, 0);
@@ -95,7 +103,7 @@ static int run_probe() {
     const uint32_t lbo_a = variant == 0 ? aks : ags, sbo_a = variant == 0 ? ags : aks;
     const uint32_t lbo_b = variant == 0 ? bks : bgs, sbo_b = variant == 0 ? bgs : bks;
     CK(cudaMemset(dd, 0, d.size() * 4));
-    umma_probe_kernel<<<1, 128>>>(da, db, dd, aks, ags, bks, bgs, lbo_a, sbo_a, lbo_b, sbo_b);
+    umma_probe_kernel<<<1, 128>>>(da, db, dd, aks, ags, bks, bgs, lbo_a, sbo_a, lbo_b, sbo_b, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       printf("probe variant %d: kernel failed: %s\n", variant, cudaGetErrorString(e));
@@ -113,6 +121,38 @@ static int run_probe() {
            variant == 0 ? "LBO = K-chunk stride, SBO = 8-row-group stride" : "swapped", maxerr,
            maxerr == 0 ? "MATCH" : "mismatch");
     if (maxerr == 0) ok_any |= 1 << variant;
+  }
+  {  // M=64: print the TMEM lane each accumulator row landed in
+    CK(cudaMemset(dd, 0, d.size() * 4));
+    umma_probe_kernel<<<1, 128>>>(da, db, dd, 2112, 128, 512, 128, 2112, 128, 512, 128, 1);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("probe M=64: kernel failed: %s\n", cudaGetErrorString(e));
+      return -1;
+    }
+    CK(cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost));
+    printf("probe M=64 row->lane:");
+    for (int m = 0; m < 64; ++m) {
+      int found = -1;
+      for (int l = 0; l < 128 && found < 0; ++l) {
+        bool same = true, nz = false;
+        for (int n = 0; n < 32; ++n) {
+          double ref = 0;
+          for (int k = 0; k < 8; ++k) ref += (double)a[m * 8 + k] * b[n * 8 + k];
+          same = same && ref == d[l * 32 + n];
+          nz = nz || ref != 0;
+        }
+        if (same && nz) found = l;
+      }
+      printf(" %d", found);
+    }
+    int nzl = 0;
+    for (int l = 0; l < 128; ++l) {
+      bool nz = false;
+      for (int n = 0; n < 32; ++n) nz = nz || d[l * 32 + n] != 0;
+      nzl += nz;
+    }
+    printf("\nprobe M=64: %d non-zero lanes\n", nzl);
   }
   cudaFree(da);
   cudaFree(db);
@@ -258,10 +298,266 @@ static void time_layer(int kind, int N, int C, int K, int relu) {
   cudaFree(dy);
 }
 
+// ------------------------------------------------------------------------------------------------ TMA latency probe
+// What bounds a small-batch layer: how long after a kernel starts do `total` bytes per CTA, requested as `pieces`
+// concurrent 1-D bulk copies from an L2-warm buffer, take to land in shared memory? Thread 0 of every CTA issues the
+// copies at once and times issue -> mbarrier completion with clock64; the host prints min / median / max over CTAs.
+__global__ void tma_probe_kernel(const uint8_t* src, long long* out, int total, int pieces, int distinct) {
+  using namespace wg;
+  extern __shared__ __align__(1024) uint8_t dyn[];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint8_t* s = src + (distinct ? (size_t)blockIdx.x * total : 0);
+    const int piece = total / pieces;
+    const long long t0 = clock64();
+    mbar_arrive_expect_tx(&bar, total);
+    for (int p = 0; p < pieces; ++p) tma_bulk_g2s(dyn + p * piece, s + (size_t)p * piece, piece, &bar);
+    mbar_wait(&bar, 0);
+    out[blockIdx.x] = clock64() - t0;
+  }
+}
+
+static void time_tma(int grid, int total, int pieces, int distinct) {
+  static uint8_t* src = nullptr;
+  static long long* out = nullptr;
+  const size_t bytes = (size_t)148 * 192 * 1024;
+  if (!src) {
+    CK(cudaMalloc(&src, bytes));
+    CK(cudaMemset(src, 1, bytes));
+    CK(cudaMalloc(&out, 148 * sizeof(long long)));
+    CK(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  std::vector<long long> h(grid), best(grid, 1ll << 60);
+  for (int rep = 0; rep < 5; ++rep) {  // first rep warms L2 / TLBs; keep the per-CTA minimum of the rest
+    tma_probe_kernel<<<grid, 32, total, 0>>>(src, out, total, pieces, distinct);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), out, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (rep > 0)
+      for (int i = 0; i < grid; ++i) best[i] = h[i] < best[i] ? h[i] : best[i];
+  }
+  std::vector<long long> s = best;
+  for (size_t i = 0; i < s.size(); ++i)
+    for (size_t j = i + 1; j < s.size(); ++j)
+      if (s[j] < s[i]) std::swap(s[i], s[j]);
+  printf("tma grid=%3d total=%6d B in %2d pieces %s: clk min %lld median %lld max %lld  -> %.1f B/clk/SM at the median\n",
+         grid, total, pieces, distinct ? "distinct" : "shared  ", s[0], s[grid / 2], s[grid - 1],
+         (double)total / s[grid / 2]);
+}
+
+// ------------------------------------------------------------------------------------------------ MMA issue probe
+// Time `count` back-to-back tcgen05.mma kind::tf32 (K=8, operands from shared memory, no-swizzle K-major layout as in
+// the 3x3 kernels) from first issue to commit completion. acc_stride = TMEM column distance between consecutive MMAs'
+// accumulators (0 = all into the same accumulator).
+// MODE 0: `if (threadIdx.x == 0)` around the issue loop; 1: `if (elect_one())`; 2: the whole warp runs the loop
+// (uniform control flow and operands) and only the tcgen05.mma itself is predicated on an elected lane.
+template <int M, int N, int MODE>
+__global__ void mma_probe_kernel(long long* out, int count, int acc_stride, int distinct_ops) {
+  using namespace wg;
+  extern __shared__ __align__(1024) uint8_t dyn[];  // A images then B images, zero-filled
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dyn)[i] = 0;
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc<512>(&tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tptr;
+  const uint32_t a0 = smem_u32(dyn), b0 = a0 + 96 * 1024;
+  constexpr uint32_t kALbo = M * 16 + 64, kAPer = kALbo + M * 16, kBLbo = N * 16, kBPer = 2 * N * 16;
+  constexpr uint32_t idesc = make_idesc(kFmtTF32, M, N);
+  if (threadIdx.x < 32) {
+    long long t0 = 0, t1 = 0;
+    if constexpr (MODE == 2) {
+      t0 = clock64();
+      for (int i = 0; i < count; ++i) {
+        const int p = distinct_ops ? (i & 15) : 0;
+        const uint64_t ad = make_smem_desc(a0 + p * kAPer, kALbo, 128, kLayoutNone);
+        const uint64_t bd = make_smem_desc(b0 + p * kBPer, kBLbo, 128, kLayoutNone);
+        if (elect_one()) umma_tf32_ss(tb + ((i * acc_stride) & 511 & ~(N - 1)), ad, bd, idesc, 1u);
+      }
+      t1 = clock64();
+      if (elect_one()) umma_commit(&bar);
+    } else if (MODE == 1 ? elect_one() : threadIdx.x == 0) {
+      t0 = clock64();
+      for (int i = 0; i < count; ++i) {
+        const int p = distinct_ops ? (i & 15) : 0;
+        const uint64_t ad = make_smem_desc(a0 + p * kAPer, kALbo, 128, kLayoutNone);
+        const uint64_t bd = make_smem_desc(b0 + p * kBPer, kBLbo, 128, kLayoutNone);
+        umma_tf32_ss(tb + ((i * acc_stride) & 511 & ~(N - 1)), ad, bd, idesc, 1u);
+      }
+      t1 = clock64();
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (threadIdx.x == 0) {
+      out[0] = t1 - t0;
+      out[1] = clock64() - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<512>(tb);
+}
+
+template <int M, int N, int MODE>
+static void time_mma(int count, int acc_stride, int distinct_ops) {
+  static long long* out = nullptr;
+  if (!out) CK(cudaMalloc(&out, 2 * sizeof(long long)));
+  CK(cudaFuncSetAttribute(mma_probe_kernel<M, N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  long long h[2] = {0, 0};
+  for (int rep = 0; rep < 2; ++rep) {
+    mma_probe_kernel<M, N, MODE><<<1, 128, 160 * 1024>>>(out, count, acc_stride, distinct_ops);
+    CK(cudaDeviceSynchronize());
+  }
+  CK(cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost));
+  printf("mma mode %d M=%3d N=%3d K=8 tf32 x%3d acc_stride=%3d %s operands: issue %5lld clk, issue->complete %5lld clk = %.1f clk/MMA\n",
+         MODE, M, N, count, acc_stride, distinct_ops ? "16 distinct" : "same       ", h[0], h[1], (double)h[1] / count);
+}
+
+// ------------------------------------------------------------------------------------------------ launch floor
+// What an N=1 layer cannot go below: empty kernels launched back to back the way the product launches its own
+// (dynamic smem opt-in, 128-byte __grid_constant__ parameter, optional cluster), timed with the same event loop.
+struct Blob128 {
+  uint8_t b[128];
+};
+// spin_clk: busy body of that many clocks (stands in for a layer); pdl: 1 = griddepcontrol.launch_dependents at entry
+// and griddepcontrol.wait before the body (programmatic dependent launch), 2 = wait first, trigger after the body.
+__global__ void floor_kernel(const __grid_constant__ Blob128 blob, float* out, int touch_tmem, int spin_clk, int pdl) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  __shared__ uint32_t slot;
+  if (pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (touch_tmem) {
+    if (threadIdx.x < 32) wg::tmem_alloc<512>(&slot);
+    __syncthreads();
+  }
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  const long long t0 = clock64();
+  while (clock64() - t0 < spin_clk) {
+  }
+  if (pdl == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (touch_tmem) {
+    __syncthreads();
+    if (threadIdx.x < 32) wg::tmem_dealloc<512>(slot);
+  }
+  if (out != nullptr && threadIdx.x == 0 && blob.b[0] == 77) out[blockIdx.x] = dyn[0];
+}
+
+static void time_floor(int grid, int threads, int smem, int cluster, int tmem, int spin_clk = 0, int pdl = 0,
+                       int graph = 0) {
+  CK(cudaFuncSetAttribute(floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(floor_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  Blob128 blob;
+  memset(&blob, 0, sizeof(blob));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cluster > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cluster;
+    at[na].val.clusterDim.y = at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  cfg.stream = st;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 20;
+  cudaGraphExec_t gx = nullptr;
+  if (graph) {
+    cudaGraph_t g;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < iters; ++i) CK(cudaLaunchKernelEx(&cfg, floor_kernel, blob, (float*)nullptr, tmem, spin_clk, pdl));
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(&gx, g, 0));
+    CK(cudaGraphLaunch(gx, st));
+  } else {
+    for (int i = 0; i < 3; ++i) CK(cudaLaunchKernelEx(&cfg, floor_kernel, blob, (float*)nullptr, tmem, spin_clk, pdl));
+  }
+  CK(cudaStreamSynchronize(st));
+  cudaEventRecord(e0, st);
+  if (graph) {
+    CK(cudaGraphLaunch(gx, st));
+  } else {
+    for (int i = 0; i < iters; ++i) cudaLaunchKernelEx(&cfg, floor_kernel, blob, (float*)nullptr, tmem, spin_clk, pdl);
+  }
+  cudaEventRecord(e1, st);
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  printf("floor grid=%3d threads=%d smem=%6d cluster=%d tmem=%d spin=%5d clk pdl=%d graph=%d: %.2f us/launch\n", grid,
+         threads, smem, cluster, tmem, spin_clk, pdl, graph, ms * 1000.0 / iters);
+  cudaStreamDestroy(st);
+}
+
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   printf("sm_100 devices: %d\n", wg_device_count());
   if (wg_device_count() == 0) return 1;
+  if (argc > 1 && !strcmp(argv[1], "mma")) {
+    for (int count : {1, 16, 96}) {
+      time_mma<64, 32, 0>(count, 32, 1);
+      time_mma<64, 32, 1>(count, 32, 1);
+      time_mma<64, 32, 2>(count, 32, 1);
+      time_mma<128, 64, 0>(count, 64, 1);
+      time_mma<128, 64, 1>(count, 64, 1);
+      time_mma<128, 64, 2>(count, 64, 1);
+      time_mma<128, 128, 2>(count, 128, 1);
+    }
+    time_mma<128, 64, 2>(96, 0, 1);
+    time_mma<128, 64, 2>(96, 64, 0);
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "tma")) {
+    for (int grid : {1, 16, 64, 128})
+      for (int total : {1024, 16384, 65536, 163840}) {
+        time_tma(grid, total, 1, 1);
+        if (total >= 16384) time_tma(grid, total, total / 4096, 1);
+      }
+    time_tma(128, 16384, 1, 0);
+    time_tma(128, 65536, 4, 0);
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "floor")) {
+    time_floor(1, 32, 0, 1, 0);
+    time_floor(148, 320, 0, 1, 0);
+    time_floor(148, 320, 230000, 1, 0);
+    time_floor(148, 320, 230000, 1, 1);
+    time_floor(144, 320, 230000, 8, 0);
+    time_floor(144, 320, 230000, 8, 1);
+    time_floor(32, 192, 200000, 8, 1);
+    time_floor(16, 192, 200000, 1, 1);
+    for (int graph = 0; graph < 2; ++graph)
+      for (int pdl = 0; pdl < 3; ++pdl) {
+        time_floor(32, 320, 230000, 8, 1, 0, pdl, graph);
+        time_floor(32, 320, 230000, 8, 1, 10000, pdl, graph);
+        time_floor(148, 320, 230000, 1, 1, 10000, pdl, graph);
+      }
+    run_probe();
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "timen1")) {  // small-batch latency only
     for (int n : {1, 2, 4, 8}) {
       time_layer(0, n, 128, 128, 1);
