@@ -56,7 +56,7 @@ static_assert(kTotal <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ float tf32_rn_operand(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
-template <int CS, bool BULK>
+template <int CS>
 __global__ void __launch_bounds__(small::kThreads, 1)
 wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
@@ -98,11 +98,8 @@ wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
       mbar_init(&u_empty[i], 1);
     }
     mbar_init(acc_full, 1);
-    // inbox: BULK -> one arrival (below) + the bytes of CS bulk copies; else one arrival per (tile row, cout half)
-    // thread of all CS sources = 2 * RO * CS
-    mbar_init(inbox_full, BULK ? 1 : 2 * kMB);
+    mbar_init(inbox_full, 2 * kMB);  // one arrival per (tile row, cout half) thread of all CS sources: 2 * RO * CS
     fence_mbar_init();
-    if (BULK) mbar_arrive_expect_tx(inbox_full, kInboxBytes);
   }
   __syncthreads();  // barriers are initialised CTA-wide; TMEM allocation below overlaps the first loads
   if constexpr (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -267,7 +264,6 @@ wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
     const bool evalid = pusher && erow < valid_rows;
     const int owner = erow / RO, lr = erow % RO;
     const uint32_t inbox_local = smem_u32(smem + kOffInbox);
-    const uint32_t stage_local = smem_u32(smem + kOffV);  // bulk mode: partial staged here (MMAs are complete)
     uint32_t dst, dst_bar;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
                  : "=r"(dst)
@@ -303,19 +299,7 @@ wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
           o[2][e] = s1[0] + s1[1] + s1[2];
           o[3][e] = s1[1] - s1[2] - s1[3];
         }
-        if (BULK) {
-          // stage in the idle V buffers as [row][px][32 couts] (chunks swizzled by the row); one bulk copy per owner below
-          if (pusher) {
-#pragma unroll
-            for (int px = 0; px < 4; ++px)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint32_t pos = (uint32_t)((c0 / 4 + h) ^ (lr & 7));
-                st_shared_v4(stage_local + (uint32_t)(erow * 4 + px) * (kKN * 4) + pos * 16, o[px][4 * h],
-                             o[px][4 * h + 1], o[px][4 * h + 2], o[px][4 * h + 3]);
-              }
-          }
-        } else if (evalid) {
+        if (evalid) {
 #pragma unroll
           for (int px = 0; px < 4; ++px)
 #pragma unroll
@@ -330,25 +314,9 @@ wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
     }
     tc_fence_before();
     if (threadIdx.x == 0) WG_TS(8);
-    if constexpr (BULK) {
-      // one cp.async.bulk shared::cta -> shared::cluster per owner: its RO rows of this CTA's partial, completion
-      // counted in bytes on the owner's inbox barrier (which expects CS * RO * 512 bytes)
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kWorkerWarps) : "memory");
-      if (threadIdx.x < CS) {
-        constexpr uint32_t kPart = RO * 4 * kKN * 4;
-        uint32_t rdst, rbar;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                     : "=r"(rdst)
-                     : "r"(inbox_local + crank * kPart), "r"(threadIdx.x));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(inbox_full)), "r"(threadIdx.x));
-        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                         "r"(rdst), "r"(stage_local + threadIdx.x * kPart), "r"(kPart), "r"(rbar)
-                     : "memory");
-      }
-    } else {
-      if (pusher) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(dst_bar) : "memory");
-    }
+    // (staging the partial locally and sending it with one cp.async.bulk shared::cta -> shared::cluster per owner was
+    // measured too: the copies are faster, but every CTA then has to outwait its peers before it may retire -- a net loss)
+    if (pusher) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(dst_bar) : "memory");
     if (threadIdx.x == 0) WG_TS(9);
 
     // ------------------------------------------------------------------ owner: sum the CS partials, BN, ReLU, store
@@ -410,9 +378,6 @@ wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
     __syncwarp();  // the single-lane roles rejoin their warps
     if constexpr (CS > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // pairs with the arrive above
   }
-  // bulk mode: a CTA's outgoing copies read its shared memory until the owners' barriers complete, so nobody leaves
-  // before every CTA of the cluster has seen its inbox full
-  if constexpr (CS > 1 && BULK) cluster_sync_all();
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc<512>(*tmem_ptr);
@@ -442,7 +407,7 @@ int wino_small_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
 }
 
 // clusters of CS CTAs of this kernel that can be resident at once (0: not launchable); cached per device
-template <int CS, bool BULK = false>
+template <int CS>
 static int small_max_clusters() {
   static int cached[64];
   int dev_ = 0;
@@ -450,15 +415,11 @@ static int small_max_clusters() {
   int& slot = cached[dev_ & 63];
   if (slot == 0) {
     int n = 0;
-    bool ok = cudaFuncSetAttribute(wino3x3_small_kernel<CS, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    bool ok = cudaFuncSetAttribute(wino3x3_small_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)small::kTotal) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(wino3x3_small_kernel<CS, !BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)small::kTotal) == cudaSuccess;
     if (ok && CS > 8)
-      ok = cudaFuncSetAttribute(wino3x3_small_kernel<CS, BULK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
-               cudaSuccess &&
-           cudaFuncSetAttribute(wino3x3_small_kernel<CS, !BULK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
-               cudaSuccess;
+      ok = cudaFuncSetAttribute(wino3x3_small_kernel<CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
+           cudaSuccess;
     if (ok && CS == 1) {
       cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev_);
     } else if (ok) {
@@ -473,7 +434,7 @@ static int small_max_clusters() {
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      if (cudaOccupancyMaxActiveClusters(&n, wino3x3_small_kernel<CS, BULK>, &cfg) != cudaSuccess) n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, wino3x3_small_kernel<CS>, &cfg) != cudaSuccess) n = 0;
     }
     cudaGetLastError();
     slot = n > 0 ? n : -1;
@@ -481,7 +442,7 @@ static int small_max_clusters() {
   return slot > 0 ? slot : 0;
 }
 
-template <int CS, bool BULK>
+template <int CS>
 static int launch_small(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                         int n_img, int C, int K, int relu, int out_padded, int n_items, int debug,
                         cudaStream_t stream) {
@@ -506,7 +467,7 @@ static int launch_small(const CUtensorMap& tmap, const float* u_img, const float
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_small_kernel<CS, BULK>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_small_kernel<CS>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
                                      out_padded, debug);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
@@ -550,16 +511,8 @@ int wino_small_launch(const CUtensorMap& tmap_small, const float* u_plain, const
     debug = e ? atoi(e) : 0;
   }
   const int n_items = ((n_img * 49 + small::kMB - 1) / small::kMB) * (K / small::kKN);
-  static int bulk = -1;  // WG_WINO_BULK=0: per-thread st.shared::cluster pushes instead of bulk DSMEM copies
-  if (bulk < 0) {
-    const char* e = getenv("WG_WINO_BULK");
-    bulk = e ? atoi(e) : 1;
-  }
-#define WG_SMALL(CS_)                                                                                              \
-  return bulk ? launch_small<CS_, true>(tmap_small, u_plain, scale, shift, y, n_img, C, K, relu, out_padded,      \
-                                        n_items, debug, stream)                                                    \
-              : launch_small<CS_, false>(tmap_small, u_plain, scale, shift, y, n_img, C, K, relu, out_padded,     \
-                                         n_items, debug, stream)
+#define WG_SMALL(CS_) \
+  return launch_small<CS_>(tmap_small, u_plain, scale, shift, y, n_img, C, K, relu, out_padded, n_items, debug, stream)
   if (cs == 2) WG_SMALL(2);
   if (cs == 4) WG_SMALL(4);
   if (cs == 8) WG_SMALL(8);

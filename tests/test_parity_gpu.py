@@ -84,11 +84,14 @@ def test_3x3_ragged_batches(lib_loaded, torch_cuda, n, c, k, relu):
 
 
 @pytest.mark.parametrize("n,c,k", [(1, 128, 128), (1, 256, 256), (2, 256, 256), (4, 128, 128), (1, 64, 64), (3, 32, 64),
-                                   (9, 128, 128)])
+                                   (9, 128, 128), (6, 256, 256), (8, 128, 128), (1, 8, 32), (1, 256, 32), (2, 16, 64),
+                                   (1, 24, 32), (5, 512, 64)])
 @pytest.mark.parametrize("padded", [False, True])
 def test_3x3_small_batch_split_c_mode(lib_loaded, torch_cuda, n, c, k, padded):
-    """Small batches take the latency path: a cluster of 4/8 CTAs splits the channel loop and reduces partial outputs
-    through distributed shared memory. Same tolerance, zero border, every image checked."""
+    """Small batches take the latency kernel (wino_small_kernel.cu): one 64-tile x 32-cout item per cluster of 2..16
+    CTAs, M=64 MMAs, channel loop split over the cluster, partial outputs reduced through distributed shared memory
+    (every split factor the host can pick is hit by one of these shapes; C=24 has none and falls back). Same
+    tolerance, zero border, every image checked."""
     torch = torch_cuda
     x, w, sc, sh = _rand3x3(np.random.RandomState(400 + n + c), n, c, k)
     layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True)
@@ -138,7 +141,42 @@ def test_bf16_is_rejected_where_it_does_not_exist(lib_loaded):
                                  np.ones(32, np.float32), dtype=lib_loaded.WG_BF16)
 
 
-@pytest.mark.parametrize("n,cin,cout", [(1, 32, 128), (2, 96, 256), (3, 64, 384), (7, 512, 128)])
+@pytest.mark.parametrize("n", [1, 4, 64])
+def test_back_to_back_launches_are_ordered(lib_loaded, torch_cuda, n):
+    """Every kernel is launched with programmatic dependent launch: the next launch may start while the previous one
+    still runs and must wait (griddepcontrol.wait) before it touches activations. A ping-pong chain 3x3 -> 1x1 -> 3x3
+    -> ... over two buffers, 24 launches with no host sync, must give bit-identical results to the same chain with a
+    device synchronize after every launch (a missed dependency would read half-written frames)."""
+    torch = torch_cuda
+    rs = np.random.RandomState(900 + n)
+    c = 128
+    w3 = ((rs.rand(c, c, 3, 3) - 0.5) * 0.1).astype(np.float32)
+    w1 = ((rs.rand(c, c) - 0.5) * 0.2).astype(np.float32)
+    sc, sh = (rs.rand(c) + 0.5).astype(np.float32), (rs.rand(c) - 0.5).astype(np.float32)
+    l3 = lib_loaded.Conv3x3BnRelu(w3, sc, sh, relu=True)
+    l1 = lib_loaded.Conv1x1Bn(w1, sc, sh, relu=True)
+    x0 = torch.from_numpy((rs.rand(n, 16, 16, c) - 0.5).astype(np.float32)).cuda()
+
+    def chain(sync):
+        frame = x0.clone()
+        dense = torch.empty((n, 196, c), device="cuda")
+        for _ in range(12):
+            l3(frame, out=dense.view(n, 14, 14, c))          # frame -> dense
+            if sync:
+                torch.cuda.synchronize()
+            l1(dense, out=frame, out_padded=True)            # dense -> the same frame buffer (zero border rewritten)
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return frame.cpu().numpy()
+
+    a, b = chain(False), chain(True)
+    assert np.isfinite(a).all() and np.abs(a).max() > 0
+    np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,cin,cout", [(1, 32, 128), (2, 96, 256), (3, 64, 384), (7, 512, 128), (4, 256, 1024),
+                                        (2, 1024, 256), (1, 128, 512), (6, 2048, 128)])
 def test_1x1_ragged_batches(lib_loaded, torch_cuda, n, cin, cout):
     torch = torch_cuda
     rs = np.random.RandomState(200 + n)
