@@ -265,6 +265,27 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// registers -> TMEM: thread i of the warp writes 4 consecutive 32-bit columns of lane base+i (same addressing as the
+// 32x32b loads below). tmem_st_wait() makes the stores of this thread complete before a following fence / arrive.
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32: A is read from TMEM (lane = row, 8 consecutive 32-bit columns = the
+// K=8 slice), so the A operand costs no shared-memory bandwidth.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x N consecutive 32-bit columns (thread i <- lane base+i).
 __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float* v) {
   uint32_t r0, r1, r2, r3;

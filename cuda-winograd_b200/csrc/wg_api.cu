@@ -15,7 +15,7 @@ namespace wg {
 static thread_local char g_last_cuda_error[256] = "";
 static std::atomic<long long> g_launches{0};
 static int g_max_ctas = 0;  // 0 = number of SMs
-static int g_wino_kn = 64;  // 64 = folded accumulation (default), 32 = one accumulator per Winograd point
+static int g_wino_kn = 48;  // 48 = V-in-TMEM kernel (default); 64 / 32 = the shared-memory-operand kernels (folded / per point)
 
 static int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
@@ -135,7 +135,9 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   float* d_w = nullptr;
   size_t filter_elems = 0;
   if (kind == 0) {
-    L->tile_n = (dtype != WG_TF32) ? 64 : ((g_wino_kn == 32 || cout % 64 != 0) ? 32 : 64);
+    if (dtype != WG_TF32) L->tile_n = 64;
+    else if (g_wino_kn == 48) L->tile_n = 48;
+    else L->tile_n = (g_wino_kn == 32 || cout % 64 != 0) ? 32 : 64;
     filter_elems = (size_t)16 * cin * cout;
   } else {
     L->tile_n = (cout % 256 == 0) ? 256 : 128;
@@ -157,8 +159,9 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   WG_TRY(cudaMemcpyAsync(d_w, w, w_elems * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_scale, scale, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
-  rc = kind == 0 ? filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)dtype, L->stream)
-                 : weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
+  if (kind == 0 && L->tile_n == 48) rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->stream);
+  else if (kind == 0) rc = filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)dtype, L->stream);
+  else rc = weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
   g_launches++;
   if (rc == WG_OK && kind == 0 && dtype == WG_TF32) {
     if (L->tile_n == 32) {
@@ -222,8 +225,9 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
     }
   }
   if (L->tmap_x != x || L->tmap_n != N) {
-    int rc = L->kind == 0 ? wino_make_tmap(&L->tmap, x, N, L->cin)
-                          : one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin);
+    int rc = L->kind == 1 ? one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin)
+             : L->tile_n == 48 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin)
+                               : wino_make_tmap(&L->tmap, x, N, L->cin);
     if (rc != WG_OK) return rc;
     L->tmap_x = x;
     L->tmap_n = N;
@@ -235,7 +239,10 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
     L->tmap_y_n = N;
   }
   int rc;
-  if (L->kind == 0)
+  if (L->kind == 0 && L->tile_n == 48)
+    rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->relu,
+                        out_padded ? 1 : 0, max_ctas, stream);
+  else if (L->kind == 0)
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,
                      L->dtype, L->relu, out_padded ? 1 : 0, max_ctas, stream);
   else
@@ -381,6 +388,6 @@ void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean,
 }
 
 void wg_set_max_ctas(int max_ctas) { g_max_ctas = max_ctas; }
-void wg_set_wino_kn(int kn) { g_wino_kn = (kn == 32) ? 32 : 64; }
+void wg_set_wino_kn(int kn) { g_wino_kn = (kn == 32 || kn == 64) ? kn : 48; }
 
 }  // extern "C"

@@ -1,0 +1,536 @@
+// Fused 3x3 conv (Winograd F(2x2,3x3)) + folded BatchNorm + ReLU for sm_100a -- throughput kernel, TF32 operands,
+// transformed input V kept in TENSOR MEMORY as the MMA's A operand.
+//
+// Replaces kernel_{128,256}_winograd_BtdB -> kernel_*_OuterProduct_* -> kernel_*_winograd_AtIA
+// (/root/reference/Kernel128_winograd.cu:28-213, Kernel256_winograd.cu:27-218). Same decomposition as
+// wino3x3_bn_relu_kernel (winograd_kernels.cu: 128-tile M-blocks x cout slices, 8-channel stages, folded accumulation
+// Z[a][j] = sum_i A^T[a][i] M[i][j] with the negate-A bit), but that kernel was bound by the shared-memory data path:
+// per stage it moved 64 KB of V stores + 96 KB of A-operand reads through it, on top of the raw-tile loads. Here
+//
+//   * the transform warps write V = B^T d B straight from registers into TMEM (tcgen05.st, thread = tile row,
+//     4 channels = 4 columns) and the MMA reads A from there (tcgen05.mma ... [d], [a_tmem], b_desc): no V in shared
+//     memory at all, and the MMA runs at the tensor-core floor (measured 27.7 clk for M=128 N=48 K=8 vs 53 clk with
+//     A and B in shared memory, tools/selftest ts|mma);
+//   * TMEM budget: 8 folded accumulators x 48 couts = 384 columns + two 64-column V halves (8 points x 8 channels
+//     each; half jh holds the points with j in {2jh, 2jh+1}) = 512. So cout slices are 48 wide (then 32 for the
+//     remainder: 256 = 4x48 + 2x32, 128 = 2x48 + 32), and V is single-buffered per half: the stores of stage s+1,
+//     half jh wait for the 12 MMAs of stage s, half jh (tcgen05.commit -> v_empty[jh]) while its loads and FADDs overlap
+//     them;
+//   * raw tiles land through a SWIZZLE_32B tensor map so that 32 consecutive tile rows (one warp) read their 16-byte
+//     channel halves without systematic bank conflicts;
+//   * the epilogue stages relu(scale*Y+shift) in its own shared-memory area ([tile][pixel][couts], rows padded by 16 B)
+//     and writes full runs per output pixel.
+#include "ptx.cuh"
+#include "wg_internal.h"
+
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace wg {
+
+namespace tm {
+constexpr int kWorkerWarps = 8;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kThreads = 32 * 10;
+constexpr int kRawRows = 48;  // input rows (n*16+y) one 128-tile M-block can touch
+constexpr uint32_t kRawBytes = kRawRows * 2 * 8 * 32;  // [ny][x parity][x/2][8 ch] fp32 = 24576
+constexpr int kRawStages = 3, kUBufs = 4;
+constexpr int kKNmax = 48;
+constexpr uint32_t kUChunkMax = 8 * 2 * kKNmax * 16;   // 8 points x [2 k-chunks][KN couts][4 ch] = 12288
+constexpr uint32_t kStgBytes = 128 * (16 * kKNmax + 16);  // [128 tiles][4 px][KN couts] fp32, tile rows padded by 16 B
+constexpr uint32_t kAccStride = 48;                    // TMEM columns between the 8 accumulators
+constexpr uint32_t kVCol0 = 8 * kAccStride;            // 384: V half jh at kVCol0 + 64*jh, point p8 at +8*p8
+constexpr uint32_t kOffRaw = 0;
+constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawBytes;
+constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
+constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
+constexpr uint32_t kOffBar = kOffPix + 128 * 4;
+constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kUBufs + 4 + 2;
+constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr uint32_t kTotal = kOffTmemPtr + 16;
+static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kTotal <= 227 * 1024, "shared memory budget");
+}  // namespace tm
+
+__device__ __forceinline__ float tm_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
+__global__ void __launch_bounds__(tm::kThreads, 1)
+wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
+                  const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
+                  int C, int K, int n48, int relu, int out_padded, int mv) {
+  using namespace tm;
+  pdl_launch_dependents();  // the next launch in the stream may start its prologue (it waits before touching x / y)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* raw_full = bars;
+  uint64_t* raw_empty = raw_full + kRawStages;
+  uint64_t* u_full = raw_empty + kRawStages;
+  uint64_t* u_empty = u_full + kUBufs;
+  uint64_t* v_full = u_empty + kUBufs;  // [2] per V half
+  uint64_t* v_empty = v_full + 2;       // [2]
+  uint64_t* acc_full = v_empty + 2;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
+  int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < kRawStages; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], kWorkerWarps);
+    }
+    for (int i = 0; i < kUBufs; ++i) {
+      mbar_init(&u_full[i], 1);
+      mbar_init(&u_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], kWorkerWarps);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kWorkerWarps);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_kb = C / 8;
+  const int n_slices = n48 + (K - 48 * n48) / 32;
+  const int total_tiles = n_img * 49;
+  const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host to balance waves
+  const int n_items = n_mblocks * n_slices;
+  const int item0 = blockIdx.x, item_step = gridDim.x;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t rs = 0, rph = 0, us = 0, uph = 0;
+      bool u_primed = false;
+      if (item0 < n_items) {
+        // the filter does not depend on the previous kernel in the stream: request the first stage's U chunks before
+        // waiting for that kernel (programmatic dependent launch), the activations after
+        const int s = item0 % n_slices;
+        const int kn = s < n48 ? 48 : 32;
+        const int c0 = s < n48 ? 48 * s : 48 * n48 + 32 * (s - n48);
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
+        for (int h = 0; h < 2; ++h) {
+          mbar_arrive_expect_tx(&u_full[us], 256u * kn);
+          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (size_t)h * 256 * kn, 256u * kn, &u_full[us]);
+          ++us;
+        }
+        u_primed = true;
+      }
+      pdl_wait();
+      for (int item = item0; item < n_items; item += item_step) {
+        const int s = item % n_slices;
+        const int mb = item / n_slices;
+        const int kn = s < n48 ? 48 : 32;
+        const int c0 = s < n48 ? 48 * s : 48 * n48 + 32 * (s - n48);
+        const int t0 = mb * mv;
+        const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&raw_empty[rs], rph ^ 1);
+          mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
+          tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
+          if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          if (u_primed) {  // already requested above
+            u_primed = false;
+            continue;
+          }
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&u_empty[us], uph ^ 1);
+            mbar_arrive_expect_tx(&u_full[us], 256u * kn);
+            tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)kb * 2 + h) * 256 * kn, 256u * kn,
+                         &u_full[us]);
+            if (++us == kUBufs) { us = 0; uph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    if (elect_one()) {
+      const uint32_t u_base = smem_u32(smem + kOffU);
+      uint32_t vph = 0, us = 0, uph = 0, aph = 0;
+      for (int item = item0; item < n_items; item += item_step) {
+        const int s = item % n_slices;
+        const uint32_t kn = s < n48 ? 48u : 32u;
+        const uint32_t idesc = make_idesc(kFmtTF32, 128, kn);
+        const uint32_t idesc_neg = make_idesc(kFmtTF32, 128, kn, 1);  // D += (-A) * B
+        const uint32_t u_per_point = 2 * kn * 16, u_lbo = kn * 16;
+        mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
+        tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb) {
+          const uint32_t acc = kb > 0 ? 1u : 0u;
+#pragma unroll
+          for (int jh = 0; jh < 2; ++jh) {
+            mbar_wait(&v_full[jh], vph);
+            mbar_wait(&u_full[us], uph);
+            tc_fence_after();
+            const uint32_t ua = u_base + us * kUChunkMax;
+            const uint32_t va = tmem_base + kVCol0 + jh * 64;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = jh * 2 + jj;
+              const uint32_t z0 = tmem_base + (j * 2 + 0) * kAccStride;  // Z[0][j] = M0j + M1j + M2j
+              const uint32_t z1 = tmem_base + (j * 2 + 1) * kAccStride;  // Z[1][j] = M1j - M2j - M3j
+              uint64_t b_desc[4];
+              uint32_t a_tm[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                a_tm[i] = va + (i * 2 + jj) * 8;
+                b_desc[i] = make_smem_desc(ua + (i * 2 + jj) * u_per_point, u_lbo, 128, kLayoutNone);
+              }
+              umma_tf32_ts(z0, a_tm[1], b_desc[1], idesc, acc);  // first writer of both accumulators
+              umma_tf32_ts(z1, a_tm[1], b_desc[1], idesc, acc);
+              umma_tf32_ts(z0, a_tm[0], b_desc[0], idesc, 1u);
+              umma_tf32_ts(z0, a_tm[2], b_desc[2], idesc, 1u);
+              umma_tf32_ts(z1, a_tm[2], b_desc[2], idesc_neg, 1u);
+              umma_tf32_ts(z1, a_tm[3], b_desc[3], idesc_neg, 1u);
+            }
+            umma_commit(&u_empty[us]);
+            umma_commit(&v_empty[jh]);  // this V half may be overwritten with the next stage
+            if (++us == kUBufs) { us = 0; uph ^= 1; }
+          }
+          vph ^= 1;
+        }
+        umma_commit(acc_full);
+        aph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ transform + epilogue warps
+    // thread = (tile row of the M-block = TMEM lane, 4-channel half): warp w owns TMEM lanes 32*(w&3)..+31
+    const int quad = warp & 3;
+    const int half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t raw_base = smem_u32(smem + kOffRaw);
+    const uint32_t stg_base = smem_u32(smem + kOffStg);
+
+    uint32_t rs = 0, rph = 0, vph = 0, aph = 0;
+    for (int item = item0; item < n_items; item += item_step) {
+      const int s = item % n_slices;
+      const int mb = item / n_slices;
+      const int kn = s < n48 ? 48 : 32;
+      const int c0s = s < n48 ? 48 * s : 48 * n48 + 32 * (s - n48);
+      const int t0 = mb * mv;
+      const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+      const int T = t0 + row;
+      const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
+      const bool tvalid = row < valid_rows;
+      const bool warp_active = quad * 32 < valid_rows;  // warp-uniform
+      const int n = T / 49, t = T % 49, ty = t / 7, tx = t % 7;
+      const uint32_t raw_off = tvalid ? (uint32_t)((n * 16 + 2 * ty - ny0) * 512 + tx * 32) : 0u;
+      // SWIZZLE_32B: the 16-byte half of a pixel's 32 bytes is XORed with bit 2 of its x/2 index (address bit 7)
+      const uint32_t h0 = (uint32_t)((half ^ ((tx >> 2) & 1)) * 16);        // pixels with x/2 = tx
+      const uint32_t h1 = (uint32_t)((half ^ (((tx + 1) >> 2) & 1)) * 16);  // pixels with x/2 = tx + 1
+
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&raw_full[rs], rph);
+        if (!warp_active) {
+          // nothing to transform: release the raw stage and report "V ready" in step with the other warps
+          if (lane == 0) mbar_arrive(&raw_empty[rs]);
+          if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+#pragma unroll
+          for (int jh = 0; jh < 2; ++jh) {
+            mbar_wait(&v_empty[jh], vph ^ 1);
+            if (lane == 0) mbar_arrive(&v_full[jh]);
+          }
+          vph ^= 1;
+          continue;
+        }
+        float4 d[4][4];
+        if (tvalid) {
+          const uint32_t a = raw_base + rs * kRawBytes + raw_off;
+#pragma unroll
+          for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx)
+              d[dy][dx] = ld_shared_v4(a + dy * 512 + (dx & 1) * 256 + (dx >> 1) * 32 + ((dx >> 1) ? h1 : h0));
+        } else {
+#pragma unroll
+          for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx) d[dy][dx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // column pass t = B^T d, in place over dy
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+          const float4 d0 = d[0][dx], d1 = d[1][dx], d2 = d[2][dx], d3 = d[3][dx];
+          d[0][dx] = make_float4(d0.x - d2.x, d0.y - d2.y, d0.z - d2.z, d0.w - d2.w);
+          d[1][dx] = make_float4(d1.x + d2.x, d1.y + d2.y, d1.z + d2.z, d1.w + d2.w);
+          d[2][dx] = make_float4(d2.x - d1.x, d2.y - d1.y, d2.z - d1.z, d2.w - d1.w);
+          d[3][dx] = make_float4(d1.x - d3.x, d1.y - d3.y, d1.z - d3.z, d1.w - d3.w);
+        }
+        // the raw stage is in registers now: hand it back to the producer before the row pass
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+
+        // row pass V = t B by halves (half jh = points with j in {2jh, 2jh+1}), round to TF32, store into TMEM
+        const uint32_t vcol = tmem_base + lane_base + kVCol0 + (uint32_t)half * 4;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+          mbar_wait(&v_empty[jh], vph ^ 1);  // the MMAs that read this half (previous stage) have completed
+          tc_fence_after();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
+            const uint32_t dst = vcol + jh * 64 + (i * 2) * 8;
+            if (jh == 0) {
+              tmem_st_x4(dst, tm_tf32(a0.x - a2.x), tm_tf32(a0.y - a2.y), tm_tf32(a0.z - a2.z), tm_tf32(a0.w - a2.w));
+              tmem_st_x4(dst + 8, tm_tf32(a1.x + a2.x), tm_tf32(a1.y + a2.y), tm_tf32(a1.z + a2.z),
+                         tm_tf32(a1.w + a2.w));
+            } else {
+              tmem_st_x4(dst, tm_tf32(a2.x - a1.x), tm_tf32(a2.y - a1.y), tm_tf32(a2.z - a1.z), tm_tf32(a2.w - a1.w));
+              tmem_st_x4(dst + 8, tm_tf32(a1.x - a3.x), tm_tf32(a1.y - a3.y), tm_tf32(a1.z - a3.z),
+                         tm_tf32(a1.w - a3.w));
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&v_full[jh]);
+        }
+        vph ^= 1;
+      }
+
+      // ---- epilogue: rest of Y = A^T M A, BN, ReLU, staged, written out as full runs per pixel
+      const bool evalid = tvalid;
+      const int W = out_padded ? 16 : 14;
+      const int o = out_padded ? 1 : 0;
+      const int pix0 = evalid ? ((n * W + 2 * ty + o) * W + 2 * tx + o) : -1;  // first output pixel of this tile
+      if (half == 0) pixtab[row] = pix0;
+      const uint32_t tstride = (uint32_t)(16 * kn + 16);
+      const int ncc = kn / 2;  // couts drained by this warp: [half*ncc, (half+1)*ncc)
+
+      mbar_wait(acc_full, aph);
+      aph ^= 1;
+      tc_fence_after();
+      if (warp_active) {
+#pragma unroll 1
+        for (int cc = 0; cc < ncc; cc += 8) {
+          const int c0 = half * ncc + cc;
+          const uint32_t taddr = tmem_base + lane_base + c0;
+          float z[8][8];  // z[j*2 + a][e]
+#pragma unroll
+          for (int p = 0; p < 8; ++p) tmem_ld_x8(taddr + p * kAccStride, z[p]);
+          tmem_ld_wait();
+          const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + c0s + c0));
+          const float4 sc1 = __ldg(reinterpret_cast<const float4*>(scale + c0s + c0 + 4));
+          const float4 sh0 = __ldg(reinterpret_cast<const float4*>(shift + c0s + c0));
+          const float4 sh1 = __ldg(reinterpret_cast<const float4*>(shift + c0s + c0 + 4));
+          const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+          const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+          float ov[4][8];  // Y[a][b] at ov[2*a + b]
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ov[0][e] = fmaf(sc[e], z[0][e] + z[2][e] + z[4][e], sh[e]);
+            ov[1][e] = fmaf(sc[e], z[2][e] - z[4][e] - z[6][e], sh[e]);
+            ov[2][e] = fmaf(sc[e], z[1][e] + z[3][e] + z[5][e], sh[e]);
+            ov[3][e] = fmaf(sc[e], z[3][e] - z[5][e] - z[7][e], sh[e]);
+            if (relu) {
+#pragma unroll
+              for (int p = 0; p < 4; ++p) ov[p][e] = fmaxf(ov[p][e], 0.f);
+            }
+          }
+          const uint32_t sdst = stg_base + (uint32_t)row * tstride + (uint32_t)c0 * 4;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            st_shared_v4(sdst + p * (4 * kn), ov[p][0], ov[p][1], ov[p][2], ov[p][3]);
+            st_shared_v4(sdst + p * (4 * kn) + 16, ov[p][4], ov[p][5], ov[p][6], ov[p][7]);
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging + pixel table complete, TMEM drained by all 8 warps
+      if (lane == 0) mbar_arrive(acc_empty);
+      {
+        const int tid = threadIdx.x;  // 0..255
+        const int chunks = kn / 4;    // 16-byte chunks per pixel
+        const int units = valid_rows * kn;  // (tile, pixel, chunk)
+        for (int u = tid; u < units; u += kWorkerWarps * 32) {
+          const int tile = u / kn;
+          const int r = u - tile * kn;
+          const int px = r / chunks;
+          const int ch = r - px * chunks;
+          const float4 v = ld_shared_v4(stg_base + (uint32_t)tile * tstride + (uint32_t)(px * 4 * kn + ch * 16));
+          const int pix = pixtab[tile] + (px >> 1) * W + (px & 1);
+          *reinterpret_cast<float4*>(y + (size_t)pix * K + c0s + ch * 4) = v;
+        }
+        if (out_padded && evalid && (ty == 0 || ty == 6 || tx == 0 || tx == 6)) {
+          // zero border of the reference's 16x16 frame (Kernel128_winograd.cu:163,243): edge tiles own their share
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const size_t rstride = (size_t)W * K;
+          float* p = y + (size_t)pix0 * K + c0s + half * ncc;
+          const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
+          const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
+#pragma unroll 1
+          for (int e = 0; e < ncc; e += 4) {
+            if (dyb != 0) {
+              *reinterpret_cast<float4*>(p + dyb + e) = z4;
+              *reinterpret_cast<float4*>(p + dyb + K + e) = z4;
+            }
+            if (dxb != 0) {
+              *reinterpret_cast<float4*>(p + dxb + e) = z4;
+              *reinterpret_cast<float4*>(p + dxb + rstride + e) = z4;
+            }
+            if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(p + dyb + dxb + e) = z4;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging area and pixel table free for the next item
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Once per layer: U = G g G^T (F(2x2,3x3)), RN-rounded to TF32, in the shared-memory image of this kernel's bulk
+// copies: cout slices of 48 (n48 of them) then 32; per slice [C/8 k-block][2 j-halves][4 i][2 jj][2 k-chunks][KN couts]
+// [4 channels] (j = 2*jh + jj). 512 bytes per (k-block, cout), so slice s starts at byte (C/8)*512*c0(s).
+// Replaces the offline weight_generator loop (/root/reference/data_generator.py:63-78; that one is F(4x4), 36 points).
+__global__ void filter_transform_tm_kernel(const float* __restrict__ w_kcrs, float* __restrict__ u_img, int C, int K,
+                                           int n48) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * K) return;
+  const int ch = idx % C;
+  const int k = idx / C;
+  const float* g = w_kcrs + ((size_t)k * C + ch) * 9;
+  float gg[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) gg[r][s] = g[r * 3 + s];
+  float tt[4][3];  // t = G g
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    tt[0][s] = gg[0][s];
+    tt[1][s] = 0.5f * (gg[0][s] + gg[1][s] + gg[2][s]);
+    tt[2][s] = 0.5f * (gg[0][s] - gg[1][s] + gg[2][s]);
+    tt[3][s] = gg[2][s];
+  }
+  int kn, c0;
+  if (k < 48 * n48) {
+    kn = 48;
+    c0 = (k / 48) * 48;
+  } else {
+    kn = 32;
+    c0 = 48 * n48 + ((k - 48 * n48) / 32) * 32;
+  }
+  const int kl = k - c0;
+  const int kb = ch / 8, chunk = (ch % 8) / 4, e = ch % 4;
+  const size_t base = (size_t)(C / 8) * 128 * c0 + (size_t)kb * 128 * kn;  // floats
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float u[4];
+    u[0] = tt[i][0];
+    u[1] = 0.5f * (tt[i][0] + tt[i][1] + tt[i][2]);
+    u[2] = 0.5f * (tt[i][0] - tt[i][1] + tt[i][2]);
+    u[3] = tt[i][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = (j >> 1) * 8 + i * 2 + (j & 1);
+      u_img[base + (size_t)p * (2 * kn * 4) + ((size_t)chunk * kn + kl) * 4 + e] = to_tf32_rn(u[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+
+int wino_tm_n48(int K) {  // 48*a + 32*b = K with a as large as possible
+  const int m = K / 16;
+  int a = m / 3;
+  while (a > 0 && ((m - 3 * a) & 1)) --a;
+  return a;
+}
+
+int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return WG_ERR_DRIVER;
+  // x[N][16][16][C] viewed as (c, x/2, x&1, n*16+y), 32-byte swizzle on the 8-channel inner box
+  cuuint64_t dims[4] = {(cuuint64_t)C, 8, 2, (cuuint64_t)n_img * 16};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * C * 4, (cuuint64_t)C * 4, (cuuint64_t)16 * C * 4};
+  cuuint32_t box[4] = {8, 8, 2, (cuuint32_t)tm::kRawRows};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, wg::l2_promotion(),
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
+}
+
+int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, cudaStream_t stream) {
+  const int n = C * K;
+  filter_transform_tm_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, wino_tm_n48(K));
+  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                   int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+  static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
+  if (!(configured & dev_bit_)) {
+    if (cudaFuncSetAttribute(wino3x3_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm::kTotal) !=
+        cudaSuccess)
+      return WG_ERR_CUDA;
+    configured |= dev_bit_;
+  }
+  const int n48 = wino_tm_n48(K);
+  const int n_slices = n48 + (K - 48 * n48) / 32;
+  const int total_tiles = n_img * 49;
+  // Tiles per M-block: the MMA is always M=128 but only `mv` rows carry tiles; transform warps own 32 rows each, so
+  // the per-item cost scales with ceil(mv/32) quarters. Pick the mv that minimises waves x cost (WG_WINO_MV pins it).
+  int mv = 128;
+  static int mv_env = -1;
+  if (mv_env < 0) {
+    const char* e = getenv("WG_WINO_MV");
+    mv_env = e ? atoi(e) : 0;
+  }
+  if (mv_env >= 16 && mv_env <= 128) {
+    mv = mv_env;
+  } else {
+    double best = 1e30;
+    for (int cand = 128; cand >= 64; cand -= 32) {
+      const long long items = (long long)((total_tiles + cand - 1) / cand) * n_slices;
+      const long long waves = (items + max_ctas - 1) / max_ctas;
+      const double cost = (double)waves * (0.35 + 0.65 * cand / 128.0);
+      if (cost < best - 1e-9) {
+        best = cost;
+        mv = cand;
+      }
+    }
+  }
+  const int n_items = ((total_tiles + mv - 1) / mv) * n_slices;
+  int grid = n_items < max_ctas ? n_items : max_ctas;
+  if (grid < 1) grid = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(tm::kThreads);
+  cfg.dynamicSmemBytes = tm::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_tm_kernel, tmap, u_img, scale, shift, y, n_img, C, K, n48, relu,
+                                     out_padded, mv);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+}  // namespace wg

@@ -83,8 +83,9 @@ int wg_device_count(void);              /* number of sm_100 devices visible; 0 =
 void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                 float* scale_out, float* shift_out);
 
-/* Tuning knobs (process-wide; for benchmarking): max CTAs per launch (default = #SMs); 3x3 kernel variant for layers
- * created afterwards: 64 = folded accumulation, 64 couts per CTA (default), 32 = one TMEM accumulator per Winograd point. */
+/* Tuning knobs (process-wide; for benchmarking): max CTAs per launch (default = #SMs); 3x3 TF32 kernel variant for
+ * layers created afterwards: 48 = transformed input kept in tensor memory, cout slices of 48/32 (default); 64 / 32 = the
+ * earlier kernels with both MMA operands in shared memory (folded accumulation / one accumulator per Winograd point). */
 void wg_set_max_ctas(int max_ctas);
 void wg_set_wino_kn(int kn);
 

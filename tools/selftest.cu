@@ -425,6 +425,112 @@ static void time_mma(int count, int acc_stride, int distinct_ops) {
          MODE, M, N, count, acc_stride, distinct_ops ? "16 distinct" : "same       ", h[0], h[1], (double)h[1] / count);
 }
 
+// ------------------------------------------------------------------------------------------------ A-from-TMEM probe
+// tcgen05.mma kind::tf32 with the A operand in TMEM: A[128][8] written with tcgen05.st (thread = row, 8 columns),
+// B[48][8] in shared memory (no-swizzle K-major), D = A*B into columns 0..47, D2 = (-A)*B (negate-A bit) into columns
+// 64..111. Then `count` such MMAs back to back for the issue -> complete rate.
+__global__ void umma_ts_probe_kernel(const float* a, const float* b, float* d, long long* clk, int count) {
+  using namespace wg;
+  __shared__ __align__(1024) uint8_t sb[2 * 48 * 16];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 8; i += blockDim.x) {
+    const int r = i / 8, k = i % 8;
+    *reinterpret_cast<float*>(sb + (k / 4) * (48 * 16) + r * 16 + (k % 4) * 4) = b[i];
+  }
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc<512>(&tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tptr;
+  const uint32_t a_col = 256;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  tmem_st_x4(tb + lane_base + a_col, a[tid * 8 + 0], a[tid * 8 + 1], a[tid * 8 + 2], a[tid * 8 + 3]);
+  tmem_st_x4(tb + lane_base + a_col + 4, a[tid * 8 + 4], a[tid * 8 + 5], a[tid * 8 + 6], a[tid * 8 + 7]);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  long long t0 = 0, t1 = 0;
+  if (tid < 32) {
+    if (elect_one()) {
+      const uint64_t bd = make_smem_desc(smem_u32(sb), 48 * 16, 128, kLayoutNone);
+      umma_tf32_ts(tb, tb + a_col, bd, make_idesc(kFmtTF32, 128, 48), 0);
+      umma_tf32_ts(tb + 64, tb + a_col, bd, make_idesc(kFmtTF32, 128, 48, 1), 0);
+      umma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  float v[16];
+  for (int c0 = 0; c0 < 112; c0 += 16) {
+    tmem_ld_x16(tb + lane_base + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) d[tid * 112 + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid < 32) {
+    if (elect_one()) {
+      const uint64_t bd = make_smem_desc(smem_u32(sb), 48 * 16, 128, kLayoutNone);
+      t0 = clock64();
+      for (int i = 0; i < count; ++i)
+        umma_tf32_ts(tb + (i & 3) * 48, tb + a_col, bd, make_idesc(kFmtTF32, 128, 48), 1u);
+      t1 = clock64();
+      umma_commit(&bar);
+      mbar_wait(&bar, 1);
+      clk[0] = t1 - t0;
+      clk[1] = clock64() - t0;
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<512>(tb);
+}
+
+static void run_ts_probe() {
+  std::vector<float> a(128 * 8), b(48 * 8), d(128 * 112);
+  for (auto& v : a) v = roundf(frand() * 16.f);
+  for (auto& v : b) v = roundf(frand() * 16.f);
+  float *da, *db, *dd;
+  long long* dc;
+  CK(cudaMalloc(&da, a.size() * 4));
+  CK(cudaMalloc(&db, b.size() * 4));
+  CK(cudaMalloc(&dd, d.size() * 4));
+  CK(cudaMalloc(&dc, 16));
+  CK(cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  umma_ts_probe_kernel<<<1, 128>>>(da, db, dd, dc, 96);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("TS probe: kernel failed: %s\n", cudaGetErrorString(e));
+    return;
+  }
+  long long clk[2];
+  CK(cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(clk, dc, 16, cudaMemcpyDeviceToHost));
+  double e1 = 0, e2 = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < 48; ++n) {
+      double ref = 0;
+      for (int k = 0; k < 8; ++k) ref += (double)a[m * 8 + k] * b[n * 8 + k];
+      e1 = fmax(e1, fabs(ref - d[m * 112 + n]));
+      e2 = fmax(e2, fabs(-ref - d[m * 112 + 64 + n]));
+    }
+  printf("TS probe (A from TMEM, M=128 N=48 K=8 tf32): max abs err %.3g, negate-A %.3g -> %s; 96 MMAs: issue %lld clk, "
+         "issue->complete %lld clk = %.1f clk/MMA\n",
+         e1, e2, (e1 == 0 && e2 == 0) ? "MATCH" : "mismatch", clk[0], clk[1], clk[1] / 96.0);
+}
+
 // ------------------------------------------------------------------------------------------------ launch floor
 // What an N=1 layer cannot go below: empty kernels launched back to back the way the product launches its own
 // (dynamic smem opt-in, 128-byte __grid_constant__ parameter, optional cluster), timed with the same event loop.
@@ -516,6 +622,10 @@ int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   printf("sm_100 devices: %d\n", wg_device_count());
   if (wg_device_count() == 0) return 1;
+  if (argc > 1 && !strcmp(argv[1], "ts")) {
+    run_ts_probe();
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "mma")) {
     for (int count : {1, 16, 96}) {
       time_mma<64, 32, 0>(count, 32, 1);
@@ -580,7 +690,7 @@ int main(int argc, char** argv) {
   auto bad = [&](double rel, double tol) {
     if (!(rel <= tol)) ++fails;
   };
-  for (int kn : {64, 32}) {
+  for (int kn : {48, 64, 32}) {
     wg_set_wino_kn(kn);
     printf("-- 3x3 variant KN=%d\n", kn);
     bad(check3x3(1, 128, 128, 1, 0, {0}), 1e-3);
@@ -593,7 +703,7 @@ int main(int argc, char** argv) {
       time_layer(0, 256, 256, 256, 1);
     }
   }
-  wg_set_wino_kn(64);
+  wg_set_wino_kn(48);
   g_dtype = WG_BF16;
   printf("-- 3x3 bf16 operand variant (tolerance 1e-2)\n");
   bad(check3x3(1, 128, 128, 1, 1, {0}), 1e-2);
