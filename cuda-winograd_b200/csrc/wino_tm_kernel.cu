@@ -172,8 +172,8 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           const uint32_t acc = kb > 0 ? 1u : 0u;
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
+            mbar_wait(&u_full[us], uph);  // there long before V: checked first, off the V -> MMA critical path
             mbar_wait(&v_full[jh], vph);
-            mbar_wait(&u_full[us], uph);
             tc_fence_after();
             const uint32_t ua = u_base + us * kUChunkMax;
             const uint32_t va = tmem_base + kVCol0 + jh * 64;

@@ -349,6 +349,90 @@ static void time_tma(int grid, int total, int pieces, int distinct) {
          (double)total / s[grid / 2]);
 }
 
+// ------------------------------------------------------------------------------------------------ TMA tensor-load probe
+// How fast does one SM's TMA unit deliver the 3x3 kernels' raw-tile boxes? x[N][16][16][C] viewed as
+// (c, x/2, x&1, n*16+y); box = (cb channels, 8, 2, rows): the inner run is only cb*4 bytes. `count` loads, `depth` in
+// flight, every CTA walks its own images; clk per load from thread 0 of each CTA.
+#include <cuda.h>
+__global__ void tma_tensor_probe_kernel(const __grid_constant__ CUtensorMap tmap, long long* out, int count, int depth,
+                                        int box_bytes, int n_img, int C, int cb) {
+  using namespace wg;
+  extern __shared__ __align__(1024) uint8_t dyn[];
+  __shared__ uint64_t bar[4];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && elect_one()) {
+    const long long t0 = clock64();
+    int issued = 0, done = 0;
+    uint32_t ph[4] = {0, 0, 0, 0};
+    while (done < count) {
+      while (issued < count && issued - done < depth) {
+        const int b = issued % depth;
+        const int img = (blockIdx.x * 7 + issued / (C / cb)) % (n_img - 3);
+        mbar_arrive_expect_tx(&bar[b], box_bytes);
+        tma_tensor_4d_g2s(dyn + b * 32768, &tmap, (issued % (C / cb)) * cb, 0, 0, img * 16, &bar[b]);
+        ++issued;
+      }
+      const int b = done % depth;
+      mbar_wait(&bar[b], ph[b]);
+      ph[b] ^= 1;
+      ++done;
+    }
+    out[blockIdx.x] = clock64() - t0;
+  }
+}
+
+static void time_tma_tensor(int grid, int cb, int rows, int swz, int depth) {
+  const int n_img = 256, C = 256, count = 64;
+  static float* x = nullptr;
+  static long long* out = nullptr;
+  if (!x) {
+    CK(cudaMalloc(&x, (size_t)n_img * 256 * C * 4));
+    CK(cudaMemset(x, 0, (size_t)n_img * 256 * C * 4));
+    CK(cudaMalloc(&out, 148 * sizeof(long long)));
+    CK(cudaFuncSetAttribute(tma_tensor_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768));
+  }
+  typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+  CUtensorMap tmap;
+  cuuint64_t dims[4] = {(cuuint64_t)C, 8, 2, (cuuint64_t)n_img * 16};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * C * 4, (cuuint64_t)C * 4, (cuuint64_t)16 * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)cb, 8, 2, (cuuint32_t)rows};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (reinterpret_cast<PFN>(fp)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    printf("tensor map encode failed (cb=%d swz=%d)\n", cb, swz);
+    return;
+  }
+  const int box_bytes = cb * 4 * 16 * rows;
+  std::vector<long long> h(grid);
+  long long best = 1ll << 60, worst = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    tma_tensor_probe_kernel<<<grid, 32, 4 * 32768>>>(tmap, out, count, depth, box_bytes, n_img, C, cb);
+    CK(cudaDeviceSynchronize());
+  }
+  CK(cudaMemcpy(h.data(), out, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (long long v : h) {
+    best = v < best ? v : best;
+    worst = v > worst ? v : worst;
+  }
+  printf("tma tensor grid=%3d box=(%2d ch x 16 px x %2d rows = %5d B) swizzle=%3d depth=%d: %.0f .. %.0f clk/load -> "
+         "%.1f B/clk/SM\n",
+         grid, cb, rows, box_bytes, swz, depth, (double)best / count, (double)worst / count,
+         (double)box_bytes * count / worst);
+}
+
 // ------------------------------------------------------------------------------------------------ MMA issue probe
 // Time `count` back-to-back tcgen05.mma kind::tf32 (K=8, operands from shared memory, no-swizzle K-major layout as in
 // the 3x3 kernels) from first issue to commit completion. acc_stride = TMEM column distance between consecutive MMAs'
@@ -638,6 +722,20 @@ int main(int argc, char** argv) {
     }
     time_mma<128, 64, 2>(96, 0, 1);
     time_mma<128, 64, 2>(96, 64, 0);
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "tmat")) {
+    for (int grid : {1, 148}) {
+      for (int depth : {1, 3}) {
+        time_tma_tensor(grid, 8, 48, 0, depth);
+        time_tma_tensor(grid, 8, 48, 32, depth);
+        time_tma_tensor(grid, 16, 24, 0, depth);
+        time_tma_tensor(grid, 16, 24, 64, depth);
+        time_tma_tensor(grid, 32, 12, 0, depth);
+        time_tma_tensor(grid, 32, 12, 128, depth);
+        time_tma_tensor(grid, 64, 6, 0, depth);
+      }
+    }
     return 0;
   }
   if (argc > 1 && !strcmp(argv[1], "tma")) {
