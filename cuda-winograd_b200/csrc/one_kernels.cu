@@ -20,17 +20,20 @@ namespace wg {
 constexpr int kOneThreads = 32 * 6;
 constexpr int kBK = 32;  // fp32 channels per stage = one 128-byte swizzle row
 
-template <int BN>
+// WS = weight-stationary: the whole [BN x Cin] weight tile stays resident in shared memory (<= 128 KB) while the CTA
+// walks the M-tiles of ONE N-tile; the stage ring then carries activations only.
+template <int BN, bool WS = false>
 struct OneSmem {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStages = WS ? 4 : (BN == 256 ? 4 : 6);
   static constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 128 B
-  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kBBytes = BN * 128;   // one 32-channel block of the weight tile
+  static constexpr uint32_t kBResident = 128 * 1024;
   static constexpr uint32_t kStageOutBytes = 32 * 128;  // one warp's 32 rows x 32 fp32 columns
   static constexpr uint32_t kOffA = 0;
   static constexpr uint32_t kOffB = kOffA + kStages * kABytes;
-  static constexpr uint32_t kOffOut = kOffB + kStages * kBBytes;  // [4 warps][2 buffers]
+  static constexpr uint32_t kOffOut = kOffB + (WS ? kBResident : kStages * kBBytes);  // [4 warps][2 buffers]
   static constexpr uint32_t kOffBar = kOffOut + 4 * 2 * kStageOutBytes;
-  static constexpr uint32_t kNumBars = 2 * kStages + 4;
+  static constexpr uint32_t kNumBars = 2 * kStages + 5;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;  // + slack for manual 1024-B alignment
   static_assert(kOffOut % 1024 == 0, "swizzled staging must be 1024-byte aligned");
@@ -40,13 +43,17 @@ struct OneSmem {
 // CL = thread-block cluster size: the CL CTAs of a cluster work on CL consecutive M-tiles of the same N-tile and share
 // the weight tile -- each loads 1/CL of it and multicasts it to all (L2->SM traffic for B divided by CL; that feed,
 // ~10 TB/s on B200, is what capped the non-clustered kernel on the Cin=1024 shape).
-template <int BN, int CL>
+// WS (with CL == 1): weight-stationary schedule for Cin*BN*4 <= 128 KB (128->512): CTA b keeps N-tile b % n_ntiles
+// for its whole life and loads that weight tile ONCE; per output tile the TMA unit then moves A + the output instead
+// of A + B + the output (measured 31.9 -> 29.6 us at N=256; see one_launch for the variant that lost).
+template <int BN, int CL, bool WS = false>
 __global__ void __launch_bounds__(kOneThreads, 1)
 conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                       const float* __restrict__ w_img, const float* __restrict__ scale,
                       const float* __restrict__ shift, float* __restrict__ y_padded, long long m_rows, int Cin,
-                      int Cout, int relu) {
-  using S = OneSmem<BN>;
+                      int Cout, int relu, int bn_packed) {
+  using S = OneSmem<BN, WS>;
+  static_assert(!WS || CL == 1, "weight-stationary schedule has no cluster variant");
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -61,6 +68,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint64_t* empty = full + S::kStages;
   uint64_t* acc_full = empty + S::kStages;  // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint64_t* b_full = acc_empty + 2;         // WS: the resident weight tile has landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
 
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
@@ -76,6 +84,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);
     }
+    mbar_init(b_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
@@ -87,28 +96,47 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int n_kb = Cin / kBK;
   const int n_ntiles = Cout / BN;
   const int n_mtiles = (int)((m_rows + 127) / 128);
-  const int n_items = ((n_mtiles + CL - 1) / CL) * n_ntiles;  // an item = CL consecutive M-tiles x one N-tile
-  const int first_item = blockIdx.x / CL;
-  const int item_stride = gridDim.x / CL;
+  // an item = CL consecutive M-tiles x one N-tile, N-tile fastest; WS: an item = one M-tile of this CTA's fixed N-tile
+  // (the host makes gridDim.x a multiple of n_ntiles)
+  const int n_items = WS ? n_mtiles : ((n_mtiles + CL - 1) / CL) * n_ntiles;
+  const int first_item = WS ? (int)blockIdx.x / n_ntiles : (int)blockIdx.x / CL;
+  const int item_stride = WS ? (int)gridDim.x / n_ntiles : (int)gridDim.x / CL;
+  const int ws_nt = (int)blockIdx.x % n_ntiles;
+  // weight image: [Cout/bn_packed][Cin/32][bn_packed rows][128 B]; this kernel's N-tile may be a BN-row slice of a packed
+  // tile (bn_packed is a multiple of BN; the swizzle only depends on row % 8)
+  const size_t b_kb_stride = (size_t)bn_packed * 128;
+  auto b_tile = [&](int nt) {
+    const int col0 = nt * BN;
+    return reinterpret_cast<const uint8_t*>(w_img) + ((size_t)(col0 / bn_packed) * n_kb * bn_packed + col0 % bn_packed) * 128;
+  };
+#define WG_ITEM_NT(item) (WS ? ws_nt : (item) % n_ntiles)
+#define WG_ITEM_MT(item) (WS ? (item) : ((item) / n_ntiles) * CL + (int)crank)
 
   if (warp == 0) {
     if (elect_one()) {  // elect.sync, not lane == 0: lets ptxas keep descriptors in uniform registers (no per-MMA waterfall loop)
       uint32_t st = 0, ph = 0;
+      if constexpr (WS) {  // the resident weight tile: requested before waiting for the previous kernel
+        const uint8_t* b_src = b_tile(ws_nt);
+        mbar_arrive_expect_tx(b_full, (uint32_t)n_kb * S::kBBytes);
+        for (int kb = 0; kb < n_kb; ++kb)
+          tma_bulk_g2s(smem + S::kOffB + kb * S::kBBytes, b_src + (size_t)kb * b_kb_stride, S::kBBytes, b_full);
+      }
       pdl_wait();  // activations come from the previous kernel in the stream
       for (int item = first_item; item < n_items; item += item_stride) {
-        const int nt = item % n_ntiles;
-        const int mt = (item / n_ntiles) * CL + crank;
-        const uint8_t* b_src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)nt * n_kb * S::kBBytes;
+        const int nt = WG_ITEM_NT(item);
+        const int mt = WG_ITEM_MT(item);
+        const uint8_t* b_src = b_tile(nt);
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full[st], S::kABytes + S::kBBytes);
+          mbar_arrive_expect_tx(&full[st], WS ? S::kABytes : S::kABytes + S::kBBytes);
           tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, kb * kBK, mt * 128, &full[st]);
-          if constexpr (CL == 1) {
-            tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * S::kBBytes, S::kBBytes, &full[st]);
+          if constexpr (WS) {
+          } else if constexpr (CL == 1) {
+            tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * b_kb_stride, S::kBBytes, &full[st]);
           } else {
             constexpr uint32_t part = S::kBBytes / CL;  // rows [crank*BN/CL, (crank+1)*BN/CL) of the swizzled image
             tma_bulk_g2s_mcast(smem + S::kOffB + st * S::kBBytes + crank * part,
-                               b_src + (size_t)kb * S::kBBytes + crank * part, part, &full[st], kClusterMask);
+                               b_src + (size_t)kb * b_kb_stride + crank * part, part, &full[st], kClusterMask);
           }
           if (++st == S::kStages) { st = 0; ph ^= 1; }
         }
@@ -121,6 +149,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t b_base = smem_u32(smem + S::kOffB);
       uint32_t st = 0, ph = 0;
       uint32_t it = 0;
+      if constexpr (WS) mbar_wait(b_full, 0);
       for (int item = first_item; item < n_items; item += item_stride, ++it) {
         const uint32_t buf = it & 1;
         const uint32_t aph = (it >> 1) & 1;
@@ -132,7 +161,8 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             const uint64_t a_desc = make_smem_desc(a_base + st * S::kABytes + k * 32, 0, 1024, kLayoutSW128);
-            const uint64_t b_desc = make_smem_desc(b_base + st * S::kBBytes + k * 32, 0, 1024, kLayoutSW128);
+            const uint64_t b_desc =
+                make_smem_desc(b_base + (WS ? kb : (int)st) * S::kBBytes + k * 32, 0, 1024, kLayoutSW128);
             umma_tf32_ss(tmem_base + buf * BN, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           if constexpr (CL == 1) umma_commit(&empty[st]); else umma_commit_mcast(&empty[st], kClusterMask);
@@ -147,8 +177,8 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t stage_u32 = smem_u32(stage_out);
     uint32_t it = 0, chunk = 0;
     for (int item = first_item; item < n_items; item += item_stride, ++it) {
-      const int nt = item % n_ntiles;
-      const int mt = (item / n_ntiles) * CL + crank;
+      const int nt = WG_ITEM_NT(item);
+      const int mt = WG_ITEM_MT(item);
       const uint32_t buf = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const float* sc = scale + nt * BN;
@@ -227,11 +257,13 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   tc_fence_before();
   if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may leave while peers still multicast to it
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+#undef WG_ITEM_NT
+#undef WG_ITEM_MT
 }
 
 // Small batches (latency): one cluster per (128-row M-tile, 64-cout sub-tile), split-K across its CS CTAs.
 // With M = N*196 rows there are only a handful of 128-row tiles; what a layer costs at N=1 is (a) how fast the weights
-// (the bulk of the bytes) stream out of L2 -- ~36 B/clk per SM, so they are spread over as many SMs as possible: 64-cout
+// (the bulk of the bytes) stream out of L2 -- one SM's TMA unit delivers 37-100 B/clk, so they are spread over as many SMs as possible: 64-cout
 // sub-tiles of the packed weight image and Cin/CS channels per CTA -- and (b) the reduction of the CS partial tiles,
 // which goes over distributed shared memory (~20 B/clk per SM), so the partial tile is kept small (128 x 64 fp32).
 // Each CTA pushes row r of its partial accumulator to the CTA owning that row (st.shared::cluster into a dedicated,
@@ -465,17 +497,17 @@ int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int C
   return encode_2d(tmap, y, Cout, m_rows, 32, 32);
 }
 
-template <int BN, int CL>
+template <int BN, int CL, bool WS = false>
 static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
                       const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int relu,
-                      int max_ctas, cudaStream_t stream) {
-  using S = OneSmem<BN>;
+                      int max_ctas, cudaStream_t stream, int bn_packed = BN) {
+  using S = OneSmem<BN, WS>;
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN, CL, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
     configured |= dev_bit_;
@@ -485,6 +517,12 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   long long n_clusters = max_ctas / CL;
   if (n_clusters > n_items) n_clusters = n_items;
   if (n_clusters < 1) n_clusters = 1;
+  if (WS) {  // every CTA owns one N-tile: grid = a multiple of the N-tile count
+    const long long n_nt = Cout / BN;
+    n_clusters = (max_ctas / n_nt) * n_nt;
+    if (n_clusters > n_mtiles * n_nt) n_clusters = n_mtiles * n_nt;
+    if (n_clusters < n_nt) n_clusters = n_nt;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_clusters * CL));
   cfg.blockDim = dim3(kOneThreads);
@@ -499,8 +537,8 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL>, tmap, tmap_y, w_img, scale, shift, y_padded,
-                                     m_rows, Cin, Cout, relu);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL, WS>, tmap, tmap_y, w_img, scale, shift, y_padded,
+                                     m_rows, Cin, Cout, relu, bn_packed);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
@@ -574,7 +612,7 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
   float* y_padded = out_padded ? y : nullptr;
   {
     // latency mode: every (M-tile, 64-cout sub-tile) fits on the chip at once -> the small kernel, split-K factor CS
-    // chosen by a two-term model in clocks (weight/activation ingest of Cin/CS channels at ~36 B/clk, DSMEM reduction
+    // chosen by a two-term model in clocks (weight/activation ingest of Cin/CS channels at ~36 B/clk per SM, DSMEM reduction
     // of (CS-1)/CS of a 32 KB partial at ~18 B/clk + fixed cost). WG_ONE_SPLITK=1 disables, WG_ONE_CS=n forces CS.
     static int sk_env = -1, cs_env = 0;
     if (sk_env < 0) {
@@ -620,6 +658,32 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
     if (cl != 1 && cl != 2 && cl != 4) cl = 1;
   }
   const int use = (m_rows <= 128) ? 1 : cl;  // a single M-tile has nobody to share the weight tile with
+  {
+    // weight-stationary schedule when the packed [BN x Cin] tile fits 128 KB and every CTA gets several M-tiles of one
+    // N-tile. Measured at N=256: 128->512 31.9 -> 29.6 us. Narrower stationary tiles (a 128-row slice of a 256-row
+    // packed tile, WG_ONE_WS_BN=128) make Cin=256 eligible but lose (256->1024: 64 -> 79 us: A is then re-read per
+    // N-tile through the tensor-map path, ~37 B/clk per SM), so they are not used.
+    static int ws_env = -1;  // WG_ONE_WS=0 disables
+    if (ws_env < 0) {
+      const char* e = getenv("WG_ONE_WS");
+      ws_env = e ? atoi(e) : 1;
+    }
+    static int ws_bn_env = -1;  // WG_ONE_WS_BN=128: also allow 128-row stationary slices (experiments)
+    if (ws_bn_env < 0) {
+      const char* e = getenv("WG_ONE_WS_BN");
+      ws_bn_env = e ? atoi(e) : 0;
+    }
+    int bn_ws = (long long)Cin * BN * 4 <= 128 * 1024 ? BN : 0;
+    if (ws_bn_env == 128 && (long long)Cin * 128 * 4 <= 128 * 1024) bn_ws = 128;
+    const long long n_mt = (m_rows + 127) / 128, n_nt = bn_ws ? Cout / bn_ws : 0;
+    if (ws_env && use == 1 && bn_ws && max_ctas >= n_nt && n_mt >= 4 * (max_ctas / n_nt)) {
+      if (bn_ws == 128)
+        return launch_one<128, 1, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas,
+                                        stream, BN);
+      return launch_one<256, 1, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas,
+                                      stream, BN);
+    }
+  }
 #define WG_ONE(BN_, CL_) \
   return launch_one<BN_, CL_>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas, stream)
   if (BN == 128) {

@@ -6,7 +6,8 @@
 //
 //   * work item = 64 consecutive tiles x 32 output channels, one item per thread-block CLUSTER of CS CTAs; each CTA
 //     runs C/CS of the channel loop (at N=1, 256->256: 8 items x 16 CTAs = 128 SMs pull the 4 MB filter image out of
-//     L2 in parallel -- per-SM ingest, ~36 B/clk, is the floor of this mode);
+//     L2 in parallel: one SM's TMA unit delivers ~31-37 B/clk of tiled boxes and 65-110 B/clk of 1-D bulk copies,
+//     profiles/tma_probe_r01.txt, tma_tensor_probe_r01.txt);
 //   * tcgen05.mma with M=64 (half the A-operand shared-memory reads of M=128; TMEM row r lives in lane 32*(r/16)+r%16,
 //     probed with tools/selftest), one accumulator per Winograd point (16 x 32 columns), no folding: 16 MMAs per stage;
 //   * the CS partial outputs are reduced through distributed shared memory: after the inverse transform every thread
@@ -473,7 +474,7 @@ static int launch_small(const CUtensorMap& tmap, const float* u_img, const float
 }
 
 // Split factor for (n_img, C, K) on `max_ctas` SMs, 0 = the small kernel does not apply (the batch is large enough for
-// the persistent kernel). Model in clocks: per 8-channel stage ~700 (ingest of 16 KB U + the raw rows at ~36 B/clk),
+// the persistent kernel). Model in clocks: per 8-channel stage ~700 (ingest of 16 KB U + the raw rows through one SM's TMA unit),
 // reduction ~ (CS-1)/CS of a 32 KB partial over DSMEM at ~18 B/clk + a fixed cost. WG_WINO_CS=1 disables the latency
 // mode, any other value forces that CS when it is legal.
 int wino_small_cs(int n_img, int C, int K, int max_ctas) {

@@ -16,8 +16,10 @@
 //     remainder: 256 = 4x48 + 2x32, 128 = 2x48 + 32), and V is single-buffered per half: the stores of stage s+1,
 //     half jh wait for the 12 MMAs of stage s, half jh (tcgen05.commit -> v_empty[jh]) while its loads and FADDs overlap
 //     them;
-//   * raw tiles land through a SWIZZLE_32B tensor map so that 32 consecutive tile rows (one warp) read their 16-byte
-//     channel halves without systematic bank conflicts;
+//   * raw tiles land through a SWIZZLE_32B tensor map, which spreads the 16-byte channel halves of the 7 tiles of an
+//     image row over 7 different bank groups. A quarter warp is 8 consecutive tiles, though, so it always wraps into
+//     the next image row and pays a second wavefront (ncu: 58 % of the load wavefronts are conflicts). Padding the
+//     rows to 8 slots removes them but costs 1/8 of the MMA rows and a fifth wave at N=256 -- measured slower;
 //   * the epilogue stages relu(scale*Y+shift) in its own shared-memory area ([tile][pixel][couts], rows padded by 16 B)
 //     and writes full runs per output pixel.
 #include "ptx.cuh"
