@@ -307,3 +307,51 @@ def gather_output(y_local, n_total: int, group=None):
     if all(h - l == nmax for l, h in sizes):
         return out
     return torch.cat([out[r * nmax:r * nmax + (h - l)] for r, (l, h) in enumerate(sizes)], dim=0)
+
+
+WG_OUT_PADDED, WG_OUT_MULTICAST = 1, 2
+
+
+class FusedGatherConv3x3:
+    """conv3x3 + BN + ReLU fused with the all-gather of its output over NVSwitch (SURVEY.md section 8e names one gather
+    of the fp32 output as the path's only exchange). Every rank owns `n_local` images; the gathered
+    [world * n_local, 14, 14, K] tensor lives in torch symmetric memory bound to an NVLS multicast object, and each rank's
+    kernel writes its shard through the MULTICAST address with multimem.st (wg_run flag WG_OUT_MULTICAST): the switch
+    replicates every 16-byte store into all GPUs' copies, so the gather costs no extra kernel, no extra HBM read and
+    overlaps the convolution. `__call__` returns the gathered tensor after a cross-rank barrier on the stream.
+    Needs multicast support (NVSwitch + fabric manager); otherwise construction raises and gather_output() (NCCL) is
+    the fallback."""
+
+    def __init__(self, layer, n_local: int, group=None, out_padded=False):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        assert layer.kind == 0, "3x3 layers only"
+        self.layer, self.n_local, self.out_padded = layer, n_local, bool(out_padded)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        shape = (self.world * n_local,) + layer.out_shape(out_padded)
+        dev = torch.device("cuda", layer.device)
+        self.full = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.full, self.group)
+        if not self.hdl.multicast_ptr:
+            raise WinogradB200Error("no NVLS multicast support on this system; use gather_output() (NCCL) instead")
+        self.shard_bytes = n_local * int(np_prod(layer.out_shape(out_padded))) * 4
+        self.y_mc = self.hdl.multicast_ptr + self.rank * self.shard_bytes
+
+    def __call__(self, x):
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == self.n_local
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        flags = WG_OUT_MULTICAST | (WG_OUT_PADDED if self.out_padded else 0)
+        _check(lib().wg_run(self.layer._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(self.y_mc), self.n_local,
+                            flags, ctypes.c_void_p(stream)), "wg_run (multicast)")
+        self.hdl.barrier()          # all ranks' kernels are complete: every shard has landed everywhere
+        return self.full
+
+
+def np_prod(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n

@@ -108,6 +108,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Output store that can target an NVLS multicast ("multimem") address: with mc = true the 16 bytes are replicated by
+// the NVSwitch into the same offset of every GPU's buffer bound to the multicast object (fused conv + all-gather of the
+// output); plain ld/st on such addresses is undefined, hence the dedicated instruction.
+__device__ __forceinline__ void st_out_v4(float* p, float4 v, bool mc) {
+  if (mc)
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  else
+    *reinterpret_cast<float4*>(p) = v;
+}
+
 // ---------------------------------------------------------------- proxy fences
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / TMA reading shared memory)
 __device__ __forceinline__ void fence_proxy_async_smem() {

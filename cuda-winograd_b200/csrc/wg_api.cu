@@ -203,6 +203,12 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   if (!L || !x || !y || N <= 0) return WG_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return WG_ERR_ARG;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  // out_padded is a flag word: WG_OUT_PADDED (1) = zero-bordered frame, WG_OUT_MULTICAST (2) = y is an NVLS multicast
+  // address (stores go out as multimem.st and land in every GPU's buffer: fused conv + all-gather of the output).
+  if (out_padded & ~3) return WG_ERR_ARG;
+  const int out_flags = out_padded & 3;
+  if ((out_flags & 2) && !(L->kind == 0 && L->dtype == WG_TF32 && L->tile_n == 48)) return WG_ERR_ARG;
+  out_padded &= 1;
   int cur = -1;
   WG_CUDA(cudaGetDevice(&cur));
   if (cur != L->device) WG_CUDA(cudaSetDevice(L->device));
@@ -218,7 +224,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
         L->tmap_small_n = N;
       }
       int rc = wino_small_launch(L->tmap_small, L->d_filter_small, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
-                                 L->relu, out_padded ? 1 : 0, cs, stream);
+                                 L->relu, out_flags, cs, stream);
       g_launches++;
       if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
       return rc;
@@ -241,7 +247,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   int rc;
   if (L->kind == 0 && L->tile_n == 48)
     rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->relu,
-                        out_padded ? 1 : 0, max_ctas, stream);
+                        out_flags, max_ctas, stream);
   else if (L->kind == 0)
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,
                      L->dtype, L->relu, out_padded ? 1 : 0, max_ctas, stream);

@@ -64,6 +64,8 @@ wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
                      int n_img, int C, int K, int relu, int out_padded, int debug) {
   using namespace small;
   constexpr int RO = kMB / CS;  // tile rows each CTA finishes
+  const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
+  out_padded &= 1;
   pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -359,7 +361,7 @@ wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
       const int n = T / 49, t = T % 49, ty = t / 7, tx = t % 7;
       const int pix = (n * W + 2 * ty + o + (px >> 1)) * W + 2 * tx + o + (px & 1);
       float* g = y + (size_t)pix * K + cout0;
-      *reinterpret_cast<float4*>(g) = acc;
+      st_out_v4(g, acc, mc);
       if (out_padded) {
         // zero border of the reference's 16x16 frame (Kernel128_winograd.cu:163,243), written by whichever corner
         // pixel of an edge tile is nearest
@@ -367,9 +369,9 @@ wino3x3_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
         const int a = px >> 1, b = px & 1;
         const ptrdiff_t dyb = (ty == 0 && a == 0) ? -(ptrdiff_t)W * K : ((ty == 6 && a == 1) ? (ptrdiff_t)W * K : 0);
         const ptrdiff_t dxb = (tx == 0 && b == 0) ? -(ptrdiff_t)K : ((tx == 6 && b == 1) ? (ptrdiff_t)K : 0);
-        if (dyb != 0) *reinterpret_cast<float4*>(g + dyb) = z4;
-        if (dxb != 0) *reinterpret_cast<float4*>(g + dxb) = z4;
-        if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(g + dyb + dxb) = z4;
+        if (dyb != 0) st_out_v4(g + dyb, z4, mc);
+        if (dxb != 0) st_out_v4(g + dxb, z4, mc);
+        if (dyb != 0 && dxb != 0) st_out_v4(g + dyb + dxb, z4, mc);
       }
     }
     if (threadIdx.x == 0) WG_TS(11);

@@ -62,6 +62,8 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
                   int C, int K, int n48, int relu, int out_padded, int mv) {
   using namespace tm;
+  const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
+  out_padded &= 1;
   pdl_launch_dependents();  // the next launch in the stream may start its prologue (it waits before touching x / y)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -367,7 +369,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           const int ch = r - px * chunks;
           const float4 v = ld_shared_v4(stg_base + (uint32_t)tile * tstride + (uint32_t)(px * 4 * kn + ch * 16));
           const int pix = pixtab[tile] + (px >> 1) * W + (px & 1);
-          *reinterpret_cast<float4*>(y + (size_t)pix * K + c0s + ch * 4) = v;
+          st_out_v4(y + (size_t)pix * K + c0s + ch * 4, v, mc);
         }
         if (out_padded && evalid && (ty == 0 || ty == 6 || tx == 0 || tx == 6)) {
           // zero border of the reference's 16x16 frame (Kernel128_winograd.cu:163,243): edge tiles own their share
@@ -379,14 +381,14 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 #pragma unroll 1
           for (int e = 0; e < ncc; e += 4) {
             if (dyb != 0) {
-              *reinterpret_cast<float4*>(p + dyb + e) = z4;
-              *reinterpret_cast<float4*>(p + dyb + K + e) = z4;
+              st_out_v4(p + dyb + e, z4, mc);
+              st_out_v4(p + dyb + K + e, z4, mc);
             }
             if (dxb != 0) {
-              *reinterpret_cast<float4*>(p + dxb + e) = z4;
-              *reinterpret_cast<float4*>(p + dxb + rstride + e) = z4;
+              st_out_v4(p + dxb + e, z4, mc);
+              st_out_v4(p + dxb + rstride + e, z4, mc);
             }
-            if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(p + dyb + dxb + e) = z4;
+            if (dyb != 0 && dxb != 0) st_out_v4(p + dyb + dxb + e, z4, mc);
           }
         }
       }

@@ -63,7 +63,14 @@ int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_co
  * Replaces the timed region of kernel_128()/kernel_256() (three launches, Kernel128_winograd.cu:263-265) and of
  * kernel_*_1_in/out() (one launch, Kernel128_one.cu:98,316). For a 1x1 layer out_padded != 0 writes the same
  * zero-bordered [N][16][16][Cout] frame instead of [N][196][Cout], i.e. exactly the input a following 3x3 layer
- * reads, so bottleneck chains 1x1 -> 3x3 -> 1x1 need no padding pass in between. */
+ * reads, so bottleneck chains 1x1 -> 3x3 -> 1x1 need no padding pass in between.
+ * out_padded is a flag word: WG_OUT_PADDED (1) as above; WG_OUT_MULTICAST (2, 3x3 TF32 layers): y_dev is an NVLS
+ * multicast address (cuMulticast* / torch symmetric memory) and every output store is issued as multimem.st, i.e. the
+ * NVSwitch replicates this GPU's shard into the buffers of all GPUs bound to the multicast object -- conv + BN + ReLU
+ * fused with the all-gather of the output, no NCCL call (the caller still has to barrier across ranks before reading
+ * the gathered tensor). Other values / layer kinds with the multicast flag: WG_ERR_ARG. */
+#define WG_OUT_PADDED 1
+#define WG_OUT_MULTICAST 2
 int wg_run(wg_layer_t* layer, const float* x_dev, float* y_dev, int N, int out_padded, void* cuda_stream);
 
 /* Same, end to end with HOST buffers: H2D copy of x, wg_run, D2H copy of y, stream-synchronised on return.

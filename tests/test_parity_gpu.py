@@ -378,3 +378,30 @@ def test_legacy_entry_points_and_test_binary(lib_loaded, seeded_data, tmp_path):
         assert "Average Total Time: [Mine:" in r.stdout
     finally:
         os.chdir(cwd)
+
+
+# ------------------------------------------------------------------------------------------ fused output all-gather
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_per_gpu", [4, 48])
+def test_fused_output_allgather_over_nvls_multicast(torch_cuda, n_per_gpu):
+    """the path's one exchange is the gather of the fp32 output. With WG_OUT_MULTICAST the kernel's
+    own stores do it (multimem.st to an NVLS multicast address); tools/fused_gather_check.py runs it on 2 ranks and
+    demands a bit-identical result to kernel + NCCL all_gather (dense and padded frame). n=4 takes the small-batch
+    kernel, n=48 the throughput kernel. Needs >= 2 GPUs with multicast support; skipped otherwise."""
+    import json
+    import subprocess
+    import sys
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, WG_CHECK_N=str(n_per_gpu), MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29600 + n_per_gpu),
+                        os.path.join(root, "tools", "fused_gather_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1])
+    if "unavailable" in res:
+        pytest.skip(res["unavailable"])
+    assert r.returncode == 0 and res["ok"] and res["bit_identical_padded0"] and res["bit_identical_padded1"], res

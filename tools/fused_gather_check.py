@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Multi-GPU check + timing of the fused conv3x3+BN+ReLU -> all-gather (NVLS multicast stores, WG_OUT_MULTICAST) against
+the two-step path (the same kernel, then one NCCL all_gather_into_tensor). Run under torchrun on >= 2 GPUs of one node:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/fused_gather_check.py
+
+Rank 0 prints one JSON line; exit code 0 only if the fused result is bit-identical to the NCCL-gathered one on every
+rank. Writes nothing else. (tests/test_parity_gpu.py launches this when the box has >= 2 GPUs.)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import wg_loader  # noqa: E402
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    wg = wg_loader.load()
+    n, c, k = int(os.environ.get("WG_CHECK_N", "256")), 256, 256
+    rs = np.random.RandomState(0)                         # same weights on every rank
+    w = (rs.rand(k, c, 3, 3) - 0.5).astype(np.float32)
+    sc, sh = (rs.rand(k) + 0.5).astype(np.float32), (rs.rand(k) - 0.5).astype(np.float32)
+    layer = wg.Conv3x3BnRelu(w, sc, sh, relu=True, device=local)
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)                             # different images per rank
+    x = torch.rand((n, 16, 16, c), device=dev, generator=g) - 0.5
+
+    ok = True
+    result = dict(world=world, n_per_gpu=n)
+    for padded in (False, True):
+        y_local = layer(x, out_padded=padded)
+        ref = wg.gather_output(y_local, world * n)
+        try:
+            fused = wg.FusedGatherConv3x3(layer, n, out_padded=padded)
+        except wg.WinogradB200Error as e:
+            result["unavailable"] = str(e)
+            break
+        out = fused(x)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(out, ref))
+        ok = ok and same
+        result[f"bit_identical_padded{int(padded)}"] = same
+        if padded:
+            continue
+        # timing: K steps of (kernel -> NCCL all-gather) vs K fused steps (multicast stores + barrier)
+        steps = 50
+        buf = torch.empty((world * n,) + tuple(y_local.shape[1:]), device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for mode in ("nccl", "fused"):
+            for i in range(steps + 5):
+                if i == 5:
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    torch.cuda.synchronize()
+                    e0.record()
+                if mode == "nccl":
+                    layer(x, out=y_local)
+                    dist.all_gather_into_tensor(buf, y_local)
+                else:
+                    fused(x)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            result[f"{mode}_ms_per_step"] = float(t.item())
+            result[f"{mode}_images_per_s"] = world * n / (float(t.item()) * 1e-3)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    result["ok"] = bool(flag.item())
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if result["ok"] else 1)
+
+
+if __name__ == "__main__":
+    main()
