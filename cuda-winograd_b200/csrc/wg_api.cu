@@ -70,6 +70,7 @@ struct wg_layer {
   int kind;  // 0 = 3x3 Winograd, 1 = 1x1 GEMM
   int cin, cout, relu, dtype, device;
   int tile_n;  // 3x3: cout slice KN; 1x1: BN
+  int tm_db;   // 3x3 TM kernel: 1 = double-buffered V, 32-wide slices
   int num_sms;
   float* d_filter;  // packed filter image (U or swizzled W^T)
   float* d_filter_small;  // 3x3 TF32 only: U in the plain KN=32 image the small-batch kernel reads (may alias d_filter)
@@ -159,7 +160,10 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   WG_TRY(cudaMemcpyAsync(d_w, w, w_elems * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_scale, scale, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
-  if (kind == 0 && L->tile_n == 48) rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->stream);
+  if (kind == 0 && L->tile_n == 48) {
+    L->tm_db = wino_tm_choose_db(cin, cout);
+    rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->tm_db, L->stream);
+  }
   else if (kind == 0) rc = filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)dtype, L->stream);
   else rc = weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
   g_launches++;
@@ -246,7 +250,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   }
   int rc;
   if (L->kind == 0 && L->tile_n == 48)
-    rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->relu,
+    rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, L->relu,
                         out_flags, max_ctas, stream);
   else if (L->kind == 0)
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,

@@ -29,9 +29,10 @@ int filter_transform_launch(const float* w_kcrs, void* u_img, int C, int K, int 
 
 // throughput kernel with V in tensor memory (wino_tm_kernel.cu): TF32, cout slices of 48 / 32, its own filter image
 int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
-int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, cudaStream_t stream);
+int wino_tm_choose_db(int C, int K);  // 1 = double-buffered V / 32-wide slices, 0 = one V stage / 48-wide slices
+int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, int db, cudaStream_t stream);
 int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                   int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream);
+                   int n_img, int C, int K, int db, int relu, int out_padded, int max_ctas, cudaStream_t stream);
 
 // small-batch latency variant (wino_small_kernel.cu): TF32 only, filter in the plain KN=32 image
 int wino_small_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);

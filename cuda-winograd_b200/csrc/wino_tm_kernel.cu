@@ -41,14 +41,20 @@ constexpr int kRawStages = 3, kUBufs = 4;
 constexpr int kKNmax = 48;
 constexpr uint32_t kUChunkMax = 8 * 2 * kKNmax * 16;   // 8 points x [2 k-chunks][KN couts][4 ch] = 12288
 constexpr uint32_t kStgBytes = 128 * (16 * kKNmax + 16);  // [128 tiles][4 px][KN couts] fp32, tile rows padded by 16 B
-constexpr uint32_t kAccStride = 48;                    // TMEM columns between the 8 accumulators
-constexpr uint32_t kVCol0 = 8 * kAccStride;            // 384: V half jh at kVCol0 + 64*jh, point p8 at +8*p8
+// TMEM map. DB = false: 8 accumulators x 48 columns, then ONE V stage (two 64-column halves).
+//           DB = true : 8 accumulators x 32 columns (all cout slices 32 wide), then TWO V stages (double-buffered).
+// V stage vb, half jh at kVCol0 + 128*vb + 64*jh, point p8 at +8*p8.
+template <bool DB> struct Tmem {
+  static constexpr uint32_t kAccStride = DB ? 32 : 48;
+  static constexpr uint32_t kVCol0 = 8 * kAccStride;
+  static constexpr int kVBufs = DB ? 2 : 1;
+};
 constexpr uint32_t kOffRaw = 0;
 constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawBytes;
 constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
 constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
 constexpr uint32_t kOffBar = kOffPix + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kUBufs + 4 + 2;
+constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kUBufs + 8 + 2;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kTotal = kOffTmemPtr + 16;
 static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alignment");
@@ -57,11 +63,16 @@ static_assert(kTotal <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ float tm_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
+// DB: V double-buffered in TMEM at the price of 32-wide cout slices (see Tmem). With one V stage the transform of stage
+// s+1 cannot store before the MMAs of stage s have completed, and those cannot start before the slowest of the 8 warps
+// has stored stage s: every stage ends in an implicit barrier. With two stages the warps run up to one stage ahead.
+template <bool DB>
 __global__ void __launch_bounds__(tm::kThreads, 1)
 wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
                   int C, int K, int n48, int relu, int out_padded, int mv) {
   using namespace tm;
+  constexpr uint32_t kAccStride = Tmem<DB>::kAccStride, kVCol0 = Tmem<DB>::kVCol0;
   const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
   out_padded &= 1;
   pdl_launch_dependents();  // the next launch in the stream may start its prologue (it waits before touching x / y)
@@ -74,9 +85,9 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   uint64_t* raw_empty = raw_full + kRawStages;
   uint64_t* u_full = raw_empty + kRawStages;
   uint64_t* u_empty = u_full + kUBufs;
-  uint64_t* v_full = u_empty + kUBufs;  // [2] per V half
-  uint64_t* v_empty = v_full + 2;       // [2]
-  uint64_t* acc_full = v_empty + 2;
+  uint64_t* v_full = u_empty + kUBufs;  // [V stage][half]
+  uint64_t* v_empty = v_full + 4;       // [V stage][half]
+  uint64_t* acc_full = v_empty + 4;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
@@ -91,7 +102,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       mbar_init(&u_full[i], 1);
       mbar_init(&u_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&v_full[i], kWorkerWarps);
       mbar_init(&v_empty[i], 1);
     }
@@ -163,7 +174,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     // ------------------------------------------------------------------ MMA issuer (one elected thread)
     if (elect_one()) {
       const uint32_t u_base = smem_u32(smem + kOffU);
-      uint32_t vph = 0, us = 0, uph = 0, aph = 0;
+      uint32_t g = 0, us = 0, uph = 0, aph = 0;  // g = stages issued; V stage g % kVBufs, its phase (g / kVBufs) & 1
       for (int item = item0; item < n_items; item += item_step) {
         const int s = item % n_slices;
         const uint32_t kn = s < n48 ? 48u : 32u;
@@ -177,10 +188,11 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
             mbar_wait(&u_full[us], uph);  // there long before V: checked first, off the V -> MMA critical path
-            mbar_wait(&v_full[jh], vph);
+            const uint32_t vb = DB ? (g & 1) : 0u, vph = DB ? ((g >> 1) & 1) : (g & 1);
+            mbar_wait(&v_full[vb * 2 + jh], vph);
             tc_fence_after();
             const uint32_t ua = u_base + us * kUChunkMax;
-            const uint32_t va = tmem_base + kVCol0 + jh * 64;
+            const uint32_t va = tmem_base + kVCol0 + vb * 128 + jh * 64;
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
               const int j = jh * 2 + jj;
@@ -201,10 +213,10 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
               umma_tf32_ts(z1, a_tm[3], b_desc[3], idesc_neg, 1u);
             }
             umma_commit(&u_empty[us]);
-            umma_commit(&v_empty[jh]);  // this V half may be overwritten with the next stage
+            umma_commit(&v_empty[vb * 2 + jh]);  // this V half may be overwritten
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
-          vph ^= 1;
+          ++g;
         }
         umma_commit(acc_full);
         aph ^= 1;
@@ -220,7 +232,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     const uint32_t raw_base = smem_u32(smem + kOffRaw);
     const uint32_t stg_base = smem_u32(smem + kOffStg);
 
-    uint32_t rs = 0, rph = 0, vph = 0, aph = 0;
+    uint32_t rs = 0, rph = 0, g = 0, aph = 0;  // g = stages transformed (same counting as the MMA thread)
     for (int item = item0; item < n_items; item += item_step) {
       const int s = item % n_slices;
       const int mb = item / n_slices;
@@ -244,12 +256,13 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           // nothing to transform: release the raw stage and report "V ready" in step with the other warps
           if (lane == 0) mbar_arrive(&raw_empty[rs]);
           if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          const uint32_t vb = DB ? (g & 1) : 0u, vph = DB ? ((g >> 1) & 1) : (g & 1);
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
-            mbar_wait(&v_empty[jh], vph ^ 1);
-            if (lane == 0) mbar_arrive(&v_full[jh]);
+            mbar_wait(&v_empty[vb * 2 + jh], vph ^ 1);
+            if (lane == 0) mbar_arrive(&v_full[vb * 2 + jh]);
           }
-          vph ^= 1;
+          ++g;
           continue;
         }
         float4 d[4][4];
@@ -281,10 +294,11 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         if (++rs == kRawStages) { rs = 0; rph ^= 1; }
 
         // row pass V = t B by halves (half jh = points with j in {2jh, 2jh+1}), round to TF32, store into TMEM
-        const uint32_t vcol = tmem_base + lane_base + kVCol0 + (uint32_t)half * 4;
+        const uint32_t vb = DB ? (g & 1) : 0u, vph = DB ? ((g >> 1) & 1) : (g & 1);
+        const uint32_t vcol = tmem_base + lane_base + kVCol0 + vb * 128 + (uint32_t)half * 4;
 #pragma unroll
         for (int jh = 0; jh < 2; ++jh) {
-          mbar_wait(&v_empty[jh], vph ^ 1);  // the MMAs that read this half (previous stage) have completed
+          mbar_wait(&v_empty[vb * 2 + jh], vph ^ 1);  // the MMAs that last read this V half have completed
           tc_fence_after();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -303,9 +317,9 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&v_full[jh]);
+          if (lane == 0) mbar_arrive(&v_full[vb * 2 + jh]);
         }
-        vph ^= 1;
+        ++g;
       }
 
       // ---- epilogue: rest of Y = A^T M A, BN, ReLU, staged, written out as full runs per pixel
@@ -476,25 +490,40 @@ int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
 
-int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, cudaStream_t stream) {
+// Which TM variant a layer uses (decided once, at create: the filter image differs). WG_WINO_TM=48|32 pins it.
+int wino_tm_choose_db(int C, int K) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("WG_WINO_TM");
+    env = e ? atoi(e) : 0;
+  }
+  if (env == 48) return 0;
+  if (env == 32) return 1;
+  (void)C;
+  (void)K;
+  return 0;
+}
+
+int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, int db, cudaStream_t stream) {
   const int n = C * K;
-  filter_transform_tm_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, wino_tm_n48(K));
+  filter_transform_tm_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, db ? 0 : wino_tm_n48(K));
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                   int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+template <bool DB>
+static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                     int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm::kTotal) !=
+    if (cudaFuncSetAttribute(wino3x3_tm_kernel<DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm::kTotal) !=
         cudaSuccess)
       return WG_ERR_CUDA;
     configured |= dev_bit_;
   }
-  const int n48 = wino_tm_n48(K);
+  const int n48 = DB ? 0 : wino_tm_n48(K);
   const int n_slices = n48 + (K - 48 * n48) / 32;
   const int total_tiles = n_img * 49;
   // Tiles per M-block: the MMA is always M=128 but only `mv` rows carry tiles; transform warps own 32 rows each, so
@@ -532,9 +561,15 @@ int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* sca
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_tm_kernel, tmap, u_img, scale, shift, y, n_img, C, K, n48, relu,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_tm_kernel<DB>, tmap, u_img, scale, shift, y, n_img, C, K, n48, relu,
                                      out_padded, mv);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                   int n_img, int C, int K, int db, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+  return db ? launch_tm<true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream)
+            : launch_tm<false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
 }
 
 }  // namespace wg
