@@ -283,6 +283,11 @@ __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, float a, float b, flo
                "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
                : "memory");
 }
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, float a, float b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b))
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32: A is read from TMEM (lane = row, 8 consecutive 32-bit columns = the
@@ -355,6 +360,11 @@ __device__ __forceinline__ void st_shared_f16x4(uint32_t addr, float a, float b,
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b), "f"(a));
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(d), "f"(c));
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ float2 ld_shared_v2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;

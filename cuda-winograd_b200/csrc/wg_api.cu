@@ -236,7 +236,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   }
   if (L->tmap_x != x || L->tmap_n != N) {
     int rc = L->kind == 1 ? one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin)
-             : L->tile_n == 48 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin)
+             : L->tile_n == 48 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin, wino_tm_cls(L->cout, L->tm_db))
                                : wino_make_tmap(&L->tmap, x, N, L->cin);
     if (rc != WG_OK) return rc;
     L->tmap_x = x;

@@ -28,7 +28,8 @@ int wino_launch(const CUtensorMap& tmap, const void* u_img, const float* scale, 
 int filter_transform_launch(const float* w_kcrs, void* u_img, int C, int K, int KN, int bf16, cudaStream_t stream);
 
 // throughput kernel with V in tensor memory (wino_tm_kernel.cu): TF32, cout slices of 48 / 32, its own filter image
-int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
+int wino_tm_cls(int K, int db);  // cluster size (CTAs sharing the raw tiles of one M-block)
+int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C, int cls);
 int wino_tm_choose_db(int C, int K);  // 1 = double-buffered V / 32-wide slices, 0 = one V stage / 48-wide slices
 int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, int db, cudaStream_t stream);
 int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,

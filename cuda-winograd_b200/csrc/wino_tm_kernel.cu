@@ -31,10 +31,8 @@
 namespace wg {
 
 namespace tm {
-constexpr int kWorkerWarps = 8;
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kThreads = 32 * 10;
+// WW worker warps (8 or 16) + the TMA producer warp + the MMA warp. A worker thread owns one MMA row (= TMEM lane; warp
+// w may only touch lanes 32*(w%4)..+31) and 32/WW of the 8 channels of a stage: 4 channels with WW=8, 2 with WW=16.
 constexpr int kRawRows = 48;  // input rows (n*16+y) one 128-tile M-block can touch
 constexpr uint32_t kRawBytes = kRawRows * 2 * 8 * 32;  // [ny][x parity][x/2][8 ch] fp32 = 24576
 constexpr int kRawStages = 3, kUBufs = 4;
@@ -54,7 +52,7 @@ constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawBytes;
 constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
 constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
 constexpr uint32_t kOffBar = kOffPix + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kUBufs + 8 + 2;
+constexpr uint32_t kNumBars = 3 * kRawStages + 2 * kUBufs + 8 + 2;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kTotal = kOffTmemPtr + 16;
 static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alignment");
@@ -66,13 +64,22 @@ __device__ __forceinline__ float tm_tf32(float x) { return __uint_as_float(__flo
 // DB: V double-buffered in TMEM at the price of 32-wide cout slices (see Tmem). With one V stage the transform of stage
 // s+1 cannot store before the MMAs of stage s have completed, and those cannot start before the slowest of the 8 warps
 // has stored stage s: every stage ends in an implicit barrier. With two stages the warps run up to one stage ahead.
-template <bool DB>
-__global__ void __launch_bounds__(tm::kThreads, 1)
+// CLS > 1: thread-block clusters of CLS CTAs work on the SAME M-block, each on its own cout slice, and share the raw
+// tiles: CTA r loads rows [r*48/CLS, (r+1)*48/CLS) of every stage's box and multicasts them to all CLS CTAs. The kernel
+// is bound by what one SM's TMA unit can deliver (tiled boxes with 32-byte runs: ~31 B/clk, profiles/
+// tma_tensor_probe_r01.txt; with everything but TMA and barriers switched off it still needs 62 % of its time), and
+// the raw tile is the same for all cout slices of an M-block. EXPERIMENT, default off: measured 1.4x (CLS=2) to 3x
+// (CLS=3) slower than CLS=1, see wino_tm_cls().
+template <bool DB, int WW, int CLS>
+__global__ void __launch_bounds__(32 * (WW + 2), 1)
 wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
-                  int C, int K, int n48, int relu, int out_padded, int mv) {
+                  int C, int K, int n48, int relu, int out_padded, int mv, int debug) {
   using namespace tm;
   constexpr uint32_t kAccStride = Tmem<DB>::kAccStride, kVCol0 = Tmem<DB>::kVCol0;
+  constexpr int kWorkerWarps = WW, kProducerWarp = WW, kMmaWarp = WW + 1;
+  constexpr int NC = 32 / WW;       // channels per worker thread (4 or 2)
+  constexpr int EC = WW == 8 ? 8 : 4;  // couts per epilogue step
   const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
   out_padded &= 1;
   pdl_launch_dependents();  // the next launch in the stream may start its prologue (it waits before touching x / y)
@@ -89,6 +96,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   uint64_t* v_empty = v_full + 4;       // [V stage][half]
   uint64_t* acc_full = v_empty + 4;
   uint64_t* acc_empty = acc_full + 1;
+  uint64_t* peer_empty = acc_empty + 1;  // [kRawStages] CLS > 1: every CTA of the cluster has released this raw stage
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
 
@@ -108,20 +116,24 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, kWorkerWarps);
+    for (int i = 0; i < kRawStages; ++i) mbar_init(&peer_empty[i], CLS);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CLS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  const uint32_t crank = CLS > 1 ? cluster_ctarank() : 0u;
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_kb = C / 8;
   const int n_slices = n48 + (K - 48 * n48) / 32;
   const int total_tiles = n_img * 49;
   const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host to balance waves
-  const int n_items = n_mblocks * n_slices;
-  const int item0 = blockIdx.x, item_step = gridDim.x;
+  // an item = (M-block, group of CLS consecutive cout slices); the CTAs of a cluster take one slice of the group each
+  const int n_groups = n_slices / CLS;
+  const int n_items = n_mblocks * n_groups;
+  const int item0 = blockIdx.x / CLS, item_step = gridDim.x / CLS;
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -131,7 +143,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       if (item0 < n_items) {
         // the filter does not depend on the previous kernel in the stream: request the first stage's U chunks before
         // waiting for that kernel (programmatic dependent launch), the activations after
-        const int s = item0 % n_slices;
+        const int s = (item0 % n_groups) * CLS + (int)crank;
         const int kn = s < n48 ? 48 : 32;
         const int c0 = s < n48 ? 48 * s : 48 * n48 + 32 * (s - n48);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
@@ -144,8 +156,8 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       }
       pdl_wait();
       for (int item = item0; item < n_items; item += item_step) {
-        const int s = item % n_slices;
-        const int mb = item / n_slices;
+        const int s = (item % n_groups) * CLS + (int)crank;
+        const int mb = item / n_groups;
         const int kn = s < n48 ? 48 : 32;
         const int c0 = s < n48 ? 48 * s : 48 * n48 + 32 * (s - n48);
         const int t0 = mb * mv;
@@ -154,7 +166,18 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&raw_empty[rs], rph ^ 1);
           mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
-          tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
+          if constexpr (CLS == 1) {
+            tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
+          } else {
+            // this CTA is done with the buffer: tell every CTA of the cluster, wait until all of them are, then send
+            // this CTA's share of the rows to everybody (each raw_full collects the CLS shares = kRawBytes)
+#pragma unroll
+            for (int p = 0; p < CLS; ++p) mbar_arrive_remote(&peer_empty[rs], (uint32_t)p);
+            mbar_wait_cluster(&peer_empty[rs], rph);
+            constexpr int kRowsPer = kRawRows / CLS;
+            tma_tensor_4d_g2s_mcast(smem + kOffRaw + rs * kRawBytes + crank * (kRawBytes / CLS), &tmap_x, kb * 8, 0, 0,
+                                    ny0 + (int)crank * kRowsPer, &raw_full[rs], (uint16_t)((1u << CLS) - 1u));
+          }
           if (++rs == kRawStages) { rs = 0; rph ^= 1; }
           if (u_primed) {  // already requested above
             u_primed = false;
@@ -176,7 +199,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       const uint32_t u_base = smem_u32(smem + kOffU);
       uint32_t g = 0, us = 0, uph = 0, aph = 0;  // g = stages issued; V stage g % kVBufs, its phase (g / kVBufs) & 1
       for (int item = item0; item < n_items; item += item_step) {
-        const int s = item % n_slices;
+        const int s = (item % n_groups) * CLS + (int)crank;
         const uint32_t kn = s < n48 ? 48u : 32u;
         const uint32_t idesc = make_idesc(kFmtTF32, 128, kn);
         const uint32_t idesc_neg = make_idesc(kFmtTF32, 128, kn, 1);  // D += (-A) * B
@@ -205,6 +228,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                 a_tm[i] = va + (i * 2 + jj) * 8;
                 b_desc[i] = make_smem_desc(ua + (i * 2 + jj) * u_per_point, u_lbo, 128, kLayoutNone);
               }
+              if (debug & 16) continue;  // ablation: no MMAs
               umma_tf32_ts(z0, a_tm[1], b_desc[1], idesc, acc);  // first writer of both accumulators
               umma_tf32_ts(z1, a_tm[1], b_desc[1], idesc, acc);
               umma_tf32_ts(z0, a_tm[0], b_desc[0], idesc, 1u);
@@ -224,18 +248,20 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     }
   } else {
     // ------------------------------------------------------------------ transform + epilogue warps
-    // thread = (tile row of the M-block = TMEM lane, 4-channel half): warp w owns TMEM lanes 32*(w&3)..+31
+    // thread = (MMA row = TMEM lane, channel group cq of NC channels): warp w owns TMEM lanes 32*(w&3)..+31
     const int quad = warp & 3;
-    const int half = warp >> 2;
+    const int cq = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t raw_base = smem_u32(smem + kOffRaw);
     const uint32_t stg_base = smem_u32(smem + kOffStg);
+    const int half = (cq * NC) >> 2;                       // which 16-byte half of a pixel's 32 bytes
+    const uint32_t sub = (uint32_t)((cq * NC) & 3) * 4;    // byte offset inside that half
 
     uint32_t rs = 0, rph = 0, g = 0, aph = 0;  // g = stages transformed (same counting as the MMA thread)
     for (int item = item0; item < n_items; item += item_step) {
-      const int s = item % n_slices;
-      const int mb = item / n_slices;
+      const int s = (item % n_groups) * CLS + (int)crank;
+      const int mb = item / n_groups;
       const int kn = s < n48 ? 48 : 32;
       const int c0s = s < n48 ? 48 * s : 48 * n48 + 32 * (s - n48);
       const int t0 = mb * mv;
@@ -247,8 +273,8 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       const int n = T / 49, t = T % 49, ty = t / 7, tx = t % 7;
       const uint32_t raw_off = tvalid ? (uint32_t)((n * 16 + 2 * ty - ny0) * 512 + tx * 32) : 0u;
       // SWIZZLE_32B: the 16-byte half of a pixel's 32 bytes is XORed with bit 2 of its x/2 index (address bit 7)
-      const uint32_t h0 = (uint32_t)((half ^ ((tx >> 2) & 1)) * 16);        // pixels with x/2 = tx
-      const uint32_t h1 = (uint32_t)((half ^ (((tx + 1) >> 2) & 1)) * 16);  // pixels with x/2 = tx + 1
+      const uint32_t h0 = (uint32_t)((half ^ ((tx >> 2) & 1)) * 16) + sub;        // pixels with x/2 = tx
+      const uint32_t h1 = (uint32_t)((half ^ (((tx + 1) >> 2) & 1)) * 16) + sub;  // pixels with x/2 = tx + 1
 
       for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(&raw_full[rs], rph);
@@ -265,29 +291,41 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           ++g;
           continue;
         }
-        float4 d[4][4];
-        if (tvalid) {
+        float d[4][4][NC];
+        if (tvalid && !(debug & 8)) {
           const uint32_t a = raw_base + rs * kRawBytes + raw_off;
 #pragma unroll
           for (int dy = 0; dy < 4; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 4; ++dx)
-              d[dy][dx] = ld_shared_v4(a + dy * 512 + (dx & 1) * 256 + (dx >> 1) * 32 + ((dx >> 1) ? h1 : h0));
+            for (int dx = 0; dx < 4; ++dx) {
+              const uint32_t ad = a + dy * 512 + (dx & 1) * 256 + (dx >> 1) * 32 + ((dx >> 1) ? h1 : h0);
+              if constexpr (NC == 4) {
+                const float4 v = ld_shared_v4(ad);
+                d[dy][dx][0] = v.x, d[dy][dx][1] = v.y, d[dy][dx][2] = v.z, d[dy][dx][3] = v.w;
+              } else {
+                const float2 v = ld_shared_v2(ad);
+                d[dy][dx][0] = v.x, d[dy][dx][1] = v.y;
+              }
+            }
         } else {
 #pragma unroll
           for (int dy = 0; dy < 4; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 4; ++dx) d[dy][dx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+              for (int c = 0; c < NC; ++c) d[dy][dx][c] = 0.f;
         }
         // column pass t = B^T d, in place over dy
 #pragma unroll
-        for (int dx = 0; dx < 4; ++dx) {
-          const float4 d0 = d[0][dx], d1 = d[1][dx], d2 = d[2][dx], d3 = d[3][dx];
-          d[0][dx] = make_float4(d0.x - d2.x, d0.y - d2.y, d0.z - d2.z, d0.w - d2.w);
-          d[1][dx] = make_float4(d1.x + d2.x, d1.y + d2.y, d1.z + d2.z, d1.w + d2.w);
-          d[2][dx] = make_float4(d2.x - d1.x, d2.y - d1.y, d2.z - d1.z, d2.w - d1.w);
-          d[3][dx] = make_float4(d1.x - d3.x, d1.y - d3.y, d1.z - d3.z, d1.w - d3.w);
-        }
+        for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const float d0 = d[0][dx][c], d1 = d[1][dx][c], d2 = d[2][dx][c], d3 = d[3][dx][c];
+            d[0][dx][c] = d0 - d2;
+            d[1][dx][c] = d1 + d2;
+            d[2][dx][c] = d2 - d1;
+            d[3][dx][c] = d1 - d3;
+          }
         // the raw stage is in registers now: hand it back to the producer before the row pass
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[rs]);
@@ -295,23 +333,28 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 
         // row pass V = t B by halves (half jh = points with j in {2jh, 2jh+1}), round to TF32, store into TMEM
         const uint32_t vb = DB ? (g & 1) : 0u, vph = DB ? ((g >> 1) & 1) : (g & 1);
-        const uint32_t vcol = tmem_base + lane_base + kVCol0 + vb * 128 + (uint32_t)half * 4;
+        const uint32_t vcol = tmem_base + lane_base + kVCol0 + vb * 128 + (uint32_t)(cq * NC);
 #pragma unroll
         for (int jh = 0; jh < 2; ++jh) {
           mbar_wait(&v_empty[vb * 2 + jh], vph ^ 1);  // the MMAs that last read this V half have completed
           tc_fence_after();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 a0 = d[i][0], a1 = d[i][1], a2 = d[i][2], a3 = d[i][3];
+            float v0[NC], v1[NC];  // points (i, 2jh) and (i, 2jh+1)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              const float a0 = d[i][0][c], a1 = d[i][1][c], a2 = d[i][2][c], a3 = d[i][3][c];
+              v0[c] = tm_tf32(jh == 0 ? a0 - a2 : a2 - a1);
+              v1[c] = tm_tf32(jh == 0 ? a1 + a2 : a1 - a3);
+            }
             const uint32_t dst = vcol + jh * 64 + (i * 2) * 8;
-            if (jh == 0) {
-              tmem_st_x4(dst, tm_tf32(a0.x - a2.x), tm_tf32(a0.y - a2.y), tm_tf32(a0.z - a2.z), tm_tf32(a0.w - a2.w));
-              tmem_st_x4(dst + 8, tm_tf32(a1.x + a2.x), tm_tf32(a1.y + a2.y), tm_tf32(a1.z + a2.z),
-                         tm_tf32(a1.w + a2.w));
+            if (debug & 8) continue;  // ablation: TMA + barriers only
+            if constexpr (NC == 4) {
+              tmem_st_x4(dst, v0[0], v0[1], v0[2], v0[3]);
+              tmem_st_x4(dst + 8, v1[0], v1[1], v1[2], v1[3]);
             } else {
-              tmem_st_x4(dst, tm_tf32(a2.x - a1.x), tm_tf32(a2.y - a1.y), tm_tf32(a2.z - a1.z), tm_tf32(a2.w - a1.w));
-              tmem_st_x4(dst + 8, tm_tf32(a1.x - a3.x), tm_tf32(a1.y - a3.y), tm_tf32(a1.z - a3.z),
-                         tm_tf32(a1.w - a3.w));
+              tmem_st_x2(dst, v0[0], v0[1]);
+              tmem_st_x2(dst + 8, v1[0], v1[1]);
             }
           }
           tmem_st_wait();
@@ -327,31 +370,36 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       const int W = out_padded ? 16 : 14;
       const int o = out_padded ? 1 : 0;
       const int pix0 = evalid ? ((n * W + 2 * ty + o) * W + 2 * tx + o) : -1;  // first output pixel of this tile
-      if (half == 0) pixtab[row] = pix0;
+      if (cq == 0) pixtab[row] = pix0;
       const uint32_t tstride = (uint32_t)(16 * kn + 16);
-      const int ncc = kn / 2;  // couts drained by this warp: [half*ncc, (half+1)*ncc)
+      const int ncc = kn / (WW / 4);  // couts drained by this warp: [cq*ncc, (cq+1)*ncc)
 
       mbar_wait(acc_full, aph);
       aph ^= 1;
       tc_fence_after();
       if (warp_active) {
 #pragma unroll 1
-        for (int cc = 0; cc < ncc; cc += 8) {
-          const int c0 = half * ncc + cc;
+        for (int cc = 0; cc < ncc; cc += EC) {
+          const int c0 = cq * ncc + cc;
           const uint32_t taddr = tmem_base + lane_base + c0;
-          float z[8][8];  // z[j*2 + a][e]
+          float z[8][EC];  // z[j*2 + a][e]
 #pragma unroll
-          for (int p = 0; p < 8; ++p) tmem_ld_x8(taddr + p * kAccStride, z[p]);
+          for (int p = 0; p < 8; ++p) {
+            if constexpr (EC == 8) tmem_ld_x8(taddr + p * kAccStride, z[p]);
+            else tmem_ld_x4(taddr + p * kAccStride, z[p]);
+          }
           tmem_ld_wait();
-          const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + c0s + c0));
-          const float4 sc1 = __ldg(reinterpret_cast<const float4*>(scale + c0s + c0 + 4));
-          const float4 sh0 = __ldg(reinterpret_cast<const float4*>(shift + c0s + c0));
-          const float4 sh1 = __ldg(reinterpret_cast<const float4*>(shift + c0s + c0 + 4));
-          const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-          const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-          float ov[4][8];  // Y[a][b] at ov[2*a + b]
+          float sc[EC], sh[EC];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int q4 = 0; q4 < EC / 4; ++q4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c0s + c0 + 4 * q4));
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(shift + c0s + c0 + 4 * q4));
+            sc[4 * q4] = s4.x, sc[4 * q4 + 1] = s4.y, sc[4 * q4 + 2] = s4.z, sc[4 * q4 + 3] = s4.w;
+            sh[4 * q4] = h4.x, sh[4 * q4 + 1] = h4.y, sh[4 * q4 + 2] = h4.z, sh[4 * q4 + 3] = h4.w;
+          }
+          float ov[4][EC];  // Y[a][b] at ov[2*a + b]
+#pragma unroll
+          for (int e = 0; e < EC; ++e) {
             ov[0][e] = fmaf(sc[e], z[0][e] + z[2][e] + z[4][e], sh[e]);
             ov[1][e] = fmaf(sc[e], z[2][e] - z[4][e] - z[6][e], sh[e]);
             ov[2][e] = fmaf(sc[e], z[1][e] + z[3][e] + z[5][e], sh[e]);
@@ -363,17 +411,18 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
           const uint32_t sdst = stg_base + (uint32_t)row * tstride + (uint32_t)c0 * 4;
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            st_shared_v4(sdst + p * (4 * kn), ov[p][0], ov[p][1], ov[p][2], ov[p][3]);
-            st_shared_v4(sdst + p * (4 * kn) + 16, ov[p][4], ov[p][5], ov[p][6], ov[p][7]);
-          }
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q4 = 0; q4 < EC / 4; ++q4)
+              st_shared_v4(sdst + p * (4 * kn) + 16 * q4, ov[p][4 * q4], ov[p][4 * q4 + 1], ov[p][4 * q4 + 2],
+                           ov[p][4 * q4 + 3]);
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging + pixel table complete, TMEM drained by all 8 warps
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * WW) : "memory");  // staging + pixel table complete, TMEM drained
       if (lane == 0) mbar_arrive(acc_empty);
       {
-        const int tid = threadIdx.x;  // 0..255
+        const int tid = threadIdx.x;  // 0 .. 32*WW-1
         const int chunks = kn / 4;    // 16-byte chunks per pixel
         const int units = valid_rows * kn;  // (tile, pixel, chunk)
         for (int u = tid; u < units; u += kWorkerWarps * 32) {
@@ -389,7 +438,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           // zero border of the reference's 16x16 frame (Kernel128_winograd.cu:163,243): edge tiles own their share
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
           const size_t rstride = (size_t)W * K;
-          float* p = y + (size_t)pix0 * K + c0s + half * ncc;
+          float* p = y + (size_t)pix0 * K + c0s + cq * ncc;
           const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
           const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
 #pragma unroll 1
@@ -406,10 +455,14 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging area and pixel table free for the next item
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * WW) : "memory");  // staging area and pixel table free for the next item
     }
   }
 
+  if constexpr (CLS > 1) {  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+    __syncwarp();
+    cluster_sync_all();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
@@ -476,13 +529,35 @@ int wino_tm_n48(int K) {  // 48*a + 32*b = K with a as large as possible
   return a;
 }
 
-int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
+// Cluster size of the throughput kernel for K output channels: the cout slices of an M-block are spread over the CTAs
+// of a cluster, so it must divide their number. Default 1 (no clusters); WG_WINO_CLS=2|3 enables the experiment.
+int wino_tm_cls(int K, int db) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("WG_WINO_CLS");
+    env = e ? atoi(e) : 0;
+  }
+  static int ww16 = -1;  // the 16-worker-warp experiment has no cluster variant
+  if (ww16 < 0) {
+    const char* e = getenv("WG_WINO_WW");
+    ww16 = (e && atoi(e) == 16) ? 1 : 0;
+  }
+  // Measured (256->256, N=256): clusters of 2 -> 216 us, of 3 -> 478 us, against 151 us without: the per-stage
+  // cross-CTA release/acquire handshake and the lock-step of the CTAs cost far more than the TMA requests they save.
+  // Off unless asked for.
+  if (db || ww16 || env < 2) return 1;
+  const int n48 = wino_tm_n48(K);
+  const int n_slices = n48 + (K - 48 * n48) / 32;
+  return (env == 2 || env == 3) && n_slices % env == 0 ? env : 1;
+}
+
+int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C, int cls) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return WG_ERR_DRIVER;
   // x[N][16][16][C] viewed as (c, x/2, x&1, n*16+y), 32-byte swizzle on the 8-channel inner box
   cuuint64_t dims[4] = {(cuuint64_t)C, 8, 2, (cuuint64_t)n_img * 16};
   cuuint64_t strides[3] = {(cuuint64_t)2 * C * 4, (cuuint64_t)C * 4, (cuuint64_t)16 * C * 4};
-  cuuint32_t box[4] = {8, 8, 2, (cuuint32_t)tm::kRawRows};
+  cuuint32_t box[4] = {8, 8, 2, (cuuint32_t)(tm::kRawRows / cls)};  // a cluster of cls CTAs loads the box in cls row shares
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, wg::l2_promotion(),
@@ -510,7 +585,7 @@ int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, 
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-template <bool DB>
+template <bool DB, int WW, int CLS>
 static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                      int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
@@ -518,7 +593,7 @@ static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* s
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_tm_kernel<DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm::kTotal) !=
+    if (cudaFuncSetAttribute(wino3x3_tm_kernel<DB, WW, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm::kTotal) !=
         cudaSuccess)
       return WG_ERR_CUDA;
     configured |= dev_bit_;
@@ -539,8 +614,9 @@ static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* s
   } else {
     double best = 1e30;
     for (int cand = 128; cand >= 64; cand -= 32) {
-      const long long items = (long long)((total_tiles + cand - 1) / cand) * n_slices;
-      const long long waves = (items + max_ctas - 1) / max_ctas;
+      const long long items = (long long)((total_tiles + cand - 1) / cand) * (n_slices / CLS);
+      const long long slots = max_ctas / CLS > 0 ? max_ctas / CLS : 1;
+      const long long waves = (items + slots - 1) / slots;
       const double cost = (double)waves * (0.35 + 0.65 * cand / 128.0);
       if (cost < best - 1e-9) {
         best = cost;
@@ -548,28 +624,62 @@ static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* s
       }
     }
   }
-  const int n_items = ((total_tiles + mv - 1) / mv) * n_slices;
-  int grid = n_items < max_ctas ? n_items : max_ctas;
-  if (grid < 1) grid = 1;
+  const int n_items = ((total_tiles + mv - 1) / mv) * (n_slices / CLS);  // items per cluster
+  int n_cl = max_ctas / CLS;
+  if (n_cl > n_items) n_cl = n_items;
+  if (n_cl < 1) n_cl = 1;
+  const int grid = n_cl * CLS;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(tm::kThreads);
+  cfg.blockDim = dim3(32 * (WW + 2));
   cfg.dynamicSmemBytes = tm::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CLS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CLS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_tm_kernel<DB>, tmap, u_img, scale, shift, y, n_img, C, K, n48, relu,
-                                     out_padded, mv);
+  cfg.numAttrs = na;
+  static int debug = -1;  // WG_DEBUG_ABLATE: 8 = no patch loads / TMEM stores, 16 = no MMAs (timing experiments only)
+  if (debug < 0) {
+    const char* e = getenv("WG_DEBUG_ABLATE");
+    debug = e ? atoi(e) : 0;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_tm_kernel<DB, WW, CLS>, tmap, u_img, scale, shift, y, n_img, C, K, n48, relu,
+                                     out_padded, mv, debug);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                    int n_img, int C, int K, int db, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
-  return db ? launch_tm<true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream)
-            : launch_tm<false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream);
+  static int ww = -1;  // WG_WINO_WW=8|16: worker warps (4 or 2 channels per thread); 16 and db are experiments
+  if (ww < 0) {
+    const char* e = getenv("WG_WINO_WW");
+    ww = e ? atoi(e) : 8;
+    if (ww != 16) ww = 8;
+  }
+#define WG_TM(DB_, WW_, CLS_) \
+  return launch_tm<DB_, WW_, CLS_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream)
+  if (db) {
+    if (ww == 16) WG_TM(true, 16, 1);
+    WG_TM(true, 8, 1);
+  }
+  if (ww == 16) WG_TM(false, 16, 1);
+  const int cls = wino_tm_cls(K, db);
+  if (cls == 3) WG_TM(false, 8, 3);
+  if (cls == 2) WG_TM(false, 8, 2);
+  WG_TM(false, 8, 1);
+#undef WG_TM
 }
 
 }  // namespace wg
