@@ -74,7 +74,7 @@ template <bool DB, int WW, int CLS>
 __global__ void __launch_bounds__(32 * (WW + 2), 1)
 wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
-                  int C, int K, int n48, int relu, int out_padded, int mv, int debug) {
+                  int C, int K, int n48, int relu, int out_padded, int mv) {
   using namespace tm;
   constexpr uint32_t kAccStride = Tmem<DB>::kAccStride, kVCol0 = Tmem<DB>::kVCol0;
   constexpr int kWorkerWarps = WW, kProducerWarp = WW, kMmaWarp = WW + 1;
@@ -228,7 +228,6 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                 a_tm[i] = va + (i * 2 + jj) * 8;
                 b_desc[i] = make_smem_desc(ua + (i * 2 + jj) * u_per_point, u_lbo, 128, kLayoutNone);
               }
-              if (debug & 16) continue;  // ablation: no MMAs
               umma_tf32_ts(z0, a_tm[1], b_desc[1], idesc, acc);  // first writer of both accumulators
               umma_tf32_ts(z1, a_tm[1], b_desc[1], idesc, acc);
               umma_tf32_ts(z0, a_tm[0], b_desc[0], idesc, 1u);
@@ -292,7 +291,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           continue;
         }
         float d[4][4][NC];
-        if (tvalid && !(debug & 8)) {
+        if (tvalid) {
           const uint32_t a = raw_base + rs * kRawBytes + raw_off;
 #pragma unroll
           for (int dy = 0; dy < 4; ++dy)
@@ -348,7 +347,6 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
               v1[c] = tm_tf32(jh == 0 ? a1 + a2 : a1 - a3);
             }
             const uint32_t dst = vcol + jh * 64 + (i * 2) * 8;
-            if (debug & 8) continue;  // ablation: TMA + barriers only
             if constexpr (NC == 4) {
               tmem_st_x4(dst, v0[0], v0[1], v0[2], v0[3]);
               tmem_st_x4(dst + 8, v1[0], v1[1], v1[2], v1[3]);
@@ -650,13 +648,10 @@ static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* s
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  static int debug = -1;  // WG_DEBUG_ABLATE: 8 = no patch loads / TMEM stores, 16 = no MMAs (timing experiments only)
-  if (debug < 0) {
-    const char* e = getenv("WG_DEBUG_ABLATE");
-    debug = e ? atoi(e) : 0;
-  }
+  // (A build of this kernel with switches for "no patch loads / TMEM stores" and "no MMAs" gave, 256->256 N=256:
+  //  153 us full, 111 us without the transform, 130 us without the MMAs, 95 us with neither; profiles/README.md.)
   cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_tm_kernel<DB, WW, CLS>, tmap, u_img, scale, shift, y, n_img, C, K, n48, relu,
-                                     out_padded, mv, debug);
+                                     out_padded, mv);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
