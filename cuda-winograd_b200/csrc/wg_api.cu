@@ -73,6 +73,7 @@ struct wg_layer {
   int tm_db;   // 3x3 TM kernel: 1 = double-buffered V, 32-wide slices
   int num_sms;
   float* d_filter;  // packed filter image (U or swizzled W^T)
+  float* d_filter_tm16;   // 3x3 bf16/fp16 only: U in the 16-bit image of the V-in-TMEM throughput kernel (48/32 slices)
   float* d_filter_small;  // 3x3 TF32 only: U in the plain KN=32 image the small-batch kernel reads (may alias d_filter)
   float* d_scale;
   float* d_shift;
@@ -80,6 +81,9 @@ struct wg_layer {
   const float* tmap_x;
   int tmap_n;
   CUtensorMap tmap;
+  const float* tmap_tm_x;     // 3x3 bf16/fp16: tensor map of the V-in-TMEM kernel (32-byte swizzle)
+  int tmap_tm_n;
+  CUtensorMap tmap_tm;
   const float* tmap_small_x;  // 3x3 small-batch kernel: same view, 26-row box
   int tmap_small_n;
   CUtensorMap tmap_small;
@@ -162,11 +166,18 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   if (kind == 0 && L->tile_n == 48) {
     L->tm_db = wino_tm_choose_db(cin, cout);
-    rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->tm_db, L->stream);
+    rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->tm_db, 0, L->stream);
   }
   else if (kind == 0) rc = filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)dtype, L->stream);
   else rc = weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
   g_launches++;
+  if (rc == WG_OK && kind == 0 && dtype != WG_TF32 && g_wino_kn == 48) {
+    // 16-bit operands: the throughput kernel keeps V packed in TMEM (its own filter image); small batches stay on the
+    // split-C variant of the shared-memory-operand kernel (d_filter)
+    WG_TRY(cudaMalloc(&L->d_filter_tm16, filter_elems * sizeof(uint16_t)));
+    rc = filter_transform_tm_launch(d_w, L->d_filter_tm16, cin, cout, 0, dtype == WG_FP16 ? 2 : 1, L->stream);
+    g_launches++;
+  }
   if (rc == WG_OK && kind == 0 && dtype == WG_TF32) {
     if (L->tile_n == 32) {
       L->d_filter_small = L->d_filter;
@@ -234,6 +245,23 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
       return rc;
     }
   }
+  if (L->kind == 0 && L->d_filter_tm16 != nullptr && !(out_flags & 2)) {
+    // bf16 / fp16 operands, throughput-sized batch (the split-C latency mode of the other kernel takes the small ones)
+    const long long items64 = (long long)((N * 49 + 63) / 64) * (L->cout / 64);
+    if (items64 * 4 > max_ctas) {
+      if (L->tmap_tm_x != x || L->tmap_tm_n != N) {
+        int rc = wino_tm_make_tmap(&L->tmap_tm, x, N, L->cin, 1);
+        if (rc != WG_OK) return rc;
+        L->tmap_tm_x = x;
+        L->tmap_tm_n = N;
+      }
+      int rc = wino_tm_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0,
+                              L->dtype == WG_FP16 ? 2 : 1, L->relu, out_flags, max_ctas, stream);
+      g_launches++;
+      if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
+      return rc;
+    }
+  }
   if (L->tmap_x != x || L->tmap_n != N) {
     int rc = L->kind == 1 ? one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin)
              : L->tile_n == 48 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin, wino_tm_cls(L->cout, L->tm_db))
@@ -250,7 +278,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   }
   int rc;
   if (L->kind == 0 && L->tile_n == 48)
-    rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, L->relu,
+    rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, 0, L->relu,
                         out_flags, max_ctas, stream);
   else if (L->kind == 0)
     rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,
@@ -331,6 +359,7 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
 int wg_destroy(wg_layer_t* L) {
   if (!L) return WG_ERR_ARG;
   if (L->d_filter_small && L->d_filter_small != L->d_filter) cudaFree(L->d_filter_small);
+  if (L->d_filter_tm16) cudaFree(L->d_filter_tm16);
   if (L->d_filter) cudaFree(L->d_filter);
   if (L->d_scale) cudaFree(L->d_scale);
   if (L->d_shift) cudaFree(L->d_shift);

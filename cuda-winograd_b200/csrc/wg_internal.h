@@ -31,9 +31,11 @@ int filter_transform_launch(const float* w_kcrs, void* u_img, int C, int K, int 
 int wino_tm_cls(int K, int db);  // cluster size (CTAs sharing the raw tiles of one M-block)
 int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C, int cls);
 int wino_tm_choose_db(int C, int K);  // 1 = double-buffered V / 32-wide slices, 0 = one V stage / 48-wide slices
-int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, int db, cudaStream_t stream);
+int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, int db, int op16,
+                               cudaStream_t stream);  // op16: 0 tf32, 1 bf16, 2 fp16
 int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                   int n_img, int C, int K, int db, int relu, int out_padded, int max_ctas, cudaStream_t stream);
+                   int n_img, int C, int K, int db, int op16, int relu, int out_padded, int max_ctas,
+                   cudaStream_t stream);
 
 // small-batch latency variant (wino_small_kernel.cu): TF32 only, filter in the plain KN=32 image
 int wino_small_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);

@@ -26,6 +26,8 @@
 #include "wg_internal.h"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace wg {
@@ -61,6 +63,23 @@ static_assert(kTotal <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ float tm_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
+template <bool H16>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (H16) umma_f16_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+  else umma_tf32_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+}
+
+// two fp32 -> one 32-bit TMEM column of 16-bit operands (first value in the low half), round to nearest
+__device__ __forceinline__ float pack16(float lo, float hi, int fp16) {
+  if (fp16) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+  }
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return __uint_as_float(*reinterpret_cast<const uint32_t*>(&b));
+}
+
 // DB: V double-buffered in TMEM at the price of 32-wide cout slices (see Tmem). With one V stage the transform of stage
 // s+1 cannot store before the MMAs of stage s have completed, and those cannot start before the slowest of the 8 warps
 // has stored stage s: every stage ends in an implicit barrier. With two stages the warps run up to one stage ahead.
@@ -70,16 +89,21 @@ __device__ __forceinline__ float tm_tf32(float x) { return __uint_as_float(__flo
 // tma_tensor_probe_r01.txt; with everything but TMA and barriers switched off it still needs 62 % of its time), and
 // the raw tile is the same for all cout slices of an M-block. EXPERIMENT, default off: measured 1.4x (CLS=2) to 3x
 // (CLS=3) slower than CLS=1, see wino_tm_cls().
-template <bool DB, int WW, int CLS>
+// H16: 16-bit operands (bf16, or fp16 with `fp16` set): V is stored in TMEM as packed pairs (column c = channels 2c
+// and 2c+1), tcgen05.mma kind::f16 with K = 16, so a V stage covers 16 channels = TWO 8-channel raw stages and the
+// per-stage hand-offs (and the MMA count) per channel halve. I/O stays fp32.
+template <bool DB, int WW, int CLS, bool H16 = false>
 __global__ void __launch_bounds__(32 * (WW + 2), 1)
 wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
-                  int C, int K, int n48, int relu, int out_padded, int mv) {
+                  int C, int K, int n48, int relu, int out_padded, int mv, int fp16) {
   using namespace tm;
   constexpr uint32_t kAccStride = Tmem<DB>::kAccStride, kVCol0 = Tmem<DB>::kVCol0;
   constexpr int kWorkerWarps = WW, kProducerWarp = WW, kMmaWarp = WW + 1;
   constexpr int NC = 32 / WW;       // channels per worker thread (4 or 2)
   constexpr int EC = WW == 8 ? 8 : 4;  // couts per epilogue step
+  constexpr int kSub = H16 ? 2 : 1;    // 8-channel raw stages per V stage
+  static_assert(!H16 || (WW == 8 && !DB && CLS == 1), "16-bit operands: 8 worker warps, one V stage, no clusters");
   const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
   out_padded &= 1;
   pdl_launch_dependents();  // the next launch in the stream may start its prologue (it waits before touching x / y)
@@ -126,7 +150,7 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   const uint32_t crank = CLS > 1 ? cluster_ctarank() : 0u;
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_kb = C / 8;
+  const int n_kb = C / (8 * kSub);  // V stages (8 or 16 channels each)
   const int n_slices = n48 + (K - 48 * n48) / 32;
   const int total_tiles = n_img * 49;
   const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host to balance waves
@@ -164,10 +188,17 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
         for (int kb = 0; kb < n_kb; ++kb) {
+          if constexpr (H16) {  // first of the two raw stages of this V stage (the second one follows below)
+            mbar_wait(&raw_empty[rs], rph ^ 1);
+            mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
+            tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawBytes, &tmap_x, kb * 16, 0, 0, ny0, &raw_full[rs]);
+            if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          }
           mbar_wait(&raw_empty[rs], rph ^ 1);
           mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
           if constexpr (CLS == 1) {
-            tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawBytes, &tmap_x, kb * 8, 0, 0, ny0, &raw_full[rs]);
+            tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawBytes, &tmap_x, H16 ? kb * 16 + 8 : kb * 8, 0, 0, ny0,
+                              &raw_full[rs]);
           } else {
             // this CTA is done with the buffer: tell every CTA of the cluster, wait until all of them are, then send
             // this CTA's share of the rows to everybody (each raw_full collects the CLS shares = kRawBytes)
@@ -201,8 +232,9 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       for (int item = item0; item < n_items; item += item_step) {
         const int s = (item % n_groups) * CLS + (int)crank;
         const uint32_t kn = s < n48 ? 48u : 32u;
-        const uint32_t idesc = make_idesc(kFmtTF32, 128, kn);
-        const uint32_t idesc_neg = make_idesc(kFmtTF32, 128, kn, 1);  // D += (-A) * B
+        const uint32_t fmt = H16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
+        const uint32_t idesc = make_idesc(fmt, 128, kn);
+        const uint32_t idesc_neg = make_idesc(fmt, 128, kn, 1);  // D += (-A) * B
         const uint32_t u_per_point = 2 * kn * 16, u_lbo = kn * 16;
         mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
@@ -228,12 +260,12 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                 a_tm[i] = va + (i * 2 + jj) * 8;
                 b_desc[i] = make_smem_desc(ua + (i * 2 + jj) * u_per_point, u_lbo, 128, kLayoutNone);
               }
-              umma_tf32_ts(z0, a_tm[1], b_desc[1], idesc, acc);  // first writer of both accumulators
-              umma_tf32_ts(z1, a_tm[1], b_desc[1], idesc, acc);
-              umma_tf32_ts(z0, a_tm[0], b_desc[0], idesc, 1u);
-              umma_tf32_ts(z0, a_tm[2], b_desc[2], idesc, 1u);
-              umma_tf32_ts(z1, a_tm[2], b_desc[2], idesc_neg, 1u);
-              umma_tf32_ts(z1, a_tm[3], b_desc[3], idesc_neg, 1u);
+              umma_ts<H16>(z0, a_tm[1], b_desc[1], idesc, acc);  // first writer of both accumulators
+              umma_ts<H16>(z1, a_tm[1], b_desc[1], idesc, acc);
+              umma_ts<H16>(z0, a_tm[0], b_desc[0], idesc, 1u);
+              umma_ts<H16>(z0, a_tm[2], b_desc[2], idesc, 1u);
+              umma_ts<H16>(z1, a_tm[2], b_desc[2], idesc_neg, 1u);
+              umma_ts<H16>(z1, a_tm[3], b_desc[3], idesc_neg, 1u);
             }
             umma_commit(&u_empty[us]);
             umma_commit(&v_empty[vb * 2 + jh]);  // this V half may be overwritten
@@ -276,11 +308,14 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       const uint32_t h1 = (uint32_t)((half ^ (((tx + 1) >> 2) & 1)) * 16) + sub;  // pixels with x/2 = tx + 1
 
       for (int kb = 0; kb < n_kb; ++kb) {
-        mbar_wait(&raw_full[rs], rph);
         if (!warp_active) {
-          // nothing to transform: release the raw stage and report "V ready" in step with the other warps
-          if (lane == 0) mbar_arrive(&raw_empty[rs]);
-          if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          // nothing to transform: release the raw stage(s) and report "V ready" in step with the other warps
+#pragma unroll
+          for (int sb = 0; sb < kSub; ++sb) {
+            mbar_wait(&raw_full[rs], rph);
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);
+            if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          }
           const uint32_t vb = DB ? (g & 1) : 0u, vph = DB ? ((g >> 1) & 1) : (g & 1);
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
@@ -290,6 +325,10 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           ++g;
           continue;
         }
+        const uint32_t vb = DB ? (g & 1) : 0u, vph = DB ? ((g >> 1) & 1) : (g & 1);
+#pragma unroll
+        for (int sb = 0; sb < kSub; ++sb) {  // H16: two 8-channel raw stages fill one 16-channel V stage
+        mbar_wait(&raw_full[rs], rph);
         float d[4][4][NC];
         if (tvalid) {
           const uint32_t a = raw_base + rs * kRawBytes + raw_off;
@@ -330,24 +369,31 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         if (lane == 0) mbar_arrive(&raw_empty[rs]);
         if (++rs == kRawStages) { rs = 0; rph ^= 1; }
 
-        // row pass V = t B by halves (half jh = points with j in {2jh, 2jh+1}), round to TF32, store into TMEM
-        const uint32_t vb = DB ? (g & 1) : 0u, vph = DB ? ((g >> 1) & 1) : (g & 1);
-        const uint32_t vcol = tmem_base + lane_base + kVCol0 + vb * 128 + (uint32_t)(cq * NC);
+        // row pass V = t B by halves (half jh = points with j in {2jh, 2jh+1}), round to the operand type, store into
+        // TMEM (tf32: one column per channel; 16-bit: one column per channel pair, raw stage sb fills columns 4*sb..)
+        const uint32_t vcol = tmem_base + lane_base + kVCol0 + vb * 128 +
+                              (uint32_t)(H16 ? sb * 4 + cq * 2 : cq * NC);
 #pragma unroll
         for (int jh = 0; jh < 2; ++jh) {
-          mbar_wait(&v_empty[vb * 2 + jh], vph ^ 1);  // the MMAs that last read this V half have completed
-          tc_fence_after();
+          if (sb == 0) {
+            mbar_wait(&v_empty[vb * 2 + jh], vph ^ 1);  // the MMAs that last read this V half have completed
+            tc_fence_after();
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float v0[NC], v1[NC];  // points (i, 2jh) and (i, 2jh+1)
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
               const float a0 = d[i][0][c], a1 = d[i][1][c], a2 = d[i][2][c], a3 = d[i][3][c];
-              v0[c] = tm_tf32(jh == 0 ? a0 - a2 : a2 - a1);
-              v1[c] = tm_tf32(jh == 0 ? a1 + a2 : a1 - a3);
+              v0[c] = jh == 0 ? a0 - a2 : a2 - a1;
+              v1[c] = jh == 0 ? a1 + a2 : a1 - a3;
+              if constexpr (!H16) v0[c] = tm_tf32(v0[c]), v1[c] = tm_tf32(v1[c]);
             }
             const uint32_t dst = vcol + jh * 64 + (i * 2) * 8;
-            if constexpr (NC == 4) {
+            if constexpr (H16) {
+              tmem_st_x2(dst, pack16(v0[0], v0[1], fp16), pack16(v0[2], v0[3], fp16));
+              tmem_st_x2(dst + 8, pack16(v1[0], v1[1], fp16), pack16(v1[2], v1[3], fp16));
+            } else if constexpr (NC == 4) {
               tmem_st_x4(dst, v0[0], v0[1], v0[2], v0[3]);
               tmem_st_x4(dst + 8, v1[0], v1[1], v1[2], v1[3]);
             } else {
@@ -355,11 +401,14 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
               tmem_st_x2(dst + 8, v1[0], v1[1]);
             }
           }
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&v_full[vb * 2 + jh]);
+          if (sb == kSub - 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&v_full[vb * 2 + jh]);
+          }
         }
+        }  // sb
         ++g;
       }
 
@@ -471,8 +520,9 @@ wino3x3_tm_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 // copies: cout slices of 48 (n48 of them) then 32; per slice [C/8 k-block][2 j-halves][4 i][2 jj][2 k-chunks][KN couts]
 // [4 channels] (j = 2*jh + jj). 512 bytes per (k-block, cout), so slice s starts at byte (C/8)*512*c0(s).
 // Replaces the offline weight_generator loop (/root/reference/data_generator.py:63-78; that one is F(4x4), 36 points).
+// op16 = 1 (bf16) / 2 (fp16): 16-channel k-blocks, 8 channels per 16-byte chunk, same 512 bytes per (k-block, cout).
 __global__ void filter_transform_tm_kernel(const float* __restrict__ w_kcrs, float* __restrict__ u_img, int C, int K,
-                                           int n48) {
+                                           int n48, int op16) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * K) return;
   const int ch = idx % C;
@@ -502,6 +552,9 @@ __global__ void filter_transform_tm_kernel(const float* __restrict__ w_kcrs, flo
   const int kl = k - c0;
   const int kb = ch / 8, chunk = (ch % 8) / 4, e = ch % 4;
   const size_t base = (size_t)(C / 8) * 128 * c0 + (size_t)kb * 128 * kn;  // floats
+  // 16-bit image, in 2-byte elements: 256 per (16-channel block, cout)
+  const int kb16 = ch / 16, chunk16 = (ch % 16) / 8, e16 = ch % 8;
+  const size_t base16 = (size_t)(C / 16) * 256 * c0 + (size_t)kb16 * 256 * kn;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float u[4];
@@ -512,7 +565,10 @@ __global__ void filter_transform_tm_kernel(const float* __restrict__ w_kcrs, flo
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = (j >> 1) * 8 + i * 2 + (j & 1);
-      u_img[base + (size_t)p * (2 * kn * 4) + ((size_t)chunk * kn + kl) * 4 + e] = to_tf32_rn(u[j]);
+      const size_t o16 = base16 + (size_t)p * (2 * kn * 8) + ((size_t)chunk16 * kn + kl) * 8 + e16;
+      if (op16 == 2) reinterpret_cast<__half*>(u_img)[o16] = __float2half_rn(u[j]);
+      else if (op16 == 1) reinterpret_cast<__nv_bfloat16*>(u_img)[o16] = __float2bfloat16_rn(u[j]);
+      else u_img[base + (size_t)p * (2 * kn * 4) + ((size_t)chunk * kn + kl) * 4 + e] = to_tf32_rn(u[j]);
     }
   }
 }
@@ -577,21 +633,23 @@ int wino_tm_choose_db(int C, int K) {
   return 0;
 }
 
-int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, int db, cudaStream_t stream) {
+int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, int db, int op16,
+                               cudaStream_t stream) {
   const int n = C * K;
-  filter_transform_tm_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, db ? 0 : wino_tm_n48(K));
+  filter_transform_tm_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, db ? 0 : wino_tm_n48(K), op16);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-template <bool DB, int WW, int CLS>
+template <bool DB, int WW, int CLS, bool H16 = false>
 static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                     int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+                     int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream,
+                     int fp16 = 0) {
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_tm_kernel<DB, WW, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm::kTotal) !=
+    if (cudaFuncSetAttribute(wino3x3_tm_kernel<DB, WW, CLS, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm::kTotal) !=
         cudaSuccess)
       return WG_ERR_CUDA;
     configured |= dev_bit_;
@@ -650,13 +708,18 @@ static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* s
   cfg.numAttrs = na;
   // (A build of this kernel with switches for "no patch loads / TMEM stores" and "no MMAs" gave, 256->256 N=256:
   //  153 us full, 111 us without the transform, 130 us without the MMAs, 95 us with neither; profiles/README.md.)
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_tm_kernel<DB, WW, CLS>, tmap, u_img, scale, shift, y, n_img, C, K, n48, relu,
-                                     out_padded, mv);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_tm_kernel<DB, WW, CLS, H16>, tmap, u_img, scale, shift, y, n_img, C,
+                                     K, n48, relu, out_padded, mv, fp16);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                   int n_img, int C, int K, int db, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+                   int n_img, int C, int K, int db, int op16, int relu, int out_padded, int max_ctas,
+                   cudaStream_t stream) {
+  // op16: 0 = TF32 operands, 1 = bf16, 2 = fp16 (V packed in TMEM, 16-channel stages)
+  if (op16)
+    return launch_tm<false, 8, 1, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream,
+                                        op16 == 2);
   static int ww = -1;  // WG_WINO_WW=8|16: worker warps (4 or 2 channels per thread); 16 and db are experiments
   if (ww < 0) {
     const char* e = getenv("WG_WINO_WW");

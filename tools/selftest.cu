@@ -2,6 +2,7 @@
 // against an in-program FP64 direct convolution, plus a one-instruction UMMA descriptor probe that tells which
 // (LBO, SBO) reading of the no-swizzle K-major layout the hardware implements. Run on a B200:
 //   tools/selftest [quick]
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -581,6 +582,93 @@ __global__ void umma_ts_probe_kernel(const float* a, const float* b, float* d, l
   if (tid < 32) tmem_dealloc<512>(tb);
 }
 
+// 16-bit operands (kind::f16, bf16 here): A[128][16] packed two per TMEM column (k = 2c in the low half), B[48][16] in
+// shared memory (K-major no-swizzle: 16-byte chunks of 8 elements), D = A*B.
+__global__ void umma_ts16_probe_kernel(const float* a, const float* b, float* d) {
+  using namespace wg;
+  __shared__ __align__(1024) uint8_t sb[2 * 48 * 16];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 16; i += blockDim.x) {
+    const int r = i / 16, k = i % 16;
+    *reinterpret_cast<__nv_bfloat16*>(sb + (k / 8) * (48 * 16) + r * 16 + (k % 8) * 2) = __float2bfloat16_rn(b[i]);
+  }
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc<512>(&tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tptr, a_col = 256;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  float pk[8];
+  for (int c = 0; c < 8; ++c) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a[tid * 16 + 2 * c], a[tid * 16 + 2 * c + 1]);  // .x = low half
+    pk[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h2));
+  }
+  tmem_st_x4(tb + lane_base + a_col, pk[0], pk[1], pk[2], pk[3]);
+  tmem_st_x4(tb + lane_base + a_col + 4, pk[4], pk[5], pk[6], pk[7]);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid < 32) {
+    if (elect_one()) {
+      const uint64_t bd = make_smem_desc(smem_u32(sb), 48 * 16, 128, kLayoutNone);
+      umma_f16_ts(tb, tb + a_col, bd, make_idesc(kFmtBF16, 128, 48), 0);
+      umma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  float v[16];
+  for (int c0 = 0; c0 < 48; c0 += 16) {
+    tmem_ld_x16(tb + lane_base + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) d[tid * 48 + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<512>(tb);
+}
+
+static void run_ts16_probe() {
+  std::vector<float> a(128 * 16), b(48 * 16), d(128 * 48);
+  for (auto& v : a) v = roundf(frand() * 16.f);  // small integers: exact in bf16
+  for (auto& v : b) v = roundf(frand() * 16.f);
+  float *da, *db, *dd;
+  CK(cudaMalloc(&da, a.size() * 4));
+  CK(cudaMalloc(&db, b.size() * 4));
+  CK(cudaMalloc(&dd, d.size() * 4));
+  CK(cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  umma_ts16_probe_kernel<<<1, 128>>>(da, db, dd);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("TS16 probe: kernel failed: %s\n", cudaGetErrorString(e));
+    return;
+  }
+  CK(cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost));
+  double e1 = 0, e2 = 0;  // e2: hypothesis "k = 2c in the HIGH half"
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < 48; ++n) {
+      double r1 = 0, r2 = 0;
+      for (int k = 0; k < 16; ++k) {
+        r1 += (double)a[m * 16 + k] * b[n * 16 + k];
+        r2 += (double)a[m * 16 + (k ^ 1)] * b[n * 16 + k];
+      }
+      e1 = fmax(e1, fabs(r1 - d[m * 48 + n]));
+      e2 = fmax(e2, fabs(r2 - d[m * 48 + n]));
+    }
+  printf("TS16 probe (bf16 A from TMEM, M=128 N=48 K=16): max abs err %.3g with k=2c in the low half, %.3g with the halves "
+         "swapped -> %s\n", e1, e2, e1 == 0 ? "low-half-first MATCH" : (e2 == 0 ? "high-half-first MATCH" : "mismatch"));
+}
+
 static void run_ts_probe() {
   std::vector<float> a(128 * 8), b(48 * 8), d(128 * 112);
   for (auto& v : a) v = roundf(frand() * 16.f);
@@ -708,6 +796,7 @@ int main(int argc, char** argv) {
   if (wg_device_count() == 0) return 1;
   if (argc > 1 && !strcmp(argv[1], "ts")) {
     run_ts_probe();
+    run_ts16_probe();
     return 0;
   }
   if (argc > 1 && !strcmp(argv[1], "mma")) {
