@@ -72,7 +72,8 @@ def test_1x1_reference_shapes_n1(lib_loaded, torch_cuda, seeded_data, mode, cin,
 
 
 # ------------------------------------------------------------------------------------------------------- batch / edges
-@pytest.mark.parametrize("n,c,k", [(2, 32, 32), (3, 64, 96), (5, 128, 128), (8, 8, 32), (11, 40, 64)])
+@pytest.mark.parametrize("n,c,k", [(2, 32, 32), (3, 64, 96), (5, 128, 128), (8, 8, 32), (11, 40, 64), (300, 16, 32),
+                                   (131, 24, 96), (37, 64, 160)])
 @pytest.mark.parametrize("relu", [True, False])
 def test_3x3_ragged_batches(lib_loaded, torch_cuda, n, c, k, relu):
     """Batches whose 49*N tiles do not fill the last 128-tile M-block, odd channel-block counts, no-ReLU variant."""
@@ -106,7 +107,7 @@ def test_3x3_small_batch_split_c_mode(lib_loaded, torch_cuda, n, c, k, padded):
 TOL_BF16 = 1e-2
 
 
-@pytest.mark.parametrize("n,c,k", [(1, 128, 128), (1, 256, 256), (3, 64, 64), (5, 48, 128), (64, 128, 128)])
+@pytest.mark.parametrize("n,c,k", [(1, 128, 128), (1, 256, 256), (3, 64, 64), (5, 48, 128), (64, 128, 128), (131, 48, 192)])
 def test_3x3_bf16_operand_variant(lib_loaded, torch_cuda, n, c, k):
     """The stated bf16 variant (north_star): bf16 V/U operands, fp32 I/O + accumulation, tolerance 1e-2."""
     torch = torch_cuda
@@ -120,7 +121,7 @@ def test_3x3_bf16_operand_variant(lib_loaded, torch_cuda, n, c, k):
     assert np.all(yp[:, 0] == 0) and np.all(yp[:, :, 15] == 0)
 
 
-@pytest.mark.parametrize("n,c,k", [(1, 128, 128), (2, 256, 256), (5, 48, 128), (64, 128, 128)])
+@pytest.mark.parametrize("n,c,k", [(1, 128, 128), (2, 256, 256), (5, 48, 128), (64, 128, 128), (131, 32, 64)])
 def test_3x3_fp16_operand_variant(lib_loaded, torch_cuda, n, c, k):
     """fp16 V/U operands: the same 10-bit mantissa as TF32 (so the TF32 bar, 1e-3) at the bf16 variant's speed; valid
     while |V| < 65504, which the reference's data distributions (and post-BN/ReLU feature maps) satisfy by far."""
