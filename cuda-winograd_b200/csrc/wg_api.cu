@@ -15,7 +15,18 @@ namespace wg {
 static thread_local char g_last_cuda_error[256] = "";
 static std::atomic<long long> g_launches{0};
 static int g_max_ctas = 0;  // 0 = number of SMs
-static int g_wino_kn = 48;  // 48 = V-in-TMEM kernel (default); 64 / 32 = the shared-memory-operand kernels (folded / per point)
+// 96 = V-in-TMEM kernel with the whole inverse transform folded into the MMAs (default); 48 = V-in-TMEM, half fold;
+// 64 / 32 = the shared-memory-operand kernels (half fold / one accumulator per Winograd point)
+static int g_wino_kn = -1;
+static int wino_kn() {
+  if (g_wino_kn < 0) {
+    const char* e = getenv("WG_WINO_KN");  // same meaning as wg_set_wino_kn()
+    const int v = e ? atoi(e) : 96;
+    g_wino_kn = (v == 32 || v == 64 || v == 48) ? v : 96;
+  }
+  return g_wino_kn;
+}
+static bool kn_tm(int kn) { return kn == 48 || kn == 96; }  // V-in-TMEM kernels
 
 static int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
@@ -71,6 +82,7 @@ struct wg_layer {
   int cin, cout, relu, dtype, device;
   int tile_n;  // 3x3: cout slice KN; 1x1: BN
   int tm_db;   // 3x3 TM kernel: 1 = double-buffered V, 32-wide slices
+  int tm16_ff; // 3x3 bf16/fp16: d_filter_tm16 is the full-fold kernel's image (96-wide slices)
   int num_sms;
   float* d_filter;  // packed filter image (U or swizzled W^T)
   float* d_filter_tm16;   // 3x3 bf16/fp16 only: U in the 16-bit image of the V-in-TMEM throughput kernel (48/32 slices)
@@ -141,8 +153,8 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   size_t filter_elems = 0;
   if (kind == 0) {
     if (dtype != WG_TF32) L->tile_n = 64;
-    else if (g_wino_kn == 48) L->tile_n = 48;
-    else L->tile_n = (g_wino_kn == 32 || cout % 64 != 0) ? 32 : 64;
+    else if (kn_tm(wino_kn())) L->tile_n = wino_kn();
+    else L->tile_n = (wino_kn() == 32 || cout % 64 != 0) ? 32 : 64;
     filter_elems = (size_t)16 * cin * cout;
   } else {
     L->tile_n = (cout % 256 == 0) ? 256 : 128;
@@ -164,18 +176,23 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   WG_TRY(cudaMemcpyAsync(d_w, w, w_elems * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_scale, scale, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
-  if (kind == 0 && L->tile_n == 48) {
+  if (kind == 0 && L->tile_n == 96) {
+    rc = filter_transform_ff_launch(d_w, L->d_filter, cin, cout, 0, L->stream);
+  } else if (kind == 0 && L->tile_n == 48) {
     L->tm_db = wino_tm_choose_db(cin, cout);
     rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->tm_db, 0, L->stream);
   }
   else if (kind == 0) rc = filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)dtype, L->stream);
   else rc = weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
   g_launches++;
-  if (rc == WG_OK && kind == 0 && dtype != WG_TF32 && g_wino_kn == 48) {
+  if (rc == WG_OK && kind == 0 && dtype != WG_TF32 && kn_tm(wino_kn())) {
     // 16-bit operands: the throughput kernel keeps V packed in TMEM (its own filter image); small batches stay on the
     // split-C variant of the shared-memory-operand kernel (d_filter)
     WG_TRY(cudaMalloc(&L->d_filter_tm16, filter_elems * sizeof(uint16_t)));
-    rc = filter_transform_tm_launch(d_w, L->d_filter_tm16, cin, cout, 0, dtype == WG_FP16 ? 2 : 1, L->stream);
+    L->tm16_ff = wino_kn() == 96;
+    rc = L->tm16_ff ? filter_transform_ff_launch(d_w, L->d_filter_tm16, cin, cout, dtype == WG_FP16 ? 2 : 1, L->stream)
+                    : filter_transform_tm_launch(d_w, L->d_filter_tm16, cin, cout, 0, dtype == WG_FP16 ? 2 : 1,
+                                                 L->stream);
     g_launches++;
   }
   if (rc == WG_OK && kind == 0 && dtype == WG_TF32) {
@@ -222,7 +239,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   // address (stores go out as multimem.st and land in every GPU's buffer: fused conv + all-gather of the output).
   if (out_padded & ~3) return WG_ERR_ARG;
   const int out_flags = out_padded & 3;
-  if ((out_flags & 2) && !(L->kind == 0 && L->dtype == WG_TF32 && L->tile_n == 48)) return WG_ERR_ARG;
+  if ((out_flags & 2) && !(L->kind == 0 && L->dtype == WG_TF32 && kn_tm(L->tile_n))) return WG_ERR_ARG;
   out_padded &= 1;
   int cur = -1;
   WG_CUDA(cudaGetDevice(&cur));
@@ -255,8 +272,11 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
         L->tmap_tm_x = x;
         L->tmap_tm_n = N;
       }
-      int rc = wino_tm_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0,
-                              L->dtype == WG_FP16 ? 2 : 1, L->relu, out_flags, max_ctas, stream);
+      const int op16 = L->dtype == WG_FP16 ? 2 : 1;
+      int rc = L->tm16_ff ? wino_ff_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
+                                           op16, L->relu, out_flags, max_ctas, stream)
+                          : wino_tm_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
+                                           0, op16, L->relu, out_flags, max_ctas, stream);
       g_launches++;
       if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
       return rc;
@@ -264,6 +284,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   }
   if (L->tmap_x != x || L->tmap_n != N) {
     int rc = L->kind == 1 ? one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin)
+             : L->tile_n == 96 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin, 1)
              : L->tile_n == 48 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin, wino_tm_cls(L->cout, L->tm_db))
                                : wino_make_tmap(&L->tmap, x, N, L->cin);
     if (rc != WG_OK) return rc;
@@ -277,7 +298,10 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
     L->tmap_y_n = N;
   }
   int rc;
-  if (L->kind == 0 && L->tile_n == 48)
+  if (L->kind == 0 && L->tile_n == 96)
+    rc = wino_ff_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, L->relu, out_flags,
+                        max_ctas, stream);
+  else if (L->kind == 0 && L->tile_n == 48)
     rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, 0, L->relu,
                         out_flags, max_ctas, stream);
   else if (L->kind == 0)
@@ -427,6 +451,6 @@ void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean,
 }
 
 void wg_set_max_ctas(int max_ctas) { g_max_ctas = max_ctas; }
-void wg_set_wino_kn(int kn) { g_wino_kn = (kn == 32 || kn == 64) ? kn : 48; }
+void wg_set_wino_kn(int kn) { g_wino_kn = (kn == 32 || kn == 64 || kn == 48) ? kn : 96; }
 
 }  // extern "C"

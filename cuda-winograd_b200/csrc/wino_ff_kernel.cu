@@ -1,0 +1,604 @@
+// Fused 3x3 conv (Winograd F(2x2,3x3)) + folded BatchNorm + ReLU for sm_100a -- throughput kernel with the WHOLE
+// inverse transform folded into the tensor core ("full fold"): 4 accumulators x 96 couts.
+//
+// Replaces kernel_{128,256}_winograd_BtdB -> kernel_*_OuterProduct_* -> kernel_*_winograd_AtIA
+// (/root/reference/Kernel128_winograd.cu:28-213, Kernel256_winograd.cu:27-218). Same skeleton as wino3x3_tm_kernel
+// (wino_tm_kernel.cu: persistent, 128-tile M-blocks x cout slices, 8-channel stages, V = B^T d B written by the
+// transform warps straight into TENSOR MEMORY and read from there as the MMA's A operand), but
+//
+//   * the accumulators are the four output pixels of a tile themselves: Y[a][b] = sum_{i,j} A^T[a][i] A^T[b][j] M[i][j],
+//     so accumulator (a,b) collects the 9 Winograd points with A^T[a][i] != 0 and A^T[b][j] != 0, the sign
+//     A^T[a][i] * A^T[b][j] going through the instruction descriptor's negate-A bit. 36 MMAs per stage instead of 24
+//     (half fold, 8 accumulators) or 16 (no fold, 16 accumulators) -- the MMA FLOPs of a direct convolution -- but
+//     only 4 accumulators: 4 x 96 couts = 384 TMEM columns + the two 64-column V halves = 512. A 96-wide slice means
+//     the raw tile is fetched and transformed 3 times per M-block for K = 256 (96 + 96 + 64) instead of 6 times
+//     (4 x 48 + 2 x 32): the kernel is bound by the transform warps and the TMA feed, not by the tensor core, so
+//     halving the transform passes wins even though the MMA work grows by 1.5x;
+//   * the epilogue has no arithmetic left but BN + ReLU: it drains the accumulators in chunks of (32 couts, output row a)
+//     through a [tile][2 pixels][32 couts] staging area and writes full 128-byte runs per output pixel; the two warps
+//     that own the same 32 TMEM lanes stage and write out their 32 tiles on their own (64-thread named barriers).
+//
+// Numerically this is still F(2x2,3x3): the operands of every product are the TF32-rounded V = B^T d B and
+// U = G g G^T; only the order of the fp32 additions differs from the un-folded form.
+#include "ptx.cuh"
+#include "wg_internal.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace wg {
+
+namespace ff {
+constexpr int kWorkerWarps = 8, kProducerWarp = 8, kMmaWarp = 9;
+constexpr int kRawRows = 48;                           // input rows (n*16+y) one 128-tile M-block can touch
+constexpr uint32_t kRawBytes = kRawRows * 2 * 8 * 32;  // [ny][x parity][x/2][8 ch] fp32 = 24576
+constexpr int kRawStages = 3, kUBufs = 4;
+constexpr int kKNmax = 96;
+constexpr uint32_t kAccStride = 96;                    // TMEM: accumulator (a,b) at column (2a+b)*96 ...
+constexpr uint32_t kVCol0 = 4 * kAccStride;            // ... V half jh at 384 + 64*jh, point (i, jj) at +8*(2i+jj)
+constexpr uint32_t kUChunkMax = 8 * 2 * kKNmax * 16;   // 8 points x [2 k-chunks][KN couts][16 B] = 24576
+constexpr int kEW = 32;                                // couts per epilogue chunk
+constexpr uint32_t kStgRow = 2 * kEW * 4 + 16;         // [2 px][32 couts] fp32 per tile, rows padded by 16 B
+constexpr uint32_t kStgBytes = 128 * kStgRow;
+constexpr uint32_t kOffRaw = 0;
+constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawBytes;
+constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
+constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
+constexpr uint32_t kOffBar = kOffPix + 128 * 4;
+constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kUBufs + 4 + 2;
+constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr uint32_t kTotal = kOffTmemPtr + 16;
+static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kTotal <= 227 * 1024, "shared memory budget");
+
+// cout slices: ceil(K/96) of them, widths in multiples of 32 as even as possible, wider ones first
+// (256 = 96 + 96 + 64, 128 = 64 + 64, 512 = 4 x 96 + 2 x 64).
+__host__ __device__ inline int n_slices(int K) { return (K + 95) / 96; }
+struct Slice { int kn, c0; };  // width and first cout
+__host__ __device__ inline Slice slice(int K, int s) {
+  const int ns = n_slices(K), units = K / 32, base = units / ns, rem = units % ns;
+  return Slice{32 * (base + (s < rem ? 1 : 0)), 32 * (s * base + (s < rem ? s : rem))};
+}
+__host__ __device__ inline int slice_of(int K, int k) {
+  const int ns = n_slices(K), units = K / 32, base = units / ns, rem = units % ns;
+  const int wide = rem * (base + 1) * 32;
+  return k < wide ? k / ((base + 1) * 32) : rem + (k - wide) / (base * 32);
+}
+}  // namespace ff
+
+__device__ __forceinline__ float ff_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
+template <bool H16>
+__device__ __forceinline__ void ff_umma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (H16) umma_f16_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+  else umma_tf32_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+}
+
+// two fp32 -> one 32-bit TMEM column of 16-bit operands (first value in the low half), round to nearest
+__device__ __forceinline__ float ff_pack16(float lo, float hi, int fp16) {
+  if (fp16) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+  }
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return __uint_as_float(*reinterpret_cast<const uint32_t*>(&b));
+}
+
+// H16: 16-bit operands (bf16, or fp16 with `fp16` set): V is stored in TMEM as packed pairs (column c = channels 2c
+// and 2c+1), tcgen05.mma kind::f16 with K = 16, so a V stage covers 16 channels = TWO 8-channel raw stages.
+template <bool H16>
+__global__ void __launch_bounds__(32 * (ff::kWorkerWarps + 2), 1)
+wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
+                  const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
+                  int C, int K, int relu, int out_padded, int mv, int fp16) {
+  using namespace ff;
+  constexpr int kSub = H16 ? 2 : 1;  // 8-channel raw stages per V stage
+  const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
+  out_padded &= 1;
+  pdl_launch_dependents();  // the next launch in the stream may start its prologue (it waits before touching x / y)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* raw_full = bars;
+  uint64_t* raw_empty = raw_full + kRawStages;
+  uint64_t* u_full = raw_empty + kRawStages;
+  uint64_t* u_empty = u_full + kUBufs;
+  uint64_t* v_full = u_empty + kUBufs;  // [half]
+  uint64_t* v_empty = v_full + 2;       // [half]
+  uint64_t* acc_full = v_empty + 2;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
+  int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < kRawStages; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], kWorkerWarps);
+    }
+    for (int i = 0; i < kUBufs; ++i) {
+      mbar_init(&u_full[i], 1);
+      mbar_init(&u_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], kWorkerWarps);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kWorkerWarps);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_kb = C / (8 * kSub);  // V stages (8 or 16 channels each)
+  const int n_sl = n_slices(K);
+  const int total_tiles = n_img * 49;
+  const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host
+  const int n_items = n_mblocks * n_sl;               // item = (M-block, cout slice); slices of an M-block are adjacent
+  const int item0 = blockIdx.x, item_step = gridDim.x;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t rs = 0, rph = 0, us = 0, uph = 0;
+      int u_primed = 0;
+      if (item0 < n_items) {
+        // the filter does not depend on the previous kernel in the stream: request the first stage's U chunks before
+        // waiting for that kernel (programmatic dependent launch), the activations after
+        const Slice sl = slice(K, item0 % n_sl);
+        const int kn = sl.kn, c0 = sl.c0;
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
+        for (int h = 0; h < 2; ++h) {
+          mbar_arrive_expect_tx(&u_full[us], 256u * kn);
+          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (size_t)h * 256 * kn, 256u * kn, &u_full[us]);
+          ++us;
+        }
+        u_primed = 1;
+      }
+      pdl_wait();
+      for (int item = item0; item < n_items; item += item_step) {
+        const Slice sl = slice(K, item % n_sl);
+        const int kn = sl.kn, c0 = sl.c0;
+        const int mb = item / n_sl;
+        const int t0 = mb * mv;
+        const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+#pragma unroll
+          for (int sb = 0; sb < kSub; ++sb) {
+            mbar_wait(&raw_empty[rs], rph ^ 1);
+            mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
+            tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawBytes, &tmap_x, (kb * kSub + sb) * 8, 0, 0, ny0, &raw_full[rs]);
+            if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          }
+          if (u_primed) {  // already requested above
+            u_primed = 0;
+            continue;
+          }
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&u_empty[us], uph ^ 1);
+            mbar_arrive_expect_tx(&u_full[us], 256u * kn);
+            tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)kb * 2 + h) * 256 * kn, 256u * kn,
+                         &u_full[us]);
+            if (++us == kUBufs) { us = 0; uph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    if (elect_one()) {
+      const uint32_t u_base = smem_u32(smem + kOffU);
+      uint32_t g = 0, us = 0, uph = 0, aph = 0;  // g = V stages issued (V phase = g & 1)
+      for (int item = item0; item < n_items; item += item_step) {
+        const uint32_t kn = (uint32_t)slice(K, item % n_sl).kn;
+        const uint32_t fmt = H16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
+        const uint32_t idesc_pos = make_idesc(fmt, 128, kn);
+        const uint32_t idesc_neg = make_idesc(fmt, 128, kn, 1);  // D += (-A) * B
+        const uint32_t u_per_point = 2 * kn * 16, u_lbo = kn * 16;
+        mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
+        tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb) {
+          // bit p set = accumulator p has been written in this item (first MMA into it overwrites)
+          uint32_t written = kb > 0 ? 0xFu : 0u;
+#pragma unroll
+          for (int jh = 0; jh < 2; ++jh) {
+            mbar_wait(&u_full[us], uph);  // there long before V: checked first, off the V -> MMA critical path
+            mbar_wait(&v_full[jh], g & 1);
+            tc_fence_after();
+            const uint32_t ua = u_base + us * kUChunkMax;
+            const uint32_t va = tmem_base + kVCol0 + jh * 64;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = jh * 2 + jj;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t a_tm = va + (i * 2 + jj) * 8;
+                const uint64_t b_desc = make_smem_desc(ua + (i * 2 + jj) * u_per_point, u_lbo, 128, kLayoutNone);
+                // A^T = [[1,1,1,0],[0,1,-1,-1]]: row a uses point index i with sign sa, column b uses j with sign sb
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                  if ((a == 0 && i == 3) || (a == 1 && i == 0)) continue;
+                  const int sa = (a == 1 && i >= 2) ? -1 : 1;
+#pragma unroll
+                  for (int b = 0; b < 2; ++b) {
+                    if ((b == 0 && j == 3) || (b == 1 && j == 0)) continue;
+                    const int sb = (b == 1 && j >= 2) ? -1 : 1;
+                    const uint32_t p = (uint32_t)(2 * a + b);
+                    ff_umma<H16>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
+                                 (written >> p) & 1u);
+                    written |= 1u << p;
+                  }
+                }
+              }
+            }
+            umma_commit(&u_empty[us]);
+            umma_commit(&v_empty[jh]);  // this V half may be overwritten
+            if (++us == kUBufs) { us = 0; uph ^= 1; }
+          }
+          ++g;
+        }
+        umma_commit(acc_full);
+        aph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ transform + epilogue warps
+    // thread = (MMA row = TMEM lane, channel half cq): warp w owns TMEM lanes 32*(w&3)..+31
+    const int quad = warp & 3;
+    const int cq = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t raw_base = smem_u32(smem + kOffRaw);
+    const uint32_t stg_base = smem_u32(smem + kOffStg);
+
+    uint32_t rs = 0, rph = 0, g = 0, aph = 0;  // g = V stages transformed (same counting as the MMA thread)
+    for (int item = item0; item < n_items; item += item_step) {
+      const Slice sl = slice(K, item % n_sl);
+      const int kn = sl.kn, c0s = sl.c0;
+      const int mb = item / n_sl;
+      const int t0 = mb * mv;
+      const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+      const int T = t0 + row;
+      const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
+      const bool tvalid = row < valid_rows;
+      const bool warp_active = quad * 32 < valid_rows;  // warp-uniform
+      const int n = T / 49, t = T % 49, ty = t / 7, tx = t % 7;
+      const uint32_t raw_off = tvalid ? (uint32_t)((n * 16 + 2 * ty - ny0) * 512 + tx * 32) : 0u;
+      // SWIZZLE_32B: the 16-byte half of a pixel's 32 bytes is XORed with bit 2 of its x/2 index (address bit 7)
+      const uint32_t h0 = (uint32_t)((cq ^ ((tx >> 2) & 1)) * 16);        // pixels with x/2 = tx
+      const uint32_t h1 = (uint32_t)((cq ^ (((tx + 1) >> 2) & 1)) * 16);  // pixels with x/2 = tx + 1
+
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const uint32_t vph = g & 1;
+        if (!warp_active) {
+          // nothing to transform: release the raw stage(s) and report "V ready" in step with the other warps
+#pragma unroll
+          for (int sb = 0; sb < kSub; ++sb) {
+            mbar_wait(&raw_full[rs], rph);
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);
+            if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          }
+#pragma unroll
+          for (int jh = 0; jh < 2; ++jh) {
+            mbar_wait(&v_empty[jh], vph ^ 1);
+            if (lane == 0) mbar_arrive(&v_full[jh]);
+          }
+          ++g;
+          continue;
+        }
+#pragma unroll
+        for (int sb = 0; sb < kSub; ++sb) {  // H16: two 8-channel raw stages fill one 16-channel V stage
+          mbar_wait(&raw_full[rs], rph);
+          float d[4][4][4];
+          if (tvalid) {
+            const uint32_t a = raw_base + rs * kRawBytes + raw_off;
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 4; ++dx) {
+                const uint32_t ad = a + dy * 512 + (dx & 1) * 256 + (dx >> 1) * 32 + ((dx >> 1) ? h1 : h0);
+                const float4 v = ld_shared_v4(ad);
+                d[dy][dx][0] = v.x, d[dy][dx][1] = v.y, d[dy][dx][2] = v.z, d[dy][dx][3] = v.w;
+              }
+          } else {
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d[dy][dx][c] = 0.f;
+          }
+          // column pass t = B^T d, in place over dy
+#pragma unroll
+          for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float d0 = d[0][dx][c], d1 = d[1][dx][c], d2 = d[2][dx][c], d3 = d[3][dx][c];
+              d[0][dx][c] = d0 - d2;
+              d[1][dx][c] = d1 + d2;
+              d[2][dx][c] = d2 - d1;
+              d[3][dx][c] = d1 - d3;
+            }
+          // the raw stage is in registers now: hand it back to the producer before the row pass
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&raw_empty[rs]);
+          if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+
+          // row pass V = t B by halves (half jh = points with j in {2jh, 2jh+1}), round to the operand type, store into
+          // TMEM (tf32: one column per channel; 16-bit: one column per channel pair, raw stage sb fills columns 4*sb..)
+          const uint32_t vcol = tmem_base + lane_base + kVCol0 + (uint32_t)(H16 ? sb * 4 + cq * 2 : cq * 4);
+#pragma unroll
+          for (int jh = 0; jh < 2; ++jh) {
+            if (sb == 0) {
+              mbar_wait(&v_empty[jh], vph ^ 1);  // the MMAs that last read this V half have completed
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float v0[4], v1[4];  // points (i, 2jh) and (i, 2jh+1)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float a0 = d[i][0][c], a1 = d[i][1][c], a2 = d[i][2][c], a3 = d[i][3][c];
+                v0[c] = jh == 0 ? a0 - a2 : a2 - a1;
+                v1[c] = jh == 0 ? a1 + a2 : a1 - a3;
+                if constexpr (!H16) v0[c] = ff_tf32(v0[c]), v1[c] = ff_tf32(v1[c]);
+              }
+              const uint32_t dst = vcol + jh * 64 + (i * 2) * 8;
+              if constexpr (H16) {
+                tmem_st_x2(dst, ff_pack16(v0[0], v0[1], fp16), ff_pack16(v0[2], v0[3], fp16));
+                tmem_st_x2(dst + 8, ff_pack16(v1[0], v1[1], fp16), ff_pack16(v1[2], v1[3], fp16));
+              } else {
+                tmem_st_x4(dst, v0[0], v0[1], v0[2], v0[3]);
+                tmem_st_x4(dst + 8, v1[0], v1[1], v1[2], v1[3]);
+              }
+            }
+            if (sb == kSub - 1) {
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&v_full[jh]);
+            }
+          }
+        }  // sb
+        ++g;
+      }
+
+      // ---- epilogue: the accumulators ARE the output pixels; BN, ReLU, staged per (32 couts, output row a), full runs
+      // per pixel. Warps (quad, cq = 0/1) own the same 32 tiles: they share staging rows 32*quad..+31 and barrier 1+quad.
+      const int W = out_padded ? 16 : 14;
+      const int o = out_padded ? 1 : 0;
+      const int pix0 = tvalid ? ((n * W + 2 * ty + o) * W + 2 * tx + o) : -1;  // first output pixel of this tile
+      if (cq == 0) pixtab[row] = pix0;
+      const int n_chunks = kn / kEW;
+      const int qrows = min(32, valid_rows - quad * 32);  // real tiles among this quad's rows (<= 0: none)
+      const int tid64 = cq * 32 + lane;
+
+      mbar_wait(acc_full, aph);
+      aph ^= 1;
+      tc_fence_after();
+      if (warp_active) {
+#pragma unroll 1
+        for (int ec = 0; ec < n_chunks; ++ec) {
+          float sc[16], sh[16];  // this thread's 16 couts of the chunk
+          const int cl = cq * 16;           // cout inside the chunk
+          const int c0 = ec * kEW + cl;     // cout inside the slice
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c0s + c0 + 4 * q4));
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(shift + c0s + c0 + 4 * q4));
+            sc[4 * q4] = s4.x, sc[4 * q4 + 1] = s4.y, sc[4 * q4 + 2] = s4.z, sc[4 * q4 + 3] = s4.w;
+            sh[4 * q4] = h4.x, sh[4 * q4 + 1] = h4.y, sh[4 * q4 + 2] = h4.z, sh[4 * q4 + 3] = h4.w;
+          }
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * kAccStride + (uint32_t)c0;
+            float z[2][16];  // z[b][e] = Y[a][b]
+            tmem_ld_x16(taddr, z[0]);
+            tmem_ld_x16(taddr + kAccStride, z[1]);
+            tmem_ld_wait();
+            if (ec == n_chunks - 1 && a == 1) {  // this warp has read its last accumulator columns
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_empty);
+            }
+            const uint32_t sdst = stg_base + (uint32_t)row * kStgRow + (uint32_t)cl * 4;
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                float ov[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  ov[e] = fmaf(sc[4 * q4 + e], z[b][4 * q4 + e], sh[4 * q4 + e]);
+                  if (relu) ov[e] = fmaxf(ov[e], 0.f);
+                }
+                st_shared_v4(sdst + b * (4 * kEW) + 16 * q4, ov[0], ov[1], ov[2], ov[3]);
+              }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // this quad's staging rows (+ pixtab) complete
+            {
+              const int units = qrows * 16;  // (tile, pixel b, 16-byte chunk)
+              float* ybase = y + c0s + ec * kEW + (size_t)a * W * K;
+              for (int u = tid64; u < units; u += 64) {
+                const int tile = quad * 32 + (u >> 4);
+                const int b = (u >> 3) & 1;
+                const int ch = u & 7;
+                const float4 v = ld_shared_v4(stg_base + (uint32_t)tile * kStgRow + (uint32_t)(b * 128 + ch * 16));
+                st_out_v4(ybase + (size_t)(pixtab[tile] + b) * K + ch * 4, v, mc);
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // staging rows free again
+          }
+        }
+        if (out_padded && tvalid && (ty == 0 || ty == 6 || tx == 0 || tx == 6)) {
+          // zero border of the reference's 16x16 frame (Kernel128_winograd.cu:163,243): edge tiles own their share
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const size_t rstride = (size_t)W * K;
+          const int ncc = kn / 2;
+          float* p = y + (size_t)pix0 * K + c0s + cq * ncc;
+          const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
+          const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
+#pragma unroll 1
+          for (int e = 0; e < ncc; e += 4) {
+            if (dyb != 0) {
+              st_out_v4(p + dyb + e, z4, mc);
+              st_out_v4(p + dyb + K + e, z4, mc);
+            }
+            if (dxb != 0) {
+              st_out_v4(p + dxb + e, z4, mc);
+              st_out_v4(p + dxb + rstride + e, z4, mc);
+            }
+            if (dyb != 0 && dxb != 0) st_out_v4(p + dyb + dxb + e, z4, mc);
+          }
+        }
+      } else {
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Once per layer: U = G g G^T (F(2x2,3x3)), RN-rounded to the operand type, in the shared-memory image of this kernel's
+// bulk copies: per cout slice (ff::slice) [C/8 k-block][2 j-halves][4 i][2 jj][2 k-chunks][KN couts][4 channels]
+// (j = 2*jh + jj). 512 bytes per (k-block, cout), so slice s starts at byte (C/8)*512*c0(s).
+// Replaces the offline weight_generator loop (/root/reference/data_generator.py:63-78; that one is F(4x4), 36 points).
+// op16 = 1 (bf16) / 2 (fp16): 16-channel k-blocks, 8 channels per 16-byte chunk, same 512 bytes per (k-block, cout).
+__global__ void filter_transform_ff_kernel(const float* __restrict__ w_kcrs, float* __restrict__ u_img, int C, int K,
+                                           int op16) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * K) return;
+  const int ch = idx % C;
+  const int k = idx / C;
+  const float* g = w_kcrs + ((size_t)k * C + ch) * 9;
+  float gg[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) gg[r][s] = g[r * 3 + s];
+  float tt[4][3];  // t = G g
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    tt[0][s] = gg[0][s];
+    tt[1][s] = 0.5f * (gg[0][s] + gg[1][s] + gg[2][s]);
+    tt[2][s] = 0.5f * (gg[0][s] - gg[1][s] + gg[2][s]);
+    tt[3][s] = gg[2][s];
+  }
+  const ff::Slice sl = ff::slice(K, ff::slice_of(K, k));
+  const int kn = sl.kn, c0 = sl.c0;
+  const int kl = k - c0;
+  const int kb = ch / 8, chunk = (ch % 8) / 4, e = ch % 4;
+  const size_t base = (size_t)(C / 8) * 128 * c0 + (size_t)kb * 128 * kn;  // floats
+  // 16-bit image, in 2-byte elements: 256 per (16-channel block, cout)
+  const int kb16 = ch / 16, chunk16 = (ch % 16) / 8, e16 = ch % 8;
+  const size_t base16 = (size_t)(C / 16) * 256 * c0 + (size_t)kb16 * 256 * kn;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float u[4];
+    u[0] = tt[i][0];
+    u[1] = 0.5f * (tt[i][0] + tt[i][1] + tt[i][2]);
+    u[2] = 0.5f * (tt[i][0] - tt[i][1] + tt[i][2]);
+    u[3] = tt[i][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = (j >> 1) * 8 + i * 2 + (j & 1);
+      const size_t o16 = base16 + (size_t)p * (2 * kn * 8) + ((size_t)chunk16 * kn + kl) * 8 + e16;
+      if (op16 == 2) reinterpret_cast<__half*>(u_img)[o16] = __float2half_rn(u[j]);
+      else if (op16 == 1) reinterpret_cast<__nv_bfloat16*>(u_img)[o16] = __float2bfloat16_rn(u[j]);
+      else u_img[base + (size_t)p * (2 * kn * 4) + ((size_t)chunk * kn + kl) * 4 + e] = to_tf32_rn(u[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+
+int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, cudaStream_t stream) {
+  const int n = C * K;
+  filter_transform_ff_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, op16);
+  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+template <bool H16>
+static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                     int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream, int fp16) {
+  static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
+  if (!(configured & dev_bit_)) {
+    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
+        cudaSuccess)
+      return WG_ERR_CUDA;
+    configured |= dev_bit_;
+  }
+  const int n_sl = ff::n_slices(K);
+  const int total_tiles = n_img * 49;
+  // Tiles per M-block: the MMA is always M=128 but only `mv` rows carry tiles; transform warps own 32 rows each, so
+  // the per-item cost scales with ceil(mv/32) quarters. Pick the mv that minimises waves x cost (WG_WINO_MV pins it).
+  int mv = 128;
+  static int mv_env = -1;
+  if (mv_env < 0) {
+    const char* e = getenv("WG_WINO_MV");
+    mv_env = e ? atoi(e) : 0;
+  }
+  if (mv_env >= 16 && mv_env <= 128) {
+    mv = mv_env;
+  } else {
+    double best = 1e30;
+    for (int cand = 128; cand >= 64; cand -= 32) {
+      const long long items = (long long)((total_tiles + cand - 1) / cand) * n_sl;
+      const long long slots = max_ctas > 0 ? max_ctas : 1;
+      const long long waves = (items + slots - 1) / slots;
+      const double cost = (double)waves * (0.35 + 0.65 * cand / 128.0);
+      if (cost < best - 1e-9) {
+        best = cost;
+        mv = cand;
+      }
+    }
+  }
+  const int n_items = ((total_tiles + mv - 1) / mv) * n_sl;
+  int grid = max_ctas;
+  if (grid > n_items) grid = n_items;
+  if (grid < 1) grid = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(32 * (ff::kWorkerWarps + 2));
+  cfg.dynamicSmemBytes = ff::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ff_kernel<H16>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
+                                     out_padded, mv, fp16);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+int wino_ff_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                   int n_img, int C, int K, int op16, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+  // op16: 0 = TF32 operands, 1 = bf16, 2 = fp16 (V packed in TMEM, 16-channel stages)
+  if (op16)
+    return launch_ff<true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, op16 == 2);
+  return launch_ff<false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, 0);
+}
+
+}  // namespace wg

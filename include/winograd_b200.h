@@ -91,8 +91,10 @@ void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean,
                 float* scale_out, float* shift_out);
 
 /* Tuning knobs (process-wide; for benchmarking): max CTAs per launch (default = #SMs); 3x3 TF32 kernel variant for
- * layers created afterwards: 48 = transformed input kept in tensor memory, cout slices of 48/32 (default); 64 / 32 = the
- * earlier kernels with both MMA operands in shared memory (folded accumulation / one accumulator per Winograd point). */
+ * layers created afterwards: 96 = transformed input kept in tensor memory, whole inverse transform folded into the MMAs,
+ * cout slices of 96/64 (default); 48 = same with half of the inverse transform folded, slices of 48/32; 64 / 32 = the
+ * earlier kernels with both MMA operands in shared memory (half fold / one accumulator per Winograd point).
+ * The environment variable WG_WINO_KN sets the initial value. */
 void wg_set_max_ctas(int max_ctas);
 void wg_set_wino_kn(int kn);
 
