@@ -186,6 +186,14 @@ __device__ __forceinline__ void tma_tensor_4d_g2s(void* dst_smem, const void* tm
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_tensor_5d_g2s(void* dst_smem, const void* tmap, int c0, int c1, int c2, int c3, int c4,
+                                                  uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+      "%5, %6}], [%7];" ::"r"(smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
 // Tiled tensor store shared -> global (SASS: UTMASTG), bulk-group completion.
 __device__ __forceinline__ void tma_tensor_2d_s2g(const void* tmap, const void* src_smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),

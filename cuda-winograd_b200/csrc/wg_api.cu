@@ -267,7 +267,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
     const long long items64 = (long long)((N * 49 + 63) / 64) * (L->cout / 64);
     if (items64 * 4 > max_ctas) {
       if (L->tmap_tm_x != x || L->tmap_tm_n != N) {
-        int rc = wino_tm_make_tmap(&L->tmap_tm, x, N, L->cin, 1);
+        int rc = L->tm16_ff ? wino_ff_make_tmap(&L->tmap_tm, x, N, L->cin) : wino_tm_make_tmap(&L->tmap_tm, x, N, L->cin, 1);
         if (rc != WG_OK) return rc;
         L->tmap_tm_x = x;
         L->tmap_tm_n = N;
@@ -284,7 +284,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   }
   if (L->tmap_x != x || L->tmap_n != N) {
     int rc = L->kind == 1 ? one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin)
-             : L->tile_n == 96 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin, 1)
+             : L->tile_n == 96 ? wino_ff_make_tmap(&L->tmap, x, N, L->cin)
              : L->tile_n == 48 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin, wino_tm_cls(L->cout, L->tm_db))
                                : wino_make_tmap(&L->tmap, x, N, L->cin);
     if (rc != WG_OK) return rc;

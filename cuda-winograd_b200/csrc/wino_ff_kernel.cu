@@ -34,6 +34,15 @@ namespace ff {
 constexpr int kWorkerWarps = 8, kProducerWarp = 8, kMmaWarp = 9;
 constexpr int kRawRows = 48;                           // input rows (n*16+y) one 128-tile M-block can touch
 constexpr uint32_t kRawBytes = kRawRows * 2 * 8 * 32;  // [ny][x parity][x/2][8 ch] fp32 = 24576
+// P9 raw layout (conflict-free patch loads): four planes (y parity, x parity), each [24 row pairs][9 slots][8 ch] fp32
+// with slot = x/2 + 1 (slot 0 = the out-of-bounds column x/2 = -1, zero-filled, never read). The row pitch of 9 slots
+// puts the 32-byte slot of tile (ty, tx) at 9*(ty + dy/2) + tx + dx/2 + 1: with the tiles of an M-block numbered
+// right-to-left inside each tile row, consecutive tiles sit in consecutive slots modulo 8 -- also across the end of a
+// tile row -- so the 8 lanes of a quarter warp (16 bytes each, half selected by the 32-byte swizzle) hit 8 different
+// bank groups. (Only a quarter warp that straddles two IMAGES still pays a second wavefront.)
+constexpr uint32_t kPlaneBytes = 24 * 9 * 32;          // 6912 = 27 * 256
+constexpr uint32_t kRawBytesP9 = 4 * kPlaneBytes;      // 27648
+constexpr uint32_t kRawStride = kRawBytesP9;           // stage pitch of both layouts
 constexpr int kRawStages = 3, kUBufs = 4;
 constexpr int kKNmax = 96;
 constexpr uint32_t kAccStride = 96;                    // TMEM: accumulator (a,b) at column (2a+b)*96 ...
@@ -43,7 +52,7 @@ constexpr int kEW = 32;                                // couts per epilogue chu
 constexpr uint32_t kStgRow = 2 * kEW * 4 + 16;         // [2 px][32 couts] fp32 per tile, rows padded by 16 B
 constexpr uint32_t kStgBytes = 128 * kStgRow;
 constexpr uint32_t kOffRaw = 0;
-constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawBytes;
+constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawStride;
 constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
 constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
 constexpr uint32_t kOffBar = kOffPix + 128 * 4;
@@ -89,12 +98,17 @@ __device__ __forceinline__ float ff_pack16(float lo, float hi, int fp16) {
 
 // H16: 16-bit operands (bf16, or fp16 with `fp16` set): V is stored in TMEM as packed pairs (column c = channels 2c
 // and 2c+1), tcgen05.mma kind::f16 with K = 16, so a V stage covers 16 channels = TWO 8-channel raw stages.
-template <bool H16>
+// DBG: developer build with ablation switches (WG_FF_DEBUG=<bits>: 1 no MMAs, 2 no patch loads / transform / TMEM
+// stores, 4 no filter loads, 8 no raw-tile loads, 16 no output stores); results are garbage, only the time is of interest.
+// The product instantiation (DBG = false) contains none of it.
+template <bool H16, bool DBG, bool P9>
 __global__ void __launch_bounds__(32 * (ff::kWorkerWarps + 2), 1)
 wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
-                  int C, int K, int relu, int out_padded, int mv, int fp16) {
+                  int C, int K, int relu, int out_padded, int mv, int fp16, int dbg) {
   using namespace ff;
+  const bool no_mma = DBG && (dbg & 1), no_xf = DBG && (dbg & 2), no_u = DBG && (dbg & 4), no_raw = DBG && (dbg & 8),
+             no_out = DBG && (dbg & 16);
   constexpr int kSub = H16 ? 2 : 1;  // 8-channel raw stages per V stage
   const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
   out_padded &= 1;
@@ -176,8 +190,19 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 #pragma unroll
           for (int sb = 0; sb < kSub; ++sb) {
             mbar_wait(&raw_empty[rs], rph ^ 1);
-            mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
-            tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawBytes, &tmap_x, (kb * kSub + sb) * 8, 0, 0, ny0, &raw_full[rs]);
+            if (no_raw) {
+              mbar_arrive(&raw_full[rs]);
+            } else if constexpr (P9) {
+              mbar_arrive_expect_tx(&raw_full[rs], kRawBytesP9);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)  // plane q = (y parity q>>1, x parity q&1); x/2 starts at -1 (zero-filled)
+                tma_tensor_5d_g2s(smem + kOffRaw + rs * kRawStride + q * kPlaneBytes, &tmap_x, (kb * kSub + sb) * 8, -1,
+                                  q & 1, q >> 1, ny0 >> 1, &raw_full[rs]);
+            } else {
+              mbar_arrive_expect_tx(&raw_full[rs], kRawBytes);
+              tma_tensor_4d_g2s(smem + kOffRaw + rs * kRawStride, &tmap_x, (kb * kSub + sb) * 8, 0, 0, ny0,
+                                &raw_full[rs]);
+            }
             if (++rs == kRawStages) { rs = 0; rph ^= 1; }
           }
           if (u_primed) {  // already requested above
@@ -186,9 +211,13 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
           for (int h = 0; h < 2; ++h) {
             mbar_wait(&u_empty[us], uph ^ 1);
-            mbar_arrive_expect_tx(&u_full[us], 256u * kn);
-            tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)kb * 2 + h) * 256 * kn, 256u * kn,
-                         &u_full[us]);
+            if (no_u) {
+              mbar_arrive(&u_full[us]);
+            } else {
+              mbar_arrive_expect_tx(&u_full[us], 256u * kn);
+              tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)kb * 2 + h) * 256 * kn, 256u * kn,
+                           &u_full[us]);
+            }
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
         }
@@ -234,8 +263,9 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                     if ((b == 0 && j == 3) || (b == 1 && j == 0)) continue;
                     const int sb = (b == 1 && j >= 2) ? -1 : 1;
                     const uint32_t p = (uint32_t)(2 * a + b);
-                    ff_umma<H16>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
-                                 (written >> p) & 1u);
+                    if (!no_mma)
+                      ff_umma<H16>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
+                                   (written >> p) & 1u);
                     written |= 1u << p;
                   }
                 }
@@ -272,11 +302,24 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
       const bool tvalid = row < valid_rows;
       const bool warp_active = quad * 32 < valid_rows;  // warp-uniform
-      const int n = T / 49, t = T % 49, ty = t / 7, tx = t % 7;
+      const int n = T / 49, t = T % 49, ty = t / 7;
+      const int tx = P9 ? 6 - t % 7 : t % 7;  // P9: tiles run right-to-left inside a tile row (see kPlaneBytes)
       const uint32_t raw_off = tvalid ? (uint32_t)((n * 16 + 2 * ty - ny0) * 512 + tx * 32) : 0u;
       // SWIZZLE_32B: the 16-byte half of a pixel's 32 bytes is XORed with bit 2 of its x/2 index (address bit 7)
       const uint32_t h0 = (uint32_t)((cq ^ ((tx >> 2) & 1)) * 16);        // pixels with x/2 = tx
       const uint32_t h1 = (uint32_t)((cq ^ (((tx + 1) >> 2) & 1)) * 16);  // pixels with x/2 = tx + 1
+      // P9: byte offset inside a plane of the pixel (dy/2, dx/2) of this tile's patch, swizzled half included
+      uint32_t p9off[2][2];
+      if constexpr (P9) {
+        const uint32_t s0 = tvalid ? (uint32_t)(((n * 16 + 2 * ty - ny0) >> 1) * 9 + tx + 1) : 1u;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const uint32_t sl = s0 + 9 * a + b;
+            p9off[a][b] = sl * 32 + (uint32_t)((cq ^ ((sl >> 2) & 1)) * 16);
+          }
+      }
 
       for (int kb = 0; kb < n_kb; ++kb) {
         const uint32_t vph = g & 1;
@@ -300,13 +343,27 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         for (int sb = 0; sb < kSub; ++sb) {  // H16: two 8-channel raw stages fill one 16-channel V stage
           mbar_wait(&raw_full[rs], rph);
           float d[4][4][4];
+          if (no_xf) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);
+            if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+            if (sb == kSub - 1) {
+#pragma unroll
+              for (int jh = 0; jh < 2; ++jh) {
+                mbar_wait(&v_empty[jh], vph ^ 1);
+                if (lane == 0) mbar_arrive(&v_full[jh]);
+              }
+            }
+            continue;
+          }
           if (tvalid) {
-            const uint32_t a = raw_base + rs * kRawBytes + raw_off;
+            const uint32_t a = raw_base + rs * kRawStride + (P9 ? 0u : raw_off);
 #pragma unroll
             for (int dy = 0; dy < 4; ++dy)
 #pragma unroll
               for (int dx = 0; dx < 4; ++dx) {
-                const uint32_t ad = a + dy * 512 + (dx & 1) * 256 + (dx >> 1) * 32 + ((dx >> 1) ? h1 : h0);
+                const uint32_t ad = P9 ? a + ((dy & 1) * 2 + (dx & 1)) * kPlaneBytes + p9off[dy >> 1][dx >> 1]
+                                       : a + dy * 512 + (dx & 1) * 256 + (dx >> 1) * 32 + ((dx >> 1) ? h1 : h0);
                 const float4 v = ld_shared_v4(ad);
                 d[dy][dx][0] = v.x, d[dy][dx][1] = v.y, d[dy][dx][2] = v.z, d[dy][dx][3] = v.w;
               }
@@ -433,7 +490,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                 const int b = (u >> 3) & 1;
                 const int ch = u & 7;
                 const float4 v = ld_shared_v4(stg_base + (uint32_t)tile * kStgRow + (uint32_t)(b * 128 + ch * 16));
-                st_out_v4(ybase + (size_t)(pixtab[tile] + b) * K + ch * 4, v, mc);
+                if (!no_out) st_out_v4(ybase + (size_t)(pixtab[tile] + b) * K + ch * 4, v, mc);
               }
             }
             asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // staging rows free again
@@ -526,21 +583,49 @@ __global__ void filter_transform_ff_kernel(const float* __restrict__ w_kcrs, flo
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 
+// Raw-tile layout: 1 (default) = four parity planes with a 9-slot row pitch, conflict-free patch loads (kPlaneBytes);
+// 0 = the TM kernel's single box with an 8-slot pitch (WG_FF_P9=0; A/B measurements).
+int wino_ff_p9() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WG_FF_P9");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v;
+}
+
+int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
+  if (!wino_ff_p9()) return wino_tm_make_tmap(tmap, x, n_img, C, 1);
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return WG_ERR_DRIVER;
+  // x[N][16][16][C] viewed as (c, x/2, x&1, y&1, (n*16+y)/2); a box is one parity plane: 8 channels x 9 column pairs
+  // (starting at x/2 = -1) x 24 row pairs, 32-byte swizzle
+  cuuint64_t dims[5] = {(cuuint64_t)C, 8, 2, 2, (cuuint64_t)n_img * 8};
+  cuuint64_t strides[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)C * 4, (cuuint64_t)16 * C * 4, (cuuint64_t)32 * C * 4};
+  cuuint32_t box[5] = {8, 9, 1, 1, 24};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, wg::l2_promotion(),
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
+}
+
 int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, cudaStream_t stream) {
   const int n = C * K;
   filter_transform_ff_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, op16);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-template <bool H16>
+template <bool H16, bool DBG, bool P9>
 static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                     int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream, int fp16) {
+                     int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream, int fp16,
+                     int dbg) {
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
+    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16, DBG, P9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
         cudaSuccess)
       return WG_ERR_CUDA;
     configured |= dev_bit_;
@@ -588,17 +673,38 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ff_kernel<H16>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
-                                     out_padded, mv, fp16);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ff_kernel<H16, DBG, P9>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
+                                     out_padded, mv, fp16, dbg);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_ff_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                    int n_img, int C, int K, int op16, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
   // op16: 0 = TF32 operands, 1 = bf16, 2 = fp16 (V packed in TMEM, 16-channel stages)
-  if (op16)
-    return launch_ff<true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, op16 == 2);
-  return launch_ff<false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, 0);
+  static int dbg = -1;  // WG_FF_DEBUG: ablation switches of the developer build (see the kernel)
+  if (dbg < 0) {
+    const char* e = getenv("WG_FF_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  const int fp16 = op16 == 2;
+#define WG_FF(H16_, DBG_, P9_)                                                                                        \
+  return launch_ff<H16_, DBG_, P9_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, fp16, \
+                                    dbg)
+  if (wino_ff_p9()) {
+    if (dbg > 0) {
+      if (op16) WG_FF(true, true, true);
+      WG_FF(false, true, true);
+    }
+    if (op16) WG_FF(true, false, true);
+    WG_FF(false, false, true);
+  }
+  if (dbg > 0) {
+    if (op16) WG_FF(true, true, false);
+    WG_FF(false, true, false);
+  }
+  if (op16) WG_FF(true, false, false);
+  WG_FF(false, false, false);
+#undef WG_FF
 }
 
 }  // namespace wg

@@ -703,6 +703,76 @@ static void run_ts_probe() {
          e1, e2, (e1 == 0 && e2 == 0) ? "MATCH" : "mismatch", clk[0], clk[1], clk[1] / 96.0);
 }
 
+
+// ------------------------------------------------------------------------------------------------ A-from-TMEM MMA rate
+// Issue -> complete rate of `count` back-to-back tcgen05.mma with A in TMEM (M=128, K=8 tf32 or K=16 bf16) for a range of
+// N, rotating over as many accumulators as fit next to the A columns, B = 16 distinct K-major no-swizzle operands in
+// shared memory ([2 k-chunks][N][16 B] each), as the full-fold 3x3 kernel issues them.
+template <int N, bool H16>
+__global__ void umma_ts_rate_kernel(long long* clk, int count) {
+  using namespace wg;
+  extern __shared__ __align__(1024) uint8_t sb[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16 * 2 * N * 4; i += blockDim.x) reinterpret_cast<float*>(sb)[i] = 0.f;
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc<512>(&tptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tptr;
+  const uint32_t a_col = 448;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  for (int c = 0; c < 64; c += 4) tmem_st_x4(tb + lane_base + a_col + c, 0.f, 0.f, 0.f, 0.f);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  constexpr int kAcc = (448 / N) < 4 ? (448 / N) : 4;
+  if (tid < 32) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(H16 ? kFmtBF16 : kFmtTF32, 128, N);
+      const long long t0 = clock64();
+      for (int i = 0; i < count; ++i) {
+        const uint64_t bd = make_smem_desc(smem_u32(sb) + (i & 15) * (2 * N * 16), N * 16, 128, kLayoutNone);
+        if constexpr (H16) umma_f16_ts(tb + (i % kAcc) * N, tb + a_col + (i & 7) * 8, bd, idesc, 1u);
+        else umma_tf32_ts(tb + (i % kAcc) * N, tb + a_col + (i & 7) * 8, bd, idesc, 1u);
+      }
+      const long long t1 = clock64();
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      clk[0] = t1 - t0;
+      clk[1] = clock64() - t0;
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<512>(tb);
+}
+
+template <int N, bool H16>
+static void time_ts_rate(int count) {
+  long long* dc;
+  CK(cudaMalloc(&dc, 16));
+  const int smem = 16 * 2 * N * 16;
+  CK(cudaFuncSetAttribute(umma_ts_rate_kernel<N, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int rep = 0; rep < 2; ++rep) {
+    umma_ts_rate_kernel<N, H16><<<1, 128, smem>>>(dc, count);
+    CK(cudaDeviceSynchronize());
+  }
+  long long clk[2];
+  CK(cudaMemcpy(clk, dc, 16, cudaMemcpyDeviceToHost));
+  printf("TS rate M=128 N=%3d K=%2d %s x%3d: issue %5lld clk, issue->complete %5lld clk = %.1f clk/MMA (tensor floor %.1f)\n",
+         N, H16 ? 16 : 8, H16 ? "bf16" : "tf32", count, clk[0], clk[1], (double)clk[1] / count, 128.0 * N * 8 / 2048.0 / 8);
+  cudaFree(dc);
+}
+
 // ------------------------------------------------------------------------------------------------ launch floor
 // What an N=1 layer cannot go below: empty kernels launched back to back the way the product launches its own
 // (dynamic smem opt-in, 128-byte __grid_constant__ parameter, optional cluster), timed with the same event loop.
@@ -799,6 +869,21 @@ int main(int argc, char** argv) {
     run_ts16_probe();
     return 0;
   }
+  if (argc > 1 && !strcmp(argv[1], "tsrate")) {
+    time_ts_rate<32, false>(144);
+    time_ts_rate<48, false>(144);
+    time_ts_rate<64, false>(144);
+    time_ts_rate<96, false>(144);
+    time_ts_rate<128, false>(144);
+    time_ts_rate<192, false>(144);
+    time_ts_rate<256, false>(144);
+    time_ts_rate<48, true>(144);
+    time_ts_rate<64, true>(144);
+    time_ts_rate<96, true>(144);
+    time_ts_rate<128, true>(144);
+    time_ts_rate<256, true>(144);
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "mma")) {
     for (int count : {1, 16, 96}) {
       time_mma<64, 32, 0>(count, 32, 1);
@@ -890,7 +975,7 @@ int main(int argc, char** argv) {
       time_layer(0, 256, 256, 256, 1);
     }
   }
-  wg_set_wino_kn(48);
+  wg_set_wino_kn(96);
   g_dtype = WG_BF16;
   printf("-- 3x3 bf16 operand variant (tolerance 1e-2)\n");
   bad(check3x3(1, 128, 128, 1, 1, {0}), 1e-2);
