@@ -244,7 +244,7 @@ def run_gpu(args):
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": tflops / tf32_peak, "traffic": traffic,
-                         "kernel": "wino3x3_tm_kernel (V in TMEM, 48-wide cout slices)",
+                         "kernel": "wino3x3_ff_kernel (V in TMEM, inverse transform folded into the MMAs, 96-wide cout slices)",
                          "algorithmic": "direct-conv-equivalent 2*196*256*256*9 = 231.21 MFLOP/image x 256 images/launch",
                          "peak_note": "dense TF32 = half of the measured sustained bf16 cuBLAS rate in " + pk["source"],
                          "hbm": {"achieved_gbs": (BYTES_PER_IMAGE * n + WEIGHT_BYTES) / (ms_per_step * 1e-3) / 1e9,

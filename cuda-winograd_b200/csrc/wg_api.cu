@@ -273,7 +273,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
         L->tmap_tm_n = N;
       }
       const int op16 = L->dtype == WG_FP16 ? 2 : 1;
-      int rc = L->tm16_ff ? wino_ff_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
+      int rc = L->tm16_ff ? wino_ff_launch(L->tmap_tm, x, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
                                            op16, L->relu, out_flags, max_ctas, stream)
                           : wino_tm_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
                                            0, op16, L->relu, out_flags, max_ctas, stream);
@@ -299,7 +299,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   }
   int rc;
   if (L->kind == 0 && L->tile_n == 96)
-    rc = wino_ff_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, L->relu, out_flags,
+    rc = wino_ff_launch(L->tmap, x, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, L->relu, out_flags,
                         max_ctas, stream);
   else if (L->kind == 0 && L->tile_n == 48)
     rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, 0, L->relu,

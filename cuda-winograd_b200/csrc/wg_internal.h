@@ -42,8 +42,9 @@ int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* sca
 int wino_ff_p9();  // raw-tile layout of the full-fold kernel (1 = parity planes with a 9-slot pitch)
 int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
 int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, cudaStream_t stream);
-int wino_ff_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                   int n_img, int C, int K, int op16, int relu, int out_padded, int max_ctas, cudaStream_t stream);
+int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* scale, const float* shift,
+                   float* y, int n_img, int C, int K, int op16, int relu, int out_padded, int max_ctas,
+                   cudaStream_t stream);
 
 // small-batch latency variant (wino_small_kernel.cu): TF32 only, filter in the plain KN=32 image
 int wino_small_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);

@@ -56,7 +56,7 @@ constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawStride;
 constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
 constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
 constexpr uint32_t kOffBar = kOffPix + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kRawStages + 2 * kUBufs + 4 + 2;
+constexpr uint32_t kNumBars = 2 * kRawStages + 8 + 2;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kTotal = kOffTmemPtr + 16;
 static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alignment");
@@ -109,6 +109,17 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   using namespace ff;
   const bool no_mma = DBG && (dbg & 1), no_xf = DBG && (dbg & 2), no_u = DBG && (dbg & 4), no_raw = DBG && (dbg & 8),
              no_out = DBG && (dbg & 16);
+  // dbg & 32 (with 16): CTA 0 records clock64() at the hand-off points of stages 8..15 of its first item and dumps
+  // them into y: [stage][8] from worker warp 0 at y, [stage][8] from the MMA thread at y + 1024 B
+  // dbg & 64 also records globaltimer_ns() per CTA: [12] kernel entry, [13] producer past griddepcontrol.wait,
+  // [14] first raw stage landed (worker warp 0), [15] CTA done
+  long long* ts_g = reinterpret_cast<long long*>(y) + 4096 + 16 * blockIdx.x;
+  if (DBG && (dbg & 64) && threadIdx.x == 0) ts_g[12] = (long long)globaltimer_ns();
+  const bool ts_on = DBG && (dbg & 32) && blockIdx.x == 0;
+  long long* ts_w = reinterpret_cast<long long*>(y);
+  long long* ts_m = reinterpret_cast<long long*>(y) + 128;
+#define WG_TS(buf, slot)                                                             \
+  if (DBG && ts_on && item == item0 && kb >= 8 && kb < 16) (buf)[(kb - 8) * 8 + (slot)] = clock64()
   constexpr int kSub = H16 ? 2 : 1;  // 8-channel raw stages per V stage
   const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
   out_padded &= 1;
@@ -120,11 +131,13 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* raw_full = bars;
   uint64_t* raw_empty = raw_full + kRawStages;
-  uint64_t* u_full = raw_empty + kRawStages;
-  uint64_t* u_empty = u_full + kUBufs;
-  uint64_t* v_full = u_empty + kUBufs;  // [half]
-  uint64_t* v_empty = v_full + 2;       // [half]
-  uint64_t* acc_full = v_empty + 2;
+  // One "full" / "done" barrier pair per filter-ring slot = (stage parity, V half): full[s] collects the 8 transform
+  // warps' "V half stored" AND the filter chunk's TMA bytes, so the MMA thread waits once per half; done[s] is the single
+  // tcgen05.commit of that half's 18 MMAs and releases both the filter chunk (producer) and the V half (transform warps).
+  static_assert(kUBufs == 4, "ring slot = 2 * (stage & 1) + half");
+  uint64_t* full = raw_empty + kRawStages;  // [4]
+  uint64_t* done = full + 4;                // [4]
+  uint64_t* acc_full = done + 4;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
@@ -135,13 +148,9 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       mbar_init(&raw_full[i], 1);
       mbar_init(&raw_empty[i], kWorkerWarps);
     }
-    for (int i = 0; i < kUBufs; ++i) {
-      mbar_init(&u_full[i], 1);
-      mbar_init(&u_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&v_full[i], kWorkerWarps);
-      mbar_init(&v_empty[i], 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full[i], kWorkerWarps + 1);
+      mbar_init(&done[i], 1);
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, kWorkerWarps);
@@ -172,13 +181,14 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         const int kn = sl.kn, c0 = sl.c0;
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
         for (int h = 0; h < 2; ++h) {
-          mbar_arrive_expect_tx(&u_full[us], 256u * kn);
-          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (size_t)h * 256 * kn, 256u * kn, &u_full[us]);
+          mbar_arrive_expect_tx(&full[us], 256u * kn);
+          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (size_t)h * 256 * kn, 256u * kn, &full[us]);
           ++us;
         }
         u_primed = 1;
       }
       pdl_wait();
+      if (DBG && (dbg & 64)) ts_g[13] = (long long)globaltimer_ns();
       for (int item = item0; item < n_items; item += item_step) {
         const Slice sl = slice(K, item % n_sl);
         const int kn = sl.kn, c0 = sl.c0;
@@ -210,13 +220,13 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             continue;
           }
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&u_empty[us], uph ^ 1);
+            mbar_wait(&done[us], uph ^ 1);
             if (no_u) {
-              mbar_arrive(&u_full[us]);
+              mbar_arrive(&full[us]);
             } else {
-              mbar_arrive_expect_tx(&u_full[us], 256u * kn);
+              mbar_arrive_expect_tx(&full[us], 256u * kn);
               tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)kb * 2 + h) * 256 * kn, 256u * kn,
-                           &u_full[us]);
+                           &full[us]);
             }
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
@@ -241,9 +251,10 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           uint32_t written = kb > 0 ? 0xFu : 0u;
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
-            mbar_wait(&u_full[us], uph);  // there long before V: checked first, off the V -> MMA critical path
-            mbar_wait(&v_full[jh], g & 1);
+            WG_TS(ts_m, jh * 4 + 0);
+            mbar_wait(&full[us], uph);  // filter chunk landed and V half stored by all 8 transform warps
             tc_fence_after();
+            WG_TS(ts_m, jh * 4 + 1);
             const uint32_t ua = u_base + us * kUChunkMax;
             const uint32_t va = tmem_base + kVCol0 + jh * 64;
 #pragma unroll
@@ -271,8 +282,8 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                 }
               }
             }
-            umma_commit(&u_empty[us]);
-            umma_commit(&v_empty[jh]);  // this V half may be overwritten
+            WG_TS(ts_m, jh * 4 + 2);
+            umma_commit(&done[us]);  // frees the filter chunk and this V half
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
           ++g;
@@ -292,7 +303,13 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     const uint32_t stg_base = smem_u32(smem + kOffStg);
 
     uint32_t rs = 0, rph = 0, g = 0, aph = 0;  // g = V stages transformed (same counting as the MMA thread)
-    for (int item = item0; item < n_items; item += item_step) {
+    // dbg & 64 (with 16): every CTA records clock64() at item start / main loop end / epilogue end of its first four
+    // items: long long y[4096 + 16 * blockIdx.x + 4 * item_index + {0, 1, 2}], slot 3 = item number
+    long long* ts_i = reinterpret_cast<long long*>(y) + 4096 + 16 * blockIdx.x;
+    const bool ts_item = DBG && (dbg & 64) && warp == 0 && lane == 0;
+    int item_idx = 0;
+    for (int item = item0; item < n_items; item += item_step, ++item_idx) {
+      if (DBG && ts_item && item_idx < 4) ts_i[4 * item_idx] = clock64(), ts_i[4 * item_idx + 3] = item;
       const Slice sl = slice(K, item % n_sl);
       const int kn = sl.kn, c0s = sl.c0;
       const int mb = item / n_sl;
@@ -322,7 +339,9 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       }
 
       for (int kb = 0; kb < n_kb; ++kb) {
-        const uint32_t vph = g & 1;
+        // this stage's ring slots are slot, slot + 1; the previous stage's (whose MMAs must have completed before a V
+        // half is overwritten) pslot, pslot + 1, completing for the ((g - 1) >> 1)-th time
+        const uint32_t slot = (g & 1) * 2, pslot = slot ^ 2, pph = ((g - 1) >> 1) & 1;
         if (!warp_active) {
           // nothing to transform: release the raw stage(s) and report "V ready" in step with the other warps
 #pragma unroll
@@ -333,15 +352,18 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
-            mbar_wait(&v_empty[jh], vph ^ 1);
-            if (lane == 0) mbar_arrive(&v_full[jh]);
+            if (g > 0) mbar_wait(&done[pslot + jh], pph);
+            if (lane == 0) mbar_arrive(&full[slot + jh]);
           }
           ++g;
           continue;
         }
 #pragma unroll
         for (int sb = 0; sb < kSub; ++sb) {  // H16: two 8-channel raw stages fill one 16-channel V stage
+          if (warp == 0 && lane == 0 && sb == 0) { WG_TS(ts_w, 0); }
           mbar_wait(&raw_full[rs], rph);
+          if (warp == 0 && lane == 0 && sb == 0) { WG_TS(ts_w, 1); }
+          if (DBG && ts_item && item_idx == 0 && kb == 0 && sb == 0) ts_g[14] = (long long)globaltimer_ns();
           float d[4][4][4];
           if (no_xf) {
             __syncwarp();
@@ -350,8 +372,8 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             if (sb == kSub - 1) {
 #pragma unroll
               for (int jh = 0; jh < 2; ++jh) {
-                mbar_wait(&v_empty[jh], vph ^ 1);
-                if (lane == 0) mbar_arrive(&v_full[jh]);
+                if (g > 0) mbar_wait(&done[pslot + jh], pph);
+                if (lane == 0) mbar_arrive(&full[slot + jh]);
               }
             }
             continue;
@@ -396,10 +418,12 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           const uint32_t vcol = tmem_base + lane_base + kVCol0 + (uint32_t)(H16 ? sb * 4 + cq * 2 : cq * 4);
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
+            if (warp == 0 && lane == 0 && sb == kSub - 1) { WG_TS(ts_w, 2 + jh * 3); }
             if (sb == 0) {
-              mbar_wait(&v_empty[jh], vph ^ 1);  // the MMAs that last read this V half have completed
+              if (g > 0) mbar_wait(&done[pslot + jh], pph);  // the MMAs that last read this V half have completed
               tc_fence_after();
             }
+            if (warp == 0 && lane == 0 && sb == kSub - 1) { WG_TS(ts_w, 3 + jh * 3); }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float v0[4], v1[4];  // points (i, 2jh) and (i, 2jh+1)
@@ -423,7 +447,8 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
               tmem_st_wait();
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&v_full[jh]);
+              if (lane == 0) mbar_arrive(&full[slot + jh]);
+              if (warp == 0 && lane == 0) { WG_TS(ts_w, 4 + jh * 3); }
             }
           }
         }  // sb
@@ -443,6 +468,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       mbar_wait(acc_full, aph);
       aph ^= 1;
       tc_fence_after();
+      if (DBG && ts_item && item_idx < 4) ts_i[4 * item_idx + 1] = clock64();
       if (warp_active) {
 #pragma unroll 1
         for (int ec = 0; ec < n_chunks; ++ec) {
@@ -520,11 +546,13 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       } else {
         if (lane == 0) mbar_arrive(acc_empty);
       }
+      if (DBG && ts_item && item_idx < 4) ts_i[4 * item_idx + 2] = clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (DBG && (dbg & 64) && threadIdx.x == 0) ts_g[15] = (long long)globaltimer_ns();
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
@@ -678,8 +706,12 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-int wino_ff_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                   int n_img, int C, int K, int op16, int relu, int out_padded, int max_ctas, cudaStream_t stream) {
+int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* scale, const float* shift,
+                   float* y, int n_img, int C, int K, int op16, int relu, int out_padded, int max_ctas,
+                   cudaStream_t stream) {
+  // (An L2 prefetch of the next item's raw rows, cp.async.bulk.prefetch.L2 spread over the stages of the current
+  //  item, was measured: no gain -- the kernel is as fast with HBM-cold as with L2-resident input.)
+  (void)x;
   // op16: 0 = TF32 operands, 1 = bf16, 2 = fp16 (V packed in TMEM, 16-channel stages)
   static int dbg = -1;  // WG_FF_DEBUG: ablation switches of the developer build (see the kernel)
   if (dbg < 0) {

@@ -6,6 +6,7 @@ checked, come prebuilt from oracle/_ref/ (see test_reference_gpu.py).
 """
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -105,6 +106,46 @@ def test_3x3_small_batch_split_c_mode(lib_loaded, torch_cuda, n, c, k, padded):
 
 
 TOL_BF16 = 1e-2
+
+
+@pytest.mark.parametrize("kn", [96, 48, 64])
+@pytest.mark.parametrize("n,c,k", [(40, 64, 256), (33, 32, 96), (50, 24, 160), (20, 16, 512), (64, 128, 128),
+                                   (131, 48, 192), (37, 8, 32), (29, 40, 64), (300, 16, 32)])
+def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
+    """Every throughput kernel on batches that do not fill the last 128-tile M-block and on every cout-slice width:
+    kn = 96 the full-fold kernel (wino_ff_kernel.cu: 4 accumulators, slices of 96 / 64 / 32 -- the default), kn = 48 the
+    half-fold V-in-TMEM kernel (slices of 48 / 32), kn = 64 the shared-memory-operand kernel. TF32 and, where the shape
+    allows them, bf16 / fp16 operands; dense output and the zero-bordered frame must agree bit for bit."""
+    torch = torch_cuda
+    if kn == 64 and k % 64:
+        pytest.skip("the KN=64 kernel needs K % 64 == 0")
+    x, w, sc, sh = _rand3x3(np.random.RandomState(900 + n + c + k), n, c, k)
+    gold = golden.conv3x3_bn_relu(x, w, sc, sh, True)
+    xd = torch.from_numpy(x).cuda()
+    lib_loaded.lib().wg_set_wino_kn(kn)
+    try:
+        for dt, tol in ((lib_loaded.WG_TF32, TOL_TF32), (lib_loaded.WG_BF16, TOL_BF16), (lib_loaded.WG_FP16, TOL_TF32)):
+            if dt != lib_loaded.WG_TF32 and (c % 16 or k % 64):
+                continue
+            layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=dt)
+            y = layer(xd).cpu().numpy()
+            yp = layer(xd, out_padded=True).cpu().numpy()
+            assert golden.rel_err(y, gold) <= tol
+            np.testing.assert_array_equal(yp[:, 1:15, 1:15], y)
+            assert np.all(yp[:, 0] == 0) and np.all(yp[:, 15] == 0) and np.all(yp[:, :, 0] == 0) and np.all(yp[:, :, 15] == 0)
+            layer.close()
+    finally:
+        lib_loaded.lib().wg_set_wino_kn(96)
+
+
+def test_3x3_full_fold_kernel_with_the_plain_raw_layout(lib_loaded):
+    """WG_FF_P9=0 (an A/B knob: the full-fold kernel on the TM kernel's single-box raw layout) stays correct; the knob
+    is read once per process, hence the subprocess."""
+    env = dict(os.environ, WG_FF_P9="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ff_check.py"), "--quick", "--kns", "96",
+                        "--iters", "3", "--out", os.path.join(ROOT, "gpurun_out", "ff_check_p9_0.json")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("n,c,k", [(1, 128, 128), (1, 256, 256), (3, 64, 64), (5, 48, 128), (64, 128, 128), (131, 48, 192)])

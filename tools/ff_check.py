@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--time-only", action="store_true", help="skip the parity section, never fail (ablation runs)")
     ap.add_argument("--dtypes", default="tf32,bf16,fp16")
+    ap.add_argument("--sets", type=int, default=4, help="rotating input/output sets (1 = L2-warm input)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -79,7 +80,7 @@ def main():
         rs = np.random.RandomState(7)
         w = (rs.rand(k, c, 3, 3) - 0.5).astype(np.float32)
         sc, sh = golden.fold_bn(rs.rand(k) - 0.5, rs.rand(k) - 0.5, rs.rand(k) - 0.5, rs.rand(k) * 3 + 5)
-        sets = 4
+        sets = args.sets
         g = torch.Generator(device=dev)
         g.manual_seed(5)
         xs = [torch.rand((n, 16, 16, c), device=dev, generator=g) - 0.5 for _ in range(sets)]

@@ -773,6 +773,67 @@ static void time_ts_rate(int count) {
   cudaFree(dc);
 }
 
+// ------------------------------------------------------------------------------------------------ patch-load probe
+// Shared-memory cost of the transform warps' 16 LDS.128 per stage under three address patterns: 0 = one 16-byte chunk
+// per lane, consecutive (the conflict-free reference), 1 = the full-fold kernel's parity-plane layout (9-slot pitch,
+// tiles right-to-left), 2 = the single-box layout of the TM kernel (8-slot pitch). 8 warps as in the kernels.
+__global__ void lds_probe_kernel(long long* out, int pattern, int iters) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 28 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = (float)i;
+  __syncthreads();
+  const int quad = warp & 3, cq = warp >> 2, row = quad * 32 + lane;
+  const int t = row % 49, n = row / 49, ty = t / 7;
+  uint32_t ad[16];
+  for (int dy = 0; dy < 4; ++dy)
+    for (int dx = 0; dx < 4; ++dx) {
+      uint32_t a;
+      if (pattern == 0) {
+        a = (uint32_t)((dy * 4 + dx) * 1024 + tid * 16) % (24 * 1024);
+      } else if (pattern == 1) {
+        const int tx = 6 - t % 7;
+        const uint32_t sl = (uint32_t)(((n * 16 + 2 * ty) >> 1) * 9 + tx + 1 + 9 * (dy >> 1) + (dx >> 1));
+        a = ((dy & 1) * 2 + (dx & 1)) * 6912 + sl * 32 + ((cq ^ ((sl >> 2) & 1)) * 16);
+      } else {
+        const int tx = t % 7;
+        const int x2 = tx + (dx >> 1);
+        a = (uint32_t)((n * 16 + 2 * ty + dy) * 512 + (dx & 1) * 256 + x2 * 32 + ((cq ^ ((x2 >> 2) & 1)) * 16));
+      }
+      ad[dy * 4 + dx] = wg::smem_u32(sm) + a;
+    }
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float4 v;  // "memory" clobber: keeps the loop-invariant loads inside the loop
+      asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ad[k]) : "memory");
+      acc += v.x + v.y + v.z + v.w;
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid == 0) out[0] = t1 - t0;
+  if (acc == 123.456f) out[1] = 1;
+}
+
+static void time_lds(int pattern) {
+  long long* dc;
+  CK(cudaMalloc(&dc, 16));
+  CK(cudaFuncSetAttribute(lds_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 28 * 1024));
+  const int iters = 200;
+  for (int rep = 0; rep < 2; ++rep) {
+    lds_probe_kernel<<<1, 256, 28 * 1024>>>(dc, pattern, iters);
+    CK(cudaDeviceSynchronize());
+  }
+  long long clk = 0;
+  CK(cudaMemcpy(&clk, dc, 8, cudaMemcpyDeviceToHost));
+  printf("LDS.128 probe pattern %d: %lld clk for %d x 16 loads x 8 warps = %.2f clk per warp-level LDS.128 (4.00 = "
+         "conflict-free)\n", pattern, clk, iters, (double)clk / (iters * 16 * 8));
+  cudaFree(dc);
+}
+
 // ------------------------------------------------------------------------------------------------ launch floor
 // What an N=1 layer cannot go below: empty kernels launched back to back the way the product launches its own
 // (dynamic smem opt-in, 128-byte __grid_constant__ parameter, optional cluster), timed with the same event loop.
@@ -867,6 +928,10 @@ int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "ts")) {
     run_ts_probe();
     run_ts16_probe();
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "lds")) {
+    for (int p = 0; p < 3; ++p) time_lds(p);
     return 0;
   }
   if (argc > 1 && !strcmp(argv[1], "tsrate")) {
