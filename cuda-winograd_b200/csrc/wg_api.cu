@@ -83,6 +83,7 @@ struct wg_layer {
   int tile_n;  // 3x3: cout slice KN; 1x1: BN
   int tm_db;   // 3x3 TM kernel: 1 = double-buffered V, 32-wide slices
   int tm16_ff; // 3x3 bf16/fp16: d_filter_tm16 is the full-fold kernel's image (96-wide slices)
+  int ff_cg2;  // 3x3 full-fold kernel: CTA-pair variant (filter image split in cout halves)
   int num_sms;
   float* d_filter;  // packed filter image (U or swizzled W^T)
   float* d_filter_tm16;   // 3x3 bf16/fp16 only: U in the 16-bit image of the V-in-TMEM throughput kernel (48/32 slices)
@@ -176,8 +177,9 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   WG_TRY(cudaMemcpyAsync(d_w, w, w_elems * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_scale, scale, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
+  if (kind == 0) L->ff_cg2 = wino_ff_cg2();
   if (kind == 0 && L->tile_n == 96) {
-    rc = filter_transform_ff_launch(d_w, L->d_filter, cin, cout, 0, L->stream);
+    rc = filter_transform_ff_launch(d_w, L->d_filter, cin, cout, 0, L->ff_cg2, L->stream);
   } else if (kind == 0 && L->tile_n == 48) {
     L->tm_db = wino_tm_choose_db(cin, cout);
     rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->tm_db, 0, L->stream);
@@ -190,7 +192,8 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
     // split-C variant of the shared-memory-operand kernel (d_filter)
     WG_TRY(cudaMalloc(&L->d_filter_tm16, filter_elems * sizeof(uint16_t)));
     L->tm16_ff = wino_kn() == 96;
-    rc = L->tm16_ff ? filter_transform_ff_launch(d_w, L->d_filter_tm16, cin, cout, dtype == WG_FP16 ? 2 : 1, L->stream)
+    rc = L->tm16_ff ? filter_transform_ff_launch(d_w, L->d_filter_tm16, cin, cout, dtype == WG_FP16 ? 2 : 1, L->ff_cg2,
+                                                 L->stream)
                     : filter_transform_tm_launch(d_w, L->d_filter_tm16, cin, cout, 0, dtype == WG_FP16 ? 2 : 1,
                                                  L->stream);
     g_launches++;
@@ -274,7 +277,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
       }
       const int op16 = L->dtype == WG_FP16 ? 2 : 1;
       int rc = L->tm16_ff ? wino_ff_launch(L->tmap_tm, x, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
-                                           op16, L->relu, out_flags, max_ctas, stream)
+                                           op16, L->ff_cg2, L->relu, out_flags, max_ctas, stream)
                           : wino_tm_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
                                            0, op16, L->relu, out_flags, max_ctas, stream);
       g_launches++;
@@ -299,8 +302,8 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   }
   int rc;
   if (L->kind == 0 && L->tile_n == 96)
-    rc = wino_ff_launch(L->tmap, x, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, L->relu, out_flags,
-                        max_ctas, stream);
+    rc = wino_ff_launch(L->tmap, x, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, L->ff_cg2, L->relu,
+                        out_flags, max_ctas, stream);
   else if (L->kind == 0 && L->tile_n == 48)
     rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, 0, L->relu,
                         out_flags, max_ctas, stream);

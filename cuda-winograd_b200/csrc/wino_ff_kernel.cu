@@ -56,7 +56,7 @@ constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawStride;
 constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
 constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
 constexpr uint32_t kOffBar = kOffPix + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kRawStages + 8 + 2;
+constexpr uint32_t kNumBars = 2 * kRawStages + 8 + 2 + 4;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kTotal = kOffTmemPtr + 16;
 static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alignment");
@@ -79,11 +79,16 @@ __host__ __device__ inline int slice_of(int K, int k) {
 
 __device__ __forceinline__ float ff_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
-template <bool H16>
+template <bool H16, bool CG2>
 __device__ __forceinline__ void ff_umma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
-  if constexpr (H16) umma_f16_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
-  else umma_tf32_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+  if constexpr (CG2) {
+    if constexpr (H16) umma_f16_ts_cg2(d_tmem, a_tmem, b_desc, idesc, accumulate);
+    else umma_tf32_ts_cg2(d_tmem, a_tmem, b_desc, idesc, accumulate);
+  } else {
+    if constexpr (H16) umma_f16_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+    else umma_tf32_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+  }
 }
 
 // two fp32 -> one 32-bit TMEM column of 16-bit operands (first value in the low half), round to nearest
@@ -101,7 +106,15 @@ __device__ __forceinline__ float ff_pack16(float lo, float hi, int fp16) {
 // DBG: developer build with ablation switches (WG_FF_DEBUG=<bits>: 1 no MMAs, 2 no patch loads / transform / TMEM
 // stores, 4 no filter loads, 8 no raw-tile loads, 16 no output stores); results are garbage, only the time is of interest.
 // The product instantiation (DBG = false) contains none of it.
-template <bool H16, bool DBG, bool P9>
+// CG2: CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2). The two CTAs take neighbouring M-blocks and the
+// same cout slice; each loads, transforms and drains its own 128 tiles, but the MMAs are issued by the leader CTA
+// (cluster rank 0) with M = 256: each CTA supplies HALF of the couts of every filter chunk from its own shared memory,
+// so the tensor core's B-operand reads and the filter's TMA traffic per SM halve -- the shared-memory data path is what
+// the transform warps' patch loads, the MMAs' operand reads and the TMA writes compete for. Cross-CTA hand-offs: the
+// peer's transform warps arrive on the LEADER's full[] barriers (mbarrier.arrive.release.cluster), the peer's otherwise
+// idle MMA warp relays "my half of the filter chunk has landed", the leader's tcgen05.commit multicasts done[] /
+// acc_full to both CTAs.
+template <bool H16, bool DBG, bool P9, bool CG2>
 __global__ void __launch_bounds__(32 * (ff::kWorkerWarps + 2), 1)
 wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
@@ -139,6 +152,9 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   uint64_t* done = full + 4;                // [4]
   uint64_t* acc_full = done + 4;
   uint64_t* acc_empty = acc_full + 1;
+  uint64_t* u_land = acc_empty + 1;  // [4] CG2, peer CTA only: its half of a filter chunk has landed
+  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
+  const bool peer = CG2 && crank != 0;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
 
@@ -149,16 +165,22 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       mbar_init(&raw_empty[i], kWorkerWarps);
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], kWorkerWarps + 1);
+      // CG2 (leader): both CTAs' transform warps + own TMA bytes + the peer's relay
+      mbar_init(&full[i], CG2 ? 2 * kWorkerWarps + 2 : kWorkerWarps + 1);
       mbar_init(&done[i], 1);
+      mbar_init(&u_land[i], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kWorkerWarps);
+    mbar_init(acc_empty, CG2 ? 2 * kWorkerWarps : kWorkerWarps);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr);
+  if (warp == kMmaWarp) {
+    if constexpr (CG2) tmem_alloc_cg2<512>(tmem_ptr);
+    else tmem_alloc<512>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all();  // the peer's barriers exist before anybody arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -166,8 +188,10 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   const int n_sl = n_slices(K);
   const int total_tiles = n_img * 49;
   const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host
-  const int n_items = n_mblocks * n_sl;               // item = (M-block, cout slice); slices of an M-block are adjacent
-  const int item0 = blockIdx.x, item_step = gridDim.x;
+  // item = (M-block, cout slice), slices of an M-block adjacent; CG2: (pair of M-blocks, slice), one item per cluster
+  const int n_items = (CG2 ? (n_mblocks + 1) / 2 : n_mblocks) * n_sl;
+  const int item0 = CG2 ? blockIdx.x / 2 : blockIdx.x, item_step = CG2 ? gridDim.x / 2 : gridDim.x;
+  const uint32_t u_bytes_per_kn = CG2 ? 128u : 256u;  // bytes of a filter chunk this CTA loads, per cout of the slice
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -181,8 +205,10 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         const int kn = sl.kn, c0 = sl.c0;
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
         for (int h = 0; h < 2; ++h) {
-          mbar_arrive_expect_tx(&full[us], 256u * kn);
-          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (size_t)h * 256 * kn, 256u * kn, &full[us]);
+          uint64_t* ubar = peer ? &u_land[us] : &full[us];
+          mbar_arrive_expect_tx(ubar, u_bytes_per_kn * kn);
+          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)h * 256 + crank * 128) * kn, u_bytes_per_kn * kn,
+                       ubar);
           ++us;
         }
         u_primed = 1;
@@ -192,7 +218,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       for (int item = item0; item < n_items; item += item_step) {
         const Slice sl = slice(K, item % n_sl);
         const int kn = sl.kn, c0 = sl.c0;
-        const int mb = item / n_sl;
+        const int mb = CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl;
         const int t0 = mb * mv;
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
@@ -220,13 +246,15 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             continue;
           }
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&done[us], uph ^ 1);
+            if constexpr (CG2) mbar_wait_cluster(&done[us], uph ^ 1);
+            else mbar_wait(&done[us], uph ^ 1);
+            uint64_t* ubar = peer ? &u_land[us] : &full[us];
             if (no_u) {
-              mbar_arrive(&full[us]);
+              mbar_arrive(ubar);
             } else {
-              mbar_arrive_expect_tx(&full[us], 256u * kn);
-              tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)kb * 2 + h) * 256 * kn, 256u * kn,
-                           &full[us]);
+              mbar_arrive_expect_tx(ubar, u_bytes_per_kn * kn);
+              tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (((size_t)kb * 2 + h) * 256 + crank * 128) * kn,
+                           u_bytes_per_kn * kn, ubar);
             }
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
@@ -235,16 +263,29 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one elected thread)
-    if (elect_one()) {
+    if (peer) {
+      // CG2, peer CTA: no MMAs to issue here; relay "my half of filter chunk us has landed" to the leader's full[us]
+      if (elect_one()) {
+        uint32_t us = 0, uph = 0;
+        for (int item = item0; item < n_items; item += item_step)
+          for (int c = 0; c < 2 * n_kb; ++c) {
+            mbar_wait(&u_land[us], uph);
+            mbar_arrive_remote(&full[us], 0);
+            if (++us == kUBufs) { us = 0; uph ^= 1; }
+          }
+      }
+    } else if (elect_one()) {
       const uint32_t u_base = smem_u32(smem + kOffU);
       uint32_t g = 0, us = 0, uph = 0, aph = 0;  // g = V stages issued (V phase = g & 1)
       for (int item = item0; item < n_items; item += item_step) {
         const uint32_t kn = (uint32_t)slice(K, item % n_sl).kn;
         const uint32_t fmt = H16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
-        const uint32_t idesc_pos = make_idesc(fmt, 128, kn);
-        const uint32_t idesc_neg = make_idesc(fmt, 128, kn, 1);  // D += (-A) * B
-        const uint32_t u_per_point = 2 * kn * 16, u_lbo = kn * 16;
-        mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
+        const uint32_t idesc_pos = make_idesc(fmt, CG2 ? 256 : 128, kn);
+        const uint32_t idesc_neg = make_idesc(fmt, CG2 ? 256 : 128, kn, 1);  // D += (-A) * B
+        // CG2: this CTA's shared memory holds kn/2 couts of every point
+        const uint32_t u_per_point = (CG2 ? 1 : 2) * kn * 16, u_lbo = (CG2 ? kn / 2 : kn) * 16;
+        if constexpr (CG2) mbar_wait_cluster(acc_empty, aph ^ 1);
+        else mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
         for (int kb = 0; kb < n_kb; ++kb) {
           // bit p set = accumulator p has been written in this item (first MMA into it overwrites)
@@ -252,7 +293,9 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
             WG_TS(ts_m, jh * 4 + 0);
-            mbar_wait(&full[us], uph);  // filter chunk landed and V half stored by all 8 transform warps
+            // filter chunk landed and V half stored by all transform warps (of both CTAs)
+            if constexpr (CG2) mbar_wait_cluster(&full[us], uph);
+            else mbar_wait(&full[us], uph);
             tc_fence_after();
             WG_TS(ts_m, jh * 4 + 1);
             const uint32_t ua = u_base + us * kUChunkMax;
@@ -275,20 +318,22 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                     const int sb = (b == 1 && j >= 2) ? -1 : 1;
                     const uint32_t p = (uint32_t)(2 * a + b);
                     if (!no_mma)
-                      ff_umma<H16>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
-                                   (written >> p) & 1u);
+                      ff_umma<H16, CG2>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
+                                        (written >> p) & 1u);
                     written |= 1u << p;
                   }
                 }
               }
             }
             WG_TS(ts_m, jh * 4 + 2);
-            umma_commit(&done[us]);  // frees the filter chunk and this V half
+            if constexpr (CG2) umma_commit_mcast_cg2(&done[us], 3);  // frees the filter chunk and this V half, both CTAs
+            else umma_commit(&done[us]);
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
           ++g;
         }
-        umma_commit(acc_full);
+        if constexpr (CG2) umma_commit_mcast_cg2(acc_full, 3);
+        else umma_commit(acc_full);
         aph ^= 1;
       }
     }
@@ -303,6 +348,15 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     const uint32_t stg_base = smem_u32(smem + kOffStg);
 
     uint32_t rs = 0, rph = 0, g = 0, aph = 0;  // g = V stages transformed (same counting as the MMA thread)
+    // CG2: full[] / acc_empty live in the leader CTA; done[] / acc_full are signalled by the leader's multicast commit
+    auto arrive_leader = [&](uint64_t* bar) {
+      if (peer) mbar_arrive_remote(bar, 0);
+      else mbar_arrive(bar);
+    };
+    auto wait_done = [&](uint64_t* bar, uint32_t parity) {
+      if constexpr (CG2) mbar_wait_cluster(bar, parity);
+      else mbar_wait(bar, parity);
+    };
     // dbg & 64 (with 16): every CTA records clock64() at item start / main loop end / epilogue end of its first four
     // items: long long y[4096 + 16 * blockIdx.x + 4 * item_index + {0, 1, 2}], slot 3 = item number
     long long* ts_i = reinterpret_cast<long long*>(y) + 4096 + 16 * blockIdx.x;
@@ -312,7 +366,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       if (DBG && ts_item && item_idx < 4) ts_i[4 * item_idx] = clock64(), ts_i[4 * item_idx + 3] = item;
       const Slice sl = slice(K, item % n_sl);
       const int kn = sl.kn, c0s = sl.c0;
-      const int mb = item / n_sl;
+      const int mb = CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl;
       const int t0 = mb * mv;
       const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
       const int T = t0 + row;
@@ -352,8 +406,8 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
-            if (g > 0) mbar_wait(&done[pslot + jh], pph);
-            if (lane == 0) mbar_arrive(&full[slot + jh]);
+            if (g > 0) wait_done(&done[pslot + jh], pph);
+            if (lane == 0) arrive_leader(&full[slot + jh]);
           }
           ++g;
           continue;
@@ -372,8 +426,8 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             if (sb == kSub - 1) {
 #pragma unroll
               for (int jh = 0; jh < 2; ++jh) {
-                if (g > 0) mbar_wait(&done[pslot + jh], pph);
-                if (lane == 0) mbar_arrive(&full[slot + jh]);
+                if (g > 0) wait_done(&done[pslot + jh], pph);
+                if (lane == 0) arrive_leader(&full[slot + jh]);
               }
             }
             continue;
@@ -420,7 +474,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           for (int jh = 0; jh < 2; ++jh) {
             if (warp == 0 && lane == 0 && sb == kSub - 1) { WG_TS(ts_w, 2 + jh * 3); }
             if (sb == 0) {
-              if (g > 0) mbar_wait(&done[pslot + jh], pph);  // the MMAs that last read this V half have completed
+              if (g > 0) wait_done(&done[pslot + jh], pph);  // the MMAs that last read this V half have completed
               tc_fence_after();
             }
             if (warp == 0 && lane == 0 && sb == kSub - 1) { WG_TS(ts_w, 3 + jh * 3); }
@@ -447,7 +501,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
               tmem_st_wait();
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&full[slot + jh]);
+              if (lane == 0) arrive_leader(&full[slot + jh]);
               if (warp == 0 && lane == 0) { WG_TS(ts_w, 4 + jh * 3); }
             }
           }
@@ -465,7 +519,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       const int qrows = min(32, valid_rows - quad * 32);  // real tiles among this quad's rows (<= 0: none)
       const int tid64 = cq * 32 + lane;
 
-      mbar_wait(acc_full, aph);
+      wait_done(acc_full, aph);
       aph ^= 1;
       tc_fence_after();
       if (DBG && ts_item && item_idx < 4) ts_i[4 * item_idx + 1] = clock64();
@@ -492,7 +546,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             if (ec == n_chunks - 1 && a == 1) {  // this warp has read its last accumulator columns
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(acc_empty);
+              if (lane == 0) arrive_leader(acc_empty);
             }
             const uint32_t sdst = stg_base + (uint32_t)row * kStgRow + (uint32_t)cl * 4;
 #pragma unroll
@@ -544,16 +598,20 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
         }
       } else {
-        if (lane == 0) mbar_arrive(acc_empty);
+        if (lane == 0) arrive_leader(acc_empty);
       }
       if (DBG && ts_item && item_idx < 4) ts_i[4 * item_idx + 2] = clock64();
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all();  // the peer's shared memory, TMEM and barriers stay alive until the pair is done
+  else __syncthreads();
   if (DBG && (dbg & 64) && threadIdx.x == 0) ts_g[15] = (long long)globaltimer_ns();
-  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+  if (warp == kMmaWarp) {
+    if constexpr (CG2) tmem_dealloc_cg2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -562,8 +620,10 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 // (j = 2*jh + jj). 512 bytes per (k-block, cout), so slice s starts at byte (C/8)*512*c0(s).
 // Replaces the offline weight_generator loop (/root/reference/data_generator.py:63-78; that one is F(4x4), 36 points).
 // op16 = 1 (bf16) / 2 (fp16): 16-channel k-blocks, 8 channels per 16-byte chunk, same 512 bytes per (k-block, cout).
+// cg2: image of the CTA-pair kernel -- inside every (k-block, j-half) chunk the couts of the slice are split in two
+// halves, [rank 2][8 points][2 k-chunks][KN/2 couts][16 B], CTA `rank` of a pair loads its 128*KN contiguous bytes.
 __global__ void filter_transform_ff_kernel(const float* __restrict__ w_kcrs, float* __restrict__ u_img, int C, int K,
-                                           int op16) {
+                                           int op16, int cg2) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * K) return;
   const int ch = idx % C;
@@ -600,10 +660,18 @@ __global__ void filter_transform_ff_kernel(const float* __restrict__ w_kcrs, flo
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = (j >> 1) * 8 + i * 2 + (j & 1);
-      const size_t o16 = base16 + (size_t)p * (2 * kn * 8) + ((size_t)chunk16 * kn + kl) * 8 + e16;
+      size_t o16 = base16 + (size_t)p * (2 * kn * 8) + ((size_t)chunk16 * kn + kl) * 8 + e16;
+      size_t o32 = base + (size_t)p * (2 * kn * 4) + ((size_t)chunk * kn + kl) * 4 + e;
+      if (cg2) {
+        const int hk = kn / 2, rank = kl / hk, klr = kl % hk, jh = j >> 1, p8 = i * 2 + (j & 1);
+        o16 = base16 + (size_t)jh * (128 * kn) + (size_t)rank * (64 * kn) + (size_t)p8 * (8 * kn) +
+              ((size_t)chunk16 * hk + klr) * 8 + e16;
+        o32 = base + (size_t)jh * (64 * kn) + (size_t)rank * (32 * kn) + (size_t)p8 * (4 * kn) +
+              ((size_t)chunk * hk + klr) * 4 + e;
+      }
       if (op16 == 2) reinterpret_cast<__half*>(u_img)[o16] = __float2half_rn(u[j]);
       else if (op16 == 1) reinterpret_cast<__nv_bfloat16*>(u_img)[o16] = __float2bfloat16_rn(u[j]);
-      else u_img[base + (size_t)p * (2 * kn * 4) + ((size_t)chunk * kn + kl) * 4 + e] = to_tf32_rn(u[j]);
+      else u_img[o32] = to_tf32_rn(u[j]);
     }
   }
 }
@@ -622,6 +690,20 @@ int wino_ff_p9() {
   return v;
 }
 
+// CTA pairs (cta_group::2) for layers created from now on: WG_FF_CG2=1. Needs the parity-plane raw layout.
+// EXPERIMENT, default off. Measured (N=256, B200): 256->256 TF32 163 us against 99 us for single CTAs, bf16 118 against
+// 83, 128->128 84 against 48: with V single-buffered in TMEM every half-stage hand-off (V stored -> MMA -> V free) now
+// crosses the SM pair twice (remote mbarrier arrive, multicast commit), and that round trip, not the shared-memory
+// traffic the pairing halves, sets the stage time. Results are bit-identical to the single-CTA kernel.
+int wino_ff_cg2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WG_FF_CG2");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v && wino_ff_p9();
+}
+
 int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
   if (!wino_ff_p9()) return wino_tm_make_tmap(tmap, x, n_img, C, 1);
   PFN_encodeTiled enc = get_encode_tiled();
@@ -638,13 +720,14 @@ int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
 
-int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, cudaStream_t stream) {
+int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, int cg2,
+                               cudaStream_t stream) {
   const int n = C * K;
-  filter_transform_ff_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, op16);
+  filter_transform_ff_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, op16, cg2);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-template <bool H16, bool DBG, bool P9>
+template <bool H16, bool DBG, bool P9, bool CG2>
 static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                      int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream, int fp16,
                      int dbg) {
@@ -653,7 +736,7 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16, DBG, P9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
+    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16, DBG, P9, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
         cudaSuccess)
       return WG_ERR_CUDA;
     configured |= dev_bit_;
@@ -683,17 +766,26 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
       }
     }
   }
-  const int n_items = ((total_tiles + mv - 1) / mv) * n_sl;
-  int grid = max_ctas;
+  const int n_mblocks = (total_tiles + mv - 1) / mv;
+  const int n_items = (CG2 ? (n_mblocks + 1) / 2 : n_mblocks) * n_sl;  // CG2: one item per CTA pair
+  int grid = CG2 ? max_ctas / 2 : max_ctas;
   if (grid > n_items) grid = n_items;
   if (grid < 1) grid = 1;
+  if (CG2) grid *= 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(32 * (ff::kWorkerWarps + 2));
   cfg.dynamicSmemBytes = ff::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int na = 0;
+  if (CG2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -701,13 +793,13 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ff_kernel<H16, DBG, P9>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ff_kernel<H16, DBG, P9, CG2>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
                                      out_padded, mv, fp16, dbg);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* scale, const float* shift,
-                   float* y, int n_img, int C, int K, int op16, int relu, int out_padded, int max_ctas,
+                   float* y, int n_img, int C, int K, int op16, int cg2, int relu, int out_padded, int max_ctas,
                    cudaStream_t stream) {
   // (An L2 prefetch of the next item's raw rows, cp.async.bulk.prefetch.L2 spread over the stages of the current
   //  item, was measured: no gain -- the kernel is as fast with HBM-cold as with L2-resident input.)
@@ -719,23 +811,23 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
     dbg = e ? atoi(e) : 0;
   }
   const int fp16 = op16 == 2;
-#define WG_FF(H16_, DBG_, P9_)                                                                                        \
-  return launch_ff<H16_, DBG_, P9_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, fp16, \
-                                    dbg)
+#define WG_FF(H16_, DBG_, P9_, CG2_)                                                                                \
+  return launch_ff<H16_, DBG_, P9_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, \
+                                          fp16, dbg)
+  if (cg2) {  // CTA pairs: parity-plane raw layout only, no developer build
+    if (op16) WG_FF(true, false, true, true);
+    WG_FF(false, false, true, true);
+  }
   if (wino_ff_p9()) {
     if (dbg > 0) {
-      if (op16) WG_FF(true, true, true);
-      WG_FF(false, true, true);
+      if (op16) WG_FF(true, true, true, false);
+      WG_FF(false, true, true, false);
     }
-    if (op16) WG_FF(true, false, true);
-    WG_FF(false, false, true);
+    if (op16) WG_FF(true, false, true, false);
+    WG_FF(false, false, true, false);
   }
-  if (dbg > 0) {
-    if (op16) WG_FF(true, true, false);
-    WG_FF(false, true, false);
-  }
-  if (op16) WG_FF(true, false, false);
-  WG_FF(false, false, false);
+  if (op16) WG_FF(true, false, false, false);
+  WG_FF(false, false, false, false);
 #undef WG_FF
 }
 

@@ -138,12 +138,15 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
         lib_loaded.lib().wg_set_wino_kn(96)
 
 
-def test_3x3_full_fold_kernel_with_the_plain_raw_layout(lib_loaded):
-    """WG_FF_P9=0 (an A/B knob: the full-fold kernel on the TM kernel's single-box raw layout) stays correct; the knob
-    is read once per process, hence the subprocess."""
-    env = dict(os.environ, WG_FF_P9="0")
+@pytest.mark.parametrize("knob", ["WG_FF_P9=0", "WG_FF_CG2=1"])
+def test_3x3_full_fold_kernel_experiment_knobs(lib_loaded, knob):
+    """The full-fold kernel's A/B knobs stay correct: WG_FF_P9=0 = the TM kernel's single-box raw layout, WG_FF_CG2=1 =
+    CTA pairs (tcgen05 cta_group::2, clusters of 2; measured slower, default off). The knobs are read once per process,
+    hence the subprocess."""
+    k, v = knob.split("=")
+    env = dict(os.environ, **{k: v})
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ff_check.py"), "--quick", "--kns", "96",
-                        "--iters", "3", "--out", os.path.join(ROOT, "gpurun_out", "ff_check_p9_0.json")],
+                        "--iters", "3", "--out", os.path.join(ROOT, "gpurun_out", "ff_check_" + k.lower() + ".json")],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
