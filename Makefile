@@ -7,7 +7,7 @@ ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude
 CSRC    := cuda-winograd_b200/csrc
 LIB     := cuda-winograd_b200/libwinograd_b200.so
-KSRCS   := $(CSRC)/winograd_kernels.cu $(CSRC)/wino_small_kernel.cu $(CSRC)/wino_tm_kernel.cu $(CSRC)/wino_ff_kernel.cu $(CSRC)/one_kernels.cu $(CSRC)/wg_api.cu $(CSRC)/legacy_entry.cu
+KSRCS   := $(CSRC)/winograd_kernels.cu $(CSRC)/wino_small_kernel.cu $(CSRC)/wino_tm_kernel.cu $(CSRC)/wino_ff_kernel.cu $(CSRC)/wino_ffw_kernel.cu $(CSRC)/one_kernels.cu $(CSRC)/wg_api.cu $(CSRC)/legacy_entry.cu
 HDRS    := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 all: $(LIB) Test

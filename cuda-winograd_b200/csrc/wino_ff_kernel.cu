@@ -20,86 +20,13 @@
 //
 // Numerically this is still F(2x2,3x3): the operands of every product are the TF32-rounded V = B^T d B and
 // U = G g G^T; only the order of the fp32 additions differs from the un-folded form.
-#include "ptx.cuh"
+#include "wino_ff_common.cuh"
 #include "wg_internal.h"
 
 #include <cuda.h>
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace wg {
-
-namespace ff {
-constexpr int kWorkerWarps = 8, kProducerWarp = 8, kMmaWarp = 9;
-constexpr int kRawRows = 48;                           // input rows (n*16+y) one 128-tile M-block can touch
-constexpr uint32_t kRawBytes = kRawRows * 2 * 8 * 32;  // [ny][x parity][x/2][8 ch] fp32 = 24576
-// P9 raw layout (conflict-free patch loads): four planes (y parity, x parity), each [24 row pairs][9 slots][8 ch] fp32
-// with slot = x/2 + 1 (slot 0 = the out-of-bounds column x/2 = -1, zero-filled, never read). The row pitch of 9 slots
-// puts the 32-byte slot of tile (ty, tx) at 9*(ty + dy/2) + tx + dx/2 + 1: with the tiles of an M-block numbered
-// right-to-left inside each tile row, consecutive tiles sit in consecutive slots modulo 8 -- also across the end of a
-// tile row -- so the 8 lanes of a quarter warp (16 bytes each, half selected by the 32-byte swizzle) hit 8 different
-// bank groups. (Only a quarter warp that straddles two IMAGES still pays a second wavefront.)
-constexpr uint32_t kPlaneBytes = 24 * 9 * 32;          // 6912 = 27 * 256
-constexpr uint32_t kRawBytesP9 = 4 * kPlaneBytes;      // 27648
-constexpr uint32_t kRawStride = kRawBytesP9;           // stage pitch of both layouts
-constexpr int kRawStages = 3, kUBufs = 4;
-constexpr int kKNmax = 96;
-constexpr uint32_t kAccStride = 96;                    // TMEM: accumulator (a,b) at column (2a+b)*96 ...
-constexpr uint32_t kVCol0 = 4 * kAccStride;            // ... V half jh at 384 + 64*jh, point (i, jj) at +8*(2i+jj)
-constexpr uint32_t kUChunkMax = 8 * 2 * kKNmax * 16;   // 8 points x [2 k-chunks][KN couts][16 B] = 24576
-constexpr int kEW = 32;                                // couts per epilogue chunk
-constexpr uint32_t kStgRow = 2 * kEW * 4 + 16;         // [2 px][32 couts] fp32 per tile, rows padded by 16 B
-constexpr uint32_t kStgBytes = 128 * kStgRow;
-constexpr uint32_t kOffRaw = 0;
-constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawStride;
-constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
-constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
-constexpr uint32_t kOffBar = kOffPix + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kRawStages + 8 + 2 + 4;
-constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
-constexpr uint32_t kTotal = kOffTmemPtr + 16;
-static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alignment");
-static_assert(kTotal <= 227 * 1024, "shared memory budget");
-
-// cout slices: ceil(K/96) of them, widths in multiples of 32 as even as possible, wider ones first
-// (256 = 96 + 96 + 64, 128 = 64 + 64, 512 = 4 x 96 + 2 x 64).
-__host__ __device__ inline int n_slices(int K) { return (K + 95) / 96; }
-struct Slice { int kn, c0; };  // width and first cout
-__host__ __device__ inline Slice slice(int K, int s) {
-  const int ns = n_slices(K), units = K / 32, base = units / ns, rem = units % ns;
-  return Slice{32 * (base + (s < rem ? 1 : 0)), 32 * (s * base + (s < rem ? s : rem))};
-}
-__host__ __device__ inline int slice_of(int K, int k) {
-  const int ns = n_slices(K), units = K / 32, base = units / ns, rem = units % ns;
-  const int wide = rem * (base + 1) * 32;
-  return k < wide ? k / ((base + 1) * 32) : rem + (k - wide) / (base * 32);
-}
-}  // namespace ff
-
-__device__ __forceinline__ float ff_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
-
-template <bool H16, bool CG2>
-__device__ __forceinline__ void ff_umma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  if constexpr (CG2) {
-    if constexpr (H16) umma_f16_ts_cg2(d_tmem, a_tmem, b_desc, idesc, accumulate);
-    else umma_tf32_ts_cg2(d_tmem, a_tmem, b_desc, idesc, accumulate);
-  } else {
-    if constexpr (H16) umma_f16_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
-    else umma_tf32_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
-  }
-}
-
-// two fp32 -> one 32-bit TMEM column of 16-bit operands (first value in the low half), round to nearest
-__device__ __forceinline__ float ff_pack16(float lo, float hi, int fp16) {
-  if (fp16) {
-    const __half2 h = __floats2half2_rn(lo, hi);
-    return __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
-  }
-  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
-  return __uint_as_float(*reinterpret_cast<const uint32_t*>(&b));
-}
 
 // H16: 16-bit operands (bf16, or fp16 with `fp16` set): V is stored in TMEM as packed pairs (column c = channels 2c
 // and 2c+1), tcgen05.mma kind::f16 with K = 16, so a V stage covers 16 channels = TWO 8-channel raw stages.
@@ -284,6 +211,11 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         const uint32_t idesc_neg = make_idesc(fmt, CG2 ? 256 : 128, kn, 1);  // D += (-A) * B
         // CG2: this CTA's shared memory holds kn/2 couts of every point
         const uint32_t u_per_point = (CG2 ? 1 : 2) * kn * 16, u_lbo = (CG2 ? kn / 2 : kn) * 16;
+        // slices of 64 or fewer couts leave room for a SECOND V stage in TMEM (4 x 64 accumulator columns + 2 x 128):
+        // the transform warps may then run a whole stage ahead of the MMAs. Accumulator p at p * acc_stride, V stage
+        // (g & 1) at v_col0 + 128 * (g & 1).
+        const bool db = !CG2 && kn <= 64;
+        const uint32_t acc_stride = db ? 64u : kAccStride, v_col0 = db ? 256u : kVCol0;
         if constexpr (CG2) mbar_wait_cluster(acc_empty, aph ^ 1);
         else mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
@@ -299,7 +231,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             tc_fence_after();
             WG_TS(ts_m, jh * 4 + 1);
             const uint32_t ua = u_base + us * kUChunkMax;
-            const uint32_t va = tmem_base + kVCol0 + jh * 64;
+            const uint32_t va = tmem_base + v_col0 + (db ? (g & 1) * 128 : 0u) + jh * 64;
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
               const int j = jh * 2 + jj;
@@ -318,7 +250,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                     const int sb = (b == 1 && j >= 2) ? -1 : 1;
                     const uint32_t p = (uint32_t)(2 * a + b);
                     if (!no_mma)
-                      ff_umma<H16, CG2>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
+                      ff_umma<H16, CG2>(tmem_base + p * acc_stride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
                                         (written >> p) & 1u);
                     written |= 1u << p;
                   }
@@ -373,6 +305,8 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
       const bool tvalid = row < valid_rows;
       const bool warp_active = quad * 32 < valid_rows;  // warp-uniform
+      const bool db = !CG2 && kn <= 64;                 // two V stages in TMEM (see the MMA thread)
+      const uint32_t acc_stride = db ? 64u : kAccStride, v_col0 = db ? 256u : kVCol0;
       const int n = T / 49, t = T % 49, ty = t / 7;
       const int tx = P9 ? 6 - t % 7 : t % 7;  // P9: tiles run right-to-left inside a tile row (see kPlaneBytes)
       const uint32_t raw_off = tvalid ? (uint32_t)((n * 16 + 2 * ty - ny0) * 512 + tx * 32) : 0u;
@@ -395,7 +329,11 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       for (int kb = 0; kb < n_kb; ++kb) {
         // this stage's ring slots are slot, slot + 1; the previous stage's (whose MMAs must have completed before a V
         // half is overwritten) pslot, pslot + 1, completing for the ((g - 1) >> 1)-th time
-        const uint32_t slot = (g & 1) * 2, pslot = slot ^ 2, pph = ((g - 1) >> 1) & 1;
+        // One V stage (slices wider than 64): the MMAs of stage g - 1 must have completed. Two V stages (db): those of
+        // stage g - 2, which used this stage's own ring slots. The first stage(s) of an item wait for nothing: this
+        // thread has passed the previous item's acc_full, i.e. every earlier MMA has completed.
+        const uint32_t slot = (g & 1) * 2, pslot = db ? slot : slot ^ 2, pph = ((g - (db ? 2u : 1u)) >> 1) & 1;
+        const bool wait_v = kb >= (db ? 2 : 1);
         if (!warp_active) {
           // nothing to transform: release the raw stage(s) and report "V ready" in step with the other warps
 #pragma unroll
@@ -406,7 +344,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
-            if (g > 0) wait_done(&done[pslot + jh], pph);
+            if (wait_v) wait_done(&done[pslot + jh], pph);
             if (lane == 0) arrive_leader(&full[slot + jh]);
           }
           ++g;
@@ -426,7 +364,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             if (sb == kSub - 1) {
 #pragma unroll
               for (int jh = 0; jh < 2; ++jh) {
-                if (g > 0) wait_done(&done[pslot + jh], pph);
+                if (wait_v) wait_done(&done[pslot + jh], pph);
                 if (lane == 0) arrive_leader(&full[slot + jh]);
               }
             }
@@ -469,12 +407,13 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 
           // row pass V = t B by halves (half jh = points with j in {2jh, 2jh+1}), round to the operand type, store into
           // TMEM (tf32: one column per channel; 16-bit: one column per channel pair, raw stage sb fills columns 4*sb..)
-          const uint32_t vcol = tmem_base + lane_base + kVCol0 + (uint32_t)(H16 ? sb * 4 + cq * 2 : cq * 4);
+          const uint32_t vcol = tmem_base + lane_base + v_col0 + (db ? (g & 1) * 128 : 0u) +
+                                (uint32_t)(H16 ? sb * 4 + cq * 2 : cq * 4);
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
             if (warp == 0 && lane == 0 && sb == kSub - 1) { WG_TS(ts_w, 2 + jh * 3); }
             if (sb == 0) {
-              if (g > 0) wait_done(&done[pslot + jh], pph);  // the MMAs that last read this V half have completed
+              if (wait_v) wait_done(&done[pslot + jh], pph);  // the MMAs that last read this V half have completed
               tc_fence_after();
             }
             if (warp == 0 && lane == 0 && sb == kSub - 1) { WG_TS(ts_w, 3 + jh * 3); }
@@ -538,10 +477,10 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
-            const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * kAccStride + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * acc_stride + (uint32_t)c0;
             float z[2][16];  // z[b][e] = Y[a][b]
             tmem_ld_x16(taddr, z[0]);
-            tmem_ld_x16(taddr + kAccStride, z[1]);
+            tmem_ld_x16(taddr + acc_stride, z[1]);
             tmem_ld_wait();
             if (ec == n_chunks - 1 && a == 1) {  // this warp has read its last accumulator columns
               tc_fence_before();
@@ -727,24 +666,12 @@ int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, 
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-template <bool H16, bool DBG, bool P9, bool CG2>
-static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                     int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream, int fp16,
-                     int dbg) {
-  static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
-  int dev_ = 0;
-  cudaGetDevice(&dev_);
-  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
-  if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16, DBG, P9, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
-        cudaSuccess)
-      return WG_ERR_CUDA;
-    configured |= dev_bit_;
-  }
+// Tiles per M-block and grid size. The MMA is always M=128 but only `mv` rows carry tiles; transform warps own 32 rows
+// each, so the per-item cost scales with ceil(mv/32) quarters: pick the mv that minimises waves x cost (WG_WINO_MV pins
+// it). cg2: one item per CTA pair.
+static void ff_plan(int n_img, int K, int max_ctas, bool cg2, int* mv_out, int* grid_out) {
   const int n_sl = ff::n_slices(K);
   const int total_tiles = n_img * 49;
-  // Tiles per M-block: the MMA is always M=128 but only `mv` rows carry tiles; transform warps own 32 rows each, so
-  // the per-item cost scales with ceil(mv/32) quarters. Pick the mv that minimises waves x cost (WG_WINO_MV pins it).
   int mv = 128;
   static int mv_env = -1;
   if (mv_env < 0) {
@@ -767,11 +694,31 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
     }
   }
   const int n_mblocks = (total_tiles + mv - 1) / mv;
-  const int n_items = (CG2 ? (n_mblocks + 1) / 2 : n_mblocks) * n_sl;  // CG2: one item per CTA pair
-  int grid = CG2 ? max_ctas / 2 : max_ctas;
+  const int n_items = (cg2 ? (n_mblocks + 1) / 2 : n_mblocks) * n_sl;
+  int grid = cg2 ? max_ctas / 2 : max_ctas;
   if (grid > n_items) grid = n_items;
   if (grid < 1) grid = 1;
-  if (CG2) grid *= 2;
+  if (cg2) grid *= 2;
+  *mv_out = mv;
+  *grid_out = grid;
+}
+
+template <bool H16, bool DBG, bool P9, bool CG2>
+static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                     int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream, int fp16,
+                     int dbg) {
+  static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
+  if (!(configured & dev_bit_)) {
+    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16, DBG, P9, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
+        cudaSuccess)
+      return WG_ERR_CUDA;
+    configured |= dev_bit_;
+  }
+  int mv = 128, grid = 1;
+  ff_plan(n_img, K, max_ctas, CG2, &mv, &grid);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(32 * (ff::kWorkerWarps + 2));
@@ -811,6 +758,21 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
     dbg = e ? atoi(e) : 0;
   }
   const int fp16 = op16 == 2;
+  // Sixteen transform warps, one group per V half (wino_ffw_kernel.cu). Measured at N=256: bf16 / fp16 operands
+  // 256->256 82.1 -> 77.9 us (there the transform chain is the longer one), 128->128 39.7 -> 40.1; TF32 256->256
+  // 98.5 -> 98.4, 128->128 47.1 -> 49.8 (1.5x the patch-load traffic on a shared-memory path that is already ~80 % busy).
+  // Default: 16-bit operands with C >= 256 only; WG_FF_W16=0|1 forces it off / on for everything.
+  static int w16 = -1;
+  if (w16 < 0) {
+    const char* e = getenv("WG_FF_W16");
+    w16 = e ? (atoi(e) != 0) : 2;
+  }
+  const bool use_w16 = w16 == 1 || (w16 == 2 && op16 != 0 && C >= 256);
+  if (use_w16 && !cg2 && dbg == 0 && wino_ff_p9()) {
+    int mv = 128, grid = 1;
+    ff_plan(n_img, K, max_ctas, false, &mv, &grid);
+    return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, relu, out_padded, mv, grid, stream);
+  }
 #define WG_FF(H16_, DBG_, P9_, CG2_)                                                                                \
   return launch_ff<H16_, DBG_, P9_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, \
                                           fp16, dbg)

@@ -1,0 +1,458 @@
+// Full-fold 3x3 Winograd kernel (see wino_ff_kernel.cu for the algorithm, the TMEM / shared-memory layout and the
+// barrier scheme) with SIXTEEN transform warps: one group of 8 warps per V half.
+//
+// In wino3x3_ff_kernel a transform thread owns a tile and 4 channels and produces BOTH V halves of a stage one after the
+// other (16 patch loads -> column pass -> row pass + TMEM stores of half 0 -> ... of half 1); that serial chain
+// (~2.1 k clk per 8-channel stage) is what the bf16 / fp16 kernel waits for, and what the TF32 kernel's MMA chain only
+// partially overlaps. Here warps 0-7 produce half 0 (points with j in {0,1}: patch columns 0..2) and warps 8-15 half 1
+// (j in {2,3}: patch columns 1..3), each thread loading 12 instead of 16 pixels: the two halves are transformed
+// concurrently, the per-stage chain of a thread shrinks to 12 loads + 48 + 32 FADDs + 8 TMEM stores, at the price of 1.5x
+// the patch-load traffic and a duplicated column pass for the two shared patch columns.
+//
+// Same filter image, tensor map, raw layout (parity planes, 9-slot pitch), accumulators and epilogue staging as the
+// 8-warp kernel; the epilogue splits the 32-cout chunk over the four warps that share a TMEM lane quadrant.
+// Replaces kernel_{128,256}_winograd_BtdB -> kernel_*_OuterProduct_* -> kernel_*_winograd_AtIA
+// (/root/reference/Kernel128_winograd.cu:28-213, Kernel256_winograd.cu:27-218).
+#include "wino_ff_common.cuh"
+#include "wg_internal.h"
+
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace wg {
+
+namespace ffw {
+constexpr int kWorkerWarps = 16, kProducerWarp = 16, kMmaWarp = 17;
+constexpr int kThreads = 32 * (kWorkerWarps + 2);
+}  // namespace ffw
+
+// Row pass V = t B for one V half. d[i][c] = column-pass output of patch column c + JH (c = 0..2):
+// JH = 0: points (i,0) = t0 - t2, (i,1) = t1 + t2; JH = 1: points (i,2) = t2 - t1, (i,3) = t1 - t3.
+template <int JH, bool H16>
+__device__ __forceinline__ void ffw_row_pass(const float (&d)[4][3][4], uint32_t vcol, int fp16) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v0[4], v1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = d[i][0][e], x1 = d[i][1][e], x2 = d[i][2][e];
+      v0[e] = JH ? x1 - x0 : x0 - x2;
+      v1[e] = JH ? x0 - x2 : x1 + x2;
+      if constexpr (!H16) v0[e] = ff_tf32(v0[e]), v1[e] = ff_tf32(v1[e]);
+    }
+    const uint32_t dst = vcol + (i * 2) * 8;
+    if constexpr (H16) {
+      tmem_st_x2(dst, ff_pack16(v0[0], v0[1], fp16), ff_pack16(v0[2], v0[3], fp16));
+      tmem_st_x2(dst + 8, ff_pack16(v1[0], v1[1], fp16), ff_pack16(v1[2], v1[3], fp16));
+    } else {
+      tmem_st_x4(dst, v0[0], v0[1], v0[2], v0[3]);
+      tmem_st_x4(dst + 8, v1[0], v1[1], v1[2], v1[3]);
+    }
+  }
+}
+
+template <bool H16>
+__global__ void __launch_bounds__(ffw::kThreads, 1)
+wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
+                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
+                   int C, int K, int relu, int out_padded, int mv, int fp16) {
+  using namespace ff;
+  using ffw::kMmaWarp;
+  using ffw::kProducerWarp;
+  using ffw::kWorkerWarps;
+  constexpr int kSub = H16 ? 2 : 1;       // 8-channel raw stages per V stage
+  const bool mc = (out_padded & 2) != 0;  // y is an NVLS multicast address: stores go out as multimem.st
+  out_padded &= 1;
+  pdl_launch_dependents();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* raw_full = bars;
+  uint64_t* raw_empty = raw_full + kRawStages;
+  uint64_t* full = raw_empty + kRawStages;  // [2 * (stage & 1) + half]: V half stored (8 warps) + filter chunk landed
+  uint64_t* done = full + 4;                // [same]: that half's 18 MMAs have completed
+  uint64_t* acc_full = done + 4;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
+  int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < kRawStages; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], kWorkerWarps);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full[i], kWorkerWarps / 2 + 1);
+      mbar_init(&done[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kWorkerWarps);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_kb = C / (8 * kSub);
+  const int n_sl = n_slices(K);
+  const int total_tiles = n_img * 49;
+  const int n_mblocks = (total_tiles + mv - 1) / mv;
+  const int n_items = n_mblocks * n_sl;
+  const int item0 = blockIdx.x, item_step = gridDim.x;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t rs = 0, rph = 0, us = 0, uph = 0;
+      int u_primed = 0;
+      if (item0 < n_items) {  // the filter does not depend on the previous kernel in the stream
+        const Slice sl = slice(K, item0 % n_sl);
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * sl.c0;
+        for (int h = 0; h < 2; ++h) {
+          mbar_arrive_expect_tx(&full[us], 256u * sl.kn);
+          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (size_t)h * 256 * sl.kn, 256u * sl.kn, &full[us]);
+          ++us;
+        }
+        u_primed = 1;
+      }
+      pdl_wait();
+      for (int item = item0; item < n_items; item += item_step) {
+        const Slice sl = slice(K, item % n_sl);
+        const int kn = sl.kn;
+        const int t0 = (item / n_sl) * mv;
+        const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * sl.c0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+#pragma unroll
+          for (int sb = 0; sb < kSub; ++sb) {
+            mbar_wait(&raw_empty[rs], rph ^ 1);
+            mbar_arrive_expect_tx(&raw_full[rs], kRawBytesP9);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)  // plane q = (y parity q>>1, x parity q&1); x/2 starts at -1 (zero-filled)
+              tma_tensor_5d_g2s(smem + kOffRaw + rs * kRawStride + q * kPlaneBytes, &tmap_x, (kb * kSub + sb) * 8, -1,
+                                q & 1, q >> 1, ny0 >> 1, &raw_full[rs]);
+            if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          }
+          if (u_primed) {
+            u_primed = 0;
+            continue;
+          }
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&done[us], uph ^ 1);
+            mbar_arrive_expect_tx(&full[us], 256u * kn);
+            tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)kb * 2 + h) * 256 * kn, 256u * kn,
+                         &full[us]);
+            if (++us == kUBufs) { us = 0; uph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    if (elect_one()) {
+      const uint32_t u_base = smem_u32(smem + kOffU);
+      uint32_t us = 0, uph = 0, aph = 0;
+      for (int item = item0; item < n_items; item += item_step) {
+        const uint32_t kn = (uint32_t)slice(K, item % n_sl).kn;
+        const uint32_t fmt = H16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
+        const uint32_t idesc_pos = make_idesc(fmt, 128, kn);
+        const uint32_t idesc_neg = make_idesc(fmt, 128, kn, 1);  // D += (-A) * B
+        const uint32_t u_per_point = 2 * kn * 16, u_lbo = kn * 16;
+        mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
+        tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb) {
+          uint32_t written = kb > 0 ? 0xFu : 0u;  // bit p set = accumulator p has been written in this item
+#pragma unroll
+          for (int jh = 0; jh < 2; ++jh) {
+            mbar_wait(&full[us], uph);  // filter chunk landed and V half stored by its 8 transform warps
+            tc_fence_after();
+            const uint32_t ua = u_base + us * kUChunkMax;
+            const uint32_t va = tmem_base + kVCol0 + jh * 64;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = jh * 2 + jj;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t a_tm = va + (i * 2 + jj) * 8;
+                const uint64_t b_desc = make_smem_desc(ua + (i * 2 + jj) * u_per_point, u_lbo, 128, kLayoutNone);
+                // A^T = [[1,1,1,0],[0,1,-1,-1]]: row a uses point index i with sign sa, column b uses j with sign sb
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                  if ((a == 0 && i == 3) || (a == 1 && i == 0)) continue;
+                  const int sa = (a == 1 && i >= 2) ? -1 : 1;
+#pragma unroll
+                  for (int b = 0; b < 2; ++b) {
+                    if ((b == 0 && j == 3) || (b == 1 && j == 0)) continue;
+                    const int sb = (b == 1 && j >= 2) ? -1 : 1;
+                    const uint32_t p = (uint32_t)(2 * a + b);
+                    ff_umma<H16, false>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
+                                        (written >> p) & 1u);
+                    written |= 1u << p;
+                  }
+                }
+              }
+            }
+            umma_commit(&done[us]);  // frees the filter chunk and this V half
+            if (++us == kUBufs) { us = 0; uph ^= 1; }
+          }
+        }
+        umma_commit(acc_full);
+        aph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ transform + epilogue warps
+    // thread = (tile = TMEM lane, channel half cq, V half jh): warp w owns TMEM lanes 32*(w&3)..+31
+    const int quad = warp & 3;
+    const int cq = (warp >> 2) & 1;
+    const int jh = warp >> 3;
+    const int esub = warp >> 2;  // epilogue: which 8 couts of a 32-cout chunk
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t raw_base = smem_u32(smem + kOffRaw);
+    const uint32_t stg_base = smem_u32(smem + kOffStg);
+
+    uint32_t rs = 0, rph = 0, g = 0, aph = 0;  // g = V stages transformed (same counting as the MMA thread)
+    for (int item = item0; item < n_items; item += item_step) {
+      const Slice sl = slice(K, item % n_sl);
+      const int kn = sl.kn, c0s = sl.c0;
+      const int t0 = (item / n_sl) * mv;
+      const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+      const int T = t0 + row;
+      const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
+      const bool tvalid = row < valid_rows;
+      const bool warp_active = quad * 32 < valid_rows;  // warp-uniform
+      const int n = T / 49, t = T % 49, ty = t / 7;
+      const int tx = 6 - t % 7;  // tiles run right-to-left inside a tile row (conflict-free slots, wino_ff_common.cuh)
+      // byte offset, inside the raw stage, of patch pixel (dy, c + jh) for c = 0..2: plane (dy&1, dx&1) + slot + half
+      uint32_t poff[2][3];  // [dy >> 1][c]; add (dy & 1) * 2 * kPlaneBytes
+      {
+        const uint32_t s0 = tvalid ? (uint32_t)(((n * 16 + 2 * ty - ny0) >> 1) * 9 + tx + 1) : 1u;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const uint32_t dx = (uint32_t)(c + jh);
+            const uint32_t slot = s0 + 9 * a + (dx >> 1);
+            poff[a][c] = (dx & 1) * kPlaneBytes + slot * 32 + (uint32_t)((cq ^ ((slot >> 2) & 1)) * 16);
+          }
+      }
+
+      for (int kb = 0; kb < n_kb; ++kb) {
+        // this stage's ring slot for this half; the previous stage's (whose MMAs must have completed before the V half
+        // is overwritten) completes for the ((g - 1) >> 1)-th time
+        const uint32_t slot = (g & 1) * 2 + jh, pslot = slot ^ 2, pph = ((g - 1) >> 1) & 1;
+        if (!warp_active) {
+#pragma unroll
+          for (int sb = 0; sb < kSub; ++sb) {
+            mbar_wait(&raw_full[rs], rph);
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);
+            if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          }
+          if (g > 0) mbar_wait(&done[pslot], pph);
+          if (lane == 0) mbar_arrive(&full[slot]);
+          ++g;
+          continue;
+        }
+#pragma unroll
+        for (int sb = 0; sb < kSub; ++sb) {  // H16: two 8-channel raw stages fill one 16-channel V stage
+          mbar_wait(&raw_full[rs], rph);
+          float d[4][3][4];  // patch columns c + jh, c = 0..2
+          if (tvalid) {
+            const uint32_t a = raw_base + rs * kRawStride;
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const float4 v = ld_shared_v4(a + (dy & 1) * 2 * kPlaneBytes + poff[dy >> 1][c]);
+                d[dy][c][0] = v.x, d[dy][c][1] = v.y, d[dy][c][2] = v.z, d[dy][c][3] = v.w;
+              }
+          } else {
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d[dy][c][e] = 0.f;
+          }
+          // column pass t = B^T d, in place over dy
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float d0 = d[0][c][e], d1 = d[1][c][e], d2 = d[2][c][e], d3 = d[3][c][e];
+              d[0][c][e] = d0 - d2;
+              d[1][c][e] = d1 + d2;
+              d[2][c][e] = d2 - d1;
+              d[3][c][e] = d1 - d3;
+            }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&raw_empty[rs]);  // the raw stage is in registers now
+          if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+
+          // row pass for this half, rounded to the operand type and stored into TMEM (tf32: one column per channel;
+          // 16-bit: one column per channel pair, raw stage sb fills columns 4*sb..)
+          if (sb == 0) {
+            if (g > 0) mbar_wait(&done[pslot], pph);  // the MMAs that last read this V half have completed
+            tc_fence_after();
+          }
+          const uint32_t vcol = tmem_base + lane_base + kVCol0 + jh * 64 + (uint32_t)(H16 ? sb * 4 + cq * 2 : cq * 4);
+          if (jh == 0) ffw_row_pass<0, H16>(d, vcol, fp16);  // warp-uniform
+          else ffw_row_pass<1, H16>(d, vcol, fp16);
+          if (sb == kSub - 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[slot]);
+          }
+        }  // sb
+        ++g;
+      }
+
+      // ---- epilogue: the accumulators ARE the output pixels; BN, ReLU, staged per (32 couts, output row a), full runs
+      // per pixel. The four warps of a TMEM lane quadrant take 8 couts of the chunk each and share barrier 1 + quad.
+      const int W = out_padded ? 16 : 14;
+      const int o = out_padded ? 1 : 0;
+      const int pix0 = tvalid ? ((n * W + 2 * ty + o) * W + 2 * tx + o) : -1;  // first output pixel of this tile
+      if (esub == 0) pixtab[row] = pix0;
+      const int n_chunks = kn / kEW;
+      const int qrows = min(32, valid_rows - quad * 32);  // real tiles among this quadrant's rows (<= 0: none)
+      const int tid128 = esub * 32 + lane;
+
+      mbar_wait(acc_full, aph);
+      aph ^= 1;
+      tc_fence_after();
+      if (warp_active) {
+#pragma unroll 1
+        for (int ec = 0; ec < n_chunks; ++ec) {
+          const int cl = esub * 8;       // cout inside the chunk
+          const int c0 = ec * kEW + cl;  // cout inside the slice
+          float sc[8], sh[8];
+#pragma unroll
+          for (int q4 = 0; q4 < 2; ++q4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c0s + c0 + 4 * q4));
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(shift + c0s + c0 + 4 * q4));
+            sc[4 * q4] = s4.x, sc[4 * q4 + 1] = s4.y, sc[4 * q4 + 2] = s4.z, sc[4 * q4 + 3] = s4.w;
+            sh[4 * q4] = h4.x, sh[4 * q4 + 1] = h4.y, sh[4 * q4 + 2] = h4.z, sh[4 * q4 + 3] = h4.w;
+          }
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * kAccStride + (uint32_t)c0;
+            float z[2][8];  // z[b][e] = Y[a][b]
+            tmem_ld_x8(taddr, z[0]);
+            tmem_ld_x8(taddr + kAccStride, z[1]);
+            tmem_ld_wait();
+            if (ec == n_chunks - 1 && a == 1) {  // this warp has read its last accumulator columns
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_empty);
+            }
+            const uint32_t sdst = stg_base + (uint32_t)row * kStgRow + (uint32_t)cl * 4;
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+              for (int q4 = 0; q4 < 2; ++q4) {
+                float ov[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  ov[e] = fmaf(sc[4 * q4 + e], z[b][4 * q4 + e], sh[4 * q4 + e]);
+                  if (relu) ov[e] = fmaxf(ov[e], 0.f);
+                }
+                st_shared_v4(sdst + b * (4 * kEW) + 16 * q4, ov[0], ov[1], ov[2], ov[3]);
+              }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");  // this quadrant's staging rows (+ pixtab) complete
+            {
+              const int units = qrows * 16;  // (tile, pixel b, 16-byte chunk)
+              float* ybase = y + c0s + ec * kEW + (size_t)a * W * K;
+              for (int u = tid128; u < units; u += 128) {
+                const int tile = quad * 32 + (u >> 4);
+                const int b = (u >> 3) & 1;
+                const int ch = u & 7;
+                const float4 v = ld_shared_v4(stg_base + (uint32_t)tile * kStgRow + (uint32_t)(b * 128 + ch * 16));
+                st_out_v4(ybase + (size_t)(pixtab[tile] + b) * K + ch * 4, v, mc);
+              }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");  // staging rows free again
+          }
+        }
+        if (out_padded && tvalid && (ty == 0 || ty == 6 || tx == 0 || tx == 6)) {
+          // zero border of the reference's 16x16 frame (Kernel128_winograd.cu:163,243): edge tiles own their share
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const size_t rstride = (size_t)W * K;
+          const int ncc = kn / 4;
+          float* p = y + (size_t)pix0 * K + c0s + esub * ncc;
+          const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
+          const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
+#pragma unroll 1
+          for (int e = 0; e < ncc; e += 4) {
+            if (dyb != 0) {
+              st_out_v4(p + dyb + e, z4, mc);
+              st_out_v4(p + dyb + K + e, z4, mc);
+            }
+            if (dxb != 0) {
+              st_out_v4(p + dxb + e, z4, mc);
+              st_out_v4(p + dxb + rstride + e, z4, mc);
+            }
+            if (dyb != 0 && dxb != 0) st_out_v4(p + dyb + dxb + e, z4, mc);
+          }
+        }
+      } else {
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+
+template <bool H16>
+static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                      int n_img, int C, int K, int relu, int out_padded, int mv, int grid, cudaStream_t stream,
+                      int fp16) {
+  static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
+  if (!(configured & dev_bit_)) {
+    if (cudaFuncSetAttribute(wino3x3_ffw_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
+        cudaSuccess)
+      return WG_ERR_CUDA;
+    configured |= dev_bit_;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(ffw::kThreads);
+  cfg.dynamicSmemBytes = ff::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ffw_kernel<H16>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
+                                     out_padded, mv, fp16);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+int wino_ffw_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
+                    int n_img, int C, int K, int op16, int relu, int out_padded, int mv, int grid,
+                    cudaStream_t stream) {
+  if (op16) return launch_ffw<true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, mv, grid, stream, op16 == 2);
+  return launch_ffw<false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, mv, grid, stream, 0);
+}
+
+}  // namespace wg

@@ -110,7 +110,7 @@ TOL_BF16 = 1e-2
 
 @pytest.mark.parametrize("kn", [96, 48, 64])
 @pytest.mark.parametrize("n,c,k", [(40, 64, 256), (33, 32, 96), (50, 24, 160), (20, 16, 512), (64, 128, 128),
-                                   (131, 48, 192), (37, 8, 32), (29, 40, 64), (300, 16, 32)])
+                                   (131, 48, 192), (37, 8, 32), (29, 40, 64), (300, 16, 32), (24, 256, 128)])
 def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
     """Every throughput kernel on batches that do not fill the last 128-tile M-block and on every cout-slice width:
     kn = 96 the full-fold kernel (wino_ff_kernel.cu: 4 accumulators, slices of 96 / 64 / 32 -- the default), kn = 48 the
@@ -138,13 +138,15 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
         lib_loaded.lib().wg_set_wino_kn(96)
 
 
-@pytest.mark.parametrize("knob", ["WG_FF_P9=0", "WG_FF_CG2=1"])
+@pytest.mark.parametrize("knob", ["WG_FF_P9=0", "WG_FF_CG2=1", "WG_FF_W16=1", "WG_FF_W16=0"])
 def test_3x3_full_fold_kernel_experiment_knobs(lib_loaded, knob):
     """The full-fold kernel's A/B knobs stay correct: WG_FF_P9=0 = the TM kernel's single-box raw layout, WG_FF_CG2=1 =
-    CTA pairs (tcgen05 cta_group::2, clusters of 2; measured slower, default off). The knobs are read once per process,
-    hence the subprocess."""
+    CTA pairs (tcgen05 cta_group::2, clusters of 2; measured slower, default off), WG_FF_W16=1 / 0 = sixteen transform
+    warps (wino_ffw_kernel.cu) for every layer / for none (default: 16-bit operands with C >= 256). The knobs are read
+    once per process, hence the subprocess."""
     k, v = knob.split("=")
     env = dict(os.environ, **{k: v})
+    k = k + "_" + v
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ff_check.py"), "--quick", "--kns", "96",
                         "--iters", "3", "--out", os.path.join(ROOT, "gpurun_out", "ff_check_" + k.lower() + ".json")],
                        env=env, capture_output=True, text=True, timeout=600)
