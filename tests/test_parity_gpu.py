@@ -133,6 +133,10 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
             assert golden.rel_err(y, gold) <= tol
             np.testing.assert_array_equal(yp[:, 1:15, 1:15], y)
             assert np.all(yp[:, 0] == 0) and np.all(yp[:, 15] == 0) and np.all(yp[:, :, 0] == 0) and np.all(yp[:, :, 15] == 0)
+            # run to run: bit-identical (fixed accumulation order, no atomics; a hand-off race would show up here)
+            y0 = layer(xd)
+            for _ in range(8):
+                assert torch.equal(layer(xd), y0)
             layer.close()
     finally:
         lib_loaded.lib().wg_set_wino_kn(96)
