@@ -61,6 +61,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time; test_wait returns at once).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: a pipeline bug must surface as a trapped kernel (launch error), never as a hung GPU.
 #ifndef WG_WAIT_TIMEOUT_NS
 #define WG_WAIT_TIMEOUT_NS 4000000000ull
@@ -208,6 +221,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// Same without the cluster-scope release: for hand-offs whose payload is NOT ordinary memory (data in TMEM, ordered by
+// tcgen05.fence::before_thread_sync / after_thread_sync on the two sides; the form CUTLASS's ClusterBarrier::arrive uses).
+__device__ __forceinline__ void mbar_arrive_remote_plain(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

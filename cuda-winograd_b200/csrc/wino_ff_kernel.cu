@@ -173,8 +173,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             continue;
           }
           for (int h = 0; h < 2; ++h) {
-            if constexpr (CG2) mbar_wait_cluster(&done[us], uph ^ 1);
-            else mbar_wait(&done[us], uph ^ 1);
+            mbar_wait(&done[us], uph ^ 1);
             uint64_t* ubar = peer ? &u_land[us] : &full[us];
             if (no_u) {
               mbar_arrive(ubar);
@@ -197,13 +196,15 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         for (int item = item0; item < n_items; item += item_step)
           for (int c = 0; c < 2 * n_kb; ++c) {
             mbar_wait(&u_land[us], uph);
-            mbar_arrive_remote(&full[us], 0);
+            mbar_arrive_remote_plain(&full[us], 0);
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
       }
     } else if (elect_one()) {
       const uint32_t u_base = smem_u32(smem + kOffU);
       uint32_t g = 0, us = 0, uph = 0, aph = 0;  // g = V stages issued (V phase = g & 1)
+      // (Probing the next half's barrier with mbarrier.test_wait while 6 of the 18 MMAs were still to be issued, so
+      //  that the ~90 clk of an already-complete try_wait stay off the issue path, was measured: no gain.)
       for (int item = item0; item < n_items; item += item_step) {
         const uint32_t kn = (uint32_t)slice(K, item % n_sl).kn;
         const uint32_t fmt = H16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
@@ -216,8 +217,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         // (g & 1) at v_col0 + 128 * (g & 1).
         const bool db = !CG2 && kn <= 64;
         const uint32_t acc_stride = db ? 64u : kAccStride, v_col0 = db ? 256u : kVCol0;
-        if constexpr (CG2) mbar_wait_cluster(acc_empty, aph ^ 1);
-        else mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
+        mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
         for (int kb = 0; kb < n_kb; ++kb) {
           // bit p set = accumulator p has been written in this item (first MMA into it overwrites)
@@ -226,8 +226,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           for (int jh = 0; jh < 2; ++jh) {
             WG_TS(ts_m, jh * 4 + 0);
             // filter chunk landed and V half stored by all transform warps (of both CTAs)
-            if constexpr (CG2) mbar_wait_cluster(&full[us], uph);
-            else mbar_wait(&full[us], uph);
+            mbar_wait(&full[us], uph);
             tc_fence_after();
             WG_TS(ts_m, jh * 4 + 1);
             const uint32_t ua = u_base + us * kUChunkMax;
@@ -282,12 +281,11 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     uint32_t rs = 0, rph = 0, g = 0, aph = 0;  // g = V stages transformed (same counting as the MMA thread)
     // CG2: full[] / acc_empty live in the leader CTA; done[] / acc_full are signalled by the leader's multicast commit
     auto arrive_leader = [&](uint64_t* bar) {
-      if (peer) mbar_arrive_remote(bar, 0);
+      if (peer) mbar_arrive_remote_plain(bar, 0);
       else mbar_arrive(bar);
     };
     auto wait_done = [&](uint64_t* bar, uint32_t parity) {
-      if constexpr (CG2) mbar_wait_cluster(bar, parity);
-      else mbar_wait(bar, parity);
+      mbar_wait(bar, parity);  // payload is TMEM state, ordered by the tcgen05 fences around the wait
     };
     // dbg & 64 (with 16): every CTA records clock64() at item start / main loop end / epilogue end of its first four
     // items: long long y[4096 + 16 * blockIdx.x + 4 * item_index + {0, 1, 2}], slot 3 = item number
@@ -630,10 +628,15 @@ int wino_ff_p9() {
 }
 
 // CTA pairs (cta_group::2) for layers created from now on: WG_FF_CG2=1. Needs the parity-plane raw layout.
-// EXPERIMENT, default off. Measured (N=256, B200): 256->256 TF32 163 us against 99 us for single CTAs, bf16 118 against
-// 83, 128->128 84 against 48: with V single-buffered in TMEM every half-stage hand-off (V stored -> MMA -> V free) now
-// crosses the SM pair twice (remote mbarrier arrive, multicast commit), and that round trip, not the shared-memory
-// traffic the pairing halves, sets the stage time. Results are bit-identical to the single-CTA kernel.
+// EXPERIMENT, default off; results are bit-identical to the single-CTA kernel. Measured (N=256, B200, us):
+//                          256->256 tf32 | bf16 | 128->128 tf32 | bf16
+//   single CTAs                 97.8-98.7 | 83.9 |     47.0      | 37.8
+//   pairs, first version            163.4 | 118.3|     84.2      | 61.6   hand-off barriers with .release.cluster /
+//                                                                         .acquire.cluster: ~1 k clk per hand-off
+//   pairs, plain arrive / wait  96.8-96.9 | 85.1 |     47.6      | 40.4   (the payload is TMEM state, ordered by the
+//                                                                         tcgen05 fences on both sides)
+//   pairs + 16 transform warps       96.7 | 79.2 |     50.5      | 40.9
+// i.e. halving the B-operand reads and the filter traffic per SM buys 1 % on the shape it was built for.
 int wino_ff_cg2() {
   static int v = -1;
   if (v < 0) {
@@ -768,10 +771,10 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
     w16 = e ? (atoi(e) != 0) : 2;
   }
   const bool use_w16 = w16 == 1 || (w16 == 2 && op16 != 0 && C >= 256);
-  if (use_w16 && !cg2 && dbg == 0 && wino_ff_p9()) {
+  if (use_w16 && dbg == 0 && wino_ff_p9()) {
     int mv = 128, grid = 1;
-    ff_plan(n_img, K, max_ctas, false, &mv, &grid);
-    return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, relu, out_padded, mv, grid, stream);
+    ff_plan(n_img, K, max_ctas, cg2 != 0, &mv, &grid);
+    return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, cg2, relu, out_padded, mv, grid, stream);
   }
 #define WG_FF(H16_, DBG_, P9_, CG2_)                                                                                \
   return launch_ff<H16_, DBG_, P9_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, \

@@ -51,7 +51,9 @@ __device__ __forceinline__ void ffw_row_pass(const float (&d)[4][3][4], uint32_t
   }
 }
 
-template <bool H16>
+// CG2: CTA pairs (clusters of 2, tcgen05 cta_group::2), exactly as in wino3x3_ff_kernel: neighbouring M-blocks, same cout
+// slice, MMAs with M = 256 issued by the leader CTA, each CTA supplying half of the couts of every filter chunk.
+template <bool H16, bool CG2>
 __global__ void __launch_bounds__(ffw::kThreads, 1)
 wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
@@ -75,6 +77,9 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
   uint64_t* done = full + 4;                // [same]: that half's 18 MMAs have completed
   uint64_t* acc_full = done + 4;
   uint64_t* acc_empty = acc_full + 1;
+  uint64_t* u_land = acc_empty + 1;  // [4] CG2, peer CTA only: its half of a filter chunk has landed
+  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
+  const bool peer = CG2 && crank != 0;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
 
@@ -85,16 +90,22 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       mbar_init(&raw_empty[i], kWorkerWarps);
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], kWorkerWarps / 2 + 1);
+      // CG2 (leader): the half's 8 warps of both CTAs + own TMA bytes + the peer's relay
+      mbar_init(&full[i], CG2 ? kWorkerWarps + 2 : kWorkerWarps / 2 + 1);
       mbar_init(&done[i], 1);
+      mbar_init(&u_land[i], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kWorkerWarps);
+    mbar_init(acc_empty, CG2 ? 2 * kWorkerWarps : kWorkerWarps);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr);
+  if (warp == kMmaWarp) {
+    if constexpr (CG2) tmem_alloc_cg2<512>(tmem_ptr);
+    else tmem_alloc<512>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all();  // the peer's barriers exist before anybody arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -102,8 +113,9 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
   const int n_sl = n_slices(K);
   const int total_tiles = n_img * 49;
   const int n_mblocks = (total_tiles + mv - 1) / mv;
-  const int n_items = n_mblocks * n_sl;
-  const int item0 = blockIdx.x, item_step = gridDim.x;
+  const int n_items = (CG2 ? (n_mblocks + 1) / 2 : n_mblocks) * n_sl;  // CG2: one item per CTA pair
+  const int item0 = CG2 ? blockIdx.x / 2 : blockIdx.x, item_step = CG2 ? gridDim.x / 2 : gridDim.x;
+  const uint32_t u_bytes_per_kn = CG2 ? 128u : 256u;  // bytes of a filter chunk this CTA loads, per cout of the slice
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
@@ -114,8 +126,10 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
         const Slice sl = slice(K, item0 % n_sl);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * sl.c0;
         for (int h = 0; h < 2; ++h) {
-          mbar_arrive_expect_tx(&full[us], 256u * sl.kn);
-          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (size_t)h * 256 * sl.kn, 256u * sl.kn, &full[us]);
+          uint64_t* ubar = peer ? &u_land[us] : &full[us];
+          mbar_arrive_expect_tx(ubar, u_bytes_per_kn * sl.kn);
+          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)h * 256 + crank * 128) * sl.kn,
+                       u_bytes_per_kn * sl.kn, ubar);
           ++us;
         }
         u_primed = 1;
@@ -124,7 +138,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       for (int item = item0; item < n_items; item += item_step) {
         const Slice sl = slice(K, item % n_sl);
         const int kn = sl.kn;
-        const int t0 = (item / n_sl) * mv;
+        const int t0 = (CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl) * mv;
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * sl.c0;
         for (int kb = 0; kb < n_kb; ++kb) {
@@ -144,9 +158,10 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
           }
           for (int h = 0; h < 2; ++h) {
             mbar_wait(&done[us], uph ^ 1);
-            mbar_arrive_expect_tx(&full[us], 256u * kn);
-            tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)kb * 2 + h) * 256 * kn, 256u * kn,
-                         &full[us]);
+            uint64_t* ubar = peer ? &u_land[us] : &full[us];
+            mbar_arrive_expect_tx(ubar, u_bytes_per_kn * kn);
+            tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (((size_t)kb * 2 + h) * 256 + crank * 128) * kn,
+                         u_bytes_per_kn * kn, ubar);
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
         }
@@ -154,22 +169,34 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one elected thread)
-    if (elect_one()) {
+    if (peer) {
+      // CG2, peer CTA: no MMAs to issue here; relay "my half of filter chunk us has landed" to the leader's full[us]
+      if (elect_one()) {
+        uint32_t us = 0, uph = 0;
+        for (int item = item0; item < n_items; item += item_step)
+          for (int c = 0; c < 2 * n_kb; ++c) {
+            mbar_wait(&u_land[us], uph);
+            mbar_arrive_remote_plain(&full[us], 0);
+            if (++us == kUBufs) { us = 0; uph ^= 1; }
+          }
+      }
+    } else if (elect_one()) {
       const uint32_t u_base = smem_u32(smem + kOffU);
       uint32_t us = 0, uph = 0, aph = 0;
       for (int item = item0; item < n_items; item += item_step) {
         const uint32_t kn = (uint32_t)slice(K, item % n_sl).kn;
         const uint32_t fmt = H16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
-        const uint32_t idesc_pos = make_idesc(fmt, 128, kn);
-        const uint32_t idesc_neg = make_idesc(fmt, 128, kn, 1);  // D += (-A) * B
-        const uint32_t u_per_point = 2 * kn * 16, u_lbo = kn * 16;
+        const uint32_t idesc_pos = make_idesc(fmt, CG2 ? 256 : 128, kn);
+        const uint32_t idesc_neg = make_idesc(fmt, CG2 ? 256 : 128, kn, 1);  // D += (-A) * B
+        // CG2: this CTA's shared memory holds kn/2 couts of every point
+        const uint32_t u_per_point = (CG2 ? 1 : 2) * kn * 16, u_lbo = (CG2 ? kn / 2 : kn) * 16;
         mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
         for (int kb = 0; kb < n_kb; ++kb) {
           uint32_t written = kb > 0 ? 0xFu : 0u;  // bit p set = accumulator p has been written in this item
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
-            mbar_wait(&full[us], uph);  // filter chunk landed and V half stored by its 8 transform warps
+            mbar_wait(&full[us], uph);  // filter chunk landed and V half stored by its transform warps
             tc_fence_after();
             const uint32_t ua = u_base + us * kUChunkMax;
             const uint32_t va = tmem_base + kVCol0 + jh * 64;
@@ -190,18 +217,20 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
                     if ((b == 0 && j == 3) || (b == 1 && j == 0)) continue;
                     const int sb = (b == 1 && j >= 2) ? -1 : 1;
                     const uint32_t p = (uint32_t)(2 * a + b);
-                    ff_umma<H16, false>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
+                    ff_umma<H16, CG2>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
                                         (written >> p) & 1u);
                     written |= 1u << p;
                   }
                 }
               }
             }
-            umma_commit(&done[us]);  // frees the filter chunk and this V half
+            if constexpr (CG2) umma_commit_mcast_cg2(&done[us], 3);  // frees the filter chunk and this V half, both CTAs
+            else umma_commit(&done[us]);
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
         }
-        umma_commit(acc_full);
+        if constexpr (CG2) umma_commit_mcast_cg2(acc_full, 3);
+        else umma_commit(acc_full);
         aph ^= 1;
       }
     }
@@ -218,10 +247,16 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
     const uint32_t stg_base = smem_u32(smem + kOffStg);
 
     uint32_t rs = 0, rph = 0, g = 0, aph = 0;  // g = V stages transformed (same counting as the MMA thread)
+    // CG2: full[] / acc_empty live in the leader CTA (the payload of these hand-offs is TMEM state, ordered by the
+    // tcgen05 fences, so a plain remote arrive will do); done[] / acc_full arrive by the leader's multicast commit
+    auto arrive_leader = [&](uint64_t* bar) {
+      if (peer) mbar_arrive_remote_plain(bar, 0);
+      else mbar_arrive(bar);
+    };
     for (int item = item0; item < n_items; item += item_step) {
       const Slice sl = slice(K, item % n_sl);
       const int kn = sl.kn, c0s = sl.c0;
-      const int t0 = (item / n_sl) * mv;
+      const int t0 = (CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl) * mv;
       const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
       const int T = t0 + row;
       const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
@@ -255,7 +290,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
             if (++rs == kRawStages) { rs = 0; rph ^= 1; }
           }
           if (g > 0) mbar_wait(&done[pslot], pph);
-          if (lane == 0) mbar_arrive(&full[slot]);
+          if (lane == 0) arrive_leader(&full[slot]);
           ++g;
           continue;
         }
@@ -308,7 +343,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[slot]);
+            if (lane == 0) arrive_leader(&full[slot]);
           }
         }  // sb
         ++g;
@@ -350,7 +385,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
             if (ec == n_chunks - 1 && a == 1) {  // this warp has read its last accumulator columns
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(acc_empty);
+              if (lane == 0) arrive_leader(acc_empty);
             }
             const uint32_t sdst = stg_base + (uint32_t)row * kStgRow + (uint32_t)cl * 4;
 #pragma unroll
@@ -402,20 +437,24 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
           }
         }
       } else {
-        if (lane == 0) mbar_arrive(acc_empty);
+        if (lane == 0) arrive_leader(acc_empty);
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+  if constexpr (CG2) cluster_sync_all();  // the peer's shared memory, TMEM and barriers stay alive until the pair is done
+  else __syncthreads();
+  if (warp == kMmaWarp) {
+    if constexpr (CG2) tmem_dealloc_cg2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 
-template <bool H16>
+template <bool H16, bool CG2>
 static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                       int n_img, int C, int K, int relu, int out_padded, int mv, int grid, cudaStream_t stream,
                       int fp16) {
@@ -424,7 +463,7 @@ static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* 
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_ffw_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
+    if (cudaFuncSetAttribute(wino3x3_ffw_kernel<H16, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
         cudaSuccess)
       return WG_ERR_CUDA;
     configured |= dev_bit_;
@@ -434,8 +473,15 @@ static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* 
   cfg.blockDim = dim3(ffw::kThreads);
   cfg.dynamicSmemBytes = ff::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int na = 0;
+  if (CG2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -443,16 +489,23 @@ static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ffw_kernel<H16>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ffw_kernel<H16, CG2>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
                                      out_padded, mv, fp16);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_ffw_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                    int n_img, int C, int K, int op16, int relu, int out_padded, int mv, int grid,
+                    int n_img, int C, int K, int op16, int cg2, int relu, int out_padded, int mv, int grid,
                     cudaStream_t stream) {
-  if (op16) return launch_ffw<true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, mv, grid, stream, op16 == 2);
-  return launch_ffw<false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, mv, grid, stream, 0);
+#define WG_FFW(H16_, CG2_) \
+  return launch_ffw<H16_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, mv, grid, stream, op16 == 2)
+  if (cg2) {
+    if (op16) WG_FFW(true, true);
+    WG_FFW(false, true);
+  }
+  if (op16) WG_FFW(true, false);
+  WG_FFW(false, false);
+#undef WG_FFW
 }
 
 }  // namespace wg
