@@ -46,7 +46,17 @@ struct OneSmem {
 // WS (with CL == 1): weight-stationary schedule for Cin*BN*4 <= 128 KB (128->512): CTA b keeps N-tile b % n_ntiles
 // for its whole life and loads that weight tile ONCE; per output tile the TMA unit then moves A + the output instead
 // of A + B + the output (measured 31.9 -> 29.6 us at N=256; see one_launch for the variant that lost).
-template <int BN, int CL, bool WS = false>
+// PAIR (with CL == 2): the two CTAs of a cluster form a tcgen05 cta_group::2 pair -- two consecutive M-tiles of the same
+// N-tile computed by ONE stream of M = 256 MMAs issued by the leader CTA. Each CTA loads its own activation tile and only
+// HALF of the weight tile (rows [rank*BN/2, +BN/2), no multicast), and the tensor core reads each half from the shared
+// memory it lives in: per SM the weight tile costs half the L2 -> SM traffic, half the shared-memory writes and half the
+// B-operand reads. Hand-offs: the peer's (otherwise idle) MMA warp relays "stage landed" to the leader's full[] barrier,
+// the leader's commits are multicast to both CTAs, the peer's epilogue warps arrive on the leader's acc_empty[].
+// EXPERIMENT (WG_ONE_PAIR=1), bit-identical, measured at N=256: 256->1024 65.3 -> 64.7 us, 1024->256 56.7 -> 57.7,
+// 512->128 27.2 -> 27.5: the weight traffic is not what these kernels wait for. (Neither is the epilogue's instruction
+// count per se: eight epilogue warps ran 256->1024 in 78 us, epilogue warps storing the dense output themselves instead
+// of TMA tensor stores in 85 us.) Default off.
+template <int BN, int CL, bool WS = false, bool PAIR = false>
 __global__ void __launch_bounds__(kOneThreads, 1)
 conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                       const float* __restrict__ w_img, const float* __restrict__ scale,
@@ -54,6 +64,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                       int Cout, int relu, int bn_packed) {
   using S = OneSmem<BN, WS>;
   static_assert(!WS || CL == 1, "weight-stationary schedule has no cluster variant");
+  static_assert(!PAIR || (CL == 2 && !WS), "CTA pairs are clusters of 2");
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -77,17 +88,21 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_y);
     for (int i = 0; i < S::kStages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], CL);  // every CTA of the cluster must have consumed a stage before it is refilled
+      // PAIR, leader: own TMA bytes + the peer's relay; one multicast commit frees a stage in both CTAs
+      mbar_init(&full[i], (PAIR && crank == 0) ? 2 : 1);
+      mbar_init(&empty[i], PAIR ? 1 : CL);  // every CTA of the cluster must have consumed a stage before it is refilled
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], PAIR ? 8 : 4);
     }
     mbar_init(b_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_cg2<kTmemCols>(tmem_ptr);
+    else tmem_alloc<kTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
   if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -128,9 +143,12 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const uint8_t* b_src = b_tile(nt);
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full[st], WS ? S::kABytes : S::kABytes + S::kBBytes);
+          mbar_arrive_expect_tx(&full[st], WS ? S::kABytes : (PAIR ? S::kABytes + S::kBBytes / 2 : S::kABytes + S::kBBytes));
           tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, kb * kBK, mt * 128, &full[st]);
           if constexpr (WS) {
+          } else if constexpr (PAIR) {  // this CTA's half of the weight rows, at offset 0 of the stage in BOTH CTAs
+            tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * b_kb_stride + crank * (S::kBBytes / 2),
+                         S::kBBytes / 2, &full[st]);
           } else if constexpr (CL == 1) {
             tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * b_kb_stride, S::kBBytes, &full[st]);
           } else {
@@ -142,9 +160,20 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
       }
     }
+  } else if (warp == 1 && PAIR && crank != 0) {
+    // peer of a CTA pair: no MMAs to issue; relay "stage st has landed here" to the leader's full[st]
+    if (elect_one()) {
+      uint32_t st = 0, ph = 0;
+      for (int item = first_item; item < n_items; item += item_stride)
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full[st], ph);
+          mbar_arrive_remote_plain(&full[st], 0);
+          if (++st == S::kStages) { st = 0; ph ^= 1; }
+        }
+    }
   } else if (warp == 1) {
     if (elect_one()) {  // elect.sync, not lane == 0: lets ptxas keep descriptors in uniform registers (no per-MMA waterfall loop)
-      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, BN);
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, PAIR ? 256 : 128, BN);
       const uint32_t a_base = smem_u32(smem + S::kOffA);
       const uint32_t b_base = smem_u32(smem + S::kOffB);
       uint32_t st = 0, ph = 0;
@@ -163,12 +192,16 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint64_t a_desc = make_smem_desc(a_base + st * S::kABytes + k * 32, 0, 1024, kLayoutSW128);
             const uint64_t b_desc =
                 make_smem_desc(b_base + (WS ? kb : (int)st) * S::kBBytes + k * 32, 0, 1024, kLayoutSW128);
-            umma_tf32_ss(tmem_base + buf * BN, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_tf32_ss_cg2(tmem_base + buf * BN, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_tf32_ss(tmem_base + buf * BN, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          if constexpr (CL == 1) umma_commit(&empty[st]); else umma_commit_mcast(&empty[st], kClusterMask);
+          if constexpr (PAIR) umma_commit_mcast_cg2(&empty[st], kClusterMask);
+          else if constexpr (CL == 1) umma_commit(&empty[st]);
+          else umma_commit_mcast(&empty[st], kClusterMask);
           if (++st == S::kStages) { st = 0; ph ^= 1; }
         }
-        umma_commit(&acc_full[buf]);
+        if constexpr (PAIR) umma_commit_mcast_cg2(&acc_full[buf], kClusterMask);
+        else umma_commit(&acc_full[buf]);
       }
     }
   } else {
@@ -249,14 +282,20 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_remote_plain(&acc_empty[buf], 0);  // the leader issues the MMAs of both CTAs
+        else mbar_arrive(&acc_empty[buf]);
+      }
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
   if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may leave while peers still multicast to it
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_cg2<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
+  }
 #undef WG_ITEM_NT
 #undef WG_ITEM_MT
 }
@@ -497,7 +536,7 @@ int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int C
   return encode_2d(tmap, y, Cout, m_rows, 32, 32);
 }
 
-template <int BN, int CL, bool WS = false>
+template <int BN, int CL, bool WS = false, bool PAIR = false>
 static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
                       const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int relu,
                       int max_ctas, cudaStream_t stream, int bn_packed = BN) {
@@ -507,7 +546,7 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN, CL, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN, CL, WS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
     configured |= dev_bit_;
@@ -537,7 +576,7 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL, WS>, tmap, tmap_y, w_img, scale, shift, y_padded,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL, WS, PAIR>, tmap, tmap_y, w_img, scale, shift, y_padded,
                                      m_rows, Cin, Cout, relu, bn_packed);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
@@ -686,6 +725,21 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
   }
 #define WG_ONE(BN_, CL_) \
   return launch_one<BN_, CL_>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas, stream)
+  // CTA pairs (tcgen05 cta_group::2, M = 256 over two consecutive M-tiles, each CTA holding half of the weight tile):
+  // WG_ONE_PAIR=1; experiment, default off (see the kernel).
+  static int pair = -1;
+  if (pair < 0) {
+    const char* e = getenv("WG_ONE_PAIR");
+    pair = e ? (atoi(e) != 0) : 0;
+  }
+  if (pair && m_rows > 128 && max_ctas >= 2) {
+    if (BN == 128)
+      return launch_one<128, 2, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
+                                             max_ctas, stream);
+    if (BN == 256)
+      return launch_one<256, 2, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
+                                             max_ctas, stream);
+  }
   if (BN == 128) {
     if (use == 1) WG_ONE(128, 1);
     if (use == 2) WG_ONE(128, 2);

@@ -311,6 +311,16 @@ def test_1x1_full_batch_256_properties(lib_loaded, torch_cuda, cin, cout, relu):
 
 
 # ------------------------------------------------------------------------------ "next" row: the bottleneck chain
+def test_1x1_cta_pair_variant(lib_loaded):
+    """WG_ONE_PAIR=1 (experiment, default off): the 1x1 throughput kernel as tcgen05 cta_group::2 pairs. The knob is
+    read once per process, hence the subprocess; it re-runs this file's 1x1 and chain tests with the knob set."""
+    env = dict(os.environ, WG_ONE_PAIR="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "1x1_ragged or 1x1_full_batch or 1x1_padded or bottleneck_chain_vs"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("n,cin,cout", [(1, 512, 128), (3, 64, 256), (5, 1024, 256)])
 def test_1x1_padded_frame_output(lib_loaded, torch_cuda, n, cin, cout):
     """1x1 with out_padded: the [N,16,16,Cout] frame a 3x3 layer reads -- interior == dense result, border == 0."""
