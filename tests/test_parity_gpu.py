@@ -311,6 +311,36 @@ def test_1x1_full_batch_256_properties(lib_loaded, torch_cuda, cin, cout, relu):
 
 
 # ------------------------------------------------------------------------------ "next" row: the bottleneck chain
+@pytest.mark.parametrize("max_ctas", [1, 5, 37])
+def test_results_do_not_depend_on_the_grid_size(lib_loaded, torch_cuda, max_ctas):
+    """wg_set_max_ctas: the persistent kernels walk many items per CTA (every ring and phase wraps many times) and must
+    produce bit-identical results however the items are dealt out -- 3x3 full-fold kernel (TF32 and bf16 operands, both
+    slice widths and the double-buffered 64-wide case) and the 1x1 kernel. (Batches large enough that the throughput
+    kernels are picked for every grid size; the small-batch kernels sum in a different order.)"""
+    torch = torch_cuda
+    rs = np.random.RandomState(4242)
+    x, w, sc, sh = _rand3x3(rs, 64, 32, 160)
+    xb, wb, scb, shb = _rand3x3(rs, 64, 48, 128)
+    x1 = ((rs.rand(40, 196, 96) - 0.5) * 4).astype(np.float32)
+    w1 = (rs.rand(96, 256) - 0.5).astype(np.float32)
+    s1, h1 = rs.rand(256).astype(np.float32), rs.rand(256).astype(np.float32)
+    layers = [(lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True), x),
+              (lib_loaded.Conv3x3BnRelu(wb, scb, shb, relu=True, dtype=lib_loaded.WG_BF16), xb),
+              (lib_loaded.Conv1x1Bn(w1, s1, h1, relu=True), x1)]
+    try:
+        for layer, xin in layers:
+            xd = torch.from_numpy(xin).cuda()
+            lib_loaded.lib().wg_set_max_ctas(0)
+            ref = layer(xd).clone()
+            lib_loaded.lib().wg_set_max_ctas(max_ctas)
+            got = layer(xd)
+            assert torch.equal(got, ref), float((got - ref).abs().max())
+    finally:
+        lib_loaded.lib().wg_set_max_ctas(0)
+        for layer, _ in layers:
+            layer.close()
+
+
 def test_1x1_cta_pair_variant(lib_loaded):
     """WG_ONE_PAIR=1 (experiment, default off): the 1x1 throughput kernel as tcgen05 cta_group::2 pairs. The knob is
     read once per process, hence the subprocess; it re-runs this file's 1x1 and chain tests with the knob set."""
