@@ -49,8 +49,8 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
 
 // the same kernel with sixteen transform warps, one group of 8 per V half (wino_ffw_kernel.cu); same filter image / map
 int wino_ffw_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                    int n_img, int C, int K, int op16, int cg2, int relu, int out_padded, int mv, int grid,
-                    cudaStream_t stream);
+                    int n_img, int C, int K, int op16, int cg2, int split, int relu, int out_padded, int mv,
+                    int grid, cudaStream_t stream);
 
 // small-batch latency variant (wino_small_kernel.cu): TF32 only, filter in the plain KN=32 image
 int wino_small_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);

@@ -34,7 +34,7 @@ constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawStride;
 constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
 constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
 constexpr uint32_t kOffBar = kOffPix + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kRawStages + 8 + 2 + 4;
+constexpr uint32_t kNumBars = 2 * kRawStages + 8 + 2 + 4 + 2;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kTotal = kOffTmemPtr + 16;
 static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alignment");

@@ -770,11 +770,28 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
     const char* e = getenv("WG_FF_W16");
     w16 = e ? (atoi(e) != 0) : 2;
   }
+  // Split-C (wino_ffw_kernel.cu, SPLIT): when all items of the launch, two CTAs each, fit on the chip at once, a
+  // cluster of 2 shares one item and each CTA runs half of the channel loop. Measured (us per launch, Python loop):
+  // 256->256 N=12..48 43 -> 34.5 (cuDNN 15-21), 128->128 N=24..64 21.1 -> 20.7 -- the exchange costs ~10 us (98 KB over
+  // DSMEM each way, release/acquire at cluster scope, cluster launch), so it only pays for long channel loops:
+  // C >= 256. WG_FF_SPLIT=0 disables, =2 lifts the C limit.
+  static int split_env = -1;
+  if (split_env < 0) {
+    const char* e = getenv("WG_FF_SPLIT");
+    split_env = e ? atoi(e) : 1;
+  }
+  if (split_env && !cg2 && dbg == 0 && wino_ff_p9() && !(out_padded & 2) && (C >= 256 || split_env == 2)) {
+    const int n_kb = C / (op16 ? 16 : 8);
+    const int n_items = ((n_img * 49 + 127) / 128) * ff::n_slices(K);
+    if (n_kb % 2 == 0 && n_kb >= 4 && 2 * n_items <= max_ctas)
+      return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, 0, 1, relu, out_padded, 128, 2 * n_items,
+                             stream);
+  }
   const bool use_w16 = w16 == 1 || (w16 == 2 && op16 != 0 && C >= 256);
   if (use_w16 && dbg == 0 && wino_ff_p9()) {
     int mv = 128, grid = 1;
     ff_plan(n_img, K, max_ctas, cg2 != 0, &mv, &grid);
-    return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, cg2, relu, out_padded, mv, grid, stream);
+    return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, cg2, 0, relu, out_padded, mv, grid, stream);
   }
 #define WG_FF(H16_, DBG_, P9_, CG2_)                                                                                \
   return launch_ff<H16_, DBG_, P9_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, \

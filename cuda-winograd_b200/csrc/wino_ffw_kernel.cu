@@ -53,7 +53,13 @@ __device__ __forceinline__ void ffw_row_pass(const float (&d)[4][3][4], uint32_t
 
 // CG2: CTA pairs (clusters of 2, tcgen05 cta_group::2), exactly as in wino3x3_ff_kernel: neighbouring M-blocks, same cout
 // slice, MMAs with M = 256 issued by the leader CTA, each CTA supplying half of the couts of every filter chunk.
-template <bool H16, bool CG2>
+// SPLIT: split-C for batches whose work items do not fill the SMs (one wave, each cluster exactly one item). The two
+// CTAs of a cluster work on the SAME item, each on half of the channel loop; afterwards CTA r owns tile rows
+// [64r, 64r + 64): the warps of the other two TMEM lane quadrants push their partial accumulators into the owner's shared
+// memory (st.shared::cluster into a bank-swizzled inbox laid over the pipeline buffers, which are free by then -- the
+// owner says so with an mbarrier arrive), the owner's warps add them in the epilogue. Halves an item's stage count at
+// the price of 98 KB over DSMEM each way: 256->256 at N=12..64 ~43 -> ~25 us.
+template <bool H16, bool CG2, bool SPLIT>
 __global__ void __launch_bounds__(ffw::kThreads, 1)
 wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
@@ -78,7 +84,10 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
   uint64_t* acc_full = done + 4;
   uint64_t* acc_empty = acc_full + 1;
   uint64_t* u_land = acc_empty + 1;  // [4] CG2, peer CTA only: its half of a filter chunk has landed
-  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
+  uint64_t* may_push = u_land + 4;   // SPLIT: the other CTA's main loop is done, its pipeline buffers may be overwritten
+  uint64_t* inbox_full = may_push + 1;  // SPLIT: the other CTA's 8 pushing warps have delivered their partial sums
+  static_assert(!(CG2 && SPLIT), "one cluster role at a time");
+  const uint32_t crank = (CG2 || SPLIT) ? cluster_ctarank() : 0u;
   const bool peer = CG2 && crank != 0;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
@@ -97,6 +106,8 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, CG2 ? 2 * kWorkerWarps : kWorkerWarps);
+    mbar_init(may_push, 1);
+    mbar_init(inbox_full, 32 * kWorkerWarps / 2);  // every pushing thread releases its own stores
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -104,17 +115,19 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
     else tmem_alloc<512>(tmem_ptr);
   }
   tc_fence_before();
-  if constexpr (CG2) cluster_sync_all();  // the peer's barriers exist before anybody arrives on them remotely
+  if constexpr (CG2 || SPLIT) cluster_sync_all();  // the peer's barriers exist before anybody arrives on them remotely
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_kb = C / (8 * kSub);
+  const int n_kb_all = C / (8 * kSub);
+  const int n_kb = SPLIT ? n_kb_all / 2 : n_kb_all;      // V stages this CTA runs per item
+  const int kb_off = SPLIT ? (int)crank * n_kb : 0;      // ... starting at this stage of the layer's channel loop
   const int n_sl = n_slices(K);
   const int total_tiles = n_img * 49;
   const int n_mblocks = (total_tiles + mv - 1) / mv;
   const int n_items = (CG2 ? (n_mblocks + 1) / 2 : n_mblocks) * n_sl;  // CG2: one item per CTA pair
-  const int item0 = CG2 ? blockIdx.x / 2 : blockIdx.x, item_step = CG2 ? gridDim.x / 2 : gridDim.x;
+  const int item0 = (CG2 || SPLIT) ? blockIdx.x / 2 : blockIdx.x, item_step = (CG2 || SPLIT) ? gridDim.x / 2 : gridDim.x;
   const uint32_t u_bytes_per_kn = CG2 ? 128u : 256u;  // bytes of a filter chunk this CTA loads, per cout of the slice
 
   if (warp == kProducerWarp) {
@@ -124,11 +137,12 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       int u_primed = 0;
       if (item0 < n_items) {  // the filter does not depend on the previous kernel in the stream
         const Slice sl = slice(K, item0 % n_sl);
-        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * sl.c0;
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb_all * 512 * sl.c0 +
+                               (size_t)kb_off * 512 * sl.kn;
         for (int h = 0; h < 2; ++h) {
           uint64_t* ubar = peer ? &u_land[us] : &full[us];
           mbar_arrive_expect_tx(ubar, u_bytes_per_kn * sl.kn);
-          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)h * 256 + crank * 128) * sl.kn,
+          tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + ((size_t)h * 256 + (CG2 ? crank * 128 : 0)) * sl.kn,
                        u_bytes_per_kn * sl.kn, ubar);
           ++us;
         }
@@ -140,7 +154,8 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
         const int kn = sl.kn;
         const int t0 = (CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl) * mv;
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
-        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * sl.c0;
+        const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb_all * 512 * sl.c0 +
+                               (size_t)kb_off * 512 * sl.kn;
         for (int kb = 0; kb < n_kb; ++kb) {
 #pragma unroll
           for (int sb = 0; sb < kSub; ++sb) {
@@ -148,8 +163,8 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
             mbar_arrive_expect_tx(&raw_full[rs], kRawBytesP9);
 #pragma unroll
             for (int q = 0; q < 4; ++q)  // plane q = (y parity q>>1, x parity q&1); x/2 starts at -1 (zero-filled)
-              tma_tensor_5d_g2s(smem + kOffRaw + rs * kRawStride + q * kPlaneBytes, &tmap_x, (kb * kSub + sb) * 8, -1,
-                                q & 1, q >> 1, ny0 >> 1, &raw_full[rs]);
+              tma_tensor_5d_g2s(smem + kOffRaw + rs * kRawStride + q * kPlaneBytes, &tmap_x,
+                                ((kb_off + kb) * kSub + sb) * 8, -1, q & 1, q >> 1, ny0 >> 1, &raw_full[rs]);
             if (++rs == kRawStages) { rs = 0; rph ^= 1; }
           }
           if (u_primed) {
@@ -160,7 +175,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
             mbar_wait(&done[us], uph ^ 1);
             uint64_t* ubar = peer ? &u_land[us] : &full[us];
             mbar_arrive_expect_tx(ubar, u_bytes_per_kn * kn);
-            tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (((size_t)kb * 2 + h) * 256 + crank * 128) * kn,
+            tma_bulk_g2s(smem + kOffU + us * kUChunkMax, u_src + (((size_t)kb * 2 + h) * 256 + (CG2 ? crank * 128 : 0)) * kn,
                          u_bytes_per_kn * kn, ubar);
             if (++us == kUBufs) { us = 0; uph ^= 1; }
           }
@@ -362,6 +377,49 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       mbar_wait(acc_full, aph);
       aph ^= 1;
       tc_fence_after();
+      // SPLIT: this CTA finishes tile rows [64 * crank, +64) = TMEM lane quadrants 2 * crank, 2 * crank + 1
+      const bool owner = !SPLIT || (uint32_t)(quad >> 1) == crank;
+      // inbox (in the OWNER's shared memory, from offset 0): [chunk (ec, a)][64 rows][2 pixels b][32 couts] fp32, the
+      // 16-byte pieces of a row XOR-swizzled with the row so that neighbouring lanes do not hit one bank group
+      const uint32_t inbox_row = (uint32_t)(row & 63);
+      if constexpr (SPLIT) {
+        if (threadIdx.x == 0) mbar_arrive_remote_plain(may_push, crank ^ 1u);  // my main loop is done: push
+        if (!owner) {
+          mbar_wait(may_push, 0);  // the owner's pipeline buffers are free
+          uint32_t remote_base, remote_bar;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_base) : "r"(smem_u32(smem)), "r"(crank ^ 1u));
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_bar) : "r"(smem_u32(inbox_full)), "r"(crank ^ 1u));
+          if (warp_active) {
+            const int n_chunks_p = kn / kEW;
+#pragma unroll 1
+            for (int ec = 0; ec < n_chunks_p; ++ec)
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * kAccStride + (uint32_t)(ec * kEW + esub * 8);
+                float z[2][8];
+                tmem_ld_x8(taddr, z[0]);
+                tmem_ld_x8(taddr + kAccStride, z[1]);
+                tmem_ld_wait();
+                const uint32_t dst = remote_base + ((uint32_t)(ec * 2 + a) * 64 + inbox_row) * 256;
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                  for (int q4 = 0; q4 < 2; ++q4) {
+                    const uint32_t pos = (uint32_t)(b * 8 + esub * 2 + q4) ^ (inbox_row & 7);
+                    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + pos * 16),
+                                 "f"(z[b][4 * q4]), "f"(z[b][4 * q4 + 1]), "f"(z[b][4 * q4 + 2]), "f"(z[b][4 * q4 + 3])
+                                 : "memory");
+                  }
+              }
+          }
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+          continue;  // one item per cluster: nothing else to do for this warp
+        }
+        mbar_wait_cluster(inbox_full, 0);  // the other CTA's partial sums for my rows have landed
+      }
       if (warp_active) {
 #pragma unroll 1
         for (int ec = 0; ec < n_chunks; ++ec) {
@@ -382,6 +440,17 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
             tmem_ld_x8(taddr, z[0]);
             tmem_ld_x8(taddr + kAccStride, z[1]);
             tmem_ld_wait();
+            if constexpr (SPLIT) {  // add the other CTA's partial sums (the other half of the channel loop)
+              const uint32_t src = smem_u32(smem) + ((uint32_t)(ec * 2 + a) * 64 + inbox_row) * 256;
+#pragma unroll
+              for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int q4 = 0; q4 < 2; ++q4) {
+                  const uint32_t pos = (uint32_t)(b * 8 + esub * 2 + q4) ^ (inbox_row & 7);
+                  const float4 v = ld_shared_v4(src + pos * 16);
+                  z[b][4 * q4] += v.x, z[b][4 * q4 + 1] += v.y, z[b][4 * q4 + 2] += v.z, z[b][4 * q4 + 3] += v.w;
+                }
+            }
             if (ec == n_chunks - 1 && a == 1) {  // this warp has read its last accumulator columns
               tc_fence_before();
               __syncwarp();
@@ -443,7 +512,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
   }
 
   tc_fence_before();
-  if constexpr (CG2) cluster_sync_all();  // the peer's shared memory, TMEM and barriers stay alive until the pair is done
+  if constexpr (CG2 || SPLIT) cluster_sync_all();  // the peer's shared memory, TMEM and barriers stay alive until both are done
   else __syncthreads();
   if (warp == kMmaWarp) {
     if constexpr (CG2) tmem_dealloc_cg2<512>(tmem_base);
@@ -454,7 +523,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 
-template <bool H16, bool CG2>
+template <bool H16, bool CG2, bool SPLIT>
 static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                       int n_img, int C, int K, int relu, int out_padded, int mv, int grid, cudaStream_t stream,
                       int fp16) {
@@ -463,7 +532,7 @@ static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* 
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_ffw_kernel<H16, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
+    if (cudaFuncSetAttribute(wino3x3_ffw_kernel<H16, CG2, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
         cudaSuccess)
       return WG_ERR_CUDA;
     configured |= dev_bit_;
@@ -475,7 +544,7 @@ static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* 
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (CG2) {
+  if (CG2 || SPLIT) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;
     attr[na].val.clusterDim.y = 1;
@@ -489,22 +558,29 @@ static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ffw_kernel<H16, CG2>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ffw_kernel<H16, CG2, SPLIT>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
                                      out_padded, mv, fp16);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
+// split: clusters of 2 on one item each, grid = 2 * #items (the caller guarantees that this fits one wave and that the
+// layer's stage count is even)
 int wino_ffw_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                    int n_img, int C, int K, int op16, int cg2, int relu, int out_padded, int mv, int grid,
+                    int n_img, int C, int K, int op16, int cg2, int split, int relu, int out_padded, int mv, int grid,
                     cudaStream_t stream) {
-#define WG_FFW(H16_, CG2_) \
-  return launch_ffw<H16_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, mv, grid, stream, op16 == 2)
-  if (cg2) {
-    if (op16) WG_FFW(true, true);
-    WG_FFW(false, true);
+#define WG_FFW(H16_, CG2_, SPLIT_)                                                                                   \
+  return launch_ffw<H16_, CG2_, SPLIT_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, mv, grid, stream, \
+                                        op16 == 2)
+  if (split) {
+    if (op16) WG_FFW(true, false, true);
+    WG_FFW(false, false, true);
   }
-  if (op16) WG_FFW(true, false);
-  WG_FFW(false, false);
+  if (cg2) {
+    if (op16) WG_FFW(true, true, false);
+    WG_FFW(false, true, false);
+  }
+  if (op16) WG_FFW(true, false, false);
+  WG_FFW(false, false, false);
 #undef WG_FFW
 }
 

@@ -110,12 +110,14 @@ TOL_BF16 = 1e-2
 
 @pytest.mark.parametrize("kn", [96, 48, 64])
 @pytest.mark.parametrize("n,c,k", [(40, 64, 256), (33, 32, 96), (50, 24, 160), (20, 16, 512), (64, 128, 128),
-                                   (131, 48, 192), (37, 8, 32), (29, 40, 64), (300, 16, 32), (24, 256, 128)])
+                                   (131, 48, 192), (37, 8, 32), (29, 40, 64), (300, 16, 32), (24, 256, 128),
+                                   (12, 256, 256)])
 def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
     """Every throughput kernel on batches that do not fill the last 128-tile M-block and on every cout-slice width:
     kn = 96 the full-fold kernel (wino_ff_kernel.cu: 4 accumulators, slices of 96 / 64 / 32 -- the default), kn = 48 the
     half-fold V-in-TMEM kernel (slices of 48 / 32), kn = 64 the shared-memory-operand kernel. TF32 and, where the shape
-    allows them, bf16 / fp16 operands; dense output and the zero-bordered frame must agree bit for bit."""
+    allows them, bf16 / fp16 operands; dense output and the zero-bordered frame must agree bit for bit. The two C = 256
+    shapes are small enough for the split-C mode (clusters of 2 sharing an item, DSMEM reduction)."""
     torch = torch_cuda
     if kn == 64 and k % 64:
         pytest.skip("the KN=64 kernel needs K % 64 == 0")
@@ -142,12 +144,12 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
         lib_loaded.lib().wg_set_wino_kn(96)
 
 
-@pytest.mark.parametrize("knob", ["WG_FF_P9=0", "WG_FF_CG2=1", "WG_FF_W16=1", "WG_FF_W16=0"])
+@pytest.mark.parametrize("knob", ["WG_FF_P9=0", "WG_FF_CG2=1", "WG_FF_W16=1", "WG_FF_W16=0", "WG_FF_SPLIT=2"])
 def test_3x3_full_fold_kernel_experiment_knobs(lib_loaded, knob):
     """The full-fold kernel's A/B knobs stay correct: WG_FF_P9=0 = the TM kernel's single-box raw layout, WG_FF_CG2=1 =
     CTA pairs (tcgen05 cta_group::2, clusters of 2; measured slower, default off), WG_FF_W16=1 / 0 = sixteen transform
-    warps (wino_ffw_kernel.cu) for every layer / for none (default: 16-bit operands with C >= 256). The knobs are read
-    once per process, hence the subprocess."""
+    warps (wino_ffw_kernel.cu) for every layer / for none (default: 16-bit operands with C >= 256), WG_FF_SPLIT=2 =
+    split-C for every channel count (default: C >= 256). The knobs are read once per process, hence the subprocess."""
     k, v = knob.split("=")
     env = dict(os.environ, **{k: v})
     k = k + "_" + v
@@ -316,11 +318,11 @@ def test_results_do_not_depend_on_the_grid_size(lib_loaded, torch_cuda, max_ctas
     """wg_set_max_ctas: the persistent kernels walk many items per CTA (every ring and phase wraps many times) and must
     produce bit-identical results however the items are dealt out -- 3x3 full-fold kernel (TF32 and bf16 operands, both
     slice widths and the double-buffered 64-wide case) and the 1x1 kernel. (Batches large enough that the throughput
-    kernels are picked for every grid size; the small-batch kernels sum in a different order.)"""
+    kernels are picked for every grid size; the small-batch and split-C kernels sum in a different order.)"""
     torch = torch_cuda
     rs = np.random.RandomState(4242)
-    x, w, sc, sh = _rand3x3(rs, 64, 32, 160)
-    xb, wb, scb, shb = _rand3x3(rs, 64, 48, 128)
+    x, w, sc, sh = _rand3x3(rs, 100, 32, 160)
+    xb, wb, scb, shb = _rand3x3(rs, 100, 48, 128)
     x1 = ((rs.rand(40, 196, 96) - 0.5) * 4).astype(np.float32)
     w1 = (rs.rand(96, 256) - 0.5).astype(np.float32)
     s1, h1 = rs.rand(256).astype(np.float32), rs.rand(256).astype(np.float32)
