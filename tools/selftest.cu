@@ -359,16 +359,16 @@ __global__ void tma_tensor_probe_kernel(const __grid_constant__ CUtensorMap tmap
                                         int box_bytes, int n_img, int C, int cb) {
   using namespace wg;
   extern __shared__ __align__(1024) uint8_t dyn[];
-  __shared__ uint64_t bar[4];
+  __shared__ uint64_t bar[8];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
     fence_mbar_init();
   }
   __syncthreads();
   if (threadIdx.x < 32 && elect_one()) {
     const long long t0 = clock64();
     int issued = 0, done = 0;
-    uint32_t ph[4] = {0, 0, 0, 0};
+    uint32_t ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     while (done < count) {
       while (issued < count && issued - done < depth) {
         const int b = issued % depth;
@@ -394,7 +394,7 @@ static void time_tma_tensor(int grid, int cb, int rows, int swz, int depth) {
     CK(cudaMalloc(&x, (size_t)n_img * 256 * C * 4));
     CK(cudaMemset(x, 0, (size_t)n_img * 256 * C * 4));
     CK(cudaMalloc(&out, 148 * sizeof(long long)));
-    CK(cudaFuncSetAttribute(tma_tensor_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768));
+    CK(cudaFuncSetAttribute(tma_tensor_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 32768));
   }
   typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -420,7 +420,7 @@ static void time_tma_tensor(int grid, int cb, int rows, int swz, int depth) {
   std::vector<long long> h(grid);
   long long best = 1ll << 60, worst = 0;
   for (int rep = 0; rep < 3; ++rep) {
-    tma_tensor_probe_kernel<<<grid, 32, 4 * 32768>>>(tmap, out, count, depth, box_bytes, n_img, C, cb);
+    tma_tensor_probe_kernel<<<grid, 32, 6 * 32768>>>(tmap, out, count, depth, box_bytes, n_img, C, cb);
     CK(cudaDeviceSynchronize());
   }
   CK(cudaMemcpy(h.data(), out, grid * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -965,7 +965,7 @@ int main(int argc, char** argv) {
   }
   if (argc > 1 && !strcmp(argv[1], "tmat")) {
     for (int grid : {1, 148}) {
-      for (int depth : {1, 3}) {
+      for (int depth : {1, 3, 6}) {
         time_tma_tensor(grid, 8, 48, 0, depth);
         time_tma_tensor(grid, 8, 48, 32, depth);
         time_tma_tensor(grid, 16, 24, 0, depth);
