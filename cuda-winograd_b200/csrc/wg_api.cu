@@ -84,6 +84,8 @@ struct wg_layer {
   int tm_db;   // 3x3 TM kernel: 1 = double-buffered V, 32-wide slices
   int tm16_ff; // 3x3 bf16/fp16: d_filter_tm16 is the full-fold kernel's image (96-wide slices)
   int ff_cg2;  // 3x3 full-fold kernel: CTA-pair variant (filter image split in cout halves)
+  float* d_filter_n64;       // 3x3 full-fold kernel: second image with all slices 64 wide (one-wave launches), or null
+  float* d_filter_tm16_n64;  // the same for the 16-bit operand image
   int num_sms;
   float* d_filter;  // packed filter image (U or swizzled W^T)
   float* d_filter_tm16;   // 3x3 bf16/fp16 only: U in the 16-bit image of the V-in-TMEM throughput kernel (48/32 slices)
@@ -179,7 +181,12 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   if (kind == 0) L->ff_cg2 = wino_ff_cg2();
   if (kind == 0 && L->tile_n == 96) {
-    rc = filter_transform_ff_launch(d_w, L->d_filter, cin, cout, 0, L->ff_cg2, L->stream);
+    rc = filter_transform_ff_launch(d_w, L->d_filter, cin, cout, 0, L->ff_cg2, 0, L->stream);
+    if (rc == WG_OK && !L->ff_cg2 && wino_ff_has_narrow(cout)) {
+      WG_TRY(cudaMalloc(&L->d_filter_n64, filter_elems * sizeof(float)));
+      rc = filter_transform_ff_launch(d_w, L->d_filter_n64, cin, cout, 0, 0, 1, L->stream);
+      g_launches++;
+    }
   } else if (kind == 0 && L->tile_n == 48) {
     L->tm_db = wino_tm_choose_db(cin, cout);
     rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->tm_db, 0, L->stream);
@@ -193,10 +200,15 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
     WG_TRY(cudaMalloc(&L->d_filter_tm16, filter_elems * sizeof(uint16_t)));
     L->tm16_ff = wino_kn() == 96;
     rc = L->tm16_ff ? filter_transform_ff_launch(d_w, L->d_filter_tm16, cin, cout, dtype == WG_FP16 ? 2 : 1, L->ff_cg2,
-                                                 L->stream)
+                                                 0, L->stream)
                     : filter_transform_tm_launch(d_w, L->d_filter_tm16, cin, cout, 0, dtype == WG_FP16 ? 2 : 1,
                                                  L->stream);
     g_launches++;
+    if (rc == WG_OK && L->tm16_ff && !L->ff_cg2 && wino_ff_has_narrow(cout)) {
+      WG_TRY(cudaMalloc(&L->d_filter_tm16_n64, filter_elems * sizeof(uint16_t)));
+      rc = filter_transform_ff_launch(d_w, L->d_filter_tm16_n64, cin, cout, dtype == WG_FP16 ? 2 : 1, 0, 1, L->stream);
+      g_launches++;
+    }
   }
   if (rc == WG_OK && kind == 0 && dtype == WG_TF32) {
     if (L->tile_n == 32) {
@@ -276,7 +288,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
         L->tmap_tm_n = N;
       }
       const int op16 = L->dtype == WG_FP16 ? 2 : 1;
-      int rc = L->tm16_ff ? wino_ff_launch(L->tmap_tm, x, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
+      int rc = L->tm16_ff ? wino_ff_launch(L->tmap_tm, x, L->d_filter_tm16, L->d_filter_tm16_n64, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
                                            op16, L->ff_cg2, L->relu, out_flags, max_ctas, stream)
                           : wino_tm_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
                                            0, op16, L->relu, out_flags, max_ctas, stream);
@@ -302,7 +314,7 @@ int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void*
   }
   int rc;
   if (L->kind == 0 && L->tile_n == 96)
-    rc = wino_ff_launch(L->tmap, x, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, L->ff_cg2, L->relu,
+    rc = wino_ff_launch(L->tmap, x, L->d_filter, L->d_filter_n64, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, L->ff_cg2, L->relu,
                         out_flags, max_ctas, stream);
   else if (L->kind == 0 && L->tile_n == 48)
     rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, 0, L->relu,
@@ -387,6 +399,8 @@ int wg_destroy(wg_layer_t* L) {
   if (!L) return WG_ERR_ARG;
   if (L->d_filter_small && L->d_filter_small != L->d_filter) cudaFree(L->d_filter_small);
   if (L->d_filter_tm16) cudaFree(L->d_filter_tm16);
+  if (L->d_filter_n64) cudaFree(L->d_filter_n64);
+  if (L->d_filter_tm16_n64) cudaFree(L->d_filter_tm16_n64);
   if (L->d_filter) cudaFree(L->d_filter);
   if (L->d_scale) cudaFree(L->d_scale);
   if (L->d_shift) cudaFree(L->d_shift);

@@ -42,15 +42,17 @@ int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* sca
 int wino_ff_p9();  // raw-tile layout of the full-fold kernel (1 = parity planes with a 9-slot pitch)
 int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
 int wino_ff_cg2();  // 1 = CTA pairs (cta_group::2): filter image split in cout halves, clusters of 2
-int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, int cg2, cudaStream_t stream);
-int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* scale, const float* shift,
-                   float* y, int n_img, int C, int K, int op16, int cg2, int relu, int out_padded, int max_ctas,
-                   cudaStream_t stream);
+int wino_ff_has_narrow(int K);  // 1 = the layer also gets a filter image with all slices 64 wide (one-wave launches)
+int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, int cg2, int narrow,
+                               cudaStream_t stream);
+int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* u_img_narrow,
+                   const float* scale, const float* shift, float* y, int n_img, int C, int K, int op16, int cg2, int relu,
+                   int out_padded, int max_ctas, cudaStream_t stream);
 
 // the same kernel with sixteen transform warps, one group of 8 per V half (wino_ffw_kernel.cu); same filter image / map
 int wino_ffw_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                    int n_img, int C, int K, int op16, int cg2, int split, int relu, int out_padded, int mv,
-                    int grid, cudaStream_t stream);
+                    int n_img, int C, int K, int op16, int cg2, int split, int narrow, int relu, int out_padded,
+                    int mv, int grid, cudaStream_t stream);
 
 // small-batch latency variant (wino_small_kernel.cu): TF32 only, filter in the plain KN=32 image
 int wino_small_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);

@@ -41,18 +41,24 @@ static_assert(kOffU % 1024 == 0 && kOffStg % 128 == 0 && kOffBar % 8 == 0, "alig
 static_assert(kTotal <= 227 * 1024, "shared memory budget");
 
 // cout slices: ceil(K/96) of them, widths in multiples of 32 as even as possible, wider ones first
-// (256 = 96 + 96 + 64, 128 = 64 + 64, 512 = 4 x 96 + 2 x 64).
-__host__ __device__ inline int n_slices(int K) { return (K + 95) / 96; }
+// (256 = 96 + 96 + 64, 128 = 64 + 64, 512 = 4 x 96 + 2 x 64). narrow: K/64 slices of 64 (K % 64 == 0) -- the second
+// filter image of a layer, for launches whose items do not fill the SMs: a 64-wide slice leaves room for two V stages in
+// TMEM and needs only two thirds of a 96-wide slice's MMA time per stage.
+__host__ __device__ inline int n_slices(int K, int narrow = 0) { return narrow ? K / 64 : (K + 95) / 96; }
 struct Slice { int kn, c0; };  // width and first cout
-__host__ __device__ inline Slice slice(int K, int s) {
+__host__ __device__ inline Slice slice(int K, int s, int narrow = 0) {
+  if (narrow) return Slice{64, 64 * s};
   const int ns = n_slices(K), units = K / 32, base = units / ns, rem = units % ns;
   return Slice{32 * (base + (s < rem ? 1 : 0)), 32 * (s * base + (s < rem ? s : rem))};
 }
-__host__ __device__ inline int slice_of(int K, int k) {
+__host__ __device__ inline int slice_of(int K, int k, int narrow = 0) {
+  if (narrow) return k / 64;
   const int ns = n_slices(K), units = K / 32, base = units / ns, rem = units % ns;
   const int wide = rem * (base + 1) * 32;
   return k < wide ? k / ((base + 1) * 32) : rem + (k - wide) / (base * 32);
 }
+// a layer gets a narrow image when that slicing differs from the default one
+__host__ __device__ inline bool has_narrow(int K) { return K % 64 == 0 && K / 64 != n_slices(K); }
 }  // namespace ff
 
 __device__ __forceinline__ float ff_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }

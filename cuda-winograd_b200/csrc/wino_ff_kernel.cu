@@ -559,8 +559,9 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 // op16 = 1 (bf16) / 2 (fp16): 16-channel k-blocks, 8 channels per 16-byte chunk, same 512 bytes per (k-block, cout).
 // cg2: image of the CTA-pair kernel -- inside every (k-block, j-half) chunk the couts of the slice are split in two
 // halves, [rank 2][8 points][2 k-chunks][KN/2 couts][16 B], CTA `rank` of a pair loads its 128*KN contiguous bytes.
+// narrow: the all-64-wide slicing (ff::slice(..., narrow)).
 __global__ void filter_transform_ff_kernel(const float* __restrict__ w_kcrs, float* __restrict__ u_img, int C, int K,
-                                           int op16, int cg2) {
+                                           int op16, int cg2, int narrow) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * K) return;
   const int ch = idx % C;
@@ -579,7 +580,7 @@ __global__ void filter_transform_ff_kernel(const float* __restrict__ w_kcrs, flo
     tt[2][s] = 0.5f * (gg[0][s] - gg[1][s] + gg[2][s]);
     tt[3][s] = gg[2][s];
   }
-  const ff::Slice sl = ff::slice(K, ff::slice_of(K, k));
+  const ff::Slice sl = ff::slice(K, ff::slice_of(K, k, narrow), narrow);
   const int kn = sl.kn, c0 = sl.c0;
   const int kl = k - c0;
   const int kb = ch / 8, chunk = (ch % 8) / 4, e = ch % 4;
@@ -662,10 +663,12 @@ int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
 
-int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, int cg2,
+int wino_ff_has_narrow(int K) { return ff::has_narrow(K) ? 1 : 0; }
+
+int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, int cg2, int narrow,
                                cudaStream_t stream) {
   const int n = C * K;
-  filter_transform_ff_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, op16, cg2);
+  filter_transform_ff_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_kcrs, u_img, C, K, op16, cg2, narrow);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
@@ -748,9 +751,9 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* scale, const float* shift,
-                   float* y, int n_img, int C, int K, int op16, int cg2, int relu, int out_padded, int max_ctas,
-                   cudaStream_t stream) {
+int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* u_img_narrow,
+                   const float* scale, const float* shift, float* y, int n_img, int C, int K, int op16, int cg2, int relu,
+                   int out_padded, int max_ctas, cudaStream_t stream) {
   // (An L2 prefetch of the next item's raw rows, cp.async.bulk.prefetch.L2 spread over the stages of the current
   //  item, was measured: no gain -- the kernel is as fast with HBM-cold as with L2-resident input.)
   (void)x;
@@ -770,28 +773,44 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
     const char* e = getenv("WG_FF_W16");
     w16 = e ? (atoi(e) != 0) : 2;
   }
-  // Split-C (wino_ffw_kernel.cu, SPLIT): when all items of the launch, two CTAs each, fit on the chip at once, a
-  // cluster of 2 shares one item and each CTA runs half of the channel loop. Measured (us per launch, Python loop):
-  // 256->256 N=12..48 43 -> 34.5 (cuDNN 15-21), 128->128 N=24..64 21.1 -> 20.7 -- the exchange costs ~10 us (98 KB over
-  // DSMEM each way, release/acquire at cluster scope, cluster launch), so it only pays for long channel loops:
-  // C >= 256. WG_FF_SPLIT=0 disables, =2 lifts the C limit.
-  static int split_env = -1;
+  // Launches whose work items do not fill the SMs (one wave): the time is that of ONE item, so make the item short.
+  //  * narrow slices: with the layer's second filter image (all slices 64 wide) an M-block is K/64 items instead of
+  //    ceil(K/96), each with two V stages in TMEM and 2/3 of the MMA time per stage; used when those items still fit
+  //    one wave, with the 16-warp kernel;
+  //  * split-C (wino_ffw_kernel.cu, SPLIT): when the items, two CTAs each, fit on the chip at once, a cluster of 2
+  //    shares one item and each CTA runs half of the channel loop. The exchange costs ~10 us (DSMEM both ways,
+  //    release/acquire at cluster scope, cluster launch), so it only pays for long channel loops: C >= 256.
+  // WG_FF_SPLIT=0 disables split-C, =2 lifts its C limit; WG_FF_NARROW=0 disables the narrow image.
+  static int split_env = -1, narrow_env = -1;
   if (split_env < 0) {
     const char* e = getenv("WG_FF_SPLIT");
     split_env = e ? atoi(e) : 1;
+    const char* n = getenv("WG_FF_NARROW");
+    narrow_env = n ? atoi(n) : 1;
   }
-  if (split_env && !cg2 && dbg == 0 && wino_ff_p9() && !(out_padded & 2) && (C >= 256 || split_env == 2)) {
+  if (!cg2 && dbg == 0 && wino_ff_p9()) {
     const int n_kb = C / (op16 ? 16 : 8);
-    const int n_items = ((n_img * 49 + 127) / 128) * ff::n_slices(K);
-    if (n_kb % 2 == 0 && n_kb >= 4 && 2 * n_items <= max_ctas)
-      return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, 0, 1, relu, out_padded, 128, 2 * n_items,
+    const int n_mb = (n_img * 49 + 127) / 128;
+    const bool split_ok = split_env && !(out_padded & 2) && (C >= 256 || split_env == 2) && n_kb % 2 == 0 && n_kb >= 4;
+    // measured, 256->256, us per launch (Python loop): narrow + split 29-30 (N <= 32), default slices + split 34.5-36
+    // (N <= 48), narrow 43.8 (N <= 96), default 46-50
+    const bool narrow_ok = narrow_env && u_img_narrow != nullptr;
+    const int items_n = n_mb * (K / 64), items_d = n_mb * ff::n_slices(K);
+    if (narrow_ok && split_ok && 2 * items_n <= max_ctas)
+      return wino_ffw_launch(tmap, u_img_narrow, scale, shift, y, n_img, C, K, op16, 0, 1, 1, relu, out_padded, 128,
+                             2 * items_n, stream);
+    if (split_ok && 2 * items_d <= max_ctas)
+      return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, 0, 1, 0, relu, out_padded, 128, 2 * items_d,
                              stream);
+    if (narrow_ok && items_n <= max_ctas)
+      return wino_ffw_launch(tmap, u_img_narrow, scale, shift, y, n_img, C, K, op16, 0, 0, 1, relu, out_padded, 128,
+                             items_n, stream);
   }
   const bool use_w16 = w16 == 1 || (w16 == 2 && op16 != 0 && C >= 256);
   if (use_w16 && dbg == 0 && wino_ff_p9()) {
     int mv = 128, grid = 1;
     ff_plan(n_img, K, max_ctas, cg2 != 0, &mv, &grid);
-    return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, cg2, 0, relu, out_padded, mv, grid, stream);
+    return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, cg2, 0, 0, relu, out_padded, mv, grid, stream);
   }
 #define WG_FF(H16_, DBG_, P9_, CG2_)                                                                                \
   return launch_ff<H16_, DBG_, P9_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, \

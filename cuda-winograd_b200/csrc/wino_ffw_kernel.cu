@@ -63,7 +63,7 @@ template <bool H16, bool CG2, bool SPLIT>
 __global__ void __launch_bounds__(ffw::kThreads, 1)
 wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
-                   int C, int K, int relu, int out_padded, int mv, int fp16) {
+                   int C, int K, int relu, int out_padded, int mv, int fp16, int narrow) {
   using namespace ff;
   using ffw::kMmaWarp;
   using ffw::kProducerWarp;
@@ -123,7 +123,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
   const int n_kb_all = C / (8 * kSub);
   const int n_kb = SPLIT ? n_kb_all / 2 : n_kb_all;      // V stages this CTA runs per item
   const int kb_off = SPLIT ? (int)crank * n_kb : 0;      // ... starting at this stage of the layer's channel loop
-  const int n_sl = n_slices(K);
+  const int n_sl = n_slices(K, narrow);
   const int total_tiles = n_img * 49;
   const int n_mblocks = (total_tiles + mv - 1) / mv;
   const int n_items = (CG2 ? (n_mblocks + 1) / 2 : n_mblocks) * n_sl;  // CG2: one item per CTA pair
@@ -136,7 +136,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       uint32_t rs = 0, rph = 0, us = 0, uph = 0;
       int u_primed = 0;
       if (item0 < n_items) {  // the filter does not depend on the previous kernel in the stream
-        const Slice sl = slice(K, item0 % n_sl);
+        const Slice sl = slice(K, item0 % n_sl, narrow);
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb_all * 512 * sl.c0 +
                                (size_t)kb_off * 512 * sl.kn;
         for (int h = 0; h < 2; ++h) {
@@ -150,7 +150,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       }
       pdl_wait();
       for (int item = item0; item < n_items; item += item_step) {
-        const Slice sl = slice(K, item % n_sl);
+        const Slice sl = slice(K, item % n_sl, narrow);
         const int kn = sl.kn;
         const int t0 = (CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl) * mv;
         const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
@@ -197,24 +197,28 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       }
     } else if (elect_one()) {
       const uint32_t u_base = smem_u32(smem + kOffU);
-      uint32_t us = 0, uph = 0, aph = 0;
+      uint32_t us = 0, uph = 0, aph = 0, gm = 0;  // gm = V stages issued
       for (int item = item0; item < n_items; item += item_step) {
-        const uint32_t kn = (uint32_t)slice(K, item % n_sl).kn;
+        const uint32_t kn = (uint32_t)slice(K, item % n_sl, narrow).kn;
         const uint32_t fmt = H16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
         const uint32_t idesc_pos = make_idesc(fmt, CG2 ? 256 : 128, kn);
         const uint32_t idesc_neg = make_idesc(fmt, CG2 ? 256 : 128, kn, 1);  // D += (-A) * B
         // CG2: this CTA's shared memory holds kn/2 couts of every point
         const uint32_t u_per_point = (CG2 ? 1 : 2) * kn * 16, u_lbo = (CG2 ? kn / 2 : kn) * 16;
+        // slices of 64 or fewer couts: two V stages in TMEM (accumulator p at 64 p, V stage (g & 1) at 256 + 128 (g & 1)),
+        // see wino_ff_kernel.cu
+        const bool db = !CG2 && kn <= 64;
+        const uint32_t acc_stride = db ? 64u : kAccStride, v_col0 = db ? 256u : kVCol0;
         mbar_wait(acc_empty, aph ^ 1);  // epilogue of the previous item has drained TMEM
         tc_fence_after();
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = 0; kb < n_kb; ++kb, ++gm) {
           uint32_t written = kb > 0 ? 0xFu : 0u;  // bit p set = accumulator p has been written in this item
 #pragma unroll
           for (int jh = 0; jh < 2; ++jh) {
             mbar_wait(&full[us], uph);  // filter chunk landed and V half stored by its transform warps
             tc_fence_after();
             const uint32_t ua = u_base + us * kUChunkMax;
-            const uint32_t va = tmem_base + kVCol0 + jh * 64;
+            const uint32_t va = tmem_base + v_col0 + (db ? (gm & 1) * 128 : 0u) + jh * 64;
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
               const int j = jh * 2 + jj;
@@ -232,7 +236,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
                     if ((b == 0 && j == 3) || (b == 1 && j == 0)) continue;
                     const int sb = (b == 1 && j >= 2) ? -1 : 1;
                     const uint32_t p = (uint32_t)(2 * a + b);
-                    ff_umma<H16, CG2>(tmem_base + p * kAccStride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
+                    ff_umma<H16, CG2>(tmem_base + p * acc_stride, a_tm, b_desc, sa * sb > 0 ? idesc_pos : idesc_neg,
                                         (written >> p) & 1u);
                     written |= 1u << p;
                   }
@@ -269,7 +273,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       else mbar_arrive(bar);
     };
     for (int item = item0; item < n_items; item += item_step) {
-      const Slice sl = slice(K, item % n_sl);
+      const Slice sl = slice(K, item % n_sl, narrow);
       const int kn = sl.kn, c0s = sl.c0;
       const int t0 = (CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl) * mv;
       const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
@@ -277,6 +281,8 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
       const bool tvalid = row < valid_rows;
       const bool warp_active = quad * 32 < valid_rows;  // warp-uniform
+      const bool db = !CG2 && kn <= 64;                 // two V stages in TMEM (see the MMA thread)
+      const uint32_t acc_stride = db ? 64u : kAccStride, v_col0 = db ? 256u : kVCol0;
       const int n = T / 49, t = T % 49, ty = t / 7;
       const int tx = 6 - t % 7;  // tiles run right-to-left inside a tile row (conflict-free slots, wino_ff_common.cuh)
       // byte offset, inside the raw stage, of patch pixel (dy, c + jh) for c = 0..2: plane (dy&1, dx&1) + slot + half
@@ -296,7 +302,10 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
       for (int kb = 0; kb < n_kb; ++kb) {
         // this stage's ring slot for this half; the previous stage's (whose MMAs must have completed before the V half
         // is overwritten) completes for the ((g - 1) >> 1)-th time
-        const uint32_t slot = (g & 1) * 2 + jh, pslot = slot ^ 2, pph = ((g - 1) >> 1) & 1;
+        // (two V stages: the MMAs of stage g - 2, which used this very slot; the first stage(s) of an item wait for
+        // nothing -- this thread has passed the previous item's acc_full)
+        const uint32_t slot = (g & 1) * 2 + jh, pslot = db ? slot : slot ^ 2, pph = ((g - (db ? 2u : 1u)) >> 1) & 1;
+        const bool wait_v = kb >= (db ? 2 : 1);
         if (!warp_active) {
 #pragma unroll
           for (int sb = 0; sb < kSub; ++sb) {
@@ -304,7 +313,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
             if (lane == 0) mbar_arrive(&raw_empty[rs]);
             if (++rs == kRawStages) { rs = 0; rph ^= 1; }
           }
-          if (g > 0) mbar_wait(&done[pslot], pph);
+          if (wait_v) mbar_wait(&done[pslot], pph);
           if (lane == 0) arrive_leader(&full[slot]);
           ++g;
           continue;
@@ -348,10 +357,11 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
           // row pass for this half, rounded to the operand type and stored into TMEM (tf32: one column per channel;
           // 16-bit: one column per channel pair, raw stage sb fills columns 4*sb..)
           if (sb == 0) {
-            if (g > 0) mbar_wait(&done[pslot], pph);  // the MMAs that last read this V half have completed
+            if (wait_v) mbar_wait(&done[pslot], pph);  // the MMAs that last read this V half have completed
             tc_fence_after();
           }
-          const uint32_t vcol = tmem_base + lane_base + kVCol0 + jh * 64 + (uint32_t)(H16 ? sb * 4 + cq * 2 : cq * 4);
+          const uint32_t vcol = tmem_base + lane_base + v_col0 + (db ? (g & 1) * 128 : 0u) + jh * 64 +
+                                (uint32_t)(H16 ? sb * 4 + cq * 2 : cq * 4);
           if (jh == 0) ffw_row_pass<0, H16>(d, vcol, fp16);  // warp-uniform
           else ffw_row_pass<1, H16>(d, vcol, fp16);
           if (sb == kSub - 1) {
@@ -395,10 +405,10 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
             for (int ec = 0; ec < n_chunks_p; ++ec)
 #pragma unroll
               for (int a = 0; a < 2; ++a) {
-                const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * kAccStride + (uint32_t)(ec * kEW + esub * 8);
+                const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * acc_stride + (uint32_t)(ec * kEW + esub * 8);
                 float z[2][8];
                 tmem_ld_x8(taddr, z[0]);
-                tmem_ld_x8(taddr + kAccStride, z[1]);
+                tmem_ld_x8(taddr + acc_stride, z[1]);
                 tmem_ld_wait();
                 const uint32_t dst = remote_base + ((uint32_t)(ec * 2 + a) * 64 + inbox_row) * 256;
 #pragma unroll
@@ -435,10 +445,10 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
           }
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
-            const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * kAccStride + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + lane_base + (uint32_t)(2 * a) * acc_stride + (uint32_t)c0;
             float z[2][8];  // z[b][e] = Y[a][b]
             tmem_ld_x8(taddr, z[0]);
-            tmem_ld_x8(taddr + kAccStride, z[1]);
+            tmem_ld_x8(taddr + acc_stride, z[1]);
             tmem_ld_wait();
             if constexpr (SPLIT) {  // add the other CTA's partial sums (the other half of the channel loop)
               const uint32_t src = smem_u32(smem) + ((uint32_t)(ec * 2 + a) * 64 + inbox_row) * 256;
@@ -526,7 +536,7 @@ wino3x3_ffw_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __re
 template <bool H16, bool CG2, bool SPLIT>
 static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                       int n_img, int C, int K, int relu, int out_padded, int mv, int grid, cudaStream_t stream,
-                      int fp16) {
+                      int fp16, int narrow) {
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
   cudaGetDevice(&dev_);
@@ -559,18 +569,18 @@ static int launch_ffw(const CUtensorMap& tmap, const float* u_img, const float* 
   cfg.attrs = attr;
   cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ffw_kernel<H16, CG2, SPLIT>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
-                                     out_padded, mv, fp16);
+                                     out_padded, mv, fp16, narrow);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 // split: clusters of 2 on one item each, grid = 2 * #items (the caller guarantees that this fits one wave and that the
 // layer's stage count is even)
 int wino_ffw_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
-                    int n_img, int C, int K, int op16, int cg2, int split, int relu, int out_padded, int mv, int grid,
-                    cudaStream_t stream) {
+                    int n_img, int C, int K, int op16, int cg2, int split, int narrow, int relu, int out_padded, int mv,
+                    int grid, cudaStream_t stream) {
 #define WG_FFW(H16_, CG2_, SPLIT_)                                                                                   \
   return launch_ffw<H16_, CG2_, SPLIT_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, mv, grid, stream, \
-                                        op16 == 2)
+                                        op16 == 2, narrow)
   if (split) {
     if (op16) WG_FFW(true, false, true);
     WG_FFW(false, false, true);

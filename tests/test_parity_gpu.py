@@ -144,12 +144,14 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
         lib_loaded.lib().wg_set_wino_kn(96)
 
 
-@pytest.mark.parametrize("knob", ["WG_FF_P9=0", "WG_FF_CG2=1", "WG_FF_W16=1", "WG_FF_W16=0", "WG_FF_SPLIT=2"])
+@pytest.mark.parametrize("knob", ["WG_FF_P9=0", "WG_FF_CG2=1", "WG_FF_W16=1", "WG_FF_W16=0", "WG_FF_SPLIT=2", "WG_FF_SPLIT=0",
+                                  "WG_FF_NARROW=0"])
 def test_3x3_full_fold_kernel_experiment_knobs(lib_loaded, knob):
     """The full-fold kernel's A/B knobs stay correct: WG_FF_P9=0 = the TM kernel's single-box raw layout, WG_FF_CG2=1 =
     CTA pairs (tcgen05 cta_group::2, clusters of 2; measured slower, default off), WG_FF_W16=1 / 0 = sixteen transform
     warps (wino_ffw_kernel.cu) for every layer / for none (default: 16-bit operands with C >= 256), WG_FF_SPLIT=2 =
-    split-C for every channel count (default: C >= 256). The knobs are read once per process, hence the subprocess."""
+    split-C for every channel count (default: C >= 256; 0 = never), WG_FF_NARROW=0 = never the 64-wide filter image.
+    The knobs are read once per process, hence the subprocess."""
     k, v = knob.split("=")
     env = dict(os.environ, **{k: v})
     k = k + "_" + v
