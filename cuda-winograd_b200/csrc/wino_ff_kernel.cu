@@ -791,7 +791,8 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
   if (!cg2 && dbg == 0 && wino_ff_p9()) {
     const int n_kb = C / (op16 ? 16 : 8);
     const int n_mb = (n_img * 49 + 127) / 128;
-    const bool split_ok = split_env && !(out_padded & 2) && (C >= 256 || split_env == 2) && n_kb % 2 == 0 && n_kb >= 4;
+    // (same choice with and without WG_OUT_MULTICAST: the fused gather must reproduce kernel + all-gather bit for bit)
+    const bool split_ok = split_env && (C >= 256 || split_env == 2) && n_kb % 2 == 0 && n_kb >= 4;
     // measured, 256->256, us per launch (Python loop): narrow + split 29-30 (N <= 32), default slices + split 34.5-36
     // (N <= 48), narrow 43.8 (N <= 96), default 46-50
     const bool narrow_ok = narrow_env && u_img_narrow != nullptr;
