@@ -61,19 +61,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time; test_wait returns at once).
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
 // Bounded wait: a pipeline bug must surface as a trapped kernel (launch error), never as a hung GPU.
 #ifndef WG_WAIT_TIMEOUT_NS
 #define WG_WAIT_TIMEOUT_NS 4000000000ull
