@@ -14,6 +14,10 @@ Batch-sharded across ranks with no collective on the hot path (weak scaling: 256
   e2e        images/s through the C-ABI call with HOST buffers (wg_run_host: pinned H2D + kernel + D2H every step)
   roofline   direct-conv-equivalent FLOPs per launch / measured launch time vs the tensor peak
   cpu_baseline  the NumPy FP32 golden (9 shifted sgemms + BN + ReLU, oracle/golden.py) timed on this box's host cores
+Extra keys (reported, outside the timed region): all_shapes (six README shapes, N=1 and N=256), strong_scaling
+(BASELINE configs[3]: global N=256 sharded over the ranks, 128/128 and 256/256, TF32 and bf16), bottleneck_block
+(configs[4]: 1x1 -> 3x3 -> 1x1 + residual + ReLU), cudnn_baseline (cuDNN on the same B200, reported baseline only),
+tensor_peak (the tcgen05 dense peaks measured on this device in this run: the roofline denominator).
 """
 import argparse
 import json
@@ -58,6 +62,58 @@ def peaks():
         return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
                     source="MEASURED_PEAKS.json")
     return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def measure_tensor_peaks(wg, dev_index):
+    """Roofline denominators measured on this device in this run: back-to-back tcgen05.mma on
+    every SM (wg_measure_tensor_peak; ms-long launches, i.e. the same burst regime the kernel launches are timed in),
+    next to cuBLAS TF32 / bf16 8192^3 matmuls through torch as a cross-check (reported only)."""
+    import torch
+    out = {}
+    for name, dt in (("tf32", wg.WG_TF32), ("bf16", wg.WG_BF16)):
+        tf, clk = wg.measure_tensor_peak(dt, dev_index)
+        out[f"{name}_tcgen05_tflops"] = tf
+        out[f"{name}_clk_per_mma_m128_n256"] = clk
+    try:
+        dev = torch.device("cuda", dev_index)
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        best = {}
+        for name, (x, y) in (("tf32", (a, b)), ("bf16", (a.bfloat16(), b.bfloat16()))):
+            torch.matmul(x, y)
+            torch.cuda.synchronize(dev)
+            t_best = 1e9
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(x, y)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                t_best = min(t_best, e0.elapsed_time(e1))
+            best[name] = 2 * 8192.0 ** 3 / (t_best * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = old
+        out["tf32_cublas_8192_tflops"] = best["tf32"]
+        out["bf16_cublas_8192_tflops"] = best["bf16"]
+        del a, b
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["cublas_note"] = str(e)[:120]
+    out["how"] = ("tcgen05: wg_measure_tensor_peak -- 20000 back-to-back M=128 N=256 MMAs per SM, operands in shared "
+                  "memory, best of 3 launches, CUDA events; cublas: torch.matmul 8192^3 best of 5 (allow_tf32)")
+    return out
+
+
+def traffic_from_profiles():
+    """Per-launch memory traffic of the headline kernel from THIS round's ncu capture (profiles/traffic_r02.json, written
+    by tools/ncu_summary.py from the committed raw CSV of an `ncu --set full` run with rotating buffers)."""
+    tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if not os.path.exists(tpath):
+        return None, None
+    d = json.load(open(tpath))
+    k = d.get("wino3x3_256_n256", {})
+    return k.get("dram_bytes_per_launch"), k
 
 
 class ClockSampler(threading.Thread):
@@ -178,7 +234,44 @@ def run_gpu(args):
         layer.run_host_ptr(xh[i % 2].data_ptr(), yh.data_ptr(), n)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    loss_like = float(yh[0, 0, 0, 0])  # the step's result is read on the host
+    # the step's result is read on the host: checksum of the whole host output, next to the device arm's on the same input
+    last = (e2e_steps - 1) % 2
+    host_sum = float(yh.double().sum())
+    host_abs = float(yh.double().abs().sum())
+    dev_y = layer(xs[last], out=ys[0])
+    dev_sum = float(dev_y.double().sum())
+    dev_maxdiff = float((dev_y.cpu() - yh).abs().max())
+    e2e_check = {"host_sum": host_sum, "device_sum": dev_sum, "sum_abs": host_abs,
+                 "rel_diff": abs(host_sum - dev_sum) / max(host_abs, 1e-30), "max_abs_diff_vs_device_arm": dev_maxdiff,
+                 "note": "wg_run_host output (chunks of 64,64,64,32,16,16 images, each through the kernel its size "
+                         "selects) vs the one-launch device arm on the same input; differences are fp32 summation order"}
+    # PCIe ceiling of this box for the same bytes: pinned H2D and D2H copies running concurrently on two streams
+    pcie = None
+    try:
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        xd_tmp, yd_tmp = torch.empty_like(xs[0]), ys[0]
+        for _ in range(2):
+            with torch.cuda.stream(s_in):
+                xd_tmp.copy_(xh[0], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                yh.copy_(yd_tmp, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(s_in):
+                xd_tmp.copy_(xh[0], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                yh.copy_(yd_tmp, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / reps
+        pcie = {"ms_per_step_copies_only": dt * 1e3, "images_per_s_ceiling": n / dt,
+                "h2d_gbs": n * 256 * C_IN * 4 / dt / 1e9, "d2h_gbs": n * 196 * C_OUT * 4 / dt / 1e9,
+                "how": "one 67 MB pinned H2D and one 51 MB pinned D2H copy per step, concurrently on two streams, "
+                       "no kernel: the ceiling of any host-buffer path on this box"}
+        del xd_tmp
+    except Exception as e:  # noqa: BLE001
+        pcie = {"unavailable": str(e)[:120]}
 
     # ---- optional: the one exchange step, an all-gather of the output shards (north_star), timed separately
     gather_ms = None
@@ -219,16 +312,19 @@ def run_gpu(args):
         gather_ms = gmax if gather_ms is not None else None
         fused_ms = fmax if fused_ms is not None else None
 
+    # ---- BASELINE configs[3] (strong scaling: global N=256 sharded over the ranks) and configs[4] (bottleneck block)
+    del xh
+    strong = strong_scaling(wg, dev, dist, world, rank)
+    block = bottleneck_block_bench(wg, dev, dist, world)
+
     if rank == 0:
         pk = peaks()
+        tpk = measure_tensor_peaks(wg, local)
         ms_per_step = ms / args.steps
         value = world * n * args.steps / (ms * 1e-3)
         tflops = FLOP_PER_IMAGE * n / (ms_per_step * 1e-3) / 1e12
-        tf32_peak = pk["bf16_sustained"] / 2.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("wino3x3_256_n256_dram_bytes_per_launch")
+        tf32_peak = tpk["tf32_tcgen05_tflops"]
+        traffic, traffic_detail = traffic_from_profiles()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -240,16 +336,26 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 256 * C_IN * 4,
                     "d2h_bytes_per_step": n * 196 * C_OUT * 4, "steps": e2e_steps, "api": "wg_run_host (C-ABI)",
-                    "result_read": loss_like},
+                    "result_check": e2e_check, "pcie_ceiling": pcie,
+                    "frac_of_pcie_ceiling": (n * e2e_steps / e2e_s) / pcie["images_per_s_ceiling"]
+                    if pcie and "images_per_s_ceiling" in pcie else None},
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": tflops / tf32_peak, "traffic": traffic,
                          "kernel": "wino3x3_ff_kernel (V in TMEM, inverse transform folded into the MMAs, 96-wide cout slices)",
                          "algorithmic": "direct-conv-equivalent 2*196*256*256*9 = 231.21 MFLOP/image x 256 images/launch",
-                         "peak_note": "dense TF32 = half of the measured sustained bf16 cuBLAS rate in " + pk["source"],
+                         "peak_note": "dense TF32 tcgen05 peak MEASURED in this run on this device (tensor_peak.tf32_tcgen05_tflops: "
+                                      "back-to-back kind::tf32 MMAs on every SM, ms-long launch = the burst regime the kernel "
+                                      "launches are timed in); MEASURED_PEAKS.json holds no TF32 figure",
+                         "frac_of_half_bf16_burst": tflops / (pk["bf16_burst"] / 2.0),
+                         "frac_of_half_bf16_sustained": tflops / (pk["bf16_sustained"] / 2.0),
+                         "traffic_detail": traffic_detail,
                          "hbm": {"achieved_gbs": (BYTES_PER_IMAGE * n + WEIGHT_BYTES) / (ms_per_step * 1e-3) / 1e9,
                                  "peak_gbs": pk["hbm"],
                                  "frac": (BYTES_PER_IMAGE * n + WEIGHT_BYTES) / (ms_per_step * 1e-3) / 1e9 / pk["hbm"]}},
+            "tensor_peak": tpk,
+            "strong_scaling": strong,
+            "bottleneck_block": block,
         }
         if gather_ms is not None:
             line["with_output_allgather"] = {"ms_per_step": gather_ms, "value": world * n / (gather_ms * 1e-3),
@@ -264,18 +370,199 @@ def run_gpu(args):
         if world == 1:
             # BASELINE.json's metric has two halves: us/layer at N=1 and throughput at N=256, for the six README
             # shapes. The headline above is one of them; the rest ride along (outside the timed region, 60 launches each).
-            del xs, ys, xh, yh
+            del xs, ys, yh
             torch.cuda.empty_cache()
             line["all_shapes"] = [
                 {"layer": f"{r['kind']} {r['cin']}->{r['cout']}" + ("+relu" if r["relu"] else ""), "n": r["n"],
                  "us_per_layer": round(r["us_per_layer"], 2), "images_per_s": round(r["images_per_s"]),
                  "frac_tf32_peak": round(r["frac_tf32_peak"], 4), "frac_hbm_peak": round(r["frac_hbm_peak"], 4)}
-                for r in measure_shapes(wg, dev, iters=60, sets_n256=3, verbose=False)]
+                for r in measure_shapes(wg, dev, iters=60, sets_n256=3, verbose=False, tf32_peak=tf32_peak)]
+            line["cudnn_baseline"] = cudnn_baseline(dev)
             line["cpu_baseline"] = cpu_baseline(budget_s=12.0)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------- BASELINE configs[3] / configs[4] / cuDNN
+def _time_loop(torch, dev, fn, sets, iters, dist=None):
+    """CUDA events around `iters` back-to-back calls (rotating `sets` buffers), barrier on both sides, max over ranks."""
+    for i in range(4):
+        fn(i % sets)
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % sets)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    if dist is not None:
+        t = torch.tensor([us], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item())
+    return us
+
+
+def strong_scaling(wg, dev, dist, world, rank):
+    """BASELINE.json configs[3]: 3x3 128/128 and 256/256 at GLOBAL batch N=256 sharded over the ranks (256 / world images
+    per GPU), TF32 and bf16 operands, compute only (no collective on the hot path) and -- 256/256 TF32, world > 1 -- with
+    the output all-gather fused into the kernel. At world == 1 the shard sizes of 2 / 4 / 8 GPUs are also timed on this
+    one GPU: shards are independent, so that IS the per-GPU time of the sharded run (efficiency_projected); the driver's
+    multi-GPU runs report the measured time at their own world size (efficiency vs the same line's n=256 single shard)."""
+    import numpy as np
+    import torch
+    out = {"global_batch": 256, "world": world, "rows": []}
+    shards = [256, 128, 64, 32] if world == 1 else [256, 256 // world]
+    for c in (128, 256):
+        rs = np.random.RandomState(c)
+        w = (rs.rand(c, c, 3, 3) - 0.5).astype(np.float32)
+        sc, sh = (rs.rand(c) + 0.5).astype(np.float32), (rs.rand(c) - 0.5).astype(np.float32)
+        for name, dt in (("tf32", wg.WG_TF32), ("bf16", wg.WG_BF16)):
+            layer = wg.Conv3x3BnRelu(w, sc, sh, relu=True, device=dev.index, dtype=dt)
+            base_us = None
+            for nl in shards:
+                sets = max(2, min(8, int(300e6 // (nl * (256 * c + 196 * c) * 4)) + 1))
+                xs = [torch.rand((nl, 16, 16, c), device=dev) - 0.5 for _ in range(sets)]
+                ys = [torch.empty((nl, 14, 14, c), device=dev) for _ in range(sets)]
+                us = _time_loop(torch, dev, lambda i: layer(xs[i], out=ys[i]), sets, 60, dist)
+                if nl == 256:
+                    base_us = us
+                row = {"layer": f"3x3 {c}->{c}", "dtype": name, "images_per_gpu": nl, "gpus": 256 // nl,
+                       "us_per_step": round(us, 2), "images_per_s_global": round(256 / (us * 1e-6)),
+                       "speedup_vs_1gpu": round(base_us / us, 3) if base_us else None,
+                       "efficiency": round(base_us / us / (256 // nl), 3) if base_us else None,
+                       "measured_on": f"{world} GPU(s)" + ("" if world > 1 or nl == 256 else
+                                                             " (one shard of the sharded run, timed on this GPU)")}
+                if world > 1 and nl != 256 and c == 256 and name == "tf32":
+                    try:
+                        fused = wg.FusedGatherConv3x3(layer, nl)
+                        row["with_fused_gather_us"] = round(_time_loop(torch, dev, lambda i: fused(xs[i]), sets, 30, dist), 2)
+                        gathered = torch.empty((world * nl, 14, 14, c), device=dev)
+
+                        def nccl_step(i):
+                            layer(xs[i], out=ys[i])
+                            dist.all_gather_into_tensor(gathered, ys[i])
+                        row["with_nccl_allgather_us"] = round(_time_loop(torch, dev, nccl_step, sets, 30, dist), 2)
+                        del fused, gathered
+                    except Exception as e:  # noqa: BLE001
+                        row["fused_gather_note"] = str(e)[:160]
+                out["rows"].append(row)
+                del xs, ys
+            layer.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def bottleneck_block_bench(wg, dev, dist, world):
+    """BASELINE.json configs[4]: the full ResNet-50 bottleneck residual block 1x1 -> 3x3 -> 1x1 (+ x, ReLU), three fused
+    launches (cuda_winograd_b200.Bottleneck(residual=True)), 256 images per GPU per step (weak) and global N=256 sharded
+    (strong), max over ranks; at world == 1 next to cuDNN's fused conv+bias+ReLU chain (+ add + ReLU) through torch."""
+    import numpy as np
+    import torch
+    rows = []
+    for ch, c in ((512, 128), (1024, 256)):
+        rs = np.random.RandomState(ch)
+        w1 = ((rs.rand(ch, c) - 0.5) * 0.2).astype(np.float32)
+        w3 = ((rs.rand(c, c, 3, 3) - 0.5) * 0.2).astype(np.float32)
+        w2 = ((rs.rand(c, ch) - 0.5) * 0.2).astype(np.float32)
+        bn = [((rs.rand(k) + 0.5).astype(np.float32), (rs.rand(k) - 0.3).astype(np.float32)) for k in (c, c, ch)]
+        block = wg.Bottleneck(w1, *bn[0], w3, *bn[1], w2, *bn[2], device=dev.index, residual=True)
+        flop_img = 2.0 * 196 * (ch * c + 9 * c * c + c * ch)
+        for nl in sorted({256, 256 // world}, reverse=True):
+            sets = 2 if nl == 256 else 4
+            xs = [torch.rand((nl, 196, ch), device=dev) - 0.5 for _ in range(sets)]
+            outs = [torch.empty((nl, 196, ch), device=dev) for _ in range(sets)]
+            us = _time_loop(torch, dev, lambda i: block(xs[i], out=outs[i]), sets, 30, dist)
+            row = {"block": f"{ch}->{c}->{c}->{ch} +residual", "images_per_gpu": nl, "gpus": world,
+                   "scaling": "weak" if nl == 256 else "strong (global N=256)", "us_per_step": round(us, 1),
+                   "images_per_s": round(world * nl / (us * 1e-6)),
+                   "tflops_direct_equiv_per_gpu": round(flop_img * nl / us * 1e-6, 1), "launches_per_step": 3}
+            if world == 1:
+                try:
+                    row["cudnn_tf32_us"] = round(_cudnn_block_us(torch, dev, xs, w1, w3, w2, bn, nl, ch, c), 1)
+                except Exception as e:  # noqa: BLE001
+                    row["cudnn_note"] = str(e)[:160]
+            rows.append(row)
+            del xs, outs
+        del block
+    torch.cuda.empty_cache()
+    return rows
+
+
+def _cudnn_block_us(torch, dev, xs, w1, w3, w2, bn, n, ch, c):
+    """cuDNN on the same GPU (reported baseline only): fused conv+bias+ReLU x2, conv+bias, add, ReLU; channels_last."""
+    cl = torch.channels_last
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    k1 = torch.from_numpy((w1.T * bn[0][0][:, None])[:, :, None, None].copy()).to(dev).contiguous(memory_format=cl)
+    k3 = torch.from_numpy(w3 * bn[1][0][:, None, None, None]).to(dev).contiguous(memory_format=cl)
+    k2 = torch.from_numpy((w2.T * bn[2][0][:, None])[:, :, None, None].copy()).to(dev).contiguous(memory_format=cl)
+    b1, b3, b2 = (torch.from_numpy(b[1]).to(dev) for b in bn)
+    x_cl = [t.view(n, 14, 14, ch).permute(0, 3, 1, 2) for t in xs]
+
+    def chain(i):
+        a = torch.cudnn_convolution_relu(x_cl[i], k1, b1, (1, 1), (0, 0), (1, 1), 1)
+        a = torch.cudnn_convolution_relu(a, k3, b3, (1, 1), (1, 1), (1, 1), 1)
+        return torch.relu_(torch.nn.functional.conv2d(a, k2, b2).add_(x_cl[i]))
+    return _time_loop(torch, dev, chain, len(xs), 30)
+
+
+def cudnn_baseline(dev):
+    """Reported baseline only (north_star: "cuDNN's Winograd/implicit-GEMM fused conv+BN+ReLU on the same B200"): cuDNN
+    through torch (cudnn_convolution_relu = cudnnConvolutionBiasActivationForward, BN scale folded into the weights,
+    shift as bias, channels_last), the six README shapes at N=256 (rotating buffers) and N=1 (CUDA graph of back-to-back
+    launches), TF32 allowed; 3x3 also with bf16 tensors. Never on the product path: nothing under cuda-winograd_b200/
+    links or calls cuDNN."""
+    import numpy as np
+    import torch
+    rows = []
+    try:
+        torch.backends.cudnn.benchmark = True
+        for kind, cin, cout, relu in [("3x3", 128, 128, True), ("3x3", 256, 256, True), ("1x1", 512, 128, True),
+                                      ("1x1", 128, 512, False), ("1x1", 1024, 256, True), ("1x1", 256, 1024, False)]:
+            rs = np.random.RandomState(0)
+            ks = 3 if kind == "3x3" else 1
+            wt = torch.from_numpy((rs.rand(cout, cin, ks, ks) - 0.5).astype(np.float32)).to(dev)
+            wt = wt.contiguous(memory_format=torch.channels_last)
+            bias = torch.from_numpy((rs.rand(cout) - 0.5).astype(np.float32)).to(dev)
+            hw = 16 if kind == "3x3" else 14
+            row = {"layer": f"{kind} {cin}->{cout}" + ("+relu" if relu else "")}
+            for n in (256, 1):
+                sets = 3 if n == 256 else 1
+                xs = [(torch.rand((n, hw, hw, cin), device=dev) - 0.5).permute(0, 3, 1, 2) for _ in range(sets)]
+                for name, dt in (("tf32", torch.float32),) + ((("bf16", torch.bfloat16),) if kind == "3x3" else ()):
+                    torch.backends.cudnn.allow_tf32 = True
+                    xq = [t.to(dt) for t in xs] if dt != torch.float32 else xs
+                    wq, bq = wt.to(dt), bias.to(dt)
+                    if relu:
+                        f = lambda i: torch.cudnn_convolution_relu(xq[i], wq, bq, (1, 1), (0, 0), (1, 1), 1)  # noqa: E731
+                    else:
+                        f = lambda i: torch.nn.functional.conv2d(xq[i], wq, bq)  # noqa: E731
+                    if n == 256:
+                        us = _time_loop(torch, dev, f, sets, 40)
+                    else:
+                        for _ in range(3):
+                            f(0)
+                        torch.cuda.synchronize(dev)
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            for _ in range(100):
+                                f(0)
+                        us = _time_loop(torch, dev, lambda i: g.replay(), 1, 5) / 100
+                        del g
+                    row[f"cudnn_{name}_n{n}_us"] = round(us, 2)
+                del xs
+            rows.append(row)
+        torch.cuda.empty_cache()
+        return {"cudnn_version": torch.backends.cudnn.version(), "rows": rows,
+                "note": "reported baseline only; same process, same GPU, CUDA events; N=256 rotating buffers, N=1 CUDA graph"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200], "rows": rows}
 
 
 # ----------------------------------------------------------------------------------------------------------- CPU arm
@@ -359,12 +646,14 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- all README shapes
-def measure_shapes(wg, dev, iters=200, sets_n256=N_SETS, verbose=True):
+def measure_shapes(wg, dev, iters=200, sets_n256=N_SETS, verbose=True, tf32_peak=None):
     """Every README shape: N=1 latency (L2-warm, like the reference's loop) and N=256 throughput (rotating buffers),
     CUDA events. Returns one row per (shape, N)."""
     import numpy as np
     import torch
     pk = peaks()
+    if tf32_peak is None:
+        tf32_peak = wg.measure_tensor_peak(wg.WG_TF32, dev.index)[0]
     rows = []
     shapes = [("3x3", 128, 128, True), ("3x3", 256, 256, True), ("1x1", 512, 128, True), ("1x1", 128, 512, False),
               ("1x1", 1024, 256, True), ("1x1", 256, 1024, False)]
@@ -416,7 +705,7 @@ def measure_shapes(wg, dev, iters=200, sets_n256=N_SETS, verbose=True):
                        timing="cuda graph of back-to-back launches" if n == 1 else "python loop, rotating buffers",
                        images_per_s=n / (us * 1e-6), tflops_direct_equiv=flops / us * 1e-6,
                        hbm_gbs_algorithmic=byts / us * 1e-3,
-                       frac_tf32_peak=flops / us * 1e-6 / (pk["bf16_sustained"] / 2),
+                       frac_tf32_peak=flops / us * 1e-6 / tf32_peak,
                        frac_hbm_peak=byts / us * 1e-3 / pk["hbm"])
             rows.append(row)
             if verbose:

@@ -18,14 +18,22 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libwinograd_b200.so")
+# developer build (make dev): superseded kernel generations, ablation instantiations, WG_* environment knobs. Only the
+# tools/ scripts and the developer tests select it, with WG_B200_DEV_LIB=1 in the environment.
+DEV_LIB_PATH = os.path.join(_ROOT, "tools", "libwinograd_b200_dev.so")
+IS_DEV_LIB = os.environ.get("WG_B200_DEV_LIB", "0") == "1"
+if IS_DEV_LIB:
+    LIB_PATH = DEV_LIB_PATH
 
 WG_TF32, WG_BF16, WG_FP16 = 0, 1, 2
+WG_OUT_PADDED, WG_OUT_MULTICAST, WG_OUT_RELU_AFTER_ADD = 1, 2, 4
 
 # every symbol include/winograd_b200.h, include/wg_legacy.h and include/util.h declare
 ABI_SYMBOLS = (
-    "wg_conv3x3_create", "wg_conv1x1_create", "wg_run", "wg_run_host", "wg_destroy", "wg_layer_info",
+    "wg_conv3x3_create", "wg_conv1x1_create", "wg_run", "wg_run_residual", "wg_run_host", "wg_host_chunk_schedule",
+    "wg_destroy", "wg_layer_info", "wg_layer_serialize", "wg_layer_deserialize", "wg_layer_save", "wg_layer_load",
     "wg_launch_count", "wg_strerror", "wg_last_cuda_error", "wg_device_count", "wg_fold_bn", "wg_set_max_ctas",
-    "wg_set_wino_kn",
+    "wg_measure_tensor_peak",
     "kernel_128", "kernel_256", "kernel_128_1_in", "kernel_128_1_out", "kernel_256_1_in", "kernel_256_1_out",
     "wg_set_baseline_hook", "wg_legacy_last_output",
     "get_parameter", "transpose", "getTimeMicroseconds64", "output_checker",
@@ -63,7 +71,18 @@ def lib() -> ctypes.CDLL:
         L.wg_conv1x1_create.argtypes = L.wg_conv3x3_create.argtypes
         L.wg_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                              ctypes.c_void_p]
+        L.wg_run_residual.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_void_p]
         L.wg_run_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.wg_host_chunk_schedule.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        L.wg_layer_serialize.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                         ctypes.POINTER(ctypes.c_size_t)]
+        L.wg_layer_deserialize.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_int]
+        L.wg_layer_save.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.wg_layer_load.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_int]
+        L.wg_measure_tensor_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                             ctypes.POINTER(ctypes.c_double)]
         L.wg_destroy.argtypes = [ctypes.c_void_p]
         L.wg_layer_info.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 4
         L.wg_launch_count.restype = ctypes.c_longlong
@@ -73,7 +92,8 @@ def lib() -> ctypes.CDLL:
         L.wg_fold_bn.argtypes = [ctypes.c_int, c_fp, c_fp, c_fp, c_fp, ctypes.c_float, c_fp, c_fp]
         L.wg_fold_bn.restype = None
         L.wg_set_max_ctas.argtypes = [ctypes.c_int]
-        L.wg_set_wino_kn.argtypes = [ctypes.c_int]
+        if IS_DEV_LIB:
+            L.wg_dev_set_wino_kn.argtypes = [ctypes.c_int]
         L.wg_legacy_last_output.argtypes = [c_fp, ctypes.c_int]
         _lib = L
     return _lib
@@ -99,6 +119,21 @@ def launch_count() -> int:
     return int(lib().wg_launch_count())
 
 
+def host_chunk_schedule(n: int):
+    """Chunk sizes wg_run_host uses for a batch of n images (host-only logic; no GPU needed)."""
+    buf = (ctypes.c_int * 64)()
+    k = int(lib().wg_host_chunk_schedule(int(n), buf, 64))
+    assert 0 <= k <= 64, k
+    return [int(buf[i]) for i in range(k)]
+
+
+def measure_tensor_peak(dtype=WG_TF32, device=0):
+    """(TFLOP/s, clocks per M=128 N=256 MMA) of back-to-back tcgen05.mma on every SM of `device` (wg_measure_tensor_peak)."""
+    tf, clk = ctypes.c_double(), ctypes.c_double()
+    _check(lib().wg_measure_tensor_peak(device, dtype, ctypes.byref(tf), ctypes.byref(clk)), "wg_measure_tensor_peak")
+    return tf.value, clk.value
+
+
 def fold_bn(gamma, beta, mean, var, eps=1e-5):
     """Folded BN exactly as data_generator.py:41-47 (float32)."""
     import numpy as np
@@ -115,6 +150,7 @@ class _Layer:
     def __init__(self, cin, cout, w, scale, shift, relu, device=0, dtype=WG_TF32):
         import numpy as np
         self.cin, self.cout, self.relu, self.device = int(cin), int(cout), bool(relu), int(device)
+        self.dtype = int(dtype)
         w = np.ascontiguousarray(w, np.float32)
         scale = np.ascontiguousarray(scale, np.float32)
         shift = np.ascontiguousarray(shift, np.float32)
@@ -124,8 +160,46 @@ class _Layer:
         _check(create(ctypes.byref(self._h), cin, cout, _fptr(w), _fptr(scale), _fptr(shift), int(relu), dtype,
                       device), "create")
 
+    # -- packed blob (wg_layer_save / wg_layer_load): cold start without the filter transform
+    def save(self, path):
+        _check(lib().wg_layer_save(self._h, os.fsencode(path)), "wg_layer_save")
+
+    def serialize(self) -> bytes:
+        need = ctypes.c_size_t()
+        _check(lib().wg_layer_serialize(self._h, None, 0, ctypes.byref(need)), "wg_layer_serialize")
+        buf = ctypes.create_string_buffer(need.value)
+        _check(lib().wg_layer_serialize(self._h, buf, need.value, ctypes.byref(need)), "wg_layer_serialize")
+        return buf.raw
+
+    @classmethod
+    def _from_handle(cls, h, device):
+        kind, cin, cout, relu = (ctypes.c_int() for _ in range(4))
+        _check(lib().wg_layer_info(h, ctypes.byref(kind), ctypes.byref(cin), ctypes.byref(cout), ctypes.byref(relu)),
+               "wg_layer_info")
+        sub = Conv3x3BnRelu if kind.value == 0 else Conv1x1Bn
+        self = sub.__new__(sub)
+        self.cin, self.cout, self.relu, self.device = cin.value, cout.value, bool(relu.value), int(device)
+        self.dtype = WG_TF32
+        self._h = h
+        return self
+
+    @staticmethod
+    def load(path, device=0):
+        """Layer from a blob written by save(): Conv3x3BnRelu or Conv1x1Bn, whichever the blob holds."""
+        h = ctypes.c_void_p()
+        _check(lib().wg_layer_load(ctypes.byref(h), os.fsencode(path), device), "wg_layer_load")
+        return _Layer._from_handle(h, device)
+
+    @staticmethod
+    def deserialize(blob: bytes, device=0):
+        h = ctypes.c_void_p()
+        _check(lib().wg_layer_deserialize(ctypes.byref(h), blob, len(blob), device), "wg_layer_deserialize")
+        return _Layer._from_handle(h, device)
+
     # -- device tensors (torch is only the allocator / stream provider here)
-    def __call__(self, x, out=None, out_padded=False):
+    def __call__(self, x, out=None, out_padded=False, residual=None, relu_after_add=False):
+        """One fused launch. residual (1x1 layers, dense output): y = act2(act(scale * conv + shift) + residual), the
+        add that follows the reference's `_out` layers (Kernel128_one.cu:271-272), act2 = ReLU iff relu_after_add."""
         import torch
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.device.index == self.device
         n = x.shape[0]
@@ -134,9 +208,19 @@ class _Layer:
         if out is None:
             out = torch.empty(oshape, device=x.device, dtype=torch.float32)
         assert tuple(out.shape) == oshape and out.is_contiguous() and out.dtype == torch.float32
+        assert out.device == x.device
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        _check(lib().wg_run(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n,
-                            int(bool(out_padded)), ctypes.c_void_p(stream)), "wg_run")
+        flags = WG_OUT_PADDED if out_padded else 0
+        if residual is not None:
+            assert residual.is_cuda and residual.dtype == torch.float32 and residual.is_contiguous()
+            assert residual.device == x.device and residual.numel() == out.numel() and not out_padded
+            flags |= WG_OUT_RELU_AFTER_ADD if relu_after_add else 0
+            _check(lib().wg_run_residual(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(residual.data_ptr()),
+                                         ctypes.c_void_p(out.data_ptr()), n, flags, ctypes.c_void_p(stream)),
+                   "wg_run_residual")
+            return out
+        _check(lib().wg_run(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, flags,
+                            ctypes.c_void_p(stream)), "wg_run")
         return out
 
     # -- host buffers, end to end (H2D + kernel + D2H inside)
@@ -147,6 +231,10 @@ class _Layer:
         assert tuple(x_host.shape[1:]) == self.in_shape()
         if y_host is None:
             y_host = np.empty((n,) + self.out_shape(out_padded), np.float32)
+        # the C side writes n * prod(out_shape) floats through this pointer: it must be exactly that buffer
+        assert isinstance(y_host, np.ndarray) and y_host.dtype == np.float32 and y_host.flags["C_CONTIGUOUS"] \
+            and y_host.flags["WRITEABLE"] and tuple(y_host.shape) == (n,) + self.out_shape(out_padded), \
+            "y_host must be a writable C-contiguous float32 array of shape (n,) + out_shape(out_padded)"
         _check(lib().wg_run_host(self._h, x_host.ctypes.data, y_host.ctypes.data, n, int(bool(out_padded))),
                "wg_run_host")
         return y_host
@@ -194,9 +282,11 @@ class Conv1x1Bn(_Layer):
     Kernel256_one.cu:100,318)."""
     kind = 1
 
-    def __init__(self, w_cin_cout, scale, shift, relu, device=0):
+    def __init__(self, w_cin_cout, scale, shift, relu, device=0, dtype=WG_TF32):
+        """dtype = WG_TF32 (default; tolerance 1e-3) or WG_BF16 (bf16 operands: the activation stage is converted into
+        tensor memory by four extra warps, bf16 weight image; fp32 I/O and accumulation; tolerance 1e-2)."""
         cin, cout = w_cin_cout.shape
-        super().__init__(cin, cout, w_cin_cout, scale, shift, relu, device)
+        super().__init__(cin, cout, w_cin_cout, scale, shift, relu, device, dtype)
 
     def in_shape(self):
         return (196, self.cin)
@@ -211,14 +301,18 @@ class Bottleneck:
     three layer kinds of the reference chained the way its layouts suggest (SURVEY.md section 8f rank 1;
     BASELINE.json configs[4]): the first 1x1 writes the zero-bordered 16x16 frame (Kernel128_winograd.cu:163,243
     layout) that the 3x3 consumes, the 3x3 writes dense [N,14,14,C] = [N,196,C] for the last 1x1. Three kernel
-    launches, intermediates stay in L2/HBM, no padding or layout pass in between. The residual add is not part of
-    the reference (its `_out` kernels stop before it, Kernel128_one.cu:272) and is not done here."""
+    launches, intermediates stay in L2/HBM, no padding or layout pass in between.
+    residual=True (needs Cin == Cout) completes the block: out = relu(chain(x) + x), the add and the final ReLU fused
+    into the last 1x1 launch's epilogue (the reference's `_out` kernels stop right before it, Kernel128_one.cu:271-272,
+    Kernel256_one.cu:273) -- still three launches."""
 
-    def __init__(self, w1, s1, b1, w3, s3, b3, w2, s2, b2, device=0, dtype=WG_TF32):
+    def __init__(self, w1, s1, b1, w3, s3, b3, w2, s2, b2, device=0, dtype=WG_TF32, residual=False):
         self.l1 = Conv1x1Bn(w1, s1, b1, relu=True, device=device)
         self.l3 = Conv3x3BnRelu(w3, s3, b3, relu=True, device=device, dtype=dtype)
         self.l2 = Conv1x1Bn(w2, s2, b2, relu=False, device=device)
         assert self.l1.cout == self.l3.cin and self.l3.cout == self.l2.cin
+        self.residual = bool(residual)
+        assert not self.residual or self.l1.cin == self.l2.cout, "the identity shortcut needs Cin == Cout"
         self._bufs = {}
 
     def __call__(self, x, out=None):
@@ -231,6 +325,8 @@ class Bottleneck:
         frame, mid = self._bufs[key]
         self.l1(x, out=frame, out_padded=True)
         self.l3(frame, out=mid)
+        if self.residual:
+            return self.l2(mid.view(n, 196, self.l3.cout), out=out, residual=x, relu_after_add=True)
         return self.l2(mid.view(n, 196, self.l3.cout), out=out)
 
     def capture(self, x, out=None):
@@ -309,9 +405,6 @@ def gather_output(y_local, n_total: int, group=None):
     return torch.cat([out[r * nmax:r * nmax + (h - l)] for r, (l, h) in enumerate(sizes)], dim=0)
 
 
-WG_OUT_PADDED, WG_OUT_MULTICAST = 1, 2
-
-
 class FusedGatherConv3x3:
     """conv3x3 + BN + ReLU fused with the all-gather of its output over NVSwitch (SURVEY.md section 8e names one gather
     of the fp32 output as the path's only exchange). Every rank owns `n_local` images; the gathered
@@ -340,10 +433,16 @@ class FusedGatherConv3x3:
         self.y_mc = self.hdl.multicast_ptr + self.rank * self.shard_bytes
 
     def __call__(self, x):
+        """Returns the gathered tensor (symmetric memory, REUSED by the next call). Two cross-rank barriers on the
+        stream per call: one BEFORE the kernel -- a fast rank's multimem.st must not land in a slower rank's copy while
+        that rank's consumers of the previous result are still reading it (work enqueued on this stream before this
+        call is covered; readers on other streams are the caller's to order) -- and one after it (all shards landed)."""
         import torch
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == self.n_local
+        assert x.device.index == self.layer.device
         stream = torch.cuda.current_stream(x.device).cuda_stream
         flags = WG_OUT_MULTICAST | (WG_OUT_PADDED if self.out_padded else 0)
+        self.hdl.barrier()          # every rank has finished reading the previous gathered result
         _check(lib().wg_run(self.layer._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(self.y_mc), self.n_local,
                             flags, ctypes.c_void_p(stream)), "wg_run (multicast)")
         self.hdl.barrier()          # all ranks' kernels are complete: every shard has landed everywhere

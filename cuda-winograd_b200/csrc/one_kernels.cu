@@ -12,6 +12,8 @@
 // (full 128-byte lines to L2; rows beyond M are clipped by the tensor map).
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+
 #include "ptx.cuh"
 #include "wg_internal.h"
 
@@ -22,18 +24,20 @@ constexpr int kBK = 32;  // fp32 channels per stage = one 128-byte swizzle row
 
 // WS = weight-stationary: the whole [BN x Cin] weight tile stays resident in shared memory (<= 128 KB) while the CTA
 // walks the M-tiles of ONE N-tile; the stage ring then carries activations only.
-template <int BN, bool WS = false>
+// H16: bf16 operands -- the weight block is [4 k-chunks][BN couts][8 bf16] (K-major, no swizzle), half the bytes.
+template <int BN, bool WS = false, bool H16 = false>
 struct OneSmem {
   static constexpr int kStages = WS ? 4 : (BN == 256 ? 4 : 6);
   static constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 128 B
-  static constexpr uint32_t kBBytes = BN * 128;   // one 32-channel block of the weight tile
+  static constexpr uint32_t kBBytes = BN * (H16 ? 64 : 128);  // one 32-channel block of the weight tile
   static constexpr uint32_t kBResident = 128 * 1024;
   static constexpr uint32_t kStageOutBytes = 32 * 128;  // one warp's 32 rows x 32 fp32 columns
   static constexpr uint32_t kOffA = 0;
   static constexpr uint32_t kOffB = kOffA + kStages * kABytes;
   static constexpr uint32_t kOffOut = kOffB + (WS ? kBResident : kStages * kBBytes);  // [4 warps][2 buffers]
   static constexpr uint32_t kOffBar = kOffOut + 4 * 2 * kStageOutBytes;
-  static constexpr uint32_t kNumBars = 2 * kStages + 5;
+  // + [4 epilogue warps][2 buffers] "residual sub-tile landed" + H16: [stages] "A stage converted into TMEM"
+  static constexpr uint32_t kNumBars = 2 * kStages + 5 + 8 + kStages;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;  // + slack for manual 1024-B alignment
   static_assert(kOffOut % 1024 == 0, "swizzled staging must be 1024-byte aligned");
@@ -56,16 +60,29 @@ struct OneSmem {
 // 512->128 27.2 -> 27.5: the weight traffic is not what these kernels wait for. (Neither is the epilogue's instruction
 // count per se: eight epilogue warps ran 256->1024 in 78 us, epilogue warps storing the dense output themselves instead
 // of TMA tensor stores in 85 us.) Default off.
-template <int BN, int CL, bool WS = false, bool PAIR = false>
-__global__ void __launch_bounds__(kOneThreads, 1)
+// RES: residual add fused into the epilogue (the step that follows the reference's `_out` layers, which is why those
+// stop before the ReLU -- Kernel128_one.cu:271-272, Kernel256_one.cu:273): y = [relu](scale * acc + shift + r). The
+// residual sub-tile (32 rows x 32 couts, same geometry as the output sub-tile) is TMA-loaded straight INTO the warp's
+// output staging buffer one chunk ahead, the epilogue adds in place and TMA-stores the same buffer: no extra shared
+// memory, one extra HBM read of the output's size.
+// H16: bf16 operands (the stated bf16 variant of the 1x1 path; fp32 I/O and accumulation, tolerance 1e-2). The activation
+// still arrives as fp32 through TMA; four extra warps (6..9) convert each 128 x 32 stage to bf16 pairs and write it into
+// TENSOR MEMORY (16 columns per stage, ring of kStages), from where the MMAs (kind::f16, K = 16, two per stage) read it
+// as their A operand -- the same V-in-TMEM hand-off as the 3x3 kernels. B = bf16 weight image in shared memory.
+template <int BN, int CL, bool WS = false, bool PAIR = false, bool RES = false, bool H16 = false>
+__global__ void __launch_bounds__(H16 ? kOneThreads + 128 : kOneThreads, 1)
 conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
-                      const float* __restrict__ w_img, const float* __restrict__ scale,
-                      const float* __restrict__ shift, float* __restrict__ y_padded, long long m_rows, int Cin,
-                      int Cout, int relu, int bn_packed) {
-  using S = OneSmem<BN, WS>;
+                      const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ w_img,
+                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y_padded,
+                      long long m_rows, int Cin, int Cout, int relu, int bn_packed, int relu_after) {
+  using S = OneSmem<BN, WS, H16>;
+  static_assert(!RES || (CL == 1 && !PAIR), "the residual epilogue exists for the plain and weight-stationary schedules");
   static_assert(!WS || CL == 1, "weight-stationary schedule has no cluster variant");
   static_assert(!PAIR || (CL == 2 && !WS), "CTA pairs are clusters of 2");
-  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers
+  static_assert(!H16 || (BN == 128 && CL == 1 && !WS && !PAIR), "bf16 operands: plain schedule, 128-wide N-tiles");
+  // two accumulator buffers (+ H16: the A ring, 16 columns per stage, after them; allocation is a power of two)
+  constexpr uint32_t kTmemCols = H16 ? 512 : 2 * BN;
+  constexpr uint32_t kACol0 = 2 * BN;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage buffers
@@ -80,6 +97,8 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint64_t* acc_full = empty + S::kStages;  // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint64_t* b_full = acc_empty + 2;         // WS: the resident weight tile has landed
+  uint64_t* res_full = b_full + 1;          // RES: [epilogue warp][buffer]
+  uint64_t* a_ready = res_full + 8;         // H16: [stage] converted A stage is in TMEM (4 converter warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
 
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
@@ -90,13 +109,17 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     for (int i = 0; i < S::kStages; ++i) {
       // PAIR, leader: own TMA bytes + the peer's relay; one multicast commit frees a stage in both CTAs
       mbar_init(&full[i], (PAIR && crank == 0) ? 2 : 1);
-      mbar_init(&empty[i], PAIR ? 1 : CL);  // every CTA of the cluster must have consumed a stage before it is refilled
+      // every CTA of the cluster must have consumed a stage before it is refilled; H16: the 4 converter warps (done
+      // reading the fp32 stage) + the commit of the MMAs that read the weight block and the TMEM A slot
+      mbar_init(&empty[i], H16 ? 5 : (PAIR ? 1 : CL));
+      mbar_init(&a_ready[i], 4);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], PAIR ? 8 : 4);
     }
     mbar_init(b_full, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -119,8 +142,10 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int ws_nt = (int)blockIdx.x % n_ntiles;
   // weight image: [Cout/bn_packed][Cin/32][bn_packed rows][128 B]; this kernel's N-tile may be a BN-row slice of a packed
   // tile (bn_packed is a multiple of BN; the swizzle only depends on row % 8)
-  const size_t b_kb_stride = (size_t)bn_packed * 128;
+  // (H16: [Cout/BN][Cin/32][4 k-chunks][BN couts][8 bf16], one contiguous block per (N-tile, 32-channel block))
+  const size_t b_kb_stride = H16 ? (size_t)S::kBBytes : (size_t)bn_packed * 128;
   auto b_tile = [&](int nt) {
+    if constexpr (H16) return reinterpret_cast<const uint8_t*>(w_img) + (size_t)nt * n_kb * S::kBBytes;
     const int col0 = nt * BN;
     return reinterpret_cast<const uint8_t*>(w_img) + ((size_t)(col0 / bn_packed) * n_kb * bn_packed + col0 % bn_packed) * 128;
   };
@@ -186,7 +211,18 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         tc_fence_after();
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full[st], ph);
+          if constexpr (H16) mbar_wait(&a_ready[st], ph);  // the converter warps have written this stage's A into TMEM
           tc_fence_after();
+          if constexpr (H16) {
+            constexpr uint32_t idesc16 = make_idesc(kFmtBF16, 128, BN);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // B: [4 k-chunks][BN couts][16 B]; MMA k uses chunks 2k, 2k+1 (LBO = chunk pitch, SBO = 8 couts)
+              const uint64_t b_desc = make_smem_desc(b_base + st * S::kBBytes + k * 2 * (BN * 16), BN * 16, 128, kLayoutNone);
+              umma_f16_ts(tmem_base + buf * BN, tmem_base + kACol0 + st * 16 + k * 8, b_desc, idesc16,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             const uint64_t a_desc = make_smem_desc(a_base + st * S::kABytes + k * 32, 0, 1024, kLayoutSW128);
@@ -194,6 +230,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 make_smem_desc(b_base + (WS ? kb : (int)st) * S::kBBytes + k * 32, 0, 1024, kLayoutSW128);
             if constexpr (PAIR) umma_tf32_ss_cg2(tmem_base + buf * BN, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             else umma_tf32_ss(tmem_base + buf * BN, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
           }
           if constexpr (PAIR) umma_commit_mcast_cg2(&empty[st], kClusterMask);
           else if constexpr (CL == 1) umma_commit(&empty[st]);
@@ -204,11 +241,61 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         else umma_commit(&acc_full[buf]);
       }
     }
+  } else if (H16 && warp >= 6) {
+    // bf16 operands: converter warps. Thread = one row of the 128 x 32 fp32 stage (TMEM lane = row): 8 LDS.128 of its
+    // swizzled 128-byte row, 16 bf16 pairs (column c = channels 2c | 2c+1 << 16), 4 tcgen05.st.x4.
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t a_base = smem_u32(smem + S::kOffA);
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + kACol0;
+    uint32_t st = 0, ph = 0;
+    for (int item = first_item; item < n_items; item += item_stride)
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&full[st], ph);
+        const uint32_t src = a_base + st * S::kABytes + (uint32_t)row * 128;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = ld_shared_v4(src + ((j ^ (row & 7)) << 4));
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // 8 channels -> 4 columns per x4 store
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[2 * q].x, v[2 * q].y);
+          const __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2 * q].z, v[2 * q].w);
+          const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[2 * q + 1].x, v[2 * q + 1].y);
+          const __nv_bfloat162 p3 = __floats2bfloat162_rn(v[2 * q + 1].z, v[2 * q + 1].w);
+          tmem_st_x4(trow + st * 16 + q * 4, __uint_as_float(*reinterpret_cast<const uint32_t*>(&p0)),
+                     __uint_as_float(*reinterpret_cast<const uint32_t*>(&p1)),
+                     __uint_as_float(*reinterpret_cast<const uint32_t*>(&p2)),
+                     __uint_as_float(*reinterpret_cast<const uint32_t*>(&p3)));
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_ready[st]);
+          mbar_arrive(&empty[st]);  // this warp is done with the fp32 stage
+        }
+        if (++st == S::kStages) { st = 0; ph ^= 1; }
+      }
   } else {
     const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
     uint8_t* stage_out = smem + S::kOffOut + quad * 2 * S::kStageOutBytes;
     const uint32_t stage_u32 = smem_u32(stage_out);
     uint32_t it = 0, chunk = 0;
+    constexpr int kChunks = BN / 32;  // 32-cout sub-tiles per item
+    uint64_t* rbar = res_full + quad * 2;
+    // RES: request the residual sub-tile of (item, chunk index ci) into staging buffer `b`
+    auto res_request = [&](int item, int ci, uint32_t b) {
+      const int nt = WG_ITEM_NT(item);
+      const int mt = WG_ITEM_MT(item);
+      mbar_arrive_expect_tx(&rbar[b], S::kStageOutBytes);
+      tma_tensor_2d_g2s(stage_out + b * S::kStageOutBytes, &tmap_r, nt * BN + ci * 32, mt * 128 + quad * 32, &rbar[b]);
+    };
+    if constexpr (RES) {
+      pdl_wait();  // the residual may come from the previous kernel in the stream
+      if (lane == 0 && first_item < n_items && (long long)WG_ITEM_MT(first_item) * 128 + quad * 32 < m_rows)
+        res_request(first_item, 0, 0);
+    }
     for (int item = first_item; item < n_items; item += item_stride, ++it) {
       const int nt = WG_ITEM_NT(item);
       const int mt = WG_ITEM_MT(item);
@@ -216,6 +303,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t aph = (it >> 1) & 1;
       const float* sc = scale + nt * BN;
       const float* sh = shift + nt * BN;
+      const bool rows_here = (long long)mt * 128 + quad * 32 < m_rows;  // warp-uniform: this warp's 32 rows exist
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
@@ -224,9 +312,23 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         float v[32];
         tmem_ld_x16(taddr + c0, v);
         tmem_ld_x16(taddr + c0 + 16, v + 16);
-        // the staging buffer written two chunks ago must have been read by its TMA store
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
+        if constexpr (RES) {
+          // next sub-tile's residual goes into the OTHER buffer: the store that last read it (previous chunk) must be
+          // done reading; then wait for this chunk's residual (requested one chunk ago)
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            const int ci = c0 / 32 + 1;
+            const int nitem = ci < kChunks ? item : item + item_stride;
+            if (nitem < n_items && (long long)WG_ITEM_MT(nitem) * 128 + quad * 32 < m_rows)
+              res_request(nitem, ci < kChunks ? ci : 0, (chunk + 1) & 1);
+          }
+          __syncwarp();
+          if (rows_here) mbar_wait(&rbar[chunk & 1], (chunk >> 1) & 1);
+        } else {
+          // the staging buffer written two chunks ago must have been read by its TMA store
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+        }
         tmem_ld_wait();
         const uint32_t dst = stage_u32 + (chunk & 1) * S::kStageOutBytes + lane * 128;
 #pragma unroll
@@ -244,7 +346,20 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             o.z = fmaxf(o.z, 0.f);
             o.w = fmaxf(o.w, 0.f);
           }
-          st_shared_v4(dst + ((j ^ (lane & 7)) << 4), o.x, o.y, o.z, o.w);  // 128-byte swizzle
+          const uint32_t sa = dst + ((j ^ (lane & 7)) << 4);  // 128-byte swizzle
+          if constexpr (RES) {
+            if (rows_here) {
+              const float4 r4 = ld_shared_v4(sa);  // the TMA load used the same swizzle: this thread's own row
+              o.x += r4.x, o.y += r4.y, o.z += r4.z, o.w += r4.w;
+              if (relu_after) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
+              }
+            }
+          }
+          st_shared_v4(sa, o.x, o.y, o.z, o.w);
         }
         if (y_padded != nullptr) {
           // chain mode: write into the zero-bordered [N][16][16][Cout] frame a following 3x3 layer reads
@@ -275,7 +390,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && (long long)mt * 128 + quad * 32 < m_rows) {
+        if (lane == 0 && rows_here) {
           tma_tensor_2d_s2g(&tmap_y, stage_out + (chunk & 1) * S::kStageOutBytes, nt * BN + c0, mt * 128 + quad * 32);
           tma_store_commit();
         }
@@ -328,7 +443,8 @@ template <int CS>
 __global__ void __launch_bounds__(kOneThreads, 1)
 conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ w_img,
                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
-                     long long m_rows, int Cin, int Cout, int BN, int relu, int out_padded) {
+                     long long m_rows, int Cin, int Cout, int BN, int relu, int out_padded,
+                     const float* __restrict__ residual, int relu_after) {
   using S = SmallSmem;
   constexpr uint32_t kTmemCols = kNS;
   constexpr int RO = 128 / CS;  // rows of the tile each CTA finishes
@@ -451,6 +567,7 @@ conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __
       asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(dst_bar) : "memory");
     }
     mbar_wait_cluster(inbox_full, 0);  // all CS partials of this CTA's rows have landed
+    if (residual != nullptr) pdl_wait();  // the residual may have been written by the previous kernel in the stream
     const int t = threadIdx.x - 64;  // 0..127
     constexpr int kChunks = kNS / 4;  // 16-byte chunks per row
     for (int u = t; u < RO * kChunks; u += 128) {
@@ -480,6 +597,16 @@ conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __
         acc.z = fmaxf(acc.z, 0.f);
         acc.w = fmaxf(acc.w, 0.f);
       }
+      if (residual != nullptr) {  // fused residual add (dense output only), optional ReLU on the sum
+        const float4 r4 = *reinterpret_cast<const float4*>(residual + (size_t)m * Cout + col);
+        acc.x += r4.x, acc.y += r4.y, acc.z += r4.z, acc.w += r4.w;
+        if (relu_after) {
+          acc.x = fmaxf(acc.x, 0.f);
+          acc.y = fmaxf(acc.y, 0.f);
+          acc.z = fmaxf(acc.z, 0.f);
+          acc.w = fmaxf(acc.w, 0.f);
+        }
+      }
       if (!out_padded) {
         *reinterpret_cast<float4*>(y + (size_t)m * Cout + col) = acc;
       } else {
@@ -503,13 +630,20 @@ conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __
 // Once per layer: W[Cin][Cout] (reference layout, Kernel128_one.cu:41-48) -> per (n-tile, 32-channel block) the
 // K-major 128-byte-swizzled shared-memory image [BN couts][32 cin], RN-rounded to TF32. The reference's cuDNN half
 // does the same [Cin][Cout] -> [Cout][Cin] transpose on the host (util.c:15-26, Kernel128_one.cu:131).
-__global__ void weight_pack_kernel(const float* __restrict__ w, float* __restrict__ w_img, int Cin, int Cout, int BN) {
+__global__ void weight_pack_kernel(const float* __restrict__ w, float* __restrict__ w_img, int Cin, int Cout, int BN,
+                                   int op16) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cin * Cout) return;
   const int co = idx % Cout;
   const int ci = idx / Cout;
   const int nt = co / BN, r = co % BN;
   const int kb = ci / kBK, kk = ci % kBK;
+  if (op16) {
+    // bf16 image: [Cout/BN][Cin/32][4 k-chunks of 8 channels][BN couts][8 bf16] (K-major, no swizzle; RN)
+    const size_t off = (((size_t)nt * (Cin / kBK) + kb) * 4 + (kk >> 3)) * (size_t)(BN * 8) + (size_t)r * 8 + (kk & 7);
+    reinterpret_cast<__nv_bfloat16*>(w_img)[off] = __float2bfloat16_rn(w[idx]);
+    return;
+  }
   const int chunk = (kk >> 2) ^ (r & 7);
   const size_t off = ((size_t)nt * (Cin / kBK) + kb) * (size_t)(BN * kBK) + (size_t)r * kBK + chunk * 4 + (kk & 3);
   w_img[off] = to_tf32_rn(w[idx]);
@@ -536,18 +670,23 @@ int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int C
   return encode_2d(tmap, y, Cout, m_rows, 32, 32);
 }
 
-template <int BN, int CL, bool WS = false, bool PAIR = false>
+struct OneRes {  // residual operand of a launch (RES instantiations)
+  const CUtensorMap* tmap_r;
+  int relu_after;
+};
+
+template <int BN, int CL, bool WS = false, bool PAIR = false, bool RES = false, bool H16 = false>
 static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
                       const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int relu,
-                      int max_ctas, cudaStream_t stream, int bn_packed = BN) {
-  using S = OneSmem<BN, WS>;
+                      int max_ctas, cudaStream_t stream, int bn_packed = BN, OneRes res = OneRes{nullptr, 0}) {
+  using S = OneSmem<BN, WS, H16>;
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN, CL, WS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(conv1x1_bn_act_kernel<BN, CL, WS, PAIR, RES, H16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kTotal);
     if (e != cudaSuccess) return WG_ERR_CUDA;
     configured |= dev_bit_;
   }
@@ -564,7 +703,7 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_clusters * CL));
-  cfg.blockDim = dim3(kOneThreads);
+  cfg.blockDim = dim3(H16 ? kOneThreads + 128 : kOneThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -576,8 +715,9 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL, WS, PAIR>, tmap, tmap_y, w_img, scale, shift, y_padded,
-                                     m_rows, Cin, Cout, relu, bn_packed);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL, WS, PAIR, RES, H16>, tmap, tmap_y,
+                                     res.tmap_r ? *res.tmap_r : tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout,
+                                     relu, bn_packed, res.relu_after);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
@@ -617,7 +757,8 @@ static int small_max_clusters() {
 
 template <int CS>
 static int launch_small(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
-                        int out_padded, long long m_rows, int Cin, int Cout, int BN, int relu, cudaStream_t stream) {
+                        int out_padded, long long m_rows, int Cin, int Cout, int BN, int relu, const float* residual,
+                        int relu_after, cudaStream_t stream) {
   const long long n_items = ((m_rows + 127) / 128) * (Cout / kNS);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_items * CS));
@@ -641,23 +782,38 @@ static int launch_small(const CUtensorMap& tmap, const float* w_img, const float
   cfg.attrs = attr;
   cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_small_kernel<CS>, tmap, w_img, scale, shift, y, m_rows, Cin, Cout,
-                                     BN, relu, out_padded);
+                                     BN, relu, out_padded, residual, relu_after);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
-int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
-               const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout, int BN, int relu,
-               int max_ctas, cudaStream_t stream) {
+// bf16 operands: one kernel for every batch size (128-wide N-tiles, A converted into TMEM by four extra warps)
+static int one_bf16_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtensorMap& tmap_res,
+                           const float* w_img, const float* scale, const float* shift, float* y_padded, long long m_rows,
+                           int Cin, int Cout, int relu, const float* residual, int relu_after, int max_ctas,
+                           cudaStream_t stream) {
+  if (residual)
+    return launch_one<128, 1, false, false, true, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout,
+                                                        relu, max_ctas, stream, 128, OneRes{&tmap_res, relu_after});
+  return launch_one<128, 1, false, false, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout,
+                                                       relu, max_ctas, stream, 128);
+}
+
+int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtensorMap& tmap_res, const float* w_img,
+               const float* scale, const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout,
+               int BN, int bf16, int relu, const float* residual, int relu_after, int max_ctas, cudaStream_t stream) {
   float* y_padded = out_padded ? y : nullptr;
+  if (bf16)  // bf16 operands: its own kernel (conv1x1_bf16_kernel), every batch size
+    return one_bf16_launch(tmap, tmap_y, tmap_res, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, residual,
+                           relu_after, max_ctas, stream);
   {
     // latency mode: every (M-tile, 64-cout sub-tile) fits on the chip at once -> the small kernel, split-K factor CS
     // chosen by a two-term model in clocks (weight/activation ingest of Cin/CS channels at ~36 B/clk per SM, DSMEM reduction
     // of (CS-1)/CS of a 32 KB partial at ~18 B/clk + fixed cost). WG_ONE_SPLITK=1 disables, WG_ONE_CS=n forces CS.
     static int sk_env = -1, cs_env = 0;
     if (sk_env < 0) {
-      const char* e = getenv("WG_ONE_SPLITK");
+      const char* e = dev_env("WG_ONE_SPLITK");
       sk_env = e ? atoi(e) : 0;
-      const char* c = getenv("WG_ONE_CS");
+      const char* c = dev_env("WG_ONE_CS");
       cs_env = c ? atoi(c) : 0;
     }
     const int n_kb = Cin / kBK;
@@ -678,7 +834,8 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
         }
       }
 #define WG_SMALL(CS_) \
-  return launch_small<CS_>(tmap, w_img, scale, shift, y, out_padded, m_rows, Cin, Cout, BN, relu, stream)
+  return launch_small<CS_>(tmap, w_img, scale, shift, y, out_padded, m_rows, Cin, Cout, BN, relu, residual, relu_after, \
+                           stream)
       if (best == 1) WG_SMALL(1);
       if (best == 2) WG_SMALL(2);
       if (best == 4) WG_SMALL(4);
@@ -692,7 +849,7 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
   // multicast does not reduce, not L2 output bandwidth.
   static int cl = -1;
   if (cl < 0) {
-    const char* e = getenv("WG_ONE_CLUSTER");
+    const char* e = dev_env("WG_ONE_CLUSTER");
     cl = e ? atoi(e) : 1;
     if (cl != 1 && cl != 2 && cl != 4) cl = 1;
   }
@@ -704,24 +861,37 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
     // N-tile through the tensor-map path, ~37 B/clk per SM), so they are not used.
     static int ws_env = -1;  // WG_ONE_WS=0 disables
     if (ws_env < 0) {
-      const char* e = getenv("WG_ONE_WS");
+      const char* e = dev_env("WG_ONE_WS");
       ws_env = e ? atoi(e) : 1;
     }
     static int ws_bn_env = -1;  // WG_ONE_WS_BN=128: also allow 128-row stationary slices (experiments)
     if (ws_bn_env < 0) {
-      const char* e = getenv("WG_ONE_WS_BN");
+      const char* e = dev_env("WG_ONE_WS_BN");
       ws_bn_env = e ? atoi(e) : 0;
     }
     int bn_ws = (long long)Cin * BN * 4 <= 128 * 1024 ? BN : 0;
     if (ws_bn_env == 128 && (long long)Cin * 128 * 4 <= 128 * 1024) bn_ws = 128;
     const long long n_mt = (m_rows + 127) / 128, n_nt = bn_ws ? Cout / bn_ws : 0;
     if (ws_env && use == 1 && bn_ws && max_ctas >= n_nt && n_mt >= 4 * (max_ctas / n_nt)) {
+      if (bn_ws == 128 && residual)
+        return launch_one<128, 1, true, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
+                                                     max_ctas, stream, BN, OneRes{&tmap_res, relu_after});
       if (bn_ws == 128)
         return launch_one<128, 1, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas,
                                         stream, BN);
+      if (residual)
+        return launch_one<256, 1, true, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
+                                                     max_ctas, stream, BN, OneRes{&tmap_res, relu_after});
       return launch_one<256, 1, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas,
                                       stream, BN);
     }
+  }
+  if (residual) {
+    if (BN == 128)
+      return launch_one<128, 1, false, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
+                                                    max_ctas, stream, 128, OneRes{&tmap_res, relu_after});
+    return launch_one<256, 1, false, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
+                                                  max_ctas, stream, 256, OneRes{&tmap_res, relu_after});
   }
 #define WG_ONE(BN_, CL_) \
   return launch_one<BN_, CL_>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas, stream)
@@ -729,34 +899,33 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* 
   // WG_ONE_PAIR=1; experiment, default off (see the kernel).
   static int pair = -1;
   if (pair < 0) {
-    const char* e = getenv("WG_ONE_PAIR");
+    const char* e = dev_env("WG_ONE_PAIR");
     pair = e ? (atoi(e) != 0) : 0;
   }
-  if (pair && m_rows > 128 && max_ctas >= 2) {
-    if (BN == 128)
-      return launch_one<128, 2, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
-                                             max_ctas, stream);
-    if (BN == 256)
-      return launch_one<256, 2, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
-                                             max_ctas, stream);
+  if constexpr (kDev) {  // experiments that lost (see the kernel's header): CTA pairs, weight-tile multicast clusters
+    if (pair && m_rows > 128 && max_ctas >= 2) {
+      if (BN == 128)
+        return launch_one<128, 2, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
+                                               max_ctas, stream);
+      if (BN == 256)
+        return launch_one<256, 2, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
+                                               max_ctas, stream);
+    }
+    if (BN == 128 && use == 2) WG_ONE(128, 2);
+    if (BN == 128 && use == 4) WG_ONE(128, 4);
+    if (BN == 256 && use == 2) WG_ONE(256, 2);
+    if (BN == 256 && use == 4) WG_ONE(256, 4);
   }
-  if (BN == 128) {
-    if (use == 1) WG_ONE(128, 1);
-    if (use == 2) WG_ONE(128, 2);
-    WG_ONE(128, 4);
-  }
-  if (BN == 256) {
-    if (use == 1) WG_ONE(256, 1);
-    if (use == 2) WG_ONE(256, 2);
-    WG_ONE(256, 4);
-  }
+  if (BN == 128) WG_ONE(128, 1);
+  if (BN == 256) WG_ONE(256, 1);
 #undef WG_ONE
   return WG_ERR_ARG;
 }
 
-int weight_pack_launch(const float* w_cin_cout, float* w_img, int Cin, int Cout, int BN, cudaStream_t stream) {
+int weight_pack_launch(const float* w_cin_cout, float* w_img, int Cin, int Cout, int BN, int op16,
+                       cudaStream_t stream) {
   const int n = Cin * Cout;
-  weight_pack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_cin_cout, w_img, Cin, Cout, BN);
+  weight_pack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w_cin_cout, w_img, Cin, Cout, BN, op16);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 

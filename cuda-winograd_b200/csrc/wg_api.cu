@@ -1,12 +1,15 @@
 // C-ABI of libwinograd_b200.so (include/winograd_b200.h): layer handles, one-time filter packing, the single-launch
-// hot path, and the host-buffer end-to-end call. No cuDNN, no cuBLAS, no CPU fallback: without an sm_100 device every
-// create() returns WG_ERR_NODEVICE.
+// hot path, the host-buffer end-to-end call and the packed per-layer blob. No cuDNN, no cuBLAS, no CPU fallback: without
+// an sm_100 device every create() returns WG_ERR_NODEVICE.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
 #include <cmath>
+#include <mutex>
+#include <new>
+#include <vector>
 
 #include "wg_internal.h"
 
@@ -14,18 +17,26 @@ namespace wg {
 
 static thread_local char g_last_cuda_error[256] = "";
 static std::atomic<long long> g_launches{0};
-static int g_max_ctas = 0;  // 0 = number of SMs
-// 96 = V-in-TMEM kernel with the whole inverse transform folded into the MMAs (default); 48 = V-in-TMEM, half fold;
-// 64 / 32 = the shared-memory-operand kernels (half fold / one accumulator per Winograd point)
-static int g_wino_kn = -1;
+static std::atomic<int> g_max_ctas{0};  // 0 = number of SMs; process-wide benchmarking knob (wg_set_max_ctas)
+
+// 3x3 TF32 kernel generation for layers created from now on. The product build has exactly one: 96 = V in tensor
+// memory, whole inverse transform folded into the MMAs. The developer build also keeps 48 (V in TMEM, half fold) and
+// 64 / 32 (both operands in shared memory), selectable with wg_dev_set_wino_kn() / WG_WINO_KN.
+#ifdef WG_DEV_BUILD
+static std::atomic<int> g_wino_kn{-1};
 static int wino_kn() {
-  if (g_wino_kn < 0) {
-    const char* e = getenv("WG_WINO_KN");  // same meaning as wg_set_wino_kn()
-    const int v = e ? atoi(e) : 96;
-    g_wino_kn = (v == 32 || v == 64 || v == 48) ? v : 96;
+  int v = g_wino_kn.load();
+  if (v < 0) {
+    const char* e = dev_env("WG_WINO_KN");
+    v = e ? atoi(e) : 96;
+    v = (v == 32 || v == 64 || v == 48) ? v : 96;
+    g_wino_kn.store(v);
   }
-  return g_wino_kn;
+  return v;
 }
+#else
+static int wino_kn() { return 96; }
+#endif
 static bool kn_tm(int kn) { return kn == 48 || kn == 96; }  // V-in-TMEM kernels
 
 static int cuda_fail(cudaError_t e, const char* what) {
@@ -40,22 +51,21 @@ static int cuda_fail(cudaError_t e, const char* what) {
 
 PFN_encodeTiled get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
       fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
+  });
   return fn;
 }
 
 CUtensorMapL2promotion l2_promotion() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("WG_L2_PROMO");
+    const char* e = dev_env("WG_L2_PROMO");
     v = e ? atoi(e) : 128;
   }
   switch (v) {
@@ -69,54 +79,98 @@ CUtensorMapL2promotion l2_promotion() {
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("WG_PDL");
+    const char* e = dev_env("WG_PDL");
     v = e ? (atoi(e) != 0) : 1;
   }
   return v != 0;
 }
 
-}  // namespace wg
-
-struct wg_layer {
-  int kind;  // 0 = 3x3 Winograd, 1 = 1x1 GEMM
-  int cin, cout, relu, dtype, device;
-  int tile_n;  // 3x3: cout slice KN; 1x1: BN
-  int tm_db;   // 3x3 TM kernel: 1 = double-buffered V, 32-wide slices
-  int tm16_ff; // 3x3 bf16/fp16: d_filter_tm16 is the full-fold kernel's image (96-wide slices)
-  int ff_cg2;  // 3x3 full-fold kernel: CTA-pair variant (filter image split in cout halves)
-  float* d_filter_n64;       // 3x3 full-fold kernel: second image with all slices 64 wide (one-wave launches), or null
-  float* d_filter_tm16_n64;  // the same for the 16-bit operand image
-  int num_sms;
-  float* d_filter;  // packed filter image (U or swizzled W^T)
-  float* d_filter_tm16;   // 3x3 bf16/fp16 only: U in the 16-bit image of the V-in-TMEM throughput kernel (48/32 slices)
-  float* d_filter_small;  // 3x3 TF32 only: U in the plain KN=32 image the small-batch kernel reads (may alias d_filter)
-  float* d_scale;
-  float* d_shift;
-  // tensor-map cache for the last (x, N) seen
-  const float* tmap_x;
-  int tmap_n;
-  CUtensorMap tmap;
-  const float* tmap_tm_x;     // 3x3 bf16/fp16: tensor map of the V-in-TMEM kernel (32-byte swizzle)
-  int tmap_tm_n;
-  CUtensorMap tmap_tm;
-  const float* tmap_small_x;  // 3x3 small-batch kernel: same view, 26-row box
-  int tmap_small_n;
-  CUtensorMap tmap_small;
-  const float* tmap_y_ptr;  // 1x1 only: output tensor map for the TMA-store epilogue
-  int tmap_y_n;
-  CUtensorMap tmap_out;
-  // staging for wg_run_host
-  float* d_x;
-  float* d_y;
-  size_t d_x_bytes, d_y_bytes;
-  cudaStream_t stream;
-  // wg_run_host pipeline: copy-in / compute / copy-out streams and per-chunk events (created on first use)
-  cudaStream_t s_h2d, s_d2h;
-  cudaEvent_t ev_in[64], ev_done[64];
-  int n_events;
+// Restores the caller's current device on every exit path (a wg_* call on a layer that lives on another GPU must not
+// change the calling thread's device for its later CUDA calls).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int enter(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return WG_ERR_CUDA;
+    if (prev != device) {
+      if (cudaSetDevice(device) != cudaSuccess) return WG_ERR_CUDA;
+      switched = true;
+    }
+    return WG_OK;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
 };
 
+// Tensor maps are keyed on (base pointer, rows): a few entries per kind so that callers rotating buffers (bench.py,
+// ping-pong chains) do not re-encode on every call. Looked up and filled under the layer's mutex; the launch uses a
+// by-value copy (the kernels take the map as a __grid_constant__ parameter), so concurrent wg_run calls on one layer
+// from several host threads are safe.
+struct TmapCache {
+  static constexpr int kWays = 4;
+  struct Entry {
+    const void* ptr = nullptr;
+    long long n = -1;
+    CUtensorMap map;
+  } e[kWays];
+  int next = 0;
+  void clear() {
+    for (auto& x : e) x.ptr = nullptr, x.n = -1;
+  }
+  template <class Make>
+  int get(const void* ptr, long long n, CUtensorMap* out, Make make) {
+    for (auto& x : e)
+      if (x.ptr == ptr && x.n == n) {
+        *out = x.map;
+        return WG_OK;
+      }
+    Entry& slot = e[next];
+    next = (next + 1) % kWays;
+    slot.ptr = nullptr;
+    int rc = make(&slot.map);
+    if (rc != WG_OK) return rc;
+    slot.ptr = ptr;
+    slot.n = n;
+    *out = slot.map;
+    return WG_OK;
+  }
+};
+
+}  // namespace wg
+
 using namespace wg;
+
+struct wg_layer {
+  int kind = 0;  // 0 = 3x3 Winograd, 1 = 1x1 GEMM
+  int cin = 0, cout = 0, relu = 0, dtype = 0, device = 0;
+  int tile_n = 0;   // 3x3: cout slice KN; 1x1: BN
+  int tm_db = 0;    // 3x3 TM kernel (developer build): 1 = double-buffered V, 32-wide slices
+  int tm16_ff = 0;  // 3x3 bf16/fp16: d_filter_tm16 is the full-fold kernel's image (96-wide slices)
+  int ff_cg2 = 0;   // 3x3 full-fold kernel: CTA-pair variant (developer build)
+  int num_sms = 0;
+  // packed images (device). Sizes in bytes in img_bytes[], same order as the blob sections.
+  float* d_filter = nullptr;           // packed filter image (U or swizzled W^T)
+  float* d_filter_n64 = nullptr;       // 3x3 full-fold kernel: second image with all slices 64 wide, or null
+  float* d_filter_tm16 = nullptr;      // 3x3 bf16/fp16: U in the 16-bit image of the V-in-TMEM throughput kernel
+  float* d_filter_tm16_n64 = nullptr;  // the same with all slices 64 wide
+  float* d_filter_small = nullptr;     // 3x3 TF32: U in the plain KN=32 image of the small-batch kernel (may alias d_filter)
+  float* d_scale = nullptr;
+  float* d_shift = nullptr;
+  size_t img_bytes[5] = {0, 0, 0, 0, 0};
+  std::vector<float> w_host;  // the raw weights as given to create() (kept for wg_layer_serialize)
+  // tensor-map caches
+  std::mutex mu;
+  TmapCache tm_x, tm_x16, tm_small, tm_y, tm_res;
+  // staging for wg_run_host
+  float* d_x = nullptr;
+  float* d_y = nullptr;
+  size_t d_x_bytes = 0, d_y_bytes = 0;
+  cudaStream_t stream = nullptr;
+  // wg_run_host pipeline: copy-in / compute / copy-out streams and per-chunk events (created on first use)
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
+};
 
 static int check_device(int device, int* num_sms) {
   int count = 0;
@@ -126,23 +180,120 @@ static int check_device(int device, int* num_sms) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return WG_ERR_NODEVICE;
-  if (prop.major != 10) return WG_ERR_NODEVICE;  // tcgen05 / TMEM: sm_100 family only
+  // the library embeds sm_100a SASS only (tcgen05 / TMEM, arch-specific target): exactly compute capability 10.0
+  if (prop.major != 10 || prop.minor != 0) return WG_ERR_NODEVICE;
   *num_sms = prop.multiProcessorCount;
   return WG_OK;
+}
+
+// ---- layer construction: (1) shape-dependent kernel choices, (2) device buffers, (3) images packed on the GPU from
+// the raw weights (create) or uploaded as they are (deserialize)
+static void layer_plan(wg_layer* L) {
+  if (L->kind == 0) {
+    if (L->dtype != WG_TF32) L->tile_n = 64;
+    else if (kn_tm(wino_kn())) L->tile_n = wino_kn();
+    else L->tile_n = (wino_kn() == 32 || L->cout % 64 != 0) ? 32 : 64;
+    L->ff_cg2 = wino_ff_cg2();
+#ifdef WG_DEV_BUILD
+    if (L->tile_n == 48) L->tm_db = wino_tm_choose_db(L->cin, L->cout);
+#endif
+    L->tm16_ff = (L->dtype != WG_TF32 && wino_kn() == 96) ? 1 : 0;
+    const size_t fe = (size_t)16 * L->cin * L->cout;
+    L->img_bytes[0] = fe * 4;
+    L->img_bytes[1] = (L->tile_n == 96 && !L->ff_cg2 && wino_ff_has_narrow(L->cout)) ? fe * 4 : 0;
+    const bool t16 = L->dtype != WG_TF32 && kn_tm(wino_kn());
+    L->img_bytes[2] = t16 ? fe * 2 : 0;
+    L->img_bytes[3] = (t16 && L->tm16_ff && !L->ff_cg2 && wino_ff_has_narrow(L->cout)) ? fe * 2 : 0;
+    L->img_bytes[4] = (L->dtype == WG_TF32 && L->tile_n != 32) ? fe * 4 : 0;  // tile_n == 32: aliases d_filter
+  } else {
+    L->tile_n = (L->cout % 256 == 0 && L->dtype == WG_TF32) ? 256 : 128;  // bf16 operands: 128-wide N-tiles
+    L->img_bytes[0] = (size_t)L->cin * L->cout * (L->dtype == WG_TF32 ? 4 : 2);
+  }
+}
+
+static float** layer_img_slot(wg_layer* L, int i) {
+  switch (i) {
+    case 0: return &L->d_filter;
+    case 1: return &L->d_filter_n64;
+    case 2: return &L->d_filter_tm16;
+    case 3: return &L->d_filter_tm16_n64;
+    default: return &L->d_filter_small;
+  }
+}
+
+static int layer_alloc(wg_layer* L) {
+  WG_CUDA(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; ++i)
+    if (L->img_bytes[i]) WG_CUDA(cudaMalloc(layer_img_slot(L, i), L->img_bytes[i]));
+  if (L->kind == 0 && L->dtype == WG_TF32 && L->tile_n == 32) L->d_filter_small = L->d_filter;
+  WG_CUDA(cudaMalloc(&L->d_scale, L->cout * sizeof(float)));
+  WG_CUDA(cudaMalloc(&L->d_shift, L->cout * sizeof(float)));
+  return WG_OK;
+}
+
+static int layer_pack(wg_layer* L, const float* d_w) {
+  const int cin = L->cin, cout = L->cout;
+  const int op16 = L->dtype == WG_FP16 ? 2 : (L->dtype == WG_BF16 ? 1 : 0);
+  int rc = WG_OK;
+  auto count = [&] { g_launches++; };
+  if (L->kind == 1) {
+    rc = weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, op16, L->stream);
+    count();
+    return rc;
+  }
+  if (L->tile_n == 96) {
+    rc = filter_transform_ff_launch(d_w, L->d_filter, cin, cout, 0, L->ff_cg2, 0, L->stream);
+    count();
+    if (rc == WG_OK && L->d_filter_n64) {
+      rc = filter_transform_ff_launch(d_w, L->d_filter_n64, cin, cout, 0, 0, 1, L->stream);
+      count();
+    }
+  }
+#ifdef WG_DEV_BUILD
+  else if (L->tile_n == 48) {
+    rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->tm_db, 0, L->stream);
+    count();
+  }
+#endif
+  else {
+    rc = filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)L->dtype, L->stream);
+    count();
+  }
+  if (rc == WG_OK && L->d_filter_tm16) {
+    // 16-bit operands: the throughput kernel keeps V packed in TMEM (its own filter image); small batches stay on the
+    // split-C variant of the shared-memory-operand kernel (d_filter)
+    if (L->tm16_ff) rc = filter_transform_ff_launch(d_w, L->d_filter_tm16, cin, cout, op16, L->ff_cg2, 0, L->stream);
+#ifdef WG_DEV_BUILD
+    else rc = filter_transform_tm_launch(d_w, L->d_filter_tm16, cin, cout, 0, op16, L->stream);
+#endif
+    count();
+    if (rc == WG_OK && L->d_filter_tm16_n64) {
+      rc = filter_transform_ff_launch(d_w, L->d_filter_tm16_n64, cin, cout, op16, 0, 1, L->stream);
+      count();
+    }
+  }
+  if (rc == WG_OK && L->img_bytes[4]) {
+    rc = filter_transform_launch(d_w, L->d_filter_small, cin, cout, 32, 0, L->stream);
+    count();
+  }
+  return rc;
 }
 
 static int create_common(wg_layer_t** out, int kind, int cin, int cout, const float* w, size_t w_elems,
                          const float* scale, const float* shift, int relu, wg_dtype_t dtype, int device) {
   if (!out || !w || !scale || !shift) return WG_ERR_ARG;
   if (dtype != WG_TF32 && dtype != WG_BF16 && dtype != WG_FP16) return WG_ERR_ARG;
-  // bf16 operands: 3x3 only (the 1x1 activation operand goes HBM -> TMA -> MMA untouched, there is nothing to convert it)
-  if (dtype != WG_TF32 && (kind != 0 || cin % 16 != 0 || cout % 64 != 0)) return WG_ERR_ARG;
+  // 16-bit operands: 3x3 needs C % 16 == 0 and K % 64 == 0; 1x1 has a bf16 variant (no fp16 one: the reference's 1x1
+  // activations are U(-20,20) pre-BN sums, outside what fp16 operands are stated for)
+  if (dtype != WG_TF32 && kind == 0 && (cin % 16 != 0 || cout % 64 != 0)) return WG_ERR_ARG;
+  if (dtype == WG_FP16 && kind == 1) return WG_ERR_ARG;
   int num_sms = 0;
   int rc = check_device(device, &num_sms);
   if (rc != WG_OK) return rc;
-  WG_CUDA(cudaSetDevice(device));
+  DeviceGuard guard;
+  if (guard.enter(device) != WG_OK) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
 
-  wg_layer* L = static_cast<wg_layer*>(calloc(1, sizeof(wg_layer)));
+  wg_layer* L = new (std::nothrow) wg_layer();
   if (!L) return WG_ERR_NOMEM;
   L->kind = kind;
   L->cin = cin;
@@ -151,85 +302,192 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   L->dtype = dtype;
   L->device = device;
   L->num_sms = num_sms;
-
+  layer_plan(L);
   float* d_w = nullptr;
-  size_t filter_elems = 0;
-  if (kind == 0) {
-    if (dtype != WG_TF32) L->tile_n = 64;
-    else if (kn_tm(wino_kn())) L->tile_n = wino_kn();
-    else L->tile_n = (wino_kn() == 32 || cout % 64 != 0) ? 32 : 64;
-    filter_elems = (size_t)16 * cin * cout;
-  } else {
-    L->tile_n = (cout % 256 == 0) ? 256 : 128;
-    filter_elems = (size_t)cin * cout;
+  auto fail = [&](int code) {
+    wg_destroy(L);
+    if (d_w) cudaFree(d_w);
+    return code;
+  };
+  try {
+    L->w_host.assign(w, w + w_elems);
+  } catch (...) {
+    return fail(WG_ERR_NOMEM);
   }
+  if ((rc = layer_alloc(L)) != WG_OK) return fail(rc);
   cudaError_t e;
-#define WG_TRY(call)                \
+#define WG_TRY(call)                 \
   if ((e = (call)) != cudaSuccess) { \
-    cuda_fail(e, #call);            \
-    wg_destroy(L);                  \
-    if (d_w) cudaFree(d_w);         \
-    return WG_ERR_CUDA;             \
+    cuda_fail(e, #call);             \
+    return fail(WG_ERR_CUDA);        \
   }
-  WG_TRY(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
   WG_TRY(cudaMalloc(&d_w, w_elems * sizeof(float)));
-  WG_TRY(cudaMalloc(&L->d_filter, filter_elems * sizeof(float)));
-  WG_TRY(cudaMalloc(&L->d_scale, cout * sizeof(float)));
-  WG_TRY(cudaMalloc(&L->d_shift, cout * sizeof(float)));
   WG_TRY(cudaMemcpyAsync(d_w, w, w_elems * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_scale, scale, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, cout * sizeof(float), cudaMemcpyHostToDevice, L->stream));
-  if (kind == 0) L->ff_cg2 = wino_ff_cg2();
-  if (kind == 0 && L->tile_n == 96) {
-    rc = filter_transform_ff_launch(d_w, L->d_filter, cin, cout, 0, L->ff_cg2, 0, L->stream);
-    if (rc == WG_OK && !L->ff_cg2 && wino_ff_has_narrow(cout)) {
-      WG_TRY(cudaMalloc(&L->d_filter_n64, filter_elems * sizeof(float)));
-      rc = filter_transform_ff_launch(d_w, L->d_filter_n64, cin, cout, 0, 0, 1, L->stream);
-      g_launches++;
-    }
-  } else if (kind == 0 && L->tile_n == 48) {
-    L->tm_db = wino_tm_choose_db(cin, cout);
-    rc = filter_transform_tm_launch(d_w, L->d_filter, cin, cout, L->tm_db, 0, L->stream);
-  }
-  else if (kind == 0) rc = filter_transform_launch(d_w, L->d_filter, cin, cout, L->tile_n, (int)dtype, L->stream);
-  else rc = weight_pack_launch(d_w, L->d_filter, cin, cout, L->tile_n, L->stream);
-  g_launches++;
-  if (rc == WG_OK && kind == 0 && dtype != WG_TF32 && kn_tm(wino_kn())) {
-    // 16-bit operands: the throughput kernel keeps V packed in TMEM (its own filter image); small batches stay on the
-    // split-C variant of the shared-memory-operand kernel (d_filter)
-    WG_TRY(cudaMalloc(&L->d_filter_tm16, filter_elems * sizeof(uint16_t)));
-    L->tm16_ff = wino_kn() == 96;
-    rc = L->tm16_ff ? filter_transform_ff_launch(d_w, L->d_filter_tm16, cin, cout, dtype == WG_FP16 ? 2 : 1, L->ff_cg2,
-                                                 0, L->stream)
-                    : filter_transform_tm_launch(d_w, L->d_filter_tm16, cin, cout, 0, dtype == WG_FP16 ? 2 : 1,
-                                                 L->stream);
-    g_launches++;
-    if (rc == WG_OK && L->tm16_ff && !L->ff_cg2 && wino_ff_has_narrow(cout)) {
-      WG_TRY(cudaMalloc(&L->d_filter_tm16_n64, filter_elems * sizeof(uint16_t)));
-      rc = filter_transform_ff_launch(d_w, L->d_filter_tm16_n64, cin, cout, dtype == WG_FP16 ? 2 : 1, 0, 1, L->stream);
-      g_launches++;
-    }
-  }
-  if (rc == WG_OK && kind == 0 && dtype == WG_TF32) {
-    if (L->tile_n == 32) {
-      L->d_filter_small = L->d_filter;
-    } else {
-      WG_TRY(cudaMalloc(&L->d_filter_small, filter_elems * sizeof(float)));
-      rc = filter_transform_launch(d_w, L->d_filter_small, cin, cout, 32, 0, L->stream);
-      g_launches++;
-    }
-  }
+  rc = layer_pack(L, d_w);
   if (rc != WG_OK) {
     cuda_fail(cudaGetLastError(), "filter pack launch");
-    wg_destroy(L);
-    cudaFree(d_w);
-    return rc;
+    return fail(rc);
   }
   WG_TRY(cudaStreamSynchronize(L->stream));
 #undef WG_TRY
   cudaFree(d_w);
   *out = L;
   return WG_OK;
+}
+
+// ---- wg_run_host chunk schedule (host-only logic, exported for the unit tests)
+// Full chunks of `chunk` images, then a tapering tail (halving down to 16 images): the copy-in stream is the critical
+// path from t = 0 whatever the chunking; what is exposed at the end is the LAST chunk's kernel + copy-out, so the last
+// chunks are small (256 images: 64, 64, 64, 32, 16, 16). At most kMaxChunks chunks: the chunk size grows with N so that
+// the schedule (and the per-chunk events) stay bounded for any N.
+static constexpr int kMaxChunks = 64;
+static int chunk_schedule(int N, int chunk, int taper, int* sizes, int cap) {
+  if (N <= 0 || chunk <= 0) return 0;
+  // equal chunks are capped well below kMaxChunks: the taper adds about log2(chunk / 8) more
+  const int max_equal = kMaxChunks - 24;
+  if ((N + chunk - 1) / chunk > max_equal) chunk = (N + max_equal - 1) / max_equal;
+  int n = 0;
+  for (int rem = N; rem > 0;) {
+    int c = rem < chunk ? rem : chunk;
+    if (taper && rem <= 2 * chunk && rem > 16) {
+      c = rem / 2;
+      if (c < 16) c = 16;
+      if (c > chunk) c = chunk;
+    }
+    if (n == kMaxChunks - 1) c = rem;  // hard bound: whatever is left goes out as one last chunk
+    if (sizes && n < cap) sizes[n] = c;
+    ++n;
+    rem -= c;
+  }
+  return n;
+}
+
+// ---- packed per-layer blob (wg_layer_serialize / wg_layer_deserialize). Little-endian; every field is 4 or 8 bytes
+// and the header is a multiple of 8 bytes.
+struct BlobHeader {
+  char magic[8];          // "WGB200L\0"
+  uint32_t version;       // kBlobVersion
+  uint32_t header_bytes;  // sizeof(BlobHeader)
+  int32_t kind, cin, cout, relu, dtype, tile_n, tm_db, tm16_ff, ff_cg2, dev_build;
+  int32_t height, width;   // output map (14 x 14 for every reference shape)
+  uint64_t w_elems;        // raw weights (fp32): first payload section, then scale[cout], shift[cout]
+  uint64_t img_bytes[5];   // packed images, in layer_img_slot() order
+  uint64_t payload_bytes;  // everything after the header
+  uint64_t checksum;       // FNV-1a 64 over the payload
+};
+static constexpr uint32_t kBlobVersion = 2;
+static_assert(sizeof(BlobHeader) % 8 == 0, "header layout");
+
+static uint64_t fnv1a(const uint8_t* p, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+static int run_impl(wg_layer_t* L, const float* x, const float* residual, float* y, int N, int flags,
+                    cudaStream_t stream) {
+  if (!L || !x || !y || N <= 0) return WG_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+      (reinterpret_cast<uintptr_t>(residual) & 15))
+    return WG_ERR_ARG;
+  // flags: WG_OUT_PADDED (1) = zero-bordered frame, WG_OUT_MULTICAST (2) = y is an NVLS multicast address (stores go
+  // out as multimem.st and land in every GPU's buffer: fused conv + all-gather of the output), WG_OUT_RELU_AFTER_ADD
+  // (4, with a residual) = ReLU applied to the sum.
+  if (flags & ~7) return WG_ERR_ARG;
+  if ((flags & WG_OUT_MULTICAST) && !(L->kind == 0 && L->dtype == WG_TF32 && kn_tm(L->tile_n))) return WG_ERR_ARG;
+  if ((flags & WG_OUT_RELU_AFTER_ADD) && !residual) return WG_ERR_ARG;
+  // the residual add exists where the reference's block structure puts it: after the 1x1 `_out` layers, dense output
+  if (residual && (L->kind != 1 || (flags & (WG_OUT_PADDED | WG_OUT_MULTICAST)))) return WG_ERR_ARG;
+  const int out_flags = flags & 3;
+  const int out_padded = flags & 1;
+  DeviceGuard guard;
+  if (guard.enter(L->device) != WG_OK) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  const int mc = g_max_ctas.load();
+  const int max_ctas = mc > 0 ? mc : L->num_sms;
+  CUtensorMap tmap, tmap_y, tmap_res;
+  int rc = WG_OK;
+  auto launched = [&](int r) {
+    g_launches++;
+    if (r == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
+    return r;
+  };
+
+  if (L->kind == 0 && L->d_filter_small != nullptr) {
+    // small batches: the latency variant (one 64-tile x 32-cout item per cluster, split-C), see wino_small_kernel.cu
+    const int cs = wino_small_cs(N, L->cin, L->cout, max_ctas);
+    if (cs > 0) {
+      {
+        std::lock_guard<std::mutex> lk(L->mu);
+        rc = L->tm_small.get(x, N, &tmap, [&](CUtensorMap* m) { return wino_small_make_tmap(m, x, N, L->cin); });
+      }
+      if (rc != WG_OK) return rc;
+      return launched(wino_small_launch(tmap, L->d_filter_small, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->relu,
+                                        out_flags, cs, stream));
+    }
+  }
+  if (L->kind == 0 && L->d_filter_tm16 != nullptr && !(out_flags & 2)) {
+    // bf16 / fp16 operands, throughput-sized batch (the split-C latency mode of the other kernel takes the small ones)
+    const long long items64 = (long long)((N * 49 + 63) / 64) * (L->cout / 64);
+    if (items64 * 4 > max_ctas) {
+      {
+        std::lock_guard<std::mutex> lk(L->mu);
+        rc = L->tm_x16.get(x, N, &tmap, [&](CUtensorMap* m) {
+#ifdef WG_DEV_BUILD
+          if (!L->tm16_ff) return wino_tm_make_tmap(m, x, N, L->cin, 1);
+#endif
+          return wino_ff_make_tmap(m, x, N, L->cin);
+        });
+      }
+      if (rc != WG_OK) return rc;
+      const int op16 = L->dtype == WG_FP16 ? 2 : 1;
+#ifdef WG_DEV_BUILD
+      if (!L->tm16_ff)
+        return launched(wino_tm_launch(tmap, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, op16,
+                                       L->relu, out_flags, max_ctas, stream));
+#endif
+      return launched(wino_ff_launch(tmap, x, L->d_filter_tm16, L->d_filter_tm16_n64, L->d_scale, L->d_shift, y, N,
+                                     L->cin, L->cout, op16, L->ff_cg2, L->relu, out_flags, max_ctas, stream));
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(L->mu);
+    rc = L->tm_x.get(x, N, &tmap, [&](CUtensorMap* m) {
+      if (L->kind == 1) return one_make_tmap(m, x, (long long)N * 196, L->cin);
+      if (L->tile_n == 96) return wino_ff_make_tmap(m, x, N, L->cin);
+#ifdef WG_DEV_BUILD
+      if (L->tile_n == 48) return wino_tm_make_tmap(m, x, N, L->cin, wino_tm_cls(L->cout, L->tm_db));
+#endif
+      return wino_make_tmap(m, x, N, L->cin);
+    });
+    if (rc == WG_OK && L->kind == 1)
+      rc = L->tm_y.get(y, N, &tmap_y,
+                       [&](CUtensorMap* m) { return one_make_tmap_out(m, y, (long long)N * 196, L->cout); });
+    if (rc == WG_OK && L->kind == 1 && residual)
+      rc = L->tm_res.get(residual, N, &tmap_res,
+                         [&](CUtensorMap* m) { return one_make_tmap_out(m, residual, (long long)N * 196, L->cout); });
+  }
+  if (rc != WG_OK) return rc;
+  if (L->kind == 1) {
+    if (!residual) tmap_res = tmap_y;
+    return launched(one_launch(tmap, tmap_y, tmap_res, L->d_filter, L->d_scale, L->d_shift, y, out_padded,
+                               (long long)N * 196, L->cin, L->cout, L->tile_n, L->dtype != WG_TF32, L->relu, residual,
+                               (flags & WG_OUT_RELU_AFTER_ADD) ? 1 : 0, max_ctas, stream));
+  }
+  if (L->tile_n == 96)
+    return launched(wino_ff_launch(tmap, x, L->d_filter, L->d_filter_n64, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
+                                   0, L->ff_cg2, L->relu, out_flags, max_ctas, stream));
+#ifdef WG_DEV_BUILD
+  if (L->tile_n == 48)
+    return launched(wino_tm_launch(tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, 0,
+                                   L->relu, out_flags, max_ctas, stream));
+#endif
+  return launched(wino_launch(tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n, L->dtype,
+                              L->relu, out_padded, max_ctas, stream));
 }
 
 extern "C" {
@@ -246,95 +504,23 @@ int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_co
   return create_common(out, 1, Cin, Cout, w_cin_cout, (size_t)Cin * Cout, scale, shift, relu, dtype, device);
 }
 
-int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_padded, void* cuda_stream) {
-  if (!L || !x || !y || N <= 0) return WG_ERR_ARG;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return WG_ERR_ARG;
-  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-  // out_padded is a flag word: WG_OUT_PADDED (1) = zero-bordered frame, WG_OUT_MULTICAST (2) = y is an NVLS multicast
-  // address (stores go out as multimem.st and land in every GPU's buffer: fused conv + all-gather of the output).
-  if (out_padded & ~3) return WG_ERR_ARG;
-  const int out_flags = out_padded & 3;
-  if ((out_flags & 2) && !(L->kind == 0 && L->dtype == WG_TF32 && kn_tm(L->tile_n))) return WG_ERR_ARG;
-  out_padded &= 1;
-  int cur = -1;
-  WG_CUDA(cudaGetDevice(&cur));
-  if (cur != L->device) WG_CUDA(cudaSetDevice(L->device));
-  const int max_ctas = g_max_ctas > 0 ? g_max_ctas : L->num_sms;
-  if (L->kind == 0 && L->d_filter_small != nullptr) {
-    // small batches: the latency variant (one 64-tile x 32-cout item per cluster, split-C), see wino_small_kernel.cu
-    const int cs = wino_small_cs(N, L->cin, L->cout, max_ctas);
-    if (cs > 0) {
-      if (L->tmap_small_x != x || L->tmap_small_n != N) {
-        int rc = wino_small_make_tmap(&L->tmap_small, x, N, L->cin);
-        if (rc != WG_OK) return rc;
-        L->tmap_small_x = x;
-        L->tmap_small_n = N;
-      }
-      int rc = wino_small_launch(L->tmap_small, L->d_filter_small, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
-                                 L->relu, out_flags, cs, stream);
-      g_launches++;
-      if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
-      return rc;
-    }
-  }
-  if (L->kind == 0 && L->d_filter_tm16 != nullptr && !(out_flags & 2)) {
-    // bf16 / fp16 operands, throughput-sized batch (the split-C latency mode of the other kernel takes the small ones)
-    const long long items64 = (long long)((N * 49 + 63) / 64) * (L->cout / 64);
-    if (items64 * 4 > max_ctas) {
-      if (L->tmap_tm_x != x || L->tmap_tm_n != N) {
-        int rc = L->tm16_ff ? wino_ff_make_tmap(&L->tmap_tm, x, N, L->cin) : wino_tm_make_tmap(&L->tmap_tm, x, N, L->cin, 1);
-        if (rc != WG_OK) return rc;
-        L->tmap_tm_x = x;
-        L->tmap_tm_n = N;
-      }
-      const int op16 = L->dtype == WG_FP16 ? 2 : 1;
-      int rc = L->tm16_ff ? wino_ff_launch(L->tmap_tm, x, L->d_filter_tm16, L->d_filter_tm16_n64, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
-                                           op16, L->ff_cg2, L->relu, out_flags, max_ctas, stream)
-                          : wino_tm_launch(L->tmap_tm, L->d_filter_tm16, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
-                                           0, op16, L->relu, out_flags, max_ctas, stream);
-      g_launches++;
-      if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
-      return rc;
-    }
-  }
-  if (L->tmap_x != x || L->tmap_n != N) {
-    int rc = L->kind == 1 ? one_make_tmap(&L->tmap, x, (long long)N * 196, L->cin)
-             : L->tile_n == 96 ? wino_ff_make_tmap(&L->tmap, x, N, L->cin)
-             : L->tile_n == 48 ? wino_tm_make_tmap(&L->tmap, x, N, L->cin, wino_tm_cls(L->cout, L->tm_db))
-                               : wino_make_tmap(&L->tmap, x, N, L->cin);
-    if (rc != WG_OK) return rc;
-    L->tmap_x = x;
-    L->tmap_n = N;
-  }
-  if (L->kind == 1 && (L->tmap_y_ptr != y || L->tmap_y_n != N)) {
-    int rc = one_make_tmap_out(&L->tmap_out, y, (long long)N * 196, L->cout);
-    if (rc != WG_OK) return rc;
-    L->tmap_y_ptr = y;
-    L->tmap_y_n = N;
-  }
-  int rc;
-  if (L->kind == 0 && L->tile_n == 96)
-    rc = wino_ff_launch(L->tmap, x, L->d_filter, L->d_filter_n64, L->d_scale, L->d_shift, y, N, L->cin, L->cout, 0, L->ff_cg2, L->relu,
-                        out_flags, max_ctas, stream);
-  else if (L->kind == 0 && L->tile_n == 48)
-    rc = wino_tm_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, 0, L->relu,
-                        out_flags, max_ctas, stream);
-  else if (L->kind == 0)
-    rc = wino_launch(L->tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tile_n,
-                     L->dtype, L->relu, out_padded ? 1 : 0, max_ctas, stream);
-  else
-    rc = one_launch(L->tmap, L->tmap_out, L->d_filter, L->d_scale, L->d_shift, y, out_padded ? 1 : 0,
-                    (long long)N * 196, L->cin, L->cout, L->tile_n, L->relu, max_ctas, stream);
-  g_launches++;
-  if (rc == WG_ERR_CUDA) cuda_fail(cudaGetLastError(), "kernel launch");
-  return rc;
+int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_flags, void* cuda_stream) {
+  if (out_flags & WG_OUT_RELU_AFTER_ADD) return WG_ERR_ARG;
+  return run_impl(L, x, nullptr, y, N, out_flags, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int wg_run_residual(wg_layer_t* L, const float* x, const float* residual, float* y, int N, int out_flags,
+                    void* cuda_stream) {
+  if (!residual) return WG_ERR_ARG;
+  return run_impl(L, x, residual, y, N, out_flags, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int wg_host_chunk_schedule(int N, int* sizes, int cap) { return chunk_schedule(N, 64, 1, sizes, cap); }
+
 int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int out_padded) {
-  if (!L || !x_host || !y_host || N <= 0) return WG_ERR_ARG;
-  int cur = -1;
-  WG_CUDA(cudaGetDevice(&cur));
-  if (cur != L->device) WG_CUDA(cudaSetDevice(L->device));
+  if (!L || !x_host || !y_host || N <= 0 || (out_padded & ~1)) return WG_ERR_ARG;
+  DeviceGuard guard;
+  if (guard.enter(L->device) != WG_OK) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
   const size_t in_px = L->kind == 0 ? 256 : 196;
   const size_t out_px = out_padded ? 256 : 196;
   const size_t xb = (size_t)N * in_px * L->cin * sizeof(float);
@@ -343,7 +529,10 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
     if (L->d_x) cudaFree(L->d_x);
     L->d_x = nullptr;
     L->d_x_bytes = 0;
-    L->tmap_x = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(L->mu);  // the freed address may come back with other contents / sizes
+      L->tm_x.clear(), L->tm_x16.clear(), L->tm_small.clear();
+    }
     WG_CUDA(cudaMalloc(&L->d_x, xb));
     L->d_x_bytes = xb;
   }
@@ -351,74 +540,80 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
     if (L->d_y) cudaFree(L->d_y);
     L->d_y = nullptr;
     L->d_y_bytes = 0;
-    L->tmap_y_ptr = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(L->mu);
+      L->tm_y.clear();
+    }
     WG_CUDA(cudaMalloc(&L->d_y, yb));
     L->d_y_bytes = yb;
   }
   // Chunked three-stream pipeline: H2D of chunk c+1, the kernel on chunk c and D2H of chunk c-1 overlap (PCIe is
   // full duplex), so a large batch costs ~max(copy-in, copy-out) instead of their sum plus the kernel. Host buffers
   // should be pinned for the copies to be asynchronous; pageable memory still works, just without the overlap.
-  if (!L->s_h2d) {
-    WG_CUDA(cudaStreamCreateWithFlags(&L->s_h2d, cudaStreamNonBlocking));
-    WG_CUDA(cudaStreamCreateWithFlags(&L->s_d2h, cudaStreamNonBlocking));
-  }
-  static int chunk_env = -1;  // WG_HOST_CHUNK=<images per chunk> (experiments); default 64 (measured: 64 > 32 > 16 on PCIe Gen5; per-chunk event and launch costs outweigh the shorter pipeline tail)
+  if (!L->s_h2d) WG_CUDA(cudaStreamCreateWithFlags(&L->s_h2d, cudaStreamNonBlocking));
+  if (!L->s_d2h) WG_CUDA(cudaStreamCreateWithFlags(&L->s_d2h, cudaStreamNonBlocking));
+  // images per chunk: 64 (measured: 64 > 32 > 16 on PCIe Gen5; per-chunk event and launch costs outweigh the shorter
+  // pipeline tail); developer build: WG_HOST_CHUNK / WG_HOST_TAPER=0 for the A/B measurements
+  static int chunk_env = -1, taper_env = -1;
   if (chunk_env < 0) {
-    const char* e = getenv("WG_HOST_CHUNK");
+    const char* t = dev_env("WG_HOST_TAPER");
+    taper_env = t ? atoi(t) : 1;
+    const char* e = dev_env("WG_HOST_CHUNK");
     chunk_env = e ? atoi(e) : 0;
   }
-  int chunk = chunk_env > 0 ? chunk_env : 64;
-  if ((N + chunk - 1) / chunk > 56) chunk = (N + 55) / 56;
-  // Chunk schedule: full chunks, then a tapering tail (halving down to 16 images). The copy-in stream is the critical
-  // path from t = 0 whatever the chunking; what is exposed at the end is the LAST chunk's kernel + copy-out, so the
-  // last chunks are small (256 images: 64, 64, 64, 32, 16, 16). WG_HOST_TAPER=0 keeps equal chunks. Measured (3x3
-  // 256->256, 256 images per call, PCIe Gen5): 152-159 -> 162-164 k images/s; with the taper, chunk = 32 / 48 / 64 / 96 /
-  // 128 give 157 / 161 / 163 / 157 / 151 k.
-  static int taper_env = -1;
-  if (taper_env < 0) {
-    const char* e = getenv("WG_HOST_TAPER");
-    taper_env = e ? atoi(e) : 1;
+  int sizes[kMaxChunks];
+  const int n_chunks = chunk_schedule(N, chunk_env > 0 ? chunk_env : 64, taper_env, sizes, kMaxChunks);
+  if (n_chunks <= 0 || n_chunks > kMaxChunks) return WG_ERR_ARG;
+  while ((int)L->ev_in.size() < n_chunks) {
+    cudaEvent_t a = nullptr;
+    WG_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    L->ev_in.push_back(a);
   }
-  int sizes[64];
-  int n_chunks = 0;
-  for (int rem = N; rem > 0;) {
-    int c = rem < chunk ? rem : chunk;
-    if (taper_env && rem <= 2 * chunk && rem > 16) {
-      c = rem / 2;
-      if (c < 16) c = 16;
-      if (c > chunk) c = chunk;
-    }
-    sizes[n_chunks++] = c;
-    rem -= c;
-  }
-  while (L->n_events < n_chunks) {
-    WG_CUDA(cudaEventCreateWithFlags(&L->ev_in[L->n_events], cudaEventDisableTiming));
-    WG_CUDA(cudaEventCreateWithFlags(&L->ev_done[L->n_events], cudaEventDisableTiming));
-    L->n_events++;
+  while ((int)L->ev_done.size() < n_chunks) {
+    cudaEvent_t b = nullptr;
+    WG_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    L->ev_done.push_back(b);
   }
   const size_t x_img = in_px * L->cin, y_img = out_px * L->cout;  // floats per image
-  int n0 = 0;
-  for (int c = 0; c < n_chunks; ++c) {
+  int n0 = 0, rc = WG_OK;
+  cudaError_t e = cudaSuccess;
+  const char* what = "";
+#define WG_STEP(call)                               \
+  if (rc == WG_OK && (e = (call)) != cudaSuccess) { \
+    rc = WG_ERR_CUDA;                               \
+    what = #call;                                   \
+  }
+  for (int c = 0; c < n_chunks && rc == WG_OK; ++c) {
     const int nc = sizes[c];
-    WG_CUDA(cudaMemcpyAsync(L->d_x + (size_t)n0 * x_img, x_host + (size_t)n0 * x_img, (size_t)nc * x_img * sizeof(float),
+    WG_STEP(cudaMemcpyAsync(L->d_x + (size_t)n0 * x_img, x_host + (size_t)n0 * x_img, (size_t)nc * x_img * sizeof(float),
                             cudaMemcpyHostToDevice, L->s_h2d));
-    WG_CUDA(cudaEventRecord(L->ev_in[c], L->s_h2d));
-    WG_CUDA(cudaStreamWaitEvent(L->stream, L->ev_in[c], 0));
-    int rc = wg_run(L, L->d_x + (size_t)n0 * x_img, L->d_y + (size_t)n0 * y_img, nc, out_padded, L->stream);
-    if (rc != WG_OK) return rc;
-    WG_CUDA(cudaEventRecord(L->ev_done[c], L->stream));
-    WG_CUDA(cudaStreamWaitEvent(L->s_d2h, L->ev_done[c], 0));
-    WG_CUDA(cudaMemcpyAsync(y_host + (size_t)n0 * y_img, L->d_y + (size_t)n0 * y_img, (size_t)nc * y_img * sizeof(float),
+    WG_STEP(cudaEventRecord(L->ev_in[c], L->s_h2d));
+    WG_STEP(cudaStreamWaitEvent(L->stream, L->ev_in[c], 0));
+    if (rc == WG_OK)
+      rc = run_impl(L, L->d_x + (size_t)n0 * x_img, nullptr, L->d_y + (size_t)n0 * y_img, nc, out_padded, L->stream);
+    WG_STEP(cudaEventRecord(L->ev_done[c], L->stream));
+    WG_STEP(cudaStreamWaitEvent(L->s_d2h, L->ev_done[c], 0));
+    WG_STEP(cudaMemcpyAsync(y_host + (size_t)n0 * y_img, L->d_y + (size_t)n0 * y_img, (size_t)nc * y_img * sizeof(float),
                             cudaMemcpyDeviceToHost, L->s_d2h));
     n0 += nc;
   }
-  WG_CUDA(cudaStreamSynchronize(L->s_d2h));
-  WG_CUDA(cudaStreamSynchronize(L->stream));
+#undef WG_STEP
+  // on success AND on failure: nothing may still read x_host / write y_host when this function returns
+  const cudaError_t s0 = cudaStreamSynchronize(L->s_h2d);
+  const cudaError_t s1 = cudaStreamSynchronize(L->stream);
+  const cudaError_t s2 = cudaStreamSynchronize(L->s_d2h);
+  if (rc == WG_ERR_CUDA && e != cudaSuccess) return cuda_fail(e, what);
+  if (rc != WG_OK) return rc;
+  if (s0 != cudaSuccess) return cuda_fail(s0, "cudaStreamSynchronize(h2d)");
+  if (s1 != cudaSuccess) return cuda_fail(s1, "cudaStreamSynchronize(compute)");
+  if (s2 != cudaSuccess) return cuda_fail(s2, "cudaStreamSynchronize(d2h)");
   return WG_OK;
 }
 
 int wg_destroy(wg_layer_t* L) {
   if (!L) return WG_ERR_ARG;
+  DeviceGuard guard;
+  guard.enter(L->device);
   if (L->d_filter_small && L->d_filter_small != L->d_filter) cudaFree(L->d_filter_small);
   if (L->d_filter_tm16) cudaFree(L->d_filter_tm16);
   if (L->d_filter_n64) cudaFree(L->d_filter_n64);
@@ -428,15 +623,164 @@ int wg_destroy(wg_layer_t* L) {
   if (L->d_shift) cudaFree(L->d_shift);
   if (L->d_x) cudaFree(L->d_x);
   if (L->d_y) cudaFree(L->d_y);
-  for (int i = 0; i < L->n_events; ++i) {
-    cudaEventDestroy(L->ev_in[i]);
-    cudaEventDestroy(L->ev_done[i]);
-  }
+  for (cudaEvent_t ev : L->ev_in) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : L->ev_done) cudaEventDestroy(ev);
   if (L->s_h2d) cudaStreamDestroy(L->s_h2d);
   if (L->s_d2h) cudaStreamDestroy(L->s_d2h);
   if (L->stream) cudaStreamDestroy(L->stream);
-  free(L);
+  delete L;
   return WG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ packed blob
+int wg_layer_serialize(const wg_layer_t* Lc, void* buf, size_t cap, size_t* need) {
+  wg_layer* L = const_cast<wg_layer*>(Lc);
+  if (!L || !need) return WG_ERR_ARG;
+  size_t payload = L->w_host.size() * 4 + (size_t)L->cout * 8;
+  for (int i = 0; i < 5; ++i) payload += L->img_bytes[i];
+  *need = sizeof(BlobHeader) + payload;
+  if (!buf) return WG_OK;  // size query
+  if (cap < *need) return WG_ERR_ARG;
+  DeviceGuard guard;
+  if (guard.enter(L->device) != WG_OK) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  uint8_t* p = static_cast<uint8_t*>(buf) + sizeof(BlobHeader);
+  memcpy(p, L->w_host.data(), L->w_host.size() * 4);
+  p += L->w_host.size() * 4;
+  WG_CUDA(cudaMemcpy(p, L->d_scale, (size_t)L->cout * 4, cudaMemcpyDeviceToHost));
+  p += (size_t)L->cout * 4;
+  WG_CUDA(cudaMemcpy(p, L->d_shift, (size_t)L->cout * 4, cudaMemcpyDeviceToHost));
+  p += (size_t)L->cout * 4;
+  for (int i = 0; i < 5; ++i)
+    if (L->img_bytes[i]) {
+      WG_CUDA(cudaMemcpy(p, *layer_img_slot(L, i), L->img_bytes[i], cudaMemcpyDeviceToHost));
+      p += L->img_bytes[i];
+    }
+  BlobHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "WGB200L", 8);
+  h.version = kBlobVersion;
+  h.header_bytes = (uint32_t)sizeof(BlobHeader);
+  h.kind = L->kind, h.cin = L->cin, h.cout = L->cout, h.relu = L->relu, h.dtype = L->dtype, h.tile_n = L->tile_n;
+  h.tm_db = L->tm_db, h.tm16_ff = L->tm16_ff, h.ff_cg2 = L->ff_cg2, h.dev_build = kDev ? 1 : 0;
+  h.height = 14, h.width = 14;
+  h.w_elems = L->w_host.size();
+  for (int i = 0; i < 5; ++i) h.img_bytes[i] = L->img_bytes[i];
+  h.payload_bytes = payload;
+  h.checksum = fnv1a(static_cast<const uint8_t*>(buf) + sizeof(BlobHeader), payload);
+  memcpy(buf, &h, sizeof(h));
+  return WG_OK;
+}
+
+int wg_layer_deserialize(wg_layer_t** out, const void* buf, size_t bytes, int device) {
+  if (!out || !buf) return WG_ERR_ARG;
+  if (bytes < sizeof(BlobHeader)) return WG_ERR_IO;
+  BlobHeader h;
+  memcpy(&h, buf, sizeof(h));
+  if (memcmp(h.magic, "WGB200L", 8) != 0 || h.version != kBlobVersion || h.header_bytes != sizeof(BlobHeader))
+    return WG_ERR_IO;
+  if (h.payload_bytes != bytes - sizeof(BlobHeader)) return WG_ERR_IO;
+  const uint8_t* payload = static_cast<const uint8_t*>(buf) + sizeof(BlobHeader);
+  if (fnv1a(payload, h.payload_bytes) != h.checksum) return WG_ERR_IO;
+  if (h.kind < 0 || h.kind > 1 || h.cin <= 0 || h.cout <= 0 || h.height != 14 || h.width != 14) return WG_ERR_IO;
+  const size_t w_expect = h.kind == 0 ? (size_t)h.cout * h.cin * 9 : (size_t)h.cin * h.cout;
+  if (h.w_elems != w_expect) return WG_ERR_IO;
+  size_t total = h.w_elems * 4 + (size_t)h.cout * 8;
+  for (int i = 0; i < 5; ++i) total += h.img_bytes[i];
+  if (total != h.payload_bytes) return WG_ERR_IO;
+  const float* w = reinterpret_cast<const float*>(payload);
+  const float* scale = w + h.w_elems;
+  const float* shift = scale + h.cout;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(shift + h.cout);
+
+  int num_sms = 0;
+  int rc = check_device(device, &num_sms);
+  if (rc != WG_OK) return rc;
+  DeviceGuard guard;
+  if (guard.enter(device) != WG_OK) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  wg_layer* L = new (std::nothrow) wg_layer();
+  if (!L) return WG_ERR_NOMEM;
+  L->kind = h.kind, L->cin = h.cin, L->cout = h.cout, L->relu = h.relu, L->dtype = h.dtype, L->device = device;
+  L->num_sms = num_sms;
+  layer_plan(L);
+  // The images are the shared-memory images of THIS build's kernels. A blob written by a build with other kernel
+  // choices (developer knobs, an older version) still carries the raw weights: re-pack from those instead of failing.
+  bool same = L->tile_n == h.tile_n && L->tm_db == h.tm_db && L->tm16_ff == h.tm16_ff && L->ff_cg2 == h.ff_cg2;
+  for (int i = 0; i < 5; ++i) same = same && L->img_bytes[i] == h.img_bytes[i];
+  if (!same) {
+    delete L;
+    return create_common(out, h.kind, h.cin, h.cout, w, h.w_elems, scale, shift, h.relu, (wg_dtype_t)h.dtype, device);
+  }
+  auto fail = [&](int code) {
+    wg_destroy(L);
+    return code;
+  };
+  try {
+    L->w_host.assign(w, w + h.w_elems);
+  } catch (...) {
+    return fail(WG_ERR_NOMEM);
+  }
+  if ((rc = layer_alloc(L)) != WG_OK) return fail(rc);
+  cudaError_t e;
+#define WG_TRY(call)                 \
+  if ((e = (call)) != cudaSuccess) { \
+    cuda_fail(e, #call);             \
+    return fail(WG_ERR_CUDA);        \
+  }
+  WG_TRY(cudaMemcpyAsync(L->d_scale, scale, (size_t)h.cout * 4, cudaMemcpyHostToDevice, L->stream));
+  WG_TRY(cudaMemcpyAsync(L->d_shift, shift, (size_t)h.cout * 4, cudaMemcpyHostToDevice, L->stream));
+  for (int i = 0; i < 5; ++i)
+    if (L->img_bytes[i]) {
+      WG_TRY(cudaMemcpyAsync(*layer_img_slot(L, i), img, L->img_bytes[i], cudaMemcpyHostToDevice, L->stream));
+      img += L->img_bytes[i];
+    }
+  WG_TRY(cudaStreamSynchronize(L->stream));
+#undef WG_TRY
+  *out = L;
+  return WG_OK;
+}
+
+int wg_layer_save(const wg_layer_t* L, const char* path) {
+  if (!L || !path) return WG_ERR_ARG;
+  size_t need = 0;
+  int rc = wg_layer_serialize(L, nullptr, 0, &need);
+  if (rc != WG_OK) return rc;
+  std::vector<uint8_t> buf;
+  try {
+    buf.resize(need);
+  } catch (...) {
+    return WG_ERR_NOMEM;
+  }
+  rc = wg_layer_serialize(L, buf.data(), buf.size(), &need);
+  if (rc != WG_OK) return rc;
+  FILE* f = fopen(path, "wb");
+  if (!f) return WG_ERR_IO;
+  const size_t wr = fwrite(buf.data(), 1, buf.size(), f);
+  const int cl = fclose(f);
+  return (wr == buf.size() && cl == 0) ? WG_OK : WG_ERR_IO;
+}
+
+int wg_layer_load(wg_layer_t** out, const char* path, int device) {
+  if (!out || !path) return WG_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) return WG_ERR_IO;
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  if (sz < (long)sizeof(BlobHeader)) {
+    fclose(f);
+    return WG_ERR_IO;
+  }
+  std::vector<uint8_t> buf;
+  try {
+    buf.resize((size_t)sz);
+  } catch (...) {
+    fclose(f);
+    return WG_ERR_NOMEM;
+  }
+  const size_t rd = fread(buf.data(), 1, buf.size(), f);
+  fclose(f);
+  if (rd != buf.size()) return WG_ERR_IO;
+  return wg_layer_deserialize(out, buf.data(), buf.size(), device);
 }
 
 int wg_layer_info(const wg_layer_t* L, int* kind, int* cin, int* cout, int* relu) {
@@ -459,7 +803,7 @@ const char* wg_strerror(int status) {
     case WG_ERR_TMAP: return "tensor map encoding failed";
     case WG_ERR_NOMEM: return "out of memory";
     case WG_ERR_NODEVICE: return "no sm_100 (B200) device; this library has no CPU fallback";
-    case WG_ERR_IO: return "data file missing or short";
+    case WG_ERR_IO: return "file missing, short or not a layer blob of this version";
     default: return "unknown status";
   }
 }
@@ -475,7 +819,7 @@ int wg_device_count(void) {
   int n = 0;
   for (int i = 0; i < count; ++i) {
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++n;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10 && prop.minor == 0) ++n;
   }
   return n;
 }
@@ -489,7 +833,11 @@ void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean,
   }
 }
 
-void wg_set_max_ctas(int max_ctas) { g_max_ctas = max_ctas; }
-void wg_set_wino_kn(int kn) { g_wino_kn = (kn == 32 || kn == 64 || kn == 48) ? kn : 96; }
+void wg_set_max_ctas(int max_ctas) { g_max_ctas.store(max_ctas); }
+
+#ifdef WG_DEV_BUILD
+// developer build only (tools/libwinograd_b200_dev.so): choose a superseded 3x3 kernel generation
+void wg_dev_set_wino_kn(int kn) { g_wino_kn.store((kn == 32 || kn == 64 || kn == 48) ? kn : 96); }
+#endif
 
 }  // extern "C"

@@ -3,10 +3,22 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/winograd_b200.h"
 
 namespace wg {
+
+// Product build: no environment variable changes what the library computes or which kernel it launches. The developer
+// build (make dev -> tools/libwinograd_b200_dev.so, -DWG_DEV_BUILD) keeps the A/B knobs (WG_FF_*, WG_ONE_*, WG_WINO_*),
+// the ablation instantiations and the superseded kernel generations that the profiles under profiles/ were taken with.
+#ifdef WG_DEV_BUILD
+constexpr bool kDev = true;
+inline const char* dev_env(const char* name) { return getenv(name); }
+#else
+constexpr bool kDev = false;
+inline const char* dev_env(const char*) { return nullptr; }
+#endif
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -27,7 +39,8 @@ int wino_launch(const CUtensorMap& tmap, const void* u_img, const float* scale, 
                 cudaStream_t stream);
 int filter_transform_launch(const float* w_kcrs, void* u_img, int C, int K, int KN, int bf16, cudaStream_t stream);
 
-// throughput kernel with V in tensor memory (wino_tm_kernel.cu): TF32, cout slices of 48 / 32, its own filter image
+// previous generation, developer build only (wino_tm_kernel.cu): V in tensor memory, half fold, cout slices of 48 / 32
+#ifdef WG_DEV_BUILD
 int wino_tm_cls(int K, int db);  // cluster size (CTAs sharing the raw tiles of one M-block)
 int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C, int cls);
 int wino_tm_choose_db(int C, int K);  // 1 = double-buffered V / 32-wide slices, 0 = one V stage / 48-wide slices
@@ -36,6 +49,7 @@ int filter_transform_tm_launch(const float* w_kcrs, float* u_img, int C, int K, 
 int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                    int n_img, int C, int K, int db, int op16, int relu, int out_padded, int max_ctas,
                    cudaStream_t stream);
+#endif
 
 // throughput kernel with V in tensor memory and the whole inverse transform folded into the MMAs (wino_ff_kernel.cu):
 // 4 accumulators x 96-wide cout slices, its own filter image; same tensor map as the TM kernel (cls = 1)
@@ -63,9 +77,10 @@ int wino_small_launch(const CUtensorMap& tmap_small, const float* u_plain, const
 // ---- 1x1 GEMM path (one_kernels.cu)
 int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);
 int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout);
-int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
-               const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout, int BN, int relu,
-               int max_ctas, cudaStream_t stream);
-int weight_pack_launch(const float* w_cin_cout, float* w_img, int Cin, int Cout, int BN, cudaStream_t stream);
+// tmap_res / residual / relu_after: fused residual add in the epilogue (null = none); bf16: bf16-operand kernel
+int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtensorMap& tmap_res, const float* w_img,
+               const float* scale, const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout,
+               int BN, int bf16, int relu, const float* residual, int relu_after, int max_ctas, cudaStream_t stream);
+int weight_pack_launch(const float* w_cin_cout, float* w_img, int Cin, int Cout, int BN, int op16, cudaStream_t stream);
 
 }  // namespace wg

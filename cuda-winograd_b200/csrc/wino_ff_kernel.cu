@@ -622,7 +622,7 @@ __global__ void filter_transform_ff_kernel(const float* __restrict__ w_kcrs, flo
 int wino_ff_p9() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("WG_FF_P9");
+    const char* e = dev_env("WG_FF_P9");
     v = e ? (atoi(e) != 0) : 1;
   }
   return v;
@@ -641,14 +641,16 @@ int wino_ff_p9() {
 int wino_ff_cg2() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("WG_FF_CG2");
+    const char* e = dev_env("WG_FF_CG2");
     v = e ? (atoi(e) != 0) : 0;
   }
   return v && wino_ff_p9();
 }
 
 int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
+#ifdef WG_DEV_BUILD
   if (!wino_ff_p9()) return wino_tm_make_tmap(tmap, x, n_img, C, 1);
+#endif
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return WG_ERR_DRIVER;
   // x[N][16][16][C] viewed as (c, x/2, x&1, y&1, (n*16+y)/2); a box is one parity plane: 8 channels x 9 column pairs
@@ -681,7 +683,7 @@ static void ff_plan(int n_img, int K, int max_ctas, bool cg2, int* mv_out, int* 
   int mv = 128;
   static int mv_env = -1;
   if (mv_env < 0) {
-    const char* e = getenv("WG_WINO_MV");
+    const char* e = dev_env("WG_WINO_MV");
     mv_env = e ? atoi(e) : 0;
   }
   if (mv_env >= 16 && mv_env <= 128) {
@@ -760,7 +762,7 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
   // op16: 0 = TF32 operands, 1 = bf16, 2 = fp16 (V packed in TMEM, 16-channel stages)
   static int dbg = -1;  // WG_FF_DEBUG: ablation switches of the developer build (see the kernel)
   if (dbg < 0) {
-    const char* e = getenv("WG_FF_DEBUG");
+    const char* e = dev_env("WG_FF_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
   const int fp16 = op16 == 2;
@@ -770,7 +772,7 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
   // Default: 16-bit operands with C >= 256 only; WG_FF_W16=0|1 forces it off / on for everything.
   static int w16 = -1;
   if (w16 < 0) {
-    const char* e = getenv("WG_FF_W16");
+    const char* e = dev_env("WG_FF_W16");
     w16 = e ? (atoi(e) != 0) : 2;
   }
   // Launches whose work items do not fill the SMs (one wave): the time is that of ONE item, so make the item short.
@@ -783,9 +785,9 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
   // WG_FF_SPLIT=0 disables split-C, =2 lifts its C limit; WG_FF_NARROW=0 disables the narrow image.
   static int split_env = -1, narrow_env = -1;
   if (split_env < 0) {
-    const char* e = getenv("WG_FF_SPLIT");
+    const char* e = dev_env("WG_FF_SPLIT");
     split_env = e ? atoi(e) : 1;
-    const char* n = getenv("WG_FF_NARROW");
+    const char* n = dev_env("WG_FF_NARROW");
     narrow_env = n ? atoi(n) : 1;
   }
   if (!cg2 && dbg == 0 && wino_ff_p9()) {
@@ -816,20 +818,24 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
 #define WG_FF(H16_, DBG_, P9_, CG2_)                                                                                \
   return launch_ff<H16_, DBG_, P9_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, \
                                           fp16, dbg)
-  if (cg2) {  // CTA pairs: parity-plane raw layout only, no developer build
-    if (op16) WG_FF(true, false, true, true);
-    WG_FF(false, false, true, true);
-  }
-  if (wino_ff_p9()) {
-    if (dbg > 0) {
+  if constexpr (kDev) {
+    // developer build only (tools/libwinograd_b200_dev.so): CTA pairs, the ablation instantiation (WG_FF_DEBUG, results
+    // are garbage by design) and the single-box raw layout. None of these exist in the product library.
+    if (cg2) {
+      if (op16) WG_FF(true, false, true, true);
+      WG_FF(false, false, true, true);
+    }
+    if (wino_ff_p9() && dbg > 0) {
       if (op16) WG_FF(true, true, true, false);
       WG_FF(false, true, true, false);
     }
-    if (op16) WG_FF(true, false, true, false);
-    WG_FF(false, false, true, false);
+    if (!wino_ff_p9()) {
+      if (op16) WG_FF(true, false, false, false);
+      WG_FF(false, false, false, false);
+    }
   }
-  if (op16) WG_FF(true, false, false, false);
-  WG_FF(false, false, false, false);
+  if (op16) WG_FF(true, false, true, false);
+  WG_FF(false, false, true, false);
 #undef WG_FF
 }
 

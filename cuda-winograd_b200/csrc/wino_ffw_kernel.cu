@@ -589,9 +589,11 @@ int wino_ffw_launch(const CUtensorMap& tmap, const float* u_img, const float* sc
     if (op16) WG_FFW(true, false, true);
     WG_FFW(false, false, true);
   }
-  if (cg2) {
-    if (op16) WG_FFW(true, true, false);
-    WG_FFW(false, true, false);
+  if constexpr (kDev) {  // CTA pairs: experiment, developer build only
+    if (cg2) {
+      if (op16) WG_FFW(true, true, false);
+      WG_FFW(false, true, false);
+    }
   }
   if (op16) WG_FFW(true, false, false);
   WG_FFW(false, false, false);

@@ -482,7 +482,7 @@ static int launch_small(const CUtensorMap& tmap, const float* u_img, const float
 int wino_small_cs(int n_img, int C, int K, int max_ctas) {
   static int cs_env = -1;
   if (cs_env < 0) {
-    const char* e = getenv("WG_WINO_CS");
+    const char* e = dev_env("WG_WINO_CS");
     cs_env = e ? atoi(e) : 0;
   }
   if (cs_env == 1 || C % 8 != 0 || K % small::kKN != 0) return 0;
@@ -510,7 +510,7 @@ int wino_small_launch(const CUtensorMap& tmap_small, const float* u_plain, const
                       float* y, int n_img, int C, int K, int relu, int out_padded, int cs, cudaStream_t stream) {
   static int debug = -1;  // WG_DEBUG_ABLATE & 64: phase timestamps (developer aid)
   if (debug < 0) {
-    const char* e = getenv("WG_DEBUG_ABLATE");
+    const char* e = dev_env("WG_DEBUG_ABLATE");
     debug = e ? atoi(e) : 0;
   }
   const int n_items = ((n_img * 49 + small::kMB - 1) / small::kMB) * (K / small::kKN);

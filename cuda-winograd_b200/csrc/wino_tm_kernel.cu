@@ -588,12 +588,12 @@ int wino_tm_n48(int K) {  // 48*a + 32*b = K with a as large as possible
 int wino_tm_cls(int K, int db) {
   static int env = -1;
   if (env < 0) {
-    const char* e = getenv("WG_WINO_CLS");
+    const char* e = dev_env("WG_WINO_CLS");
     env = e ? atoi(e) : 0;
   }
   static int ww16 = -1;  // the 16-worker-warp experiment has no cluster variant
   if (ww16 < 0) {
-    const char* e = getenv("WG_WINO_WW");
+    const char* e = dev_env("WG_WINO_WW");
     ww16 = (e && atoi(e) == 16) ? 1 : 0;
   }
   // Measured (256->256, N=256): clusters of 2 -> 216 us, of 3 -> 478 us, against 151 us without: the per-stage
@@ -623,7 +623,7 @@ int wino_tm_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C, int c
 int wino_tm_choose_db(int C, int K) {
   static int env = -1;
   if (env < 0) {
-    const char* e = getenv("WG_WINO_TM");
+    const char* e = dev_env("WG_WINO_TM");
     env = e ? atoi(e) : 0;
   }
   if (env == 48) return 0;
@@ -662,7 +662,7 @@ static int launch_tm(const CUtensorMap& tmap, const float* u_img, const float* s
   int mv = 128;
   static int mv_env = -1;
   if (mv_env < 0) {
-    const char* e = getenv("WG_WINO_MV");
+    const char* e = dev_env("WG_WINO_MV");
     mv_env = e ? atoi(e) : 0;
   }
   if (mv_env >= 16 && mv_env <= 128) {
@@ -722,7 +722,7 @@ int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* sca
                                         op16 == 2);
   static int ww = -1;  // WG_WINO_WW=8|16: worker warps (4 or 2 channels per thread); 16 and db are experiments
   if (ww < 0) {
-    const char* e = getenv("WG_WINO_WW");
+    const char* e = dev_env("WG_WINO_WW");
     ww = e ? atoi(e) : 8;
     if (ww != 16) ww = 8;
   }

@@ -764,7 +764,7 @@ static int launch_wino_split(const CUtensorMap& tmap, const void* u_img, const f
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   static int ablate = -1;  // debug only, see launch_wino
   if (ablate < 0) {
-    const char* env = getenv("WG_DEBUG_ABLATE");
+    const char* env = dev_env("WG_DEBUG_ABLATE");
     ablate = env ? atoi(env) : 0;
   }
   cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_bn_relu_kernel<true, BF16, CS>, tmap, u_img, scale, shift, y, n_img,
@@ -780,7 +780,7 @@ static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* 
     // latency mode when the whole batch is a handful of items: split the channel loop over a cluster
     static int cs_env = -1;  // WG_WINO_CS=1 disables, 4|8 forces (when legal); default auto
     if (cs_env < 0) {
-      const char* e = getenv("WG_WINO_CS");
+      const char* e = dev_env("WG_WINO_CS");
       cs_env = e ? atoi(e) : 0;
     }
     const int n_kv = C / (BF16 ? 16 : 8);
@@ -813,7 +813,7 @@ static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* 
   int mv = 128;
   static int mv_env = -1;  // WG_WINO_MV=<16..128> pins it (experiments)
   if (mv_env < 0) {
-    const char* e = getenv("WG_WINO_MV");
+    const char* e = dev_env("WG_WINO_MV");
     mv_env = e ? atoi(e) : 0;
   }
   if (mv_env >= 16 && mv_env <= 128) {
@@ -835,7 +835,7 @@ static int launch_wino(const CUtensorMap& tmap, const void* u_img, const float* 
   if (grid < 1) grid = 1;
   static int ablate = -1;  // debug only: WG_DEBUG_ABLATE=<bitmask> switches pipeline pieces off for timing experiments
   if (ablate < 0) {
-    const char* e = getenv("WG_DEBUG_ABLATE");
+    const char* e = dev_env("WG_DEBUG_ABLATE");
     ablate = e ? atoi(e) : 0;
   }
   cudaLaunchConfig_t cfg = {};
@@ -862,10 +862,12 @@ int wino_launch(const CUtensorMap& tmap, const void* u_img, const float* scale, 
     return launch_wino<true, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, bf16 == 2, max_ctas,
                                    stream);
   }
-  if (KN == 64)
-    return launch_wino<true, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, 0, max_ctas, stream);
-  if (KN == 32)
-    return launch_wino<false, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, 0, max_ctas, stream);
+  if constexpr (kDev) {  // the TF32 instantiations of this first-generation kernel: developer build only
+    if (KN == 64)
+      return launch_wino<true, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, 0, max_ctas, stream);
+    if (KN == 32)
+      return launch_wino<false, false>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, 0, max_ctas, stream);
+  }
   return WG_ERR_ARG;
 }
 

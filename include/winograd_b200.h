@@ -24,6 +24,8 @@
 #ifndef WINOGRAD_B200_H_
 #define WINOGRAD_B200_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -32,7 +34,8 @@ typedef struct wg_layer wg_layer_t; /* opaque: device copies of the packed filte
 
 /* operand type of the tensor-core GEMMs (inputs, outputs and accumulation are always fp32):
  *   WG_TF32  10-bit mantissa, fp32 range                      tolerance 1e-3   all layers (default)
- *   WG_BF16   7-bit mantissa, fp32 range                      tolerance 1e-2   3x3 layers, C % 16 == 0, K % 64 == 0
+ *   WG_BF16   7-bit mantissa, fp32 range                      tolerance 1e-2   3x3 layers with C % 16 == 0 and
+ *                                                                              K % 64 == 0; every 1x1 layer
  *   WG_FP16  10-bit mantissa, |V| = |sum of 4 inputs| < 65504  tolerance 1e-3   3x3 layers, same constraints;
  *            TF32-class accuracy at bf16 speed for bounded activations (e.g. post-BN/ReLU feature maps) */
 typedef enum { WG_TF32 = 0, WG_BF16 = 1, WG_FP16 = 2 } wg_dtype_t;
@@ -45,14 +48,15 @@ typedef enum {
   WG_ERR_TMAP = -4,   /* tensor-map encoding rejected */
   WG_ERR_NOMEM = -5,
   WG_ERR_NODEVICE = -6, /* no sm_100 device: the library never falls back to a CPU path */
-  WG_ERR_IO = -7        /* legacy entry points: a data/<name>.bin file is missing or short */
+  WG_ERR_IO = -7        /* a layer blob is missing, short, corrupt or of another version */
 } wg_status;
 
 /* One-time per layer: copies weights / BN to `device`, runs the filter transform U = G g G^T (F(2x2,3x3)) or the
  * 1x1 weight pack on the GPU, rounds the filter operand to TF32 (round-to-nearest).
  * Replaces the offline weight_generator (data_generator.py:63-78) and the per-call cudaMalloc/cudaMemcpy block of
- * kernel_128() (Kernel128_winograd.cu:236-256). All pointers are HOST pointers. C, K multiples of 32 (3x3);
- * Cin multiple of 32 and Cout multiple of 128 (1x1). */
+ * kernel_128() (Kernel128_winograd.cu:236-256). All pointers are HOST pointers. Shape constraints (else WG_ERR_ARG):
+ * 3x3: C % 8 == 0 and K % 32 == 0 (16-bit operand types: C % 16 == 0 and K % 64 == 0); 1x1: Cin % 32 == 0 and
+ * Cout % 128 == 0 (WG_FP16 does not exist for 1x1 layers). */
 int wg_conv3x3_create(wg_layer_t** out, int C, int K, const float* w_kcrs, const float* scale, const float* shift,
                       int relu, wg_dtype_t dtype, int device);
 int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_cout, const float* scale,
@@ -64,18 +68,44 @@ int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_co
  * kernel_*_1_in/out() (one launch, Kernel128_one.cu:98,316). For a 1x1 layer out_padded != 0 writes the same
  * zero-bordered [N][16][16][Cout] frame instead of [N][196][Cout], i.e. exactly the input a following 3x3 layer
  * reads, so bottleneck chains 1x1 -> 3x3 -> 1x1 need no padding pass in between.
- * out_padded is a flag word: WG_OUT_PADDED (1) as above; WG_OUT_MULTICAST (2, 3x3 TF32 layers): y_dev is an NVLS
+ * out_flags is a flag word: WG_OUT_PADDED (1) as above; WG_OUT_MULTICAST (2, 3x3 TF32 layers): y_dev is an NVLS
  * multicast address (cuMulticast* / torch symmetric memory) and every output store is issued as multimem.st, i.e. the
  * NVSwitch replicates this GPU's shard into the buffers of all GPUs bound to the multicast object -- conv + BN + ReLU
  * fused with the all-gather of the output, no NCCL call (the caller still has to barrier across ranks before reading
- * the gathered tensor). Other values / layer kinds with the multicast flag: WG_ERR_ARG. */
+ * the gathered tensor AND before the next call overwrites it). Other values / layer kinds with the multicast flag:
+ * WG_ERR_ARG. Thread safety: concurrent wg_run calls on one layer from several host threads are safe (the tensor-map
+ * cache is locked, the launch takes copies); the caller's current device is restored on return. */
 #define WG_OUT_PADDED 1
 #define WG_OUT_MULTICAST 2
-int wg_run(wg_layer_t* layer, const float* x_dev, float* y_dev, int N, int out_padded, void* cuda_stream);
+#define WG_OUT_RELU_AFTER_ADD 4
+int wg_run(wg_layer_t* layer, const float* x_dev, float* y_dev, int N, int out_flags, void* cuda_stream);
+
+/* The step that follows the reference's `_out` 1x1 layers in a ResNet bottleneck block (they stop before it:
+ * Kernel128_one.cu:271-272, Kernel256_one.cu:273 write scale*acc + shift with no ReLU): the residual add, fused into
+ * the same launch. 1x1 layers, dense output only: y = act2(act(scale * (x W) + shift) + residual), act = the layer's own
+ * ReLU flag, act2 = ReLU iff out_flags has WG_OUT_RELU_AFTER_ADD. residual_dev: [N][196][Cout] fp32 on the layer's
+ * device, 16-byte aligned; it may alias y_dev (each element is read before it is written by the same thread). */
+int wg_run_residual(wg_layer_t* layer, const float* x_dev, const float* residual_dev, float* y_dev, int N,
+                    int out_flags, void* cuda_stream);
 
 /* Same, end to end with HOST buffers: H2D copy of x, wg_run, D2H copy of y, stream-synchronised on return.
  * Device staging buffers are cached in the layer (grown on demand). This is the call bench.py's `e2e` times. */
 int wg_run_host(wg_layer_t* layer, const float* x_host, float* y_host, int N, int out_padded);
+
+/* The chunk schedule wg_run_host uses for a batch of N images (host-only, no GPU needed): writes up to `cap` chunk
+ * sizes and returns the number of chunks (<= 64 for every N; the sizes sum to N). */
+int wg_host_chunk_schedule(int N, int* sizes, int cap);
+
+/* Packed per-layer blob: everything create() produced -- the raw weights, the folded BN vectors and the kernels'
+ * packed filter images (TF32 / bf16 U = G g G^T in shared-memory order, swizzled 1x1 weight tiles) -- behind a
+ * versioned header with the layer's shape and a checksum. Replaces the 18 loose files of data_generator.py:55-78,
+ * 116-127 as the deployment format (data/<name>.bin stay valid inputs to create()); loading skips the filter transform.
+ * A blob whose images were packed for other kernel choices is re-packed from its raw weights. serialize(): buf == NULL
+ * queries the size into *need. load/deserialize: WG_ERR_IO for a missing, short, corrupt or other-version blob. */
+int wg_layer_serialize(const wg_layer_t* layer, void* buf, size_t cap, size_t* need);
+int wg_layer_deserialize(wg_layer_t** out, const void* buf, size_t bytes, int device);
+int wg_layer_save(const wg_layer_t* layer, const char* path);
+int wg_layer_load(wg_layer_t** out, const char* path, int device);
 
 int wg_destroy(wg_layer_t* layer);
 
@@ -90,13 +120,16 @@ int wg_device_count(void);              /* number of sm_100 devices visible; 0 =
 void wg_fold_bn(int K, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                 float* scale_out, float* shift_out);
 
-/* Tuning knobs (process-wide; for benchmarking): max CTAs per launch (default = #SMs); 3x3 TF32 kernel variant for
- * layers created afterwards: 96 = transformed input kept in tensor memory, whole inverse transform folded into the MMAs,
- * cout slices of 96/64 (default); 48 = same with half of the inverse transform folded, slices of 48/32; 64 / 32 = the
- * earlier kernels with both MMA operands in shared memory (half fold / one accumulator per Winograd point).
- * The environment variable WG_WINO_KN sets the initial value. */
+/* Roofline denominator measured on the device itself: runs nothing but back-to-back tcgen05.mma (M=128, N=256, both
+ * operands in shared memory) on every SM for ~1-3 ms and reports the dense tensor-pipe throughput in TFLOP/s for
+ * dtype = WG_TF32 (kind::tf32, K=8) or WG_BF16 (kind::f16, K=16); *clk_per_mma (optional) = SM clocks per MMA at the
+ * device's nominal clock. bench.py divides the kernels' achieved TFLOP/s by this number. */
+int wg_measure_tensor_peak(int device, int dtype, double* tflops, double* clk_per_mma);
+
+/* Benchmarking knob, process-wide (atomic): max CTAs per launch, 0 = the device's SM count (default). The product
+ * library reads no environment variables; A/B knobs and superseded kernel generations live in the developer build
+ * (make dev -> tools/libwinograd_b200_dev.so). */
 void wg_set_max_ctas(int max_ctas);
-void wg_set_wino_kn(int kn);
 
 #ifdef __cplusplus
 }

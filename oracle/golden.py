@@ -102,6 +102,30 @@ def bottleneck_chain(x, w1, s1, b1, w3, s3, b3, w2, s2, b2):
     return conv1x1_bn(m.reshape(n, 196, -1), w2, s2, b2, False)
 
 
+def conv1x1_bn_residual(x, w, scale, shift, relu, residual, relu_after_add, acc=np.float64):
+    """The step after the reference's `_out` 1x1 layers, which stop right before it (Kernel128_one.cu:271-272 and
+    Kernel256_one.cu:273 store scale*acc + shift without a ReLU because the residual add comes next):
+    y = act2(act(scale * (x w) + shift) + residual), act = ReLU iff `relu`, act2 = ReLU iff `relu_after_add`."""
+    y = np.asarray(x).astype(acc, copy=False) @ np.asarray(w).astype(acc, copy=False)
+    y = y * np.asarray(scale, acc) + np.asarray(shift, acc)
+    if relu:
+        y = np.maximum(y, 0)
+    y = y + np.asarray(residual).astype(acc, copy=False).reshape(y.shape)
+    if relu_after_add:
+        y = np.maximum(y, 0)
+    return y.astype(np.float32)
+
+
+def bottleneck_block(x, w1, s1, b1, w3, s3, b3, w2, s2, b2):
+    """Full ResNet bottleneck block with the identity shortcut: relu(bottleneck_chain(x) + x); needs Cin == Cout
+    (BASELINE.json configs[4]; the add + final ReLU are what the reference leaves out, see conv1x1_bn_residual)."""
+    n = x.shape[0]
+    a = conv1x1_bn(x, w1, s1, b1, True)
+    frame = pad_frame(a.reshape(n, 14, 14, -1))
+    m = conv3x3_bn_relu(frame, w3, s3, b3, True)
+    return conv1x1_bn_residual(m.reshape(n, 196, -1), w2, s2, b2, False, x, True)
+
+
 # ------------------------------------------------------------------------------------------ brute force (tiny shapes)
 def conv3x3_bn_relu_loops(x, w, scale, shift, relu=True):
     """Pure-Python loops, float64; only for tiny C, K in tests."""

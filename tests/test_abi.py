@@ -183,3 +183,58 @@ def test_shard_and_gather_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"rank {r} ok" in o, o
+
+
+def test_product_library_has_no_developer_kernels(built):
+    """The product .so ships no ablation instantiation (wino3x3_ff_kernel<..., DBG = true, ...>), no CTA-pair or
+    superseded-generation kernel, reads no environment variable (no getenv import) and exports no developer knob."""
+    syms = subprocess.run(["nm", "-D", "-C", built.LIB_PATH], capture_output=True, text=True).stdout
+    kernels = [l for l in syms.splitlines() if "wg::wino3x3" in l or "wg::conv1x1" in l]
+    assert kernels, "kernel symbols expected in the dynamic table"
+    for l in kernels:
+        m = re.search(r"wino3x3_ff_kernel<(\w+), (\w+), (\w+), (\w+)>", l)
+        if m:
+            assert m.group(2) == "false", l        # DBG
+            assert m.group(3) == "true", l         # parity-plane raw layout only
+            assert m.group(4) == "false", l        # no CTA pairs
+    assert "wino3x3_tm_kernel" not in syms
+    assert "wg_dev_set_wino_kn" not in syms and "wg_set_wino_kn" not in syms
+    # (getenv itself is still imported -- the statically linked CUDA runtime reads CUDA_* variables -- but none of the
+    #  library's own knob names survives in the product binary)
+    strs = subprocess.run(["strings", built.LIB_PATH], capture_output=True, text=True).stdout.splitlines()
+    assert not [t for t in strs if re.fullmatch(r"WG_[A-Z0-9_]+", t)], "the product library must not read WG_* knobs"
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 63, 64, 100, 255, 256, 257, 300, 2560, 2561, 3584, 100000, 300000,
+                               458000, 500000, 1000000, 2 ** 31 - 1])
+def test_host_chunk_schedule_is_bounded(built, n):
+    """wg_run_host's chunk schedule (65+ chunks overflowed fixed 64-entry arrays for N >~ 458k): at most
+    64 chunks for any N, positive sizes summing to N, tapering tail; 256 images -> 64, 64, 64, 32, 16, 16."""
+    s = built.host_chunk_schedule(n)
+    assert 1 <= len(s) <= 64 and all(c > 0 for c in s) and sum(s) == n
+    if n == 256:
+        assert s == [64, 64, 64, 32, 16, 16]
+    if n >= 128:
+        assert s[-1] <= s[0]                                       # the exposed last chunk is never the big one
+    # cap smaller than the schedule: still returns the count, writes only `cap` entries
+    buf = (ctypes.c_int * 2)(-1, -1)
+    assert built.lib().wg_host_chunk_schedule(n, buf, 2) == len(s)
+    assert [buf[i] for i in range(min(2, len(s)))] == s[:2]
+    assert built.lib().wg_host_chunk_schedule(0, buf, 2) == 0
+
+
+def test_blob_and_residual_calls_fail_loudly_without_gpu(built):
+    """No GPU here: deserialising a well-formed header must end in WG_ERR_NODEVICE or WG_ERR_IO, never in a CPU path."""
+    L = built.lib()
+    h = ctypes.c_void_p()
+    assert L.wg_layer_deserialize(ctypes.byref(h), b"x" * 16, 16, 0) == -7          # WG_ERR_IO: shorter than a header
+    assert L.wg_layer_load(ctypes.byref(h), b"/nonexistent/blob.wgb", 0) == -7
+    assert L.wg_run_residual(None, None, None, None, 1, 0, None) == -1               # WG_ERR_ARG
+    tf = ctypes.c_double()
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if not have_gpu:
+        assert L.wg_measure_tensor_peak(0, 0, ctypes.byref(tf), None) == -6          # WG_ERR_NODEVICE

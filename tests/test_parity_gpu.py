@@ -108,57 +108,33 @@ def test_3x3_small_batch_split_c_mode(lib_loaded, torch_cuda, n, c, k, padded):
 TOL_BF16 = 1e-2
 
 
-@pytest.mark.parametrize("kn", [96, 48, 64])
 @pytest.mark.parametrize("n,c,k", [(40, 64, 256), (33, 32, 96), (50, 24, 160), (20, 16, 512), (64, 128, 128),
                                    (131, 48, 192), (37, 8, 32), (29, 40, 64), (300, 16, 32), (24, 256, 128),
                                    (12, 256, 256)])
-def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, kn, n, c, k):
-    """Every throughput kernel on batches that do not fill the last 128-tile M-block and on every cout-slice width:
-    kn = 96 the full-fold kernel (wino_ff_kernel.cu: 4 accumulators, slices of 96 / 64 / 32 -- the default), kn = 48 the
-    half-fold V-in-TMEM kernel (slices of 48 / 32), kn = 64 the shared-memory-operand kernel. TF32 and, where the shape
-    allows them, bf16 / fp16 operands; dense output and the zero-bordered frame must agree bit for bit. The two C = 256
-    shapes are small enough for the split-C mode (clusters of 2 sharing an item, DSMEM reduction)."""
+def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, n, c, k):
+    """The throughput kernel (wino_ff_kernel.cu / wino_ffw_kernel.cu: 4 accumulators, cout slices of 96 / 64 / 32) on
+    batches that do not fill the last 128-tile M-block and on every cout-slice width. TF32 and, where the shape allows
+    them, bf16 / fp16 operands; dense output and the zero-bordered frame must agree bit for bit. The two C = 256 shapes
+    are small enough for the split-C mode (clusters of 2 sharing an item, DSMEM reduction). (The superseded kernel
+    generations live in the developer build: tests/test_dev_gpu.py.)"""
     torch = torch_cuda
-    if kn == 64 and k % 64:
-        pytest.skip("the KN=64 kernel needs K % 64 == 0")
     x, w, sc, sh = _rand3x3(np.random.RandomState(900 + n + c + k), n, c, k)
     gold = golden.conv3x3_bn_relu(x, w, sc, sh, True)
     xd = torch.from_numpy(x).cuda()
-    lib_loaded.lib().wg_set_wino_kn(kn)
-    try:
-        for dt, tol in ((lib_loaded.WG_TF32, TOL_TF32), (lib_loaded.WG_BF16, TOL_BF16), (lib_loaded.WG_FP16, TOL_TF32)):
-            if dt != lib_loaded.WG_TF32 and (c % 16 or k % 64):
-                continue
-            layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=dt)
-            y = layer(xd).cpu().numpy()
-            yp = layer(xd, out_padded=True).cpu().numpy()
-            assert golden.rel_err(y, gold) <= tol
-            np.testing.assert_array_equal(yp[:, 1:15, 1:15], y)
-            assert np.all(yp[:, 0] == 0) and np.all(yp[:, 15] == 0) and np.all(yp[:, :, 0] == 0) and np.all(yp[:, :, 15] == 0)
-            # run to run: bit-identical (fixed accumulation order, no atomics; a hand-off race would show up here)
-            y0 = layer(xd)
-            for _ in range(8):
-                assert torch.equal(layer(xd), y0)
-            layer.close()
-    finally:
-        lib_loaded.lib().wg_set_wino_kn(96)
-
-
-@pytest.mark.parametrize("knob", ["WG_FF_P9=0", "WG_FF_CG2=1", "WG_FF_W16=1", "WG_FF_W16=0", "WG_FF_SPLIT=2", "WG_FF_SPLIT=0",
-                                  "WG_FF_NARROW=0"])
-def test_3x3_full_fold_kernel_experiment_knobs(lib_loaded, knob):
-    """The full-fold kernel's A/B knobs stay correct: WG_FF_P9=0 = the TM kernel's single-box raw layout, WG_FF_CG2=1 =
-    CTA pairs (tcgen05 cta_group::2, clusters of 2; measured slower, default off), WG_FF_W16=1 / 0 = sixteen transform
-    warps (wino_ffw_kernel.cu) for every layer / for none (default: 16-bit operands with C >= 256), WG_FF_SPLIT=2 =
-    split-C for every channel count (default: C >= 256; 0 = never), WG_FF_NARROW=0 = never the 64-wide filter image.
-    The knobs are read once per process, hence the subprocess."""
-    k, v = knob.split("=")
-    env = dict(os.environ, **{k: v})
-    k = k + "_" + v
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ff_check.py"), "--quick", "--kns", "96",
-                        "--iters", "3", "--out", os.path.join(ROOT, "gpurun_out", "ff_check_" + k.lower() + ".json")],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for dt, tol in ((lib_loaded.WG_TF32, TOL_TF32), (lib_loaded.WG_BF16, TOL_BF16), (lib_loaded.WG_FP16, TOL_TF32)):
+        if dt != lib_loaded.WG_TF32 and (c % 16 or k % 64):
+            continue
+        layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=dt)
+        y = layer(xd).cpu().numpy()
+        yp = layer(xd, out_padded=True).cpu().numpy()
+        assert golden.rel_err(y, gold) <= tol
+        np.testing.assert_array_equal(yp[:, 1:15, 1:15], y)
+        assert np.all(yp[:, 0] == 0) and np.all(yp[:, 15] == 0) and np.all(yp[:, :, 0] == 0) and np.all(yp[:, :, 15] == 0)
+        # run to run: bit-identical (fixed accumulation order, no atomics; a hand-off race would show up here)
+        y0 = layer(xd)
+        for _ in range(8):
+            assert torch.equal(layer(xd), y0)
+        layer.close()
 
 
 @pytest.mark.parametrize("n,c,k", [(1, 128, 128), (1, 256, 256), (3, 64, 64), (5, 48, 128), (64, 128, 128), (131, 48, 192)])
@@ -186,14 +162,40 @@ def test_3x3_fp16_operand_variant(lib_loaded, torch_cuda, n, c, k):
     assert golden.rel_err(y, golden.conv3x3_bn_relu(x, w, sc, sh, True)) <= TOL_TF32
 
 
-def test_bf16_is_rejected_where_it_does_not_exist(lib_loaded):
-    with pytest.raises(lib_loaded.WinogradB200Error):   # the 1x1 activation operand is never touched by CUDA cores
-        lib_loaded._Layer.__init__(lib_loaded.Conv1x1Bn.__new__(lib_loaded.Conv1x1Bn), 32, 128,
-                                   np.zeros((32, 128), np.float32), np.ones(128, np.float32),
-                                   np.ones(128, np.float32), True, 0, lib_loaded.WG_BF16)
-    with pytest.raises(lib_loaded.WinogradB200Error):   # K must be a multiple of 64 for the folded bf16 kernel
+def test_16bit_operands_are_rejected_where_they_do_not_exist(lib_loaded):
+    with pytest.raises(lib_loaded.WinogradB200Error):   # fp16 operands are a 3x3 variant only
+        lib_loaded.Conv1x1Bn(np.zeros((32, 128), np.float32), np.ones(128, np.float32), np.ones(128, np.float32), True,
+                             dtype=lib_loaded.WG_FP16)
+    with pytest.raises(lib_loaded.WinogradB200Error):   # K must be a multiple of 64 for the 16-bit 3x3 kernels
         lib_loaded.Conv3x3BnRelu(np.zeros((32, 32, 3, 3), np.float32), np.ones(32, np.float32),
                                  np.ones(32, np.float32), dtype=lib_loaded.WG_BF16)
+
+
+@pytest.mark.parametrize("n,cin,cout,relu", [(1, 512, 128, True), (1, 128, 512, False), (1, 1024, 256, True),
+                                             (1, 256, 1024, False), (3, 64, 384, True), (37, 96, 128, False),
+                                             (256, 256, 1024, False), (256, 512, 128, True)])
+def test_1x1_bf16_operand_variant(lib_loaded, torch_cuda, n, cin, cout, relu):
+    """The stated bf16 variant of the 1x1 path (north_star): bf16 operands (activation stage converted into tensor
+    memory by four extra warps, bf16 weight image), fp32 I/O and accumulation, tolerance 1e-2; all four README shapes,
+    ragged M-tiles, N = 256, dense and padded-frame output, run-to-run bit-identical."""
+    torch = torch_cuda
+    rs = np.random.RandomState(cin + cout + n)
+    x = ((rs.rand(n, 196, cin) - 0.5) * 40).astype(np.float32)
+    w = ((rs.rand(cin, cout) - 0.5) * 40).astype(np.float32)
+    sc = ((rs.rand(cout) - 0.5) * 0.1).astype(np.float32)
+    sh = ((rs.rand(cout) - 0.5) * 40).astype(np.float32)
+    layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu, dtype=lib_loaded.WG_BF16)
+    xd = torch.from_numpy(x).cuda()
+    y = layer(xd)
+    gold = golden.conv1x1_bn(x.reshape(-1, cin), w, sc, sh, relu).reshape(n, 196, cout)
+    assert golden.rel_err(y.cpu().numpy(), gold) <= TOL_BF16
+    assert (float(y.min()) >= 0) == bool(relu)
+    for _ in range(4):
+        assert torch.equal(layer(xd), y)
+    yp = layer(xd, out_padded=True)
+    assert torch.equal(yp[:, 1:15, 1:15].reshape(n, 196, cout), y)
+    assert float(yp[:, 0].abs().max()) == 0 and float(yp[:, :, 15].abs().max()) == 0
+    layer.close()
 
 
 @pytest.mark.parametrize("n", [1, 4, 64])
@@ -262,8 +264,9 @@ def test_special_inputs(lib_loaded, torch_cuda):
 # ------------------------------------------------------------------------------------------- BASELINE.json full sizes
 @pytest.mark.parametrize("c", [128, 256])
 def test_3x3_full_batch_256_properties(lib_loaded, torch_cuda, c):
-    """N = 256 (BASELINE.json configs[3]): oracle on a sample of images; batch invariance (image i inside the batch ==
-    image i alone, bit for bit -- tiles are independent GEMM rows); border of the padded frame exactly zero."""
+    """N = 256 (BASELINE.json configs[3]): the WHOLE output tensor against the oracle (FP64-accumulating golden, all 256
+    images); batch invariance (image i inside the batch == image i alone -- tiles are independent GEMM rows); border of
+    the padded frame exactly zero."""
     torch = torch_cuda
     n = 256
     x, w, sc, sh = _rand3x3(np.random.RandomState(c), n, c, c)
@@ -276,22 +279,27 @@ def test_3x3_full_batch_256_properties(lib_loaded, torch_cuda, c):
     assert float(yp[:, 0].abs().max()) == 0 and float(yp[:, 15].abs().max()) == 0
     assert float(yp[:, :, 0].abs().max()) == 0 and float(yp[:, :, 15].abs().max()) == 0
     yh = y.cpu().numpy()
-    for i in (0, 1, 2, 77, 130, 255):
-        assert golden.rel_err(yh[i], golden.conv3x3_bn_relu(x[i:i + 1], w, sc, sh)[0]) <= TOL_TF32
+    gold = golden.conv3x3_bn_relu(x, w, sc, sh)                   # all 256 images
+    assert gold.shape == yh.shape
+    assert golden.rel_err(yh, gold) <= TOL_TF32
+    per_image = np.abs(yh - gold).reshape(n, -1).max(axis=1) / np.abs(gold).max()
+    assert per_image.max() <= TOL_TF32, int(per_image.argmax())
+    for i in (0, 77, 255):
         # a single image runs the split-C latency mode (channel loop split over a cluster, partials summed in a
         # fixed order): same products, different fp32 summation grouping -> equal to accumulation round-off
         alone = layer(xd[i:i + 1].contiguous()).cpu().numpy()[0]
         assert np.abs(alone - yh[i]).max() <= 1e-5 * np.abs(yh[i]).max()
         again = layer(xd[i:i + 1].contiguous()).cpu().numpy()[0]
         np.testing.assert_array_equal(alone, again)      # deterministic (no atomics)
-    # checksum of checksums against the oracle on a strided subset (keeps the CPU side to seconds)
-    sub = np.arange(0, n, 16)
-    gold = golden.conv3x3_bn_relu(x[sub], w, sc, sh)
-    assert abs(yh[sub].astype(np.float64).sum() - gold.astype(np.float64).sum()) <= 1e-3 * np.abs(gold).sum()
+    for dt, tol in ((lib_loaded.WG_BF16, TOL_BF16), (lib_loaded.WG_FP16, TOL_TF32)):
+        l16 = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=dt)
+        assert golden.rel_err(l16(xd).cpu().numpy(), gold) <= tol
+        l16.close()
 
 
 @pytest.mark.parametrize("cin,cout,relu", [(512, 128, True), (128, 512, False), (1024, 256, True), (256, 1024, False)])
 def test_1x1_full_batch_256_properties(lib_loaded, torch_cuda, cin, cout, relu):
+    """N = 256: the whole [256*196 x Cout] output against the oracle."""
     torch = torch_cuda
     n = 256
     rs = np.random.RandomState(cin)
@@ -302,8 +310,10 @@ def test_1x1_full_batch_256_properties(lib_loaded, torch_cuda, cin, cout, relu):
     layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu)
     xd = torch.from_numpy(x).cuda()
     yh = layer(xd).cpu().numpy()
-    for i in (0, 3, 128, 255):
-        assert golden.rel_err(yh[i], golden.conv1x1_bn(x[i], w, sc, sh, relu)) <= TOL_TF32
+    gold = golden.conv1x1_bn(x.reshape(-1, cin), w, sc, sh, relu).reshape(n, 196, cout)
+    assert golden.rel_err(yh, gold) <= TOL_TF32
+    assert (yh.min() >= 0) == bool(relu)
+    for i in (0, 128, 255):
         # a single image may run the split-K latency mode (same products, regrouped fp32 sums, fixed order)
         alone = layer(xd[i:i + 1].contiguous()).cpu().numpy()[0]
         assert np.abs(alone - yh[i]).max() <= 1e-5 * np.abs(yh[i]).max()
@@ -343,16 +353,6 @@ def test_results_do_not_depend_on_the_grid_size(lib_loaded, torch_cuda, max_ctas
         lib_loaded.lib().wg_set_max_ctas(0)
         for layer, _ in layers:
             layer.close()
-
-
-def test_1x1_cta_pair_variant(lib_loaded):
-    """WG_ONE_PAIR=1 (experiment, default off): the 1x1 throughput kernel as tcgen05 cta_group::2 pairs. The knob is
-    read once per process, hence the subprocess; it re-runs this file's 1x1 and chain tests with the knob set."""
-    env = dict(os.environ, WG_ONE_PAIR="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
-                        "1x1_ragged or 1x1_full_batch or 1x1_padded or bottleneck_chain_vs"],
-                       env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("n,cin,cout", [(1, 512, 128), (3, 64, 256), (5, 1024, 256)])
@@ -430,6 +430,177 @@ def test_host_buffer_call_equals_device_call_and_counts_launches(lib_loaded, tor
         y_s = layer(torch.from_numpy(x).cuda())
     s.synchronize()
     np.testing.assert_array_equal(y_s.cpu().numpy(), y_dev)
+
+
+@pytest.mark.parametrize("n", [100, 256, 300])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_run_host_chunked_pipeline_parity(lib_loaded, torch_cuda, n, pinned):
+    """The call bench.py's `e2e` times: wg_run_host with HOST buffers -- chunked three-stream pipeline with the tapering
+    tail (N = 256: 64, 64, 64, 32, 16, 16), each chunk routed to the kernel its size selects. Against (1) the oracle on
+    ALL images (1e-3), (2) wg_run on exactly the chunks of wg_host_chunk_schedule(n): bit-identical, (3) the one-launch
+    device call on the whole batch: equal to fp32 summation-order round-off (other kernel variants sum the channel loop
+    in another grouping). Pinned and pageable host memory; the padded frame; repeated calls on a reused layer."""
+    torch = torch_cuda
+    c = k = 256
+    x, w, sc, sh = _rand3x3(np.random.RandomState(n), n, c, k)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True)
+    xt = torch.from_numpy(x)
+    yt = torch.full((n, 14, 14, k), float("nan"))
+    if pinned:
+        xt, yt = xt.pin_memory(), yt.pin_memory()
+    layer.run_host_ptr(xt.data_ptr(), yt.data_ptr(), n)
+    yh = yt.numpy()
+    assert np.isfinite(yh).all()                                   # every element was written
+    gold = golden.conv3x3_bn_relu(x, w, sc, sh)
+    assert golden.rel_err(yh, gold) <= TOL_TF32
+    sched = lib_loaded.host_chunk_schedule(n)
+    assert sum(sched) == n and (n != 256 or sched == [64, 64, 64, 32, 16, 16])
+    xd = torch.from_numpy(x).cuda()
+    n0 = 0
+    for nc in sched:
+        part = layer(xd[n0:n0 + nc].contiguous()).cpu().numpy()
+        np.testing.assert_array_equal(yh[n0:n0 + nc], part)
+        n0 += nc
+    whole = layer(xd).cpu().numpy()
+    assert np.abs(whole - yh).max() <= 2e-5 * np.abs(whole).max()
+    # again on the same layer (staging buffers, events and tensor maps reused), padded frame, smaller batch
+    yt2 = torch.full((n, 16, 16, k), float("nan"))
+    if pinned:
+        yt2 = yt2.pin_memory()
+    layer.run_host_ptr(xt.data_ptr(), yt2.data_ptr(), n, out_padded=True)
+    np.testing.assert_array_equal(yt2.numpy()[:, 1:15, 1:15], yh)
+    assert float(yt2[:, 0].abs().max()) == 0 and float(yt2[:, :, 15].abs().max()) == 0
+    y_small = layer.run_host(x[:7])
+    np.testing.assert_array_equal(y_small, layer(xd[:7].contiguous()).cpu().numpy())
+    layer.close()
+
+
+def test_run_host_1x1_and_argument_checks(lib_loaded, torch_cuda):
+    torch = torch_cuda
+    rs = np.random.RandomState(3)
+    n, cin, cout = 130, 256, 1024
+    x = ((rs.rand(n, 196, cin) - 0.5) * 40).astype(np.float32)
+    w = ((rs.rand(cin, cout) - 0.5) * 40).astype(np.float32)
+    sc, sh = rs.rand(cout).astype(np.float32), rs.rand(cout).astype(np.float32)
+    layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu=False)
+    y = layer.run_host(x)
+    assert golden.rel_err(y, golden.conv1x1_bn(x, w, sc, sh, False)) <= TOL_TF32
+    with pytest.raises(AssertionError):                           # wrong dtype / shape must not reach the C side
+        layer.run_host(x, y_host=np.empty((n, 196, cout), np.float64))
+    with pytest.raises(AssertionError):
+        layer.run_host(x, y_host=np.empty((n - 1, 196, cout), np.float32))
+    layer.close()
+
+
+@pytest.mark.parametrize("n,cin,cout", [(1, 128, 512), (1, 256, 1024), (3, 64, 384), (32, 128, 512), (47, 256, 1024),
+                                        (256, 128, 512), (256, 256, 1024)])
+@pytest.mark.parametrize("relu_after", [True, False])
+def test_1x1_fused_residual_add(lib_loaded, torch_cuda, n, cin, cout, relu_after):
+    """f2: the residual add (+ final ReLU) fused into the 1x1 `_out` epilogue (wg_run_residual) -- the step the
+    reference's kernels stop before (Kernel128_one.cu:271-272, Kernel256_one.cu:273). Small-batch split-K kernel, the
+    weight-stationary and the plain throughput schedules, ragged last M-tile, in-place (y aliases the residual), TF32
+    and bf16 operands; the whole tensor against the oracle."""
+    torch = torch_cuda
+    rs = np.random.RandomState(n + cin + cout)
+    x = ((rs.rand(n, 196, cin) - 0.5) * 4).astype(np.float32)
+    w = ((rs.rand(cin, cout) - 0.5) * 0.5).astype(np.float32)
+    sc = (rs.rand(cout) + 0.5).astype(np.float32)
+    sh = (rs.rand(cout) - 0.5).astype(np.float32)
+    res = ((rs.rand(n, 196, cout) - 0.5) * 30).astype(np.float32)
+    gold = golden.conv1x1_bn_residual(x.reshape(-1, cin), w, sc, sh, False, res, relu_after).reshape(n, 196, cout)
+    xd, rd = torch.from_numpy(x).cuda(), torch.from_numpy(res).cuda()
+    for dt, tol in ((lib_loaded.WG_TF32, TOL_TF32), (lib_loaded.WG_BF16, TOL_BF16)):
+        layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu=False, dtype=dt)
+        before = lib_loaded.launch_count()
+        y = layer(xd, residual=rd, relu_after_add=relu_after)
+        assert lib_loaded.launch_count() == before + 1            # still ONE launch
+        assert golden.rel_err(y.cpu().numpy(), gold) <= tol
+        assert (float(y.min()) >= 0) == bool(relu_after)
+        plain = layer(xd)                                          # the add really is the only difference
+        ref = plain + rd
+        if relu_after:
+            ref = torch.relu(ref)
+        assert torch.equal(y, ref)
+        inplace = rd.clone()
+        layer(xd, out=inplace, residual=inplace, relu_after_add=relu_after)
+        assert torch.equal(inplace, y)
+        layer.close()
+    with pytest.raises(lib_loaded.WinogradB200Error):             # 3x3 layers have no residual input
+        l3 = lib_loaded.Conv3x3BnRelu(np.zeros((32, 32, 3, 3), np.float32), np.ones(32, np.float32), np.ones(32, np.float32))
+        l3(torch.zeros((1, 16, 16, 32), device="cuda"), residual=torch.zeros((1, 14, 14, 32), device="cuda"))
+
+
+@pytest.mark.parametrize("n,ch,c", [(1, 512, 128), (4, 1024, 256), (32, 512, 128), (256, 1024, 256)])
+def test_bottleneck_block_with_residual_vs_oracle(lib_loaded, torch_cuda, n, ch, c):
+    """BASELINE.json configs[4]: the full bottleneck residual block 1x1 -> 3x3 -> 1x1 (+x, ReLU) in three launches,
+    the whole output against the oracle, N up to 256."""
+    torch = torch_cuda
+    rs = np.random.RandomState(n + ch)
+    x = (rs.rand(n, 196, ch) - 0.5).astype(np.float32)
+    w1 = ((rs.rand(ch, c) - 0.5) * 0.2).astype(np.float32)
+    w3 = ((rs.rand(c, c, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    w2 = ((rs.rand(c, ch) - 0.5) * 0.2).astype(np.float32)
+    bn = [((rs.rand(k) + 0.5).astype(np.float32), (rs.rand(k) - 0.3).astype(np.float32)) for k in (c, c, ch)]
+    block = lib_loaded.Bottleneck(w1, *bn[0], w3, *bn[1], w2, *bn[2], residual=True)
+    before = lib_loaded.launch_count()
+    y = block(torch.from_numpy(x).cuda())
+    assert lib_loaded.launch_count() == before + 3
+    gold = golden.bottleneck_block(x, w1, *bn[0], w3, *bn[1], w2, *bn[2])
+    assert float(y.min()) >= 0
+    assert golden.rel_err(y.cpu().numpy(), gold) <= 3 * TOL_TF32   # three TF32 layers in sequence
+
+
+@pytest.mark.parametrize("kind,dtype", [("3x3", "tf32"), ("3x3", "bf16"), ("1x1", "tf32"), ("1x1", "bf16")])
+def test_layer_blob_round_trip(lib_loaded, torch_cuda, tmp_path, kind, dtype):
+    """f3: wg_layer_save / wg_layer_load. A layer loaded from its blob computes bit-identical results (no filter
+    transform on load: the launch counter does not move), corrupt and truncated blobs are rejected with WG_ERR_IO."""
+    torch = torch_cuda
+    rs = np.random.RandomState(5)
+    dt = lib_loaded.WG_TF32 if dtype == "tf32" else lib_loaded.WG_BF16
+    if kind == "3x3":
+        x, w, sc, sh = _rand3x3(rs, 40, 64, 128)
+        layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=dt)
+    else:
+        x = (rs.rand(40, 196, 64) - 0.5).astype(np.float32)
+        w = (rs.rand(64, 256) - 0.5).astype(np.float32)
+        sc, sh = rs.rand(256).astype(np.float32), rs.rand(256).astype(np.float32)
+        layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu=True, dtype=dt)
+    xd = torch.from_numpy(x).cuda()
+    path = str(tmp_path / "layer.wgb")
+    layer.save(path)
+    blob = open(path, "rb").read()
+    assert blob[:7] == b"WGB200L" and blob == layer.serialize()
+    before = lib_loaded.launch_count()
+    loaded = lib_loaded._Layer.load(path)
+    assert lib_loaded.launch_count() == before                    # images uploaded as they are: no pack kernel
+    assert type(loaded) is type(layer) and (loaded.cin, loaded.cout, loaded.relu) == (layer.cin, layer.cout, layer.relu)
+    for nn in (1, 40):
+        assert torch.equal(loaded(xd[:nn].contiguous()), layer(xd[:nn].contiguous()))
+    again = lib_loaded._Layer.deserialize(loaded.serialize())
+    assert torch.equal(again(xd), layer(xd))
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x40
+    for broken in (bytes(bad), blob[:-5], blob[:40], b"not a blob" * 20):
+        with pytest.raises(lib_loaded.WinogradB200Error, match="blob"):
+            lib_loaded._Layer.deserialize(broken)
+    with pytest.raises(lib_loaded.WinogradB200Error):
+        lib_loaded._Layer.load(str(tmp_path / "missing.wgb"))
+
+
+def test_current_device_is_restored(lib_loaded, torch_cuda):
+    """wg_* calls on a layer of another GPU must not change the calling thread's current device (needs >= 2 GPUs)."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("single-GPU box")
+    x, w, sc, sh = _rand3x3(np.random.RandomState(11), 4, 32, 32)
+    torch.cuda.set_device(0)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, device=1)
+    assert torch.cuda.current_device() == 0
+    layer(torch.from_numpy(x).to("cuda:1"))
+    layer.run_host(x)
+    assert torch.cuda.current_device() == 0
+    layer.close()
+    assert torch.cuda.current_device() == 0
 
 
 def test_layers_on_two_devices_in_one_process(lib_loaded, torch_cuda):

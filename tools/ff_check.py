@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ff_check.json"))
-    ap.add_argument("--kns", default="96,48")
+    ap.add_argument("--kns", default="96")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--time-only", action="store_true", help="skip the parity section, never fail (ablation runs)")
     ap.add_argument("--dtypes", default="tf32,bf16,fp16")
@@ -34,6 +34,13 @@ def main():
     wg = wg_loader.load()
     dev = torch.device("cuda", 0)
     rows = []
+
+    def set_kn(kn):
+        """kn != 96 (superseded kernel generations) exists in the developer build only: WG_B200_DEV_LIB=1."""
+        if wg.IS_DEV_LIB:
+            wg.lib().wg_dev_set_wino_kn(kn)
+        else:
+            assert kn == 96, "kn != 96 needs the developer build: make dev && WG_B200_DEV_LIB=1 python tools/ff_check.py"
 
     def rand(rs, n, c, k):
         x = (rs.rand(n, 16, 16, c) - 0.5).astype(np.float32)
@@ -51,7 +58,7 @@ def main():
     if args.time_only:
         shapes = []
     for kn in [int(v) for v in args.kns.split(",")]:
-        wg.lib().wg_set_wino_kn(kn)
+        set_kn(kn)
         for (n, c, k) in shapes:
             rs = np.random.RandomState(n + c + k)
             x, w, sc, sh = rand(rs, n, c, k)
@@ -89,7 +96,7 @@ def main():
         x_s = xs[0][sample].cpu().numpy()
         gold = golden.conv3x3_bn_relu(x_s, w, sc, sh, True)
         for kn in [int(v) for v in args.kns.split(",")]:
-            wg.lib().wg_set_wino_kn(kn)
+            set_kn(kn)
             for name, dt in dts.items():
                 layer = wg.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=dt)
                 for i in range(5):
@@ -111,7 +118,7 @@ def main():
                 layer.close()
         del xs, ys
         torch.cuda.empty_cache()
-    wg.lib().wg_set_wino_kn(96)
+    set_kn(96)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(rows, open(args.out, "w"), indent=1)
     bad = [r for r in rows if not r["ok"]]

@@ -13,6 +13,7 @@
 
 #include "../cuda-winograd_b200/csrc/ptx.cuh"
 #include "../include/winograd_b200.h"
+extern "C" void wg_dev_set_wino_kn(int kn);  // developer build only (tools/libwinograd_b200_dev.so)
 
 #define CK(x)                                                                          \
   do {                                                                                 \
@@ -1028,7 +1029,7 @@ int main(int argc, char** argv) {
     if (!(rel <= tol)) ++fails;
   };
   for (int kn : {48, 64, 32}) {
-    wg_set_wino_kn(kn);
+    wg_dev_set_wino_kn(kn);
     printf("-- 3x3 variant KN=%d\n", kn);
     bad(check3x3(1, 128, 128, 1, 0, {0}), 1e-3);
     bad(check3x3(1, 128, 128, 1, 1, {0}), 1e-3);
@@ -1040,7 +1041,7 @@ int main(int argc, char** argv) {
       time_layer(0, 256, 256, 256, 1);
     }
   }
-  wg_set_wino_kn(96);
+  wg_dev_set_wino_kn(96);
   g_dtype = WG_BF16;
   printf("-- 3x3 bf16 operand variant (tolerance 1e-2)\n");
   bad(check3x3(1, 128, 128, 1, 1, {0}), 1e-2);
