@@ -65,15 +65,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef WG_WAIT_TIMEOUT_NS
 #define WG_WAIT_TIMEOUT_NS 4000000000ull
 #endif
+// The timeout clock is only consulted every 2^16 failed polls (reading %globaltimer on every blocked wait would put a
+// slow special-register read on the critical path of every pipeline hand-off).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > WG_WAIT_TIMEOUT_NS) {
-      printf("wg: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
+    if ((++spins & 0xffff) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > WG_WAIT_TIMEOUT_NS) {
+        printf("wg: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }
@@ -81,7 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Same, but acquiring at cluster scope: pairs with mbar_arrive_remote() of threads in other CTAs of the cluster whose
 // st.shared::cluster into this CTA's shared memory must be visible after the wait.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   for (;;) {
     uint32_t ok;
@@ -93,9 +99,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (ok) return;
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > WG_WAIT_TIMEOUT_NS) {
-      printf("wg: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+    if ((++spins & 0xffff) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > WG_WAIT_TIMEOUT_NS) {
+        printf("wg: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
     }
   }
 }

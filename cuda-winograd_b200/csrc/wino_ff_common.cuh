@@ -63,6 +63,29 @@ __host__ __device__ inline bool has_narrow(int K) { return K % 64 == 0 && K / 64
 
 __device__ __forceinline__ float ff_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
+// Two packed fp32 in one 64-bit register (low word = first value): the transform warps' column / row passes run on
+// Blackwell's 2-wide fp32 pipe (add.f32x2 / fma.f32x2), i.e. half the issue slots of scalar FADDs.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+  f2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) {  // a - b = fma(b, -1, a), exact
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(b), "l"(0xBF800000BF800000ull), "l"(a));
+  return d;
+}
+// round both halves to TF32 (nearest, ties away): +0x1000 on each word; the MMA ignores the low 13 mantissa bits. A
+// carry from the low into the high word would need a low word >= 0xFFFFF000 (a negative NaN payload): not a number the
+// transform produces from finite inputs.
+__device__ __forceinline__ f2_t f2_tf32(f2_t v) { return v + 0x0000100000001000ull; }
+__device__ __forceinline__ float f2_lo(f2_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f2_hi(f2_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ void ld_shared_f2x2(uint32_t addr, f2_t& a, f2_t& b) {  // 16 bytes = 4 fp32 = two pairs
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
 template <bool H16, bool CG2>
 __device__ __forceinline__ void ff_umma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {

@@ -354,7 +354,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           mbar_wait(&raw_full[rs], rph);
           if (warp == 0 && lane == 0 && sb == 0) { WG_TS(ts_w, 1); }
           if (DBG && ts_item && item_idx == 0 && kb == 0 && sb == 0) ts_g[14] = (long long)globaltimer_ns();
-          float d[4][4][4];
+          f2_t d[4][4][2];  // [dy][dx][channel pair]: packed fp32 pairs, all passes on the 2-wide fp32 pipe
           if (no_xf) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[rs]);
@@ -376,27 +376,24 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
               for (int dx = 0; dx < 4; ++dx) {
                 const uint32_t ad = P9 ? a + ((dy & 1) * 2 + (dx & 1)) * kPlaneBytes + p9off[dy >> 1][dx >> 1]
                                        : a + dy * 512 + (dx & 1) * 256 + (dx >> 1) * 32 + ((dx >> 1) ? h1 : h0);
-                const float4 v = ld_shared_v4(ad);
-                d[dy][dx][0] = v.x, d[dy][dx][1] = v.y, d[dy][dx][2] = v.z, d[dy][dx][3] = v.w;
+                ld_shared_f2x2(ad, d[dy][dx][0], d[dy][dx][1]);
               }
           } else {
 #pragma unroll
             for (int dy = 0; dy < 4; ++dy)
 #pragma unroll
-              for (int dx = 0; dx < 4; ++dx)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) d[dy][dx][c] = 0.f;
+              for (int dx = 0; dx < 4; ++dx) d[dy][dx][0] = d[dy][dx][1] = 0ull;
           }
           // column pass t = B^T d, in place over dy
 #pragma unroll
           for (int dx = 0; dx < 4; ++dx)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float d0 = d[0][dx][c], d1 = d[1][dx][c], d2 = d[2][dx][c], d3 = d[3][dx][c];
-              d[0][dx][c] = d0 - d2;
-              d[1][dx][c] = d1 + d2;
-              d[2][dx][c] = d2 - d1;
-              d[3][dx][c] = d1 - d3;
+            for (int c = 0; c < 2; ++c) {
+              const f2_t d0 = d[0][dx][c], d1 = d[1][dx][c], d2 = d[2][dx][c], d3 = d[3][dx][c];
+              d[0][dx][c] = f2_sub(d0, d2);
+              d[1][dx][c] = f2_add(d1, d2);
+              d[2][dx][c] = f2_sub(d2, d1);
+              d[3][dx][c] = f2_sub(d1, d3);
             }
           // the raw stage is in registers now: hand it back to the producer before the row pass
           __syncwarp();
@@ -411,34 +408,41 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           for (int jh = 0; jh < 2; ++jh) {
             if (warp == 0 && lane == 0 && sb == kSub - 1) { WG_TS(ts_w, 2 + jh * 3); }
             if (sb == 0) {
-              if (wait_v) wait_done(&done[pslot + jh], pph);  // the MMAs that last read this V half have completed
+              // the MMAs that last read this V half have completed. Two V stages (db): ONE wait per stage, on the later
+              // of the two commits of stage g - 2 (commits complete in order, so the first half is free as well).
+              if (wait_v && (!db || jh == 0)) wait_done(&done[pslot + (db ? 1 : jh)], pph);
               tc_fence_after();
             }
             if (warp == 0 && lane == 0 && sb == kSub - 1) { WG_TS(ts_w, 3 + jh * 3); }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float v0[4], v1[4];  // points (i, 2jh) and (i, 2jh+1)
+              f2_t v0[2], v1[2];  // points (i, 2jh) and (i, 2jh+1)
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float a0 = d[i][0][c], a1 = d[i][1][c], a2 = d[i][2][c], a3 = d[i][3][c];
-                v0[c] = jh == 0 ? a0 - a2 : a2 - a1;
-                v1[c] = jh == 0 ? a1 + a2 : a1 - a3;
-                if constexpr (!H16) v0[c] = ff_tf32(v0[c]), v1[c] = ff_tf32(v1[c]);
+              for (int c = 0; c < 2; ++c) {
+                const f2_t a0 = d[i][0][c], a1 = d[i][1][c], a2 = d[i][2][c], a3 = d[i][3][c];
+                v0[c] = jh == 0 ? f2_sub(a0, a2) : f2_sub(a2, a1);
+                v1[c] = jh == 0 ? f2_add(a1, a2) : f2_sub(a1, a3);
+                if constexpr (!H16) v0[c] = f2_tf32(v0[c]), v1[c] = f2_tf32(v1[c]);
               }
               const uint32_t dst = vcol + jh * 64 + (i * 2) * 8;
               if constexpr (H16) {
-                tmem_st_x2(dst, ff_pack16(v0[0], v0[1], fp16), ff_pack16(v0[2], v0[3], fp16));
-                tmem_st_x2(dst + 8, ff_pack16(v1[0], v1[1], fp16), ff_pack16(v1[2], v1[3], fp16));
+                tmem_st_x2(dst, ff_pack16(f2_lo(v0[0]), f2_hi(v0[0]), fp16), ff_pack16(f2_lo(v0[1]), f2_hi(v0[1]), fp16));
+                tmem_st_x2(dst + 8, ff_pack16(f2_lo(v1[0]), f2_hi(v1[0]), fp16), ff_pack16(f2_lo(v1[1]), f2_hi(v1[1]), fp16));
               } else {
-                tmem_st_x4(dst, v0[0], v0[1], v0[2], v0[3]);
-                tmem_st_x4(dst + 8, v1[0], v1[1], v1[2], v1[3]);
+                tmem_st_x4(dst, f2_lo(v0[0]), f2_hi(v0[0]), f2_lo(v0[1]), f2_hi(v0[1]));
+                tmem_st_x4(dst + 8, f2_lo(v1[0]), f2_hi(v1[0]), f2_lo(v1[1]), f2_hi(v1[1]));
               }
             }
-            if (sb == kSub - 1) {
+            // V half stored by this warp: tell the MMA thread. Two V stages (db): one tcgen05.wait::st / fence / warp sync
+            // per STAGE, then both halves' arrivals (the MMA thread's second wait is then already satisfied).
+            if (sb == kSub - 1 && (!db || jh == 1)) {
               tmem_st_wait();
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) arrive_leader(&full[slot + jh]);
+              if (lane == 0) {
+                if (db) arrive_leader(&full[slot]);
+                arrive_leader(&full[slot + jh]);
+              }
               if (warp == 0 && lane == 0) { WG_TS(ts_w, 4 + jh * 3); }
             }
           }

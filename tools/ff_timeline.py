@@ -19,8 +19,10 @@ def main():
     import torch
     import wg_loader
     wg = wg_loader.load()
-    for name, dt in (("tf32", wg.WG_TF32), ("bf16", wg.WG_BF16)):
-        c = k = 256
+    c_arg = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    dts = (("tf32", wg.WG_TF32), ("bf16", wg.WG_BF16)) if len(sys.argv) <= 2 else (("tf32", wg.WG_TF32),)
+    for name, dt in dts:
+        c = k = c_arg
         n = 256
         rs = np.random.RandomState(0)
         w = (rs.rand(k, c, 3, 3) - 0.5).astype(np.float32)
@@ -61,8 +63,9 @@ def main():
             main = (it[:, idx, 1] - it[:, idx, 0]).astype(np.float64)
             epi = (it[:, idx, 2] - it[:, idx, 1]).astype(np.float64)
             ok = it[:, idx, 2] > 0
-            sl = it[:, idx, 3] % 3
-            for w in range(3):
+            n_sl = (k + 95) // 96
+            sl = it[:, idx, 3] % n_sl
+            for w in range(n_sl):
                 m = ok & (sl == w)
                 if m.any():
                     print(f"   item #{idx} slice {w}: {int(m.sum()):3d} CTAs  main loop {main[m].mean():8.0f} clk "
