@@ -74,8 +74,11 @@ __global__ void __launch_bounds__(H16 ? kOneThreads + 128 : kOneThreads, 1)
 conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                       const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ w_img,
                       const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y_padded,
-                      long long m_rows, int Cin, int Cout, int relu, int bn_packed, int relu_after) {
+                      long long m_rows, int Cin, int Cout, int relu, int bn_packed, int relu_after, int dev_flags) {
   using S = OneSmem<BN, WS, H16>;
+  // dev_flags: always 0 in the product build. Developer build (WG_ONE_ABLATE): 1 no weight loads, 2 no activation loads,
+  // 4 no output stores, 8 no MMAs -- results are garbage, only the time is of interest (profiles/one_ablation_r02.md).
+  const int abl = kDev ? dev_flags : 0;
   static_assert(!RES || (CL == 1 && !PAIR), "the residual epilogue exists for the plain and weight-stationary schedules");
   static_assert(!WS || CL == 1, "weight-stationary schedule has no cluster variant");
   static_assert(!PAIR || (CL == 2 && !WS), "CTA pairs are clusters of 2");
@@ -168,9 +171,12 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const uint8_t* b_src = b_tile(nt);
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full[st], WS ? S::kABytes : (PAIR ? S::kABytes + S::kBBytes / 2 : S::kABytes + S::kBBytes));
-          tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, kb * kBK, mt * 128, &full[st]);
-          if constexpr (WS) {
+          const uint32_t a_bytes = (abl & 2) ? 0u : S::kABytes;
+          const uint32_t b_bytes = (abl & 1) ? 0u : (WS ? 0u : (PAIR ? S::kBBytes / 2 : S::kBBytes));
+          mbar_arrive_expect_tx(&full[st], a_bytes + b_bytes);
+          if (!(abl & 2)) tma_tensor_2d_g2s(smem + S::kOffA + st * S::kABytes, &tmap_a, kb * kBK, mt * 128, &full[st]);
+          if (abl & 1) {
+          } else if constexpr (WS) {
           } else if constexpr (PAIR) {  // this CTA's half of the weight rows, at offset 0 of the stage in BOTH CTAs
             tma_bulk_g2s(smem + S::kOffB + st * S::kBBytes, b_src + (size_t)kb * b_kb_stride + crank * (S::kBBytes / 2),
                          S::kBBytes / 2, &full[st]);
@@ -213,7 +219,8 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           mbar_wait(&full[st], ph);
           if constexpr (H16) mbar_wait(&a_ready[st], ph);  // the converter warps have written this stage's A into TMEM
           tc_fence_after();
-          if constexpr (H16) {
+          if (abl & 8) {
+          } else if constexpr (H16) {
             constexpr uint32_t idesc16 = make_idesc(kFmtBF16, 128, BN);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
@@ -390,7 +397,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && rows_here) {
+        if (lane == 0 && rows_here && !(abl & 4)) {
           tma_tensor_2d_s2g(&tmap_y, stage_out + (chunk & 1) * S::kStageOutBytes, nt * BN + c0, mt * 128 + quad * 32);
           tma_store_commit();
         }
@@ -670,6 +677,16 @@ int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int C
   return encode_2d(tmap, y, Cout, m_rows, 32, 32);
 }
 
+// developer build only: WG_ONE_ABLATE=<bits> (see the kernel); 0 in the product build
+static int one_dev_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* a = dev_env("WG_ONE_ABLATE");
+    v = a ? atoi(a) : 0;
+  }
+  return v;
+}
+
 struct OneRes {  // residual operand of a launch (RES instantiations)
   const CUtensorMap* tmap_r;
   int relu_after;
@@ -717,7 +734,7 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL, WS, PAIR, RES, H16>, tmap, tmap_y,
                                      res.tmap_r ? *res.tmap_r : tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout,
-                                     relu, bn_packed, res.relu_after);
+                                     relu, bn_packed, res.relu_after, one_dev_flags());
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
