@@ -30,7 +30,8 @@ WG_OUT_PADDED, WG_OUT_MULTICAST, WG_OUT_RELU_AFTER_ADD = 1, 2, 4
 
 # every symbol include/winograd_b200.h, include/wg_legacy.h and include/util.h declare
 ABI_SYMBOLS = (
-    "wg_conv3x3_create", "wg_conv1x1_create", "wg_run", "wg_run_residual", "wg_run_host", "wg_host_chunk_schedule",
+    "wg_conv3x3_create", "wg_conv1x1_create", "wg_conv3x3_create_hw", "wg_conv1x1_create_hw", "wg_layer_geometry",
+    "wg_frame_dims", "wg_run", "wg_run_residual", "wg_run_host", "wg_host_chunk_schedule",
     "wg_destroy", "wg_layer_info", "wg_layer_serialize", "wg_layer_deserialize", "wg_layer_save", "wg_layer_load",
     "wg_launch_count", "wg_strerror", "wg_last_cuda_error", "wg_device_count", "wg_fold_bn", "wg_set_max_ctas",
     "wg_measure_tensor_peak",
@@ -69,6 +70,11 @@ def lib() -> ctypes.CDLL:
         L.wg_conv3x3_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, c_fp, c_fp, c_fp,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.wg_conv1x1_create.argtypes = L.wg_conv3x3_create.argtypes
+        L.wg_conv3x3_create_hw.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, c_fp, c_fp, c_fp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.wg_conv1x1_create_hw.argtypes = L.wg_conv3x3_create_hw.argtypes
+        L.wg_layer_geometry.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 4
+        L.wg_frame_dims.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 2
         L.wg_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                              ctypes.c_void_p]
         L.wg_run_residual.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
@@ -119,6 +125,13 @@ def launch_count() -> int:
     return int(lib().wg_launch_count())
 
 
+def frame_dims(h: int, w: int):
+    """(Hf, Wf) of the input frame of an h x w map (host-only; wg_frame_dims)."""
+    hf, wf = ctypes.c_int(), ctypes.c_int()
+    _check(lib().wg_frame_dims(int(h), int(w), ctypes.byref(hf), ctypes.byref(wf)), "wg_frame_dims")
+    return hf.value, wf.value
+
+
 def host_chunk_schedule(n: int):
     """Chunk sizes wg_run_host uses for a batch of n images (host-only logic; no GPU needed)."""
     buf = (ctypes.c_int * 64)()
@@ -147,18 +160,26 @@ class _Layer:
     """A fused layer living on one GPU: packed filter + folded BN on the device, one kernel launch per call."""
     kind = -1
 
-    def __init__(self, cin, cout, w, scale, shift, relu, device=0, dtype=WG_TF32):
+    def __init__(self, cin, cout, w, scale, shift, relu, device=0, dtype=WG_TF32, hw=(14, 14)):
         import numpy as np
         self.cin, self.cout, self.relu, self.device = int(cin), int(cout), bool(relu), int(device)
         self.dtype = int(dtype)
+        self.h, self.w = int(hw[0]), int(hw[1])
         w = np.ascontiguousarray(w, np.float32)
         scale = np.ascontiguousarray(scale, np.float32)
         shift = np.ascontiguousarray(shift, np.float32)
         assert scale.shape == (cout,) and shift.shape == (cout,)
         self._h = ctypes.c_void_p()
-        create = lib().wg_conv3x3_create if self.kind == 0 else lib().wg_conv1x1_create
-        _check(create(ctypes.byref(self._h), cin, cout, _fptr(w), _fptr(scale), _fptr(shift), int(relu), dtype,
-                      device), "create")
+        create = lib().wg_conv3x3_create_hw if self.kind == 0 else lib().wg_conv1x1_create_hw
+        _check(create(ctypes.byref(self._h), cin, cout, self.h, self.w, _fptr(w), _fptr(scale), _fptr(shift), int(relu),
+                      dtype, device), "create")
+        self._read_geometry()
+
+    def _read_geometry(self):
+        h, w, hf, wf = (ctypes.c_int() for _ in range(4))
+        _check(lib().wg_layer_geometry(self._h, ctypes.byref(h), ctypes.byref(w), ctypes.byref(hf), ctypes.byref(wf)),
+               "wg_layer_geometry")
+        self.h, self.w, self.hf, self.wf = h.value, w.value, hf.value, wf.value
 
     # -- packed blob (wg_layer_save / wg_layer_load): cold start without the filter transform
     def save(self, path):
@@ -181,6 +202,7 @@ class _Layer:
         self.cin, self.cout, self.relu, self.device = cin.value, cout.value, bool(relu.value), int(device)
         self.dtype = WG_TF32
         self._h = h
+        self._read_geometry()
         return self
 
     @staticmethod
@@ -262,18 +284,19 @@ class Conv3x3BnRelu(_Layer):
     Replaces kernel_128()/kernel_256()'s three launches (Kernel128_winograd.cu:263-265)."""
     kind = 0
 
-    def __init__(self, w_kcrs, scale, shift, relu=True, device=0, dtype=WG_TF32):
+    def __init__(self, w_kcrs, scale, shift, relu=True, device=0, dtype=WG_TF32, hw=(14, 14)):
         """dtype = WG_TF32 (default; tolerance 1e-3) or WG_BF16 (bf16 V/U operands, fp32 I/O and accumulation;
-        tolerance 1e-2; needs C % 16 == 0 and K % 64 == 0)."""
+        tolerance 1e-2; needs C % 16 == 0 and K % 64 == 0). hw = (H, W) output map, default the reference's 14 x 14;
+        the input frame is [N, hf, wf, C] with hf = H + 2 (H + 3 for odd H), see include/winograd_b200.h."""
         k, c = w_kcrs.shape[0], w_kcrs.shape[1]
         assert tuple(w_kcrs.shape) == (k, c, 3, 3)
-        super().__init__(c, k, w_kcrs, scale, shift, relu, device, dtype)
+        super().__init__(c, k, w_kcrs, scale, shift, relu, device, dtype, hw)
 
     def in_shape(self):
-        return (16, 16, self.cin)
+        return (self.hf, self.wf, self.cin)
 
     def out_shape(self, out_padded=False):
-        return (16, 16, self.cout) if out_padded else (14, 14, self.cout)
+        return (self.hf, self.wf, self.cout) if out_padded else (self.h, self.w, self.cout)
 
 
 class Conv1x1Bn(_Layer):
@@ -282,18 +305,19 @@ class Conv1x1Bn(_Layer):
     Kernel256_one.cu:100,318)."""
     kind = 1
 
-    def __init__(self, w_cin_cout, scale, shift, relu, device=0, dtype=WG_TF32):
+    def __init__(self, w_cin_cout, scale, shift, relu, device=0, dtype=WG_TF32, hw=(14, 14)):
         """dtype = WG_TF32 (default; tolerance 1e-3) or WG_BF16 (bf16 operands: the activation stage is converted into
-        tensor memory by four extra warps, bf16 weight image; fp32 I/O and accumulation; tolerance 1e-2)."""
+        tensor memory by four extra warps, bf16 weight image; fp32 I/O and accumulation; tolerance 1e-2).
+        hw = (H, W) pixels per image (default 14 x 14 = the reference's 196)."""
         cin, cout = w_cin_cout.shape
-        super().__init__(cin, cout, w_cin_cout, scale, shift, relu, device, dtype)
+        super().__init__(cin, cout, w_cin_cout, scale, shift, relu, device, dtype, hw)
 
     def in_shape(self):
-        return (196, self.cin)
+        return (self.h * self.w, self.cin)
 
     def out_shape(self, out_padded=False):
         # out_padded: the zero-bordered frame a following 3x3 layer reads (chain mode)
-        return (16, 16, self.cout) if out_padded else (196, self.cout)
+        return (self.hf, self.wf, self.cout) if out_padded else (self.h * self.w, self.cout)
 
 
 class Bottleneck:
@@ -306,10 +330,11 @@ class Bottleneck:
     into the last 1x1 launch's epilogue (the reference's `_out` kernels stop right before it, Kernel128_one.cu:271-272,
     Kernel256_one.cu:273) -- still three launches."""
 
-    def __init__(self, w1, s1, b1, w3, s3, b3, w2, s2, b2, device=0, dtype=WG_TF32, residual=False):
-        self.l1 = Conv1x1Bn(w1, s1, b1, relu=True, device=device)
-        self.l3 = Conv3x3BnRelu(w3, s3, b3, relu=True, device=device, dtype=dtype)
-        self.l2 = Conv1x1Bn(w2, s2, b2, relu=False, device=device)
+    def __init__(self, w1, s1, b1, w3, s3, b3, w2, s2, b2, device=0, dtype=WG_TF32, residual=False, hw=(14, 14)):
+        self.l1 = Conv1x1Bn(w1, s1, b1, relu=True, device=device, hw=hw)
+        self.l3 = Conv3x3BnRelu(w3, s3, b3, relu=True, device=device, dtype=dtype, hw=hw)
+        self.l2 = Conv1x1Bn(w2, s2, b2, relu=False, device=device, hw=hw)
+        self.px = self.l1.h * self.l1.w
         assert self.l1.cout == self.l3.cin and self.l3.cout == self.l2.cin
         self.residual = bool(residual)
         assert not self.residual or self.l1.cin == self.l2.cout, "the identity shortcut needs Cin == Cout"
@@ -320,14 +345,14 @@ class Bottleneck:
         n = x.shape[0]
         key = (n, x.device.index)
         if key not in self._bufs:
-            self._bufs[key] = (torch.empty((n, 16, 16, self.l1.cout), device=x.device),
-                               torch.empty((n, 14, 14, self.l3.cout), device=x.device))
+            self._bufs[key] = (torch.empty((n,) + self.l1.out_shape(True), device=x.device),
+                               torch.empty((n,) + self.l3.out_shape(), device=x.device))
         frame, mid = self._bufs[key]
         self.l1(x, out=frame, out_padded=True)
         self.l3(frame, out=mid)
         if self.residual:
-            return self.l2(mid.view(n, 196, self.l3.cout), out=out, residual=x, relu_after_add=True)
-        return self.l2(mid.view(n, 196, self.l3.cout), out=out)
+            return self.l2(mid.view(n, self.px, self.l3.cout), out=out, residual=x, relu_after_add=True)
+        return self.l2(mid.view(n, self.px, self.l3.cout), out=out)
 
     def capture(self, x, out=None):
         """Record the three launches on `x` into a CUDA graph (the launches are plain stream work: no allocation, no
@@ -336,7 +361,7 @@ class Bottleneck:
         import torch
         n = x.shape[0]
         if out is None:
-            out = torch.empty((n, 196, self.l2.cout), device=x.device)
+            out = torch.empty((n, self.px, self.l2.cout), device=x.device)
         self(x, out=out)                      # warm-up: tensor maps cached, kernels configured, buffers allocated
         torch.cuda.synchronize(x.device)
         graph = torch.cuda.CUDAGraph()

@@ -19,6 +19,25 @@
 
 namespace wg {
 
+// Chain mode (out_padded): pixel m of the dense [N][H][W] map goes to (+1,+1) of the zero-bordered [N][Hf][Wf][Cout]
+// frame a following 3x3 layer reads (Kernel128_winograd.cu:163,243 layout for 14x14 / 16x16; odd map sizes have a
+// 2-wide bottom / right border, see ff::Geo); edge pixels also write their share of the border zeros.
+__device__ __forceinline__ void one_frame_store(float* __restrict__ y, long long m, const OneGeo& g, int Cout, int col,
+                                                float4 val) {
+  const int P = g.H * g.W;
+  const int n = (int)(m / P), p = (int)(m % P), oy = p / g.W, ox = p % g.W;
+  float* q = y + ((size_t)(n * g.Hf + oy + 1) * g.Wf + ox + 1) * Cout + col;
+  *reinterpret_cast<float4*>(q) = val;
+  const int dy0 = oy == 0 ? -1 : 0, dy1 = oy == g.H - 1 ? g.Hf - g.H - 1 : 0;
+  const int dx0 = ox == 0 ? -1 : 0, dx1 = ox == g.W - 1 ? g.Wf - g.W - 1 : 0;
+  if ((dy0 | dy1 | dx0 | dx1) == 0) return;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const ptrdiff_t rs = (ptrdiff_t)g.Wf * Cout;
+  for (int dy = dy0; dy <= dy1; ++dy)
+    for (int dx = dx0; dx <= dx1; ++dx)
+      if (dy | dx) *reinterpret_cast<float4*>(q + dy * rs + (ptrdiff_t)dx * Cout) = z4;
+}
+
 constexpr int kOneThreads = 32 * 6;
 constexpr int kBK = 32;  // fp32 channels per stage = one 128-byte swizzle row
 
@@ -74,7 +93,8 @@ __global__ void __launch_bounds__(H16 ? kOneThreads + 128 : kOneThreads, 1)
 conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                       const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ w_img,
                       const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y_padded,
-                      long long m_rows, int Cin, int Cout, int relu, int bn_packed, int relu_after, int dev_flags) {
+                      long long m_rows, int Cin, int Cout, int relu, int bn_packed, int relu_after, int dev_flags,
+                      const OneGeo geo) {
   using S = OneSmem<BN, WS, H16>;
   // dev_flags: always 0 in the product build. Developer build (WG_ONE_ABLATE): 1 no weight loads, 2 no activation loads,
   // 4 no output stores, 8 no MMAs -- results are garbage, only the time is of interest (profiles/one_ablation_r02.md).
@@ -374,22 +394,14 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           // pixel's 128 bytes, 4 pixels per instruction; edge pixels also write their share of the border zeros.
           __syncwarp();
           const int j = lane & 7, rsub = lane >> 3;
-          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int r = i8 * 4 + rsub;
             const long long m = (long long)mt * 128 + quad * 32 + r;
             if (m < m_rows) {
-              const int n = (int)(m / 196), p = (int)(m % 196), oy = p / 14, ox = p % 14;
               const float4 val =
                   ld_shared_v4(stage_u32 + (chunk & 1) * S::kStageOutBytes + r * 128 + ((j ^ (r & 7)) << 4));
-              float* g = y_padded + ((size_t)(n * 16 + oy + 1) * 16 + ox + 1) * Cout + nt * BN + c0 + j * 4;
-              *reinterpret_cast<float4*>(g) = val;
-              const ptrdiff_t dyb = oy == 0 ? -(ptrdiff_t)16 * Cout : (oy == 13 ? (ptrdiff_t)16 * Cout : 0);
-              const ptrdiff_t dxb = ox == 0 ? -(ptrdiff_t)Cout : (ox == 13 ? (ptrdiff_t)Cout : 0);
-              if (dyb != 0) *reinterpret_cast<float4*>(g + dyb) = z4;
-              if (dxb != 0) *reinterpret_cast<float4*>(g + dxb) = z4;
-              if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(g + dyb + dxb) = z4;
+              one_frame_store(y_padded, m, geo, Cout, nt * BN + c0 + j * 4, val);
             }
           }
           __syncwarp();  // staging buffer free again
@@ -451,7 +463,7 @@ __global__ void __launch_bounds__(kOneThreads, 1)
 conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ w_img,
                      const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
                      long long m_rows, int Cin, int Cout, int BN, int relu, int out_padded,
-                     const float* __restrict__ residual, int relu_after) {
+                     const float* __restrict__ residual, int relu_after, const OneGeo geo) {
   using S = SmallSmem;
   constexpr uint32_t kTmemCols = kNS;
   constexpr int RO = 128 / CS;  // rows of the tile each CTA finishes
@@ -617,15 +629,7 @@ conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __
       if (!out_padded) {
         *reinterpret_cast<float4*>(y + (size_t)m * Cout + col) = acc;
       } else {
-        const int n = (int)(m / 196), p = (int)(m % 196), oy = p / 14, ox = p % 14;
-        float* g = y + ((size_t)(n * 16 + oy + 1) * 16 + ox + 1) * Cout + col;
-        *reinterpret_cast<float4*>(g) = acc;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const ptrdiff_t dyb = oy == 0 ? -(ptrdiff_t)16 * Cout : (oy == 13 ? (ptrdiff_t)16 * Cout : 0);
-        const ptrdiff_t dxb = ox == 0 ? -(ptrdiff_t)Cout : (ox == 13 ? (ptrdiff_t)Cout : 0);
-        if (dyb != 0) *reinterpret_cast<float4*>(g + dyb) = z4;
-        if (dxb != 0) *reinterpret_cast<float4*>(g + dxb) = z4;
-        if (dyb != 0 && dxb != 0) *reinterpret_cast<float4*>(g + dyb + dxb) = z4;
+        one_frame_store(y, m, geo, Cout, col, acc);
       }
     }
   }
@@ -695,7 +699,8 @@ struct OneRes {  // residual operand of a launch (RES instantiations)
 template <int BN, int CL, bool WS = false, bool PAIR = false, bool RES = false, bool H16 = false>
 static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
                       const float* shift, float* y_padded, long long m_rows, int Cin, int Cout, int relu,
-                      int max_ctas, cudaStream_t stream, int bn_packed = BN, OneRes res = OneRes{nullptr, 0}) {
+                      int max_ctas, cudaStream_t stream, const OneGeo& geo, int bn_packed = BN,
+                      OneRes res = OneRes{nullptr, 0}) {
   using S = OneSmem<BN, WS, H16>;
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
@@ -734,7 +739,7 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL, WS, PAIR, RES, H16>, tmap, tmap_y,
                                      res.tmap_r ? *res.tmap_r : tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout,
-                                     relu, bn_packed, res.relu_after, one_dev_flags());
+                                     relu, bn_packed, res.relu_after, one_dev_flags(), geo);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
@@ -775,7 +780,7 @@ static int small_max_clusters() {
 template <int CS>
 static int launch_small(const CUtensorMap& tmap, const float* w_img, const float* scale, const float* shift, float* y,
                         int out_padded, long long m_rows, int Cin, int Cout, int BN, int relu, const float* residual,
-                        int relu_after, cudaStream_t stream) {
+                        int relu_after, const OneGeo& geo, cudaStream_t stream) {
   const long long n_items = ((m_rows + 127) / 128) * (Cout / kNS);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_items * CS));
@@ -799,7 +804,7 @@ static int launch_small(const CUtensorMap& tmap, const float* w_img, const float
   cfg.attrs = attr;
   cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_small_kernel<CS>, tmap, w_img, scale, shift, y, m_rows, Cin, Cout,
-                                     BN, relu, out_padded, residual, relu_after);
+                                     BN, relu, out_padded, residual, relu_after, geo);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
@@ -807,21 +812,22 @@ static int launch_small(const CUtensorMap& tmap, const float* w_img, const float
 static int one_bf16_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtensorMap& tmap_res,
                            const float* w_img, const float* scale, const float* shift, float* y_padded, long long m_rows,
                            int Cin, int Cout, int relu, const float* residual, int relu_after, int max_ctas,
-                           cudaStream_t stream) {
+                           const OneGeo& geo, cudaStream_t stream) {
   if (residual)
     return launch_one<128, 1, false, false, true, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout,
-                                                        relu, max_ctas, stream, 128, OneRes{&tmap_res, relu_after});
+                                                        relu, max_ctas, stream, geo, 128, OneRes{&tmap_res, relu_after});
   return launch_one<128, 1, false, false, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout,
-                                                       relu, max_ctas, stream, 128);
+                                                       relu, max_ctas, stream, geo, 128);
 }
 
 int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtensorMap& tmap_res, const float* w_img,
                const float* scale, const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout,
-               int BN, int bf16, int relu, const float* residual, int relu_after, int max_ctas, cudaStream_t stream) {
+               int BN, int bf16, int relu, const float* residual, int relu_after, int max_ctas, const OneGeo& geo,
+               cudaStream_t stream) {
   float* y_padded = out_padded ? y : nullptr;
-  if (bf16)  // bf16 operands: its own kernel (conv1x1_bf16_kernel), every batch size
+  if (bf16)  // bf16 operands: the H16 instantiation of the throughput kernel, every batch size
     return one_bf16_launch(tmap, tmap_y, tmap_res, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, residual,
-                           relu_after, max_ctas, stream);
+                           relu_after, max_ctas, geo, stream);
   {
     // latency mode: every (M-tile, 64-cout sub-tile) fits on the chip at once -> the small kernel, split-K factor CS
     // chosen by a two-term model in clocks (weight/activation ingest of Cin/CS channels at ~36 B/clk per SM, DSMEM reduction
@@ -852,7 +858,7 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtenso
       }
 #define WG_SMALL(CS_) \
   return launch_small<CS_>(tmap, w_img, scale, shift, y, out_padded, m_rows, Cin, Cout, BN, relu, residual, relu_after, \
-                           stream)
+                           geo, stream)
       if (best == 1) WG_SMALL(1);
       if (best == 2) WG_SMALL(2);
       if (best == 4) WG_SMALL(4);
@@ -892,26 +898,26 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtenso
     if (ws_env && use == 1 && bn_ws && max_ctas >= n_nt && n_mt >= 4 * (max_ctas / n_nt)) {
       if (bn_ws == 128 && residual)
         return launch_one<128, 1, true, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
-                                                     max_ctas, stream, BN, OneRes{&tmap_res, relu_after});
+                                                     max_ctas, stream, geo, BN, OneRes{&tmap_res, relu_after});
       if (bn_ws == 128)
         return launch_one<128, 1, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas,
-                                        stream, BN);
+                                        stream, geo, BN);
       if (residual)
         return launch_one<256, 1, true, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
-                                                     max_ctas, stream, BN, OneRes{&tmap_res, relu_after});
+                                                     max_ctas, stream, geo, BN, OneRes{&tmap_res, relu_after});
       return launch_one<256, 1, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas,
-                                      stream, BN);
+                                      stream, geo, BN);
     }
   }
   if (residual) {
     if (BN == 128)
       return launch_one<128, 1, false, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
-                                                    max_ctas, stream, 128, OneRes{&tmap_res, relu_after});
+                                                    max_ctas, stream, geo, 128, OneRes{&tmap_res, relu_after});
     return launch_one<256, 1, false, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
-                                                  max_ctas, stream, 256, OneRes{&tmap_res, relu_after});
+                                                  max_ctas, stream, geo, 256, OneRes{&tmap_res, relu_after});
   }
 #define WG_ONE(BN_, CL_) \
-  return launch_one<BN_, CL_>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas, stream)
+  return launch_one<BN_, CL_>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, max_ctas, stream, geo)
   // CTA pairs (tcgen05 cta_group::2, M = 256 over two consecutive M-tiles, each CTA holding half of the weight tile):
   // WG_ONE_PAIR=1; experiment, default off (see the kernel).
   static int pair = -1;
@@ -923,10 +929,10 @@ int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtenso
     if (pair && m_rows > 128 && max_ctas >= 2) {
       if (BN == 128)
         return launch_one<128, 2, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
-                                               max_ctas, stream);
+                                               max_ctas, stream, geo);
       if (BN == 256)
         return launch_one<256, 2, false, true>(tmap, tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu,
-                                               max_ctas, stream);
+                                               max_ctas, stream, geo);
     }
     if (BN == 128 && use == 2) WG_ONE(128, 2);
     if (BN == 128 && use == 4) WG_ONE(128, 4);

@@ -149,6 +149,9 @@ struct wg_layer {
   int tm16_ff = 0;  // 3x3 bf16/fp16: d_filter_tm16 is the full-fold kernel's image (96-wide slices)
   int ff_cg2 = 0;   // 3x3 full-fold kernel: CTA-pair variant (developer build)
   int num_sms = 0;
+  int H = 14, W = 14;      // output map (the reference: 14 x 14 everywhere)
+  ff::Geo geo{};           // 3x3: tiles / frame / raw-plane geometry of the full-fold kernel
+  OneGeo one_geo{14, 14, 16, 16};  // 1x1: pixels per image and the padded frame of chain mode
   // packed images (device). Sizes in bytes in img_bytes[], same order as the blob sections.
   float* d_filter = nullptr;           // packed filter image (U or swizzled W^T)
   float* d_filter_n64 = nullptr;       // 3x3 full-fold kernel: second image with all slices 64 wide, or null
@@ -162,6 +165,10 @@ struct wg_layer {
   // tensor-map caches
   std::mutex mu;
   TmapCache tm_x, tm_x16, tm_small, tm_y, tm_res;
+  size_t in_px() const { return kind == 0 ? (size_t)geo.Hf * geo.Wf : (size_t)H * W; }
+  size_t out_px(int padded) const {
+    return padded ? (kind == 0 ? (size_t)geo.Hf * geo.Wf : (size_t)one_geo.Hf * one_geo.Wf) : (size_t)H * W;
+  }
   // staging for wg_run_host
   float* d_x = nullptr;
   float* d_y = nullptr;
@@ -204,7 +211,8 @@ static void layer_plan(wg_layer* L) {
     const bool t16 = L->dtype != WG_TF32 && kn_tm(wino_kn());
     L->img_bytes[2] = t16 ? fe * 2 : 0;
     L->img_bytes[3] = (t16 && L->tm16_ff && !L->ff_cg2 && wino_ff_has_narrow(L->cout)) ? fe * 2 : 0;
-    L->img_bytes[4] = (L->dtype == WG_TF32 && L->tile_n != 32) ? fe * 4 : 0;  // tile_n == 32: aliases d_filter
+    // the small-batch kernel (and its plain KN=32 image) exists for the reference's 14x14 geometry only
+    L->img_bytes[4] = (L->dtype == WG_TF32 && L->tile_n != 32 && ff::geo_is_ref(L->geo)) ? fe * 4 : 0;  // tile_n == 32: aliases d_filter
   } else {
     L->tile_n = (L->cout % 256 == 0 && L->dtype == WG_TF32) ? 256 : 128;  // bf16 operands: 128-wide N-tiles
     L->img_bytes[0] = (size_t)L->cin * L->cout * (L->dtype == WG_TF32 ? 4 : 2);
@@ -279,7 +287,17 @@ static int layer_pack(wg_layer* L, const float* d_w) {
   return rc;
 }
 
-static int create_common(wg_layer_t** out, int kind, int cin, int cout, const float* w, size_t w_elems,
+static int layer_set_geometry(wg_layer* L, int H, int W) {
+  L->H = H, L->W = W;
+  ff::Geo g{};
+  const int rc = wino_ff_geo(H, W, &g);  // also defines the frame a 1x1 layer writes in chain mode
+  if (rc != WG_OK) return rc;
+  L->geo = g;
+  L->one_geo = OneGeo{H, W, g.Hf, g.Wf};
+  return WG_OK;
+}
+
+static int create_common(wg_layer_t** out, int kind, int cin, int cout, int H, int W, const float* w, size_t w_elems,
                          const float* scale, const float* shift, int relu, wg_dtype_t dtype, int device) {
   if (!out || !w || !scale || !shift) return WG_ERR_ARG;
   if (dtype != WG_TF32 && dtype != WG_BF16 && dtype != WG_FP16) return WG_ERR_ARG;
@@ -302,6 +320,10 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, const fl
   L->dtype = dtype;
   L->device = device;
   L->num_sms = num_sms;
+  if ((rc = layer_set_geometry(L, H, W)) != WG_OK) {
+    delete L;
+    return rc;
+  }
   layer_plan(L);
   float* d_w = nullptr;
   auto fail = [&](int code) {
@@ -417,7 +439,11 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
     return r;
   };
 
-  if (L->kind == 0 && L->d_filter_small != nullptr) {
+  const bool ref_geo = L->H == 14 && L->W == 14;
+  const long long px = (long long)L->H * L->W;  // 1x1: GEMM rows per image
+  // map sizes other than the reference's run the full-fold kernel only (developer build: not with a superseded generation)
+  if (L->kind == 0 && !ref_geo && !(L->dtype == WG_TF32 ? L->tile_n == 96 : L->tm16_ff != 0)) return WG_ERR_ARG;
+  if (L->kind == 0 && ref_geo && L->d_filter_small != nullptr) {
     // small batches: the latency variant (one 64-tile x 32-cout item per cluster, split-C), see wino_small_kernel.cu
     const int cs = wino_small_cs(N, L->cin, L->cout, max_ctas);
     if (cs > 0) {
@@ -431,16 +457,17 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
     }
   }
   if (L->kind == 0 && L->d_filter_tm16 != nullptr && !(out_flags & 2)) {
-    // bf16 / fp16 operands, throughput-sized batch (the split-C latency mode of the other kernel takes the small ones)
+    // bf16 / fp16 operands, throughput-sized batch (the split-C latency mode of the other kernel takes the small ones
+    // of the reference geometry; other map sizes always run the full-fold kernel)
     const long long items64 = (long long)((N * 49 + 63) / 64) * (L->cout / 64);
-    if (items64 * 4 > max_ctas) {
+    if (items64 * 4 > max_ctas || !ref_geo) {
       {
         std::lock_guard<std::mutex> lk(L->mu);
         rc = L->tm_x16.get(x, N, &tmap, [&](CUtensorMap* m) {
 #ifdef WG_DEV_BUILD
           if (!L->tm16_ff) return wino_tm_make_tmap(m, x, N, L->cin, 1);
 #endif
-          return wino_ff_make_tmap(m, x, N, L->cin);
+          return wino_ff_make_tmap(m, x, N, L->cin, L->geo);
         });
       }
       if (rc != WG_OK) return rc;
@@ -451,14 +478,14 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
                                        L->relu, out_flags, max_ctas, stream));
 #endif
       return launched(wino_ff_launch(tmap, x, L->d_filter_tm16, L->d_filter_tm16_n64, L->d_scale, L->d_shift, y, N,
-                                     L->cin, L->cout, op16, L->ff_cg2, L->relu, out_flags, max_ctas, stream));
+                                     L->cin, L->cout, op16, L->ff_cg2, L->relu, out_flags, max_ctas, L->geo, stream));
     }
   }
   {
     std::lock_guard<std::mutex> lk(L->mu);
     rc = L->tm_x.get(x, N, &tmap, [&](CUtensorMap* m) {
-      if (L->kind == 1) return one_make_tmap(m, x, (long long)N * 196, L->cin);
-      if (L->tile_n == 96) return wino_ff_make_tmap(m, x, N, L->cin);
+      if (L->kind == 1) return one_make_tmap(m, x, (long long)N * px, L->cin);
+      if (L->tile_n == 96) return wino_ff_make_tmap(m, x, N, L->cin, L->geo);
 #ifdef WG_DEV_BUILD
       if (L->tile_n == 48) return wino_tm_make_tmap(m, x, N, L->cin, wino_tm_cls(L->cout, L->tm_db));
 #endif
@@ -466,21 +493,21 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
     });
     if (rc == WG_OK && L->kind == 1)
       rc = L->tm_y.get(y, N, &tmap_y,
-                       [&](CUtensorMap* m) { return one_make_tmap_out(m, y, (long long)N * 196, L->cout); });
+                       [&](CUtensorMap* m) { return one_make_tmap_out(m, y, (long long)N * px, L->cout); });
     if (rc == WG_OK && L->kind == 1 && residual)
       rc = L->tm_res.get(residual, N, &tmap_res,
-                         [&](CUtensorMap* m) { return one_make_tmap_out(m, residual, (long long)N * 196, L->cout); });
+                         [&](CUtensorMap* m) { return one_make_tmap_out(m, residual, (long long)N * px, L->cout); });
   }
   if (rc != WG_OK) return rc;
   if (L->kind == 1) {
     if (!residual) tmap_res = tmap_y;
     return launched(one_launch(tmap, tmap_y, tmap_res, L->d_filter, L->d_scale, L->d_shift, y, out_padded,
-                               (long long)N * 196, L->cin, L->cout, L->tile_n, L->dtype != WG_TF32, L->relu, residual,
-                               (flags & WG_OUT_RELU_AFTER_ADD) ? 1 : 0, max_ctas, stream));
+                               (long long)N * px, L->cin, L->cout, L->tile_n, L->dtype != WG_TF32, L->relu, residual,
+                               (flags & WG_OUT_RELU_AFTER_ADD) ? 1 : 0, max_ctas, L->one_geo, stream));
   }
   if (L->tile_n == 96)
     return launched(wino_ff_launch(tmap, x, L->d_filter, L->d_filter_n64, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
-                                   0, L->ff_cg2, L->relu, out_flags, max_ctas, stream));
+                                   0, L->ff_cg2, L->relu, out_flags, max_ctas, L->geo, stream));
 #ifdef WG_DEV_BUILD
   if (L->tile_n == 48)
     return launched(wino_tm_launch(tmap, L->d_filter, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->tm_db, 0,
@@ -492,16 +519,44 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
 
 extern "C" {
 
+int wg_conv3x3_create_hw(wg_layer_t** out, int C, int K, int H, int W, const float* w_kcrs, const float* scale,
+                         const float* shift, int relu, wg_dtype_t dtype, int device) {
+  if (C <= 0 || K <= 0 || C % 8 != 0 || K % 32 != 0 || H < 3 || W < 3) return WG_ERR_ARG;
+  return create_common(out, 0, C, K, H, W, w_kcrs, (size_t)K * C * 9, scale, shift, relu, dtype, device);
+}
+
+int wg_conv1x1_create_hw(wg_layer_t** out, int Cin, int Cout, int H, int W, const float* w_cin_cout, const float* scale,
+                         const float* shift, int relu, wg_dtype_t dtype, int device) {
+  if (Cin <= 0 || Cout <= 0 || Cin % 32 != 0 || Cout % 128 != 0 || H < 3 || W < 3) return WG_ERR_ARG;
+  return create_common(out, 1, Cin, Cout, H, W, w_cin_cout, (size_t)Cin * Cout, scale, shift, relu, dtype, device);
+}
+
 int wg_conv3x3_create(wg_layer_t** out, int C, int K, const float* w_kcrs, const float* scale, const float* shift,
                       int relu, wg_dtype_t dtype, int device) {
-  if (C <= 0 || K <= 0 || C % 8 != 0 || K % 32 != 0) return WG_ERR_ARG;
-  return create_common(out, 0, C, K, w_kcrs, (size_t)K * C * 9, scale, shift, relu, dtype, device);
+  return wg_conv3x3_create_hw(out, C, K, 14, 14, w_kcrs, scale, shift, relu, dtype, device);
 }
 
 int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_cout, const float* scale,
                       const float* shift, int relu, wg_dtype_t dtype, int device) {
-  if (Cin <= 0 || Cout <= 0 || Cin % 32 != 0 || Cout % 128 != 0) return WG_ERR_ARG;
-  return create_common(out, 1, Cin, Cout, w_cin_cout, (size_t)Cin * Cout, scale, shift, relu, dtype, device);
+  return wg_conv1x1_create_hw(out, Cin, Cout, 14, 14, w_cin_cout, scale, shift, relu, dtype, device);
+}
+
+int wg_frame_dims(int H, int W, int* frame_h, int* frame_w) {
+  ff::Geo g{};
+  const int rc = wino_ff_geo(H, W, &g);
+  if (rc != WG_OK) return rc;
+  if (frame_h) *frame_h = g.Hf;
+  if (frame_w) *frame_w = g.Wf;
+  return WG_OK;
+}
+
+int wg_layer_geometry(const wg_layer_t* L, int* H, int* W, int* frame_h, int* frame_w) {
+  if (!L) return WG_ERR_ARG;
+  if (H) *H = L->H;
+  if (W) *W = L->W;
+  if (frame_h) *frame_h = L->geo.Hf;
+  if (frame_w) *frame_w = L->geo.Wf;
+  return WG_OK;
 }
 
 int wg_run(wg_layer_t* L, const float* x, float* y, int N, int out_flags, void* cuda_stream) {
@@ -521,8 +576,8 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
   if (!L || !x_host || !y_host || N <= 0 || (out_padded & ~1)) return WG_ERR_ARG;
   DeviceGuard guard;
   if (guard.enter(L->device) != WG_OK) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
-  const size_t in_px = L->kind == 0 ? 256 : 196;
-  const size_t out_px = out_padded ? 256 : 196;
+  const size_t in_px = L->in_px();
+  const size_t out_px = L->out_px(out_padded);
   const size_t xb = (size_t)N * in_px * L->cin * sizeof(float);
   const size_t yb = (size_t)N * out_px * L->cout * sizeof(float);
   if (L->d_x_bytes < xb) {
@@ -662,7 +717,7 @@ int wg_layer_serialize(const wg_layer_t* Lc, void* buf, size_t cap, size_t* need
   h.header_bytes = (uint32_t)sizeof(BlobHeader);
   h.kind = L->kind, h.cin = L->cin, h.cout = L->cout, h.relu = L->relu, h.dtype = L->dtype, h.tile_n = L->tile_n;
   h.tm_db = L->tm_db, h.tm16_ff = L->tm16_ff, h.ff_cg2 = L->ff_cg2, h.dev_build = kDev ? 1 : 0;
-  h.height = 14, h.width = 14;
+  h.height = L->H, h.width = L->W;
   h.w_elems = L->w_host.size();
   for (int i = 0; i < 5; ++i) h.img_bytes[i] = L->img_bytes[i];
   h.payload_bytes = payload;
@@ -681,7 +736,7 @@ int wg_layer_deserialize(wg_layer_t** out, const void* buf, size_t bytes, int de
   if (h.payload_bytes != bytes - sizeof(BlobHeader)) return WG_ERR_IO;
   const uint8_t* payload = static_cast<const uint8_t*>(buf) + sizeof(BlobHeader);
   if (fnv1a(payload, h.payload_bytes) != h.checksum) return WG_ERR_IO;
-  if (h.kind < 0 || h.kind > 1 || h.cin <= 0 || h.cout <= 0 || h.height != 14 || h.width != 14) return WG_ERR_IO;
+  if (h.kind < 0 || h.kind > 1 || h.cin <= 0 || h.cout <= 0 || h.height < 3 || h.width < 3) return WG_ERR_IO;
   const size_t w_expect = h.kind == 0 ? (size_t)h.cout * h.cin * 9 : (size_t)h.cin * h.cout;
   if (h.w_elems != w_expect) return WG_ERR_IO;
   size_t total = h.w_elems * 4 + (size_t)h.cout * 8;
@@ -701,6 +756,10 @@ int wg_layer_deserialize(wg_layer_t** out, const void* buf, size_t bytes, int de
   if (!L) return WG_ERR_NOMEM;
   L->kind = h.kind, L->cin = h.cin, L->cout = h.cout, L->relu = h.relu, L->dtype = h.dtype, L->device = device;
   L->num_sms = num_sms;
+  if (layer_set_geometry(L, h.height, h.width) != WG_OK) {
+    delete L;
+    return WG_ERR_IO;
+  }
   layer_plan(L);
   // The images are the shared-memory images of THIS build's kernels. A blob written by a build with other kernel
   // choices (developer knobs, an older version) still carries the raw weights: re-pack from those instead of failing.
@@ -708,7 +767,8 @@ int wg_layer_deserialize(wg_layer_t** out, const void* buf, size_t bytes, int de
   for (int i = 0; i < 5; ++i) same = same && L->img_bytes[i] == h.img_bytes[i];
   if (!same) {
     delete L;
-    return create_common(out, h.kind, h.cin, h.cout, w, h.w_elems, scale, shift, h.relu, (wg_dtype_t)h.dtype, device);
+    return create_common(out, h.kind, h.cin, h.cout, h.height, h.width, w, h.w_elems, scale, shift, h.relu,
+                         (wg_dtype_t)h.dtype, device);
   }
   auto fail = [&](int code) {
     wg_destroy(L);

@@ -20,6 +20,22 @@ constexpr bool kDev = false;
 inline const char* dev_env(const char*) { return nullptr; }
 #endif
 
+namespace ff {
+// Spatial geometry of a 3x3 layer (runtime; the reference hard-codes 14x14 maps in 16x16 frames,
+// Kernel128_winograd.cu:26-31,263-265). Output H x W, tiles of 2x2 outputs: TX x TY per image; input frame Hf x Wf =
+// 2*TY+2 x 2*TX+2 (= H+2 x W+2 for even sizes; odd sizes carry one extra, ignored row / column so that frame rows pair
+// up -- the raw tile is fetched as four (y parity, x parity) planes). Plane = [rp_box row pairs][SP slots][8 ch], slot =
+// x/2 + 1 (slot 0 = the zero-filled column x/2 = -1), SP = TX + 2. rp_box * SP <= 216 slots (kPlaneBytes).
+struct Geo {
+  int H, W, Hf, Wf, TX, TY, TT, SP, RPI;  // TT = TX*TY tiles per image, RPI = Hf/2 frame row pairs per image
+  int rp_box;                              // row pairs per TMA box (covers every M-block of up to mv_max tiles)
+  int mv_max;                              // largest M-block (tiles) whose raw rows fit one plane
+  uint32_t raw_bytes;                      // 4 * rp_box * SP * 32: bytes one raw stage delivers
+};
+__host__ __device__ inline bool geo_is_ref(const Geo& g) { return g.H == 14 && g.W == 14; }
+
+}  // namespace ff
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -54,14 +70,15 @@ int wino_tm_launch(const CUtensorMap& tmap, const float* u_img, const float* sca
 // throughput kernel with V in tensor memory and the whole inverse transform folded into the MMAs (wino_ff_kernel.cu):
 // 4 accumulators x 96-wide cout slices, its own filter image; same tensor map as the TM kernel (cls = 1)
 int wino_ff_p9();  // raw-tile layout of the full-fold kernel (1 = parity planes with a 9-slot pitch)
-int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C);
+int wino_ff_geo(int H, int W, ff::Geo* geo);  // WG_ERR_ARG when the map cannot be tiled (H, W < 3, or no M-block fits)
+int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C, const ff::Geo& geo);
 int wino_ff_cg2();  // 1 = CTA pairs (cta_group::2): filter image split in cout halves, clusters of 2
 int wino_ff_has_narrow(int K);  // 1 = the layer also gets a filter image with all slices 64 wide (one-wave launches)
 int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, int op16, int cg2, int narrow,
                                cudaStream_t stream);
 int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* u_img_narrow,
                    const float* scale, const float* shift, float* y, int n_img, int C, int K, int op16, int cg2, int relu,
-                   int out_padded, int max_ctas, cudaStream_t stream);
+                   int out_padded, int max_ctas, const ff::Geo& geo, cudaStream_t stream);
 
 // the same kernel with sixteen transform warps, one group of 8 per V half (wino_ffw_kernel.cu); same filter image / map
 int wino_ffw_launch(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
@@ -77,10 +94,15 @@ int wino_small_launch(const CUtensorMap& tmap_small, const float* u_plain, const
 // ---- 1x1 GEMM path (one_kernels.cu)
 int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);
 int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout);
+// spatial geometry of a 1x1 layer: H x W pixels per image; Hf x Wf = the padded frame written in chain mode
+struct OneGeo {
+  int H, W, Hf, Wf;
+};
 // tmap_res / residual / relu_after: fused residual add in the epilogue (null = none); bf16: bf16-operand kernel
 int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtensorMap& tmap_res, const float* w_img,
                const float* scale, const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout,
-               int BN, int bf16, int relu, const float* residual, int relu_after, int max_ctas, cudaStream_t stream);
+               int BN, int bf16, int relu, const float* residual, int relu_after, int max_ctas, const OneGeo& geo,
+               cudaStream_t stream);
 int weight_pack_launch(const float* w_cin_cout, float* w_img, int Cin, int Cout, int BN, int op16, cudaStream_t stream);
 
 }  // namespace wg

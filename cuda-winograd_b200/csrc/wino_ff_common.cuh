@@ -2,6 +2,7 @@
 // the cout-slice rule of the filter image, operand rounding and the MMA wrapper. Internal.
 #pragma once
 #include "ptx.cuh"
+#include "wg_internal.h"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -32,8 +33,8 @@ constexpr uint32_t kStgBytes = 128 * kStgRow;
 constexpr uint32_t kOffRaw = 0;
 constexpr uint32_t kOffU = kOffRaw + kRawStages * kRawStride;
 constexpr uint32_t kOffStg = kOffU + kUBufs * kUChunkMax;
-constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128])
-constexpr uint32_t kOffBar = kOffPix + 128 * 4;
+constexpr uint32_t kOffPix = kOffStg + kStgBytes;      // first output pixel of each tile row (int[128]) + in-map mask (int[128])
+constexpr uint32_t kOffBar = kOffPix + 2 * 128 * 4;
 constexpr uint32_t kNumBars = 2 * kRawStages + 8 + 2 + 4 + 2;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kTotal = kOffTmemPtr + 16;

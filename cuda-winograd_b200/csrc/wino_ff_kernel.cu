@@ -45,7 +45,7 @@ template <bool H16, bool DBG, bool P9, bool CG2>
 __global__ void __launch_bounds__(32 * (ff::kWorkerWarps + 2), 1)
 wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
-                  int C, int K, int relu, int out_padded, int mv, int fp16, int dbg) {
+                  int C, int K, int relu, int out_padded, int mv, int fp16, int dbg, const ff::Geo geo) {
   using namespace ff;
   const bool no_mma = DBG && (dbg & 1), no_xf = DBG && (dbg & 2), no_u = DBG && (dbg & 4), no_raw = DBG && (dbg & 8),
              no_out = DBG && (dbg & 16);
@@ -84,6 +84,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   const bool peer = CG2 && crank != 0;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
   int* pixtab = reinterpret_cast<int*>(smem + kOffPix);
+  int* masktab = pixtab + 128;  // per tile: bit 2a+b set = output pixel (a, b) of the tile lies inside the H x W map
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -113,7 +114,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 
   const int n_kb = C / (8 * kSub);  // V stages (8 or 16 channels each)
   const int n_sl = n_slices(K);
-  const int total_tiles = n_img * 49;
+  const int total_tiles = n_img * geo.TT;
   const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host
   // item = (M-block, cout slice), slices of an M-block adjacent; CG2: (pair of M-blocks, slice), one item per cluster
   const int n_items = (CG2 ? (n_mblocks + 1) / 2 : n_mblocks) * n_sl;
@@ -147,7 +148,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
         const int kn = sl.kn, c0 = sl.c0;
         const int mb = CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl;
         const int t0 = mb * mv;
-        const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+        const int ny0 = (t0 / geo.TT) * geo.Hf + 2 * ((t0 % geo.TT) / geo.TX);  // first frame row (n*Hf + y), even
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
         for (int kb = 0; kb < n_kb; ++kb) {
 #pragma unroll
@@ -156,7 +157,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             if (no_raw) {
               mbar_arrive(&raw_full[rs]);
             } else if constexpr (P9) {
-              mbar_arrive_expect_tx(&raw_full[rs], kRawBytesP9);
+              mbar_arrive_expect_tx(&raw_full[rs], geo.raw_bytes);
 #pragma unroll
               for (int q = 0; q < 4; ++q)  // plane q = (y parity q>>1, x parity q&1); x/2 starts at -1 (zero-filled)
                 tma_tensor_5d_g2s(smem + kOffRaw + rs * kRawStride + q * kPlaneBytes, &tmap_x, (kb * kSub + sb) * 8, -1,
@@ -298,28 +299,28 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       const int kn = sl.kn, c0s = sl.c0;
       const int mb = CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl;
       const int t0 = mb * mv;
-      const int ny0 = (t0 / 49) * 16 + 2 * ((t0 % 49) / 7);
+      const int ny0 = (t0 / geo.TT) * geo.Hf + 2 * ((t0 % geo.TT) / geo.TX);
       const int T = t0 + row;
       const int valid_rows = min(mv, total_tiles - t0);  // rows of this M-block that hold real tiles
       const bool tvalid = row < valid_rows;
       const bool warp_active = quad * 32 < valid_rows;  // warp-uniform
       const bool db = !CG2 && kn <= 64;                 // two V stages in TMEM (see the MMA thread)
       const uint32_t acc_stride = db ? 64u : kAccStride, v_col0 = db ? 256u : kVCol0;
-      const int n = T / 49, t = T % 49, ty = t / 7;
-      const int tx = P9 ? 6 - t % 7 : t % 7;  // P9: tiles run right-to-left inside a tile row (see kPlaneBytes)
-      const uint32_t raw_off = tvalid ? (uint32_t)((n * 16 + 2 * ty - ny0) * 512 + tx * 32) : 0u;
+      const int n = T / geo.TT, t = T % geo.TT, ty = t / geo.TX;
+      const int tx = P9 ? geo.TX - 1 - t % geo.TX : t % geo.TX;  // P9: tiles run right-to-left inside a tile row (see kPlaneBytes)
+      const uint32_t raw_off = tvalid ? (uint32_t)((n * 16 + 2 * ty - ny0) * 512 + tx * 32) : 0u;  // !P9: 14x14 only
       // SWIZZLE_32B: the 16-byte half of a pixel's 32 bytes is XORed with bit 2 of its x/2 index (address bit 7)
       const uint32_t h0 = (uint32_t)((cq ^ ((tx >> 2) & 1)) * 16);        // pixels with x/2 = tx
       const uint32_t h1 = (uint32_t)((cq ^ (((tx + 1) >> 2) & 1)) * 16);  // pixels with x/2 = tx + 1
       // P9: byte offset inside a plane of the pixel (dy/2, dx/2) of this tile's patch, swizzled half included
       uint32_t p9off[2][2];
       if constexpr (P9) {
-        const uint32_t s0 = tvalid ? (uint32_t)(((n * 16 + 2 * ty - ny0) >> 1) * 9 + tx + 1) : 1u;
+        const uint32_t s0 = tvalid ? (uint32_t)(((n * geo.Hf + 2 * ty - ny0) >> 1) * geo.SP + tx + 1) : 1u;
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
-            const uint32_t sl = s0 + 9 * a + b;
+            const uint32_t sl = s0 + (uint32_t)geo.SP * a + b;
             p9off[a][b] = sl * 32 + (uint32_t)((cq ^ ((sl >> 2) & 1)) * 16);
           }
       }
@@ -452,10 +453,16 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 
       // ---- epilogue: the accumulators ARE the output pixels; BN, ReLU, staged per (32 couts, output row a), full runs
       // per pixel. Warps (quad, cq = 0/1) own the same 32 tiles: they share staging rows 32*quad..+31 and barrier 1+quad.
-      const int W = out_padded ? 16 : 14;
+      const int W = out_padded ? geo.Wf : geo.W;   // row pitch / image height of the output (frame or dense map)
+      const int Hout = out_padded ? geo.Hf : geo.H;
       const int o = out_padded ? 1 : 0;
-      const int pix0 = tvalid ? ((n * W + 2 * ty + o) * W + 2 * tx + o) : -1;  // first output pixel of this tile
-      if (cq == 0) pixtab[row] = pix0;
+      const int pix0 = tvalid ? ((n * Hout + 2 * ty + o) * W + 2 * tx + o) : -1;  // first output pixel of this tile
+      if (cq == 0) {
+        pixtab[row] = pix0;
+        // odd H / W: the last tile row / column has one output row / column outside the map
+        const int ra = (2 * ty + 1 < geo.H) ? 0xC : 0, cb = (2 * tx + 1 < geo.W) ? 0xA : 0;  // bits 2a+b
+        masktab[row] = tvalid ? (0x1 | (cb & 0x2) | (ra & 0x4) | ((ra & cb) & 0x8)) : 0;
+      }
       const int n_chunks = kn / kEW;
       const int qrows = min(32, valid_rows - quad * 32);  // real tiles among this quad's rows (<= 0: none)
       const int tid64 = cq * 32 + lane;
@@ -510,21 +517,27 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                 const int tile = quad * 32 + (u >> 4);
                 const int b = (u >> 3) & 1;
                 const int ch = u & 7;
-                const float4 v = ld_shared_v4(stg_base + (uint32_t)tile * kStgRow + (uint32_t)(b * 128 + ch * 16));
+                float4 v = ld_shared_v4(stg_base + (uint32_t)tile * kStgRow + (uint32_t)(b * 128 + ch * 16));
+                if (!((masktab[tile] >> (2 * a + b)) & 1)) {
+                  // pixel outside an odd-sized map: not part of the dense output; zero in the padded frame (it lies
+                  // in the frame's extra border row / column)
+                  if (!out_padded) continue;
+                  v = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 if (!no_out) st_out_v4(ybase + (size_t)(pixtab[tile] + b) * K + ch * 4, v, mc);
               }
             }
             asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // staging rows free again
           }
         }
-        if (out_padded && tvalid && (ty == 0 || ty == 6 || tx == 0 || tx == 6)) {
+        if (out_padded && tvalid && (ty == 0 || ty == geo.TY - 1 || tx == 0 || tx == geo.TX - 1)) {
           // zero border of the reference's 16x16 frame (Kernel128_winograd.cu:163,243): edge tiles own their share
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
           const size_t rstride = (size_t)W * K;
           const int ncc = kn / 2;
           float* p = y + (size_t)pix0 * K + c0s + cq * ncc;
-          const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == 6 ? 2 * (ptrdiff_t)rstride : 0);
-          const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == 6 ? 2 * (ptrdiff_t)K : 0);
+          const ptrdiff_t dyb = ty == 0 ? -(ptrdiff_t)rstride : (ty == geo.TY - 1 ? 2 * (ptrdiff_t)rstride : 0);
+          const ptrdiff_t dxb = tx == 0 ? -(ptrdiff_t)K : (tx == geo.TX - 1 ? 2 * (ptrdiff_t)K : 0);
 #pragma unroll 1
           for (int e = 0; e < ncc; e += 4) {
             if (dyb != 0) {
@@ -651,17 +664,49 @@ int wino_ff_cg2() {
   return v && wino_ff_p9();
 }
 
-int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C) {
+// Geometry of an H x W layer: tiles, frame, plane pitch, and the largest M-block whose raw rows fit one parity plane
+// (brute force over the M-block's first tile; the schedule is periodic in the tiles of one image).
+int wino_ff_geo(int H, int W, ff::Geo* g) {
+  if (H < 3 || W < 3 || H > 4096 || W > 4096) return WG_ERR_ARG;
+  g->H = H, g->W = W;
+  g->TX = (W + 1) / 2, g->TY = (H + 1) / 2;
+  g->TT = g->TX * g->TY;
+  g->Hf = 2 * g->TY + 2, g->Wf = 2 * g->TX + 2;
+  g->SP = g->TX + 2;
+  g->RPI = g->Hf / 2;
+  g->mv_max = 0;
+  for (int mv : {128, 96, 64, 32}) {
+    int span = 0;
+    for (int t0 = 0; t0 < g->TT; ++t0) {
+      const int t1 = t0 + mv - 1;
+      const int rp0 = (t0 / g->TT) * g->RPI + (t0 % g->TT) / g->TX;
+      const int rp1 = (t1 / g->TT) * g->RPI + (t1 % g->TT) / g->TX;
+      if (rp1 - rp0 + 2 > span) span = rp1 - rp0 + 2;  // a tile row needs row pairs ty and ty + 1
+    }
+    if ((long long)span * g->SP * 32 <= (long long)ff::kPlaneBytes && span <= 256) {
+      g->mv_max = mv;
+      g->rp_box = span;
+      break;
+    }
+  }
+  if (g->mv_max == 0) return WG_ERR_ARG;
+  if (ff::geo_is_ref(*g)) g->rp_box = 24;  // the reference geometry keeps its round-1 box (24 row pairs x 9 slots = one full plane)
+  g->raw_bytes = 4u * (uint32_t)g->rp_box * (uint32_t)g->SP * 32u;
+  return WG_OK;
+}
+
+int wino_ff_make_tmap(CUtensorMap* tmap, const float* x, int n_img, int C, const ff::Geo& g) {
 #ifdef WG_DEV_BUILD
-  if (!wino_ff_p9()) return wino_tm_make_tmap(tmap, x, n_img, C, 1);
+  if (!wino_ff_p9()) return ff::geo_is_ref(g) ? wino_tm_make_tmap(tmap, x, n_img, C, 1) : WG_ERR_ARG;
 #endif
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return WG_ERR_DRIVER;
-  // x[N][16][16][C] viewed as (c, x/2, x&1, y&1, (n*16+y)/2); a box is one parity plane: 8 channels x 9 column pairs
-  // (starting at x/2 = -1) x 24 row pairs, 32-byte swizzle
-  cuuint64_t dims[5] = {(cuuint64_t)C, 8, 2, 2, (cuuint64_t)n_img * 8};
-  cuuint64_t strides[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)C * 4, (cuuint64_t)16 * C * 4, (cuuint64_t)32 * C * 4};
-  cuuint32_t box[5] = {8, 9, 1, 1, 24};
+  // x[N][Hf][Wf][C] viewed as (c, x/2, x&1, y&1, (n*Hf+y)/2); a box is one parity plane: 8 channels x SP column pairs
+  // (starting at x/2 = -1) x rp_box row pairs, 32-byte swizzle. (Reference geometry: 16x16 frames, 9 x 24.)
+  const cuuint64_t Wf = (cuuint64_t)g.Wf, Hf = (cuuint64_t)g.Hf;
+  cuuint64_t dims[5] = {(cuuint64_t)C, Wf / 2, 2, 2, (cuuint64_t)n_img * (Hf / 2)};
+  cuuint64_t strides[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)C * 4, Wf * C * 4, 2 * Wf * C * 4};
+  cuuint32_t box[5] = {8, (cuuint32_t)g.SP, 1, 1, (cuuint32_t)g.rp_box};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(x), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, wg::l2_promotion(),
@@ -681,20 +726,20 @@ int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, 
 // Tiles per M-block and grid size. The MMA is always M=128 but only `mv` rows carry tiles; transform warps own 32 rows
 // each, so the per-item cost scales with ceil(mv/32) quarters: pick the mv that minimises waves x cost (WG_WINO_MV pins
 // it). cg2: one item per CTA pair.
-static void ff_plan(int n_img, int K, int max_ctas, bool cg2, int* mv_out, int* grid_out) {
+static void ff_plan(int n_img, int K, int max_ctas, bool cg2, const ff::Geo& geo, int* mv_out, int* grid_out) {
   const int n_sl = ff::n_slices(K);
-  const int total_tiles = n_img * 49;
-  int mv = 128;
+  const int total_tiles = n_img * geo.TT;
+  int mv = geo.mv_max;
   static int mv_env = -1;
   if (mv_env < 0) {
     const char* e = dev_env("WG_WINO_MV");
     mv_env = e ? atoi(e) : 0;
   }
-  if (mv_env >= 16 && mv_env <= 128) {
+  if (mv_env >= 16 && mv_env <= geo.mv_max) {
     mv = mv_env;
   } else {
     double best = 1e30;
-    for (int cand = 128; cand >= 64; cand -= 32) {
+    for (int cand = geo.mv_max; cand >= 64 || cand == geo.mv_max; cand -= 32) {
       const long long items = (long long)((total_tiles + cand - 1) / cand) * n_sl;
       const long long slots = max_ctas > 0 ? max_ctas : 1;
       const long long waves = (items + slots - 1) / slots;
@@ -718,7 +763,7 @@ static void ff_plan(int n_img, int K, int max_ctas, bool cg2, int* mv_out, int* 
 template <bool H16, bool DBG, bool P9, bool CG2>
 static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                      int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream, int fp16,
-                     int dbg) {
+                     int dbg, const ff::Geo& geo) {
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
   cudaGetDevice(&dev_);
@@ -730,7 +775,7 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
     configured |= dev_bit_;
   }
   int mv = 128, grid = 1;
-  ff_plan(n_img, K, max_ctas, CG2, &mv, &grid);
+  ff_plan(n_img, K, max_ctas, CG2, geo, &mv, &grid);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(32 * (ff::kWorkerWarps + 2));
@@ -753,13 +798,13 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
   cfg.attrs = attr;
   cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ff_kernel<H16, DBG, P9, CG2>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
-                                     out_padded, mv, fp16, dbg);
+                                     out_padded, mv, fp16, dbg, geo);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* u_img_narrow,
                    const float* scale, const float* shift, float* y, int n_img, int C, int K, int op16, int cg2, int relu,
-                   int out_padded, int max_ctas, cudaStream_t stream) {
+                   int out_padded, int max_ctas, const ff::Geo& geo, cudaStream_t stream) {
   // (An L2 prefetch of the next item's raw rows, cp.async.bulk.prefetch.L2 spread over the stages of the current
   //  item, was measured: no gain -- the kernel is as fast with HBM-cold as with L2-resident input.)
   (void)x;
@@ -794,7 +839,10 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
     const char* n = dev_env("WG_FF_NARROW");
     narrow_env = n ? atoi(n) : 1;
   }
-  if (!cg2 && dbg == 0 && wino_ff_p9()) {
+  // (the 16-warp sibling and its split-C / narrow modes are built for the reference's 14x14 geometry only)
+  const bool ref_geo = ff::geo_is_ref(geo);
+  if (!ref_geo && (cg2 || !wino_ff_p9())) return WG_ERR_ARG;
+  if (ref_geo && !cg2 && dbg == 0 && wino_ff_p9()) {
     const int n_kb = C / (op16 ? 16 : 8);
     const int n_mb = (n_img * 49 + 127) / 128;
     // (same choice with and without WG_OUT_MULTICAST: the fused gather must reproduce kernel + all-gather bit for bit)
@@ -814,14 +862,14 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
                              items_n, stream);
   }
   const bool use_w16 = w16 == 1 || (w16 == 2 && op16 != 0 && C >= 256);
-  if (use_w16 && dbg == 0 && wino_ff_p9()) {
+  if (ref_geo && use_w16 && dbg == 0 && wino_ff_p9()) {
     int mv = 128, grid = 1;
-    ff_plan(n_img, K, max_ctas, cg2 != 0, &mv, &grid);
+    ff_plan(n_img, K, max_ctas, cg2 != 0, geo, &mv, &grid);
     return wino_ffw_launch(tmap, u_img, scale, shift, y, n_img, C, K, op16, cg2, 0, 0, relu, out_padded, mv, grid, stream);
   }
 #define WG_FF(H16_, DBG_, P9_, CG2_)                                                                                \
   return launch_ff<H16_, DBG_, P9_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, \
-                                          fp16, dbg)
+                                          fp16, dbg, geo)
   if constexpr (kDev) {
     // developer build only (tools/libwinograd_b200_dev.so): CTA pairs, the ablation instantiation (WG_FF_DEBUG, results
     // are garbage by design) and the single-box raw layout. None of these exist in the product library.

@@ -62,6 +62,25 @@ int wg_conv3x3_create(wg_layer_t** out, int C, int K, const float* w_kcrs, const
 int wg_conv1x1_create(wg_layer_t** out, int Cin, int Cout, const float* w_cin_cout, const float* scale,
                       const float* shift, int relu, wg_dtype_t dtype, int device);
 
+/* The same layers on other feature-map sizes (the reference hard-codes 14x14 outputs in 16x16 frames,
+ * Kernel128_winograd.cu:26-31,263-265; wg_conv3x3_create == wg_conv3x3_create_hw with H = W = 14). H x W is the OUTPUT
+ * map, 3 <= H, W and W <= 104 (e.g. the ResNet-50 stages 56x56x64, 28x28x128, 14x14x256, 7x7x512). Layouts:
+ *   3x3 input   x [N][Hf][Wf][C]   the frame INCLUDING its border, Hf = H + 2 and Wf = W + 2 for even sizes; an odd H (W)
+ *                                  has Hf = H + 3 (Wf = W + 3): one extra trailing row (column) that is never read into a
+ *                                  valid output, so that frame rows pair up (F(2x2,3x3) tiles cover 2x2 outputs). The data
+ *                                  sit at rows 1..H, columns 1..W; wg_layer_geometry() reports Hf, Wf.
+ *   3x3 output  y [N][H][W][K], or with WG_OUT_PADDED the [N][Hf][Wf][K] frame (zero border, result at (+1,+1))
+ *   1x1 input / output   [N][H*W][Cin] / [N][H*W][Cout]; WG_OUT_PADDED writes the [N][Hf][Wf][Cout] frame a following
+ *                        3x3 layer of the same map size reads.
+ * Stride-2 / downsampling layers are out of scope (no Winograd form). */
+int wg_conv3x3_create_hw(wg_layer_t** out, int C, int K, int H, int W, const float* w_kcrs, const float* scale,
+                         const float* shift, int relu, wg_dtype_t dtype, int device);
+int wg_conv1x1_create_hw(wg_layer_t** out, int Cin, int Cout, int H, int W, const float* w_cin_cout,
+                         const float* scale, const float* shift, int relu, wg_dtype_t dtype, int device);
+int wg_layer_geometry(const wg_layer_t* layer, int* H, int* W, int* frame_h, int* frame_w);
+/* Frame size of an H x W map (host only, no GPU needed); WG_ERR_ARG for maps the kernels cannot tile (H or W < 3). */
+int wg_frame_dims(int H, int W, int* frame_h, int* frame_w);
+
 /* The hot path: ONE kernel launch (conv + BN + optional ReLU) on `cuda_stream` (a cudaStream_t, may be NULL),
  * asynchronous. x and y are DEVICE pointers on the layer's device, 16-byte aligned.
  * Replaces the timed region of kernel_128()/kernel_256() (three launches, Kernel128_winograd.cu:263-265) and of

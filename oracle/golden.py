@@ -38,25 +38,34 @@ def fold_bn(gamma, beta, mean, var, eps=EPS):
 
 
 # ------------------------------------------------------------------------------------------------------ direct golden
-def conv3x3_raw(x, w, acc=np.float64):
-    """x [N,16,16,C] NHWC (border included), w [K,C,3,3] -> [N,14,14,K] valid cross-correlation, `acc` accumulation."""
+def frame_dims(h, w):
+    """Input frame of an H x W map (the f4 generalisation of the reference's fixed 14x14-in-16x16, Kernel128_winograd.cu:
+    26-31): one border pixel all round, plus one extra trailing row / column for odd sizes so that frame rows pair up
+    (F(2x2,3x3) tiles cover 2x2 outputs): Hf = 2*ceil(H/2) + 2."""
+    return 2 * ((h + 1) // 2) + 2, 2 * ((w + 1) // 2) + 2
+
+
+def conv3x3_raw(x, w, acc=np.float64, hw=None):
+    """x [N,Hf,Wf,C] NHWC (border included), w [K,C,3,3] -> [N,H,W,K] valid cross-correlation, `acc` accumulation.
+    hw = (H, W) output map; default: the frame minus its 1-pixel border (the reference: [N,16,16,C] -> [N,14,14,K])."""
     x = np.asarray(x)
     w = np.asarray(w)
-    n, h, wd, c = x.shape
+    n, hf, wf, c = x.shape
     k = w.shape[0]
-    assert w.shape == (k, c, 3, 3) and h == 16 and wd == 16
-    out = np.zeros((n, 14, 14, k), acc)
+    h, wd = hw if hw is not None else (hf - 2, wf - 2)
+    assert w.shape == (k, c, 3, 3) and (hf, wf) == frame_dims(h, wd), (x.shape, hw)
+    out = np.zeros((n, h, wd, k), acc)
     xa = x.astype(acc, copy=False)
     for r in range(3):
         for s in range(3):
-            patch = xa[:, r:r + 14, s:s + 14, :].reshape(n * 196, c)
-            out += (patch @ w[:, :, r, s].T.astype(acc)).reshape(n, 14, 14, k)
+            patch = xa[:, r:r + h, s:s + wd, :].reshape(n * h * wd, c)
+            out += (patch @ w[:, :, r, s].T.astype(acc)).reshape(n, h, wd, k)
     return out
 
 
-def conv3x3_bn_relu(x, w, scale, shift, relu=True, acc=np.float64):
-    """Golden for ./Test 0 and 1 (folded form). Returns float32 [N,14,14,K]."""
-    y = conv3x3_raw(x, w, acc) * np.asarray(scale, acc) + np.asarray(shift, acc)
+def conv3x3_bn_relu(x, w, scale, shift, relu=True, acc=np.float64, hw=None):
+    """Golden for ./Test 0 and 1 (folded form). Returns float32 [N,14,14,K] ([N,H,W,K] for other map sizes)."""
+    y = conv3x3_raw(x, w, acc, hw) * np.asarray(scale, acc) + np.asarray(shift, acc)
     if relu:
         y = np.maximum(y, 0)
     return y.astype(np.float32)
@@ -83,23 +92,26 @@ def conv1x1_bn(x, w, scale, shift, relu, acc=np.float64):
 
 
 def pad_frame(y):
-    """[N,14,14,K] -> the reference's zero-bordered [N,16,16,K] output frame (Kernel128_winograd.cu:163,243)."""
-    n, _, _, k = y.shape
-    out = np.zeros((n, 16, 16, k), y.dtype)
-    out[:, 1:15, 1:15, :] = y
+    """[N,14,14,K] -> the reference's zero-bordered [N,16,16,K] output frame (Kernel128_winograd.cu:163,243); for other
+    map sizes [N,H,W,K] -> [N,Hf,Wf,K] (frame_dims)."""
+    n, h, w, k = y.shape
+    hf, wf = frame_dims(h, w)
+    out = np.zeros((n, hf, wf, k), y.dtype)
+    out[:, 1:h + 1, 1:w + 1, :] = y
     return out
 
 
-def bottleneck_chain(x, w1, s1, b1, w3, s3, b3, w2, s2, b2):
+def bottleneck_chain(x, w1, s1, b1, w3, s3, b3, w2, s2, b2, hw=(14, 14)):
     """1x1 (+BN+ReLU) -> zero-pad 1 -> 3x3 (+BN+ReLU) -> 1x1 (+BN, no ReLU): the three reference layer kinds chained
     (Kernel128_one.cu:24-54 -> Kernel128_winograd.cu:28-213 -> Kernel128_one.cu:244-273). x [N,196,Cin] -> [N,196,Cout].
     Unlike the reference's stand-alone 3x3 test input (random border, data_generator.py:49-53) the frame between the
     layers has a ZERO border -- that is what the reference's own padded output frame provides (Kernel128_winograd.cu:243)."""
     n = x.shape[0]
+    h, w = hw
     a = conv1x1_bn(x, w1, s1, b1, True)
-    frame = pad_frame(a.reshape(n, 14, 14, -1))
-    m = conv3x3_bn_relu(frame, w3, s3, b3, True)
-    return conv1x1_bn(m.reshape(n, 196, -1), w2, s2, b2, False)
+    frame = pad_frame(a.reshape(n, h, w, -1))
+    m = conv3x3_bn_relu(frame, w3, s3, b3, True, hw=hw)
+    return conv1x1_bn(m.reshape(n, h * w, -1), w2, s2, b2, False)
 
 
 def conv1x1_bn_residual(x, w, scale, shift, relu, residual, relu_after_add, acc=np.float64):
@@ -116,14 +128,15 @@ def conv1x1_bn_residual(x, w, scale, shift, relu, residual, relu_after_add, acc=
     return y.astype(np.float32)
 
 
-def bottleneck_block(x, w1, s1, b1, w3, s3, b3, w2, s2, b2):
+def bottleneck_block(x, w1, s1, b1, w3, s3, b3, w2, s2, b2, hw=(14, 14)):
     """Full ResNet bottleneck block with the identity shortcut: relu(bottleneck_chain(x) + x); needs Cin == Cout
     (BASELINE.json configs[4]; the add + final ReLU are what the reference leaves out, see conv1x1_bn_residual)."""
     n = x.shape[0]
+    h, w = hw
     a = conv1x1_bn(x, w1, s1, b1, True)
-    frame = pad_frame(a.reshape(n, 14, 14, -1))
-    m = conv3x3_bn_relu(frame, w3, s3, b3, True)
-    return conv1x1_bn_residual(m.reshape(n, 196, -1), w2, s2, b2, False, x, True)
+    frame = pad_frame(a.reshape(n, h, w, -1))
+    m = conv3x3_bn_relu(frame, w3, s3, b3, True, hw=hw)
+    return conv1x1_bn_residual(m.reshape(n, h * w, -1), w2, s2, b2, False, x, True)
 
 
 # ------------------------------------------------------------------------------------------ brute force (tiny shapes)

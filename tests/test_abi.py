@@ -238,3 +238,14 @@ def test_blob_and_residual_calls_fail_loudly_without_gpu(built):
         have_gpu = False
     if not have_gpu:
         assert L.wg_measure_tensor_peak(0, 0, ctypes.byref(tf), None) == -6          # WG_ERR_NODEVICE
+
+
+def test_frame_dims_match_the_oracle(built):
+    """f4: frame of an H x W map = one border pixel all round, rows / columns rounded up to even (host-only logic)."""
+    import golden
+    for h, w in [(14, 14), (28, 28), (56, 56), (7, 7), (3, 3), (9, 13), (104, 80), (8, 5)]:
+        assert built.frame_dims(h, w) == golden.frame_dims(h, w)
+    assert built.frame_dims(14, 14) == (16, 16) and built.frame_dims(7, 7) == (10, 10)
+    for bad in ((2, 14), (14, 2), (112, 112)):     # too small to tile / wider than one raw-tile plane holds (W <= 104)
+        with pytest.raises(built.WinogradB200Error):
+            built.frame_dims(*bad)

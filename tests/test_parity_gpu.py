@@ -587,6 +587,57 @@ def test_layer_blob_round_trip(lib_loaded, torch_cuda, tmp_path, kind, dtype):
         lib_loaded._Layer.load(str(tmp_path / "missing.wgb"))
 
 
+# ------------------------------------------------------------------ f4: other feature-map sizes (ResNet-50 stages)
+@pytest.mark.parametrize("h,w,c,k,n", [(28, 28, 128, 128, 9), (56, 56, 64, 64, 3), (7, 7, 512, 512, 37), (7, 7, 64, 96, 1),
+                                        (9, 13, 32, 64, 5), (8, 5, 16, 32, 21), (28, 28, 64, 128, 64), (3, 3, 32, 32, 200),
+                                        (30, 6, 24, 160, 4)])
+def test_3x3_other_map_sizes(lib_loaded, torch_cuda, h, w, c, k, n):
+    """wg_conv3x3_create_hw: the fused 3x3 layer on other map sizes than the reference's hard-coded 14x14
+    (Kernel128_winograd.cu:26-31,263-265) -- even (28x28x128, 56x56x64) and odd (7x7x512: edge tiles masked) sizes, ragged
+    M-blocks, every operand type; whole tensor against the oracle, padded frame == dense result with an exactly zero
+    border (two rows / columns wide on the odd side)."""
+    torch = torch_cuda
+    hf, wf = golden.frame_dims(h, w)
+    rs = np.random.RandomState(h * 100 + w + c)
+    x = (rs.rand(n, hf, wf, c) - 0.5).astype(np.float32)          # border (and the extra row / column) is random data
+    wt = (rs.rand(k, c, 3, 3) - 0.5).astype(np.float32)
+    sc, sh = golden.fold_bn(rs.rand(k) - 0.5, rs.rand(k) - 0.5, rs.rand(k) - 0.5, rs.rand(k) * 3 + 5)
+    gold = golden.conv3x3_bn_relu(x, wt, sc, sh, True, hw=(h, w))
+    xd = torch.from_numpy(x).cuda()
+    for dt, tol in ((lib_loaded.WG_TF32, TOL_TF32), (lib_loaded.WG_BF16, TOL_BF16), (lib_loaded.WG_FP16, TOL_TF32)):
+        if dt != lib_loaded.WG_TF32 and (c % 16 or k % 64):
+            continue
+        layer = lib_loaded.Conv3x3BnRelu(wt, sc, sh, relu=True, dtype=dt, hw=(h, w))
+        assert layer.in_shape() == (hf, wf, c) and layer.out_shape() == (h, w, k)
+        y = layer(xd)
+        assert golden.rel_err(y.cpu().numpy(), gold) <= tol
+        yp = layer(xd, out=torch.full((n, hf, wf, k), float("nan"), device="cuda"), out_padded=True)
+        assert torch.equal(yp[:, 1:h + 1, 1:w + 1], y)
+        border = yp.clone()
+        border[:, 1:h + 1, 1:w + 1] = 0
+        assert float(border.abs().max()) == 0 and bool(torch.isfinite(yp).all())   # every frame element written
+        assert torch.equal(layer(xd), y)
+        layer.close()
+
+
+@pytest.mark.parametrize("h,w,ch,c,n", [(28, 28, 512, 128, 8), (7, 7, 2048, 512, 16), (56, 56, 256, 128, 2)])
+def test_bottleneck_block_other_stages(lib_loaded, torch_cuda, h, w, ch, c, n):
+    """The residual bottleneck block on the other ResNet-50 map sizes (conv3_x 28x28x512/128, conv5_x 7x7x2048/512, and a
+    56x56 map; conv2_x's own 64-wide bottleneck is below the 1x1 kernel's Cout % 128 == 0 granularity): 1x1 -> padded
+    frame -> 3x3 -> 1x1 + x, ReLU, three launches; whole tensor against the oracle."""
+    torch = torch_cuda
+    rs = np.random.RandomState(h + ch)
+    x = (rs.rand(n, h * w, ch) - 0.5).astype(np.float32)
+    w1 = ((rs.rand(ch, c) - 0.5) * 0.2).astype(np.float32)
+    w3 = ((rs.rand(c, c, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    w2 = ((rs.rand(c, ch) - 0.5) * 0.2).astype(np.float32)
+    bn = [((rs.rand(k) + 0.5).astype(np.float32), (rs.rand(k) - 0.3).astype(np.float32)) for k in (c, c, ch)]
+    block = lib_loaded.Bottleneck(w1, *bn[0], w3, *bn[1], w2, *bn[2], residual=True, hw=(h, w))
+    y = block(torch.from_numpy(x).cuda())
+    gold = golden.bottleneck_block(x, w1, *bn[0], w3, *bn[1], w2, *bn[2], hw=(h, w))
+    assert golden.rel_err(y.cpu().numpy(), gold) <= 3 * TOL_TF32
+
+
 def test_current_device_is_restored(lib_loaded, torch_cuda):
     """wg_* calls on a layer of another GPU must not change the calling thread's current device (needs >= 2 GPUs)."""
     torch = torch_cuda
