@@ -22,15 +22,21 @@ namespace wg {
 // Chain mode (out_padded): pixel m of the dense [N][H][W] map goes to (+1,+1) of the zero-bordered [N][Hf][Wf][Cout]
 // frame a following 3x3 layer reads (Kernel128_winograd.cu:163,243 layout for 14x14 / 16x16; odd map sizes have a
 // 2-wide bottom / right border, see ff::Geo); edge pixels also write their share of the border zeros.
-__device__ __forceinline__ void one_frame_store(float* __restrict__ y, long long m, const OneGeo& g, int Cout, int col,
-                                                float4 val) {
+// one_frame_index: frame pixel of dense pixel m and a border code (bit 0 top, bits 1-2 bottom rows, bit 3 left,
+// bits 4-5 right columns) -- the divisions are done once per (item, row), not per stored vector.
+__device__ __forceinline__ int2 one_frame_index(long long m, const OneGeo& g) {
   const int P = g.H * g.W;
-  const int n = (int)(m / P), p = (int)(m % P), oy = p / g.W, ox = p % g.W;
-  float* q = y + ((size_t)(n * g.Hf + oy + 1) * g.Wf + ox + 1) * Cout + col;
+  const int n = (int)(m / P), p = (int)(m - (long long)n * P), oy = p / g.W, ox = p - oy * g.W;
+  const int code = (oy == 0 ? 1 : 0) | ((oy == g.H - 1 ? g.Hf - g.H - 1 : 0) << 1) | (ox == 0 ? 8 : 0) |
+                   ((ox == g.W - 1 ? g.Wf - g.W - 1 : 0) << 4);
+  return make_int2((n * g.Hf + oy + 1) * g.Wf + ox + 1, code);
+}
+__device__ __forceinline__ void one_frame_store(float* __restrict__ y, int2 pc, const OneGeo& g, int Cout, int col,
+                                                float4 val) {
+  float* q = y + (size_t)pc.x * Cout + col;
   *reinterpret_cast<float4*>(q) = val;
-  const int dy0 = oy == 0 ? -1 : 0, dy1 = oy == g.H - 1 ? g.Hf - g.H - 1 : 0;
-  const int dx0 = ox == 0 ? -1 : 0, dx1 = ox == g.W - 1 ? g.Wf - g.W - 1 : 0;
-  if ((dy0 | dy1 | dx0 | dx1) == 0) return;
+  if (pc.y == 0) return;
+  const int dy0 = -(pc.y & 1), dy1 = (pc.y >> 1) & 3, dx0 = -((pc.y >> 3) & 1), dx1 = (pc.y >> 4) & 3;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const ptrdiff_t rs = (ptrdiff_t)g.Wf * Cout;
   for (int dy = dy0; dy <= dy1; ++dy)
@@ -58,7 +64,8 @@ struct OneSmem {
   // + [4 epilogue warps][2 buffers] "residual sub-tile landed" + H16: [stages] "A stage converted into TMEM"
   static constexpr uint32_t kNumBars = 2 * kStages + 5 + 8 + kStages;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
-  static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;  // + slack for manual 1024-B alignment
+  static constexpr uint32_t kOffFrame = kOffTmemPtr + 16;  // chain mode: int2 (frame pixel, border code) per tile row
+  static constexpr uint32_t kTotal = kOffFrame + 128 * 8 + 1024;  // + slack for manual 1024-B alignment
   static_assert(kOffOut % 1024 == 0, "swizzled staging must be 1024-byte aligned");
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
@@ -94,7 +101,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                       const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ w_img,
                       const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y_padded,
                       long long m_rows, int Cin, int Cout, int relu, int bn_packed, int relu_after, int dev_flags,
-                      const OneGeo geo) {
+                      const OneGeo geo, float* __restrict__ y_dbg) {
   using S = OneSmem<BN, WS, H16>;
   // dev_flags: always 0 in the product build. Developer build (WG_ONE_ABLATE): 1 no weight loads, 2 no activation loads,
   // 4 no output stores, 8 no MMAs -- results are garbage, only the time is of interest (profiles/one_ablation_r02.md).
@@ -230,11 +237,18 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       uint32_t st = 0, ph = 0;
       uint32_t it = 0;
       if constexpr (WS) mbar_wait(b_full, 0);
+      // developer build, dev_flags & 16 (with 4 = no output stores): CTA 0 dumps clock64() stamps of its first 16 items
+      // into y: long long y[8 * it + {0: MMA thread at item start, 1: accumulator buffer free, 2: last commit issued,
+      // 4: epilogue warp 2 sees acc_full, 5: its chunk loop done}]
+      long long* ts = reinterpret_cast<long long*>(y_dbg);
+      const bool ts_on = kDev && (abl & 16) && blockIdx.x == 0;
       for (int item = first_item; item < n_items; item += item_stride, ++it) {
         const uint32_t buf = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        if (ts_on && it < 16) ts[8 * it + 0] = clock64();
         mbar_wait(&acc_empty[buf], aph ^ 1);
         tc_fence_after();
+        if (ts_on && it < 16) ts[8 * it + 1] = clock64();
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full[st], ph);
           if constexpr (H16) mbar_wait(&a_ready[st], ph);  // the converter warps have written this stage's A into TMEM
@@ -266,6 +280,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         if constexpr (PAIR) umma_commit_mcast_cg2(&acc_full[buf], kClusterMask);
         else umma_commit(&acc_full[buf]);
+        if (ts_on && it < 16) ts[8 * it + 2] = clock64();
       }
     }
   } else if (H16 && warp >= 6) {
@@ -311,6 +326,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint32_t it = 0, chunk = 0;
     constexpr int kChunks = BN / 32;  // 32-cout sub-tiles per item
     uint64_t* rbar = res_full + quad * 2;
+    int2* frame_tab = reinterpret_cast<int2*>(smem + S::kOffFrame);
     // RES: request the residual sub-tile of (item, chunk index ci) into staging buffer `b`
     auto res_request = [&](int item, int ci, uint32_t b) {
       const int nt = WG_ITEM_NT(item);
@@ -331,8 +347,15 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const float* sc = scale + nt * BN;
       const float* sh = shift + nt * BN;
       const bool rows_here = (long long)mt * 128 + quad * 32 < m_rows;  // warp-uniform: this warp's 32 rows exist
+      if (y_padded != nullptr) {  // chain mode: where this warp's 32 rows go in the padded frame (read back after a warp sync)
+        const long long m = (long long)mt * 128 + quad * 32 + lane;
+        frame_tab[quad * 32 + lane] = m < m_rows ? one_frame_index(m, geo) : make_int2(-1, 0);
+        __syncwarp();
+      }
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
+      if (kDev && (abl & 16) && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 16)
+        reinterpret_cast<long long*>(y_dbg)[8 * it + 4] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32, ++chunk) {
@@ -397,11 +420,11 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int r = i8 * 4 + rsub;
-            const long long m = (long long)mt * 128 + quad * 32 + r;
-            if (m < m_rows) {
+            const int2 pc = frame_tab[quad * 32 + r];
+            if (pc.x >= 0) {
               const float4 val =
                   ld_shared_v4(stage_u32 + (chunk & 1) * S::kStageOutBytes + r * 128 + ((j ^ (r & 7)) << 4));
-              one_frame_store(y_padded, m, geo, Cout, nt * BN + c0 + j * 4, val);
+              one_frame_store(y_padded, pc, geo, Cout, nt * BN + c0 + j * 4, val);
             }
           }
           __syncwarp();  // staging buffer free again
@@ -420,6 +443,8 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (PAIR && crank != 0) mbar_arrive_remote_plain(&acc_empty[buf], 0);  // the leader issues the MMAs of both CTAs
         else mbar_arrive(&acc_empty[buf]);
       }
+      if (kDev && (abl & 16) && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 16)
+        reinterpret_cast<long long*>(y_dbg)[8 * it + 5] = clock64();
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -629,7 +654,7 @@ conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __
       if (!out_padded) {
         *reinterpret_cast<float4*>(y + (size_t)m * Cout + col) = acc;
       } else {
-        one_frame_store(y, m, geo, Cout, col, acc);
+        one_frame_store(y, one_frame_index(m, geo), geo, Cout, col, acc);
       }
     }
   }
@@ -691,6 +716,14 @@ static int one_dev_flags() {
   return v;
 }
 
+// developer build: buffer for the timeline stamps (WG_ONE_ABLATE & 16), set by tools/one_timeline.py through
+// wg_dev_set_dbg_ptr(); never dereferenced otherwise
+static float* g_one_dbg = nullptr;
+static float* one_dbg_ptr() { return g_one_dbg; }
+#ifdef WG_DEV_BUILD
+extern "C" void wg_dev_set_dbg_ptr(void* p) { g_one_dbg = static_cast<float*>(p); }
+#endif
+
 struct OneRes {  // residual operand of a launch (RES instantiations)
   const CUtensorMap* tmap_r;
   int relu_after;
@@ -739,7 +772,7 @@ static int launch_one(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const 
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_bn_act_kernel<BN, CL, WS, PAIR, RES, H16>, tmap, tmap_y,
                                      res.tmap_r ? *res.tmap_r : tmap_y, w_img, scale, shift, y_padded, m_rows, Cin, Cout,
-                                     relu, bn_packed, res.relu_after, one_dev_flags(), geo);
+                                     relu, bn_packed, res.relu_after, one_dev_flags(), geo, one_dbg_ptr());
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 

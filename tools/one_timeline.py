@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Item timeline of the 1x1 throughput kernel (developer build, WG_ONE_ABLATE includes 16): CTA 0's MMA thread and
+epilogue warp 2 stamp clock64() per item. usage: WG_B200_DEV_LIB=1 WG_ONE_ABLATE=<16|20|31> python tools/one_timeline.py cin cout"""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import numpy as np
+    import torch
+    import wg_loader
+    wg = wg_loader.load()
+    cin, cout = int(sys.argv[1]), int(sys.argv[2])
+    rs = np.random.RandomState(0)
+    layer = wg.Conv1x1Bn((rs.rand(cin, cout) - 0.5).astype(np.float32), np.ones(cout, np.float32),
+                         np.zeros(cout, np.float32), False)
+    n = 256
+    x = torch.rand((n, 196, cin), device="cuda") - 0.5
+    y = torch.empty((n, 196, cout), device="cuda")
+    dbg = torch.zeros(4096, dtype=torch.int64, device="cuda")
+    wg.lib().wg_dev_set_dbg_ptr(ctypes.c_void_p(dbg.data_ptr()))
+    for _ in range(3):
+        layer(x, out=y)
+    torch.cuda.synchronize()
+    t = dbg.cpu().numpy()[:128].reshape(16, 8)
+    t0 = t[0, 0]
+    print(f"== {cin}->{cout} WG_ONE_ABLATE={os.environ.get('WG_ONE_ABLATE')}: per item: MMA start | acc free | last commit || epi start | epi end")
+    for i in range(16):
+        if t[i, 0] == 0:
+            break
+        r = [int(v - t0) if v else -1 for v in t[i]]
+        print(f"  item {i:2d}: {r[0]:7d} {r[1]:7d} {r[2]:7d}   || {r[4]:7d} {r[5]:7d}   (mainloop {r[2]-r[1]:6d}, epilogue {r[5]-r[4]:6d})")
+
+
+if __name__ == "__main__":
+    main()
