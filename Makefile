@@ -1,6 +1,7 @@
 # Build of the B200-native drop-in for bssrdf/CUDA-Winograd's hot path.
 #   make            -> cuda-winograd_b200/libwinograd_b200.so  (C-ABI, include/*.h) and ./Test (the reference's CLI)
 #   make dev        -> tools/libwinograd_b200_dev.so (developer build: A/B knobs, ablation and superseded kernels)
+#   make examples   -> examples/shard_batch (plain-C multi-GPU example: one host thread per GPU over the C-ABI)
 #   make selftest   -> tools/selftest (developer check against an in-program FP64 convolution)
 # The reference's own Makefile passes no -arch (Makefile:14-17 there); tcgen05 needs the arch-specific target below.
 NVCC    ?= nvcc
@@ -42,12 +43,17 @@ Test: $(CSRC)/Test.c $(LIB)
 	$(NVCC) $(ARCH) -O2 -Iinclude -o $@ $(CSRC)/Test.c -Lcuda-winograd_b200 -lwinograd_b200 \
 	    -Xlinker -rpath -Xlinker '$$ORIGIN/cuda-winograd_b200'
 
+examples: examples/shard_batch
+examples/shard_batch: examples/shard_batch.c $(LIB)
+	$(NVCC) $(ARCH) -O2 -Iinclude -o $@ examples/shard_batch.c -Lcuda-winograd_b200 -lwinograd_b200 -lpthread \
+	    -Xlinker -rpath -Xlinker '$$ORIGIN/../cuda-winograd_b200'
+
 selftest: tools/selftest
 tools/selftest: tools/selftest.cu $(DEVLIB)
 	$(NVCC) $(NVFLAGS) -o $@ tools/selftest.cu -Ltools -lwinograd_b200_dev \
 	    -Xlinker -rpath -Xlinker '$$ORIGIN'
 
 clean:
-	rm -rf $(LIB) $(DEVLIB) Test tools/selftest $(OBJDIR)
+	rm -rf $(LIB) $(DEVLIB) Test tools/selftest examples/shard_batch $(OBJDIR)
 
-.PHONY: all clean selftest dev
+.PHONY: all clean selftest dev examples

@@ -255,7 +255,7 @@ def run_gpu(args):
                 xd_tmp.copy_(xh[0], non_blocking=True)
             with torch.cuda.stream(s_out):
                 yh.copy_(yd_tmp, non_blocking=True)
-        torch.cuda.synchronize(dev)
+        barrier()                                   # all ranks copy at the same time: the ceiling under contention
         reps = 5
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -268,13 +268,14 @@ def run_gpu(args):
         pcie = {"ms_per_step_copies_only": dt * 1e3, "images_per_s_ceiling": n / dt,
                 "h2d_gbs": n * 256 * C_IN * 4 / dt / 1e9, "d2h_gbs": n * 196 * C_OUT * 4 / dt / 1e9,
                 "how": "one 67 MB pinned H2D and one 51 MB pinned D2H copy per step, concurrently on two streams, "
-                       "no kernel: the ceiling of any host-buffer path on this box"}
+                       "no kernel, all ranks at the same time: the ceiling of any host-buffer path on this box"}
         del xd_tmp
     except Exception as e:  # noqa: BLE001
         pcie = {"unavailable": str(e)[:120]}
 
     # ---- optional: the one exchange step, an all-gather of the output shards (north_star), timed separately
     gather_ms = None
+    bare_gather_ms = None
     fused_ms, fused_note = None, None
     if dist is not None:
         out_all = torch.empty((world * n, 14, 14, C_OUT), device=dev)
@@ -289,6 +290,14 @@ def run_gpu(args):
         g1.record(stream)
         barrier()
         gather_ms = g0.elapsed_time(g1) / 5
+        # the exchange alone (no kernel): what NCCL's all-gather of the same 51 MB shards costs on this box's NVLink
+        barrier()
+        g0.record(stream)
+        for i in range(10):
+            dist.all_gather_into_tensor(out_all, ys[i % N_SETS])
+        g1.record(stream)
+        barrier()
+        bare_gather_ms = g0.elapsed_time(g1) / 10
         # the same exchange fused into the kernel: output stores go to an NVLS multicast address (multimem.st), the
         # switch replicates each shard into every GPU's copy of the gathered tensor; one cross-rank barrier per step
         try:
@@ -306,9 +315,10 @@ def run_gpu(args):
             fused_note = str(e)
 
     if dist is not None:
-        t = torch.tensor([ms, e2e_s, gather_ms or 0.0, fused_ms or 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, gather_ms or 0.0, fused_ms or 0.0, bare_gather_ms or 0.0], device=dev,
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, gmax, fmax = (float(v) for v in t.tolist())
+        ms, e2e_s, gmax, fmax, bare_gather_ms = (float(v) for v in t.tolist())
         gather_ms = gmax if gather_ms is not None else None
         fused_ms = fmax if fused_ms is not None else None
 
@@ -358,11 +368,19 @@ def run_gpu(args):
             "bottleneck_block": block,
         }
         if gather_ms is not None:
-            line["with_output_allgather"] = {"ms_per_step": gather_ms, "value": world * n / (gather_ms * 1e-3),
-                                             "unit": UNIT, "collective": "nccl all_gather_into_tensor of fp32 output"}
+            shard_mb = n * 196 * C_OUT * 4 / 1e6
+            line["with_output_allgather"] = {
+                "ms_per_step": gather_ms, "value": world * n / (gather_ms * 1e-3), "unit": UNIT,
+                "collective": "nccl all_gather_into_tensor of fp32 output",
+                "nvlink_ceiling": {"bare_allgather_ms": bare_gather_ms,
+                                   "ingress_gbs_per_gpu": (world - 1) * shard_mb / bare_gather_ms,
+                                   "how": f"the same all-gather alone, no kernel: each GPU receives {world - 1} x "
+                                          f"{shard_mb:.0f} MB per step; kernel + gather cannot beat max(kernel, this)"},
+                "frac_of_ceiling": max(bare_gather_ms, ms / args.steps) / gather_ms}
             if fused_ms is not None:
                 line["with_output_allgather"]["fused_multicast"] = {
                     "ms_per_step": fused_ms, "value": world * n / (fused_ms * 1e-3), "unit": UNIT,
+                    "frac_of_ceiling": max(bare_gather_ms, ms / args.steps) / fused_ms,
                     "how": "same kernel, output stores as multimem.st to an NVLS multicast address (WG_OUT_MULTICAST) "
                            "+ one symmetric-memory barrier per step; no NCCL call"}
             elif fused_note:

@@ -9,7 +9,9 @@
 extern "C" {
 #endif
 
-/* malloc + fread of `size` float32 values; prints "Bad file path" and exit(0) if the file is missing (util.c:28-44). */
+/* malloc + fread of `size` float32 values; prints "Bad file path" and exit(0) if the file is missing (util.c:28-44).
+ * A file shorter than `size` values is not an error here either (the reference ignores fread's return value and leaves
+ * the tail uninitialised): the missing tail reads as zeros. No status code crosses this interface. */
 float* get_parameter(const char* filename, int size);
 /* [w][h] -> [h][w]; frees its argument (util.c:15-26). */
 float* transpose(float* weight, int h, int w);

@@ -638,6 +638,16 @@ def test_bottleneck_block_other_stages(lib_loaded, torch_cuda, h, w, ch, c, n):
     assert golden.rel_err(y.cpu().numpy(), gold) <= 3 * TOL_TF32
 
 
+def test_c_example_shards_the_batch_over_all_gpus(lib_loaded):
+    """examples/shard_batch.c: the multi-GPU path from plain C -- one host thread per GPU over the C-ABI (device ordinal
+    per layer), contiguous image shards, wg_run_host per shard; exit code 0 = sharded result == single-GPU result."""
+    exe = os.path.join(ROOT, "examples", "shard_batch")
+    assert os.path.exists(exe), "examples/shard_batch must be prebuilt (make examples / __graft_entry__.build())"
+    r = subprocess.run([exe, "96", "64"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "images/s" in r.stdout and "max |diff|" in r.stdout
+
+
 def test_current_device_is_restored(lib_loaded, torch_cuda):
     """wg_* calls on a layer of another GPU must not change the calling thread's current device (needs >= 2 GPUs)."""
     torch = torch_cuda
