@@ -41,12 +41,23 @@ namespace wg {
 // peer's transform warps arrive on the LEADER's full[] barriers (mbarrier.arrive.release.cluster), the peer's otherwise
 // idle MMA warp relays "my half of the filter chunk has landed", the leader's tcgen05.commit multicasts done[] /
 // acc_full to both CTAs.
-template <bool H16, bool DBG, bool P9, bool CG2>
+// ALT (all cout slices <= 64 wide, i.e. two V stages in TMEM; parity-plane raw layout; no CTA pairs): the eight transform
+// warps work as TWO GROUPS OF FOUR ON ALTERNATE V STAGES -- group w>>2 owns the stages with that parity and transforms
+// both 4-channel halves of its stage one after the other. A transform warp's stage is a chain of fixed latencies (wait
+// for the raw tile, 16 LDS.128, column / row pass, wait for the V buffer, 16 tcgen05.st, tcgen05.wait::st, arrive) of
+// ~1.9 k clk against ~1.3 k clk of MMAs per stage (N = 64); with the groups half a period apart one group's loads run
+// under the other's stores and hand-offs, and every fixed cost is paid once per TWO stages.
+// GEN: runtime map geometry (wg_conv3x3_create_hw). The reference's 14x14 / 16x16 geometry is compiled in (!GEN): tile
+// and pixel indices then divide by constants and the edge-tile masks vanish (measured: 46.3 vs 49.4 us at 128->128).
+template <bool H16, bool DBG, bool P9, bool CG2, bool ALT = false, bool GEN = false>
 __global__ void __launch_bounds__(32 * (ff::kWorkerWarps + 2), 1)
 wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ u_img,
                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y, int n_img,
-                  int C, int K, int relu, int out_padded, int mv, int fp16, int dbg, const ff::Geo geo) {
+                  int C, int K, int relu, int out_padded, int mv, int fp16, int dbg, const ff::Geo geo_arg, int narrow) {
   using namespace ff;
+  const Geo geo = GEN ? geo_arg : Geo{14, 14, 16, 16, 7, 7, 49, 9, 8, 24, 128, kRawBytesP9};
+  static_assert(!ALT || (P9 && !CG2), "alternating transform groups: parity planes, single CTAs");
+  constexpr int kGroupWarps = ALT ? kWorkerWarps / 2 : kWorkerWarps;  // transform warps that share a V stage
   const bool no_mma = DBG && (dbg & 1), no_xf = DBG && (dbg & 2), no_u = DBG && (dbg & 4), no_raw = DBG && (dbg & 8),
              no_out = DBG && (dbg & 16);
   // dbg & 32 (with 16): CTA 0 records clock64() at the hand-off points of stages 8..15 of its first item and dumps
@@ -90,11 +101,11 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     tma_prefetch_desc(&tmap_x);
     for (int i = 0; i < kRawStages; ++i) {
       mbar_init(&raw_full[i], 1);
-      mbar_init(&raw_empty[i], kWorkerWarps);
+      mbar_init(&raw_empty[i], kGroupWarps);
     }
     for (int i = 0; i < 4; ++i) {
       // CG2 (leader): both CTAs' transform warps + own TMA bytes + the peer's relay
-      mbar_init(&full[i], CG2 ? 2 * kWorkerWarps + 2 : kWorkerWarps + 1);
+      mbar_init(&full[i], CG2 ? 2 * kWorkerWarps + 2 : kGroupWarps + 1);
       mbar_init(&done[i], 1);
       mbar_init(&u_land[i], 1);
     }
@@ -113,7 +124,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_kb = C / (8 * kSub);  // V stages (8 or 16 channels each)
-  const int n_sl = n_slices(K);
+  const int n_sl = n_slices(K, narrow);
   const int total_tiles = n_img * geo.TT;
   const int n_mblocks = (total_tiles + mv - 1) / mv;  // mv = tiles per M-block (<= 128), chosen by the host
   // item = (M-block, cout slice), slices of an M-block adjacent; CG2: (pair of M-blocks, slice), one item per cluster
@@ -129,7 +140,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       if (item0 < n_items) {
         // the filter does not depend on the previous kernel in the stream: request the first stage's U chunks before
         // waiting for that kernel (programmatic dependent launch), the activations after
-        const Slice sl = slice(K, item0 % n_sl);
+        const Slice sl = slice(K, item0 % n_sl, narrow);
         const int kn = sl.kn, c0 = sl.c0;
         const uint8_t* u_src = reinterpret_cast<const uint8_t*>(u_img) + (size_t)n_kb * 512 * c0;
         for (int h = 0; h < 2; ++h) {
@@ -144,7 +155,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       pdl_wait();
       if (DBG && (dbg & 64)) ts_g[13] = (long long)globaltimer_ns();
       for (int item = item0; item < n_items; item += item_step) {
-        const Slice sl = slice(K, item % n_sl);
+        const Slice sl = slice(K, item % n_sl, narrow);
         const int kn = sl.kn, c0 = sl.c0;
         const int mb = CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl;
         const int t0 = mb * mv;
@@ -207,7 +218,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
       // (Probing the next half's barrier with mbarrier.test_wait while 6 of the 18 MMAs were still to be issued, so
       //  that the ~90 clk of an already-complete try_wait stay off the issue path, was measured: no gain.)
       for (int item = item0; item < n_items; item += item_step) {
-        const uint32_t kn = (uint32_t)slice(K, item % n_sl).kn;
+        const uint32_t kn = (uint32_t)slice(K, item % n_sl, narrow).kn;
         const uint32_t fmt = H16 ? (fp16 ? kFmtF16 : kFmtBF16) : kFmtTF32;
         const uint32_t idesc_pos = make_idesc(fmt, CG2 ? 256 : 128, kn);
         const uint32_t idesc_neg = make_idesc(fmt, CG2 ? 256 : 128, kn, 1);  // D += (-A) * B
@@ -295,7 +306,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     int item_idx = 0;
     for (int item = item0; item < n_items; item += item_step, ++item_idx) {
       if (DBG && ts_item && item_idx < 4) ts_i[4 * item_idx] = clock64(), ts_i[4 * item_idx + 3] = item;
-      const Slice sl = slice(K, item % n_sl);
+      const Slice sl = slice(K, item % n_sl, narrow);
       const int kn = sl.kn, c0s = sl.c0;
       const int mb = CG2 ? (item / n_sl) * 2 + (int)crank : item / n_sl;
       const int t0 = mb * mv;
@@ -325,6 +336,100 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
           }
       }
 
+      if constexpr (ALT) {
+        // ---- alternating groups: group `cq` (= warp >> 2) owns the V stages g with (g & 1) == cq, both channel halves
+        for (int kb = 0; kb < n_kb; ++kb) {
+          if ((int)(g & 1) != cq) {  // the other group's stage: only keep the ring position in step
+#pragma unroll
+            for (int sb = 0; sb < kSub; ++sb)
+              if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+            ++g;
+            continue;
+          }
+          const uint32_t slot = (g & 1) * 2, pph = ((g - 2u) >> 1) & 1;
+          const bool wait_v = kb >= 2;  // the MMAs of stage g - 2 (this group's previous stage) read this V buffer
+#pragma unroll
+          for (int sb = 0; sb < kSub; ++sb) {
+            mbar_wait(&raw_full[rs], rph);
+            if (warp_active) {
+#pragma unroll
+              for (int ch = 0; ch < 2; ++ch) {  // the two 4-channel halves of the 8-channel raw stage, one after the other
+                f2_t d[4][4][2];
+                if (tvalid) {
+                  const uint32_t a = raw_base + rs * kRawStride;
+#pragma unroll
+                  for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 4; ++dx) {
+                      // p9off holds the address for channel half cq; the other half is the other 16 bytes of the slot
+                      const uint32_t off = p9off[dy >> 1][dx >> 1] ^ (ch != cq ? 16u : 0u);
+                      ld_shared_f2x2(a + ((dy & 1) * 2 + (dx & 1)) * kPlaneBytes + off, d[dy][dx][0], d[dy][dx][1]);
+                    }
+                } else {
+#pragma unroll
+                  for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 4; ++dx) d[dy][dx][0] = d[dy][dx][1] = 0ull;
+                }
+#pragma unroll
+                for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+                  for (int c = 0; c < 2; ++c) {
+                    const f2_t d0 = d[0][dx][c], d1 = d[1][dx][c], d2 = d[2][dx][c], d3 = d[3][dx][c];
+                    d[0][dx][c] = f2_sub(d0, d2);
+                    d[1][dx][c] = f2_add(d1, d2);
+                    d[2][dx][c] = f2_sub(d2, d1);
+                    d[3][dx][c] = f2_sub(d1, d3);
+                  }
+                if (ch == 1) {  // both halves of the raw stage are in registers / consumed: hand it back
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&raw_empty[rs]);
+                }
+                if (sb == 0 && ch == 0) {
+                  if (wait_v) wait_done(&done[slot + 1], pph);  // later commit of stage g - 2: the whole V buffer is free
+                  tc_fence_after();
+                }
+                const uint32_t vcol = tmem_base + lane_base + 256u + (g & 1) * 128 + (uint32_t)(H16 ? sb * 4 + ch * 2 : ch * 4);
+#pragma unroll
+                for (int jh = 0; jh < 2; ++jh)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    f2_t v0[2], v1[2];  // points (i, 2jh) and (i, 2jh+1)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                      const f2_t a0 = d[i][0][c], a1 = d[i][1][c], a2 = d[i][2][c], a3 = d[i][3][c];
+                      v0[c] = jh == 0 ? f2_sub(a0, a2) : f2_sub(a2, a1);
+                      v1[c] = jh == 0 ? f2_add(a1, a2) : f2_sub(a1, a3);
+                      if constexpr (!H16) v0[c] = f2_tf32(v0[c]), v1[c] = f2_tf32(v1[c]);
+                    }
+                    const uint32_t dst = vcol + jh * 64 + (i * 2) * 8;
+                    if constexpr (H16) {
+                      tmem_st_x2(dst, ff_pack16(f2_lo(v0[0]), f2_hi(v0[0]), fp16), ff_pack16(f2_lo(v0[1]), f2_hi(v0[1]), fp16));
+                      tmem_st_x2(dst + 8, ff_pack16(f2_lo(v1[0]), f2_hi(v1[0]), fp16),
+                                 ff_pack16(f2_lo(v1[1]), f2_hi(v1[1]), fp16));
+                    } else {
+                      tmem_st_x4(dst, f2_lo(v0[0]), f2_hi(v0[0]), f2_lo(v0[1]), f2_hi(v0[1]));
+                      tmem_st_x4(dst + 8, f2_lo(v1[0]), f2_hi(v1[0]), f2_lo(v1[1]), f2_hi(v1[1]));
+                    }
+                  }
+              }
+            } else {  // no tile in this warp's 32 rows: only the hand-offs
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&raw_empty[rs]);
+              if (sb == 0 && wait_v) wait_done(&done[slot + 1], pph);
+            }
+            if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&full[slot]);
+            mbar_arrive(&full[slot + 1]);
+          }
+          ++g;
+        }
+      } else
       for (int kb = 0; kb < n_kb; ++kb) {
         // this stage's ring slots are slot, slot + 1; the previous stage's (whose MMAs must have completed before a V
         // half is overwritten) pslot, pslot + 1, completing for the ((g - 1) >> 1)-th time
@@ -518,7 +623,7 @@ wino3x3_ff_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                 const int b = (u >> 3) & 1;
                 const int ch = u & 7;
                 float4 v = ld_shared_v4(stg_base + (uint32_t)tile * kStgRow + (uint32_t)(b * 128 + ch * 16));
-                if (!((masktab[tile] >> (2 * a + b)) & 1)) {
+                if (GEN && !((masktab[tile] >> (2 * a + b)) & 1)) {
                   // pixel outside an odd-sized map: not part of the dense output; zero in the padded frame (it lies
                   // in the frame's extra border row / column)
                   if (!out_padded) continue;
@@ -726,8 +831,9 @@ int filter_transform_ff_launch(const float* w_kcrs, float* u_img, int C, int K, 
 // Tiles per M-block and grid size. The MMA is always M=128 but only `mv` rows carry tiles; transform warps own 32 rows
 // each, so the per-item cost scales with ceil(mv/32) quarters: pick the mv that minimises waves x cost (WG_WINO_MV pins
 // it). cg2: one item per CTA pair.
-static void ff_plan(int n_img, int K, int max_ctas, bool cg2, const ff::Geo& geo, int* mv_out, int* grid_out) {
-  const int n_sl = ff::n_slices(K);
+static void ff_plan(int n_img, int K, int max_ctas, bool cg2, const ff::Geo& geo, int* mv_out, int* grid_out,
+                    int narrow = 0) {
+  const int n_sl = ff::n_slices(K, narrow);
   const int total_tiles = n_img * geo.TT;
   int mv = geo.mv_max;
   static int mv_env = -1;
@@ -760,22 +866,22 @@ static void ff_plan(int n_img, int K, int max_ctas, bool cg2, const ff::Geo& geo
   *grid_out = grid;
 }
 
-template <bool H16, bool DBG, bool P9, bool CG2>
+template <bool H16, bool DBG, bool P9, bool CG2, bool ALT = false, bool GEN = false>
 static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* scale, const float* shift, float* y,
                      int n_img, int C, int K, int relu, int out_padded, int max_ctas, cudaStream_t stream, int fp16,
-                     int dbg, const ff::Geo& geo) {
+                     int dbg, const ff::Geo& geo, int narrow = 0) {
   static unsigned long long configured = 0;  // per device: the attribute is a property of the function on ONE device
   int dev_ = 0;
   cudaGetDevice(&dev_);
   const unsigned long long dev_bit_ = 1ull << (dev_ & 63);
   if (!(configured & dev_bit_)) {
-    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16, DBG, P9, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::kTotal) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(wino3x3_ff_kernel<H16, DBG, P9, CG2, ALT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)ff::kTotal) != cudaSuccess)
       return WG_ERR_CUDA;
     configured |= dev_bit_;
   }
   int mv = 128, grid = 1;
-  ff_plan(n_img, K, max_ctas, CG2, geo, &mv, &grid);
+  ff_plan(n_img, K, max_ctas, CG2, geo, &mv, &grid, narrow);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(32 * (ff::kWorkerWarps + 2));
@@ -797,10 +903,12 @@ static int launch_ff(const CUtensorMap& tmap, const float* u_img, const float* s
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ff_kernel<H16, DBG, P9, CG2>, tmap, u_img, scale, shift, y, n_img, C, K, relu,
-                                     out_padded, mv, fp16, dbg, geo);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wino3x3_ff_kernel<H16, DBG, P9, CG2, ALT, GEN>, tmap, u_img, scale, shift, y, n_img, C,
+                                     K, relu, out_padded, mv, fp16, dbg, geo, narrow);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
+
+constexpr int kFfAltDefault = 0;  // see the ALT comment in wino_ff_launch
 
 int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, const float* u_img_narrow,
                    const float* scale, const float* shift, float* y, int n_img, int C, int K, int op16, int cg2, int relu,
@@ -870,6 +978,18 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
 #define WG_FF(H16_, DBG_, P9_, CG2_)                                                                                \
   return launch_ff<H16_, DBG_, P9_, CG2_>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded, max_ctas, stream, \
                                           fp16, dbg, geo)
+  // Alternating transform groups (ALT, see the kernel): for launches whose cout slices are all <= 64 wide (two V stages
+  // in TMEM) -- K <= 64, K = 128 (64 + 64) -- and, mode 2, for wider layers through the all-64-wide filter image.
+  static int alt = -1;  // developer build: WG_FF_ALT=0|1|2
+  if (alt < 0) {
+    const char* e = dev_env("WG_FF_ALT");
+    alt = e ? atoi(e) : kFfAltDefault;
+  }
+  if constexpr (kDev) {  // developer build: ablation flags on the ALT kernel (TF32, default slicing)
+    if (ref_geo && alt > 0 && !cg2 && dbg > 0 && wino_ff_p9() && !op16 && K <= 128 && K % 64 == 0)
+      return launch_ff<false, true, true, false, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded,
+                                                       max_ctas, stream, fp16, dbg, geo, 0);
+  }
   if constexpr (kDev) {
     // developer build only (tools/libwinograd_b200_dev.so): CTA pairs, the ablation instantiation (WG_FF_DEBUG, results
     // are garbage by design) and the single-box raw layout. None of these exist in the product library.
@@ -885,6 +1005,32 @@ int wino_ff_launch(const CUtensorMap& tmap, const float* x, const float* u_img, 
       if (op16) WG_FF(true, false, false, false);
       WG_FF(false, false, false, false);
     }
+  }
+  if constexpr (kDev)  // experiment, measured +-1 us (profiles/wino_r02_notes.md): developer build only
+  if (ref_geo && alt > 0 && !cg2 && dbg == 0 && wino_ff_p9()) {
+    bool all64 = true;
+    for (int sidx = 0; sidx < ff::n_slices(K); ++sidx) all64 = all64 && ff::slice(K, sidx).kn <= 64;
+    if (all64) {
+      if (op16)
+        return launch_ff<true, false, true, false, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded,
+                                                         max_ctas, stream, fp16, 0, geo, 0);
+      return launch_ff<false, false, true, false, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded,
+                                                        max_ctas, stream, fp16, 0, geo, 0);
+    }
+    if (alt == 2 && u_img_narrow != nullptr) {
+      if (op16)
+        return launch_ff<true, false, true, false, true>(tmap, u_img_narrow, scale, shift, y, n_img, C, K, relu, out_padded,
+                                                         max_ctas, stream, fp16, 0, geo, 1);
+      return launch_ff<false, false, true, false, true>(tmap, u_img_narrow, scale, shift, y, n_img, C, K, relu, out_padded,
+                                                        max_ctas, stream, fp16, 0, geo, 1);
+    }
+  }
+  if (!ref_geo) {  // other map sizes: the runtime-geometry instantiation
+    if (op16)
+      return launch_ff<true, false, true, false, false, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded,
+                                                              max_ctas, stream, fp16, 0, geo, 0);
+    return launch_ff<false, false, true, false, false, true>(tmap, u_img, scale, shift, y, n_img, C, K, relu, out_padded,
+                                                             max_ctas, stream, fp16, 0, geo, 0);
   }
   if (op16) WG_FF(true, false, true, false);
   WG_FF(false, false, true, false);
