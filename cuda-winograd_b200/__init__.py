@@ -26,7 +26,7 @@ if IS_DEV_LIB:
     LIB_PATH = DEV_LIB_PATH
 
 WG_TF32, WG_BF16, WG_FP16 = 0, 1, 2
-WG_OUT_PADDED, WG_OUT_MULTICAST, WG_OUT_RELU_AFTER_ADD = 1, 2, 4
+WG_OUT_PADDED, WG_OUT_MULTICAST, WG_OUT_RELU_AFTER_ADD, WG_OUT_INTERIOR_ONLY = 1, 2, 4, 8
 
 # every symbol include/winograd_b200.h, include/wg_legacy.h and include/util.h declare
 ABI_SYMBOLS = (
@@ -219,7 +219,7 @@ class _Layer:
         return _Layer._from_handle(h, device)
 
     # -- device tensors (torch is only the allocator / stream provider here)
-    def __call__(self, x, out=None, out_padded=False, residual=None, relu_after_add=False):
+    def __call__(self, x, out=None, out_padded=False, residual=None, relu_after_add=False, interior_only=False):
         """One fused launch. residual (1x1 layers, dense output): y = act2(act(scale * conv + shift) + residual), the
         add that follows the reference's `_out` layers (Kernel128_one.cu:271-272), act2 = ReLU iff relu_after_add."""
         import torch
@@ -233,6 +233,9 @@ class _Layer:
         assert out.device == x.device
         stream = torch.cuda.current_stream(x.device).cuda_stream
         flags = WG_OUT_PADDED if out_padded else 0
+        if interior_only:       # 1x1 chain mode: `out`'s border is already zero (caller's guarantee), write the interior only
+            assert out_padded
+            flags |= WG_OUT_INTERIOR_ONLY
         if residual is not None:
             assert residual.is_cuda and residual.dtype == torch.float32 and residual.is_contiguous()
             assert residual.device == x.device and residual.numel() == out.numel() and not out_padded
@@ -345,10 +348,11 @@ class Bottleneck:
         n = x.shape[0]
         key = (n, x.device.index)
         if key not in self._bufs:
-            self._bufs[key] = (torch.empty((n,) + self.l1.out_shape(True), device=x.device),
+            # the frame is zeroed ONCE here; every call rewrites its interior only (WG_OUT_INTERIOR_ONLY), the border stays
+            self._bufs[key] = (torch.zeros((n,) + self.l1.out_shape(True), device=x.device),
                                torch.empty((n,) + self.l3.out_shape(), device=x.device))
         frame, mid = self._bufs[key]
-        self.l1(x, out=frame, out_padded=True)
+        self.l1(x, out=frame, out_padded=True, interior_only=True)
         self.l3(frame, out=mid)
         if self.residual:
             return self.l2(mid.view(n, self.px, self.l3.cout), out=out, residual=x, relu_after_add=True)

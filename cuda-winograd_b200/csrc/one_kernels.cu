@@ -349,7 +349,9 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const bool rows_here = (long long)mt * 128 + quad * 32 < m_rows;  // warp-uniform: this warp's 32 rows exist
       if (y_padded != nullptr) {  // chain mode: where this warp's 32 rows go in the padded frame (read back after a warp sync)
         const long long m = (long long)mt * 128 + quad * 32 + lane;
-        frame_tab[quad * 32 + lane] = m < m_rows ? one_frame_index(m, geo) : make_int2(-1, 0);
+        int2 pc = m < m_rows ? one_frame_index(m, geo) : make_int2(-1, 0);
+        if (geo.interior_only) pc.y = 0;  // WG_OUT_INTERIOR_ONLY: the caller keeps the border zero
+        frame_tab[quad * 32 + lane] = pc;
         __syncwarp();
       }
       mbar_wait(&acc_full[buf], aph);
@@ -654,7 +656,9 @@ conv1x1_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __
       if (!out_padded) {
         *reinterpret_cast<float4*>(y + (size_t)m * Cout + col) = acc;
       } else {
-        one_frame_store(y, one_frame_index(m, geo), geo, Cout, col, acc);
+        int2 pc = one_frame_index(m, geo);
+        if (geo.interior_only) pc.y = 0;
+        one_frame_store(y, pc, geo, Cout, col, acc);
       }
     }
   }
@@ -855,9 +859,12 @@ static int one_bf16_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, c
 
 int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtensorMap& tmap_res, const float* w_img,
                const float* scale, const float* shift, float* y, int out_padded, long long m_rows, int Cin, int Cout,
-               int BN, int bf16, int relu, const float* residual, int relu_after, int max_ctas, const OneGeo& geo,
+               int BN, int bf16, int relu, const float* residual, int relu_after, int max_ctas, const OneGeo& geo_in,
                cudaStream_t stream) {
-  float* y_padded = out_padded ? y : nullptr;
+  OneGeo geo = geo_in;
+  geo.interior_only = (out_padded & 2) ? 1 : 0;  // out_padded: bit 0 = padded frame, bit 1 = interior only
+  float* y_padded = (out_padded & 1) ? y : nullptr;
+  out_padded &= 1;
   if (bf16)  // bf16 operands: the H16 instantiation of the throughput kernel, every batch size
     return one_bf16_launch(tmap, tmap_y, tmap_res, w_img, scale, shift, y_padded, m_rows, Cin, Cout, relu, residual,
                            relu_after, max_ctas, geo, stream);

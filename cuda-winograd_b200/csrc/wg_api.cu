@@ -151,7 +151,7 @@ struct wg_layer {
   int num_sms = 0;
   int H = 14, W = 14;      // output map (the reference: 14 x 14 everywhere)
   ff::Geo geo{};           // 3x3: tiles / frame / raw-plane geometry of the full-fold kernel
-  OneGeo one_geo{14, 14, 16, 16};  // 1x1: pixels per image and the padded frame of chain mode
+  OneGeo one_geo{14, 14, 16, 16, 0};  // 1x1: pixels per image and the padded frame of chain mode
   // packed images (device). Sizes in bytes in img_bytes[], same order as the blob sections.
   float* d_filter = nullptr;           // packed filter image (U or swizzled W^T)
   float* d_filter_n64 = nullptr;       // 3x3 full-fold kernel: second image with all slices 64 wide, or null
@@ -293,7 +293,7 @@ static int layer_set_geometry(wg_layer* L, int H, int W) {
   const int rc = wino_ff_geo(H, W, &g);  // also defines the frame a 1x1 layer writes in chain mode
   if (rc != WG_OK) return rc;
   L->geo = g;
-  L->one_geo = OneGeo{H, W, g.Hf, g.Wf};
+  L->one_geo = OneGeo{H, W, g.Hf, g.Wf, 0};
   return WG_OK;
 }
 
@@ -420,7 +420,9 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
   // flags: WG_OUT_PADDED (1) = zero-bordered frame, WG_OUT_MULTICAST (2) = y is an NVLS multicast address (stores go
   // out as multimem.st and land in every GPU's buffer: fused conv + all-gather of the output), WG_OUT_RELU_AFTER_ADD
   // (4, with a residual) = ReLU applied to the sum.
-  if (flags & ~7) return WG_ERR_ARG;
+  if (flags & ~15) return WG_ERR_ARG;
+  // WG_OUT_INTERIOR_ONLY (8, 1x1 layers, with WG_OUT_PADDED): the caller guarantees that the frame's border is already zero
+  if ((flags & WG_OUT_INTERIOR_ONLY) && !(L->kind == 1 && (flags & WG_OUT_PADDED))) return WG_ERR_ARG;
   if ((flags & WG_OUT_MULTICAST) && !(L->kind == 0 && L->dtype == WG_TF32 && kn_tm(L->tile_n))) return WG_ERR_ARG;
   if ((flags & WG_OUT_RELU_AFTER_ADD) && !residual) return WG_ERR_ARG;
   // the residual add exists where the reference's block structure puts it: after the 1x1 `_out` layers, dense output
@@ -501,7 +503,8 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
   if (rc != WG_OK) return rc;
   if (L->kind == 1) {
     if (!residual) tmap_res = tmap_y;
-    return launched(one_launch(tmap, tmap_y, tmap_res, L->d_filter, L->d_scale, L->d_shift, y, out_padded,
+    return launched(one_launch(tmap, tmap_y, tmap_res, L->d_filter, L->d_scale, L->d_shift, y,
+                               out_padded | ((flags & WG_OUT_INTERIOR_ONLY) ? 2 : 0),
                                (long long)N * px, L->cin, L->cout, L->tile_n, L->dtype != WG_TF32, L->relu, residual,
                                (flags & WG_OUT_RELU_AFTER_ADD) ? 1 : 0, max_ctas, L->one_geo, stream));
   }

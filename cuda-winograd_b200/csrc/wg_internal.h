@@ -97,6 +97,7 @@ int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int C
 // spatial geometry of a 1x1 layer: H x W pixels per image; Hf x Wf = the padded frame written in chain mode
 struct OneGeo {
   int H, W, Hf, Wf;
+  int interior_only;  // chain mode: skip the border zeros (WG_OUT_INTERIOR_ONLY)
 };
 // tmap_res / residual / relu_after: fused residual add in the epilogue (null = none); bf16: bf16-operand kernel
 int one_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_y, const CUtensorMap& tmap_res, const float* w_img,

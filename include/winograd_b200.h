@@ -97,6 +97,9 @@ int wg_frame_dims(int H, int W, int* frame_h, int* frame_w);
 #define WG_OUT_PADDED 1
 #define WG_OUT_MULTICAST 2
 #define WG_OUT_RELU_AFTER_ADD 4
+#define WG_OUT_INTERIOR_ONLY 8 /* 1x1 layers with WG_OUT_PADDED: write the H x W interior of the frame only -- the caller
+                                  guarantees that the border is already zero (e.g. a frame buffer zeroed once and reused
+                                  by every call of a bottleneck block); saves the ~30 % extra stores of the edge pixels */
 int wg_run(wg_layer_t* layer, const float* x_dev, float* y_dev, int N, int out_flags, void* cuda_stream);
 
 /* The step that follows the reference's `_out` 1x1 layers in a ResNet bottleneck block (they stop before it:

@@ -638,6 +638,26 @@ def test_bottleneck_block_other_stages(lib_loaded, torch_cuda, h, w, ch, c, n):
     assert golden.rel_err(y.cpu().numpy(), gold) <= 3 * TOL_TF32
 
 
+def test_1x1_interior_only_frame(lib_loaded, torch_cuda):
+    """WG_OUT_INTERIOR_ONLY: chain mode without the border stores -- the interior equals the dense result, the border is
+    whatever the caller put there (zero in Bottleneck's frame buffer, a sentinel here); only valid with WG_OUT_PADDED."""
+    torch = torch_cuda
+    rs = np.random.RandomState(8)
+    for n, cin, cout in ((1, 64, 128), (40, 512, 128)):
+        x = torch.from_numpy((rs.rand(n, 196, cin) - 0.5).astype(np.float32)).cuda()
+        layer = lib_loaded.Conv1x1Bn((rs.rand(cin, cout) - 0.5).astype(np.float32), rs.rand(cout).astype(np.float32),
+                                     rs.rand(cout).astype(np.float32), True)
+        frame = torch.full((n, 16, 16, cout), 7.0, device="cuda")
+        layer(x, out=frame, out_padded=True, interior_only=True)
+        assert torch.equal(frame[:, 1:15, 1:15].reshape(n, 196, cout), layer(x))
+        border = frame.clone()
+        border[:, 1:15, 1:15] = 7.0
+        assert bool((border == 7.0).all())
+        with pytest.raises(lib_loaded.WinogradB200Error):
+            lib_loaded._check(lib_loaded.lib().wg_run(layer._h, x.data_ptr(), frame.data_ptr(), n, 8, None), "wg_run")
+        layer.close()
+
+
 def test_c_example_shards_the_batch_over_all_gpus(lib_loaded):
     """examples/shard_batch.c: the multi-GPU path from plain C -- one host thread per GPU over the C-ABI (device ordinal
     per layer), contiguous image shards, wg_run_host per shard; exit code 0 = sharded result == single-GPU result."""
