@@ -22,8 +22,16 @@ METRICS = [
     ("lts__t_sector_hit_rate.pct", "L2 hit rate"),
     ("sm__inst_executed_pipe_tensor_op_utchmma.avg.pct_of_peak_sustained_active", "tensor pipe (inst, % of peak, active)"),
     ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor subpipe hmma cycles active %"),
-    ("sm__ops_path_tensor_op_utchmma_src_tf32.avg.pct_of_peak_sustained_elapsed", "tensor ops tf32 % of peak (elapsed)"),
-    ("sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.avg.pct_of_peak_sustained_elapsed", "tensor ops bf16 % of peak (elapsed)"),
+    ("sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", "tensor ops tf32 % of peak (elapsed)"),
+    ("sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.peak_sustained", "tensor ops tf32 peak per SM"),
+    ("sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", "tensor ops bf16 % of peak (elapsed)"),
+    ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe cycles active %"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem pipe: LSU shared wavefronts %"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed", "smem pipe: LSU shared loads %"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem pipe: tensor-core operand wavefronts %"),
+    ("l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed", "smem/L1 data bank reads %"),
+    ("l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed", "smem/L1 data bank writes %"),
+    ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue active %"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed", "smem pipe: LSU wavefronts %"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.avg.pct_of_peak_sustained_elapsed", "smem pipe: LSU ld %"),
     ("l1tex__data_pipe_tensor_wavefronts.avg.pct_of_peak_sustained_elapsed", "smem pipe: tensor operand wavefronts %"),
@@ -91,12 +99,13 @@ def main():
         md.append(f"### `{path.split('/')[-1]}` -- `{name[:110]}`\n")
         md.append("| metric | value |\n|---|---|")
         vals = {}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
         for key, label in METRICS:
             if key in m:
                 v, u = m[key]
                 md.append(f"| {label} (`{key}`) | {v} {u} |")
                 try:
-                    vals[key] = float(v.replace(",", ""))
+                    vals[key] = float(v.replace(",", "")) * scale.get(u, 1.0)   # bytes / microseconds / plain numbers
                 except ValueError:
                     pass
         if not args.no_source:
@@ -112,16 +121,16 @@ def main():
         if args.json and i < len(keys):
             def g(k):
                 return vals.get(k)
-            unit = {"gpu__time_duration.sum": m.get("gpu__time_duration.sum", ("", ""))[1]}
             js[keys[i]] = {
                 "report": path.split("/")[-1], "kernel": name[:120],
-                "duration": g("gpu__time_duration.sum"), "duration_unit": unit["gpu__time_duration.sum"],
+                "duration_us_under_ncu": g("gpu__time_duration.sum"),
                 "dram_bytes_per_launch": (g("dram__bytes_read.sum") or 0) + (g("dram__bytes_write.sum") or 0),
                 "dram_read_bytes": g("dram__bytes_read.sum"), "dram_write_bytes": g("dram__bytes_write.sum"),
-                "dram_unit": m.get("dram__bytes_read.sum", ("", ""))[1],
                 "l2_to_sm_read_bytes": g("l1tex__m_xbar2l1tex_read_bytes.sum"),
-                "l2_to_sm_unit": m.get("l1tex__m_xbar2l1tex_read_bytes.sum", ("", ""))[1],
-                "tensor_tf32_pct_of_peak_elapsed": g("sm__ops_path_tensor_op_utchmma_src_tf32.avg.pct_of_peak_sustained_elapsed"),
+                "sm_to_l2_write_bytes": g("l1tex__m_l1tex2xbar_write_bytes.sum"),
+                "how": "ncu --set full --clock-control none, one launch after warm-up, rotating input/output sets; "
+                       "tools/gpu_round.sh + tools/ncu_summary.py",
+                "tensor_tf32_pct_of_peak_elapsed": g("sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"),
                 "lts_throughput_pct": g("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
                 "dram_throughput_pct": g("dram__throughput.avg.pct_of_peak_sustained_elapsed"),
             }
