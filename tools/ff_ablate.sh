@@ -1,3 +1,4 @@
+export WG_B200_DEV_LIB=1   # the knobs below exist in the developer build only (make dev)
 tools/selftest tsrate > gpurun_out/tsrate.txt 2>&1
 for d in 0 1 2 3 4 8 12 16 6 14 15 31; do
   echo "== WG_FF_DEBUG=$d" 

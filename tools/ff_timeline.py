@@ -11,6 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("WG_B200_DEV_LIB", "1")   # the ablation build lives in the developer library
 os.environ.setdefault("WG_FF_DEBUG", "112")
 
 
