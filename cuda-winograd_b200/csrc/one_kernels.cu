@@ -192,6 +192,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           tma_bulk_g2s(smem + S::kOffB + kb * S::kBBytes, b_src + (size_t)kb * b_kb_stride, S::kBBytes, b_full);
       }
       pdl_wait();  // activations come from the previous kernel in the stream
+      if (kDev && (abl & 16) && blockIdx.x == 0) reinterpret_cast<long long*>(y_dbg)[3] = clock64();  // timeline: past the wait
       for (int item = first_item; item < n_items; item += item_stride) {
         const int nt = WG_ITEM_NT(item);
         const int mt = WG_ITEM_MT(item);

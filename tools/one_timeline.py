@@ -18,7 +18,7 @@ def main():
     rs = np.random.RandomState(0)
     layer = wg.Conv1x1Bn((rs.rand(cin, cout) - 0.5).astype(np.float32), np.ones(cout, np.float32),
                          np.zeros(cout, np.float32), False)
-    n = 256
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else 256
     x = torch.rand((n, 196, cin), device="cuda") - 0.5
     y = torch.empty((n, 196, cout), device="cuda")
     dbg = torch.zeros(4096, dtype=torch.int64, device="cuda")
@@ -28,7 +28,8 @@ def main():
     torch.cuda.synchronize()
     t = dbg.cpu().numpy()[:128].reshape(16, 8)
     t0 = t[0, 0]
-    print(f"== {cin}->{cout} WG_ONE_ABLATE={os.environ.get('WG_ONE_ABLATE')}: per item: MMA start | acc free | last commit || epi start | epi end")
+    print(f"== N={n} {cin}->{cout} WG_ONE_ABLATE={os.environ.get('WG_ONE_ABLATE')}: per item: MMA start | acc free | last commit || epi start | epi end")
+    print(f"  producer past griddepcontrol.wait (previous launch complete) at {int(t[0, 3] - t0)}")
     for i in range(16):
         if t[i, 0] == 0:
             break
