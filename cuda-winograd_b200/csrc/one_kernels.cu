@@ -106,6 +106,8 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   // dev_flags: always 0 in the product build. Developer build (WG_ONE_ABLATE): 1 no weight loads, 2 no activation loads,
   // 4 no output stores, 8 no MMAs -- results are garbage, only the time is of interest (profiles/one_ablation_r02.md).
   const int abl = kDev ? dev_flags : 0;
+  if (kDev && (abl & 16) && threadIdx.x == 0)
+    reinterpret_cast<long long*>(y_dbg)[1024 + 4 * blockIdx.x + 0] = (long long)globaltimer_ns();  // timeline: CTA entry
   static_assert(!RES || (CL == 1 && !PAIR), "the residual epilogue exists for the plain and weight-stationary schedules");
   static_assert(!WS || CL == 1, "weight-stationary schedule has no cluster variant");
   static_assert(!PAIR || (CL == 2 && !WS), "CTA pairs are clusters of 2");
@@ -193,6 +195,7 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
       pdl_wait();  // activations come from the previous kernel in the stream
       if (kDev && (abl & 16) && blockIdx.x == 0) reinterpret_cast<long long*>(y_dbg)[3] = clock64();  // timeline: past the wait
+      if (kDev && (abl & 16)) reinterpret_cast<long long*>(y_dbg)[1024 + 4 * blockIdx.x + 1] = (long long)globaltimer_ns();
       for (int item = first_item; item < n_items; item += item_stride) {
         const int nt = WG_ITEM_NT(item);
         const int mt = WG_ITEM_MT(item);
@@ -454,6 +457,10 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   tc_fence_before();
   if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may leave while peers still multicast to it
+  if (kDev && (abl & 16) && threadIdx.x == 0) {  // timeline: per-CTA globaltimer at exit (and the item count)
+    reinterpret_cast<long long*>(y_dbg)[1024 + 4 * blockIdx.x + 2] = (long long)globaltimer_ns();
+    reinterpret_cast<long long*>(y_dbg)[1024 + 4 * blockIdx.x + 3] = (n_items - first_item + item_stride - 1) / item_stride;
+  }
   if (warp == 1) {
     if constexpr (PAIR) tmem_dealloc_cg2<kTmemCols>(tmem_base);
     else tmem_dealloc<kTmemCols>(tmem_base);

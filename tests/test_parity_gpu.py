@@ -658,6 +658,72 @@ def test_1x1_interior_only_frame(lib_loaded, torch_cuda):
         layer.close()
 
 
+def test_wg_run_from_several_host_threads(lib_loaded, torch_cuda):
+    """include/winograd_b200.h: wg_run on ONE layer handle is safe from several host threads (locked tensor-map cache,
+    launches take by-value copies). Four threads, each with its own stream and its own rotating buffers of different
+    batch sizes (so the 4-way cache keeps evicting), must each reproduce the single-threaded result bit for bit."""
+    import threading
+    torch = torch_cuda
+    x, w, sc, sh = _rand3x3(np.random.RandomState(21), 48, 32, 64)
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh)
+    l1 = lib_loaded.Conv1x1Bn((np.random.RandomState(22).rand(32, 128) - 0.5).astype(np.float32),
+                              np.ones(128, np.float32), np.zeros(128, np.float32), True)
+    xd = torch.from_numpy(x).cuda()
+    sizes = [48, 40, 17, 9, 3]
+    ref = {n: layer(xd[:n].contiguous()).clone() for n in sizes}
+    x1 = xd[:, 1:15, 1:15].reshape(48, 196, 32).contiguous()
+    ref1 = {n: l1(x1[:n].contiguous()).clone() for n in sizes}
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(tid):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                bufs = {n: [xd[:n].clone() for _ in range(3)] for n in sizes}
+                bufs1 = {n: [x1[:n].clone() for _ in range(3)] for n in sizes}
+                for it in range(30):
+                    n = sizes[(it + tid) % len(sizes)]
+                    y = layer(bufs[n][it % 3])
+                    y1 = l1(bufs1[n][it % 3])
+                    s.synchronize()
+                    if not torch.equal(y, ref[n]) or not torch.equal(y1, ref1[n]):
+                        errors.append((tid, it, n))
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
+
+
+def test_other_map_sizes_host_path_and_blob(lib_loaded, torch_cuda, tmp_path):
+    """f4 x e2e x f3: a 28x28 layer through wg_run_host (frame-sized staging) and through save / load."""
+    torch = torch_cuda
+    h, w_ = 28, 28
+    hf, wf = golden.frame_dims(h, w_)
+    rs = np.random.RandomState(31)
+    n, c, k = 70, 32, 64
+    x = (rs.rand(n, hf, wf, c) - 0.5).astype(np.float32)
+    wt = (rs.rand(k, c, 3, 3) - 0.5).astype(np.float32)
+    sc, sh = golden.fold_bn(rs.rand(k) - 0.5, rs.rand(k) - 0.5, rs.rand(k) - 0.5, rs.rand(k) * 3 + 5)
+    layer = lib_loaded.Conv3x3BnRelu(wt, sc, sh, hw=(h, w_))
+    gold = golden.conv3x3_bn_relu(x, wt, sc, sh, True, hw=(h, w_))
+    yh = layer.run_host(x)
+    assert yh.shape == (n, h, w_, k) and golden.rel_err(yh, gold) <= TOL_TF32
+    yp = layer.run_host(x, out_padded=True)
+    np.testing.assert_array_equal(yp[:, 1:h + 1, 1:w_ + 1], yh)
+    path = str(tmp_path / "l28.wgb")
+    layer.save(path)
+    loaded = lib_loaded._Layer.load(path)
+    assert (loaded.h, loaded.w, loaded.hf, loaded.wf) == (h, w_, hf, wf)
+    xd = torch.from_numpy(x).cuda()
+    assert torch.equal(loaded(xd), layer(xd))
+
+
 def test_c_example_shards_the_batch_over_all_gpus(lib_loaded):
     """examples/shard_batch.c: the multi-GPU path from plain C -- one host thread per GPU over the C-ABI (device ordinal
     per layer), contiguous image shards, wg_run_host per shard; exit code 0 = sharded result == single-GPU result."""

@@ -21,11 +21,25 @@ def main():
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 256
     x = torch.rand((n, 196, cin), device="cuda") - 0.5
     y = torch.empty((n, 196, cout), device="cuda")
-    dbg = torch.zeros(4096, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(8192, dtype=torch.int64, device="cuda")
     wg.lib().wg_dev_set_dbg_ptr(ctypes.c_void_p(dbg.data_ptr()))
     for _ in range(3):
         layer(x, out=y)
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        layer(x, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"  (this single-buffer loop: {e0.elapsed_time(e1) * 50:.1f} us per launch)")
+    g = dbg.cpu().numpy()[1024:1024 + 4 * 148].reshape(148, 4)
+    z = g[:, 1].min()
+    import numpy as _np
+    for k in sorted(set(g[:, 3].tolist())):
+        m = g[:, 3] == k
+        print(f"  CTAs with {k} items ({int(m.sum())}): entry {int((g[m, 0] - z).min())}..{int((g[m, 0] - z).max())} ns, past the wait "
+              f"{int((g[m, 1] - z).min())}..{int((g[m, 1] - z).max())}, exit {int((g[m, 2] - z).min())} .. median {int(_np.median(g[m, 2] - z))} .. {int((g[m, 2] - z).max())}")
     t = dbg.cpu().numpy()[:128].reshape(16, 8)
     t0 = t[0, 0]
     print(f"== N={n} {cin}->{cout} WG_ONE_ABLATE={os.environ.get('WG_ONE_ABLATE')}: per item: MMA start | acc free | last commit || epi start | epi end")
