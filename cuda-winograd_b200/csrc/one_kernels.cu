@@ -363,11 +363,17 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (kDev && (abl & 16) && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 16)
         reinterpret_cast<long long*>(y_dbg)[8 * it + 4] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32, ++chunk) {
-        float v[32];
-        tmem_ld_x16(taddr + c0, v);
-        tmem_ld_x16(taddr + c0 + 16, v + 16);
+      // One 32-cout chunk whose accumulator columns are already in v[]: BN (+ReLU, + residual), staging, store.
+      auto process_chunk = [&](float (&v)[32], int c0, bool cts, long long* cst) {
+        // Folded BN of the chunk's 32 couts, all 16 loads issued before anything that orders memory (the shared-memory
+        // stores below are asm volatile with a memory clobber: loads placed between them are NOT hoisted by the
+        // compiler and each pair then costs a full L1 round trip -- 8 x ~50 clk per chunk, measured).
+        float4 s4[8], h4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s4[j] = __ldg(reinterpret_cast<const float4*>(sc + c0 + 4 * j));
+          h4[j] = __ldg(reinterpret_cast<const float4*>(sh + c0 + 4 * j));
+        }
         if constexpr (RES) {
           // next sub-tile's residual goes into the OTHER buffer: the store that last read it (previous chunk) must be
           // done reading; then wait for this chunk's residual (requested one chunk ago)
@@ -383,19 +389,17 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         } else {
           // the staging buffer written two chunks ago must have been read by its TMA store
           if (lane == 0) tma_store_wait_read<1>();
+          if (cts) cst[1] = clock64();
           __syncwarp();
         }
-        tmem_ld_wait();
         const uint32_t dst = stage_u32 + (chunk & 1) * S::kStageOutBytes + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c0 + 4 * j));
-          const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + c0 + 4 * j));
           float4 o;
-          o.x = fmaf(s4.x, v[4 * j + 0], h4.x);
-          o.y = fmaf(s4.y, v[4 * j + 1], h4.y);
-          o.z = fmaf(s4.z, v[4 * j + 2], h4.z);
-          o.w = fmaf(s4.w, v[4 * j + 3], h4.w);
+          o.x = fmaf(s4[j].x, v[4 * j + 0], h4[j].x);
+          o.y = fmaf(s4[j].y, v[4 * j + 1], h4[j].y);
+          o.z = fmaf(s4[j].z, v[4 * j + 2], h4[j].z);
+          o.w = fmaf(s4[j].w, v[4 * j + 3], h4[j].w);
           if (relu) {
             o.x = fmaxf(o.x, 0.f);
             o.y = fmaxf(o.y, 0.f);
@@ -434,14 +438,43 @@ conv1x1_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
           }
           __syncwarp();  // staging buffer free again
-          continue;
+          ++chunk;
+          return;
         }
+        if (cts) cst[3] = clock64();
         fence_proxy_async_smem();
         __syncwarp();
+        if (cts) cst[4] = clock64();
         if (lane == 0 && rows_here && !(abl & 4)) {
           tma_tensor_2d_s2g(&tmap_y, stage_out + (chunk & 1) * S::kStageOutBytes, nt * BN + c0, mt * 128 + quad * 32);
           tma_store_commit();
         }
+        if (cts) cst[5] = clock64();
+        ++chunk;
+      };
+      // Chunk loop, software-pipelined over two register sets: the tcgen05.ld of chunk c + 1 (bound by the 64 B/clk of
+      // TMEM read bandwidth: ~350 clk for this warp's 4 KB while all four epilogue warps load) is in flight while chunk
+      // c is scaled, staged and stored. tcgen05.wait::ld covers every earlier load, so each load is issued right after
+      // the wait for its predecessor.
+      float va[32], vb[32];
+      tmem_ld_x32(taddr, va);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        // developer build timeline: phases of every chunk of CTA 0 / epilogue warp 2 / its third item
+        const bool cts = kDev && (abl & 16) && blockIdx.x == 0 && warp == 2 && lane == 0 && it == 2;
+        long long* cst = reinterpret_cast<long long*>(y_dbg) + 2048 + 8 * (c0 / 32);
+        if (cts) cst[0] = clock64();
+        tmem_ld_wait();
+        tmem_ld_x32(taddr + c0 + 32, vb);
+        if (cts) cst[2] = clock64();
+        process_chunk(va, c0, cts, cst);
+        if (cts) cst[8] = clock64();
+        tmem_ld_wait();
+        if (c0 + 64 < BN) {
+          tmem_ld_x32(taddr + c0 + 64, va);
+        }
+        if (cts) cst[10] = clock64();
+        process_chunk(vb, c0 + 32, cts, cst + 8);
       }
       tc_fence_before();
       __syncwarp();

@@ -98,3 +98,60 @@ extern "C" int wg_measure_tensor_peak(int device, int dtype, double* tflops_out,
   if (clk_per_mma_out) *clk_per_mma_out = best_ms * 1e-3 * (prop.clockRate * 1e3) / iters;
   return WG_OK;
 }
+
+#ifdef WG_DEV_BUILD
+// Developer probe: how fast do `warps` warps (one per 32-lane TMEM quadrant, two per quadrant from 5 warps on) read TMEM
+// with tcgen05.ld.32x32b.x32 -- `depth` loads in flight per tcgen05.wait::ld? Answers whether the 1x1 epilogue's
+// ~350-450 clk per 32-column chunk is the TMEM read port (per SM), a per-warp latency, or something around it.
+namespace wg {
+__global__ void __launch_bounds__(256, 1) tmem_ld_probe_kernel(int iters, int depth, int with_fence, long long* out) {
+  __shared__ uint32_t tmem_ptr;
+  __shared__ __align__(16) float sink[256 * 4];
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_ptr + ((uint32_t)((warp & 3) * 32) << 16);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    float v[4][32];
+    for (int d = 0; d < 4; ++d)
+      if (d < depth) tmem_ld_x32(tbase + (uint32_t)(((i * 4 + d) * 32) & 511), v[d]);
+    tmem_ld_wait();
+    for (int d = 0; d < 4; ++d)
+      if (d < depth)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("" ::"f"(v[d][j]));  // consumed, no dependent arithmetic
+    if (with_fence) {
+      sink[threadIdx.x * 4] = v[0][0];
+      fence_proxy_async_smem();
+      __syncwarp();
+    }
+  }
+  const long long t1 = clock64();
+  if ((threadIdx.x & 31) == 0) out[warp] = t1 - t0;
+  if (sink[(threadIdx.x * 4 + 4) & 1023] == 12345.678f) out[100] = 1;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_ptr);
+}
+}  // namespace wg
+
+extern "C" int wg_dev_tmem_ld_probe(int warps, int iters, int depth, int with_fence, long long* clk_out) {
+  long long* d = nullptr;
+  if (warps < 1 || warps > 8 || depth < 1 || depth > 4) return WG_ERR_ARG;
+  if (cudaMalloc(&d, 128 * sizeof(long long)) != cudaSuccess) return WG_ERR_CUDA;
+  cudaMemset(d, 0, 128 * sizeof(long long));
+  wg::tmem_ld_probe_kernel<<<1, warps * 32>>>(iters, depth, with_fence, d);
+  long long h[8] = {0};
+  const cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return WG_ERR_CUDA;
+  long long mx = 0;
+  for (int i = 0; i < warps; ++i) mx = h[i] > mx ? h[i] : mx;
+  *clk_out = mx;
+  return WG_OK;
+}
+#endif

@@ -40,6 +40,15 @@ def main():
         m = g[:, 3] == k
         print(f"  CTAs with {k} items ({int(m.sum())}): entry {int((g[m, 0] - z).min())}..{int((g[m, 0] - z).max())} ns, past the wait "
               f"{int((g[m, 1] - z).min())}..{int((g[m, 1] - z).max())}, exit {int((g[m, 2] - z).min())} .. median {int(_np.median(g[m, 2] - z))} .. {int((g[m, 2] - z).max())}")
+    c = dbg.cpu().numpy()[2048:2048 + 64].reshape(8, 8)
+    if c[0, 0]:
+        print("  epilogue warp 2, third item, per 32-cout chunk: start | store-read wait done | tcgen05.ld done | BN + staging done | "
+              "fence + warp sync done | TMA store issued (clk since the chunk start; last column: start of the next chunk)")
+        for i in range(8):
+            if c[i, 0] == 0:
+                break
+            nxt = int(c[i + 1, 0] - c[i, 0]) if i + 1 < 8 and c[i + 1, 0] else -1
+            print("   chunk", i, " ".join(f"{int(v - c[i, 0]):6d}" for v in c[i, 1:6]), f"{nxt:7d}")
     t = dbg.cpu().numpy()[:128].reshape(16, 8)
     t0 = t[0, 0]
     print(f"== N={n} {cin}->{cout} WG_ONE_ABLATE={os.environ.get('WG_ONE_ABLATE')}: per item: MMA start | acc free | last commit || epi start | epi end")
