@@ -141,6 +141,8 @@ struct TmapCache {
 
 using namespace wg;
 
+static constexpr int kNumImgs = 6;  // packed images per layer (device buffers and blob sections)
+
 struct wg_layer {
   int kind = 0;  // 0 = 3x3 Winograd, 1 = 1x1 GEMM
   int cin = 0, cout = 0, relu = 0, dtype = 0, device = 0;
@@ -158,13 +160,14 @@ struct wg_layer {
   float* d_filter_tm16 = nullptr;      // 3x3 bf16/fp16: U in the 16-bit image of the V-in-TMEM throughput kernel
   float* d_filter_tm16_n64 = nullptr;  // the same with all slices 64 wide
   float* d_filter_small = nullptr;     // 3x3 TF32: U in the plain KN=32 image of the small-batch kernel (may alias d_filter)
+  float* d_filter_direct = nullptr;    // 3x3 TF32, 14x14: per-tap weight blocks of the direct-convolution kernel, or null
   float* d_scale = nullptr;
   float* d_shift = nullptr;
-  size_t img_bytes[5] = {0, 0, 0, 0, 0};
+  size_t img_bytes[kNumImgs] = {0, 0, 0, 0, 0, 0};
   std::vector<float> w_host;  // the raw weights as given to create() (kept for wg_layer_serialize)
   // tensor-map caches
   std::mutex mu;
-  TmapCache tm_x, tm_x16, tm_small, tm_y, tm_res;
+  TmapCache tm_x, tm_x16, tm_small, tm_y, tm_res, tm_xd, tm_yd, tm_ydp;
   size_t in_px() const { return kind == 0 ? (size_t)geo.Hf * geo.Wf : (size_t)H * W; }
   size_t out_px(int padded) const {
     return padded ? (kind == 0 ? (size_t)geo.Hf * geo.Wf : (size_t)one_geo.Hf * one_geo.Wf) : (size_t)H * W;
@@ -213,6 +216,9 @@ static void layer_plan(wg_layer* L) {
     L->img_bytes[3] = (t16 && L->tm16_ff && !L->ff_cg2 && wino_ff_has_narrow(L->cout)) ? fe * 2 : 0;
     // the small-batch kernel (and its plain KN=32 image) exists for the reference's 14x14 geometry only
     L->img_bytes[4] = (L->dtype == WG_TF32 && L->tile_n != 32 && ff::geo_is_ref(L->geo)) ? fe * 4 : 0;  // tile_n == 32: aliases d_filter
+    // the direct-convolution kernel: TF32, reference geometry, 32-channel chunks, 128-cout blocks
+    L->img_bytes[5] = (L->dtype == WG_TF32 && ff::geo_is_ref(L->geo) && L->cin % 32 == 0 && L->cout % 128 == 0)
+                          ? (size_t)9 * L->cin * L->cout * 4 : 0;
   } else {
     L->tile_n = (L->cout % 256 == 0 && L->dtype == WG_TF32) ? 256 : 128;  // bf16 operands: 128-wide N-tiles
     L->img_bytes[0] = (size_t)L->cin * L->cout * (L->dtype == WG_TF32 ? 4 : 2);
@@ -225,13 +231,14 @@ static float** layer_img_slot(wg_layer* L, int i) {
     case 1: return &L->d_filter_n64;
     case 2: return &L->d_filter_tm16;
     case 3: return &L->d_filter_tm16_n64;
-    default: return &L->d_filter_small;
+    case 4: return &L->d_filter_small;
+    default: return &L->d_filter_direct;
   }
 }
 
 static int layer_alloc(wg_layer* L) {
   WG_CUDA(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < kNumImgs; ++i)
     if (L->img_bytes[i]) WG_CUDA(cudaMalloc(layer_img_slot(L, i), L->img_bytes[i]));
   if (L->kind == 0 && L->dtype == WG_TF32 && L->tile_n == 32) L->d_filter_small = L->d_filter;
   WG_CUDA(cudaMalloc(&L->d_scale, L->cout * sizeof(float)));
@@ -282,6 +289,10 @@ static int layer_pack(wg_layer* L, const float* d_w) {
   }
   if (rc == WG_OK && L->img_bytes[4]) {
     rc = filter_transform_launch(d_w, L->d_filter_small, cin, cout, 32, 0, L->stream);
+    count();
+  }
+  if (rc == WG_OK && L->img_bytes[5]) {
+    rc = direct_pack_launch(d_w, L->d_filter_direct, cin, cout, L->stream);
     count();
   }
   return rc;
@@ -395,11 +406,11 @@ struct BlobHeader {
   int32_t kind, cin, cout, relu, dtype, tile_n, tm_db, tm16_ff, ff_cg2, dev_build;
   int32_t height, width;   // output map (14 x 14 for every reference shape)
   uint64_t w_elems;        // raw weights (fp32): first payload section, then scale[cout], shift[cout]
-  uint64_t img_bytes[5];   // packed images, in layer_img_slot() order
+  uint64_t img_bytes[kNumImgs];   // packed images, in layer_img_slot() order
   uint64_t payload_bytes;  // everything after the header
   uint64_t checksum;       // FNV-1a 64 over the payload
 };
-static constexpr uint32_t kBlobVersion = 2;
+static constexpr uint32_t kBlobVersion = 3;  // 3: + the direct-convolution kernel's weight image
 static_assert(sizeof(BlobHeader) % 8 == 0, "header layout");
 
 static uint64_t fnv1a(const uint8_t* p, size_t n) {
@@ -409,6 +420,19 @@ static uint64_t fnv1a(const uint8_t* p, size_t n) {
     h *= 1099511628211ull;
   }
   return h;
+}
+
+// 3x3, TF32, reference geometry: batch size from which the direct-convolution kernel is used (below it the split-C
+// Winograd latency kernels win: their channel loop is divided over a cluster). WG_3X3_DIRECT_MIN (developer build)
+// overrides; a huge value keeps every batch on the Winograd kernels.
+static int direct_min_batch(int cin) {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = dev_env("WG_3X3_DIRECT_MIN");
+    env = e ? atoi(e) : -1;
+  }
+  if (env >= 0) return env;
+  return cin >= 256 ? 6 : 11;  // measured cross-over with the split-C latency kernel (profiles/direct3x3_r02.md)
 }
 
 static int run_impl(wg_layer_t* L, const float* x, const float* residual, float* y, int N, int flags,
@@ -445,6 +469,21 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
   const long long px = (long long)L->H * L->W;  // 1x1: GEMM rows per image
   // map sizes other than the reference's run the full-fold kernel only (developer build: not with a superseded generation)
   if (L->kind == 0 && !ref_geo && !(L->dtype == WG_TF32 ? L->tile_n == 96 : L->tm16_ff != 0)) return WG_ERR_ARG;
+  if (L->kind == 0 && L->d_filter_direct != nullptr && !(out_flags & 2) && N >= direct_min_batch(L->cin)) {
+    // throughput-sized batches of the reference geometry: direct convolution on the tensor core (no CUDA-core transform;
+    // measured faster than the fused Winograd pipeline from a handful of images on, see conv3x3_direct_kernel.cu)
+    {
+      std::lock_guard<std::mutex> lk(L->mu);
+      rc = L->tm_xd.get(x, N, &tmap, [&](CUtensorMap* m) { return direct_make_tmap_in(m, x, N, L->cin); });
+      if (rc == WG_OK)
+        rc = (out_padded ? L->tm_ydp : L->tm_yd).get(y, N, &tmap_y, [&](CUtensorMap* m) {
+          return direct_make_tmap_out(m, y, N, L->cout, out_padded);
+        });
+    }
+    if (rc != WG_OK) return rc;
+    return launched(direct_launch(tmap, tmap_y, L->d_filter_direct, L->d_scale, L->d_shift, N, L->cin, L->cout, 1,
+                                  L->relu, out_padded, max_ctas, 1, stream));
+  }
   if (L->kind == 0 && ref_geo && L->d_filter_small != nullptr) {
     // small batches: the latency variant (one 64-tile x 32-cout item per cluster, split-C), see wino_small_kernel.cu
     const int cs = wino_small_cs(N, L->cin, L->cout, max_ctas);
@@ -589,7 +628,7 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
     L->d_x_bytes = 0;
     {
       std::lock_guard<std::mutex> lk(L->mu);  // the freed address may come back with other contents / sizes
-      L->tm_x.clear(), L->tm_x16.clear(), L->tm_small.clear();
+      L->tm_x.clear(), L->tm_x16.clear(), L->tm_small.clear(), L->tm_xd.clear();
     }
     WG_CUDA(cudaMalloc(&L->d_x, xb));
     L->d_x_bytes = xb;
@@ -600,7 +639,7 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
     L->d_y_bytes = 0;
     {
       std::lock_guard<std::mutex> lk(L->mu);
-      L->tm_y.clear();
+      L->tm_y.clear(), L->tm_yd.clear(), L->tm_ydp.clear();
     }
     WG_CUDA(cudaMalloc(&L->d_y, yb));
     L->d_y_bytes = yb;
@@ -673,6 +712,7 @@ int wg_destroy(wg_layer_t* L) {
   DeviceGuard guard;
   guard.enter(L->device);
   if (L->d_filter_small && L->d_filter_small != L->d_filter) cudaFree(L->d_filter_small);
+  if (L->d_filter_direct) cudaFree(L->d_filter_direct);
   if (L->d_filter_tm16) cudaFree(L->d_filter_tm16);
   if (L->d_filter_n64) cudaFree(L->d_filter_n64);
   if (L->d_filter_tm16_n64) cudaFree(L->d_filter_tm16_n64);
@@ -695,7 +735,7 @@ int wg_layer_serialize(const wg_layer_t* Lc, void* buf, size_t cap, size_t* need
   wg_layer* L = const_cast<wg_layer*>(Lc);
   if (!L || !need) return WG_ERR_ARG;
   size_t payload = L->w_host.size() * 4 + (size_t)L->cout * 8;
-  for (int i = 0; i < 5; ++i) payload += L->img_bytes[i];
+  for (int i = 0; i < kNumImgs; ++i) payload += L->img_bytes[i];
   *need = sizeof(BlobHeader) + payload;
   if (!buf) return WG_OK;  // size query
   if (cap < *need) return WG_ERR_ARG;
@@ -708,7 +748,7 @@ int wg_layer_serialize(const wg_layer_t* Lc, void* buf, size_t cap, size_t* need
   p += (size_t)L->cout * 4;
   WG_CUDA(cudaMemcpy(p, L->d_shift, (size_t)L->cout * 4, cudaMemcpyDeviceToHost));
   p += (size_t)L->cout * 4;
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < kNumImgs; ++i)
     if (L->img_bytes[i]) {
       WG_CUDA(cudaMemcpy(p, *layer_img_slot(L, i), L->img_bytes[i], cudaMemcpyDeviceToHost));
       p += L->img_bytes[i];
@@ -722,7 +762,7 @@ int wg_layer_serialize(const wg_layer_t* Lc, void* buf, size_t cap, size_t* need
   h.tm_db = L->tm_db, h.tm16_ff = L->tm16_ff, h.ff_cg2 = L->ff_cg2, h.dev_build = kDev ? 1 : 0;
   h.height = L->H, h.width = L->W;
   h.w_elems = L->w_host.size();
-  for (int i = 0; i < 5; ++i) h.img_bytes[i] = L->img_bytes[i];
+  for (int i = 0; i < kNumImgs; ++i) h.img_bytes[i] = L->img_bytes[i];
   h.payload_bytes = payload;
   h.checksum = fnv1a(static_cast<const uint8_t*>(buf) + sizeof(BlobHeader), payload);
   memcpy(buf, &h, sizeof(h));
@@ -743,7 +783,7 @@ int wg_layer_deserialize(wg_layer_t** out, const void* buf, size_t bytes, int de
   const size_t w_expect = h.kind == 0 ? (size_t)h.cout * h.cin * 9 : (size_t)h.cin * h.cout;
   if (h.w_elems != w_expect) return WG_ERR_IO;
   size_t total = h.w_elems * 4 + (size_t)h.cout * 8;
-  for (int i = 0; i < 5; ++i) total += h.img_bytes[i];
+  for (int i = 0; i < kNumImgs; ++i) total += h.img_bytes[i];
   if (total != h.payload_bytes) return WG_ERR_IO;
   const float* w = reinterpret_cast<const float*>(payload);
   const float* scale = w + h.w_elems;
@@ -767,7 +807,7 @@ int wg_layer_deserialize(wg_layer_t** out, const void* buf, size_t bytes, int de
   // The images are the shared-memory images of THIS build's kernels. A blob written by a build with other kernel
   // choices (developer knobs, an older version) still carries the raw weights: re-pack from those instead of failing.
   bool same = L->tile_n == h.tile_n && L->tm_db == h.tm_db && L->tm16_ff == h.tm16_ff && L->ff_cg2 == h.ff_cg2;
-  for (int i = 0; i < 5; ++i) same = same && L->img_bytes[i] == h.img_bytes[i];
+  for (int i = 0; i < kNumImgs; ++i) same = same && L->img_bytes[i] == h.img_bytes[i];
   if (!same) {
     delete L;
     return create_common(out, h.kind, h.cin, h.cout, h.height, h.width, w, h.w_elems, scale, shift, h.relu,
@@ -791,7 +831,7 @@ int wg_layer_deserialize(wg_layer_t** out, const void* buf, size_t bytes, int de
   }
   WG_TRY(cudaMemcpyAsync(L->d_scale, scale, (size_t)h.cout * 4, cudaMemcpyHostToDevice, L->stream));
   WG_TRY(cudaMemcpyAsync(L->d_shift, shift, (size_t)h.cout * 4, cudaMemcpyHostToDevice, L->stream));
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < kNumImgs; ++i)
     if (L->img_bytes[i]) {
       WG_TRY(cudaMemcpyAsync(*layer_img_slot(L, i), img, L->img_bytes[i], cudaMemcpyHostToDevice, L->stream));
       img += L->img_bytes[i];

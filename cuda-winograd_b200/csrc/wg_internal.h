@@ -91,6 +91,16 @@ int wino_small_cs(int n_img, int C, int K, int max_ctas);  // cluster split fact
 int wino_small_launch(const CUtensorMap& tmap_small, const float* u_plain, const float* scale, const float* shift,
                       float* y, int n_img, int C, int K, int relu, int out_padded, int cs, cudaStream_t stream);
 
+// ---- 3x3 as a direct convolution on the tensor core (conv3x3_direct_kernel.cu): TF32, the reference's 14x14 map in its
+// 16x16 frame, Cin % 32 == 0, Cout % 128 == 0. Weight image: [Cout/128][Cin/32][9 taps][128 couts][32 channels].
+int direct_pack_launch(const float* w_kcrs, float* w_img, int Cin, int Cout, cudaStream_t stream);
+int direct_make_tmap_in(CUtensorMap* tmap, const float* x, int n_img, int Cin);
+int direct_make_tmap_out(CUtensorMap* tmap, const float* y, int n_img, int Cout, int out_padded);
+// cl = cluster size (weight multicast), out_padded: 0 dense, 1 frame with its zero border; mixed = half-image tail items
+int direct_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
+                  const float* shift, int n_img, int Cin, int Cout, int cl, int relu, int out_padded, int max_ctas,
+                  int mixed, cudaStream_t stream);
+
 // ---- 1x1 GEMM path (one_kernels.cu)
 int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);
 int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout);

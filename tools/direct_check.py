@@ -16,18 +16,17 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ns", default="3,32,256")
-    ap.add_argument("--bo", default="0,2", help="bit 0: base-offset field set, bit 1: CTA pairs")
+    ap.add_argument("--bo", default="1,2,4", help="mode: cluster size 1 / 2 / 4, + 8 = no mixed schedule")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--shapes", default="256x256,128x128")
-    ap.add_argument("--bns", default="256,128")
     args = ap.parse_args()
     import numpy as np
     import torch
     import golden
     L = ctypes.CDLL(os.path.join(ROOT, "tools", "libwinograd_b200_dev.so"))
     vp = ctypes.c_void_p
-    L.wg_dev_direct_pack.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
-    L.wg_dev_direct_run.argtypes = [vp] * 5 + [ctypes.c_int] * 8 + [vp]
+    L.wg_dev_direct_pack.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    L.wg_dev_direct_run.argtypes = [vp] * 5 + [ctypes.c_int] * 7 + [vp]
     dev = torch.device("cuda", 0)
     for shape in args.shapes.split(","):
         c, k = [int(v) for v in shape.split("x")]
@@ -37,11 +36,9 @@ def main():
         wd = torch.from_numpy(w).to(dev)
         scd = torch.from_numpy(np.asarray(sc, np.float32)).to(dev)
         shd = torch.from_numpy(np.asarray(sh, np.float32)).to(dev)
-        for bn in [int(v) for v in args.bns.split(",")]:
-            if k % bn:
-                continue
+        for bn in [128]:
             img = torch.zeros(9 * c * k, device=dev)
-            assert L.wg_dev_direct_pack(wd.data_ptr(), img.data_ptr(), c, k, bn) == 0
+            assert L.wg_dev_direct_pack(wd.data_ptr(), img.data_ptr(), c, k) == 0
             for n in [int(v) for v in args.ns.split(",")]:
                 x = np.zeros((n, 16, 16, c), np.float32)
                 x[:, 1:15, 1:15] = rs.rand(n, 14, 14, c) - 0.5
@@ -56,7 +53,7 @@ def main():
 
                         def run(i):
                             rc = L.wg_dev_direct_run(xs[i % sets].data_ptr(), img.data_ptr(), scd.data_ptr(),
-                                                     shd.data_ptr(), ys[i % sets].data_ptr(), n, c, k, bn, 1, padded,
+                                                     shd.data_ptr(), ys[i % sets].data_ptr(), n, c, k, 1, padded,
                                                      148, bo, None)
                             assert rc == 0, rc
                         run(0)
@@ -79,7 +76,7 @@ def main():
                         e1.record()
                         torch.cuda.synchronize()
                         us = e0.elapsed_time(e1) * 1e3 / args.iters
-                        print(f"direct {c}->{k} BN={bn} N={n} mode={bo} padded={padded}: rel_err {err:.2e} "
+                        print(f"direct {c}->{k} N={n} mode={bo} padded={padded}: rel_err {err:.2e} "
                               f"border_zero {border}  {us:8.2f} us", flush=True)
 
 
