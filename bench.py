@@ -112,7 +112,7 @@ def traffic_from_profiles():
     if not os.path.exists(tpath):
         return None, None
     d = json.load(open(tpath))
-    k = d.get("wino3x3_256_n256", {})
+    k = d.get("conv3x3_256_n256", {})
     return k.get("dram_bytes_per_launch"), k
 
 
@@ -352,8 +352,10 @@ def run_gpu(args):
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": tflops / tf32_peak, "traffic": traffic,
-                         "kernel": "wino3x3_ff_kernel (V in TMEM, inverse transform folded into the MMAs, 96-wide cout slices)",
-                         "algorithmic": "direct-conv-equivalent 2*196*256*256*9 = 231.21 MFLOP/image x 256 images/launch",
+                         "kernel": "conv3x3_direct_kernel (direct convolution on tcgen05: couts on M, one image's 14 frame rows on "
+                                   "N = 224, nine taps = nine shifted shared-memory descriptors of one activation box)",
+                         "algorithmic": "2*196*256*256*9 = 231.21 MFLOP/image x 256 images/launch (the kernel executes 224/196 "
+                                        "of that: the frame's two border columns ride along)",
                          "peak_note": "dense TF32 tcgen05 peak MEASURED in this run on this device (tensor_peak.tf32_tcgen05_tflops: "
                                       "back-to-back kind::tf32 MMAs on every SM, ms-long launch = the burst regime the kernel "
                                       "launches are timed in); MEASURED_PEAKS.json holds no TF32 figure",

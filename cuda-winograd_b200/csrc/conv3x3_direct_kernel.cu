@@ -40,7 +40,7 @@ constexpr int kDirAccCols = 256;      // TMEM columns per accumulator buffer
 
 struct DirSmem {
   static constexpr int kSX = 2;  // activation chunks in flight
-  static constexpr int kSW = 6;  // weight blocks in flight
+  static constexpr int kSW = 7;  // weight blocks in flight
   // activation rows per chunk: the image's 224 pixels + halo on both sides, as two TMA boxes (<= 256 rows each)
   static constexpr int kXRows = kDirN + 2 * kDirHalo;  // 272
   static constexpr int kXBoxRows = 136;

@@ -45,3 +45,10 @@ def test_1x1_cta_pair_variant():
                         "-m", "gpu", "-k", "1x1_ragged or 1x1_padded"],
                        env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_winograd_throughput_kernel_behind_the_direct_engine():
+    """WG_3X3_DIRECT_MIN=1000000 keeps every TF32 batch on the fused Winograd kernels (what the product ran before the
+    direct-convolution engine): the full-fold kernel still agrees with the oracle on the shapes that now default to the
+    direct engine, N = 256 included (tools/ff_check.py: parity on awkward shapes + sampled images at N = 256)."""
+    _run_ff_check({"WG_3X3_DIRECT_MIN": "1000000"})

@@ -115,7 +115,8 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, n, c, k):
     """The throughput kernel (wino_ff_kernel.cu / wino_ffw_kernel.cu: 4 accumulators, cout slices of 96 / 64 / 32) on
     batches that do not fill the last 128-tile M-block and on every cout-slice width. TF32 and, where the shape allows
     them, bf16 / fp16 operands; dense output and the zero-bordered frame must agree bit for bit. The two C = 256 shapes
-    are small enough for the split-C mode (clusters of 2 sharing an item, DSMEM reduction). (The superseded kernel
+    are small enough for the split-C mode (clusters of 2 sharing an item, DSMEM reduction) in their 16-bit variants; their
+    TF32 variant (and 64 x 128 -> 128) runs the direct-convolution engine, see the next test. (The superseded kernel
     generations live in the developer build: tests/test_dev_gpu.py.)"""
     torch = torch_cuda
     x, w, sc, sh = _rand3x3(np.random.RandomState(900 + n + c + k), n, c, k)
@@ -135,6 +136,36 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, n, c, k):
         for _ in range(8):
             assert torch.equal(layer(xd), y0)
         layer.close()
+
+
+@pytest.mark.parametrize("n,c,k", [(6, 256, 256), (11, 128, 128), (13, 32, 128), (37, 64, 256), (75, 128, 384),
+                                   (149, 256, 128), (160, 96, 128)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_3x3_direct_convolution_engine(lib_loaded, torch_cuda, n, c, k, relu):
+    """conv3x3_direct_kernel.cu (TF32, 14x14, Cin % 32 == 0, Cout % 128 == 0, from 6 / 11 images on): every tap is a
+    shifted shared-memory descriptor of one activation box. Batches that make whole-image items only, half-image items
+    only (n * k / 128 * 2 <= #SMs) and the mixed schedule (whole rounds + a half-image tail); first and last image (their
+    halo rows lie outside the tensor: TMA zero fill); dense output and frame bit-identical, frame border exactly zero;
+    a garbage-filled output buffer is fully overwritten; run-to-run bit-identical."""
+    torch = torch_cuda
+    x, w, sc, sh = _rand3x3(np.random.RandomState(1700 + n + c + k), n, c, k)
+    gold = golden.conv3x3_bn_relu(x, w, sc, sh, relu)
+    xd = torch.from_numpy(x).cuda()
+    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=relu)
+    y = torch.full((n, 14, 14, k), float("nan"), device="cuda")
+    yp = torch.full((n, 16, 16, k), float("nan"), device="cuda")
+    layer(xd, out=y)
+    layer(xd, out=yp, out_padded=True)
+    yh, yph = y.cpu().numpy(), yp.cpu().numpy()
+    assert np.isfinite(yh).all() and np.isfinite(yph).all()
+    assert golden.rel_err(yh, gold) <= TOL_TF32
+    per_image = np.abs(yh - gold).reshape(n, -1).max(axis=1) / np.abs(gold).max()
+    assert per_image.max() <= TOL_TF32, int(per_image.argmax())
+    np.testing.assert_array_equal(yph[:, 1:15, 1:15], yh)
+    assert np.all(yph[:, 0] == 0) and np.all(yph[:, 15] == 0) and np.all(yph[:, :, 0] == 0) and np.all(yph[:, :, 15] == 0)
+    for _ in range(6):
+        assert torch.equal(layer(xd), y)
+    layer.close()
 
 
 @pytest.mark.parametrize("n,c,k", [(1, 128, 128), (1, 256, 256), (3, 64, 64), (5, 48, 128), (64, 128, 128), (131, 48, 192)])
