@@ -261,7 +261,7 @@ conv3x3_direct_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_read<0>();  // the staging buffers have been read; the writes complete with the grid
   }
 #undef WG_DIR_IMG
 

@@ -10,8 +10,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
 python tools/quick.py --ns 256 --one --iters 4 --tag pre-ncu > /dev/null || exit 1
 Q="python tools/quick.py --ns 256 --one --iters 4"
 NCU="ncu --set full --clock-control none --import-source on --launch-count 1 -f"
-$NCU -k regex:wino3x3_ff_kernel --launch-skip 6 -o gpurun_out/prof_ff256_r02 $Q > gpurun_out/ncu_a.log 2>&1; echo "ncu rc=$?"
-$NCU -k regex:wino3x3_ff_kernel --launch-skip 18 -o gpurun_out/prof_ff128_r02 $Q > gpurun_out/ncu_b.log 2>&1; echo "ncu rc=$?"
+$NCU -k regex:conv3x3_direct_kernel --launch-skip 6 -o gpurun_out/prof_dir256_r02 $Q > gpurun_out/ncu_a.log 2>&1; echo "ncu rc=$?"
+$NCU -k regex:conv3x3_direct_kernel --launch-skip 18 -o gpurun_out/prof_dir128_r02 $Q > gpurun_out/ncu_b.log 2>&1; echo "ncu rc=$?"
 $NCU -k regex:conv1x1_bn_act_kernel --launch-skip 6 -o gpurun_out/prof_one_512_128_r02 $Q > gpurun_out/ncu_c.log 2>&1; echo "ncu rc=$?"
 $NCU -k regex:conv1x1_bn_act_kernel --launch-skip 30 -o gpurun_out/prof_one_128_512_r02 $Q > gpurun_out/ncu_d.log 2>&1; echo "ncu rc=$?"
 $NCU -k regex:conv1x1_bn_act_kernel --launch-skip 54 -o gpurun_out/prof_one_1024_256_r02 $Q > gpurun_out/ncu_e.log 2>&1; echo "ncu rc=$?"
