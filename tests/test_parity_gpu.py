@@ -854,4 +854,8 @@ def test_fused_output_allgather_over_nvls_multicast(torch_cuda, n_per_gpu):
     res = json.loads(lines[-1])
     if "unavailable" in res:
         pytest.skip(res["unavailable"])
-    assert r.returncode == 0 and res["ok"] and res["bit_identical_padded0"] and res["bit_identical_padded1"], res
+    assert r.returncode == 0 and res["ok"], res
+    if n_per_gpu < 6:  # both sides run the same (Winograd) kernel: bit-identical; above, the plain launch is the direct engine
+        assert res["bit_identical_padded0"] and res["bit_identical_padded1"], res
+    else:
+        assert res["max_rel_diff_padded0"] <= 1e-3 and res["max_rel_diff_padded1"] <= 1e-3, res

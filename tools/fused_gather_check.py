@@ -48,9 +48,14 @@ def main():
             break
         out = fused(x)
         torch.cuda.synchronize()
+        # The fused path always runs the Winograd kernel (its stores are multimem.st); the plain launch runs the
+        # direct-convolution engine from 6 images on: bit-identical when both are the same kernel, otherwise equal within
+        # the two algorithms' TF32 rounding (each is within 5e-4 of the FP64 oracle).
         same = bool(torch.equal(out, ref))
-        ok = ok and same
+        rel = float((out - ref).abs().max() / ref.abs().max())
+        ok = ok and (same or rel <= 1e-3)
         result[f"bit_identical_padded{int(padded)}"] = same
+        result[f"max_rel_diff_padded{int(padded)}"] = rel
         if padded:
             continue
         # timing: K steps of (kernel -> NCCL all-gather) vs K fused steps (multicast stores + barrier)
