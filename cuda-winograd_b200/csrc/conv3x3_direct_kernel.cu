@@ -28,6 +28,9 @@
 // too: same time per item as CL = 1, it shares the activations, which are the small stream, not the weights.)
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 #include "wg_internal.h"
 
@@ -270,6 +273,286 @@ conv3x3_direct_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---- 16-bit operands (WG_BF16 / WG_FP16): the same direct convolution with kind::f16 MMAs (K = 16, twice the rate).
+// The frame is still fp32 in HBM (the reference's format), so the operand tile is made on the SM: the TMA producer
+// brings a chunk's 64 channels as two fp32 half-chunks (32 channels x 272 rows each) into a two-slot staging ring, four
+// converter warps (10..13) round them to bf16 / fp16 (round to nearest) into a [272 rows][64 channels] 16-bit tile in the
+// SAME K-major 128-byte-swizzled layout a TMA box load would produce (so that the shifted-descriptor trick applies
+// unchanged), and the MMA thread reads tap (dy, dx) from that tile. Weights: [K/128][C/64][9][128 couts][64 ch] 16-bit.
+// The producer keeps the activations one chunk ahead of the weights: staging(c+1) is requested before the nine weight
+// blocks of chunk c, so that the conversion of chunk c+1 runs under the MMAs of chunk c.
+struct Dir16Smem {
+  static constexpr int kSF = 2;  // fp32 staging half-chunks in flight
+  static constexpr int kSO = 2;  // 16-bit operand tiles
+  static constexpr int kSW = 4;  // weight blocks in flight
+  static constexpr int kXRows = DirSmem::kXRows, kXBoxRows = DirSmem::kXBoxRows, kXBoxes = DirSmem::kXBoxes;
+  static constexpr uint32_t kFBytes = kXRows * 128;  // 32 fp32 channels per row
+  static constexpr uint32_t kOBytes = kXRows * 128;  // 64 16-bit channels per row
+  static constexpr uint32_t kWBytes = 128 * 128;     // [128 couts][64 channels] 16-bit
+  static constexpr uint32_t kStageOutBytes = 16 * 128;
+  static constexpr uint32_t kOffF = 0;
+  static constexpr uint32_t kOffO = kOffF + kSF * kFBytes;
+  static constexpr uint32_t kOffW = kOffO + kSO * kOBytes;
+  static constexpr uint32_t kOffOut = kOffW + kSW * kWBytes;  // [8 warps] one staging tile each
+  static constexpr uint32_t kOffZero = kOffOut + 8 * kStageOutBytes;
+  static constexpr uint32_t kOffBar = kOffZero + kStageOutBytes;
+  static constexpr uint32_t kNumBars = 2 * kSF + 2 * kSO + 2 * kSW + 4;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;
+  static_assert(kOffO % 1024 == 0 && kOffW % 1024 == 0 && kOffOut % 1024 == 0, "swizzled buffers: 1024-byte aligned");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+constexpr int kDir16Threads = 32 * 14;  // producer, MMA, 8 epilogue warps, 4 converter warps
+
+template <bool FP16>
+__global__ void __launch_bounds__(kDir16Threads, 1)
+conv3x3_direct16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+                        const uint16_t* __restrict__ w_img, const float* __restrict__ scale,
+                        const float* __restrict__ shift, int n_img, int Cin, int Cout, int relu, int out_padded,
+                        int n_big, int n_items) {
+  using S = Dir16Smem;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* f_full = bars;
+  uint64_t* f_empty = f_full + S::kSF;
+  uint64_t* o_ready = f_empty + S::kSF;
+  uint64_t* o_empty = o_ready + S::kSO;
+  uint64_t* w_full = o_empty + S::kSO;
+  uint64_t* w_empty = w_full + S::kSW;
+  uint64_t* acc_full = w_empty + S::kSW;  // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_y);
+    for (int i = 0; i < S::kSF; ++i) mbar_init(&f_full[i], 1), mbar_init(&f_empty[i], 4);   // 4 converter warps
+    for (int i = 0; i < S::kSO; ++i) mbar_init(&o_ready[i], 4), mbar_init(&o_empty[i], 1);
+    for (int i = 0; i < S::kSW; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  if (warp >= 2 && warp < 10) {  // the all-zero frame row
+    for (uint32_t i = threadIdx.x - 64; i < S::kStageOutBytes / 16; i += 256)
+      reinterpret_cast<uint4*>(smem + S::kOffZero)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_c = Cin / 64;  // 64-channel chunks
+  const int n_cb = Cout / 128;
+  const int first_item = (int)blockIdx.x, item_stride = (int)gridDim.x;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t sf = 0, pf = 0, sw = 0, pw = 0;
+      pdl_wait();  // the frame comes from the previous kernel in the stream
+      // staging of (item, chunk): two half-chunks of 32 fp32 channels
+      auto load_x = [&](int item, int c) {
+        const DirItem w = dir_item(item, n_big, n_cb);
+        const int p0 = min(w.grp, n_img - 1) * 256 + 16 + (w.half > 0 ? kDirN / 2 : 0);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&f_empty[sf], pf ^ 1);
+          mbar_arrive_expect_tx(&f_full[sf], S::kFBytes);
+#pragma unroll
+          for (int b = 0; b < S::kXBoxes; ++b)
+            tma_tensor_2d_g2s(smem + S::kOffF + sf * S::kFBytes + b * (S::kXBoxRows * 128), &tmap_x, c * 64 + h * 32,
+                              p0 - kDirHalo + b * S::kXBoxRows, &f_full[sf]);
+          if (++sf == S::kSF) { sf = 0; pf ^= 1; }
+        }
+      };
+      if (first_item < n_items) load_x(first_item, 0);
+      for (int item = first_item; item < n_items; item += item_stride) {
+        const DirItem w = dir_item(item, n_big, n_cb);
+        const uint8_t* w_src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)w.cb * n_c * 9 * S::kWBytes;
+        for (int c = 0; c < n_c; ++c) {
+          // activations one chunk ahead of the weights
+          if (c + 1 < n_c) load_x(item, c + 1);
+          else if (item + item_stride < n_items) load_x(item + item_stride, 0);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&w_empty[sw], pw ^ 1);
+            mbar_arrive_expect_tx(&w_full[sw], S::kWBytes);
+            tma_bulk_g2s(smem + S::kOffW + sw * S::kWBytes, w_src + (size_t)(c * 9 + t) * S::kWBytes, S::kWBytes,
+                         &w_full[sw]);
+            if (++sw == S::kSW) { sw = 0; pw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t o_base = smem_u32(smem + S::kOffO);
+      const uint32_t w_base = smem_u32(smem + S::kOffW);
+      uint32_t so = 0, po = 0, sw = 0, pw = 0, it = 0;
+      for (int item = first_item; item < n_items; item += item_stride, ++it) {
+        const uint32_t idesc = make_idesc(FP16 ? kFmtF16 : kFmtBF16, 128, item < n_big ? kDirN : kDirN / 2);
+        const uint32_t buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kDirAccCols;
+        for (int c = 0; c < n_c; ++c) {
+          mbar_wait(&o_ready[so], po);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&w_full[sw], pw);
+            tc_fence_after();
+            const int rshift = (t / 3 - 1) * 16 + (t % 3 - 1);
+            const uint32_t x_tap = o_base + so * S::kOBytes + (uint32_t)(kDirHalo + rshift) * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // K = 16 per MMA: 32 bytes of a row
+              const uint64_t a_desc = make_smem_desc(w_base + sw * S::kWBytes + k * 32, 0, 1024, kLayoutSW128);
+              const uint64_t b_desc = make_smem_desc(x_tap + k * 32, 0, 1024, kLayoutSW128);
+              umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&w_empty[sw]);
+            if (++sw == S::kSW) { sw = 0; pw ^= 1; }
+          }
+          umma_commit(&o_empty[so]);
+          if (++so == S::kSO) { so = 0; po ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp >= 10) {
+    // converter warps: fp32 staging half-chunk -> 16-bit operand tile. Unit = (row r, 16-byte output chunk qq): 8 floats
+    // from the two swizzled 16-byte chunks 2qq, 2qq+1 of staging row r -> chunk (4h + qq) ^ (r & 7) of tile row r.
+    const int ct = threadIdx.x - 320;
+    uint32_t sf = 0, pf = 0, so = 0, po = 0;
+    const uint32_t f_base = smem_u32(smem + S::kOffF), o_base = smem_u32(smem + S::kOffO);
+    for (int item = first_item; item < n_items; item += item_stride)
+      for (int c = 0; c < n_c; ++c) {
+        mbar_wait(&o_empty[so], po ^ 1);
+        tc_fence_after();
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&f_full[sf], pf);
+          const uint32_t src = f_base + sf * S::kFBytes, dst = o_base + so * S::kOBytes;
+#pragma unroll 2
+          for (int u = ct; u < S::kXRows * 4; u += 128) {
+            const int r = u >> 2, qq = u & 3, sw7 = r & 7;
+            const float4 a = ld_shared_v4(src + r * 128 + (((2 * qq) ^ sw7) << 4));
+            const float4 b = ld_shared_v4(src + r * 128 + (((2 * qq + 1) ^ sw7) << 4));
+            uint32_t p0, p1, p2, p3;
+            if constexpr (FP16) {
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(a.y), "f"(a.x));
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(a.w), "f"(a.z));
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b.y), "f"(b.x));
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b.w), "f"(b.z));
+            } else {
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(a.y), "f"(a.x));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(a.w), "f"(a.z));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b.y), "f"(b.x));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b.w), "f"(b.z));
+            }
+            st_shared_v4(dst + r * 128 + (((4 * h + qq) ^ sw7) << 4), __uint_as_float(p0), __uint_as_float(p1),
+                         __uint_as_float(p2), __uint_as_float(p3));
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&f_empty[sf]);  // this warp is done reading the staging slot
+          if (++sf == S::kSF) { sf = 0; pf ^= 1; }
+        }
+        fence_proxy_async_smem();  // the tile was written by the generic proxy, the MMA reads it through the async proxy
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_ready[so]);
+        if (++so == S::kSO) { so = 0; po ^= 1; }
+      }
+  } else {
+    // epilogue: as in the TF32 kernel, one staging tile per warp
+    const int ew = warp - 2;
+    const int quad = warp & 3, hsel = ew >> 2;
+    uint8_t* stage_out = smem + S::kOffOut + ew * S::kStageOutBytes;
+    const uint32_t stage_u32 = smem_u32(stage_out);
+    uint32_t it = 0;
+    for (int item = first_item; item < n_items; item += item_stride, ++it) {
+      const DirItem w = dir_item(item, n_big, n_cb);
+      const int img = min(w.grp, n_img - 1);
+      const uint32_t buf = it & 1;
+      const int cout0 = w.cb * 128 + quad * 32;
+      const float sc = __ldg(scale + cout0 + lane), sh = __ldg(shift + cout0 + lane);
+      const int rows = w.half < 0 ? 14 : 7;
+      const int y_first = 1 + (w.half > 0 ? 7 : 0);
+      const int j0 = hsel ? (rows + 1) / 2 : 0, j1 = hsel ? rows : (rows + 1) / 2;
+      if (out_padded == 1 && lane == 0) {
+        if (hsel == 0 && w.half <= 0) {
+          tma_tensor_2d_s2g(&tmap_y, smem + S::kOffZero, cout0, img * 256);
+          tma_store_commit();
+        }
+        if (hsel == 1 && w.half != 0) {
+          tma_tensor_2d_s2g(&tmap_y, smem + S::kOffZero, cout0, img * 256 + 15 * 16);
+          tma_store_commit();
+        }
+      }
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kDirAccCols;
+#pragma unroll 1
+      for (int j = j0; j < j1; ++j) {
+        float v[16];
+        tmem_ld_x16(taddr + j * 16, v);
+        if (lane == 0) tma_store_wait_read<0>();  // the previous row's store has read the staging tile
+        __syncwarp();
+        tmem_ld_wait();
+        const uint32_t dst = stage_u32 + lane * 4;
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          float o = fmaf(sc, v[x], sh);
+          if (relu) o = fmaxf(o, 0.f);
+          if (x == 0 || x == 15) o = 0.f;
+          st_shared_f32(dst + x * 128, o);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int yy = y_first + j;
+          if (out_padded) tma_tensor_2d_s2g(&tmap_y, stage_out, cout0, img * 256 + yy * 16);
+          else tma_tensor_2d_s2g(&tmap_y, stage_out + 128, cout0, img * 196 + (yy - 1) * 14);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// Once per layer, 16-bit operands: [K/128][C/64][9 taps][128 couts][64 channels], RN, 128-byte swizzle applied
+// (16-byte chunk q = 8 channels at position q ^ (cout & 7) of the cout's 128-byte row).
+__global__ void direct_pack16_kernel(const float* __restrict__ w, uint16_t* __restrict__ w_img, int Cin, int Cout,
+                                     int fp16) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cin * Cout * 9) return;
+  const int t = idx % 9;
+  const int ci = (idx / 9) % Cin;
+  const int co = idx / (9 * Cin);
+  const int nt = co / 128, r = co % 128;
+  const int c = ci / 64, kk = ci % 64;
+  const int q = (kk >> 3) ^ (r & 7);
+  const size_t blk = ((size_t)nt * (Cin / 64) + c) * 9 + t;
+  uint16_t bits;
+  if (fp16) {
+    const __half hv = __float2half_rn(w[idx]);
+    bits = *reinterpret_cast<const uint16_t*>(&hv);
+  } else {
+    const __nv_bfloat16 bv = __float2bfloat16_rn(w[idx]);
+    bits = *reinterpret_cast<const uint16_t*>(&bv);
+  }
+  w_img[blk * (size_t)(128 * 64) + (size_t)r * 64 + q * 8 + (kk & 7)] = bits;
+}
+
 // Once per layer: w[K][C][3][3] (the reference's filter layout, Kernel128_winograd.cu:274-281 reads it the same way)
 // -> per (128-cout block, 32-channel chunk, tap) the K-major 128-byte-swizzled block [128 couts][32 channels], RN-rounded
 // to TF32.
@@ -286,9 +569,12 @@ __global__ void direct_pack_kernel(const float* __restrict__ w, float* __restric
   w_img[blk * (size_t)(128 * 32) + (size_t)r * 32 + q * 4 + (kk & 3)] = to_tf32_rn(w[idx]);
 }
 
-int direct_pack_launch(const float* w, float* w_img, int Cin, int Cout, cudaStream_t stream) {
+// op16: 0 = TF32 image (fp32 words), 1 = bf16, 2 = fp16
+int direct_pack_launch(const float* w, float* w_img, int Cin, int Cout, int op16, cudaStream_t stream) {
   const int n = Cin * Cout * 9;
-  direct_pack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, w_img, Cin, Cout);
+  if (op16) direct_pack16_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, reinterpret_cast<uint16_t*>(w_img), Cin, Cout,
+                                                                    op16 == 2);
+  else direct_pack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, w_img, Cin, Cout);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
@@ -368,6 +654,62 @@ static int launch_direct(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, c
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
+template <bool FP16>
+static int launch_direct16(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
+                           const float* shift, int n_img, int Cin, int Cout, int relu, int out_padded, int max_ctas,
+                           bool mixed, cudaStream_t stream) {
+  using S = Dir16Smem;
+  static unsigned long long configured = 0;
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long bit = 1ull << (dev_ & 63);
+  if (!(configured & bit)) {
+    if (cudaFuncSetAttribute(conv3x3_direct16_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)S::kTotal) != cudaSuccess)
+      return WG_ERR_CUDA;
+    configured |= bit;
+  }
+  const int n_cb = Cout / 128;
+  long long n_ctas = max_ctas < 1 ? 1 : max_ctas;
+  long long n_big = (long long)n_img * n_cb;
+  if (mixed) {
+    const long long per_round = n_ctas / n_cb;
+    if (per_round > 0) {
+      const long long whole = ((long long)n_img / per_round) * per_round;
+      const long long rest = n_img - whole;
+      if (rest > 0 && rest * 2 * n_cb <= n_ctas) n_big = whole * n_cb;
+    }
+  }
+  const long long n_items = n_big + ((long long)n_img * n_cb - n_big) * 2;
+  if (n_ctas > n_items) n_ctas = n_items;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_ctas);
+  cfg.blockDim = dim3(kDir16Threads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_direct16_kernel<FP16>, tmap_x, tmap_y,
+                                     reinterpret_cast<const uint16_t*>(w_img), scale, shift, n_img, Cin, Cout, relu,
+                                     out_padded, (int)n_big, (int)n_items);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+// 16-bit operands (op16: 1 = bf16, 2 = fp16): Cin % 64 == 0, Cout % 128 == 0
+int direct16_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
+                    const float* shift, int n_img, int Cin, int Cout, int op16, int relu, int out_padded, int max_ctas,
+                    int mixed, cudaStream_t stream) {
+  if (Cin % 64 != 0 || Cout % 128 != 0 || (op16 != 1 && op16 != 2)) return WG_ERR_ARG;
+  if (op16 == 2)
+    return launch_direct16<true>(tmap_x, tmap_y, w_img, scale, shift, n_img, Cin, Cout, relu, out_padded, max_ctas,
+                                 mixed != 0, stream);
+  return launch_direct16<false>(tmap_x, tmap_y, w_img, scale, shift, n_img, Cin, Cout, relu, out_padded, max_ctas,
+                                mixed != 0, stream);
+}
+
 // out_padded: 0 = dense map, 1 = frame with its zero border, 3 = frame, interior rows only (WG_OUT_INTERIOR_ONLY)
 int direct_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
                   const float* shift, int n_img, int Cin, int Cout, int cl, int relu, int out_padded, int max_ctas,
@@ -386,8 +728,8 @@ int direct_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const fl
 
 #ifdef WG_DEV_BUILD
 // developer entry points: the direct kernel on caller-owned device buffers (tools/direct_check.py)
-extern "C" int wg_dev_direct_pack(const float* w_dev, float* w_img_dev, int cin, int cout) {
-  int rc = wg::direct_pack_launch(w_dev, w_img_dev, cin, cout, nullptr);
+extern "C" int wg_dev_direct_pack(const float* w_dev, float* w_img_dev, int cin, int cout, int op16) {
+  int rc = wg::direct_pack_launch(w_dev, w_img_dev, cin, cout, op16, nullptr);
   return cudaDeviceSynchronize() == cudaSuccess ? rc : WG_ERR_CUDA;
 }
 // mode: low 3 bits = cluster size (1, 2, 4), bit 3 = no mixed schedule
@@ -399,6 +741,9 @@ extern "C" int wg_dev_direct_run(const float* x_dev, const float* w_img_dev, con
   if (rc != WG_OK) return rc;
   rc = wg::direct_make_tmap_out(&ty, y_dev, n_img, cout, out_padded);
   if (rc != WG_OK) return rc;
+  if (mode & 0x300)  // bits 8 / 9: bf16 / fp16 operands
+    return wg::direct16_launch(tx, ty, w_img_dev, scale_dev, shift_dev, n_img, cin, cout, (mode & 0x200) ? 2 : 1, relu,
+                               out_padded, max_ctas, (mode & 8) ? 0 : 1, static_cast<cudaStream_t>(stream));
   return wg::direct_launch(tx, ty, w_img_dev, scale_dev, shift_dev, n_img, cin, cout, mode & 7, relu, out_padded,
                            max_ctas, (mode & 8) ? 0 : 1, static_cast<cudaStream_t>(stream));
 }

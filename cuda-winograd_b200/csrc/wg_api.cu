@@ -160,7 +160,7 @@ struct wg_layer {
   float* d_filter_tm16 = nullptr;      // 3x3 bf16/fp16: U in the 16-bit image of the V-in-TMEM throughput kernel
   float* d_filter_tm16_n64 = nullptr;  // the same with all slices 64 wide
   float* d_filter_small = nullptr;     // 3x3 TF32: U in the plain KN=32 image of the small-batch kernel (may alias d_filter)
-  float* d_filter_direct = nullptr;    // 3x3 TF32, 14x14: per-tap weight blocks of the direct-convolution kernel, or null
+  float* d_filter_direct = nullptr;    // 3x3, 14x14: per-tap weight blocks of the direct-convolution kernel (TF32 or 16-bit), or null
   float* d_scale = nullptr;
   float* d_shift = nullptr;
   size_t img_bytes[kNumImgs] = {0, 0, 0, 0, 0, 0};
@@ -217,8 +217,9 @@ static void layer_plan(wg_layer* L) {
     // the small-batch kernel (and its plain KN=32 image) exists for the reference's 14x14 geometry only
     L->img_bytes[4] = (L->dtype == WG_TF32 && L->tile_n != 32 && ff::geo_is_ref(L->geo)) ? fe * 4 : 0;  // tile_n == 32: aliases d_filter
     // the direct-convolution kernel: TF32, reference geometry, 32-channel chunks, 128-cout blocks
-    L->img_bytes[5] = (L->dtype == WG_TF32 && ff::geo_is_ref(L->geo) && L->cin % 32 == 0 && L->cout % 128 == 0)
-                          ? (size_t)9 * L->cin * L->cout * 4 : 0;
+    // (16-bit operands: 64-channel chunks, 2-byte elements)
+    const bool dir_ok = ff::geo_is_ref(L->geo) && L->cout % 128 == 0 && L->cin % (L->dtype == WG_TF32 ? 32 : 64) == 0;
+    L->img_bytes[5] = dir_ok ? (size_t)9 * L->cin * L->cout * (L->dtype == WG_TF32 ? 4 : 2) : 0;
   } else {
     L->tile_n = (L->cout % 256 == 0 && L->dtype == WG_TF32) ? 256 : 128;  // bf16 operands: 128-wide N-tiles
     L->img_bytes[0] = (size_t)L->cin * L->cout * (L->dtype == WG_TF32 ? 4 : 2);
@@ -292,7 +293,7 @@ static int layer_pack(wg_layer* L, const float* d_w) {
     count();
   }
   if (rc == WG_OK && L->img_bytes[5]) {
-    rc = direct_pack_launch(d_w, L->d_filter_direct, cin, cout, L->stream);
+    rc = direct_pack_launch(d_w, L->d_filter_direct, cin, cout, op16, L->stream);
     count();
   }
   return rc;
@@ -425,14 +426,17 @@ static uint64_t fnv1a(const uint8_t* p, size_t n) {
 // 3x3, TF32, reference geometry: batch size from which the direct-convolution kernel is used (below it the split-C
 // Winograd latency kernels win: their channel loop is divided over a cluster). WG_3X3_DIRECT_MIN (developer build)
 // overrides; a huge value keeps every batch on the Winograd kernels.
-static int direct_min_batch(int cin) {
+static int direct_min_batch(int cin, int dtype) {
   static int env = -2;
   if (env == -2) {
     const char* e = dev_env("WG_3X3_DIRECT_MIN");
     env = e ? atoi(e) : -1;
   }
   if (env >= 0) return env;
-  return cin >= 256 ? 6 : 11;  // measured cross-over with the split-C latency kernel (profiles/direct3x3_r02.md)
+  // measured cross-overs with the split-C latency kernels (profiles/direct3x3_r02.md); 16-bit operands: the direct
+  // kernel ties at N = 1..2 and wins from there on
+  if (dtype != WG_TF32) return 3;
+  return cin >= 256 ? 6 : 11;
 }
 
 static int run_impl(wg_layer_t* L, const float* x, const float* residual, float* y, int N, int flags,
@@ -469,7 +473,7 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
   const long long px = (long long)L->H * L->W;  // 1x1: GEMM rows per image
   // map sizes other than the reference's run the full-fold kernel only (developer build: not with a superseded generation)
   if (L->kind == 0 && !ref_geo && !(L->dtype == WG_TF32 ? L->tile_n == 96 : L->tm16_ff != 0)) return WG_ERR_ARG;
-  if (L->kind == 0 && L->d_filter_direct != nullptr && !(out_flags & 2) && N >= direct_min_batch(L->cin)) {
+  if (L->kind == 0 && L->d_filter_direct != nullptr && !(out_flags & 2) && N >= direct_min_batch(L->cin, L->dtype)) {
     // throughput-sized batches of the reference geometry: direct convolution on the tensor core (no CUDA-core transform;
     // measured faster than the fused Winograd pipeline from a handful of images on, see conv3x3_direct_kernel.cu)
     {
@@ -481,6 +485,9 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
         });
     }
     if (rc != WG_OK) return rc;
+    if (L->dtype != WG_TF32)
+      return launched(direct16_launch(tmap, tmap_y, L->d_filter_direct, L->d_scale, L->d_shift, N, L->cin, L->cout,
+                                      L->dtype == WG_FP16 ? 2 : 1, L->relu, out_padded, max_ctas, 1, stream));
     return launched(direct_launch(tmap, tmap_y, L->d_filter_direct, L->d_scale, L->d_shift, N, L->cin, L->cout, 1,
                                   L->relu, out_padded, max_ctas, 1, stream));
   }

@@ -93,7 +93,11 @@ int wino_small_launch(const CUtensorMap& tmap_small, const float* u_plain, const
 
 // ---- 3x3 as a direct convolution on the tensor core (conv3x3_direct_kernel.cu): TF32, the reference's 14x14 map in its
 // 16x16 frame, Cin % 32 == 0, Cout % 128 == 0. Weight image: [Cout/128][Cin/32][9 taps][128 couts][32 channels].
-int direct_pack_launch(const float* w_kcrs, float* w_img, int Cin, int Cout, cudaStream_t stream);
+// op16: 0 = TF32, 1 = bf16, 2 = fp16 ([K/128][C/64][9][128][64] 16-bit; needs Cin % 64 == 0)
+int direct_pack_launch(const float* w_kcrs, float* w_img, int Cin, int Cout, int op16, cudaStream_t stream);
+int direct16_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
+                    const float* shift, int n_img, int Cin, int Cout, int op16, int relu, int out_padded, int max_ctas,
+                    int mixed, cudaStream_t stream);
 int direct_make_tmap_in(CUtensorMap* tmap, const float* x, int n_img, int Cin);
 int direct_make_tmap_out(CUtensorMap* tmap, const float* y, int n_img, int Cout, int out_padded);
 // cl = cluster size (weight multicast), out_padded: 0 dense, 1 frame with its zero border; mixed = half-image tail items

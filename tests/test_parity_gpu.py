@@ -142,7 +142,8 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, n, c, k):
                                    (149, 256, 128), (160, 96, 128)])
 @pytest.mark.parametrize("relu", [True, False])
 def test_3x3_direct_convolution_engine(lib_loaded, torch_cuda, n, c, k, relu):
-    """conv3x3_direct_kernel.cu (TF32, 14x14, Cin % 32 == 0, Cout % 128 == 0, from 6 / 11 images on): every tap is a
+    """conv3x3_direct_kernel.cu (14x14, Cin % 32 == 0 (16-bit operands: 64), Cout % 128 == 0; TF32 from 6 / 11 images
+    on, bf16 / fp16 operands from 3): every tap is a
     shifted shared-memory descriptor of one activation box. Batches that make whole-image items only, half-image items
     only (n * k / 128 * 2 <= #SMs) and the mixed schedule (whole rounds + a half-image tail); first and last image (their
     halo rows lie outside the tensor: TMA zero fill); dense output and frame bit-identical, frame border exactly zero;
@@ -151,21 +152,26 @@ def test_3x3_direct_convolution_engine(lib_loaded, torch_cuda, n, c, k, relu):
     x, w, sc, sh = _rand3x3(np.random.RandomState(1700 + n + c + k), n, c, k)
     gold = golden.conv3x3_bn_relu(x, w, sc, sh, relu)
     xd = torch.from_numpy(x).cuda()
-    layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=relu)
-    y = torch.full((n, 14, 14, k), float("nan"), device="cuda")
-    yp = torch.full((n, 16, 16, k), float("nan"), device="cuda")
-    layer(xd, out=y)
-    layer(xd, out=yp, out_padded=True)
-    yh, yph = y.cpu().numpy(), yp.cpu().numpy()
-    assert np.isfinite(yh).all() and np.isfinite(yph).all()
-    assert golden.rel_err(yh, gold) <= TOL_TF32
-    per_image = np.abs(yh - gold).reshape(n, -1).max(axis=1) / np.abs(gold).max()
-    assert per_image.max() <= TOL_TF32, int(per_image.argmax())
-    np.testing.assert_array_equal(yph[:, 1:15, 1:15], yh)
-    assert np.all(yph[:, 0] == 0) and np.all(yph[:, 15] == 0) and np.all(yph[:, :, 0] == 0) and np.all(yph[:, :, 15] == 0)
-    for _ in range(6):
-        assert torch.equal(layer(xd), y)
-    layer.close()
+    # 16-bit operands (Cin % 64 == 0): the same kernel structure with kind::f16 MMAs; four converter warps round the fp32
+    # frame to bf16 / fp16 into the swizzled operand tile (conv3x3_direct16_kernel)
+    for dt, tol in ((lib_loaded.WG_TF32, TOL_TF32), (lib_loaded.WG_BF16, TOL_BF16), (lib_loaded.WG_FP16, TOL_TF32)):
+        if dt != lib_loaded.WG_TF32 and c % 64:
+            continue
+        layer = lib_loaded.Conv3x3BnRelu(w, sc, sh, relu=relu, dtype=dt)
+        y = torch.full((n, 14, 14, k), float("nan"), device="cuda")
+        yp = torch.full((n, 16, 16, k), float("nan"), device="cuda")
+        layer(xd, out=y)
+        layer(xd, out=yp, out_padded=True)
+        yh, yph = y.cpu().numpy(), yp.cpu().numpy()
+        assert np.isfinite(yh).all() and np.isfinite(yph).all()
+        assert golden.rel_err(yh, gold) <= tol
+        per_image = np.abs(yh - gold).reshape(n, -1).max(axis=1) / np.abs(gold).max()
+        assert per_image.max() <= tol, int(per_image.argmax())
+        np.testing.assert_array_equal(yph[:, 1:15, 1:15], yh)
+        assert np.all(yph[:, 0] == 0) and np.all(yph[:, 15] == 0) and np.all(yph[:, :, 0] == 0) and np.all(yph[:, :, 15] == 0)
+        for _ in range(6):
+            assert torch.equal(layer(xd), y)
+        layer.close()
 
 
 @pytest.mark.parametrize("n,c,k", [(1, 128, 128), (1, 256, 256), (3, 64, 64), (5, 48, 128), (64, 128, 128), (131, 48, 192)])

@@ -19,13 +19,14 @@ def main():
     ap.add_argument("--bo", default="1,2,4", help="mode: cluster size 1 / 2 / 4, + 8 = no mixed schedule")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--shapes", default="256x256,128x128")
+    ap.add_argument("--op16", default="0", help="operand types: 0 = TF32, 1 = bf16, 2 = fp16")
     args = ap.parse_args()
     import numpy as np
     import torch
     import golden
     L = ctypes.CDLL(os.path.join(ROOT, "tools", "libwinograd_b200_dev.so"))
     vp = ctypes.c_void_p
-    L.wg_dev_direct_pack.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    L.wg_dev_direct_pack.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.wg_dev_direct_run.argtypes = [vp] * 5 + [ctypes.c_int] * 7 + [vp]
     dev = torch.device("cuda", 0)
     for shape in args.shapes.split(","):
@@ -36,9 +37,11 @@ def main():
         wd = torch.from_numpy(w).to(dev)
         scd = torch.from_numpy(np.asarray(sc, np.float32)).to(dev)
         shd = torch.from_numpy(np.asarray(sh, np.float32)).to(dev)
-        for bn in [128]:
+        for op16 in [int(v) for v in args.op16.split(",")]:
+            if op16 and c % 64:
+                continue
             img = torch.zeros(9 * c * k, device=dev)
-            assert L.wg_dev_direct_pack(wd.data_ptr(), img.data_ptr(), c, k) == 0
+            assert L.wg_dev_direct_pack(wd.data_ptr(), img.data_ptr(), c, k, op16) == 0
             for n in [int(v) for v in args.ns.split(",")]:
                 x = np.zeros((n, 16, 16, c), np.float32)
                 x[:, 1:15, 1:15] = rs.rand(n, 14, 14, c) - 0.5
@@ -46,7 +49,9 @@ def main():
                 gold = golden.conv3x3_bn_relu(x[sample], w, sc, sh, True)
                 sets = 4 if n >= 64 else 1
                 xs = [torch.from_numpy(x).to(dev) for _ in range(sets)]
-                for bo in [int(v) for v in args.bo.split(",")]:
+                for bo in [int(v) | (op16 << 8) for v in args.bo.split(",")]:
+                    if op16 and (bo & 7) != 1:
+                        continue
                     for padded in (0, 1):
                         ys = [torch.full((n, 16, 16, k) if padded else (n, 14, 14, k), float("nan"), device=dev)
                               for _ in range(sets)]
