@@ -273,6 +273,251 @@ conv3x3_direct_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---- Other map sizes (wg_conv3x3_create_hw: 56x56, 28x28, 7x7 ...; TF32): the same direct convolution with the
+// geometry as launch parameters. The frame [N][Hf][Wf][C] is still one flat sequence of pixel rows, tap (dy, dx) is a
+// shift by (dy-1)*Wf + (dx-1), and a work item is a contiguous range of that sequence: R frame rows of one image
+// (R*Wf <= 256: 28x28 -> 8 rows, 56x56 -> 4) or, for small maps, G whole images (7x7: two 10x10 frames per item). Pixels of
+// the range that are border / padding / beyond the batch are computed and not stored (dense output) or stored as the
+// zeros the next layer's frame needs. Output pixels are not affine in the range index here, so the epilogue writes with
+// plain 128-byte row stores (8 lanes x 16 B per pixel) through a per-warp table of destinations.
+// DirGeo (wg_internal.h): R, bands, G: item = R frame rows of one image (bands per image), or G images (bands == 1);
+// n_pad = MMA N (pixels of an item rounded up to 16); halo = rows loaded in front of / behind the range (>= Wf + 1,
+// multiple of 8); the activation stage is n_boxes TMA boxes of box_rows rows.
+struct DirGenSmem {
+  static constexpr int kSX = 2, kSW = 5;
+  static constexpr int kXRowsMax = 384;
+  static constexpr uint32_t kXBytes = kXRowsMax * 128;
+  static constexpr uint32_t kWBytes = 128 * 128;
+  static constexpr uint32_t kStageOutBytes = 16 * 128;
+  static constexpr uint32_t kOffX = 0;
+  static constexpr uint32_t kOffW = kOffX + kSX * kXBytes;
+  static constexpr uint32_t kOffOut = kOffW + kSW * kWBytes;   // [8 warps] one staging tile each
+  static constexpr uint32_t kOffTab = kOffOut + 8 * kStageOutBytes;  // [8 warps][128] destination per column
+  static constexpr uint32_t kOffBar = kOffTab + 8 * 128 * 4;
+  static constexpr uint32_t kNumBars = 2 * kSX + 2 * kSW + 4;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;
+  static_assert(kOffW % 1024 == 0 && kOffOut % 1024 == 0, "swizzled buffers must be 1024-byte aligned");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(kDirThreads, 1)
+conv3x3_direct_gen_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w_img,
+                          const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
+                          int n_img, int Cin, int Cout, int relu, int out_padded, int n_items, const DirGeo g) {
+  using S = DirGenSmem;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = x_full + S::kSX;
+  uint64_t* w_full = x_empty + S::kSX;
+  uint64_t* w_empty = w_full + S::kSW;
+  uint64_t* acc_full = w_empty + S::kSW;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < S::kSX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 1);
+    for (int i = 0; i < S::kSW; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_c = Cin / 32;
+  const int n_cb = Cout / 128;
+  const int frame = g.Hf * g.Wf;
+  const int first_item = (int)blockIdx.x, item_stride = (int)gridDim.x;
+  // item -> (cout block, first image, first frame row of the range)
+#define WG_GEN_ITEM(item, cb_, img0_, y0_)            \
+  const int cb_ = (item) % n_cb;                      \
+  const int u_##cb_ = (item) / n_cb;                  \
+  const int img0_ = (u_##cb_ / g.bands) * g.G;        \
+  const int y0_ = 1 + (u_##cb_ % g.bands) * g.R
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t sx = 0, px = 0, sw = 0, pw = 0;
+      const uint32_t x_bytes = (uint32_t)(g.n_boxes * g.box_rows) * 128;
+      pdl_wait();
+      for (int item = first_item; item < n_items; item += item_stride) {
+        WG_GEN_ITEM(item, cb, img0, y0);
+        const int p0 = img0 * frame + y0 * g.Wf;
+        const uint8_t* w_src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)cb * n_c * 9 * S::kWBytes;
+        for (int c = 0; c < n_c; ++c) {
+          mbar_wait(&x_empty[sx], px ^ 1);
+          mbar_arrive_expect_tx(&x_full[sx], x_bytes);
+          for (int b = 0; b < g.n_boxes; ++b)
+            tma_tensor_2d_g2s(smem + S::kOffX + sx * S::kXBytes + b * (g.box_rows * 128), &tmap_x, c * 32,
+                              p0 - g.halo + b * g.box_rows, &x_full[sx]);
+          if (++sx == S::kSX) { sx = 0; px ^= 1; }
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&w_empty[sw], pw ^ 1);
+            mbar_arrive_expect_tx(&w_full[sw], S::kWBytes);
+            tma_bulk_g2s(smem + S::kOffW + sw * S::kWBytes, w_src + (size_t)(c * 9 + t) * S::kWBytes, S::kWBytes,
+                         &w_full[sw]);
+            if (++sw == S::kSW) { sw = 0; pw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t x_base = smem_u32(smem + S::kOffX);
+      const uint32_t w_base = smem_u32(smem + S::kOffW);
+      const uint32_t idesc = make_idesc(kFmtTF32, 128, (uint32_t)g.n_pad);
+      uint32_t sx = 0, px = 0, sw = 0, pw = 0, it = 0;
+      for (int item = first_item; item < n_items; item += item_stride, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kDirAccCols;
+        for (int c = 0; c < n_c; ++c) {
+          mbar_wait(&x_full[sx], px);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&w_full[sw], pw);
+            tc_fence_after();
+            const int rshift = (t / 3 - 1) * g.Wf + (t % 3 - 1);
+            const uint32_t x_tap = x_base + sx * S::kXBytes + (uint32_t)(g.halo + rshift) * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a_desc = make_smem_desc(w_base + sw * S::kWBytes + k * 32, 0, 1024, kLayoutSW128);
+              const uint64_t b_desc = make_smem_desc(x_tap + k * 32, 0, 1024, kLayoutSW128);
+              umma_tf32_ss(d_tmem, a_desc, b_desc, idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&w_empty[sw]);
+            if (++sw == S::kSW) { sw = 0; pw ^= 1; }
+          }
+          umma_commit(&x_empty[sx]);
+          if (++sx == S::kSX) { sx = 0; px ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3, hsel = ew >> 2;
+    const uint32_t stage_u32 = smem_u32(smem + S::kOffOut + ew * S::kStageOutBytes);
+    int* tab = reinterpret_cast<int*>(smem + S::kOffTab) + ew * 128;
+    const int n_chunks = g.n_pad / 16;
+    const int j0 = hsel ? (n_chunks + 1) / 2 : 0, j1 = hsel ? n_chunks : (n_chunks + 1) / 2;
+    const int sub = lane & 7, pxs = lane >> 3;  // store phase: 16-byte piece of a pixel's 128 bytes, pixel of a group of 4
+    uint32_t it = 0;
+    for (int item = first_item; item < n_items; item += item_stride, ++it) {
+      WG_GEN_ITEM(item, cb, img0, y0);
+      const uint32_t buf = it & 1;
+      const int cout0 = cb * 128 + quad * 32;
+      const float sc = __ldg(scale + cout0 + lane), sh = __ldg(shift + cout0 + lane);
+      // destinations of this warp's columns: entry = (output pixel index << 1) | store-zero, or -1 = no store
+      for (int j = j0 * 16 + lane; j < j1 * 16; j += 32) {
+        const int q = y0 * g.Wf + j;
+        const int img = img0 + q / frame, rem = q % frame, fy = rem / g.Wf, fx = rem % g.Wf;
+        const bool in_batch = img < n_img;
+        const bool interior = fy >= 1 && fy <= g.H && fx >= 1 && fx <= g.W;
+        int e = -1;
+        if (in_batch && out_padded) e = ((img * frame + rem) << 1) | (interior ? 0 : 1);
+        else if (in_batch && interior) e = ((img * g.H + fy - 1) * g.W + fx - 1) << 1;
+        tab[j - j0 * 16] = e;
+      }
+      if (out_padded) {
+        // frame rows no item range covers: row 0 of the first image of the range (hsel 0) and what lies behind the last
+        // covered row of its last image (hsel 1); zeros, this warp's 32 couts
+        const int band = ((item / n_cb) % g.bands);
+        const int rows_cov = (g.bands == 1) ? g.n_pad / g.Wf : g.R;  // whole frame rows of the range, from its first row
+        int zimg = -1, zy0 = 0, zy1 = 0;
+        if (hsel == 0 && band == 0) zimg = img0, zy0 = 0, zy1 = 1;
+        if (hsel == 1 && band == g.bands - 1) {
+          const int last = img0 + g.G - 1;
+          const int covered_to = (g.bands == 1) ? (1 + rows_cov - (g.G - 1) * g.Hf) : (y0 + rows_cov);  // first row not covered
+          zimg = last < n_img ? last : -1, zy0 = covered_to > g.H + 1 ? covered_to : g.H + 1, zy1 = g.Hf;
+        }
+        if (zimg >= 0 && zimg < n_img)
+          for (int pz = zy0 * g.Wf + pxs; pz < zy1 * g.Wf; pz += 4)
+            *reinterpret_cast<float4*>(y + ((size_t)zimg * frame + pz) * Cout + cout0 + sub * 4) =
+                make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kDirAccCols;
+#pragma unroll 1
+      for (int j = j0; j < j1; ++j) {
+        float v[16];
+        tmem_ld_x16(taddr + j * 16, v);
+        tmem_ld_wait();
+        const uint32_t dst = stage_u32 + lane * 4;
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          float o = fmaf(sc, v[x], sh);
+          if (relu) o = fmaxf(o, 0.f);
+          st_shared_f32(dst + x * 128, o);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int pxl = i4 * 4 + pxs;
+          const int e = tab[(j - j0) * 16 + pxl];
+          if (e >= 0) {
+            float4 val = ld_shared_v4(stage_u32 + pxl * 128 + sub * 16);
+            if (e & 1) val = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(y + (size_t)(e >> 1) * Cout + cout0 + sub * 4) = val;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+#undef WG_GEN_ITEM
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// geometry of the direct kernel for an H x W map in its Hf x Wf frame; false = not supported (the Winograd kernel runs)
+bool direct_gen_geo(int H, int W, int Hf, int Wf, DirGeo* out) {
+  DirGeo g{};
+  g.H = H, g.W = W, g.Hf = Hf, g.Wf = Wf;
+  g.halo = ((Wf + 1) + 7) / 8 * 8;
+  const int frame = Hf * Wf;
+  if (Wf > 128) return false;
+  int n_px;
+  if (frame + H * Wf <= 256) {  // at least two whole images per item
+    g.bands = 1;
+    g.G = (256 - H * Wf) / frame + 1;
+    g.R = 0;
+    n_px = (g.G - 1) * frame + H * Wf;
+  } else {
+    g.G = 1;
+    g.R = 256 / Wf;
+    if (g.R > H) g.R = H;
+    if (g.R < 1) return false;
+    g.bands = (H + g.R - 1) / g.R;
+    n_px = g.R * Wf;
+  }
+  g.n_pad = (n_px + 15) / 16 * 16;
+  const int rows = g.n_pad + 2 * g.halo;
+  if (g.n_pad > 256 || rows > DirGenSmem::kXRowsMax) return false;
+  g.n_boxes = (rows + 255) / 256;
+  g.box_rows = ((rows + g.n_boxes - 1) / g.n_boxes + 7) / 8 * 8;  // multiple of 8 rows: every box 1024-byte aligned
+  if (g.n_boxes * g.box_rows > DirGenSmem::kXRowsMax) return false;
+  *out = g;
+  return true;
+}
+
 // ---- 16-bit operands (WG_BF16 / WG_FP16): the same direct convolution with kind::f16 MMAs (K = 16, twice the rate).
 // The frame is still fp32 in HBM (the reference's format), so the operand tile is made on the SM: the TMA producer
 // brings a chunk's 64 channels as two fp32 half-chunks (32 channels x 272 rows each) into a two-slot staging ring, four
@@ -601,6 +846,44 @@ int direct_make_tmap_in(CUtensorMap* tmap, const float* x, int n_img, int Cin) {
 int direct_make_tmap_out(CUtensorMap* tmap, const float* y, int n_img, int Cout, int out_padded) {
   return dir_encode(tmap, y, Cout, (long long)n_img * (out_padded ? 256 : 196), 32, out_padded ? 16 : 14,
                     CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+int direct_gen_make_tmap_in(CUtensorMap* tmap, const float* x, int n_img, int Cin, const DirGeo& g) {
+  return dir_encode(tmap, x, Cin, (long long)n_img * g.Hf * g.Wf, 32, g.box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int direct_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float* scale, const float* shift, float* y,
+                      int n_img, int Cin, int Cout, int relu, int out_padded, int max_ctas, const DirGeo& g,
+                      cudaStream_t stream) {
+  using S = DirGenSmem;
+  if (Cin % 32 != 0 || Cout % 128 != 0) return WG_ERR_ARG;
+  static unsigned long long configured = 0;
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long bit = 1ull << (dev_ & 63);
+  if (!(configured & bit)) {
+    if (cudaFuncSetAttribute(conv3x3_direct_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kTotal) !=
+        cudaSuccess)
+      return WG_ERR_CUDA;
+    configured |= bit;
+  }
+  const long long units = ((long long)n_img + g.G - 1) / g.G * g.bands;
+  const long long n_items = units * (Cout / 128);
+  long long grid = n_items < max_ctas ? n_items : max_ctas;
+  if (grid < 1) grid = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kDirThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_direct_gen_kernel, tmap_x, w_img, scale, shift, y, n_img, Cin, Cout,
+                                     relu, out_padded, (int)n_items, g);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
 
 template <int CL>

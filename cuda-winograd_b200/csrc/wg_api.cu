@@ -154,6 +154,8 @@ struct wg_layer {
   int H = 14, W = 14;      // output map (the reference: 14 x 14 everywhere)
   ff::Geo geo{};           // 3x3: tiles / frame / raw-plane geometry of the full-fold kernel
   OneGeo one_geo{14, 14, 16, 16, 0};  // 1x1: pixels per image and the padded frame of chain mode
+  DirGeo dgeo{};           // 3x3 direct-convolution kernel on a map size other than 14x14
+  bool dgen = false;
   // packed images (device). Sizes in bytes in img_bytes[], same order as the blob sections.
   float* d_filter = nullptr;           // packed filter image (U or swizzled W^T)
   float* d_filter_n64 = nullptr;       // 3x3 full-fold kernel: second image with all slices 64 wide, or null
@@ -218,7 +220,11 @@ static void layer_plan(wg_layer* L) {
     L->img_bytes[4] = (L->dtype == WG_TF32 && L->tile_n != 32 && ff::geo_is_ref(L->geo)) ? fe * 4 : 0;  // tile_n == 32: aliases d_filter
     // the direct-convolution kernel: TF32, reference geometry, 32-channel chunks, 128-cout blocks
     // (16-bit operands: 64-channel chunks, 2-byte elements)
-    const bool dir_ok = ff::geo_is_ref(L->geo) && L->cout % 128 == 0 && L->cin % (L->dtype == WG_TF32 ? 32 : 64) == 0;
+    // other map sizes: TF32 only, geometry as launch parameters (direct_gen_geo decides whether the map fits)
+    L->dgen = !ff::geo_is_ref(L->geo) && L->dtype == WG_TF32 &&
+              direct_gen_geo(L->geo.H, L->geo.W, L->geo.Hf, L->geo.Wf, &L->dgeo);
+    const bool dir_ok = (ff::geo_is_ref(L->geo) || L->dgen) && L->cout % 128 == 0 &&
+                        L->cin % (L->dtype == WG_TF32 ? 32 : 64) == 0;
     L->img_bytes[5] = dir_ok ? (size_t)9 * L->cin * L->cout * (L->dtype == WG_TF32 ? 4 : 2) : 0;
   } else {
     L->tile_n = (L->cout % 256 == 0 && L->dtype == WG_TF32) ? 256 : 128;  // bf16 operands: 128-wide N-tiles
@@ -473,7 +479,18 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
   const long long px = (long long)L->H * L->W;  // 1x1: GEMM rows per image
   // map sizes other than the reference's run the full-fold kernel only (developer build: not with a superseded generation)
   if (L->kind == 0 && !ref_geo && !(L->dtype == WG_TF32 ? L->tile_n == 96 : L->tm16_ff != 0)) return WG_ERR_ARG;
-  if (L->kind == 0 && L->d_filter_direct != nullptr && !(out_flags & 2) && N >= direct_min_batch(L->cin, L->dtype)) {
+  if (L->kind == 0 && L->d_filter_direct != nullptr && L->dgen && !(out_flags & 2)) {
+    // other map sizes, TF32: the direct kernel with runtime geometry, every batch size
+    {
+      std::lock_guard<std::mutex> lk(L->mu);
+      rc = L->tm_xd.get(x, N, &tmap, [&](CUtensorMap* m) { return direct_gen_make_tmap_in(m, x, N, L->cin, L->dgeo); });
+    }
+    if (rc != WG_OK) return rc;
+    return launched(direct_gen_launch(tmap, L->d_filter_direct, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->relu,
+                                      out_padded, max_ctas, L->dgeo, stream));
+  }
+  if (L->kind == 0 && L->d_filter_direct != nullptr && !L->dgen && !(out_flags & 2) &&
+      N >= direct_min_batch(L->cin, L->dtype)) {
     // throughput-sized batches of the reference geometry: direct convolution on the tensor core (no CUDA-core transform;
     // measured faster than the fused Winograd pipeline from a handful of images on, see conv3x3_direct_kernel.cu)
     {

@@ -105,6 +105,18 @@ int direct_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const fl
                   const float* shift, int n_img, int Cin, int Cout, int cl, int relu, int out_padded, int max_ctas,
                   int mixed, cudaStream_t stream);
 
+// other map sizes (TF32): geometry as launch parameters, plain row stores (same file)
+struct DirGeo {
+  int H, W, Hf, Wf;
+  int R, bands, G;
+  int n_pad, halo, box_rows, n_boxes;
+};
+bool direct_gen_geo(int H, int W, int Hf, int Wf, DirGeo* out);
+int direct_gen_make_tmap_in(CUtensorMap* tmap, const float* x, int n_img, int Cin, const DirGeo& g);
+int direct_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float* scale, const float* shift, float* y,
+                      int n_img, int Cin, int Cout, int relu, int out_padded, int max_ctas, const DirGeo& g,
+                      cudaStream_t stream);
+
 // ---- 1x1 GEMM path (one_kernels.cu)
 int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);
 int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout);

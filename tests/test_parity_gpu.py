@@ -633,7 +633,11 @@ def test_layer_blob_round_trip(lib_loaded, torch_cuda, tmp_path, kind, dtype):
 # ------------------------------------------------------------------ f4: other feature-map sizes (ResNet-50 stages)
 @pytest.mark.parametrize("h,w,c,k,n", [(28, 28, 128, 128, 9), (56, 56, 64, 64, 3), (7, 7, 512, 512, 37), (7, 7, 64, 96, 1),
                                         (9, 13, 32, 64, 5), (8, 5, 16, 32, 21), (28, 28, 64, 128, 64), (3, 3, 32, 32, 200),
-                                        (30, 6, 24, 160, 4)])
+                                        (30, 6, 24, 160, 4),
+                                        # TF32 with C % 32 == 0, K % 128 == 0: the direct-convolution kernel with runtime
+                                        # geometry (row bands of one image / several small images per work item)
+                                        (56, 56, 64, 128, 2), (7, 7, 512, 512, 1), (10, 20, 32, 128, 3), (5, 5, 64, 128, 7),
+                                        (3, 3, 32, 128, 200), (28, 28, 128, 256, 33), (21, 9, 32, 128, 6)])
 def test_3x3_other_map_sizes(lib_loaded, torch_cuda, h, w, c, k, n):
     """wg_conv3x3_create_hw: the fused 3x3 layer on other map sizes than the reference's hard-coded 14x14
     (Kernel128_winograd.cu:26-31,263-265) -- even (28x28x128, 56x56x64) and odd (7x7x512: edge tiles masked) sizes, ragged
