@@ -378,9 +378,9 @@ static int create_common(wg_layer_t** out, int kind, int cin, int cout, int H, i
 }
 
 // ---- wg_run_host chunk schedule (host-only logic, exported for the unit tests)
-// Full chunks of `chunk` images, then a tapering tail (halving down to 16 images): the copy-in stream is the critical
-// path from t = 0 whatever the chunking; what is exposed at the end is the LAST chunk's kernel + copy-out, so the last
-// chunks are small (256 images: 64, 64, 64, 32, 16, 16). At most kMaxChunks chunks: the chunk size grows with N so that
+// A ramp-up head (16, 32), full chunks of `chunk` images, then a tapering tail (halving down to 16 images): the copy-in
+// and copy-out streams are about equally long, so both the FIRST chunk's copy-in (nothing can be copied out before it)
+// and the LAST chunk's kernel + copy-out are exposed: both ends are small (256 images: 16, 32, 64, 64, 40, 20, 20). At most kMaxChunks chunks: the chunk size grows with N so that
 // the schedule (and the per-chunk events) stay bounded for any N.
 static constexpr int kMaxChunks = 64;
 static int chunk_schedule(int N, int chunk, int taper, int* sizes, int cap) {
@@ -389,13 +389,25 @@ static int chunk_schedule(int N, int chunk, int taper, int* sizes, int cap) {
   const int max_equal = kMaxChunks - 24;
   if ((N + chunk - 1) / chunk > max_equal) chunk = (N + max_equal - 1) / max_equal;
   int n = 0;
-  for (int rem = N; rem > 0;) {
+  int rem = N;
+  // ramp-up head (16, 32 images): the copy-out stream cannot start before the first chunk has been copied in and
+  // computed, and with output bytes ~ input bytes it is as long as the copy-in stream -- what is exposed at the START is
+  // the first chunk's copy-in, so the first chunks are small too
+  if (taper && N >= 128 && chunk >= 64) {
+    for (int c = 16; c <= 32; c *= 2) {
+      if (sizes && n < cap) sizes[n] = c;
+      ++n;
+      rem -= c;
+    }
+  }
+  while (rem > 0) {
     int c = rem < chunk ? rem : chunk;
     if (taper && rem <= 2 * chunk && rem > 16) {
       c = rem / 2;
       if (c < 16) c = 16;
       if (c > chunk) c = chunk;
     }
+    if (rem - c > 0 && rem - c < 16) c = rem;  // no crumbs: a remainder below 16 images rides with this chunk
     if (n == kMaxChunks - 1) c = rem;  // hard bound: whatever is left goes out as one last chunk
     if (sizes && n < cap) sizes[n] = c;
     ++n;

@@ -209,13 +209,15 @@ def test_product_library_has_no_developer_kernels(built):
                                458000, 500000, 1000000, 2 ** 31 - 1])
 def test_host_chunk_schedule_is_bounded(built, n):
     """wg_run_host's chunk schedule (65+ chunks overflowed fixed 64-entry arrays for N >~ 458k): at most
-    64 chunks for any N, positive sizes summing to N, tapering tail; 256 images -> 64, 64, 64, 32, 16, 16."""
+    64 chunks for any N, positive sizes summing to N, small chunks at both ends (the first copy-in and the last copy-out
+    are what the pipeline exposes); 256 images -> 16, 32, 64, 64, 40, 20, 20."""
     s = built.host_chunk_schedule(n)
     assert 1 <= len(s) <= 64 and all(c > 0 for c in s) and sum(s) == n
     if n == 256:
-        assert s == [64, 64, 64, 32, 16, 16]
+        assert s == [16, 32, 64, 64, 40, 20, 20]
     if n >= 128:
-        assert s[-1] <= s[0]                                       # the exposed last chunk is never the big one
+        assert s[-1] < 32 or 2 * s[-1] <= max(s)                   # the exposed last chunk is never the big one
+        assert s[0] <= 16 or 2 * s[0] <= max(s) or len(s) == 64    # nor is the first (nothing is copied out before it)
     # cap smaller than the schedule: still returns the count, writes only `cap` entries
     buf = (ctypes.c_int * 2)(-1, -1)
     assert built.lib().wg_host_chunk_schedule(n, buf, 2) == len(s)

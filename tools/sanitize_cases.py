@@ -120,7 +120,7 @@ def main():
     # host-buffer pipeline (chunks, three streams) and the packed blob
     x, w, sc, sh = r3(100, 32, 64)
     layer = wg.Conv3x3BnRelu(w, sc, sh)
-    check("wg_run_host N=100 (chunks 50,25,16,9)", layer.run_host(x), golden.conv3x3_bn_relu(x, w, sc, sh), 1e-3)
+    check("wg_run_host N=100 (chunks 50,25,25)", layer.run_host(x), golden.conv3x3_bn_relu(x, w, sc, sh), 1e-3)
     again = wg._Layer.deserialize(layer.serialize())
     check("wg_layer_deserialize", again(torch.from_numpy(x).cuda()).cpu().numpy(), golden.conv3x3_bn_relu(x, w, sc, sh), 1e-3)
     torch.cuda.synchronize()
