@@ -9,7 +9,7 @@ ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude
 CSRC    := cuda-winograd_b200/csrc
 LIB     := cuda-winograd_b200/libwinograd_b200.so
-KSRCS   := $(CSRC)/winograd_kernels.cu $(CSRC)/wino_small_kernel.cu $(CSRC)/wino_ff_kernel.cu $(CSRC)/wino_ffw_kernel.cu $(CSRC)/conv3x3_direct_kernel.cu $(CSRC)/one_kernels.cu $(CSRC)/probe_kernels.cu $(CSRC)/wg_api.cu $(CSRC)/legacy_entry.cu
+KSRCS   := $(CSRC)/winograd_kernels.cu $(CSRC)/wino_small_kernel.cu $(CSRC)/wino_ff_kernel.cu $(CSRC)/wino_ffw_kernel.cu $(CSRC)/conv3x3_direct_kernel.cu $(CSRC)/one_kernels.cu $(CSRC)/conv1x1_t_kernel.cu $(CSRC)/probe_kernels.cu $(CSRC)/wg_api.cu $(CSRC)/legacy_entry.cu
 # developer build: + the superseded half-fold kernel, the ablation / CTA-pair instantiations and the WG_* environment knobs
 DEVLIB  := tools/libwinograd_b200_dev.so
 DEVSRCS := $(KSRCS) $(CSRC)/wino_tm_kernel.cu

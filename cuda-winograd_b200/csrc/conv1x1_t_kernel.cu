@@ -1,0 +1,301 @@
+// 1x1 conv (GEMM) + folded BatchNorm (+ ReLU) (+ residual add) for the WIDE-COUT shapes, sm_100a: the GEMM laid out
+// transposed -- M = output channels, N = pixels -- with the weight block resident in shared memory.
+//
+// Replaces kernel_128_one_512 (/root/reference/Kernel128_one.cu:244-273) and kernel_256_one_1024 (Kernel256_one.cu:
+// 246-274) at throughput batch sizes; same operator and data layouts as conv1x1_bn_act_kernel (one_kernels.cu):
+// y[M x Cout] = act(scale * (x[M x Cin] * W[Cin x Cout]) + shift (+ residual)), fp32 in / out, TF32 operands.
+//
+// Why another layout. The wide-Cout shapes are store-heavy (4x more output than input bytes) and were bound by the
+// epilogue's instruction chain (profiles/one_ablation_r02.md: the kernel with all memory traffic and MMAs switched off
+// still took half the time). With pixels on M every thread owns one pixel and 32 couts per chunk: 16 folded-BN vector
+// loads per chunk, and four epilogue warps per 128 x 256 tile. With COUTS on M (TMEM lanes) a thread owns one cout --
+// its scale / shift are two registers for the whole item -- and the 3x3 direct kernel's epilogue applies unchanged:
+// eight warps, per 16 pixels one tcgen05.ld.x16, 16 FMAs, a transposing [16 px][32 couts] staging tile written one
+// conflict-free 128-byte row per instruction, one 2 KB TMA tensor store.
+//
+// Work item = (256 pixels, 128 couts): D[128 couts][256 px] += W[128 couts][32 ch] . X[256 px][32 ch]^T, Cin/32 k-blocks
+// of 4 MMAs (M = 128, N = 256, K = 8), two TMEM accumulator buffers. A CTA keeps ONE 128-cout block for its whole life:
+// the [Cin/32][128][32] weight slab (<= 128 KB, Cin <= 256) is loaded once; the ring carries activations only.
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue (quad = 32 couts, half of the 256 pixels each).
+// RES: the residual's [16 px][32 couts] sub-tile is TMA-loaded into the staging buffer one chunk ahead (plain layout, same
+// box as the store); each thread adds its own column and the same buffer is stored.
+#include <stdlib.h>
+
+#include "ptx.cuh"
+#include "wg_internal.h"
+
+namespace wg {
+
+constexpr int kOneTThreads = 32 * 10;
+
+// CIN_MAX = 128: the [Cin/32][128][32] weight slab (<= 64 KB) is resident, the ring carries activations only.
+// CIN_MAX = 256: a resident slab (128 KB) would leave two activation stages = 64 KB in flight, a third of what the
+// latency x bandwidth product of the tiled-TMA path needs (measured: 84 us instead of 64); the weight block of a k-block
+// then rides in the same ring stage as its activations (4 stages of 32 + 16 KB) and is re-read from L2 per item.
+template <int CIN_MAX>
+struct OneTSmem {
+  static constexpr bool kResident = CIN_MAX <= 128;
+  static constexpr int kSX = 4;                          // k-blocks in flight
+  static constexpr uint32_t kXBytes = 256 * 128;         // 256 pixels x 32 channels
+  static constexpr uint32_t kWBytes = 128 * 128;         // one k-block of the slab: 128 couts x 32 channels
+  static constexpr uint32_t kSlabBytes = (kResident ? CIN_MAX / 32 : kSX) * kWBytes;
+  static constexpr uint32_t kStageOutBytes = 16 * 128;   // [16 px][32 couts]
+  static constexpr uint32_t kOffX = 0;
+  static constexpr uint32_t kOffW = kOffX + kSX * kXBytes;
+  static constexpr uint32_t kOffOut = kOffW + kSlabBytes;  // [8 warps][2 buffers]
+  static constexpr uint32_t kOffBar = kOffOut + 8 * 2 * kStageOutBytes;
+  static constexpr uint32_t kNumBars = 2 * kSX + 4 + 1 + 16;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;
+  static_assert(kOffW % 1024 == 0, "swizzled buffers must be 1024-byte aligned");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+// the residual / output sub-tile of (pixel chunk j of 16) is the same [16 px][32 couts] box
+template <int CIN_MAX, bool RES>
+__global__ void __launch_bounds__(kOneTThreads, 1)
+conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+                 const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ w_img,
+                 const float* __restrict__ scale, const float* __restrict__ shift, long long m_rows, int Cin, int Cout,
+                 int relu, int bn_packed, int relu_after) {
+  using S = OneTSmem<CIN_MAX>;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = x_full + S::kSX;
+  uint64_t* acc_full = x_empty + S::kSX;  // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint64_t* w_full = acc_empty + 2;       // the resident weight slab has landed
+  uint64_t* res_full = w_full + 1;        // RES: [8 warps][2 buffers]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_y);
+    for (int i = 0; i < S::kSX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&res_full[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_kb = Cin / 32;
+  const int n_cb = Cout / 128;
+  const int n_pt = (int)((m_rows + 255) / 256);  // 256-pixel tiles
+  // CTA b keeps cout block b % n_cb and walks the pixel tiles b / n_cb, + gridDim / n_cb, ... (grid = multiple of n_cb)
+  const int cb = (int)blockIdx.x % n_cb;
+  const int first_pt = (int)blockIdx.x / n_cb, pt_stride = (int)gridDim.x / n_cb;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // the weight slab: 128 couts of the packed image [Cout/bn_packed][Cin/32][bn_packed rows][128 B] -- requested before
+      // waiting for the previous kernel in the stream
+      const int col0 = cb * 128;
+      const uint8_t* w_src = reinterpret_cast<const uint8_t*>(w_img) +
+                             ((size_t)(col0 / bn_packed) * n_kb * bn_packed + col0 % bn_packed) * 128;
+      if constexpr (S::kResident) {
+        mbar_arrive_expect_tx(w_full, (uint32_t)n_kb * S::kWBytes);
+        for (int kb = 0; kb < n_kb; ++kb)
+          tma_bulk_g2s(smem + S::kOffW + kb * S::kWBytes, w_src + (size_t)kb * bn_packed * 128, S::kWBytes, w_full);
+      }
+      pdl_wait();  // activations come from the previous kernel in the stream
+      uint32_t sx = 0, px = 0;
+      for (int pt = first_pt; pt < n_pt; pt += pt_stride)
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&x_empty[sx], px ^ 1);
+          mbar_arrive_expect_tx(&x_full[sx], S::kXBytes + (S::kResident ? 0u : S::kWBytes));
+          tma_tensor_2d_g2s(smem + S::kOffX + sx * S::kXBytes, &tmap_x, kb * 32, pt * 256, &x_full[sx]);
+          if constexpr (!S::kResident)
+            tma_bulk_g2s(smem + S::kOffW + sx * S::kWBytes, w_src + (size_t)kb * bn_packed * 128, S::kWBytes, &x_full[sx]);
+          if (++sx == S::kSX) { sx = 0; px ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, 256);
+      const uint32_t x_base = smem_u32(smem + S::kOffX);
+      const uint32_t w_base = smem_u32(smem + S::kOffW);
+      uint32_t sx = 0, px = 0, it = 0;
+      if constexpr (S::kResident) mbar_wait(w_full, 0);
+      for (int pt = first_pt; pt < n_pt; pt += pt_stride, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&x_full[sx], px);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t a_desc =
+                make_smem_desc(w_base + (S::kResident ? (uint32_t)kb : sx) * S::kWBytes + k * 32, 0, 1024, kLayoutSW128);
+            const uint64_t b_desc = make_smem_desc(x_base + sx * S::kXBytes + k * 32, 0, 1024, kLayoutSW128);
+            umma_tf32_ss(tmem_base + buf * 256, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&x_empty[sx]);
+          if (++sx == S::kSX) { sx = 0; px ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3, hsel = ew >> 2;
+    uint8_t* stage_out = smem + S::kOffOut + ew * 2 * S::kStageOutBytes;
+    const uint32_t stage_u32 = smem_u32(stage_out);
+    uint64_t* rbar = res_full + ew * 2;
+    const int cout0 = cb * 128 + quad * 32;  // this warp's 32 couts
+    const float sc = __ldg(scale + cout0 + lane), sh = __ldg(shift + cout0 + lane);
+    uint32_t it = 0, chunk = 0;
+    // RES: request the residual sub-tile of (pixel tile pt, chunk j) into staging buffer b (rows beyond M: clipped)
+    auto res_request = [&](int pt, int j, uint32_t b) {
+      mbar_arrive_expect_tx(&rbar[b], S::kStageOutBytes);
+      tma_tensor_2d_g2s(stage_out + b * S::kStageOutBytes, &tmap_r, cout0, pt * 256 + hsel * 128 + j * 16, &rbar[b]);
+    };
+    if constexpr (RES) {
+      pdl_wait();  // the residual may come from the previous kernel in the stream
+      if (lane == 0 && first_pt < n_pt) res_request(first_pt, 0, 0);
+    }
+    for (int pt = first_pt; pt < n_pt; pt += pt_stride, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + hsel * 128;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        float v[16];
+        tmem_ld_x16(taddr + j * 16, v);
+        const uint32_t sbuf = (chunk & 1) * S::kStageOutBytes;
+        if constexpr (RES) {
+          // the OTHER buffer's store (previous chunk) must have read it before the next residual lands there
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            const int nj = j + 1 < 8 ? j + 1 : 0, npt = j + 1 < 8 ? pt : pt + pt_stride;
+            if (npt < n_pt) res_request(npt, nj, (chunk + 1) & 1);
+          }
+          __syncwarp();
+          mbar_wait(&rbar[chunk & 1], (chunk >> 1) & 1);
+        } else {
+          if (lane == 0) tma_store_wait_read<1>();  // the staging buffer written two chunks ago has been read
+          __syncwarp();
+        }
+        tmem_ld_wait();
+        const uint32_t dst = stage_u32 + sbuf + lane * 4;
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          float o = fmaf(sc, v[x], sh);
+          if (relu) o = fmaxf(o, 0.f);
+          if constexpr (RES) {
+            o += ld_shared_f32(dst + x * 128);  // this thread's own column of the residual sub-tile
+            if (relu_after) o = fmaxf(o, 0.f);
+          }
+          st_shared_f32(dst + x * 128, o);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_tensor_2d_s2g(&tmap_y, stage_out + sbuf, cout0, pt * 256 + hsel * 128 + j * 16);
+          tma_store_commit();
+        }
+        ++chunk;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+static int onet_encode(CUtensorMap* tmap, const float* base, int inner, long long rows, int box_rows,
+                       CUtensorMapSwizzle swz) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return WG_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, wg::l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
+}
+// activations: 256 pixels x 32 channels per box, 128-byte swizzle
+int onet_make_tmap_in(CUtensorMap* tmap, const float* x, long long m_rows, int Cin) {
+  return onet_encode(tmap, x, Cin, m_rows, 256, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+// output / residual: 16 pixels x 32 couts per box, plain layout
+int onet_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout) {
+  return onet_encode(tmap, y, Cout, m_rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+bool onet_eligible(long long m_rows, int Cin, int Cout, int max_ctas) {
+  if (Cin % 32 != 0 || Cin > 256 || Cout % 128 != 0 || Cout < 2 * Cin) return false;
+  const long long n_cb = Cout / 128, n_pt = (m_rows + 255) / 256;
+  // throughput regime only: every CTA gets several pixel tiles of its cout block
+  return max_ctas >= n_cb && n_pt >= 3 * (max_ctas / n_cb);
+}
+
+template <int CIN_MAX, bool RES>
+static int launch_onet(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const CUtensorMap& tmap_r,
+                       const float* w_img, const float* scale, const float* shift, long long m_rows, int Cin, int Cout,
+                       int relu, int bn_packed, int relu_after, int max_ctas, cudaStream_t stream) {
+  using S = OneTSmem<CIN_MAX>;
+  static unsigned long long configured = 0;
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long bit = 1ull << (dev_ & 63);
+  if (!(configured & bit)) {
+    if (cudaFuncSetAttribute(conv1x1_t_kernel<CIN_MAX, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)S::kTotal) != cudaSuccess)
+      return WG_ERR_CUDA;
+    configured |= bit;
+  }
+  const long long n_cb = Cout / 128, n_pt = (m_rows + 255) / 256;
+  long long grid = (max_ctas / n_cb) * n_cb;
+  if (grid > n_pt * n_cb) grid = n_pt * n_cb;
+  if (grid < n_cb) grid = n_cb;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kOneTThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_t_kernel<CIN_MAX, RES>, tmap_x, tmap_y, tmap_r, w_img, scale, shift,
+                                     m_rows, Cin, Cout, relu, bn_packed, relu_after);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+// bn_packed: row count of a packed weight tile of the layer's image (128 or 256)
+int onet_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const CUtensorMap* tmap_r, const float* w_img,
+                const float* scale, const float* shift, long long m_rows, int Cin, int Cout, int relu, int bn_packed,
+                int relu_after, int max_ctas, cudaStream_t stream) {
+#define WG_ONET(CM_, R_)                                                                                          \
+  return launch_onet<CM_, R_>(tmap_x, tmap_y, tmap_r ? *tmap_r : tmap_y, w_img, scale, shift, m_rows, Cin, Cout, relu, \
+                              bn_packed, relu_after, max_ctas, stream)
+  if (Cin <= 128) {
+    if (tmap_r) WG_ONET(128, true);
+    WG_ONET(128, false);
+  }
+  if (tmap_r) WG_ONET(256, true);
+  WG_ONET(256, false);
+#undef WG_ONET
+}
+
+}  // namespace wg

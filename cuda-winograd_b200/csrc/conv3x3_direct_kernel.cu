@@ -77,10 +77,6 @@ __device__ __forceinline__ DirItem dir_item(int i, int n_big, int n_cb) {
   return DirItem{n_big / n_cb + j / (2 * n_cb), (j % (2 * n_cb)) >> 1, j & 1};
 }
 
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-
 template <int CL>
 __global__ void __launch_bounds__(kDirThreads, 1)
 conv3x3_direct_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,

@@ -457,6 +457,16 @@ static int direct_min_batch(int cin, int dtype) {
   return cin >= 256 ? 6 : 11;
 }
 
+// developer build: WG_ONE_T=0 keeps the wide-Cout 1x1 shapes on conv1x1_bn_act_kernel (A/B runs)
+static int onet_min_rows() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = dev_env("WG_ONE_T");
+    v = (e && atoi(e) == 0) ? -1 : 0;
+  }
+  return v;
+}
+
 static int run_impl(wg_layer_t* L, const float* x, const float* residual, float* y, int N, int flags,
                     cudaStream_t stream) {
   if (!L || !x || !y || N <= 0) return WG_ERR_ARG;
@@ -557,6 +567,23 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
       return launched(wino_ff_launch(tmap, x, L->d_filter_tm16, L->d_filter_tm16_n64, L->d_scale, L->d_shift, y, N,
                                      L->cin, L->cout, op16, L->ff_cg2, L->relu, out_flags, max_ctas, L->geo, stream));
     }
+  }
+  if (L->kind == 1 && L->dtype == WG_TF32 && !out_padded && onet_min_rows() >= 0 &&
+      onet_eligible((long long)N * px, L->cin, L->cout, max_ctas)) {
+    // wide-Cout shapes at throughput sizes: couts on M, pixels on N, weight slab resident (conv1x1_t_kernel.cu)
+    const long long rows = (long long)N * px;
+    {
+      std::lock_guard<std::mutex> lk(L->mu);
+      rc = L->tm_xd.get(x, N, &tmap, [&](CUtensorMap* m) { return onet_make_tmap_in(m, x, rows, L->cin); });
+      if (rc == WG_OK) rc = L->tm_yd.get(y, N, &tmap_y, [&](CUtensorMap* m) { return onet_make_tmap_out(m, y, rows, L->cout); });
+      if (rc == WG_OK && residual)
+        rc = L->tm_ydp.get(residual, N, &tmap_res,
+                           [&](CUtensorMap* m) { return onet_make_tmap_out(m, residual, rows, L->cout); });
+    }
+    if (rc != WG_OK) return rc;
+    return launched(onet_launch(tmap, tmap_y, residual ? &tmap_res : nullptr, L->d_filter, L->d_scale, L->d_shift, rows,
+                                L->cin, L->cout, L->relu, L->tile_n, (flags & WG_OUT_RELU_AFTER_ADD) ? 1 : 0, max_ctas,
+                                stream));
   }
   {
     std::lock_guard<std::mutex> lk(L->mu);
