@@ -32,11 +32,17 @@ constexpr int kOneTThreads = 32 * 10;
 // CIN_MAX = 256: a resident slab (128 KB) would leave two activation stages = 64 KB in flight, a third of what the
 // latency x bandwidth product of the tiled-TMA path needs (measured: 84 us instead of 64); the weight block of a k-block
 // then rides in the same ring stage as its activations (4 stages of 32 + 16 KB) and is re-read from L2 per item.
-template <int CIN_MAX>
+// PAIR: the two CTAs of a cluster form a tcgen05 cta_group::2 pair on one (256 pixels, 256 couts) item: M = 256 couts (128
+// per CTA, each with its own weight blocks) and -- the point -- each CTA loads only HALF of the pixels (128 x 32 channels
+// per k-block); the tensor core reads each half of the B operand from the shared memory it lives in. The activations are
+// the stream every cout block re-reads (Cout / 128 times per layer): halving it per SM takes the kernel off the tiled-TMA
+// ceiling (~37 B/clk per SM). Hand-offs as in the other pair kernels: the peer's MMA warp relays "landed" to the leader,
+// commits are multicast, the peer's epilogue warps arrive on the leader's acc_empty.
+template <int CIN_MAX, bool PAIR = false>
 struct OneTSmem {
   static constexpr bool kResident = CIN_MAX <= 128;
-  static constexpr int kSX = 4;                          // k-blocks in flight
-  static constexpr uint32_t kXBytes = 256 * 128;         // 256 pixels x 32 channels
+  static constexpr int kSX = PAIR ? 6 : 4;               // k-blocks in flight
+  static constexpr uint32_t kXBytes = (PAIR ? 128 : 256) * 128;  // this CTA's pixels x 32 channels
   static constexpr uint32_t kWBytes = 128 * 128;         // one k-block of the slab: 128 couts x 32 channels
   static constexpr uint32_t kSlabBytes = (kResident ? CIN_MAX / 32 : kSX) * kWBytes;
   static constexpr uint32_t kStageOutBytes = 16 * 128;   // [16 px][32 couts]
@@ -52,13 +58,15 @@ struct OneTSmem {
 };
 
 // the residual / output sub-tile of (pixel chunk j of 16) is the same [16 px][32 couts] box
-template <int CIN_MAX, bool RES>
+template <int CIN_MAX, bool RES, bool PAIR>
 __global__ void __launch_bounds__(kOneTThreads, 1)
 conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                  const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ w_img,
                  const float* __restrict__ scale, const float* __restrict__ shift, long long m_rows, int Cin, int Cout,
                  int relu, int bn_packed, int relu_after) {
-  using S = OneTSmem<CIN_MAX>;
+  using S = OneTSmem<CIN_MAX, PAIR>;
+  constexpr uint16_t kPairMask = 0x3;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -77,24 +85,31 @@ conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_y);
-    for (int i = 0; i < S::kSX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
-    mbar_init(w_full, 1);
+    const uint32_t n_full = (PAIR && crank == 0) ? 2 : 1;  // leader: own TMA bytes + the peer's relay
+    for (int i = 0; i < S::kSX; ++i) mbar_init(&x_full[i], n_full), mbar_init(&x_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], PAIR ? 16 : 8);
+    mbar_init(w_full, n_full);
     for (int i = 0; i < 16; ++i) mbar_init(&res_full[i], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_cg2<512>(tmem_ptr);
+    else tmem_alloc<512>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_kb = Cin / 32;
-  const int n_cb = Cout / 128;
   const int n_pt = (int)((m_rows + 255) / 256);  // 256-pixel tiles
-  // CTA b keeps cout block b % n_cb and walks the pixel tiles b / n_cb, + gridDim / n_cb, ... (grid = multiple of n_cb)
-  const int cb = (int)blockIdx.x % n_cb;
-  const int first_pt = (int)blockIdx.x / n_cb, pt_stride = (int)gridDim.x / n_cb;
+  // Cluster (PAIR) / CTA b keeps cout group b % n_cg -- 256 couts per pair, 128 per CTA -- and walks the pixel tiles
+  // b / n_cg, + grid / n_cg, ... (the host makes the grid a multiple of n_cg)
+  constexpr int kCL = PAIR ? 2 : 1;
+  const int n_cg = Cout / (128 * kCL);
+  const int cl_id = (int)blockIdx.x / kCL, n_cl = (int)gridDim.x / kCL;
+  const int cb = (cl_id % n_cg) * kCL + (int)crank;  // this CTA's 128-cout block
+  const int first_pt = cl_id / n_cg, pt_stride = n_cl / n_cg;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -114,15 +129,31 @@ conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&x_empty[sx], px ^ 1);
           mbar_arrive_expect_tx(&x_full[sx], S::kXBytes + (S::kResident ? 0u : S::kWBytes));
-          tma_tensor_2d_g2s(smem + S::kOffX + sx * S::kXBytes, &tmap_x, kb * 32, pt * 256, &x_full[sx]);
+          tma_tensor_2d_g2s(smem + S::kOffX + sx * S::kXBytes, &tmap_x, kb * 32, pt * 256 + (PAIR ? (int)crank * 128 : 0),
+                            &x_full[sx]);
           if constexpr (!S::kResident)
             tma_bulk_g2s(smem + S::kOffW + sx * S::kWBytes, w_src + (size_t)kb * bn_packed * 128, S::kWBytes, &x_full[sx]);
           if (++sx == S::kSX) { sx = 0; px ^= 1; }
         }
     }
+  } else if (warp == 1 && PAIR && crank != 0) {
+    // peer of a pair: no MMAs to issue; relay "landed here" to the leader's barriers, in consumption order
+    if (elect_one()) {
+      uint32_t sx = 0, px = 0;
+      if constexpr (S::kResident) {
+        mbar_wait(w_full, 0);
+        mbar_arrive_remote_plain(w_full, 0);
+      }
+      for (int pt = first_pt; pt < n_pt; pt += pt_stride)
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&x_full[sx], px);
+          mbar_arrive_remote_plain(&x_full[sx], 0);
+          if (++sx == S::kSX) { sx = 0; px ^= 1; }
+        }
+    }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(kFmtTF32, 128, 256);
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, PAIR ? 256 : 128, 256);
       const uint32_t x_base = smem_u32(smem + S::kOffX);
       const uint32_t w_base = smem_u32(smem + S::kOffW);
       uint32_t sx = 0, px = 0, it = 0;
@@ -139,12 +170,15 @@ conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const uint64_t a_desc =
                 make_smem_desc(w_base + (S::kResident ? (uint32_t)kb : sx) * S::kWBytes + k * 32, 0, 1024, kLayoutSW128);
             const uint64_t b_desc = make_smem_desc(x_base + sx * S::kXBytes + k * 32, 0, 1024, kLayoutSW128);
-            umma_tf32_ss(tmem_base + buf * 256, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_tf32_ss_cg2(tmem_base + buf * 256, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_tf32_ss(tmem_base + buf * 256, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&x_empty[sx]);
+          if constexpr (PAIR) umma_commit_mcast_cg2(&x_empty[sx], kPairMask);
+          else umma_commit(&x_empty[sx]);
           if (++sx == S::kSX) { sx = 0; px ^= 1; }
         }
-        umma_commit(&acc_full[buf]);
+        if constexpr (PAIR) umma_commit_mcast_cg2(&acc_full[buf], kPairMask);
+        else umma_commit(&acc_full[buf]);
       }
     }
   } else {
@@ -210,14 +244,20 @@ conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_remote_plain(&acc_empty[buf], 0);  // the leader issues the MMAs of both CTAs
+        else mbar_arrive(&acc_empty[buf]);
+      }
     }
     if (lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();  // the peer's shared memory and barriers stay alive
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_cg2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 static int onet_encode(CUtensorMap* tmap, const float* base, int inner, long long rows, int box_rows,
@@ -232,13 +272,23 @@ static int onet_encode(CUtensorMap* tmap, const float* base, int inner, long lon
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, wg::l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? WG_OK : WG_ERR_TMAP;
 }
-// activations: 256 pixels x 32 channels per box, 128-byte swizzle
-int onet_make_tmap_in(CUtensorMap* tmap, const float* x, long long m_rows, int Cin) {
-  return onet_encode(tmap, x, Cin, m_rows, 256, CU_TENSOR_MAP_SWIZZLE_128B);
+// activations: 256 (CTA pairs: 128) pixels x 32 channels per box, 128-byte swizzle
+int onet_make_tmap_in(CUtensorMap* tmap, const float* x, long long m_rows, int Cin, int Cout) {
+  return onet_encode(tmap, x, Cin, m_rows, onet_pair(Cout) ? 128 : 256, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 // output / residual: 16 pixels x 32 couts per box, plain layout
 int onet_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout) {
   return onet_encode(tmap, y, Cout, m_rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+// CTA pairs whenever the couts come in groups of 256 (developer build: WG_ONE_T_PAIR=0 switches them off)
+bool onet_pair(int Cout) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = dev_env("WG_ONE_T_PAIR");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v && Cout % 256 == 0;
 }
 
 bool onet_eligible(long long m_rows, int Cin, int Cout, int max_ctas) {
@@ -248,36 +298,41 @@ bool onet_eligible(long long m_rows, int Cin, int Cout, int max_ctas) {
   return max_ctas >= n_cb && n_pt >= 3 * (max_ctas / n_cb);
 }
 
-template <int CIN_MAX, bool RES>
+template <int CIN_MAX, bool RES, bool PAIR>
 static int launch_onet(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const CUtensorMap& tmap_r,
                        const float* w_img, const float* scale, const float* shift, long long m_rows, int Cin, int Cout,
                        int relu, int bn_packed, int relu_after, int max_ctas, cudaStream_t stream) {
-  using S = OneTSmem<CIN_MAX>;
+  using S = OneTSmem<CIN_MAX, PAIR>;
   static unsigned long long configured = 0;
   int dev_ = 0;
   cudaGetDevice(&dev_);
   const unsigned long long bit = 1ull << (dev_ & 63);
   if (!(configured & bit)) {
-    if (cudaFuncSetAttribute(conv1x1_t_kernel<CIN_MAX, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv1x1_t_kernel<CIN_MAX, RES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)S::kTotal) != cudaSuccess)
       return WG_ERR_CUDA;
     configured |= bit;
   }
-  const long long n_cb = Cout / 128, n_pt = (m_rows + 255) / 256;
-  long long grid = (max_ctas / n_cb) * n_cb;
-  if (grid > n_pt * n_cb) grid = n_pt * n_cb;
-  if (grid < n_cb) grid = n_cb;
+  constexpr int CL = PAIR ? 2 : 1;
+  const long long n_cg = Cout / (128 * CL), n_pt = (m_rows + 255) / 256;
+  long long n_cl = (max_ctas / CL / n_cg) * n_cg;  // clusters: a multiple of the cout groups
+  if (n_cl > n_pt * n_cg) n_cl = n_pt * n_cg;
+  if (n_cl < n_cg) n_cl = n_cg;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
+  cfg.gridDim = dim3((unsigned)(n_cl * CL));
   cfg.blockDim = dim3(kOneTThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_t_kernel<CIN_MAX, RES>, tmap_x, tmap_y, tmap_r, w_img, scale, shift,
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv1x1_t_kernel<CIN_MAX, RES, PAIR>, tmap_x, tmap_y, tmap_r, w_img, scale, shift,
                                      m_rows, Cin, Cout, relu, bn_packed, relu_after);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
 }
@@ -286,15 +341,20 @@ static int launch_onet(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, con
 int onet_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const CUtensorMap* tmap_r, const float* w_img,
                 const float* scale, const float* shift, long long m_rows, int Cin, int Cout, int relu, int bn_packed,
                 int relu_after, int max_ctas, cudaStream_t stream) {
-#define WG_ONET(CM_, R_)                                                                                          \
-  return launch_onet<CM_, R_>(tmap_x, tmap_y, tmap_r ? *tmap_r : tmap_y, w_img, scale, shift, m_rows, Cin, Cout, relu, \
-                              bn_packed, relu_after, max_ctas, stream)
+#define WG_ONET(CM_, R_, P_)                                                                                  \
+  return launch_onet<CM_, R_, P_>(tmap_x, tmap_y, tmap_r ? *tmap_r : tmap_y, w_img, scale, shift, m_rows, Cin, Cout, \
+                                  relu, bn_packed, relu_after, max_ctas, stream)
+  const bool pair = onet_pair(Cout);
   if (Cin <= 128) {
-    if (tmap_r) WG_ONET(128, true);
-    WG_ONET(128, false);
+    if (tmap_r && pair) WG_ONET(128, true, true);
+    if (tmap_r) WG_ONET(128, true, false);
+    if (pair) WG_ONET(128, false, true);
+    WG_ONET(128, false, false);
   }
-  if (tmap_r) WG_ONET(256, true);
-  WG_ONET(256, false);
+  if (tmap_r && pair) WG_ONET(256, true, true);
+  if (tmap_r) WG_ONET(256, true, false);
+  if (pair) WG_ONET(256, false, true);
+  WG_ONET(256, false, false);
 #undef WG_ONET
 }
 

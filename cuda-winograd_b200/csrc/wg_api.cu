@@ -574,7 +574,7 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
     const long long rows = (long long)N * px;
     {
       std::lock_guard<std::mutex> lk(L->mu);
-      rc = L->tm_xd.get(x, N, &tmap, [&](CUtensorMap* m) { return onet_make_tmap_in(m, x, rows, L->cin); });
+      rc = L->tm_xd.get(x, N, &tmap, [&](CUtensorMap* m) { return onet_make_tmap_in(m, x, rows, L->cin, L->cout); });
       if (rc == WG_OK) rc = L->tm_yd.get(y, N, &tmap_y, [&](CUtensorMap* m) { return onet_make_tmap_out(m, y, rows, L->cout); });
       if (rc == WG_OK && residual)
         rc = L->tm_ydp.get(residual, N, &tmap_res,

@@ -119,7 +119,8 @@ int direct_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float
 
 // ---- 1x1, wide-Cout shapes at throughput sizes (conv1x1_t_kernel.cu): couts on M, pixels on N, resident weight slab
 bool onet_eligible(long long m_rows, int Cin, int Cout, int max_ctas);
-int onet_make_tmap_in(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);
+bool onet_pair(int Cout);
+int onet_make_tmap_in(CUtensorMap* tmap, const float* x, long long m_rows, int Cin, int Cout);
 int onet_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout);
 int onet_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const CUtensorMap* tmap_r, const float* w_img,
                 const float* scale, const float* shift, long long m_rows, int Cin, int Cout, int relu, int bn_packed,
