@@ -38,18 +38,22 @@ constexpr int kOneTThreads = 32 * 10;
 // the stream every cout block re-reads (Cout / 128 times per layer): halving it per SM takes the kernel off the tiled-TMA
 // ceiling (~37 B/clk per SM). Hand-offs as in the other pair kernels: the peer's MMA warp relays "landed" to the leader,
 // commits are multicast, the peer's epilogue warps arrive on the leader's acc_empty.
-template <int CIN_MAX, bool PAIR = false>
+template <int CIN_MAX, bool PAIR = false, bool RES = false>
 struct OneTSmem {
-  static constexpr bool kResident = CIN_MAX <= 128;
-  static constexpr int kSX = PAIR ? 6 : 4;               // k-blocks in flight
+  // resident slab: Cin <= 128 always; Cin = 256 with CTA pairs and no residual (16 KB activation stages: five of them +
+  // the 128 KB slab fit when every epilogue warp has one staging tile instead of the two the residual prefetch needs)
+  static constexpr bool kBigResident = CIN_MAX > 128 && PAIR && !RES;
+  static constexpr bool kResident = CIN_MAX <= 128 || kBigResident;
+  static constexpr int kOutBufs = kBigResident ? 1 : 2;
+  static constexpr int kSX = PAIR ? (kBigResident ? 5 : 6) : 4;  // k-blocks in flight
   static constexpr uint32_t kXBytes = (PAIR ? 128 : 256) * 128;  // this CTA's pixels x 32 channels
   static constexpr uint32_t kWBytes = 128 * 128;         // one k-block of the slab: 128 couts x 32 channels
   static constexpr uint32_t kSlabBytes = (kResident ? CIN_MAX / 32 : kSX) * kWBytes;
   static constexpr uint32_t kStageOutBytes = 16 * 128;   // [16 px][32 couts]
   static constexpr uint32_t kOffX = 0;
   static constexpr uint32_t kOffW = kOffX + kSX * kXBytes;
-  static constexpr uint32_t kOffOut = kOffW + kSlabBytes;  // [8 warps][2 buffers]
-  static constexpr uint32_t kOffBar = kOffOut + 8 * 2 * kStageOutBytes;
+  static constexpr uint32_t kOffOut = kOffW + kSlabBytes;  // [8 warps][kOutBufs buffers]
+  static constexpr uint32_t kOffBar = kOffOut + 8 * kOutBufs * kStageOutBytes;
   static constexpr uint32_t kNumBars = 2 * kSX + 4 + 1 + 16;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;
@@ -64,7 +68,7 @@ conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ w_img,
                  const float* __restrict__ scale, const float* __restrict__ shift, long long m_rows, int Cin, int Cout,
                  int relu, int bn_packed, int relu_after) {
-  using S = OneTSmem<CIN_MAX, PAIR>;
+  using S = OneTSmem<CIN_MAX, PAIR, RES>;
   constexpr uint16_t kPairMask = 0x3;
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   pdl_launch_dependents();
@@ -184,7 +188,7 @@ conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   } else {
     const int ew = warp - 2;
     const int quad = warp & 3, hsel = ew >> 2;
-    uint8_t* stage_out = smem + S::kOffOut + ew * 2 * S::kStageOutBytes;
+    uint8_t* stage_out = smem + S::kOffOut + ew * S::kOutBufs * S::kStageOutBytes;
     const uint32_t stage_u32 = smem_u32(stage_out);
     uint64_t* rbar = res_full + ew * 2;
     const int cout0 = cb * 128 + quad * 32;  // this warp's 32 couts
@@ -208,7 +212,7 @@ conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (int j = 0; j < 8; ++j) {
         float v[16];
         tmem_ld_x16(taddr + j * 16, v);
-        const uint32_t sbuf = (chunk & 1) * S::kStageOutBytes;
+        const uint32_t sbuf = (chunk % S::kOutBufs) * S::kStageOutBytes;
         if constexpr (RES) {
           // the OTHER buffer's store (previous chunk) must have read it before the next residual lands there
           if (lane == 0) {
@@ -219,7 +223,7 @@ conv1x1_t_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           __syncwarp();
           mbar_wait(&rbar[chunk & 1], (chunk >> 1) & 1);
         } else {
-          if (lane == 0) tma_store_wait_read<1>();  // the staging buffer written two chunks ago has been read
+          if (lane == 0) tma_store_wait_read<S::kOutBufs - 1>();  // the staging buffer about to be written has been read
           __syncwarp();
         }
         tmem_ld_wait();
@@ -302,7 +306,7 @@ template <int CIN_MAX, bool RES, bool PAIR>
 static int launch_onet(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const CUtensorMap& tmap_r,
                        const float* w_img, const float* scale, const float* shift, long long m_rows, int Cin, int Cout,
                        int relu, int bn_packed, int relu_after, int max_ctas, cudaStream_t stream) {
-  using S = OneTSmem<CIN_MAX, PAIR>;
+  using S = OneTSmem<CIN_MAX, PAIR, RES>;
   static unsigned long long configured = 0;
   int dev_ = 0;
   cudaGetDevice(&dev_);
