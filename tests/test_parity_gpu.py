@@ -270,7 +270,8 @@ def test_back_to_back_launches_are_ordered(lib_loaded, torch_cuda, n):
 
 
 @pytest.mark.parametrize("n,cin,cout", [(1, 32, 128), (2, 96, 256), (3, 64, 384), (7, 512, 128), (4, 256, 1024),
-                                        (2, 1024, 256), (1, 128, 512), (6, 2048, 128)])
+                                        (2, 1024, 256), (1, 128, 512), (6, 2048, 128),
+                                        (131, 128, 512), (77, 256, 1024), (203, 64, 128), (90, 160, 640)])
 def test_1x1_ragged_batches(lib_loaded, torch_cuda, n, cin, cout):
     torch = torch_cuda
     rs = np.random.RandomState(200 + n)
@@ -536,7 +537,10 @@ def test_run_host_1x1_and_argument_checks(lib_loaded, torch_cuda):
 
 
 @pytest.mark.parametrize("n,cin,cout", [(1, 128, 512), (1, 256, 1024), (3, 64, 384), (32, 128, 512), (47, 256, 1024),
-                                        (256, 128, 512), (256, 256, 1024)])
+                                        (256, 128, 512), (256, 256, 1024),
+                                        # the transposed wide-Cout kernel (conv1x1_t_kernel.cu: CTA pairs, couts on M) with a
+                                        # ragged last 256-pixel tile; 96 -> 384: 128-cout blocks that do not pair up
+                                        (150, 128, 512), (75, 256, 1024), (101, 256, 1024), (199, 96, 384)])
 @pytest.mark.parametrize("relu_after", [True, False])
 def test_1x1_fused_residual_add(lib_loaded, torch_cuda, n, cin, cout, relu_after):
     """f2: the residual add (+ final ReLU) fused into the 1x1 `_out` epilogue (wg_run_residual) -- the step the
