@@ -997,8 +997,10 @@ int direct_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const fl
 #define WG_DIR(CL_)                                                                                                  \
   return launch_direct<CL_>(tmap_x, tmap_y, w_img, scale, shift, n_img, Cin, Cout, relu, out_padded, max_ctas, mixed != 0, \
                             stream)
-  if (cl == 4) WG_DIR(4);
-  if (cl == 2) WG_DIR(2);
+  if constexpr (kDev) {  // weight-multicast clusters: measured no faster (profiles/direct3x3_r02.md), developer build only
+    if (cl == 4) WG_DIR(4);
+    if (cl == 2) WG_DIR(2);
+  }
   WG_DIR(1);
 #undef WG_DIR
 }
