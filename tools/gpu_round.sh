@@ -13,7 +13,7 @@ NCU="ncu --set full --clock-control none --import-source on --launch-count 1 -f"
 $NCU -k regex:conv3x3_direct_kernel --launch-skip 6 -o gpurun_out/prof_dir256_r02 $Q > gpurun_out/ncu_a.log 2>&1; echo "ncu rc=$?"
 $NCU -k regex:conv3x3_direct_kernel --launch-skip 18 -o gpurun_out/prof_dir128_r02 $Q > gpurun_out/ncu_b.log 2>&1; echo "ncu rc=$?"
 $NCU -k regex:conv1x1_bn_act_kernel --launch-skip 6 -o gpurun_out/prof_one_512_128_r02 $Q > gpurun_out/ncu_c.log 2>&1; echo "ncu rc=$?"
-$NCU -k regex:conv1x1_bn_act_kernel --launch-skip 30 -o gpurun_out/prof_one_128_512_r02 $Q > gpurun_out/ncu_d.log 2>&1; echo "ncu rc=$?"
-$NCU -k regex:conv1x1_bn_act_kernel --launch-skip 54 -o gpurun_out/prof_one_1024_256_r02 $Q > gpurun_out/ncu_e.log 2>&1; echo "ncu rc=$?"
-$NCU -k regex:conv1x1_bn_act_kernel --launch-skip 78 -o gpurun_out/prof_one_256_1024_r02 $Q > gpurun_out/ncu_f.log 2>&1; echo "ncu rc=$?"
+$NCU -k regex:conv1x1_t_kernel --launch-skip 6 -o gpurun_out/prof_one_128_512_r02 $Q > gpurun_out/ncu_d.log 2>&1; echo "ncu rc=$?"
+$NCU -k regex:conv1x1_bn_act_kernel --launch-skip 30 -o gpurun_out/prof_one_1024_256_r02 $Q > gpurun_out/ncu_e.log 2>&1; echo "ncu rc=$?"
+$NCU -k regex:conv1x1_t_kernel --launch-skip 30 -o gpurun_out/prof_one_256_1024_r02 $Q > gpurun_out/ncu_f.log 2>&1; echo "ncu rc=$?"
 ls -la gpurun_out/*.ncu-rep
