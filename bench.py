@@ -40,8 +40,9 @@ N_SETS = 4                                             # rotating buffer sets: 4
 
 
 def workload_name():
-    return ("conv3x3 Winograd F(2x2,3x3)+BN+ReLU Cin=Cout=256 14x14 (16x16 frames), N=256 images/GPU/step, "
-            "fp32 I/O, tf32 MMA [BASELINE configs[1] shape at configs[3] batch]")
+    return ("fused conv3x3+BN+ReLU (the reference's Winograd layer kernel_256) Cin=Cout=256 14x14 (16x16 frames), "
+            "N=256 images/GPU/step, fp32 I/O, tf32 MMA [BASELINE configs[1] shape at configs[3] batch]; this repo "
+            "computes it as a direct convolution on tcgen05 at this batch size, F(2x2,3x3) Winograd below 6 images")
 
 
 def make_params(seed=0):
