@@ -52,3 +52,14 @@ def test_winograd_throughput_kernel_behind_the_direct_engine():
     direct-convolution engine): the full-fold kernel still agrees with the oracle on the shapes that now default to the
     direct engine, N = 256 included (tools/ff_check.py: parity on awkward shapes + sampled images at N = 256)."""
     _run_ff_check({"WG_3X3_DIRECT_MIN": "1000000"})
+
+
+def test_direct_kernel_cluster_variants():
+    """conv3x3_direct_kernel<2> / <4>: clusters of 2 / 4 images sharing each weight block by multicast (measured no faster
+    than CL = 1, developer build only): still agree with the oracle, odd batches included (the last group repeats the
+    last image)."""
+    assert os.path.exists(DEV_LIB)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "direct_check.py"), "--ns", "3,37", "--bo", "2,4,10",
+                        "--shapes", "128x128,64x256", "--iters", "3"],
+                       env=dict(os.environ), capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -29,6 +29,7 @@ def main():
     L.wg_dev_direct_pack.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.wg_dev_direct_run.argtypes = [vp] * 5 + [ctypes.c_int] * 7 + [vp]
     dev = torch.device("cuda", 0)
+    bad = 0
     for shape in args.shapes.split(","):
         c, k = [int(v) for v in shape.split("x")]
         rs = np.random.RandomState(c + k)
@@ -81,8 +82,13 @@ def main():
                         e1.record()
                         torch.cuda.synchronize()
                         us = e0.elapsed_time(e1) * 1e3 / args.iters
+                        tol = 1e-2 if op16 == 1 else 1e-3
+                        ok = bool(err <= tol) and border
+                        bad += 0 if ok else 1
                         print(f"direct {c}->{k} N={n} mode={bo} padded={padded}: rel_err {err:.2e} "
-                              f"border_zero {border}  {us:8.2f} us", flush=True)
+                              f"border_zero {border}  {us:8.2f} us{'' if ok else '  FAILED'}", flush=True)
+    print(f"{bad} failures")
+    sys.exit(1 if bad else 0)
 
 
 if __name__ == "__main__":
