@@ -121,7 +121,9 @@ conv3x3_direct_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_c = Cin / 32;  // 32-channel chunks
-  const int n_cb = Cout / 128;
+  // 128-cout blocks; a layer with Cout % 128 == 64 has a last block whose upper 64 weight rows are zeros in the packed
+  // image (half of those MMAs' rows are idle) and whose upper two epilogue quadrants store nothing
+  const int n_cb = (Cout + 127) / 128;
   const int first_item = (int)blockIdx.x / CL;
   const int item_stride = (int)gridDim.x / CL;
   // this CTA's image of an item; the last group of an odd batch repeats the last image (same values stored twice)
@@ -210,11 +212,12 @@ conv3x3_direct_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const int img = WG_DIR_IMG(w);
       const uint32_t buf = it & 1;
       const int cout0 = w.cb * 128 + quad * 32;  // this warp's 32 couts
-      const float sc = __ldg(scale + cout0 + lane), sh = __ldg(shift + cout0 + lane);
+      const bool couts_here = cout0 < Cout;      // false: padding rows of the last block (warp-uniform)
+      const float sc = couts_here ? __ldg(scale + cout0 + lane) : 0.f, sh = couts_here ? __ldg(shift + cout0 + lane) : 0.f;
       const int rows = w.half < 0 ? 14 : 7;          // frame rows of the item
       const int y_first = 1 + (w.half > 0 ? 7 : 0);  // frame row of accumulator columns 0..15
-      const int j0 = hsel ? (rows + 1) / 2 : 0, j1 = hsel ? rows : (rows + 1) / 2;
-      if (out_padded == 1 && lane == 0) {
+      const int j0 = hsel ? (rows + 1) / 2 : 0, j1 = (!couts_here) ? j0 : (hsel ? rows : (rows + 1) / 2);
+      if (out_padded == 1 && lane == 0 && couts_here) {
         // the frame's zero rows y = 0 / y = 15 (not with WG_OUT_INTERIOR_ONLY, out_padded == 3)
         if (hsel == 0 && w.half <= 0) {
           tma_tensor_2d_s2g(&tmap_y, smem + S::kOffZero, cout0, img * 256);
@@ -331,7 +334,7 @@ conv3x3_direct_gen_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_c = Cin / 32;
-  const int n_cb = Cout / 128;
+  const int n_cb = (Cout + 127) / 128;  // the last block may be half padding (Cout % 128 == 64), see the 14x14 kernel
   const int frame = g.Hf * g.Wf;
   const int first_item = (int)blockIdx.x, item_stride = (int)gridDim.x;
   // item -> (cout block, first image, first frame row of the range)
@@ -413,7 +416,8 @@ conv3x3_direct_gen_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
       WG_GEN_ITEM(item, cb, img0, y0);
       const uint32_t buf = it & 1;
       const int cout0 = cb * 128 + quad * 32;
-      const float sc = __ldg(scale + cout0 + lane), sh = __ldg(shift + cout0 + lane);
+      const bool couts_here = cout0 < Cout;  // false: padding rows of the last block (warp-uniform): nothing to store
+      const float sc = couts_here ? __ldg(scale + cout0 + lane) : 0.f, sh = couts_here ? __ldg(shift + cout0 + lane) : 0.f;
       // destinations of this warp's columns: entry = (output pixel index << 1) | store-zero, or -1 = no store
       for (int j = j0 * 16 + lane; j < j1 * 16; j += 32) {
         const int q = y0 * g.Wf + j;
@@ -423,9 +427,9 @@ conv3x3_direct_gen_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
         int e = -1;
         if (in_batch && out_padded) e = ((img * frame + rem) << 1) | (interior ? 0 : 1);
         else if (in_batch && interior) e = ((img * g.H + fy - 1) * g.W + fx - 1) << 1;
-        tab[j - j0 * 16] = e;
+        tab[j - j0 * 16] = couts_here ? e : -1;
       }
-      if (out_padded) {
+      if (out_padded && couts_here) {
         // frame rows no item range covers: row 0 of the first image of the range (hsel 0) and what lies behind the last
         // covered row of its last image (hsel 1); zeros, this warp's 32 couts
         const int band = ((item / n_cb) % g.bands);
@@ -799,7 +803,8 @@ __global__ void direct_pack16_kernel(const float* __restrict__ w, uint16_t* __re
 // to TF32.
 __global__ void direct_pack_kernel(const float* __restrict__ w, float* __restrict__ w_img, int Cin, int Cout) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Cin * Cout * 9) return;
+  const int cout_pad = (Cout + 127) / 128 * 128;  // rows beyond Cout: zeros
+  if (idx >= Cin * cout_pad * 9) return;
   const int t = idx % 9;
   const int ci = (idx / 9) % Cin;
   const int co = idx / (9 * Cin);
@@ -807,12 +812,12 @@ __global__ void direct_pack_kernel(const float* __restrict__ w, float* __restric
   const int c = ci / 32, kk = ci % 32;
   const int q = (kk >> 2) ^ (r & 7);
   const size_t blk = ((size_t)nt * (Cin / 32) + c) * 9 + t;
-  w_img[blk * (size_t)(128 * 32) + (size_t)r * 32 + q * 4 + (kk & 3)] = to_tf32_rn(w[idx]);
+  w_img[blk * (size_t)(128 * 32) + (size_t)r * 32 + q * 4 + (kk & 3)] = co < Cout ? to_tf32_rn(w[idx]) : 0.f;
 }
 
 // op16: 0 = TF32 image (fp32 words), 1 = bf16, 2 = fp16
 int direct_pack_launch(const float* w, float* w_img, int Cin, int Cout, int op16, cudaStream_t stream) {
-  const int n = Cin * Cout * 9;
+  const int n = Cin * (op16 ? Cout : (Cout + 127) / 128 * 128) * 9;
   if (op16) direct_pack16_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, reinterpret_cast<uint16_t*>(w_img), Cin, Cout,
                                                                     op16 == 2);
   else direct_pack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, w_img, Cin, Cout);
@@ -852,7 +857,7 @@ int direct_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float
                       int n_img, int Cin, int Cout, int relu, int out_padded, int max_ctas, const DirGeo& g,
                       cudaStream_t stream) {
   using S = DirGenSmem;
-  if (Cin % 32 != 0 || Cout % 128 != 0) return WG_ERR_ARG;
+  if (Cin % 32 != 0 || Cout % 64 != 0) return WG_ERR_ARG;
   static unsigned long long configured = 0;
   int dev_ = 0;
   cudaGetDevice(&dev_);
@@ -864,7 +869,7 @@ int direct_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float
     configured |= bit;
   }
   const long long units = ((long long)n_img + g.G - 1) / g.G * g.bands;
-  const long long n_items = units * (Cout / 128);
+  const long long n_items = units * ((Cout + 127) / 128);
   long long grid = n_items < max_ctas ? n_items : max_ctas;
   if (grid < 1) grid = 1;
   cudaLaunchConfig_t cfg = {};
@@ -897,7 +902,7 @@ static int launch_direct(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, c
       return WG_ERR_CUDA;
     configured |= bit;
   }
-  const int n_cb = Cout / 128;
+  const int n_cb = (Cout + 127) / 128;
   const long long n_grp = ((long long)n_img + CL - 1) / CL;  // groups of CL images
   long long n_clusters = max_ctas / CL;
   if (n_clusters < 1) n_clusters = 1;
@@ -993,7 +998,7 @@ int direct16_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const 
 int direct_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
                   const float* shift, int n_img, int Cin, int Cout, int cl, int relu, int out_padded, int max_ctas,
                   int mixed, cudaStream_t stream) {
-  if (Cin % 32 != 0 || Cout % 128 != 0) return WG_ERR_ARG;
+  if (Cin % 32 != 0 || Cout % 64 != 0) return WG_ERR_ARG;
 #define WG_DIR(CL_)                                                                                                  \
   return launch_direct<CL_>(tmap_x, tmap_y, w_img, scale, shift, n_img, Cin, Cout, relu, out_padded, max_ctas, mixed != 0, \
                             stream)

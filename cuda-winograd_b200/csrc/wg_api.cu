@@ -223,9 +223,11 @@ static void layer_plan(wg_layer* L) {
     // other map sizes: TF32 only, geometry as launch parameters (direct_gen_geo decides whether the map fits)
     L->dgen = !ff::geo_is_ref(L->geo) && L->dtype == WG_TF32 &&
               direct_gen_geo(L->geo.H, L->geo.W, L->geo.Hf, L->geo.Wf, &L->dgeo);
-    const bool dir_ok = (ff::geo_is_ref(L->geo) || L->dgen) && L->cout % 128 == 0 &&
+    // (TF32: a last block of 64 couts is zero-padded to 128 in the image; 16-bit operands: whole 128-cout blocks only)
+    const bool dir_ok = (ff::geo_is_ref(L->geo) || L->dgen) && L->cout % (L->dtype == WG_TF32 ? 64 : 128) == 0 &&
                         L->cin % (L->dtype == WG_TF32 ? 32 : 64) == 0;
-    L->img_bytes[5] = dir_ok ? (size_t)9 * L->cin * L->cout * (L->dtype == WG_TF32 ? 4 : 2) : 0;
+    const size_t cout_pad = (size_t)(L->cout + 127) / 128 * 128;
+    L->img_bytes[5] = dir_ok ? (size_t)9 * L->cin * (L->dtype == WG_TF32 ? cout_pad * 4 : (size_t)L->cout * 2) : 0;
   } else {
     L->tile_n = (L->cout % 256 == 0 && L->dtype == WG_TF32) ? 256 : 128;  // bf16 operands: 128-wide N-tiles
     L->img_bytes[0] = (size_t)L->cin * L->cout * (L->dtype == WG_TF32 ? 4 : 2);

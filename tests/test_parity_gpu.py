@@ -139,7 +139,7 @@ def test_3x3_throughput_kernel_variants(lib_loaded, torch_cuda, n, c, k):
 
 
 @pytest.mark.parametrize("n,c,k", [(6, 256, 256), (11, 128, 128), (13, 32, 128), (37, 64, 256), (75, 128, 384),
-                                   (149, 256, 128), (160, 96, 128)])
+                                   (149, 256, 128), (160, 96, 128), (21, 64, 64), (40, 128, 192), (150, 32, 320)])
 @pytest.mark.parametrize("relu", [True, False])
 def test_3x3_direct_convolution_engine(lib_loaded, torch_cuda, n, c, k, relu):
     """conv3x3_direct_kernel.cu (14x14, Cin % 32 == 0 (16-bit operands: 64), Cout % 128 == 0; TF32 from 6 / 11 images
@@ -641,7 +641,9 @@ def test_layer_blob_round_trip(lib_loaded, torch_cuda, tmp_path, kind, dtype):
                                         # TF32 with C % 32 == 0, K % 128 == 0: the direct-convolution kernel with runtime
                                         # geometry (row bands of one image / several small images per work item)
                                         (56, 56, 64, 128, 2), (7, 7, 512, 512, 1), (10, 20, 32, 128, 3), (5, 5, 64, 128, 7),
-                                        (3, 3, 32, 128, 200), (28, 28, 128, 256, 33), (21, 9, 32, 128, 6)])
+                                        (3, 3, 32, 128, 200), (28, 28, 128, 256, 33), (21, 9, 32, 128, 6),
+                                        # K % 128 == 64: the last 128-cout block of the direct kernel is half zero padding
+                                        (56, 56, 64, 64, 5), (28, 28, 32, 192, 7), (7, 7, 64, 320, 9)])
 def test_3x3_other_map_sizes(lib_loaded, torch_cuda, h, w, c, k, n):
     """wg_conv3x3_create_hw: the fused 3x3 layer on other map sizes than the reference's hard-coded 14x14
     (Kernel128_winograd.cu:26-31,263-265) -- even (28x28x128, 56x56x64) and odd (7x7x512: edge tiles masked) sizes, ragged
