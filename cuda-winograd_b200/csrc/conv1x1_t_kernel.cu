@@ -298,8 +298,14 @@ bool onet_pair(int Cout) {
 bool onet_eligible(long long m_rows, int Cin, int Cout, int max_ctas) {
   if (Cin % 32 != 0 || Cin > 256 || Cout % 128 != 0 || Cout < 2 * Cin) return false;
   const long long n_cb = Cout / 128, n_pt = (m_rows + 255) / 256;
-  // throughput regime only: every CTA gets several pixel tiles of its cout block
-  return max_ctas >= n_cb && n_pt >= 3 * (max_ctas / n_cb);
+  // from one pixel tile per CTA on (measured against conv1x1_bn_act_kernel, profiles/one_ablation_r02.md: ahead from
+  // there, level below). Developer build: WG_ONE_T_MIN = tiles per CTA from which the kernel is used, in quarters.
+  static int q = -1;
+  if (q < 0) {
+    const char* e = dev_env("WG_ONE_T_MIN");
+    q = e ? atoi(e) : 4;
+  }
+  return max_ctas >= n_cb && 4 * n_pt >= q * (max_ctas / n_cb);
 }
 
 template <int CIN_MAX, bool RES, bool PAIR>
