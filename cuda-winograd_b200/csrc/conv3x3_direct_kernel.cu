@@ -488,7 +488,8 @@ conv3x3_direct_gen_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
 }
 
 // geometry of the direct kernel for an H x W map in its Hf x Wf frame; false = not supported (the Winograd kernel runs)
-bool direct_gen_geo(int H, int W, int Hf, int Wf, DirGeo* out) {
+// (max_rows: rows an activation stage can hold -- 384 for the TF32 kernel, 304 for the 16-bit one)
+bool direct_gen_geo(int H, int W, int Hf, int Wf, int max_rows, DirGeo* out) {
   DirGeo g{};
   g.H = H, g.W = W, g.Hf = Hf, g.Wf = Wf;
   g.halo = ((Wf + 1) + 7) / 8 * 8;
@@ -504,16 +505,17 @@ bool direct_gen_geo(int H, int W, int Hf, int Wf, DirGeo* out) {
     g.G = 1;
     g.R = 256 / Wf;
     if (g.R > H) g.R = H;
+    while (g.R >= 1 && (g.R * Wf + 15) / 16 * 16 + 2 * g.halo > max_rows) --g.R;  // a shorter band for a smaller stage
     if (g.R < 1) return false;
     g.bands = (H + g.R - 1) / g.R;
     n_px = g.R * Wf;
   }
   g.n_pad = (n_px + 15) / 16 * 16;
   const int rows = g.n_pad + 2 * g.halo;
-  if (g.n_pad > 256 || rows > DirGenSmem::kXRowsMax) return false;
+  if (g.n_pad > 256 || rows > max_rows) return false;
   g.n_boxes = (rows + 255) / 256;
   g.box_rows = ((rows + g.n_boxes - 1) / g.n_boxes + 7) / 8 * 8;  // multiple of 8 rows: every box 1024-byte aligned
-  if (g.n_boxes * g.box_rows > DirGenSmem::kXRowsMax) return false;
+  if (g.n_boxes * g.box_rows > max_rows) return false;
   *out = g;
   return true;
 }
@@ -774,6 +776,271 @@ conv3x3_direct16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---- 16-bit operands on other map sizes: conv3x3_direct16_kernel's pipeline (fp32 staging -> converter warps -> 16-bit
+// operand tile) with conv3x3_direct_gen_kernel's geometry (DirGeo) and epilogue. Stages hold up to 304 rows (28x28: 8 frame
+// rows + halo; 56x56: 3 rows; 7x7: two images).
+struct Dir16GenSmem {
+  static constexpr int kSF = 2, kSO = 2, kSW = 3;
+  static constexpr int kXRowsMax = 304;
+  static constexpr uint32_t kFBytes = kXRowsMax * 128;
+  static constexpr uint32_t kOBytes = kXRowsMax * 128;
+  static constexpr uint32_t kWBytes = 128 * 128;
+  static constexpr uint32_t kStageOutBytes = 16 * 128;
+  static constexpr uint32_t kOffF = 0;
+  static constexpr uint32_t kOffO = kOffF + kSF * kFBytes;
+  static constexpr uint32_t kOffW = kOffO + kSO * kOBytes;
+  static constexpr uint32_t kOffOut = kOffW + kSW * kWBytes;
+  static constexpr uint32_t kOffTab = kOffOut + 8 * kStageOutBytes;
+  static constexpr uint32_t kOffBar = kOffTab + 8 * 128 * 4;
+  static constexpr uint32_t kNumBars = 2 * kSF + 2 * kSO + 2 * kSW + 4;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr uint32_t kTotal = kOffTmemPtr + 16 + 1024;
+  static_assert(kOffO % 1024 == 0 && kOffW % 1024 == 0 && kOffOut % 1024 == 0, "swizzled buffers: 1024-byte aligned");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+template <bool FP16>
+__global__ void __launch_bounds__(kDir16Threads, 1)
+conv3x3_direct16_gen_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                        const uint16_t* __restrict__ w_img, const float* __restrict__ scale,
+                        const float* __restrict__ shift, float* __restrict__ y, int n_img, int Cin, int Cout, int relu,
+                        int out_padded, int n_items, const DirGeo g) {
+  using S = Dir16GenSmem;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
+  uint64_t* f_full = bars;
+  uint64_t* f_empty = f_full + S::kSF;
+  uint64_t* o_ready = f_empty + S::kSF;
+  uint64_t* o_empty = o_ready + S::kSO;
+  uint64_t* w_full = o_empty + S::kSO;
+  uint64_t* w_empty = w_full + S::kSW;
+  uint64_t* acc_full = w_empty + S::kSW;  // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::kOffTmemPtr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < S::kSF; ++i) mbar_init(&f_full[i], 1), mbar_init(&f_empty[i], 4);   // 4 converter warps
+    for (int i = 0; i < S::kSO; ++i) mbar_init(&o_ready[i], 4), mbar_init(&o_empty[i], 1);
+    for (int i = 0; i < S::kSW; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&acc_full[i], 1), mbar_init(&acc_empty[i], 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_c = Cin / 64;  // 64-channel chunks
+  const int n_cb = Cout / 128;
+  const int frame = g.Hf * g.Wf;
+  const int x_rows = g.n_boxes * g.box_rows;  // rows of a staging half-chunk / an operand tile
+  const int first_item = (int)blockIdx.x, item_stride = (int)gridDim.x;
+  // item -> (cout block, first image, first frame row of the range), as in conv3x3_direct_gen_kernel
+#define WG_GEN_ITEM(item, cb_, img0_, y0_)            \
+  const int cb_ = (item) % n_cb;                      \
+  const int u_##cb_ = (item) / n_cb;                  \
+  const int img0_ = (u_##cb_ / g.bands) * g.G;        \
+  const int y0_ = 1 + (u_##cb_ % g.bands) * g.R
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t sf = 0, pf = 0, sw = 0, pw = 0;
+      pdl_wait();  // the frame comes from the previous kernel in the stream
+      // staging of (item, chunk): two half-chunks of 32 fp32 channels
+      auto load_x = [&](int item, int c) {
+        WG_GEN_ITEM(item, cb, img0, y0);
+        (void)cb;
+        const int p0 = img0 * frame + y0 * g.Wf;
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&f_empty[sf], pf ^ 1);
+          mbar_arrive_expect_tx(&f_full[sf], (uint32_t)x_rows * 128);
+          for (int b = 0; b < g.n_boxes; ++b)
+            tma_tensor_2d_g2s(smem + S::kOffF + sf * S::kFBytes + b * (g.box_rows * 128), &tmap_x, c * 64 + h * 32,
+                              p0 - g.halo + b * g.box_rows, &f_full[sf]);
+          if (++sf == S::kSF) { sf = 0; pf ^= 1; }
+        }
+      };
+      if (first_item < n_items) load_x(first_item, 0);
+      for (int item = first_item; item < n_items; item += item_stride) {
+        const uint8_t* w_src = reinterpret_cast<const uint8_t*>(w_img) + (size_t)(item % n_cb) * n_c * 9 * S::kWBytes;
+        for (int c = 0; c < n_c; ++c) {
+          // activations one chunk ahead of the weights
+          if (c + 1 < n_c) load_x(item, c + 1);
+          else if (item + item_stride < n_items) load_x(item + item_stride, 0);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&w_empty[sw], pw ^ 1);
+            mbar_arrive_expect_tx(&w_full[sw], S::kWBytes);
+            tma_bulk_g2s(smem + S::kOffW + sw * S::kWBytes, w_src + (size_t)(c * 9 + t) * S::kWBytes, S::kWBytes,
+                         &w_full[sw]);
+            if (++sw == S::kSW) { sw = 0; pw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t o_base = smem_u32(smem + S::kOffO);
+      const uint32_t w_base = smem_u32(smem + S::kOffW);
+      uint32_t so = 0, po = 0, sw = 0, pw = 0, it = 0;
+      const uint32_t idesc = make_idesc(FP16 ? kFmtF16 : kFmtBF16, 128, (uint32_t)g.n_pad);
+      for (int item = first_item; item < n_items; item += item_stride, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kDirAccCols;
+        for (int c = 0; c < n_c; ++c) {
+          mbar_wait(&o_ready[so], po);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&w_full[sw], pw);
+            tc_fence_after();
+            const int rshift = (t / 3 - 1) * g.Wf + (t % 3 - 1);
+            const uint32_t x_tap = o_base + so * S::kOBytes + (uint32_t)(g.halo + rshift) * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // K = 16 per MMA: 32 bytes of a row
+              const uint64_t a_desc = make_smem_desc(w_base + sw * S::kWBytes + k * 32, 0, 1024, kLayoutSW128);
+              const uint64_t b_desc = make_smem_desc(x_tap + k * 32, 0, 1024, kLayoutSW128);
+              umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&w_empty[sw]);
+            if (++sw == S::kSW) { sw = 0; pw ^= 1; }
+          }
+          umma_commit(&o_empty[so]);
+          if (++so == S::kSO) { so = 0; po ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp >= 10) {
+    // converter warps: fp32 staging half-chunk -> 16-bit operand tile. Unit = (row r, 16-byte output chunk qq): 8 floats
+    // from the two swizzled 16-byte chunks 2qq, 2qq+1 of staging row r -> chunk (4h + qq) ^ (r & 7) of tile row r.
+    const int ct = threadIdx.x - 320;
+    uint32_t sf = 0, pf = 0, so = 0, po = 0;
+    const uint32_t f_base = smem_u32(smem + S::kOffF), o_base = smem_u32(smem + S::kOffO);
+    for (int item = first_item; item < n_items; item += item_stride)
+      for (int c = 0; c < n_c; ++c) {
+        mbar_wait(&o_empty[so], po ^ 1);
+        tc_fence_after();
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&f_full[sf], pf);
+          const uint32_t src = f_base + sf * S::kFBytes, dst = o_base + so * S::kOBytes;
+#pragma unroll 2
+          for (int u = ct; u < x_rows * 4; u += 128) {
+            const int r = u >> 2, qq = u & 3, sw7 = r & 7;
+            const float4 a = ld_shared_v4(src + r * 128 + (((2 * qq) ^ sw7) << 4));
+            const float4 b = ld_shared_v4(src + r * 128 + (((2 * qq + 1) ^ sw7) << 4));
+            uint32_t p0, p1, p2, p3;
+            if constexpr (FP16) {
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(a.y), "f"(a.x));
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(a.w), "f"(a.z));
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b.y), "f"(b.x));
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b.w), "f"(b.z));
+            } else {
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(a.y), "f"(a.x));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(a.w), "f"(a.z));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b.y), "f"(b.x));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b.w), "f"(b.z));
+            }
+            st_shared_v4(dst + r * 128 + (((4 * h + qq) ^ sw7) << 4), __uint_as_float(p0), __uint_as_float(p1),
+                         __uint_as_float(p2), __uint_as_float(p3));
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&f_empty[sf]);  // this warp is done reading the staging slot
+          if (++sf == S::kSF) { sf = 0; pf ^= 1; }
+        }
+        fence_proxy_async_smem();  // the tile was written by the generic proxy, the MMA reads it through the async proxy
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_ready[so]);
+        if (++so == S::kSO) { so = 0; po ^= 1; }
+      }
+  } else {
+    // epilogue: as in conv3x3_direct_gen_kernel (per-warp table of destinations, plain 128-byte row stores)
+    const int ew = warp - 2;
+    const int quad = warp & 3, hsel = ew >> 2;
+    const uint32_t stage_u32 = smem_u32(smem + S::kOffOut + ew * S::kStageOutBytes);
+    int* tab = reinterpret_cast<int*>(smem + S::kOffTab) + ew * 128;
+    const int n_chunks = g.n_pad / 16;
+    const int j0 = hsel ? (n_chunks + 1) / 2 : 0, j1 = hsel ? n_chunks : (n_chunks + 1) / 2;
+    const int sub = lane & 7, pxs = lane >> 3;
+    uint32_t it = 0;
+    for (int item = first_item; item < n_items; item += item_stride, ++it) {
+      WG_GEN_ITEM(item, cb, img0, y0);
+      const uint32_t buf = it & 1;
+      const int cout0 = cb * 128 + quad * 32;
+      const float sc = __ldg(scale + cout0 + lane), sh = __ldg(shift + cout0 + lane);
+      for (int j = j0 * 16 + lane; j < j1 * 16; j += 32) {
+        const int q = y0 * g.Wf + j;
+        const int img = img0 + q / frame, rem = q % frame, fy = rem / g.Wf, fx = rem % g.Wf;
+        const bool in_batch = img < n_img;
+        const bool interior = fy >= 1 && fy <= g.H && fx >= 1 && fx <= g.W;
+        int e = -1;
+        if (in_batch && out_padded) e = ((img * frame + rem) << 1) | (interior ? 0 : 1);
+        else if (in_batch && interior) e = ((img * g.H + fy - 1) * g.W + fx - 1) << 1;
+        tab[j - j0 * 16] = e;
+      }
+      if (out_padded) {
+        const int band = ((item / n_cb) % g.bands);
+        const int rows_cov = (g.bands == 1) ? g.n_pad / g.Wf : g.R;
+        int zimg = -1, zy0 = 0, zy1 = 0;
+        if (hsel == 0 && band == 0) zimg = img0, zy0 = 0, zy1 = 1;
+        if (hsel == 1 && band == g.bands - 1) {
+          const int last = img0 + g.G - 1;
+          const int covered_to = (g.bands == 1) ? (1 + rows_cov - (g.G - 1) * g.Hf) : (y0 + rows_cov);
+          zimg = last < n_img ? last : -1, zy0 = covered_to > g.H + 1 ? covered_to : g.H + 1, zy1 = g.Hf;
+        }
+        if (zimg >= 0 && zimg < n_img)
+          for (int pz = zy0 * g.Wf + pxs; pz < zy1 * g.Wf; pz += 4)
+            *reinterpret_cast<float4*>(y + ((size_t)zimg * frame + pz) * Cout + cout0 + sub * 4) =
+                make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kDirAccCols;
+#pragma unroll 1
+      for (int j = j0; j < j1; ++j) {
+        float v[16];
+        tmem_ld_x16(taddr + j * 16, v);
+        tmem_ld_wait();
+        const uint32_t dst = stage_u32 + lane * 4;
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          float o = fmaf(sc, v[x], sh);
+          if (relu) o = fmaxf(o, 0.f);
+          st_shared_f32(dst + x * 128, o);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int pxl = i4 * 4 + pxs;
+          const int e = tab[(j - j0) * 16 + pxl];
+          if (e >= 0) {
+            float4 val = ld_shared_v4(stage_u32 + pxl * 128 + sub * 16);
+            if (e & 1) val = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(y + (size_t)(e >> 1) * Cout + cout0 + sub * 4) = val;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+#undef WG_GEN_ITEM
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // Once per layer, 16-bit operands: [K/128][C/64][9 taps][128 couts][64 channels], RN, 128-byte swizzle applied
 // (16-byte chunk q = 8 channels at position q ^ (cout & 7) of the cout's 128-byte row).
 __global__ void direct_pack16_kernel(const float* __restrict__ w, uint16_t* __restrict__ w_img, int Cin, int Cout,
@@ -885,6 +1152,53 @@ int direct_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_direct_gen_kernel, tmap_x, w_img, scale, shift, y, n_img, Cin, Cout,
                                      relu, out_padded, (int)n_items, g);
   return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+template <bool FP16>
+static int launch_direct16_gen(const CUtensorMap& tmap_x, const float* w_img, const float* scale, const float* shift,
+                               float* y, int n_img, int Cin, int Cout, int relu, int out_padded, int max_ctas,
+                               const DirGeo& g, cudaStream_t stream) {
+  using S = Dir16GenSmem;
+  static unsigned long long configured = 0;
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  const unsigned long long bit = 1ull << (dev_ & 63);
+  if (!(configured & bit)) {
+    if (cudaFuncSetAttribute(conv3x3_direct16_gen_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)S::kTotal) != cudaSuccess)
+      return WG_ERR_CUDA;
+    configured |= bit;
+  }
+  const long long units = ((long long)n_img + g.G - 1) / g.G * g.bands;
+  const long long n_items = units * (Cout / 128);
+  long long grid = n_items < max_ctas ? n_items : max_ctas;
+  if (grid < 1) grid = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kDir16Threads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_direct16_gen_kernel<FP16>, tmap_x,
+                                     reinterpret_cast<const uint16_t*>(w_img), scale, shift, y, n_img, Cin, Cout, relu,
+                                     out_padded, (int)n_items, g);
+  return e == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+// 16-bit operands on other map sizes (op16: 1 = bf16, 2 = fp16): Cin % 64 == 0, Cout % 128 == 0, g from
+// direct_gen_geo(..., kDirect16GenMaxRows, ...)
+int direct16_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float* scale, const float* shift, float* y,
+                        int n_img, int Cin, int Cout, int op16, int relu, int out_padded, int max_ctas, const DirGeo& g,
+                        cudaStream_t stream) {
+  if (Cin % 64 != 0 || Cout % 128 != 0 || (op16 != 1 && op16 != 2)) return WG_ERR_ARG;
+  if (g.n_boxes * g.box_rows > Dir16GenSmem::kXRowsMax) return WG_ERR_ARG;
+  if (op16 == 2)
+    return launch_direct16_gen<true>(tmap_x, w_img, scale, shift, y, n_img, Cin, Cout, relu, out_padded, max_ctas, g, stream);
+  return launch_direct16_gen<false>(tmap_x, w_img, scale, shift, y, n_img, Cin, Cout, relu, out_padded, max_ctas, g, stream);
 }
 
 template <int CL>

@@ -220,9 +220,10 @@ static void layer_plan(wg_layer* L) {
     L->img_bytes[4] = (L->dtype == WG_TF32 && L->tile_n != 32 && ff::geo_is_ref(L->geo)) ? fe * 4 : 0;  // tile_n == 32: aliases d_filter
     // the direct-convolution kernel: TF32, reference geometry, 32-channel chunks, 128-cout blocks
     // (16-bit operands: 64-channel chunks, 2-byte elements)
-    // other map sizes: TF32 only, geometry as launch parameters (direct_gen_geo decides whether the map fits)
-    L->dgen = !ff::geo_is_ref(L->geo) && L->dtype == WG_TF32 &&
-              direct_gen_geo(L->geo.H, L->geo.W, L->geo.Hf, L->geo.Wf, &L->dgeo);
+    // other map sizes: geometry as launch parameters (direct_gen_geo decides whether the map fits the kernel's stages)
+    L->dgen = !ff::geo_is_ref(L->geo) &&
+              direct_gen_geo(L->geo.H, L->geo.W, L->geo.Hf, L->geo.Wf,
+                             L->dtype == WG_TF32 ? kDirectGenMaxRows : kDirect16GenMaxRows, &L->dgeo);
     // (TF32: a last block of 64 couts is zero-padded to 128 in the image; 16-bit operands: whole 128-cout blocks only)
     const bool dir_ok = (ff::geo_is_ref(L->geo) || L->dgen) && L->cout % (L->dtype == WG_TF32 ? 64 : 128) == 0 &&
                         L->cin % (L->dtype == WG_TF32 ? 32 : 64) == 0;
@@ -504,12 +505,15 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
   // map sizes other than the reference's run the full-fold kernel only (developer build: not with a superseded generation)
   if (L->kind == 0 && !ref_geo && !(L->dtype == WG_TF32 ? L->tile_n == 96 : L->tm16_ff != 0)) return WG_ERR_ARG;
   if (L->kind == 0 && L->d_filter_direct != nullptr && L->dgen && !(out_flags & 2)) {
-    // other map sizes, TF32: the direct kernel with runtime geometry, every batch size
+    // other map sizes: the direct kernels with runtime geometry, every batch size
     {
       std::lock_guard<std::mutex> lk(L->mu);
       rc = L->tm_xd.get(x, N, &tmap, [&](CUtensorMap* m) { return direct_gen_make_tmap_in(m, x, N, L->cin, L->dgeo); });
     }
     if (rc != WG_OK) return rc;
+    if (L->dtype != WG_TF32)
+      return launched(direct16_gen_launch(tmap, L->d_filter_direct, L->d_scale, L->d_shift, y, N, L->cin, L->cout,
+                                          L->dtype == WG_FP16 ? 2 : 1, L->relu, out_padded, max_ctas, L->dgeo, stream));
     return launched(direct_gen_launch(tmap, L->d_filter_direct, L->d_scale, L->d_shift, y, N, L->cin, L->cout, L->relu,
                                       out_padded, max_ctas, L->dgeo, stream));
   }

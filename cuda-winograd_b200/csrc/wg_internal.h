@@ -111,7 +111,11 @@ struct DirGeo {
   int R, bands, G;
   int n_pad, halo, box_rows, n_boxes;
 };
-bool direct_gen_geo(int H, int W, int Hf, int Wf, DirGeo* out);
+constexpr int kDirectGenMaxRows = 384, kDirect16GenMaxRows = 304;  // rows an activation stage holds (TF32 / 16-bit)
+bool direct_gen_geo(int H, int W, int Hf, int Wf, int max_rows, DirGeo* out);
+int direct16_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float* scale, const float* shift, float* y,
+                        int n_img, int Cin, int Cout, int op16, int relu, int out_padded, int max_ctas, const DirGeo& g,
+                        cudaStream_t stream);
 int direct_gen_make_tmap_in(CUtensorMap* tmap, const float* x, int n_img, int Cin, const DirGeo& g);
 int direct_gen_launch(const CUtensorMap& tmap_x, const float* w_img, const float* scale, const float* shift, float* y,
                       int n_img, int Cin, int Cout, int relu, int out_padded, int max_ctas, const DirGeo& g,

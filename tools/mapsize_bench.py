@@ -45,10 +45,16 @@ def main():
             x[:, 1:h + 1, 1:h + 1] = torch.rand((n, h, h, c), device="cuda") - 0.5
         ys = [torch.empty((n, h, h, c), device="cuda") for _ in range(sets)]
         us = timed(lambda i: layer(xs[i % sets], out=ys[i % sets]))
+        us16 = None
+        if c % 16 == 0 and c % 64 == 0:
+            l16 = wg.Conv3x3BnRelu(w, sc, sh, relu=True, hw=(h, h), dtype=wg.WG_BF16)
+            us16 = timed(lambda i: l16(xs[i % sets], out=ys[i % sets]))
+            l16.close()
         xcs = [x[:, :h + 2, :h + 2].permute(0, 3, 1, 2) for x in xs]  # NCHW view of the NHWC frame (1-px border)
         us_cudnn = timed(lambda i: torch.cudnn_convolution_relu(xcs[i % sets], wt, bt, (1, 1), (0, 0), (1, 1), 1))
         flop = 2.0 * h * h * c * c * 9 * n
-        rows.append(dict(h=h, c=c, n=n, ours_us=round(us, 2), cudnn_tf32_us=round(us_cudnn, 2),
+        rows.append(dict(h=h, c=c, n=n, ours_us=round(us, 2), ours_bf16_operands_us=us16 and round(us16, 2),
+                         cudnn_tf32_us=round(us_cudnn, 2),
                          ours_tflops=round(flop / us / 1e6, 1)))
         print(rows[-1], flush=True)
         layer.close()
