@@ -71,16 +71,22 @@ def main():
     for (n, c, k, dt, tol, hw, padded, tag) in [
             (1, 128, 128, wg.WG_TF32, 1e-3, (14, 14), True, "wino3x3_small_kernel (cluster split-C)"),
             (2, 64, 64, wg.WG_TF32, 1e-3, (14, 14), False, "wino3x3_small_kernel"),
-            (40, 32, 160, wg.WG_TF32, 1e-3, (14, 14), True, "wino3x3_ff_kernel 96+64 slices"),
+            (40, 24, 160, wg.WG_TF32, 1e-3, (14, 14), True, "wino3x3_ff_kernel 96+64 slices (C % 32 != 0)"),
             (131, 16, 96, wg.WG_TF32, 1e-3, (14, 14), False, "wino3x3_ff_kernel ragged, several items per CTA"),
-            (12, 256, 256, wg.WG_TF32, 1e-3, (14, 14), False, "wino3x3_ffw_kernel split-C + narrow"),
-            (24, 256, 128, wg.WG_TF32, 1e-3, (14, 14), True, "wino3x3_ffw_kernel split-C"),
-            (64, 64, 128, wg.WG_TF32, 1e-3, (14, 14), False, "wino3x3_ffw_kernel narrow"),
-            (40, 32, 128, wg.WG_BF16, 1e-2, (14, 14), True, "wino3x3_ff_kernel bf16 operands"),
+            (12, 256, 192, wg.WG_BF16, 1e-2, (14, 14), False, "wino3x3_ffw_kernel bf16, split-C (K % 128 != 0)"),
             (33, 256, 64, wg.WG_FP16, 1e-3, (14, 14), False, "wino3x3_ffw_kernel fp16 operands (C >= 256)"),
+            (40, 32, 64, wg.WG_BF16, 1e-2, (14, 14), True, "wino3x3_ff_kernel bf16 operands"),
             (2, 64, 64, wg.WG_BF16, 1e-2, (14, 14), False, "wino3x3_bn_relu_kernel bf16 small batch (split-C)"),
-            (9, 32, 64, wg.WG_TF32, 1e-3, (28, 28), True, "wino3x3_ff_kernel 28x28"),
-            (21, 32, 96, wg.WG_TF32, 1e-3, (7, 7), True, "wino3x3_ff_kernel 7x7 (masked edge tiles)")]:
+            (9, 24, 64, wg.WG_TF32, 1e-3, (28, 28), True, "wino3x3_ff_kernel 28x28 (C % 32 != 0)"),
+            (21, 32, 96, wg.WG_TF32, 1e-3, (7, 7), True, "wino3x3_ff_kernel 7x7 (masked edge tiles)"),
+            (12, 256, 256, wg.WG_TF32, 1e-3, (14, 14), False, "conv3x3_direct_kernel half-image items"),
+            (75, 128, 128, wg.WG_TF32, 1e-3, (14, 14), True, "conv3x3_direct_kernel mixed schedule, frame"),
+            (150, 32, 192, wg.WG_TF32, 1e-3, (14, 14), True, "conv3x3_direct_kernel K % 128 == 64"),
+            (40, 64, 128, wg.WG_BF16, 1e-2, (14, 14), True, "conv3x3_direct16_kernel bf16"),
+            (9, 128, 256, wg.WG_FP16, 1e-3, (14, 14), False, "conv3x3_direct16_kernel fp16"),
+            (9, 32, 64, wg.WG_TF32, 1e-3, (28, 28), True, "conv3x3_direct_gen_kernel 28x28 row bands"),
+            (21, 64, 128, wg.WG_TF32, 1e-3, (7, 7), True, "conv3x3_direct_gen_kernel 7x7, two images per item"),
+            (5, 64, 128, wg.WG_BF16, 1e-2, (28, 28), True, "conv3x3_direct16_gen_kernel 28x28")]:
         x, w, sc, sh = r3(n, c, k, hw)
         layer = wg.Conv3x3BnRelu(w, sc, sh, relu=True, dtype=dt, hw=hw)
         xd = torch.from_numpy(x).cuda()
@@ -98,7 +104,12 @@ def main():
             (40, 128, 512, wg.WG_TF32, 1e-3, True, False, "conv1x1_bn_act_kernel weight-stationary + residual"),
             (40, 512, 128, wg.WG_TF32, 1e-3, True, False, "conv1x1_bn_act_kernel<128> + residual"),
             (37, 64, 384, wg.WG_BF16, 1e-2, False, True, "conv1x1_bn_act_kernel bf16 operands, padded"),
-            (37, 64, 384, wg.WG_BF16, 1e-2, True, False, "conv1x1_bn_act_kernel bf16 operands + residual")]:
+            (37, 64, 384, wg.WG_BF16, 1e-2, True, False, "conv1x1_bn_act_kernel bf16 operands + residual"),
+            (150, 128, 512, wg.WG_TF32, 1e-3, False, False, "conv1x1_t_kernel<128> pairs, ragged pixel tile"),
+            (150, 128, 512, wg.WG_TF32, 1e-3, True, False, "conv1x1_t_kernel<128> pairs + residual"),
+            (75, 256, 1024, wg.WG_TF32, 1e-3, False, False, "conv1x1_t_kernel<256> pairs, resident slab"),
+            (75, 256, 1024, wg.WG_TF32, 1e-3, True, False, "conv1x1_t_kernel<256> pairs + residual (streamed weights)"),
+            (199, 96, 384, wg.WG_TF32, 1e-3, True, False, "conv1x1_t_kernel<128> no pairs + residual")]:
         x = ((rs.rand(n, 196, cin) - 0.5) * 4).astype(np.float32)
         w = (rs.rand(cin, cout) - 0.5).astype(np.float32)
         sc, sh = (rs.rand(cout) + 0.5).astype(np.float32), (rs.rand(cout) - 0.5).astype(np.float32)
