@@ -169,6 +169,9 @@ struct wg_layer {
   std::vector<float> w_host;  // the raw weights as given to create() (kept for wg_layer_serialize)
   // tensor-map caches
   std::mutex mu;
+  // tm_x / tm_x16 / tm_small / tm_y / tm_res: the Winograd and pixels-on-M 1x1 kernels' maps. tm_xd / tm_yd / tm_ydp: the
+  // direct 3x3 kernels' input, dense-output and frame-output maps; a 1x1 layer uses the same three for the transposed
+  // kernel's input, output and residual maps (a layer is one kind, the boxes never mix).
   TmapCache tm_x, tm_x16, tm_small, tm_y, tm_res, tm_xd, tm_yd, tm_ydp;
   size_t in_px() const { return kind == 0 ? (size_t)geo.Hf * geo.Wf : (size_t)H * W; }
   size_t out_px(int padded) const {
