@@ -31,7 +31,7 @@ WG_OUT_PADDED, WG_OUT_MULTICAST, WG_OUT_RELU_AFTER_ADD, WG_OUT_INTERIOR_ONLY = 1
 # every symbol include/winograd_b200.h, include/wg_legacy.h and include/util.h declare
 ABI_SYMBOLS = (
     "wg_conv3x3_create", "wg_conv1x1_create", "wg_conv3x3_create_hw", "wg_conv1x1_create_hw", "wg_layer_geometry",
-    "wg_frame_dims", "wg_run", "wg_run_residual", "wg_run_host", "wg_host_chunk_schedule",
+    "wg_frame_dims", "wg_direct_geometry", "wg_run", "wg_run_residual", "wg_run_host", "wg_host_chunk_schedule",
     "wg_destroy", "wg_layer_info", "wg_layer_serialize", "wg_layer_deserialize", "wg_layer_save", "wg_layer_load",
     "wg_launch_count", "wg_strerror", "wg_last_cuda_error", "wg_device_count", "wg_fold_bn", "wg_set_max_ctas",
     "wg_measure_tensor_peak",
@@ -75,6 +75,7 @@ def lib() -> ctypes.CDLL:
         L.wg_conv1x1_create_hw.argtypes = L.wg_conv3x3_create_hw.argtypes
         L.wg_layer_geometry.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 4
         L.wg_frame_dims.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 2
+        L.wg_direct_geometry.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         L.wg_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                              ctypes.c_void_p]
         L.wg_run_residual.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
@@ -130,6 +131,18 @@ def frame_dims(h: int, w: int):
     hf, wf = ctypes.c_int(), ctypes.c_int()
     _check(lib().wg_frame_dims(int(h), int(w), ctypes.byref(hf), ctypes.byref(wf)), "wg_frame_dims")
     return hf.value, wf.value
+
+
+def direct_geometry(h: int, w: int, dtype: int = WG_TF32):
+    """Work-item geometry of the direct-convolution 3x3 kernels for an h x w map (host-only; wg_direct_geometry):
+    dict(R, bands, G, n_pad, halo, n_boxes, box_rows, Hf, Wf), or None if the map does not fit those kernels."""
+    out = (ctypes.c_int * 9)()
+    rc = int(lib().wg_direct_geometry(int(h), int(w), int(dtype), out))
+    if rc < 0:
+        _check(rc, "wg_direct_geometry")
+    if rc == 0:
+        return None
+    return dict(zip(("R", "bands", "G", "n_pad", "halo", "n_boxes", "box_rows", "Hf", "Wf"), [int(v) for v in out]))
 
 
 def host_chunk_schedule(n: int):

@@ -664,6 +664,22 @@ int wg_frame_dims(int H, int W, int* frame_h, int* frame_w) {
   return WG_OK;
 }
 
+int wg_direct_geometry(int H, int W, wg_dtype_t dtype, int* out9) {
+  if (!out9 || (dtype != WG_TF32 && dtype != WG_BF16 && dtype != WG_FP16)) return WG_ERR_ARG;
+  ff::Geo g{};
+  const int rc = wino_ff_geo(H, W, &g);
+  if (rc != WG_OK) return rc;
+  DirGeo d{};
+  if (ff::geo_is_ref(g)) {  // the reference geometry has its own kernels: one image (or half of one) per item
+    d.R = 14, d.bands = 1, d.G = 1, d.n_pad = 224, d.halo = 24, d.n_boxes = 2, d.box_rows = 136;
+  } else if (!direct_gen_geo(g.H, g.W, g.Hf, g.Wf, dtype == WG_TF32 ? kDirectGenMaxRows : kDirect16GenMaxRows, &d)) {
+    return 0;
+  }
+  const int v[9] = {d.R, d.bands, d.G, d.n_pad, d.halo, d.n_boxes, d.box_rows, g.Hf, g.Wf};
+  for (int i = 0; i < 9; ++i) out9[i] = v[i];
+  return 1;
+}
+
 int wg_layer_geometry(const wg_layer_t* L, int* H, int* W, int* frame_h, int* frame_w) {
   if (!L) return WG_ERR_ARG;
   if (H) *H = L->H;

@@ -80,6 +80,12 @@ int wg_conv1x1_create_hw(wg_layer_t** out, int Cin, int Cout, int H, int W, cons
 int wg_layer_geometry(const wg_layer_t* layer, int* H, int* W, int* frame_h, int* frame_w);
 /* Frame size of an H x W map (host only, no GPU needed); WG_ERR_ARG for maps the kernels cannot tile (H or W < 3). */
 int wg_frame_dims(int H, int W, int* frame_h, int* frame_w);
+/* How the direct-convolution 3x3 kernels cut an H x W map into work items (host only, no GPU needed; what a layer of
+ * that map size and operand type runs when its channel counts fit the kernel's blocking). Returns 1 and fills
+ * out[0..8] = {rows per item R (0: whole images), bands per image, images per item G, pixels per item rounded up to 16
+ * (the MMA N, <= 256), halo rows, TMA boxes per stage, rows per box, frame_h, frame_w}; 0 if the map does not fit the
+ * kernel (the Winograd kernels run); WG_ERR_ARG (< 0) for a bad argument. */
+int wg_direct_geometry(int H, int W, wg_dtype_t dtype, int* out9);
 
 /* The hot path: ONE kernel launch (conv + BN + optional ReLU) on `cuda_stream` (a cudaStream_t, may be NULL),
  * asynchronous. x and y are DEVICE pointers on the layer's device, 16-byte aligned.

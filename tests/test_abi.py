@@ -225,6 +225,43 @@ def test_host_chunk_schedule_is_bounded(built, n):
     assert built.lib().wg_host_chunk_schedule(0, buf, 2) == 0
 
 
+def test_direct_kernel_geometry_invariants(built):
+    """wg_direct_geometry (host-only): how the direct-convolution 3x3 kernels cut a map into work items. For every map
+    size the frame supports: the MMA N is a multiple of 16 and at most 256, the halo covers one frame row + 1 pixel and
+    keeps the TMA boxes 1024-byte aligned, the boxes cover item + halo on both sides and fit the kernel's stage (384
+    rows TF32, 304 rows 16-bit operands), and the items of an image cover all of its output rows."""
+    assert built.direct_geometry(14, 14) == dict(R=14, bands=1, G=1, n_pad=224, halo=24, n_boxes=2, box_rows=136, Hf=16, Wf=16)
+    g28 = built.direct_geometry(28, 28)
+    assert (g28["R"], g28["bands"], g28["n_pad"]) == (8, 4, 240)
+    g7 = built.direct_geometry(7, 7)
+    assert (g7["bands"], g7["G"], g7["n_pad"]) == (1, 2, 176)
+    assert built.direct_geometry(56, 56)["R"] == 4 and built.direct_geometry(56, 56, built.WG_BF16)["R"] == 3
+    seen = 0
+    for dtype, max_rows in ((built.WG_TF32, 384), (built.WG_BF16, 304)):
+        for h in range(3, 105, 1 if dtype == built.WG_TF32 else 7):
+            for w in range(3, 105, 3):
+                g = built.direct_geometry(h, w, dtype)
+                if g is None:
+                    continue
+                seen += 1
+                if (h, w) == (14, 14):
+                    continue
+                hf, wf = built.frame_dims(h, w)
+                assert (g["Hf"], g["Wf"]) == (hf, wf)
+                assert g["n_pad"] % 16 == 0 and 16 <= g["n_pad"] <= 256
+                assert g["halo"] % 8 == 0 and g["halo"] >= wf + 1
+                rows = g["n_boxes"] * g["box_rows"]
+                assert g["box_rows"] % 8 == 0 and g["box_rows"] <= 256 and g["n_pad"] + 2 * g["halo"] <= rows <= max_rows
+                if g["bands"] == 1 and g["R"] == 0:      # whole images per item
+                    assert g["G"] >= 2 and (g["G"] - 1) * hf * wf + h * wf <= g["n_pad"] < (g["G"] - 1) * hf * wf + h * wf + 16
+                else:                                     # row bands of one image
+                    assert g["G"] == 1 and 1 <= g["R"] <= h and g["bands"] * g["R"] >= h > (g["bands"] - 1) * g["R"]
+                    assert g["R"] * wf <= g["n_pad"] < g["R"] * wf + 16
+    assert seen > 1000
+    buf = (ctypes.c_int * 9)()
+    assert built.lib().wg_direct_geometry(2, 14, 0, buf) < 0 and built.lib().wg_direct_geometry(14, 14, 7, buf) < 0
+
+
 def test_blob_and_residual_calls_fail_loudly_without_gpu(built):
     """No GPU here: deserialising a well-formed header must end in WG_ERR_NODEVICE or WG_ERR_IO, never in a CPU path."""
     L = built.lib()
