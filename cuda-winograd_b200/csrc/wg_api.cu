@@ -172,7 +172,7 @@ struct wg_layer {
   // tm_x / tm_x16 / tm_small / tm_y / tm_res: the Winograd and pixels-on-M 1x1 kernels' maps. tm_xd / tm_yd / tm_ydp: the
   // direct 3x3 kernels' input, dense-output and frame-output maps; a 1x1 layer uses the same three for the transposed
   // kernel's input, output and residual maps (a layer is one kind, the boxes never mix).
-  TmapCache tm_x, tm_x16, tm_small, tm_y, tm_res, tm_xd, tm_yd, tm_ydp;
+  TmapCache tm_x, tm_x16, tm_small, tm_y, tm_res, tm_xd, tm_yd, tm_ydp, tm_xf, tm_yf;  // tm_xf / tm_yf: 1x1 frame output
   size_t in_px() const { return kind == 0 ? (size_t)geo.Hf * geo.Wf : (size_t)H * W; }
   size_t out_px(int padded) const {
     return padded ? (kind == 0 ? (size_t)geo.Hf * geo.Wf : (size_t)one_geo.Hf * one_geo.Wf) : (size_t)H * W;
@@ -577,6 +577,18 @@ static int run_impl(wg_layer_t* L, const float* x, const float* residual, float*
                                      L->cin, L->cout, op16, L->ff_cg2, L->relu, out_flags, max_ctas, L->geo, stream));
     }
   }
+  if (L->kind == 1 && L->dtype == WG_TF32 && out_padded && !residual && ref_geo &&
+      onetf_eligible(N, L->cin, L->cout, max_ctas)) {
+    // chain mode at throughput sizes: the transposed kernel writing the next 3x3 layer's frame, one TMA store per row
+    {
+      std::lock_guard<std::mutex> lk(L->mu);
+      rc = L->tm_xf.get(x, N, &tmap, [&](CUtensorMap* m) { return onetf_make_tmap_in(m, x, (long long)N * px, L->cin, L->cout); });
+      if (rc == WG_OK) rc = L->tm_yf.get(y, N, &tmap_y, [&](CUtensorMap* m) { return onetf_make_tmap_out(m, y, N, L->cout); });
+    }
+    if (rc != WG_OK) return rc;
+    return launched(onetf_launch(tmap, tmap_y, L->d_filter, L->d_scale, L->d_shift, N, L->cin, L->cout, L->relu,
+                                 L->tile_n, (flags & WG_OUT_INTERIOR_ONLY) ? 1 : 0, max_ctas, stream));
+  }
   if (L->kind == 1 && L->dtype == WG_TF32 && !out_padded && onet_min_rows() >= 0 &&
       onet_eligible((long long)N * px, L->cin, L->cout, max_ctas)) {
     // wide-Cout shapes at throughput sizes: couts on M, pixels on N, weight slab resident (conv1x1_t_kernel.cu)
@@ -716,7 +728,7 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
     L->d_x_bytes = 0;
     {
       std::lock_guard<std::mutex> lk(L->mu);  // the freed address may come back with other contents / sizes
-      L->tm_x.clear(), L->tm_x16.clear(), L->tm_small.clear(), L->tm_xd.clear();
+      L->tm_x.clear(), L->tm_x16.clear(), L->tm_small.clear(), L->tm_xd.clear(), L->tm_xf.clear();
     }
     WG_CUDA(cudaMalloc(&L->d_x, xb));
     L->d_x_bytes = xb;
@@ -727,7 +739,7 @@ int wg_run_host(wg_layer_t* L, const float* x_host, float* y_host, int N, int ou
     L->d_y_bytes = 0;
     {
       std::lock_guard<std::mutex> lk(L->mu);
-      L->tm_y.clear(), L->tm_yd.clear(), L->tm_ydp.clear();
+      L->tm_y.clear(), L->tm_yd.clear(), L->tm_ydp.clear(), L->tm_yf.clear();
     }
     WG_CUDA(cudaMalloc(&L->d_y, yb));
     L->d_y_bytes = yb;

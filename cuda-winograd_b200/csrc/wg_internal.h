@@ -130,6 +130,14 @@ int onet_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const CUte
                 const float* scale, const float* shift, long long m_rows, int Cin, int Cout, int relu, int bn_packed,
                 int relu_after, int max_ctas, cudaStream_t stream);
 
+// frame output (WG_OUT_PADDED, 14x14 maps) of the transposed kernel: items of 16 image rows, one TMA store per frame row
+bool onetf_eligible(int n_img, int Cin, int Cout, int max_ctas);
+int onetf_make_tmap_in(CUtensorMap* tmap, const float* x, long long m_rows, int Cin, int Cout);
+int onetf_make_tmap_out(CUtensorMap* tmap, const float* y_frame, int n_img, int Cout);
+int onetf_launch(const CUtensorMap& tmap_x, const CUtensorMap& tmap_y, const float* w_img, const float* scale,
+                 const float* shift, int n_img, int Cin, int Cout, int relu, int bn_packed, int interior_only,
+                 int max_ctas, cudaStream_t stream);
+
 // ---- 1x1 GEMM path (one_kernels.cu)
 int one_make_tmap(CUtensorMap* tmap, const float* x, long long m_rows, int Cin);
 int one_make_tmap_out(CUtensorMap* tmap, const float* y, long long m_rows, int Cout);

@@ -399,6 +399,41 @@ def test_results_do_not_depend_on_the_grid_size(lib_loaded, torch_cuda, max_ctas
             layer.close()
 
 
+@pytest.mark.parametrize("n,cin,cout", [(200, 512, 128), (90, 1024, 256), (256, 1024, 256), (173, 64, 256), (97, 96, 384)])
+@pytest.mark.parametrize("interior_only", [False, True])
+def test_1x1_padded_frame_output_throughput_kernel(lib_loaded, torch_cuda, n, cin, cout, interior_only):
+    """conv1x1_tf_kernel (conv1x1_t_kernel.cu): chain-mode frame output at throughput sizes -- work items of 16 image
+    rows at any alignment to the image boundaries (n * 14 not a multiple of 16: ragged last item), one TMA store per
+    frame row, CTA pairs (Cout % 256 == 0) and single CTAs. Whole frame against the oracle; every frame element written
+    (NaN pre-fill) with an exactly zero border -- or, with WG_OUT_INTERIOR_ONLY, a border the kernel does not touch in
+    the rows y = 0 / 15."""
+    torch = torch_cuda
+    rs = np.random.RandomState(700 + n + cin)
+    x = ((rs.rand(n, 196, cin) - 0.5) * 2).astype(np.float32)
+    w = (rs.rand(cin, cout) - 0.5).astype(np.float32)
+    sc, sh = (rs.rand(cout) - 0.5).astype(np.float32), (rs.rand(cout) - 0.5).astype(np.float32)
+    gold = golden.conv1x1_bn(x, w, sc, sh, True).reshape(n, 14, 14, cout)
+    layer = lib_loaded.Conv1x1Bn(w, sc, sh, relu=True)
+    xd = torch.from_numpy(x).cuda()
+    frame = torch.full((n, 16, 16, cout), float("nan"), device="cuda")
+    if interior_only:
+        frame[:, 0] = 5.0
+        frame[:, 15] = 5.0
+    layer(xd, out=frame, out_padded=True, interior_only=interior_only)
+    fr = frame.cpu().numpy()
+    assert np.isfinite(fr).all()
+    assert golden.rel_err(fr[:, 1:15, 1:15], gold) <= TOL_TF32
+    assert np.all(fr[:, 1:15, 0] == 0) and np.all(fr[:, 1:15, 15] == 0)
+    edge = 5.0 if interior_only else 0.0
+    assert np.all(fr[:, 0] == edge) and np.all(fr[:, 15] == edge)
+    dense = layer(xd).cpu().numpy().reshape(n, 14, 14, cout)
+    assert np.abs(fr[:, 1:15, 1:15] - dense).max() <= 1e-5 * np.abs(dense).max()
+    again = torch.full((n, 16, 16, cout), float("nan"), device="cuda")
+    layer(xd, out=again, out_padded=True)
+    assert torch.equal(again[:, 1:15], frame[:, 1:15])           # run to run bit-identical
+    layer.close()
+
+
 @pytest.mark.parametrize("n,cin,cout", [(1, 512, 128), (3, 64, 256), (5, 1024, 256)])
 def test_1x1_padded_frame_output(lib_loaded, torch_cuda, n, cin, cout):
     """1x1 with out_padded: the [N,16,16,Cout] frame a 3x3 layer reads -- interior == dense result, border == 0."""

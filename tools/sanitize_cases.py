@@ -109,7 +109,9 @@ def main():
             (150, 128, 512, wg.WG_TF32, 1e-3, True, False, "conv1x1_t_kernel<128> pairs + residual"),
             (75, 256, 1024, wg.WG_TF32, 1e-3, False, False, "conv1x1_t_kernel<256> pairs, resident slab"),
             (75, 256, 1024, wg.WG_TF32, 1e-3, True, False, "conv1x1_t_kernel<256> pairs + residual (streamed weights)"),
-            (199, 96, 384, wg.WG_TF32, 1e-3, True, False, "conv1x1_t_kernel<128> no pairs + residual")]:
+            (199, 96, 384, wg.WG_TF32, 1e-3, True, False, "conv1x1_t_kernel<128> no pairs + residual"),
+            (200, 512, 128, wg.WG_TF32, 1e-3, False, True, "conv1x1_tf_kernel frame output, no pairs, ragged item"),
+            (90, 1024, 256, wg.WG_TF32, 1e-3, False, True, "conv1x1_tf_kernel frame output, pairs")]:
         x = ((rs.rand(n, 196, cin) - 0.5) * 4).astype(np.float32)
         w = (rs.rand(cin, cout) - 0.5).astype(np.float32)
         sc, sh = (rs.rand(cout) + 0.5).astype(np.float32), (rs.rand(cout) - 0.5).astype(np.float32)
